@@ -1,0 +1,136 @@
+/*
+ * sidtrace_b200.h -- C ABI of the B200-native replacement for the reference's
+ * `sidtrace` extension (AVSidorov/RAYRTRACE, sidtracemodule.c).
+ *
+ * Plain C, plain pointers and sizes; no Python, NumPy or torch types.  This is
+ * the surface a maintainer binds from the reference side (ctypes / cffi / a
+ * CPython shim -- see INTEGRATION.md).  Every entry point returns an integer
+ * status (STB_OK == 0) and never throws across the ABI; the message of the last
+ * failure on the calling thread is available from stb_last_error().
+ *
+ * The library is CUDA-only (sm_100a).  There is no CPU fallback: every compute
+ * entry point fails with STB_ERR_CUDA when no usable device is present.
+ *
+ * Reference interface replaced (file:line in /root/reference):
+ *   sidtrace.trace(x,y,kx,ky,st,dx,dy,nx,ny,ax,ay) -> int   sidtracemodule.c:8-51
+ *       per-ray call site                                    ray.py:80-83
+ *       per-beam call site (one Ray per start point)         beam.py:340-342
+ *   sidtrace.check(nx,ny,i,j,a) -> float                     sidtracemodule.c:53-69
+ *   method table / module init                               sidtracemodule.c:71-89
+ *   build                                                    setup.py:5-12
+ */
+#ifndef SIDTRACE_B200_H
+#define SIDTRACE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STB_ABI_VERSION 1
+
+/* status codes */
+#define STB_OK            0
+#define STB_ERR_ARG      -1   /* bad argument (NULL, bad shape, bad flag combination) */
+#define STB_ERR_CUDA     -2   /* CUDA runtime / no device */
+#define STB_ERR_NOMEM    -3   /* device or host allocation failed */
+#define STB_ERR_RANGE    -4   /* grid too large for int32 cell index (reference uses int, sidtracemodule.c:32,38) */
+
+/* opaque handle of an acceleration field resident in HBM */
+typedef struct stb_field_s *stb_field_t;
+
+/* ---- library ---------------------------------------------------------------- */
+int         stb_abi_version(void);
+const char *stb_last_error(void);             /* thread-local, never NULL */
+int         stb_device_count(int *count);
+int         stb_set_device(int device);       /* cudaSetDevice for the calling thread */
+
+/* ---- field: the read-only inputs ax, ay of sidtrace.trace ------------------- */
+/* ax, ay: float64, C-contiguous, shape (ny-1, nx-1), row-major with row stride
+ * nx-1 (sidtracemodule.c:38; den.py:94-95).  `on_device` != 0 means ax/ay are
+ * device pointers (copied device-to-device); otherwise host pointers.  The
+ * library keeps its own interleaved copy {ax,ay} per cell (one 16-byte gather
+ * per ray-step), so the caller may free ax/ay after the call returns. */
+int stb_field_create(const double *ax, const double *ay, int nx, int ny,
+                     int on_device, stb_field_t *out);
+int stb_field_destroy(stb_field_t f);
+int stb_field_shape(stb_field_t f, int *nx, int *ny);
+/* read one cell back from HBM: which = 0 -> ax[i, j], 1 -> ay[i, j], indexed
+ * with the TRUE row stride nx-1 (the device-side layout pin). */
+int stb_field_peek(stb_field_t f, int i, int j, int which, double *out);
+
+/* ---- legacy per-ray entry points -------------------------------------------- */
+/* Backs sidtrace.trace (sidtracemodule.c:8-51): x, y, kx, ky are HOST arrays of
+ * length L, element 0 = launch state, mutated in place for indices 1..i;
+ * *nsteps = i.  One GPU round trip per call: the correctness path, not the fast
+ * path. */
+int stb_trace(stb_field_t f, double *x, double *y, double *kx, double *ky,
+              int64_t L, double st, double dx, double dy, int64_t *nsteps);
+/* Backs sidtrace.check (sidtracemodule.c:53-69): *out = a[i*nx + j] on a HOST
+ * array (note nx, not nx-1: reproduced as the reference has it). */
+int stb_check(int nx, int ny, int i, int j, const double *a, double *out);
+
+/* ---- batched entry point: a whole beam per launch --------------------------- */
+/* flags */
+#define STB_F_HOST_IO      (1u << 0)  /* x0..ky0, st_ray, amp and all per-ray outputs are HOST pointers
+                                         (staged through pinned/HBM workspaces; traj stays a DEVICE pointer) */
+#define STB_F_DIV_IEEE     (1u << 1)  /* use the generic IEEE division (div.rn.f64) instead of the
+                                         constant-divisor correctly-rounded sequence; both are bit-exact */
+#define STB_F_NO_REFILL    (1u << 2)  /* static one-thread-per-ray grid instead of the persistent
+                                         warp-refill scheduler */
+#define STB_F_TRAJ_HOST    (1u << 3)  /* traj is a HOST pointer (copied back after the launch) */
+
+typedef struct stb_batch_s {
+    size_t   struct_size;     /* = sizeof(stb_batch_t); ABI evolution guard                     */
+    uint32_t flags;
+    int64_t  nrays;
+    int64_t  L;               /* states per ray incl. the launch state (the reference's MaxI,    */
+                              /* sidtracemodule.c:33): at most L-1 steps are taken              */
+    /* launch state in GRID units / cm^-1 (ray.py:62-68), one entry per ray */
+    const double *x0, *y0, *kx0, *ky0;
+    double   st;              /* global step (den.py:107) ...                                    */
+    const double *st_ray;     /* ... or a per-ray step (frequency sweeps); NULL -> use `st`      */
+    double   dx, dy;          /* n_field.dx[0], n_field.dy[0] (ray.py:72-73)                     */
+
+    /* outputs; any may be NULL */
+    double  *traj;            /* [ray][step][4] = (x, y, kx, ky); states 0..i written, rest      */
+                              /* untouched (sidtracemodule.c:36-48)                              */
+    int64_t  traj_ray_stride; /* in doubles, >= 4*L, multiple of 4 (0 -> 4*L)                    */
+    int32_t *nsteps;          /* [ray] i = steps taken = index of last written state            */
+    double  *end_state;       /* [4][nrays] state at index i                                     */
+
+    /* fused per-ray reductions (ray.py:113-126 and SURVEY 8c extensions); may be NULL */
+    int32_t *turn_index;      /* [ray] first index j in [1,i] where ky changes sign, else -1     */
+    double  *lax_end;         /* [ray] lax[i-1]: path-length integral over the kept states       */
+    double  *ph_end;          /* [ray] ph[i-1]:  eikonal phase over the kept states              */
+
+    /* deposition-profile extension (no reference counterpart; oracle/sidtrace_oracle.c) */
+    double  *hist;            /* [nbins] accumulated (not cleared); DEVICE pointer unless HOST_IO */
+    int32_t  nbins;
+    const double *amp;        /* [ray] launch amplitude (ray.py:56); NULL -> 1                   */
+    double   xorg, yorg;      /* physical coordinates of grid node (0,0)                         */
+    double   r_lcs, rho_max;
+} stb_batch_t;
+
+/* Traces b->nrays rays on `stream` (a cudaStream_t passed as void*; NULL = the
+ * legacy default stream).  With device pointers the call is asynchronous;
+ * with STB_F_HOST_IO / STB_F_TRAJ_HOST it returns after the results are in
+ * host memory. */
+int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream);
+
+/* number of kernel launches issued by this library so far (all threads) */
+int64_t stb_launch_count(void);
+
+/* ---- measurement helpers ----------------------------------------------------- */
+/* Dependent-free DFMA throughput of the current device in TFLOP/s (2 flops per
+ * DFMA) -- the FP64 roofline denominator that MEASURED_PEAKS.json lacks. */
+int stb_measure_fp64_peak(double *tflops);
+/* Plain streaming-store bandwidth in GB/s over `bytes` of HBM. */
+int stb_measure_store_bw(size_t bytes, double *gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIDTRACE_B200_H */

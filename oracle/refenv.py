@@ -1,0 +1,100 @@
+"""Import the reference's own Python layers (den.py, ray.py, beam.py) in THIS
+container, unmodified, on top of the compiled reference extension.
+
+TEST INFRASTRUCTURE ONLY.  Used by tests/golden/make_golden.py (fixture
+generation) and by tests that are skipped when /root/reference is absent (it
+does not exist on the GPU box).
+
+Shims (harness-side; /root/reference is never edited) -- SURVEY.md 8c:
+  * scipy.interpolate.interp2d was removed in SciPy 1.14 (den.py:4,71 imports
+    and calls it).  Replaced by a RectBivariateSpline(kx=3, ky=3, s=0) wrapper
+    returning shape (1,) for scalar queries, like the old interp2d did.  Only
+    the launch refractive index (ray.py:62) depends on it; that is an INPUT of
+    the hot path, so parity tests feed the same k0 to both sides.
+  * skimage (beam.py:5) is not installed: a stub module whose
+    measure.find_contours is a small marching-squares restatement good enough
+    for beam.py:238 (single open iso-line of a smooth field).
+  * ufile (equilibrium.py:8) is not in the reference repo: empty stub.
+"""
+from __future__ import annotations
+
+import sys
+import types
+import warnings
+
+import numpy as np
+
+from . import REFERENCE_ROOT, ref
+
+_installed = False
+
+
+class _Interp2dShim:
+    def __init__(self, x, y, z, kind="linear", fill_value=None, **_):
+        from scipy.interpolate import RectBivariateSpline
+        k = {"linear": 1, "cubic": 3, "quintic": 5}[kind]
+        self._s = RectBivariateSpline(np.asarray(x, float), np.asarray(y, float),
+                                      np.asarray(z, float).T, kx=k, ky=k, s=0)
+
+    def __call__(self, x, y):
+        x = np.atleast_1d(np.asarray(x, float))
+        y = np.atleast_1d(np.asarray(y, float))
+        out = self._s(x, y).T  # (len(y), len(x)) like interp2d
+        if out.shape[0] == 1:
+            out = out[0]
+        elif out.shape[1] == 1:
+            out = out[:, 0]
+        return out
+
+
+def _find_contours(arr, level):
+    """Marching-squares iso-line, single open contour, row/col coordinates like
+    skimage.measure.find_contours: returns [ndarray (n, 2)] of (row, col)."""
+    a = np.asarray(arr, float) - level
+    nr, nc = a.shape
+    pts = []
+    # crossings on vertical edges (between rows r and r+1) for each column
+    for c in range(nc):
+        col = a[:, c]
+        s = np.sign(col)
+        idx = np.where(s[:-1] * s[1:] < 0)[0]
+        for r in idx:
+            t = col[r] / (col[r] - col[r + 1])
+            pts.append((r + t, float(c)))
+    pts = np.array(sorted(pts, key=lambda p: p[1]))
+    return [pts]
+
+
+def install():
+    global _installed
+    if _installed:
+        return
+    import scipy.interpolate as si
+    if not hasattr(si, "_orig_interp2d"):
+        si._orig_interp2d = getattr(si, "interp2d", None)
+        si.interp2d = _Interp2dShim
+    sys.modules["sidtrace"] = ref()
+    if "skimage" not in sys.modules:
+        sk = types.ModuleType("skimage")
+        me = types.ModuleType("skimage.measure")
+        me.find_contours = _find_contours
+        sk.measure = me
+        sys.modules["skimage"] = sk
+        sys.modules["skimage.measure"] = me
+    if "ufile" not in sys.modules:
+        uf = types.ModuleType("ufile")
+        uf.Ufile = type("Ufile", (), {})
+        sys.modules["ufile"] = uf
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    _installed = True
+
+
+def modules():
+    """Returns (den, ray) reference modules, imported unmodified."""
+    install()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import den  # noqa
+        import ray  # noqa
+    return den, ray

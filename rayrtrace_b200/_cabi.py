@@ -1,0 +1,109 @@
+"""ctypes binding of the C ABI declared in include/sidtrace_b200.h.
+
+The CUDA library is the product: if it is missing this module raises at import
+time -- there is no CPU fallback anywhere in ``rayrtrace_b200``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t,
+                    c_uint32, c_void_p)
+
+from . import build as _build
+
+STB_ABI_VERSION = 1
+STB_OK = 0
+STB_ERR_ARG, STB_ERR_CUDA, STB_ERR_NOMEM, STB_ERR_RANGE = -1, -2, -3, -4
+
+F_HOST_IO = 1 << 0
+F_DIV_IEEE = 1 << 1
+F_NO_REFILL = 1 << 2
+F_TRAJ_HOST = 1 << 3
+
+# every symbol include/sidtrace_b200.h declares (tests check the .so exports them all)
+EXPORTS = (
+    "stb_abi_version", "stb_last_error", "stb_device_count", "stb_set_device",
+    "stb_field_create", "stb_field_destroy", "stb_field_shape", "stb_field_peek",
+    "stb_trace", "stb_check", "stb_trace_batch", "stb_launch_count",
+    "stb_measure_fp64_peak", "stb_measure_store_bw",
+)
+
+
+class StbBatch(Structure):
+    """Mirror of ``stb_batch_t``."""
+    _fields_ = [
+        ("struct_size", c_size_t),
+        ("flags", c_uint32),
+        ("nrays", c_int64),
+        ("L", c_int64),
+        ("x0", c_void_p), ("y0", c_void_p), ("kx0", c_void_p), ("ky0", c_void_p),
+        ("st", c_double),
+        ("st_ray", c_void_p),
+        ("dx", c_double), ("dy", c_double),
+        ("traj", c_void_p),
+        ("traj_ray_stride", c_int64),
+        ("nsteps", c_void_p),
+        ("end_state", c_void_p),
+        ("turn_index", c_void_p),
+        ("lax_end", c_void_p),
+        ("ph_end", c_void_p),
+        ("hist", c_void_p),
+        ("nbins", c_int32),
+        ("amp", c_void_p),
+        ("xorg", c_double), ("yorg", c_double),
+        ("r_lcs", c_double), ("rho_max", c_double),
+    ]
+
+
+class SidtraceError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"sidtrace_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _load() -> ctypes.CDLL:
+    path = os.environ.get("SIDTRACE_B200_LIB", _build.LIB)
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: the sidtrace_b200 CUDA library is not built. "
+            "Run `python -m rayrtrace_b200.build` (needs nvcc). There is no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    lib.stb_abi_version.restype = c_int
+    lib.stb_abi_version.argtypes = []
+    lib.stb_last_error.restype = c_char_p
+    lib.stb_last_error.argtypes = []
+    lib.stb_device_count.argtypes = [POINTER(c_int)]
+    lib.stb_set_device.argtypes = [c_int]
+    lib.stb_field_create.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]
+    lib.stb_field_destroy.argtypes = [c_void_p]
+    lib.stb_field_shape.argtypes = [c_void_p, POINTER(c_int), POINTER(c_int)]
+    lib.stb_field_peek.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_double)]
+    lib.stb_trace.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                              c_double, c_double, c_double, POINTER(c_int64)]
+    lib.stb_check.argtypes = [c_int, c_int, c_int, c_int, c_void_p, POINTER(c_double)]
+    lib.stb_trace_batch.argtypes = [c_void_p, POINTER(StbBatch), c_void_p]
+    lib.stb_launch_count.restype = c_int64
+    lib.stb_launch_count.argtypes = []
+    lib.stb_measure_fp64_peak.argtypes = [POINTER(c_double)]
+    lib.stb_measure_store_bw.argtypes = [c_size_t, POINTER(c_double)]
+    for name in ("stb_device_count", "stb_set_device", "stb_field_create", "stb_field_destroy",
+                 "stb_field_shape", "stb_field_peek", "stb_trace", "stb_check", "stb_trace_batch",
+                 "stb_measure_fp64_peak", "stb_measure_store_bw"):
+        getattr(lib, name).restype = c_int
+    if lib.stb_abi_version() != STB_ABI_VERSION:
+        raise ImportError(f"{path}: ABI version {lib.stb_abi_version()} != {STB_ABI_VERSION}")
+    return lib
+
+
+lib = _load()
+LIB_PATH = os.environ.get("SIDTRACE_B200_LIB", _build.LIB)
+
+
+def check(rc: int) -> None:
+    if rc != STB_OK:
+        raise SidtraceError(rc, lib.stb_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(lib.stb_launch_count())

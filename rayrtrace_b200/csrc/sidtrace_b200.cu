@@ -1,0 +1,493 @@
+// sidtrace_b200.cu -- C-ABI shared library (include/sidtrace_b200.h) over the
+// sm_100a kernels in trace_kernels.cuh.  No Python / torch types anywhere.
+//
+// Build (see rayrtrace_b200/build.py):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false \
+//        -Xcompiler -fPIC -shared -o libsidtrace_b200.so sidtrace_b200.cu
+#include "../../include/sidtrace_b200.h"
+#include "trace_kernels.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+namespace {
+
+constexpr int kCounters = 64;
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? STB_ERR_NOMEM : STB_ERR_CUDA,  \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return STB_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        CU(cudaMalloc(&p, want));
+        cap = want;
+        return STB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostBuf {   // pinned
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return STB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        CU(cudaMallocHost(&p, want));
+        cap = want;
+        return STB_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct stb_field_s {
+    int device = 0;
+    int nx = 0, ny = 0;
+    double2 *cells = nullptr;             // interleaved {ax, ay}, (ny-1)*(nx-1)
+    unsigned long long *counter = nullptr;   // kCounters queue heads, used round-robin so that
+                                             // launches in flight on different streams never share one
+    unsigned launch_seq = 0;
+    int num_sms = 0;
+    std::mutex mu;                        // guards the workspaces below
+    DevBuf ws_in, ws_out, ws_traj, ws_hist;
+    HostBuf pin;
+};
+
+extern "C" {
+
+int stb_abi_version(void) { return STB_ABI_VERSION; }
+
+const char *stb_last_error(void) { return g_err; }
+
+int stb_device_count(int *count)
+{
+    if (!count) return fail(STB_ERR_ARG, "count is NULL");
+    CU(cudaGetDeviceCount(count));
+    return STB_OK;
+}
+
+int stb_set_device(int device)
+{
+    CU(cudaSetDevice(device));
+    return STB_OK;
+}
+
+int64_t stb_launch_count(void) { return g_launches.load(); }
+
+int stb_field_create(const double *ax, const double *ay, int nx, int ny, int on_device, stb_field_t *out)
+{
+    if (!ax || !ay || !out) return fail(STB_ERR_ARG, "stb_field_create: NULL argument");
+    if (nx < 2 || ny < 2) return fail(STB_ERR_ARG, "stb_field_create: nx, ny must be >= 2 (got %d, %d)", nx, ny);
+    const long long ncell = (long long)(nx - 1) * (long long)(ny - 1);
+    if (ncell > 0x7fffffffLL) return fail(STB_ERR_RANGE, "stb_field_create: (nx-1)*(ny-1) = %lld exceeds int32", ncell);
+
+    stb_field_s *f = new (std::nothrow) stb_field_s;
+    if (!f) return fail(STB_ERR_NOMEM, "stb_field_create: host allocation failed");
+    f->nx = nx; f->ny = ny;
+    cudaError_t e = cudaGetDevice(&f->device);
+    if (e != cudaSuccess) { delete f; return fail(STB_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e)); }
+    cudaDeviceGetAttribute(&f->num_sms, cudaDevAttrMultiProcessorCount, f->device);
+
+    const size_t bytes = (size_t)ncell * sizeof(double);
+    double *tmp = nullptr;   // staging for host input: [ax | ay]
+    const double *dax = ax, *day = ay;
+    int rc = STB_OK;
+    do {
+        if ((e = cudaMalloc(&f->cells, 2 * bytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&f->counter, kCounters * sizeof(unsigned long long))) != cudaSuccess) break;
+        if (!on_device) {
+            if ((e = cudaMalloc(&tmp, 2 * bytes)) != cudaSuccess) break;
+            if ((e = cudaMemcpy(tmp, ax, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+            if ((e = cudaMemcpy(tmp + ncell, ay, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+            dax = tmp; day = tmp + ncell;
+        }
+        const int threads = 256;
+        long long blocks = (ncell + threads - 1) / threads;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        stb::interleave_kernel<<<(int)blocks, threads>>>(dax, day, f->cells, ncell);
+        g_launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
+    } while (0);
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) {
+        rc = fail(e == cudaErrorMemoryAllocation ? STB_ERR_NOMEM : STB_ERR_CUDA,
+                  "stb_field_create: %s", cudaGetErrorString(e));
+        if (f->cells) cudaFree(f->cells);
+        if (f->counter) cudaFree(f->counter);
+        delete f;
+        return rc;
+    }
+    *out = f;
+    return STB_OK;
+}
+
+int stb_field_destroy(stb_field_t f)
+{
+    if (!f) return STB_OK;
+    cudaFree(f->cells);
+    cudaFree(f->counter);
+    f->ws_in.release(); f->ws_out.release(); f->ws_traj.release(); f->ws_hist.release();
+    f->pin.release();
+    delete f;
+    return STB_OK;
+}
+
+int stb_field_shape(stb_field_t f, int *nx, int *ny)
+{
+    if (!f) return fail(STB_ERR_ARG, "stb_field_shape: NULL field");
+    if (nx) *nx = f->nx;
+    if (ny) *ny = f->ny;
+    return STB_OK;
+}
+
+int stb_field_peek(stb_field_t f, int i, int j, int which, double *out)
+{
+    if (!f || !out) return fail(STB_ERR_ARG, "stb_field_peek: NULL argument");
+    if (i < 0 || i >= f->ny - 1 || j < 0 || j >= f->nx - 1 || (which != 0 && which != 1))
+        return fail(STB_ERR_ARG, "stb_field_peek: index (%d, %d, %d) outside (%d, %d)", i, j, which, f->ny - 1, f->nx - 1);
+    double2 c;
+    CU(cudaMemcpy(&c, f->cells + (size_t)i * (f->nx - 1) + j, sizeof(c), cudaMemcpyDeviceToHost));
+    *out = which ? c.y : c.x;
+    return STB_OK;
+}
+
+int stb_check(int nx, int ny, int i, int j, const double *a, double *out)
+{
+    (void)ny;
+    if (!a || !out) return fail(STB_ERR_ARG, "stb_check: NULL argument");
+    // sidtracemodule.c:66 -- a[i*nx + j]; a plain host-memory probe, no compute.
+    *out = a[(long long)i * nx + j];
+    return STB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+namespace {
+
+using stb::KParams;
+
+template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC>
+int launch_variant(const KParams &p, bool refill, int num_sms, cudaStream_t s)
+{
+    const size_t smem = HIST ? (size_t)p.nbins * sizeof(double) : 0;
+    if (p.nrays <= 0) return STB_OK;
+    long long blocks_all = (p.nrays + stb::kBlock - 1) / stb::kBlock;
+    if (refill) {
+        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, true>;
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, stb::kBlock, smem));
+        if (per_sm < 1) per_sm = 1;
+        long long blocks = (long long)num_sms * per_sm;
+        if (blocks > blocks_all) blocks = blocks_all;
+        CU(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), s));
+        kern<<<(unsigned)blocks, stb::kBlock, smem, s>>>(p);
+    } else {
+        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, false>;
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (blocks_all > 0x7fffffffLL) return fail(STB_ERR_ARG, "too many rays for a static grid");
+        kern<<<(unsigned)blocks_all, stb::kBlock, smem, s>>>(p);
+    }
+    g_launches++;
+    CU(cudaGetLastError());
+    return STB_OK;
+}
+
+template <bool TRAJ, bool EXTRAS, bool HIST>
+int launch_div(const KParams &p, bool divc, bool refill, int num_sms, cudaStream_t s)
+{
+    return divc ? launch_variant<TRAJ, EXTRAS, HIST, true>(p, refill, num_sms, s)
+                : launch_variant<TRAJ, EXTRAS, HIST, false>(p, refill, num_sms, s);
+}
+
+int launch_trace(const KParams &p, bool divc, bool refill, int num_sms, cudaStream_t s)
+{
+    const bool traj = p.traj != nullptr;
+    const bool extras = p.turn || p.lax_end || p.ph_end;
+    const bool hist = p.hist != nullptr;
+    const int key = (traj ? 4 : 0) | (extras ? 2 : 0) | (hist ? 1 : 0);
+    switch (key) {
+        case 0: return launch_div<false, false, false>(p, divc, refill, num_sms, s);
+        case 1: return launch_div<false, false, true>(p, divc, refill, num_sms, s);
+        case 2: return launch_div<false, true, false>(p, divc, refill, num_sms, s);
+        case 3: return launch_div<false, true, true>(p, divc, refill, num_sms, s);
+        case 4: return launch_div<true, false, false>(p, divc, refill, num_sms, s);
+        case 5: return launch_div<true, false, true>(p, divc, refill, num_sms, s);
+        case 6: return launch_div<true, true, false>(p, divc, refill, num_sms, s);
+        default: return launch_div<true, true, true>(p, divc, refill, num_sms, s);
+    }
+}
+
+// the constant-divisor sequence is exact only while nothing under/overflows
+bool divisor_in_guarded_range(double d)
+{
+    const double a = std::fabs(d);
+    return std::isfinite(d) && a >= std::ldexp(1.0, -400) && a <= std::ldexp(1.0, 400);
+}
+
+int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
+{
+    if (b->L < 1 || b->L > 0x7fffffffLL) return fail(STB_ERR_ARG, "stb_trace_batch: L = %lld out of range", (long long)b->L);
+    if (b->nrays < 0) return fail(STB_ERR_ARG, "stb_trace_batch: nrays < 0");
+    if (b->nrays > 0 && (!b->x0 || !b->y0 || !b->kx0 || !b->ky0))
+        return fail(STB_ERR_ARG, "stb_trace_batch: NULL launch-state pointer");
+    long long stride = b->traj_ray_stride ? b->traj_ray_stride : 4 * b->L;
+    if (b->traj && (stride < 4 * b->L || (stride & 3)))
+        return fail(STB_ERR_ARG, "stb_trace_batch: traj_ray_stride %lld must be a multiple of 4 and >= 4*L", stride);
+    if (b->traj && ((uintptr_t)b->traj & 31) && !(b->flags & STB_F_TRAJ_HOST))
+        return fail(STB_ERR_ARG, "stb_trace_batch: traj must be 32-byte aligned");
+    if (b->hist && (b->nbins < 1 || b->nbins > 16384))
+        return fail(STB_ERR_ARG, "stb_trace_batch: nbins = %d outside [1, 16384]", b->nbins);
+    if (b->hist && !(b->r_lcs > 0 && b->rho_max > 0))
+        return fail(STB_ERR_ARG, "stb_trace_batch: r_lcs and rho_max must be > 0 for the histogram");
+    p.field = f->cells;
+    p.nxm1 = f->nx - 1; p.nym1 = f->ny - 1;
+    p.fx = (double)(f->nx - 1); p.fy = (double)(f->ny - 1);
+    p.nrays = b->nrays; p.L = (int)b->L;
+    p.x0 = b->x0; p.y0 = b->y0; p.kx0 = b->kx0; p.ky0 = b->ky0;
+    p.st = b->st; p.st_ray = b->st_ray;
+    p.dx = b->dx; p.dy = b->dy; p.rdx = 1.0 / b->dx; p.rdy = 1.0 / b->dy;
+    p.traj = b->traj; p.stride = stride;
+    p.nsteps = b->nsteps; p.endst = b->end_state;
+    p.turn = b->turn_index; p.lax_end = b->lax_end; p.ph_end = b->ph_end;
+    p.hist = b->hist; p.nbins = b->nbins; p.amp = b->amp;
+    p.xorg = b->xorg; p.yorg = b->yorg; p.r_lcs = b->r_lcs; p.rho_max = b->rho_max;
+    p.counter = f->counter + (f->launch_seq++ % kCounters);
+    divc = !(b->flags & STB_F_DIV_IEEE) && divisor_in_guarded_range(b->dx) && divisor_in_guarded_range(b->dy);
+    return STB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
+{
+    if (!f || !b) return fail(STB_ERR_ARG, "stb_trace_batch: NULL argument");
+    if (b->struct_size != sizeof(stb_batch_t))
+        return fail(STB_ERR_ARG, "stb_trace_batch: struct_size %zu != %zu (ABI mismatch)", b->struct_size, sizeof(stb_batch_t));
+    cudaStream_t s = (cudaStream_t)stream;
+    KParams p{};
+    bool divc = false;
+    int rc = fill_params(f, b, p, divc);
+    if (rc != STB_OK) return rc;
+    const bool refill = !(b->flags & STB_F_NO_REFILL);
+    const bool host_io = b->flags & STB_F_HOST_IO;
+    const bool traj_host = b->flags & STB_F_TRAJ_HOST;
+
+    if (!host_io && !traj_host) {
+        // the counter is per field: serialise launches that share it on different streams
+        std::lock_guard<std::mutex> lk(f->mu);
+        return launch_trace(p, divc, refill, f->num_sms, s);
+    }
+
+    std::lock_guard<std::mutex> lk(f->mu);
+    const size_t n = (size_t)b->nrays;
+    const size_t nb = n * sizeof(double);
+    const bool extras = b->turn_index || b->lax_end || b->ph_end;
+
+    if (host_io) {
+        // ---- inputs: [x0 | y0 | kx0 | ky0 | st_ray? | amp?] ----
+        const int nin = 4 + (b->st_ray ? 1 : 0) + (b->amp ? 1 : 0);
+        rc = f->ws_in.ensure(nb * nin + 64);
+        if (rc != STB_OK) return rc;
+        double *din = (double *)f->ws_in.p;
+        const double *src[6] = {b->x0, b->y0, b->kx0, b->ky0, b->st_ray, b->amp};
+        const double **dst[6] = {&p.x0, &p.y0, &p.kx0, &p.ky0, &p.st_ray, &p.amp};
+        int slot = 0;
+        for (int k = 0; k < 6; ++k) {
+            if (!src[k]) continue;
+            double *d = din + (size_t)slot * n;
+            if (n) CU(cudaMemcpyAsync(d, src[k], nb, cudaMemcpyHostToDevice, s));
+            *dst[k] = d;
+            ++slot;
+        }
+        // ---- outputs: [end 4n | lax n | ph n | nsteps n(i32) | turn n(i32)] ----
+        rc = f->ws_out.ensure(nb * 6 + 2 * n * sizeof(int32_t) + 64);
+        if (rc != STB_OK) return rc;
+        double *dout = (double *)f->ws_out.p;
+        p.endst = b->end_state ? dout : nullptr;
+        p.lax_end = b->lax_end ? dout + 4 * n : nullptr;
+        p.ph_end = b->ph_end ? dout + 5 * n : nullptr;
+        int32_t *iout = (int32_t *)(dout + 6 * n);
+        p.nsteps = b->nsteps ? iout : nullptr;
+        p.turn = b->turn_index ? iout + n : nullptr;
+        (void)extras;
+        if (b->hist) {
+            rc = f->ws_hist.ensure((size_t)b->nbins * sizeof(double));
+            if (rc != STB_OK) return rc;
+            CU(cudaMemcpyAsync(f->ws_hist.p, b->hist, (size_t)b->nbins * sizeof(double), cudaMemcpyHostToDevice, s));
+            p.hist = (double *)f->ws_hist.p;
+        }
+    }
+    if (traj_host && b->traj) {
+        rc = f->ws_traj.ensure((size_t)b->nrays * (size_t)p.stride * sizeof(double));
+        if (rc != STB_OK) return rc;
+        // entries beyond state i stay untouched for the caller: start from the caller's bytes
+        CU(cudaMemcpyAsync(f->ws_traj.p, b->traj, (size_t)b->nrays * (size_t)p.stride * sizeof(double), cudaMemcpyHostToDevice, s));
+        p.traj = (double *)f->ws_traj.p;
+    }
+
+    rc = launch_trace(p, divc, refill, f->num_sms, s);
+    if (rc != STB_OK) return rc;
+
+    if (host_io && n) {
+        if (b->end_state) CU(cudaMemcpyAsync(b->end_state, p.endst, 4 * nb, cudaMemcpyDeviceToHost, s));
+        if (b->lax_end) CU(cudaMemcpyAsync(b->lax_end, p.lax_end, nb, cudaMemcpyDeviceToHost, s));
+        if (b->ph_end) CU(cudaMemcpyAsync(b->ph_end, p.ph_end, nb, cudaMemcpyDeviceToHost, s));
+        if (b->nsteps) CU(cudaMemcpyAsync(b->nsteps, p.nsteps, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (b->turn_index) CU(cudaMemcpyAsync(b->turn_index, p.turn, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    if (host_io && b->hist)
+        CU(cudaMemcpyAsync(b->hist, p.hist, (size_t)b->nbins * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (traj_host && b->traj)
+        CU(cudaMemcpyAsync(b->traj, p.traj, (size_t)b->nrays * (size_t)p.stride * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return STB_OK;
+}
+
+int stb_trace(stb_field_t f, double *x, double *y, double *kx, double *ky, int64_t L,
+              double st, double dx, double dy, int64_t *nsteps)
+{
+    if (!f || !x || !y || !kx || !ky || !nsteps) return fail(STB_ERR_ARG, "stb_trace: NULL argument");
+    if (L < 1 || L > 0x7fffffffLL) return fail(STB_ERR_ARG, "stb_trace: L = %lld out of range", (long long)L);
+    std::lock_guard<std::mutex> lk(f->mu);
+    // workspace: launch state (4 doubles) | nsteps (i32) ; trajectory [L][4]
+    int rc = f->ws_in.ensure(64);
+    if (rc != STB_OK) return rc;
+    rc = f->ws_out.ensure(64);
+    if (rc != STB_OK) return rc;
+    rc = f->ws_traj.ensure((size_t)L * 4 * sizeof(double));
+    if (rc != STB_OK) return rc;
+    rc = f->pin.ensure((size_t)L * 4 * sizeof(double));
+    if (rc != STB_OK) return rc;
+
+    double h0[4] = {x[0], y[0], kx[0], ky[0]};
+    double *din = (double *)f->ws_in.p;
+    CU(cudaMemcpyAsync(din, h0, sizeof(h0), cudaMemcpyHostToDevice, 0));
+
+    stb_batch_t b{};
+    b.struct_size = sizeof(b);
+    b.nrays = 1; b.L = L;
+    b.x0 = din; b.y0 = din + 1; b.kx0 = din + 2; b.ky0 = din + 3;
+    b.st = st; b.dx = dx; b.dy = dy;
+    b.traj = (double *)f->ws_traj.p;
+    b.nsteps = (int32_t *)f->ws_out.p;
+    KParams p{};
+    bool divc = false;
+    rc = fill_params(f, &b, p, divc);
+    if (rc != STB_OK) return rc;
+    rc = launch_trace(p, divc, /*refill=*/false, f->num_sms, 0);
+    if (rc != STB_OK) return rc;
+    int32_t n = 0;
+    CU(cudaMemcpy(&n, b.nsteps, sizeof(n), cudaMemcpyDeviceToHost));
+    if (n > 0) {
+        double *h = (double *)f->pin.p;
+        CU(cudaMemcpy(h, b.traj, (size_t)(n + 1) * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+        // scatter the interleaved states 1..n into the caller's four arrays
+        // (sidtracemodule.c:41-45 writes xx[i+1], yy[i+1], kxx[i+1], kyy[i+1]); data marshalling only
+        for (int32_t j = 1; j <= n; ++j) {
+            x[j] = h[4 * j + 0]; y[j] = h[4 * j + 1]; kx[j] = h[4 * j + 2]; ky[j] = h[4 * j + 3];
+        }
+    }
+    *nsteps = n;
+    return STB_OK;
+}
+
+int stb_measure_fp64_peak(double *tflops)
+{
+    if (!tflops) return fail(STB_ERR_ARG, "tflops is NULL");
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *out = nullptr;
+    const int threads = 256, blocks = sms * 8, iters = 4096;
+    CU(cudaMalloc(&out, (size_t)threads * blocks * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0));
+        stb::fp64_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+        g_launches++;
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 32.0 * (double)iters * threads * (double)blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return STB_OK;
+}
+
+int stb_measure_store_bw(size_t bytes, double *gbs)
+{
+    if (!gbs || bytes < 32) return fail(STB_ERR_ARG, "stb_measure_store_bw: bad argument");
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *out = nullptr;
+    CU(cudaMalloc(&out, bytes));
+    const long long nvec = (long long)(bytes / 32);
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0));
+        stb::store_bw_kernel<<<sms * 16, 256>>>(out, nvec);
+        g_launches++;
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double g = (double)nvec * 32.0 / (ms * 1e-3) / 1e9;
+        if (rep > 0 && g > best) best = g;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    *gbs = best;
+    return STB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+// trace_kernels.cuh -- sm_100a kernels of the sidtrace hot path.
+//
+// One thread owns one ray at a time.  A warp runs a flat step loop: every
+// iteration it votes (ballot) on which lanes still own a live ray; lanes whose
+// ray left the grid or hit the cap retire it (write the per-ray results) and,
+// in the persistent "refill" schedule, the warp claims the next rays from a
+// global queue with ONE aggregated atomic and hands them out by lane rank, so
+// a reflected or trapped ray (up to MaxStep = 100000 steps, ray.py:11) never
+// holds 31 idle lanes hostage.
+//
+// Arithmetic contract (bit-exact with sidtracemodule.c:36-48 as gcc -O2
+// compiles it: no FMA, left-to-right):
+//     t = ((st*st)*M)/2 ; u = k*st ; v = t+u ; w = v/d ; x' = x + w
+//     k' = k + st*M
+// Every FP64 operation below is an explicit round-to-nearest intrinsic so no
+// contraction can happen whatever the compiler flags are.
+//
+// The two divisions per step have a loop-invariant divisor (dx, dy).  With
+// rd = RN(1/d) computed once on the host, the sequence
+//     q = RN(v*rd) ; r = RN(v - q*d) (exact, one FMA) ; q' = RN(q + r*rd)
+// returns the correctly rounded quotient RN(v/d) (Markstein's correction step:
+// q is within one ulp of v/d, so r is exactly representable and the final FMA
+// rounds the exact quotient) provided nothing under- or overflows.  div_const()
+// guards the exponent range and falls back to the generic IEEE division
+// otherwise, so the result is bit-identical to `v / d` for every input.
+// tests/test_gpu_parity.py checks the two paths against each other and against
+// the oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace stb {
+
+constexpr int kBlock = 128;   // threads per CTA (4 warps)
+
+struct KParams {
+    const double2 *field;   // {ax, ay} per cell, row stride nxm1
+    int nxm1, nym1;
+    double fx, fy;                       // (double)(nx-1), (double)(ny-1)
+    long long nrays;
+    int L;
+    const double *x0, *y0, *kx0, *ky0;
+    double st;
+    const double *st_ray;
+    double dx, dy, rdx, rdy;
+    double *traj;
+    long long stride;                    // doubles per ray
+    int *nsteps;
+    double *endst;
+    int *turn;
+    double *lax_end, *ph_end;
+    double *hist;
+    int nbins;
+    const double *amp;
+    double xorg, yorg, r_lcs, rho_max;
+    unsigned long long *counter;         // ray queue head (refill schedule)
+};
+
+__device__ __forceinline__ void st_state(double *p, double a, double b, double c, double d)
+{
+    // one ray-step = one 32-byte sector = one STG.E.ENL2.256
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+// Correctly rounded v / d for a loop-invariant divisor d with rd = RN(1/d).
+template <bool DIVC>
+__device__ __forceinline__ double div_const(double v, double d, double rd)
+{
+    if (!DIVC) return __ddiv_rn(v, d);
+    const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+    // |v| in [2^-400, 2^400]: q, r, q' all normal, r exact (host checked |d| in [2^-400, 2^400]).
+    if (e - 623u <= 800u) {
+        const double q = __dmul_rn(v, rd);
+        const double r = __fma_rn(-q, d, v);
+        return __fma_rn(r, rd, q);
+    }
+    if (v == 0.0) return __dmul_rn(v, rd);   // +-0 / d = +-0 (sign of d == sign of rd)
+    return __ddiv_rn(v, d);                  // subnormal, huge, inf, nan: generic path
+}
+
+__device__ __forceinline__ double kmod(double kx, double ky)
+{   // ray.py:115  np.sqrt(kx**2 + ky**2)
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(kx, kx), __dmul_rn(ky, ky)));
+}
+
+// Adds w to shared-memory bin b for every active lane; lanes of the warp that
+// hit the same bin are combined first (match.any) so each distinct bin costs
+// one shared atomic per warp-step.
+__device__ __forceinline__ void hist_add(double *sh, int b, double w)
+{
+    const unsigned peers = __match_any_sync(__activemask(), b);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    double sum = 0.0;
+    // fixed lane order: deterministic within the warp
+    for (unsigned m = peers; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        const double v = __shfl_sync(peers, w, src);
+        sum = __dadd_rn(sum, v);
+    }
+    if (lane == leader && b >= 0) atomicAdd(&sh[b], sum);
+}
+
+template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool REFILL>
+__global__ void __launch_bounds__(kBlock)
+trace_kernel(const KParams p)
+{
+    extern __shared__ double sh_hist[];
+    if (HIST) {
+        for (int b = threadIdx.x; b < p.nbins; b += kBlock) sh_hist[b] = 0.0;
+        __syncthreads();
+    }
+
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int Lm1 = p.L - 1;
+
+    // per-ray state
+    long long ray = -1;
+    bool active = false;
+    int i = 0;
+    double x = 0, y = 0, kx = 0, ky = 0;
+    double st = p.st, sst = __dmul_rn(p.st, p.st);
+    double *tp = nullptr;
+    // extras
+    int turn = -1;
+    double kprev = 0, lax = 0, ph = 0, a2 = 1.0;
+    int binprev = -1;
+
+    auto launch = [&](long long r) {
+        ray = r;
+        x = p.x0[r]; y = p.y0[r]; kx = p.kx0[r]; ky = p.ky0[r];
+        if (p.st_ray) { st = p.st_ray[r]; sst = __dmul_rn(st, st); }
+        i = 0;
+        if (TRAJ) {
+            tp = p.traj + r * p.stride;
+            st_state(tp, x, y, kx, ky);
+        }
+        if (EXTRAS) { turn = -1; lax = 0; ph = 0; }
+        if (HIST) { const double a = p.amp ? p.amp[r] : 1.0; a2 = __dmul_rn(a, a); }
+        active = true;
+    };
+
+    bool more = REFILL;   // warp-uniform: the queue may still hold rays
+    if (!REFILL) {
+        const long long r = (long long)blockIdx.x * kBlock + threadIdx.x;
+        if (r < p.nrays) launch(r);
+    }
+
+    for (;;) {
+        unsigned act = __ballot_sync(FULL, active);
+        if (REFILL && more && act != FULL) {
+            const unsigned idle = ~act;
+            const int leader = __ffs(idle) - 1;
+            const int want = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(p.counter, (unsigned long long)want);
+            base = __shfl_sync(FULL, base, leader);
+            if (!active) {
+                const long long r = (long long)base + __popc(idle & ((1u << lane) - 1u));
+                if (r < p.nrays) launch(r);
+            }
+            more = (long long)(base + want) < p.nrays;
+            act = __ballot_sync(FULL, active);
+        }
+        if (act == 0) break;
+
+        if (active) {
+            // sidtracemodule.c:36 -- guard on state i (NaN fails every comparison)
+            const bool in = (i < Lm1) & (x >= 0.0) & (x < p.fx) & (y >= 0.0) & (y < p.fy);
+            if (in) {
+                // :38  nearest lower-left cell, no interpolation
+                const int ind = __double2int_rz(y) * p.nxm1 + __double2int_rz(x);
+                const double2 m = __ldg(&p.field[ind]);
+
+                if (EXTRAS || HIST) {
+                    // state i is a KEPT state (ray.py:99-102 keeps [:n]); close segment (i-1, i)
+                    const double kcur = kmod(kx, ky);
+                    if (i > 0) {
+                        const double kavr = __dmul_rn(__dadd_rn(kprev, kcur), 0.5);   // ray.py:118
+                        const double sk = __dmul_rn(st, kavr);
+                        if (EXTRAS) {
+                            const double lnew = __dadd_rn(lax, sk);                  // :120 cumsum
+                            const double dl = __dsub_rn(lnew, lax);                  // :124 diff
+                            ph = __dadd_rn(ph, __dmul_rn(dl, kavr));                 // :125
+                            lax = lnew;
+                        }
+                        if (HIST) hist_add(sh_hist, binprev, __dmul_rn(a2, sk));
+                    }
+                    kprev = kcur;
+                    if (HIST) {
+                        // flux label of the segment START (oracle_deposit)
+                        const double xp = __dadd_rn(p.xorg, __dmul_rn(x, p.dx));
+                        const double yp = __dadd_rn(p.yorg, __dmul_rn(y, p.dy));
+                        const double rho = __ddiv_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(xp, xp), __dmul_rn(yp, yp))), p.r_lcs);
+                        binprev = -1;
+                        if (rho < p.rho_max) {
+                            const int b = __double2int_rz(__ddiv_rn(__dmul_rn(rho, (double)p.nbins), p.rho_max));
+                            if (b >= 0 && b < p.nbins) binprev = b;
+                        }
+                    }
+                }
+
+                const double tx = __dmul_rn(__dmul_rn(sst, m.x), 0.5);   // ((st*st)*Mx)/2
+                const double ty = __dmul_rn(__dmul_rn(sst, m.y), 0.5);
+                const double vx = __dadd_rn(tx, __dmul_rn(kx, st));
+                const double vy = __dadd_rn(ty, __dmul_rn(ky, st));
+                const double x1 = __dadd_rn(x, div_const<DIVC>(vx, p.dx, p.rdx));   // :41
+                const double y1 = __dadd_rn(y, div_const<DIVC>(vy, p.dy, p.rdy));   // :42
+                const double kx1 = __dadd_rn(kx, __dmul_rn(st, m.x));               // :44
+                const double ky1 = __dadd_rn(ky, __dmul_rn(st, m.y));               // :45
+
+                if (EXTRAS) {
+                    if (turn < 0 && ((ky > 0.0 && ky1 <= 0.0) || (ky < 0.0 && ky1 >= 0.0))) turn = i + 1;
+                }
+                x = x1; y = y1; kx = kx1; ky = ky1;
+                ++i;
+                if (TRAJ) {
+                    tp += 4;
+                    st_state(tp, x, y, kx, ky);
+                }
+            } else {
+                // retire: state i is the first out-of-domain state or the cap (sidtracemodule.c:50)
+                if (p.nsteps) p.nsteps[ray] = i;
+                if (p.endst) {
+                    p.endst[0 * p.nrays + ray] = x;
+                    p.endst[1 * p.nrays + ray] = y;
+                    p.endst[2 * p.nrays + ray] = kx;
+                    p.endst[3 * p.nrays + ray] = ky;
+                }
+                if (EXTRAS) {
+                    if (p.turn) p.turn[ray] = turn;
+                    if (p.lax_end) p.lax_end[ray] = lax;
+                    if (p.ph_end) p.ph_end[ray] = ph;
+                }
+                active = false;
+            }
+        }
+    }
+
+    if (HIST) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < p.nbins; b += kBlock) {
+            const double v = sh_hist[b];
+            if (v != 0.0) atomicAdd(&p.hist[b], v);
+        }
+    }
+}
+
+// {ax, ay} -> interleaved double2 per cell
+__global__ void interleave_kernel(const double *__restrict__ ax, const double *__restrict__ ay,
+                                  double2 *__restrict__ out, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += step) out[i] = make_double2(ax[i], ay[i]);
+}
+
+// FP64 peak: 8 independent DFMA chains per thread
+__global__ void fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double c0 = threadIdx.x, c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3, c4 = c0 + 4, c5 = c0 + 5, c6 = c0 + 6, c7 = c0 + 7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            c0 = __fma_rn(c0, a, b); c1 = __fma_rn(c1, a, b); c2 = __fma_rn(c2, a, b); c3 = __fma_rn(c3, a, b);
+            c4 = __fma_rn(c4, a, b); c5 = __fma_rn(c5, a, b); c6 = __fma_rn(c6, a, b); c7 = __fma_rn(c7, a, b);
+        }
+    }
+    const double s = ((c0 + c1) + (c2 + c3)) + ((c4 + c5) + (c6 + c7));
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// streaming 32-byte stores, fully coalesced
+__global__ void store_bw_kernel(double *out, long long nvec)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (; i < nvec; i += step) st_state(out + 4 * i, 1.0, 2.0, 3.0, (double)i);
+}
+
+}  // namespace stb

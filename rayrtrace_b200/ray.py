@@ -1,0 +1,210 @@
+"""Caller adapter of the hot path: the reference's ``Ray`` (ray.py:15-126) and
+the batched launch that replaces the serial ``for ...: Ray(...)`` loop of
+beam.py:340-342.
+
+``Ray(...)`` keeps the reference constructor, class-level settings
+(``MaxStep``, ``kStep``, ``traceType``) and attributes (``x, y, kx, ky, st,
+k, lax, ph``) and traces through ``sidtrace.trace`` on the GPU.
+
+``trace_rays(...)`` takes arrays of launch conditions, applies the same launch
+processing (ray.py:28-68) vectorised, and traces the whole set in ONE kernel
+launch; trajectories stay in HBM and are read back per ray on demand.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field as _dc_field
+from typing import Optional
+
+import numpy as np
+from scipy import constants as const
+
+from . import sidtrace as _st
+
+_DEFAULT_FREQ = 135e9   # ray.py:15 -- also the sentinel of the "infer freq from |k|" rule (ray.py:34,47)
+
+
+def _vacuum_k(kx0, ky0, freq):
+    """ray.py:28-51: normalise the launch direction to w/c, or infer the
+    frequency from |k| when |k| > 2 and freq is the default.  Returns
+    (kx0, ky0, freq).  Scalar inputs use the same numpy calls as the reference."""
+    c = const.speed_of_light * 100
+    w = 2 * np.pi * freq
+    if np.sqrt(kx0 ** 2 + ky0 ** 2) <= 2 or freq != _DEFAULT_FREQ:
+        k = np.linalg.norm((kx0, ky0))
+        kx0 = kx0 / k
+        ky0 = ky0 / k
+        kx0 = kx0 * w / c
+        ky0 = ky0 * w / c
+    elif freq == _DEFAULT_FREQ:
+        w = np.sqrt(kx0 ** 2 + ky0 ** 2) * c
+        freq = w / 2 / np.pi
+    return kx0, ky0, freq
+
+
+class Ray:
+    """One ray, traced at construction when ``n_field`` is given (ray.py:15-111)."""
+
+    MaxStep = 100000   # ray.py:11  array length handed to trace (cap = MaxStep-1 steps)
+    kStep = 1          # ray.py:12  multiplier of n_field.st
+    traceType = "c"    # ray.py:13  only the native path exists here (it runs on the GPU)
+
+    def __init__(self, x0=0, y0=0, kx0=0, ky0=1, freq=_DEFAULT_FREQ, amp=1, n_field=None):
+        self.len_unit = "cm"
+        L = int(Ray.MaxStep)
+        x = np.zeros(L)
+        y = np.zeros(L)
+        kx = np.zeros(L)
+        ky = np.zeros(L)
+        x[0], y[0] = x0, y0
+        kx0, ky0, self.freq = _vacuum_k(kx0, ky0, freq)
+        kx[0], ky[0] = kx0, ky0
+        self.amp = amp
+        self.n_field = n_field
+        self.x, self.y, self.kx, self.ky = x, y, kx, ky
+        if n_field is None:
+            return
+        if Ray.traceType != "c":
+            raise NotImplementedError(
+                "only traceType 'c' exists: the pure-Python twin (ray.py:85-96) is a CPU path; "
+                "see oracle/ for the checker")
+
+        # local refractive index scales the vacuum wave vector (ray.py:62-64)
+        refr = n_field.refractive_index(freq=self.freq, x=x[0], y=y[0])
+        refr = float(np.asarray(refr).reshape(-1)[0])
+        kx[0] = kx[0] * refr
+        ky[0] = ky[0] * refr
+        # physical -> grid coordinates (ray.py:67-68)
+        x[0] = n_field.x2grid(x[0])
+        y[0] = n_field.y2grid(y[0])
+        dx = n_field.dx[0]   # equidistant grid assumed (ray.py:70-73)
+        dy = n_field.dy[0]
+        st = n_field.st * Ray.kStep
+
+        i = _st.trace(x, y, kx, ky, st, dx, dy, n_field.nx, n_field.ny,
+                      np.ascontiguousarray(n_field.ax), np.ascontiguousarray(n_field.ay))
+        if i == 0:
+            raise ValueError(f"ray starts outside the density grid: ({x0}, {y0})")  # reference: IndexError at ray.py:105
+
+        # keep [:i] -- the first out-of-domain state is dropped (ray.py:99-102)
+        x, y, kx, ky = x[:i], y[:i], kx[:i], ky[:i]
+        # grid -> physical (ray.py:105-106)
+        self.x = x0 + (x - x[0]) * n_field.dx[0]
+        self.y = y0 + (y - y[0]) * n_field.dy[0]
+        self.kx, self.ky = kx, ky
+        # per-point step; the last point starts no segment (ray.py:110-111)
+        self.st = np.full_like(self.x, st)
+        self.st[-1] = 0
+
+    # ray.py:113-126
+    @property
+    def k(self):
+        return np.sqrt(self.kx ** 2 + self.ky ** 2)
+
+    @property
+    def lax(self):
+        k = self.k
+        kavr = (k[:-1] + k[1:]) / 2
+        return np.cumsum(np.insert(self.st[:-1] * kavr, 0, 0))
+
+    @property
+    def ph(self):
+        k = self.k
+        kavr = (k[:-1] + k[1:]) / 2
+        dl = np.diff(self.lax)
+        return np.cumsum(np.insert(dl * kavr, 0, 0))
+
+
+# --------------------------------------------------------------------------
+@dataclass
+class RayBundle:
+    """Result of ``trace_rays``: per-ray summaries on the host, trajectories in HBM."""
+    n_field: object
+    x0: np.ndarray            # physical launch positions
+    y0: np.ndarray
+    freq: float
+    st: float
+    amp: np.ndarray
+    xg0: np.ndarray           # launch state handed to the kernel (grid units / cm^-1)
+    yg0: np.ndarray
+    kx0: np.ndarray
+    ky0: np.ndarray
+    nsteps: np.ndarray        # int32, = len(Ray.x) of the reference
+    end_state: np.ndarray     # [4, n] first out-of-domain state (grid units), dropped by Ray
+    result: object = None     # sidtrace.BatchResult (traj is a CUDA tensor or None)
+    _cache: dict = _dc_field(default_factory=dict)
+
+    def __len__(self):
+        return len(self.nsteps)
+
+    def ray(self, r: int) -> "Ray":
+        """Materialise ray r as a reference-shaped Ray object (reads its
+        trajectory back from HBM)."""
+        if self.result is None or self.result.traj is None:
+            raise RuntimeError("trace_rays(..., keep_traj=False) kept no trajectories")
+        n = int(self.nsteps[r])
+        t = self.result.traj[r, :n].cpu().numpy() if hasattr(self.result.traj, "cpu") \
+            else np.asarray(self.result.traj[r, :n])
+        out = Ray.__new__(Ray)
+        out.len_unit = "cm"
+        out.freq = self.freq
+        out.amp = self.amp[r]
+        out.n_field = self.n_field
+        xg, yg = t[:, 0], t[:, 1]
+        out.x = self.x0[r] + (xg - xg[0]) * self.n_field.dx[0] if n else xg.copy()
+        out.y = self.y0[r] + (yg - yg[0]) * self.n_field.dy[0] if n else yg.copy()
+        out.kx = np.ascontiguousarray(t[:, 2])
+        out.ky = np.ascontiguousarray(t[:, 3])
+        out.st = np.full_like(out.x, self.st)
+        if n:
+            out.st[-1] = 0
+        return out
+
+
+def launch_states(n_field, x0, y0, kx0, ky0, freq):
+    """Vectorised ray.py:28-68: returns (xg0, yg0, kx, ky, freq) as the kernel
+    expects them.  Direction vectors are normalised with sqrt(kx^2+ky^2)
+    (np.linalg.norm per ray in the reference; <= 1 ulp apart)."""
+    x0 = np.atleast_1d(np.asarray(x0, np.float64))
+    y0 = np.atleast_1d(np.asarray(y0, np.float64))
+    kx0 = np.broadcast_to(np.asarray(kx0, np.float64), x0.shape).copy()
+    ky0 = np.broadcast_to(np.asarray(ky0, np.float64), x0.shape).copy()
+    c = const.speed_of_light * 100
+    w = 2 * np.pi * freq
+    kn = np.sqrt(kx0 ** 2 + ky0 ** 2)
+    if freq != _DEFAULT_FREQ or np.all(kn <= 2):
+        kx = kx0 / kn * w / c
+        ky = ky0 / kn * w / c
+    else:
+        raise ValueError("a batch must share one frequency: pass freq explicitly (ray.py:47-51 infers it per ray)")
+    den = n_field.n_interpolant_points(x0, y0) if hasattr(n_field, "n_interpolant_points") else \
+        np.array([np.asarray(n_field.n_interpolant(a, b)).reshape(-1)[0] for a, b in zip(x0, y0)])
+    from .nfield import critical_den
+    refr = np.sqrt(1 - den / critical_den(freq, den_unit=n_field.den_unit))
+    kx = kx * refr
+    ky = ky * refr
+    xg = np.ascontiguousarray(n_field.x2grid(x0), np.float64)
+    yg = np.ascontiguousarray(n_field.y2grid(y0), np.float64)
+    return xg, yg, np.ascontiguousarray(kx), np.ascontiguousarray(ky), freq
+
+
+def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional[int] = None,
+               keep_traj: bool = True, want_extras: bool = False) -> RayBundle:
+    """Trace a whole fan of rays in one kernel launch (replaces beam.py:340-342).
+
+    max_steps: array length per ray (the reference's Ray.MaxStep = 100000 would
+    be 3.2 MB per ray; default here is a bound from the grid size:
+    4*(nx+ny) states, enough for any non-trapped ray; rays hitting the cap
+    report nsteps == max_steps-1 exactly like the reference at its cap)."""
+    xg, yg, kx, ky, freq = launch_states(n_field, x0, y0, kx0, ky0, freq)
+    n = len(xg)
+    if amp is None:
+        amp = np.ones(n)
+    amp = np.broadcast_to(np.asarray(amp, np.float64), (n,)).copy()
+    L = int(max_steps) if max_steps else min(int(Ray.MaxStep), 4 * (n_field.nx + n_field.ny))
+    st = float(n_field.st * Ray.kStep)
+    f = n_field.device_field()
+    res = _st.trace_batch(f, xg, yg, kx, ky, L=L, st=st, dx=float(n_field.dx[0]), dy=float(n_field.dy[0]),
+                          traj=True if keep_traj else None, want_end=True, want_extras=want_extras)
+    return RayBundle(n_field=n_field, x0=np.atleast_1d(np.asarray(x0, np.float64)),
+                     y0=np.atleast_1d(np.asarray(y0, np.float64)), freq=freq, st=st, amp=amp,
+                     xg0=xg, yg0=yg, kx0=kx, ky0=ky, nsteps=res.nsteps, end_state=res.end_state, result=res)

@@ -1,0 +1,353 @@
+"""Python surface of the reference's ``sidtrace`` extension, backed by the
+sm_100a CUDA library through its C ABI (include/sidtrace_b200.h).
+
+Legacy calls (same names, argument meaning and return values as
+sidtracemodule.c:71-75):
+
+    trace(x, y, kx, ky, st, dx, dy, nx, ny, ax, ay) -> int      # ray.py:80-83
+    check(nx, ny, i, j, a) -> float                              # ray.py:7
+
+Unlike the reference (which performs no validation, sidtracemodule.c:22-33, and
+corrupts memory on a wrong dtype) the shim raises TypeError / ValueError.
+
+Batched call, the fast path a beam-level caller uses instead of the serial
+``for ...: Ray(...)`` loop of beam.py:340-342:
+
+    trace_batch(field, x0, y0, kx0, ky0, L=..., st=..., dx=..., dy=...) -> BatchResult
+
+PyTorch appears here only as the owner of device buffers and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import (F_DIV_IEEE, F_HOST_IO, F_NO_REFILL, F_TRAJ_HOST, SidtraceError, StbBatch, lib)
+
+__all__ = ["trace", "check", "trace_batch", "Field", "BatchResult", "invalidate", "SidtraceError"]
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _is_tensor(a) -> bool:
+    return type(a).__module__.startswith("torch") and hasattr(a, "data_ptr")
+
+
+def _f64_host(a, name: str, ndim: Optional[int] = None) -> np.ndarray:
+    if not isinstance(a, np.ndarray):
+        raise TypeError(f"{name} must be a numpy.ndarray, got {type(a).__name__}")
+    if a.dtype != np.float64:
+        raise TypeError(f"{name} must have dtype float64, got {a.dtype}")
+    if not a.flags.c_contiguous:
+        raise ValueError(f"{name} must be C-contiguous")
+    if ndim is not None and a.ndim != ndim:
+        raise ValueError(f"{name} must be {ndim}-D, got {a.ndim}-D")
+    return a
+
+
+class Field:
+    """An acceleration field (``ax``, ``ay`` of den.py:94-95) resident in HBM.
+
+    ``ax``, ``ay``: float64, shape (ny-1, nx-1), numpy arrays (uploaded) or CUDA
+    torch tensors (copied device to device).
+    """
+
+    def __init__(self, ax, ay, nx: Optional[int] = None, ny: Optional[int] = None):
+        self._h = ctypes.c_void_p()
+        on_device = _is_tensor(ax)
+        if on_device != _is_tensor(ay):
+            raise TypeError("ax and ay must both be numpy arrays or both be CUDA tensors")
+        if on_device:
+            torch = _torch()
+            for name, a in (("ax", ax), ("ay", ay)):
+                if a.dtype != torch.float64 or not a.is_cuda or not a.is_contiguous():
+                    raise TypeError(f"{name} must be a contiguous float64 CUDA tensor")
+            shape = tuple(ax.shape)
+            if tuple(ay.shape) != shape:
+                raise ValueError("ax and ay must have the same shape")
+            pax, pay = ax.data_ptr(), ay.data_ptr()
+            _cabi.check(lib.stb_set_device(ax.device.index or 0))
+            torch.cuda.current_stream(ax.device).synchronize()
+        else:
+            _f64_host(ax, "ax")
+            _f64_host(ay, "ay")
+            shape = ax.shape
+            if ay.shape != shape:
+                raise ValueError("ax and ay must have the same shape")
+            pax, pay = ax.ctypes.data, ay.ctypes.data
+        if nx is None or ny is None:
+            if len(shape) != 2:
+                raise ValueError("nx, ny are required when ax is not 2-D")
+            ny, nx = shape[0] + 1, shape[1] + 1
+        nx, ny = int(nx), int(ny)
+        n_el = int(np.prod(shape))
+        if n_el != (nx - 1) * (ny - 1):
+            raise ValueError(f"ax has {n_el} elements, expected (ny-1)*(nx-1) = {(ny - 1) * (nx - 1)}")
+        self.nx, self.ny = nx, ny
+        _cabi.check(lib.stb_field_create(pax, pay, nx, ny, 1 if on_device else 0, ctypes.byref(self._h)))
+
+    def peek(self, i: int, j: int, which: int = 0) -> float:
+        out = ctypes.c_double()
+        _cabi.check(lib.stb_field_peek(self._h, int(i), int(j), int(which), ctypes.byref(out)))
+        return out.value
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib.stb_field_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+# --------------------------------------------------------------------------
+# legacy per-ray surface
+# --------------------------------------------------------------------------
+_field_cache: dict = {}
+
+
+def _fingerprint(a: np.ndarray) -> tuple:
+    flat = a.reshape(-1)
+    step = max(1, flat.size // 4096)
+    return (a.ctypes.data, a.shape, hash(flat[::step].tobytes()))
+
+
+def _cached_field(ax: np.ndarray, ay: np.ndarray, nx: int, ny: int) -> Field:
+    """The reference re-reads ax/ay from host memory on every call; here the
+    upload is cached per (ax, ay) object pair.  Identity is (id, data pointer,
+    shape, strided content sample); a weakref drops the entry when ax dies.
+    After mutating ax/ay IN PLACE call ``invalidate()``."""
+    key = (id(ax), id(ay), nx, ny)
+    fp = (_fingerprint(ax), _fingerprint(ay))
+    ent = _field_cache.get(key)
+    if ent is not None and ent[1] == fp:
+        return ent[0]
+    if ent is not None:
+        ent[0].close()
+    f = Field(ax, ay, nx, ny)
+    try:
+        ref = weakref.ref(ax, lambda _r, k=key: _drop(k))
+    except TypeError:
+        ref = None
+    _field_cache[key] = (f, fp, ref)
+    if len(_field_cache) > 16:   # bound HBM held by stale fields
+        old = next(iter(_field_cache))
+        if old != key:
+            _drop(old)
+    return f
+
+
+def _drop(key) -> None:
+    ent = _field_cache.pop(key, None)
+    if ent is not None:
+        ent[0].close()
+
+
+def invalidate() -> None:
+    """Forget every cached field upload (call after mutating ax/ay in place)."""
+    for k in list(_field_cache):
+        _drop(k)
+
+
+def trace(x, y, kx, ky, st, dx, dy, nx, ny, ax, ay) -> int:
+    """Drop-in for ``sidtrace.trace`` (sidtracemodule.c:8-51).
+
+    x, y, kx, ky: float64 1-D C-contiguous arrays of equal length L, element 0 =
+    launch state (grid units / cm^-1); mutated in place for indices 1..i.
+    Returns i, the number of steps taken.  Runs on the GPU (one round trip)."""
+    x = _f64_host(x, "x", 1)
+    y = _f64_host(y, "y", 1)
+    kx = _f64_host(kx, "kx", 1)
+    ky = _f64_host(ky, "ky", 1)
+    L = x.shape[0]
+    if not (y.shape[0] == kx.shape[0] == ky.shape[0] == L):
+        raise ValueError("x, y, kx, ky must have equal length")
+    if L < 1:
+        raise ValueError("x must have at least one element (the launch state)")
+    ax = _f64_host(ax, "ax")
+    ay = _f64_host(ay, "ay")
+    nx, ny = int(nx), int(ny)
+    if ax.size != (nx - 1) * (ny - 1) or ay.size != ax.size:
+        raise ValueError(f"ax/ay must hold (ny-1)*(nx-1) = {(ny - 1) * (nx - 1)} elements")
+    f = _cached_field(ax, ay, nx, ny)
+    n = ctypes.c_int64()
+    _cabi.check(lib.stb_trace(f._h, x.ctypes.data, y.ctypes.data, kx.ctypes.data, ky.ctypes.data,
+                              L, float(st), float(dx), float(dy), ctypes.byref(n)))
+    return int(n.value)
+
+
+def check(nx, ny, i, j, a) -> float:
+    """Drop-in for ``sidtrace.check`` (sidtracemodule.c:53-69): ``a[i*nx + j]``."""
+    a = _f64_host(a, "a")
+    nx, ny, i, j = int(nx), int(ny), int(i), int(j)
+    ind = i * nx + j
+    if not 0 <= ind < a.size:
+        raise IndexError(f"i*nx + j = {ind} outside array of {a.size} elements")
+    out = ctypes.c_double()
+    _cabi.check(lib.stb_check(nx, ny, i, j, a.ctypes.data, ctypes.byref(out)))
+    return out.value
+
+
+# --------------------------------------------------------------------------
+# batched surface
+# --------------------------------------------------------------------------
+@dataclass
+class BatchResult:
+    nsteps: object = None       # int32 [nrays]
+    end_state: object = None    # float64 [4, nrays]  (x, y, kx, ky) at index nsteps
+    traj: object = None         # float64 [nrays, L, 4] CUDA tensor (or numpy with traj_host)
+    turn_index: object = None   # int32 [nrays]
+    lax_end: object = None      # float64 [nrays]
+    ph_end: object = None       # float64 [nrays]
+    hist: object = None         # float64 [nbins]
+
+    def ray(self, r: int):
+        """Kept part of ray r as the reference's Ray holds it (ray.py:99-102):
+        four views x, y, kx, ky of length nsteps[r] (grid units)."""
+        n = int(self.nsteps[r])
+        t = self.traj[r, :n]
+        return t[:, 0], t[:, 1], t[:, 2], t[:, 3]
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_tensor(a):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float, dy: float,
+                st_ray=None, traj=None, want_end: bool = True, want_extras: bool = False,
+                hist=None, nbins: int = 0, amp=None, xorg: float = 0.0, yorg: float = 0.0,
+                r_lcs: float = 1.0, rho_max: float = 1.0, traj_host: bool = False,
+                div_ieee: bool = False, refill: bool = True, out: Optional[BatchResult] = None,
+                stream=None) -> BatchResult:
+    """Trace ``len(x0)`` rays in one launch.
+
+    x0, y0, kx0, ky0: launch states (grid units / cm^-1, ray.py:62-68), all numpy
+    float64 arrays (host I/O: results come back as numpy arrays; pass pinned
+    memory for full PCIe speed) or all CUDA float64 tensors (device I/O:
+    asynchronous on the current torch stream, results are CUDA tensors).
+
+    traj: None -> no trajectories; True -> allocate a zeroed [nrays, L, 4] CUDA
+    tensor; or a preallocated CUDA tensor of that shape (32-byte aligned).
+    With ``traj_host=True`` and host I/O, a numpy [nrays, L, 4] array.
+    """
+    torch = _torch()
+    dev_io = _is_tensor(x0)
+    ins = {"x0": x0, "y0": y0, "kx0": kx0, "ky0": ky0}
+    if st_ray is not None:
+        ins["st_ray"] = st_ray
+    if amp is not None:
+        ins["amp"] = amp
+    n = int(x0.shape[0])
+    for name, a in ins.items():
+        if dev_io:
+            if not _is_tensor(a) or a.dtype != torch.float64 or not a.is_cuda or not a.is_contiguous():
+                raise TypeError(f"{name} must be a contiguous float64 CUDA tensor (device I/O)")
+        else:
+            _f64_host(a, name, 1)
+        if int(a.shape[0]) != n or a.ndim != 1:
+            raise ValueError(f"{name} must be 1-D of length {n}")
+    L = int(L)
+    if L < 1:
+        raise ValueError("L must be >= 1")
+
+    res = out if out is not None else BatchResult()
+    device = x0.device if dev_io else torch.device("cuda", torch.cuda.current_device())
+    _cabi.check(lib.stb_set_device(device.index or 0))
+
+    def alloc(shape, dtype_np, dtype_t):
+        if dev_io:
+            return torch.empty(shape, dtype=dtype_t, device=device)
+        return np.empty(shape, dtype=dtype_np)
+
+    if res.nsteps is None:
+        res.nsteps = alloc((n,), np.int32, torch.int32)
+    if want_end and res.end_state is None:
+        res.end_state = alloc((4, n), np.float64, torch.float64)
+    if want_extras:
+        if res.turn_index is None:
+            res.turn_index = alloc((n,), np.int32, torch.int32)
+        if res.lax_end is None:
+            res.lax_end = alloc((n,), np.float64, torch.float64)
+        if res.ph_end is None:
+            res.ph_end = alloc((n,), np.float64, torch.float64)
+
+    flags = 0
+    if not dev_io:
+        flags |= F_HOST_IO
+    if div_ieee:
+        flags |= F_DIV_IEEE
+    if not refill:
+        flags |= F_NO_REFILL
+
+    if traj is True:
+        if traj_host and not dev_io:
+            traj = np.zeros((n, L, 4), np.float64)
+        else:
+            traj = torch.zeros((n, L, 4), dtype=torch.float64, device=device)
+    if traj is not None:
+        if _is_tensor(traj):
+            if traj.dtype != torch.float64 or not traj.is_cuda or not traj.is_contiguous() \
+                    or tuple(traj.shape) != (n, L, 4):
+                raise TypeError(f"traj must be a contiguous float64 CUDA tensor of shape ({n}, {L}, 4)")
+        else:
+            _f64_host(traj, "traj", 3)
+            if traj.shape != (n, L, 4):
+                raise ValueError(f"traj must have shape ({n}, {L}, 4)")
+            flags |= F_TRAJ_HOST
+        res.traj = traj
+
+    if hist is None and nbins:
+        hist = torch.zeros(nbins, dtype=torch.float64, device=device) if dev_io else np.zeros(nbins)
+    if hist is not None:
+        nbins = int(hist.shape[0])
+        if dev_io != _is_tensor(hist):
+            raise TypeError("hist must live where the launch states live (numpy for host I/O, CUDA tensor otherwise)")
+        res.hist = hist
+
+    b = StbBatch()
+    b.struct_size = ctypes.sizeof(StbBatch)
+    b.flags = flags
+    b.nrays = n
+    b.L = L
+    b.x0, b.y0, b.kx0, b.ky0 = _ptr(x0), _ptr(y0), _ptr(kx0), _ptr(ky0)
+    b.st = float(st)
+    b.st_ray = _ptr(st_ray)
+    b.dx, b.dy = float(dx), float(dy)
+    b.traj = _ptr(res.traj) if traj is not None else None
+    b.traj_ray_stride = 4 * L
+    b.nsteps = _ptr(res.nsteps)
+    b.end_state = _ptr(res.end_state) if want_end else None
+    if want_extras:
+        b.turn_index, b.lax_end, b.ph_end = _ptr(res.turn_index), _ptr(res.lax_end), _ptr(res.ph_end)
+    if hist is not None:
+        b.hist = _ptr(hist)
+        b.nbins = nbins
+        b.amp = _ptr(amp)
+        b.xorg, b.yorg, b.r_lcs, b.rho_max = float(xorg), float(yorg), float(r_lcs), float(rho_max)
+
+    if stream is None:
+        stream = torch.cuda.current_stream(device)
+    sptr = ctypes.c_void_p(stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
+    _cabi.check(lib.stb_trace_batch(field._h, ctypes.byref(b), sptr))
+    return res

@@ -1,0 +1,176 @@
+"""Generates the committed golden fixtures from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference and oracle/_ref):
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+Everything is produced by reference code:
+  * kat.npz       -- G1..G6 of SURVEY.md section 4.1: the compiled reference
+                     extension (sidtracemodule.c) called exactly as ray.py:80-83
+                     calls it.
+  * ft2_ray.npz   -- BASELINE config 1: one ray through the FT-2 parabolic
+                     density, via the reference's den.Nfield and ray.Ray
+                     (both traceType 'c' and the pure-Python twin ray.py:85-96).
+  * ft2_fan.npz   -- a 96-ray fan through an under-dense and an over-dense
+                     (reflecting) FT-2 profile: reference Nfield + compiled trace.
+Densities are analytic (parameters stored), so fixtures stay small; the
+reference-derived field is pinned by its step `st`, SHA-256 digests of ax/ay
+and a strided sample.
+"""
+import hashlib
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import oracle  # noqa: E402
+from oracle import refenv  # noqa: E402
+
+warnings.simplefilter("ignore")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def ft2_density(nx, n0, edge=1e12, r_dia=7.85, half=10.0):
+    """n = n0 * max(0, 1 - r^2/r_dia^2) + edge on x, y = linspace(-half, half, nx)  """
+    x = np.linspace(-half, half, nx)
+    y = np.linspace(-half, half, nx)
+    X, Y = np.meshgrid(x, y)
+    n = n0 * np.maximum(0, 1 - (X ** 2 + Y ** 2) / r_dia ** 2) + edge
+    return n, x, y
+
+
+def run_ref_trace(ref, L, x0, y0, kx0, ky0, st, dx, dy, nx, ny, ax, ay):
+    x = np.zeros(L); y = np.zeros(L); kx = np.zeros(L); ky = np.zeros(L)
+    x[0], y[0], kx[0], ky[0] = x0, y0, kx0, ky0
+    n = ref.trace(x, y, kx, ky, st, dx, dy, nx, ny, ax, ay)
+    return n, x, y, kx, ky
+
+
+def make_kat(ref):
+    out = {}
+    cases = {
+        # name: (L, nx, ny, ax, ay, st, dx, dy, x0, y0, kx0, ky0)
+        "G1": (4096, 11, 9, np.full((8, 10), 0.5), np.full((8, 10), -0.25), 0.5, 1.0, 2.0, 1.2, 3.7, 0.3, 0.9),
+        "G2": (4096, 33, 17, np.zeros((16, 32)), np.zeros((16, 32)), 0.5, 1.0, 1.0, 4.0, 0.0, 0.25, 1.0),
+        "G3": (4096, 21, 41, np.zeros((40, 20)), np.full((40, 20), -0.8), 0.125, 0.5, 0.5, 10.25, 3.3, 0.0625, 2.0),
+        "G4": (4096, 7, 5, np.tile(np.arange(1.0, 7.0), (4, 1)), -np.tile(np.arange(1.0, 5.0)[:, None], (1, 6)),
+               0.25, 1.0, 1.0, 0.5, 0.5, 1.0, 2.0),
+        "G5": (8, 101, 101, np.zeros((100, 100)), np.zeros((100, 100)), 0.5, 1.0, 1.0, 50.0, 50.0, 0.0, 1.0),
+        "G6a": (4096, 101, 101, np.zeros((100, 100)), np.zeros((100, 100)), 0.5, 1.0, 1.0, -0.5, 50.0, 0.0, 1.0),
+        "G6b": (4096, 101, 101, np.zeros((100, 100)), np.zeros((100, 100)), 0.5, 1.0, 1.0, np.nan, 50.0, 0.0, 1.0),
+        "G6c": (4096, 101, 101, np.zeros((100, 100)), np.zeros((100, 100)), 0.5, 1.0, 1.0, 100.0, 50.0, 0.0, 1.0),
+    }
+    for name, (L, nx, ny, ax, ay, st, dx, dy, x0, y0, kx0, ky0) in cases.items():
+        ax = np.ascontiguousarray(ax, np.float64)
+        ay = np.ascontiguousarray(ay, np.float64)
+        n, x, y, kx, ky = run_ref_trace(ref, L, x0, y0, kx0, ky0, st, dx, dy, nx, ny, ax, ay)
+        keep = min(L, n + 2)   # states 0..n plus one untouched entry
+        out[f"{name}_params"] = np.array([L, nx, ny, st, dx, dy, x0, y0, kx0, ky0], np.float64)
+        out[f"{name}_ax"] = ax
+        out[f"{name}_ay"] = ay
+        out[f"{name}_n"] = np.int64(n)
+        out[f"{name}_x"] = x[:keep]
+        out[f"{name}_y"] = y[:keep]
+        out[f"{name}_kx"] = kx[:keep]
+        out[f"{name}_ky"] = ky[:keep]
+        print(name, "n =", n)
+    np.savez_compressed(os.path.join(HERE, "kat.npz"), **out)
+
+
+def make_ft2_ray(den, ray):
+    nx = 201
+    n, x, y = ft2_density(nx, 4e13)
+    nf = den.Nfield(n, x=x, y=y)                       # reference field producer, default freq 136.26 GHz
+    freq = 136.268e9                                   # Beam's launch frequency (beam.py:30): mismatch replicated
+    ray.Ray.traceType = "c"
+    rc = ray.Ray(-3.0, -9.5, 0, 1, freq, 1, n_field=nf)
+    ray.Ray.traceType = "py"
+    rp = ray.Ray(-3.0, -9.5, 0, 1, freq, 1, n_field=nf)
+    ray.Ray.traceType = "c"
+    assert np.array_equal(rc.x, rp.x) and np.array_equal(rc.ky, rp.ky), "C and Python twins differ"
+    # the raw grid-unit call, exactly as ray.py:59-83 prepares it
+    c = 299792458.0 * 100
+    w = 2 * np.pi * freq
+    refr = nf.refractive_index(freq=freq, x=-3.0, y=-9.5)
+    kx0 = float(np.asarray(0.0 * w / c * refr).reshape(-1)[0])
+    ky0 = float(np.asarray(1.0 * w / c * refr).reshape(-1)[0])
+    xg0 = float(nf.x2grid(-3.0)); yg0 = float(nf.y2grid(-9.5))
+    ref = oracle.ref()
+    L = 100000
+    i, gx, gy, gkx, gky = run_ref_trace(ref, L, xg0, yg0, kx0, ky0, nf.st, nf.dx[0], nf.dy[0], nf.nx, nf.ny, nf.ax, nf.ay)
+    assert i == len(rc.x)
+    assert np.array_equal(gkx[:i], rc.kx) and np.array_equal(gky[:i], rc.ky), "launch-state restatement differs from Ray"
+    np.savez_compressed(
+        os.path.join(HERE, "ft2_ray.npz"),
+        nx=np.int64(nx), n0=4e13, edge=1e12, r_dia=7.85, half=10.0,
+        field_freq=136.26e9, freq=freq, x0=-3.0, y0=-9.5,
+        st=np.float64(nf.st), dx0=np.float64(nf.dx[0]), dy0=np.float64(nf.dy[0]),
+        ax_sha=sha(nf.ax), ay_sha=sha(nf.ay), ax_sample=nf.ax[::20, ::20].copy(), ay_sample=nf.ay[::20, ::20].copy(),
+        launch=np.array([xg0, yg0, kx0, ky0]), refr=np.float64(np.asarray(refr).reshape(-1)[0]),
+        nsteps=np.int64(i), grid_traj=np.stack([gx[:i + 1], gy[:i + 1], gkx[:i + 1], gky[:i + 1]], 1),
+        ray_x=rc.x, ray_y=rc.y, ray_kx=rc.kx, ray_ky=rc.ky, ray_st=rc.st, ray_lax=rc.lax, ray_ph=rc.ph, ray_k=rc.k)
+    print("ft2_ray: n =", i, "end =", rc.x[-1], rc.y[-1])
+
+
+def make_ft2_fan(den):
+    ref = oracle.ref()
+    out = {}
+    rng = np.random.default_rng(20260101)
+    nray = 96
+    L = 4096
+    for tag, nx, n0 in (("under", 201, 4e13), ("over", 129, 3.0e14)):
+        n, x, y = ft2_density(nx, n0)
+        nf = den.Nfield(n, x=x, y=y)
+        # fan: start points on y = -9.5 cm, directions within +-0.35 rad of +y, |k| = w/c * N(edge)
+        freq = 136.268e9
+        c = 299792458.0 * 100
+        k0 = 2 * np.pi * freq / c * float(nf.refractive_index(freq=freq))
+        xs = rng.uniform(-6.0, 6.0, nray)
+        ang = rng.uniform(-0.35, 0.35, nray)
+        xg0 = np.asarray(nf.x2grid(xs), np.float64)
+        yg0 = np.full(nray, float(nf.y2grid(-9.5)))
+        kx0 = k0 * np.sin(ang)
+        ky0 = k0 * np.cos(ang)
+        nst = np.zeros(nray, np.int64)
+        end = np.zeros((4, nray))
+        dig = []
+        ymax = np.zeros(nray)
+        for r in range(nray):
+            i, gx, gy, gkx, gky = run_ref_trace(ref, L, xg0[r], yg0[r], kx0[r], ky0[r], nf.st, nf.dx[0], nf.dy[0],
+                                                nf.nx, nf.ny, nf.ax, nf.ay)
+            nst[r] = i
+            end[:, r] = gx[i], gy[i], gkx[i], gky[i]
+            dig.append(sha(np.stack([gx[:i + 1], gy[:i + 1], gkx[:i + 1], gky[:i + 1]], 1)))
+            ymax[r] = gy[:i + 1].max()
+        out.update({
+            f"{tag}_nx": np.int64(nx), f"{tag}_n0": n0, f"{tag}_st": np.float64(nf.st),
+            f"{tag}_dx0": np.float64(nf.dx[0]), f"{tag}_dy0": np.float64(nf.dy[0]),
+            f"{tag}_ax_sha": sha(nf.ax), f"{tag}_ay_sha": sha(nf.ay),
+            f"{tag}_xg0": xg0, f"{tag}_yg0": yg0, f"{tag}_kx0": kx0, f"{tag}_ky0": ky0,
+            f"{tag}_nsteps": nst, f"{tag}_end": end, f"{tag}_traj_sha": np.array(dig), f"{tag}_ymax": ymax,
+        })
+        print(f"ft2_fan[{tag}]: steps min/median/max = {nst.min()}/{int(np.median(nst))}/{nst.max()}",
+              "reflected:", int((end[3] < 0).sum()))
+    out["L"] = np.int64(L)
+    out["edge"] = 1e12
+    out["r_dia"] = 7.85
+    out["half"] = 10.0
+    np.savez_compressed(os.path.join(HERE, "ft2_fan.npz"), **out)
+
+
+if __name__ == "__main__":
+    if not oracle.have_ref():
+        oracle.build(ref=True)
+    den, ray = refenv.modules()
+    make_kat(oracle.ref())
+    make_ft2_ray(den, ray)
+    make_ft2_fan(den)
+    for f in ("kat.npz", "ft2_ray.npz", "ft2_fan.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -1,0 +1,65 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol that
+include/sidtrace_b200.h declares; the ctypes mirror of stb_batch_t matches the
+C layout.  No compute calls here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sidtrace_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(stb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_expected_symbols():
+    from rayrtrace_b200 import _cabi
+    assert _declared() == sorted(_cabi.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    from rayrtrace_b200 import _cabi
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in _declared():
+        assert hasattr(lib, name), f"{name} not exported by {_cabi.LIB_PATH}"
+    assert _cabi.lib.stb_abi_version() == _cabi.STB_ABI_VERSION
+    assert _cabi.lib.stb_last_error() is not None
+
+
+def test_batch_struct_layout_matches_c(tmp_path):
+    from rayrtrace_b200._cabi import StbBatch
+    fields = [f[0] for f in StbBatch._fields_]
+    prog = tmp_path / "layout.c"
+    body = "\n".join(f'    printf("{f} %zu\\n", offsetof(stb_batch_t, {f}));' for f in fields)
+    prog.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{HEADER}"\n'
+                    f'int main(void) {{\n    printf("sizeof %zu\\n", sizeof(stb_batch_t));\n{body}\n    return 0;\n}}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call([os.environ.get("CC", "gcc"), str(prog), "-o", str(exe)])
+    out = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    assert int(out["sizeof"]) == ctypes.sizeof(StbBatch)
+    for f in fields:
+        assert int(out[f]) == getattr(StbBatch, f).offset, f
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No CPU fallback: importing the product without the CUDA library raises."""
+    env = dict(os.environ, SIDTRACE_B200_LIB=str(tmp_path / "nope.so"), PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", "import rayrtrace_b200.sidtrace"], env=env, capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr.replace("There is no CPU fallback", "no CPU fallback")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "rayrtrace_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "sidtrace_oracle" not in text, f

@@ -1,0 +1,65 @@
+"""Argument validation and host-side marshalling of the Python surface; nothing
+here reaches a CUDA call (the checks run first)."""
+import numpy as np
+import pytest
+
+from rayrtrace_b200 import sidtrace
+
+
+def _arrs(L=8, dtype=np.float64):
+    return [np.zeros(L, dtype) for _ in range(4)]
+
+
+def test_trace_rejects_wrong_dtype_and_layout():
+    ax = np.zeros((4, 6)); ay = np.zeros((4, 6))
+    x, y, kx, ky = _arrs()
+    with pytest.raises(TypeError):
+        sidtrace.trace(x.astype(np.float32), y, kx, ky, 0.1, 1, 1, 7, 5, ax, ay)
+    with pytest.raises(TypeError):
+        sidtrace.trace(list(x), y, kx, ky, 0.1, 1, 1, 7, 5, ax, ay)
+    with pytest.raises(ValueError):
+        sidtrace.trace(np.zeros(16)[::2], y, kx, ky, 0.1, 1, 1, 7, 5, ax, ay)
+    with pytest.raises(ValueError):
+        sidtrace.trace(x, np.zeros(9), kx, ky, 0.1, 1, 1, 7, 5, ax, ay)
+    with pytest.raises(ValueError):
+        sidtrace.trace(x, y, kx, ky, 0.1, 1, 1, 8, 5, ax, ay)          # ax is not (ny-1)*(nx-1)
+    with pytest.raises(TypeError):
+        sidtrace.trace(x, y, kx, ky, 0.1, 1, 1, 7, 5, ax.astype(np.float32), ay)
+
+
+def test_check_bounds_and_type():
+    a = np.arange(35.0).reshape(5, 7)
+    with pytest.raises(IndexError):
+        sidtrace.check(7, 5, 5, 0, a)
+    with pytest.raises(TypeError):
+        sidtrace.check(7, 5, 0, 0, a.astype(np.int64))
+
+
+def test_check_value_is_reference_layout():
+    # a[i*nx + j] (sidtracemodule.c:66): a host-memory probe, runs without a GPU
+    a = np.arange(35.0).reshape(5, 7)
+    assert sidtrace.check(7, 5, 2, 3, a) == 17.0
+
+
+def test_dropin_module_resolves():
+    import importlib
+    import sys
+    import rayrtrace_b200
+    sys.path.insert(0, rayrtrace_b200.dropin_path())
+    try:
+        sys.modules.pop("sidtrace", None)
+        m = importlib.import_module("sidtrace")
+        assert m.trace is sidtrace.trace and m.check is sidtrace.check
+    finally:
+        sys.path.remove(rayrtrace_b200.dropin_path())
+        sys.modules.pop("sidtrace", None)
+
+
+def test_vacuum_k_rules():
+    """ray.py:34-51: directions are normalised to w/c; |k| > 2 at the default freq infers the frequency."""
+    from rayrtrace_b200.ray import _vacuum_k
+    c = 299792458.0 * 100
+    kx, ky, f = _vacuum_k(0.0, 2.0, 136e9)
+    assert kx == 0.0 and ky == pytest.approx(2 * np.pi * 136e9 / c, rel=1e-15) and f == 136e9
+    kx, ky, f = _vacuum_k(3.0, 4.0, 135e9)
+    assert (kx, ky) == (3.0, 4.0) and f == pytest.approx(5.0 * c / 2 / np.pi, rel=1e-15)
