@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- ray-steps/s (FP64) of the sidtrace hot path on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (rank 0 only)
+
+A "step" is one pass of the hot path over one batch of synthetic input: the
+BASELINE config-3 workload (10^6-ray seven-beam FT-2 fan through a 1001^2
+shaped-density grid) PER GPU, full-trajectory output ([ray][step][4] FP64 in
+HBM) + per-ray step counts and end states.  Weak scaling: every rank traces
+its own 10^6-ray interleaved shard of an N*10^6-ray fan; no data-path
+collective (rays are independent).
+
+Prints ONE JSON line on rank 0 (contract: task statement / DESIGN.md section 6).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ray-steps/sec (FP64)"
+UNIT = "ray-steps/s"
+BYTES_PER_RAY_STEP = 32          # x, y, kx, ky FP64 written per step
+FLOPS_PER_RAY_STEP = 16          # sidtracemodule.c:41-45
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nrays", type=int, default=1_000_000, help="rays per GPU")
+    ap.add_argument("--nx", type=int, default=1001, help="grid nodes per axis")
+    ap.add_argument("--cap", type=int, default=0, help="states per ray (0 = synth.default_cap)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
+    ap.add_argument("--extra", action="store_true", help="also time endpoint-only mode and the FP64 peak")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------
+# CPU arm: the UNMODIFIED reference extension (oracle/_ref), called per ray exactly as
+# ray.py:80-83 does, on all host cores (the extension holds the GIL -> processes).
+# --------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker_init(nx, ny, ax, ay, L, kind):
+    import oracle
+    _W["fn"] = oracle.ref().trace if kind == "reference" else oracle.trace
+    _W["ax"], _W["ay"], _W["nx"], _W["ny"] = ax, ay, nx, ny
+    # prefaulted per-worker buffers: times the C loop, not np.zeros
+    _W["buf"] = [np.zeros(L) for _ in range(4)]
+
+
+def _cpu_worker_run(job):
+    xg, yg, kx, ky, st, dx, dy = job
+    x, y, bkx, bky = _W["buf"]
+    fn, ax, ay, nx, ny = _W["fn"], _W["ax"], _W["ay"], _W["nx"], _W["ny"]
+    total = 0
+    for r in range(len(xg)):
+        x[0] = xg[r]; y[0] = yg[r]; bkx[0] = kx[r]; bky[0] = ky[r]
+        total += fn(x, y, bkx, bky, st, dx, dy, nx, ny, ax, ay)
+    return total
+
+
+class CpuArm:
+    """Times the reference on a bounded sample of the workload."""
+
+    def __init__(self, case, cores=None):
+        import multiprocessing as mp
+        import oracle
+        self.kind = "reference" if oracle.have_ref() else "port"
+        if self.kind == "port":
+            oracle.port()
+        self.cores = cores or len(os.sched_getaffinity(0))
+        self.case = case
+        nf = case.nfield
+        ctx = mp.get_context("fork")
+        self.pool = ctx.Pool(self.cores, initializer=_cpu_worker_init,
+                             initargs=(nf.nx, nf.ny, np.ascontiguousarray(nf.ax), np.ascontiguousarray(nf.ay), case.L, self.kind))
+
+    def step(self, rays_per_core):
+        """One bounded sample: rays_per_core * cores rays drawn (fixed seed) from the workload."""
+        c = self.case
+        n = rays_per_core * self.cores
+        idx = np.random.default_rng(1234).choice(c.nrays, size=min(n, c.nrays), replace=False)
+        parts = np.array_split(idx, self.cores)
+        jobs = [(c.launch[0][p], c.launch[1][p], c.launch[2][p], c.launch[3][p], c.st, c.dx, c.dy) for p in parts]
+        t0 = time.perf_counter()
+        totals = self.pool.map(_cpu_worker_run, jobs, chunksize=1)
+        dt = time.perf_counter() - t0
+        return int(sum(totals)), dt, len(idx)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def calibrate_cpu(arm, budget_s):
+    """Pick rays/core so one sample takes about budget_s."""
+    steps, dt, n = arm.step(64)
+    rate = steps / dt
+    per_ray = max(steps / max(n, 1), 1.0)
+    rays = int(max(64, min(rate * budget_s / per_ray / arm.cores, arm.case.nrays // arm.cores)))
+    return rays
+
+
+# --------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+        self.t_start = None
+        self.t_stop = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [s.strip() for s in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def workload_name(args):
+    return (f"config3: {args.nrays}-ray seven-beam FT-2 fan per GPU, {args.nx}x{args.nx} shaped-density grid, "
+            f"full trajectories [ray][step][4] f64 in HBM")
+
+
+# --------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from rayrtrace_b200 import synth
+    case = synth.beam_case(nx=args.nx, nrays=args.nrays, seed=0, L=args.cap or None)
+    arm = CpuArm(case)
+    total_iters = max(args.steps + args.warmup, 1)
+    per_step_budget = min(8.0, max(0.5, 150.0 / total_iters))
+    rays = calibrate_cpu(arm, per_step_budget)
+    for _ in range(args.warmup):
+        arm.step(rays)
+    tot_steps, tot_t, n = 0, 0.0, 0
+    for _ in range(args.steps):
+        s, dt, n = arm.step(rays)
+        tot_steps += s
+        tot_t += dt
+    arm.close()
+    value = tot_steps / tot_t
+    sample = f"{n} rays/step drawn (seed 1234) from the {case.nrays}-ray workload, ~{tot_steps // max(args.steps, 1)} ray-steps/step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "nx": args.nx, "nrays_per_gpu": args.nrays, "cap_states": case.L,
+                   "note": "reference C extension (sidtracemodule.c, gcc -O2) called per ray as ray.py:80-83 does, "
+                           "one process per host core, prefaulted MaxStep buffers"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from rayrtrace_b200 import synth
+    # this rank's interleaved shard of the N*nrays global fan (interleave for balance)
+    case = synth.beam_case(nx=args.nx, nrays=args.nrays * world, seed=0, L=args.cap or None)
+    if world > 1:
+        sl = slice(rank, None, world)
+        case.launch = tuple(np.ascontiguousarray(a[sl]) for a in case.launch)
+        case.amp = case.amp[sl]
+        case.nrays = len(case.launch[0])
+
+    # CPU baseline first (forks worker processes: must happen before CUDA is initialised)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        arm = CpuArm(case)
+        rays = calibrate_cpu(arm, args.cpu_seconds / 2)
+        s1, t1, n1 = arm.step(rays)
+        s2, t2, _ = arm.step(rays)
+        arm.close()
+        s, t = (s1, t1) if s1 / t1 > s2 / t2 else (s2, t2)
+        cpu = {"value": s / t, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+               "sample": f"{n1} rays drawn (seed 1234) from the same {case.nrays}-ray workload = {s} ray-steps, best of 2, "
+                         f"one process per core calling trace() per ray with prefaulted buffers"}
+
+    import torch
+    import torch.distributed as dist
+    from rayrtrace_b200 import _cabi, sidtrace
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    nf = case.nfield
+    field = sidtrace.Field(np.ascontiguousarray(nf.ax), np.ascontiguousarray(nf.ay), nf.nx, nf.ny)
+    n, L = case.nrays, case.L
+    d_in = [torch.from_numpy(a).to(dev) for a in case.launch]
+    traj = torch.empty((n, L, 4), dtype=torch.float64, device=dev)
+    out = sidtrace.BatchResult(nsteps=torch.empty(n, dtype=torch.int32, device=dev),
+                               end_state=torch.empty((4, n), dtype=torch.float64, device=dev), traj=traj)
+    kw = dict(L=L, st=case.st, dx=case.dx, dy=case.dy)
+
+    def step():
+        sidtrace.trace_batch(field, *d_in, traj=traj, out=out, **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    steps_per_launch = int(out.nsteps.sum().item())
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = _cabi.launch_count()
+    barrier()
+    t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    for a, b in ev:
+        a.record()
+        step()
+        b.record()
+    t_all1.record()
+    barrier()
+    launches = _cabi.launch_count() - launches0
+    total_ms = t_all0.elapsed_time(t_all1)
+    kern_ms = [a.elapsed_time(b) for a, b in ev]
+    clk = clocks.stop() if rank == 0 else None
+
+    # max over ranks (device time), sum of work
+    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    work = torch.tensor([float(steps_per_launch)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    total_ms = float(tm.item())
+    global_steps_per_step = float(work.item())
+    value = global_steps_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned): H2D launch states,
+    # kernel (full trajectories into HBM, kept resident for the device-side consumers),
+    # D2H step counts + end states.
+    h_in = [torch.from_numpy(a).pin_memory().numpy() for a in case.launch]
+    h_out = sidtrace.BatchResult(nsteps=torch.empty(n, dtype=torch.int32).pin_memory().numpy(),
+                                 end_state=torch.empty((4, n), dtype=torch.float64).pin_memory().numpy(), traj=traj)
+    for _ in range(2):
+        sidtrace.trace_batch(field, *h_in, traj=traj, out=h_out, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sidtrace.trace_batch(field, *h_in, traj=traj, out=h_out, **kw)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = global_steps_per_step * args.steps / float(e2e_t.item())
+    assert int(h_out.nsteps.astype(np.int64).sum()) == steps_per_launch
+    h2d = 4 * n * 8
+    d2h = n * 4 + 4 * n * 8
+
+    extra = {}
+    if args.extra and rank == 0:
+        import ctypes
+        tf = ctypes.c_double()
+        _cabi.check(_cabi.lib.stb_measure_fp64_peak(ctypes.byref(tf)))
+        bw = ctypes.c_double()
+        _cabi.check(_cabi.lib.stb_measure_store_bw(8 << 30, ctypes.byref(bw)))
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            sidtrace.trace_batch(field, *d_in, out=sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state), **kw)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            sidtrace.trace_batch(field, *d_in, out=sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state), **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ep = steps_per_launch * args.steps / (e0.elapsed_time(e1) * 1e-3)
+        extra = {"fp64_peak_tflops_measured": tf.value, "store_bw_gbs_measured": bw.value,
+                 "endpoint_mode_ray_steps_per_s": ep,
+                 "endpoint_mode_fp64_frac": ep * FLOPS_PER_RAY_STEP / (tf.value * 1e12) if tf.value else None}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+
+    peak, peak_src = load_peaks()
+    avg_kernel_ms = float(np.mean(kern_ms))
+    achieved = BYTES_PER_RAY_STEP * steps_per_launch / (avg_kernel_ms * 1e-3) / 1e9
+    tr = load_traffic()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "nx": args.nx, "nrays_per_gpu": n, "cap_states": L,
+                   "ray_steps_per_gpu_per_step": steps_per_launch,
+                   "l2": "no explicit flush: every step streams %.1f GB of trajectory stores (>> 126 MB L2)" % (steps_per_launch * 32 / 1e9),
+                   "parallelism": f"rays interleaved over {world} rank(s), field replicated, no data-path collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": (tr or {}).get("dram_bytes_per_launch"),
+                     "kernel": "stb::trace_kernel<TRAJ=1,EXTRAS=0,HIST=0,DIVC=1,REFILL=1>",
+                     "algorithmic_bytes_per_launch": BYTES_PER_RAY_STEP * steps_per_launch,
+                     "avg_launch_ms": avg_kernel_ms, "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "host launch states in (pinned) -> kernel -> per-ray step counts + end states out; "
+                        "trajectories stay resident in HBM"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+    }
+    if extra:
+        line["extra"] = extra
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,133 @@
+"""Synthetic workloads shaped like BASELINE.json's configs (there are no public
+data sets for this path): an FT-2-like shaped density on a square grid and
+the seven-antenna Gaussian-beam fan of ft2.phases (ft2.py:12-16, 47-54) sampled
+with as many rays as asked.
+
+Everything here is host-side input generation; nothing is traced.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+from scipy import constants as const
+
+from .nfield import Nfield
+from .ray import launch_states
+
+R_DIA = 7.85      # limiter radius, cm (ft2.py:6)
+R_ANT = 10.0      # antenna radius, cm (ft2.py:7)
+BEAM_FREQ = 136.268e9   # beam.py:30
+WAIST = 0.35      # beam.py:31
+FOCUS = -1.0      # beam.py:31: the waist lies 1 cm behind the antenna
+DIST = 3.0        # beam.py:25: rays start on the wavefront 3 cm from the focus
+AMPBND = 1e-3     # beam.py:26
+
+
+def shaped_density(nx, *, ny=None, n0=4e13, edge=1e12, shift=0.6, elon=1.1, alpha=1.0, half=10.0):
+    """Parabolic profile on Shafranov-shifted, elongated flux surfaces:
+    s = rho^2 solves (x - shift*(1 - s))^2 + (y/elon)^2 = R_DIA^2 * s (closed form).
+    Returns (n[ny, nx], x, y) in cm^-3 / cm.  With shift=0, elon=1 it is the
+    parabolic FT-2 profile of SURVEY 8d config 1."""
+    ny = nx if ny is None else ny
+    x = np.linspace(-half, half, nx)
+    y = np.linspace(-half, half, ny)
+    X, Y = np.meshgrid(x, y)
+    C = (X - shift) ** 2 + (Y / elon) ** 2
+    if shift == 0:
+        s = C / R_DIA ** 2
+    else:
+        A = shift * shift
+        B = 2 * shift * (X - shift) - R_DIA ** 2          # < 0 on the whole grid
+        disc = np.maximum(B * B - 4 * A * C, 0.0)
+        s = 2 * C / (-B + np.sqrt(disc))                  # smaller root, cancellation-free
+    n = n0 * np.maximum(0.0, 1 - s) ** alpha + edge
+    return n, x, y
+
+
+def antenna_positions():
+    """The seven FT-2 antennas on the lower half of the r = 10 cm circle (ft2.py:12-16, 30-31)."""
+    xa = np.linspace(-6.9, 6.9, 7)
+    return xa, -np.sqrt(R_ANT ** 2 - xa ** 2)
+
+
+def gaussian_fan(nrays, *, freq=BEAM_FREQ, n_edge=1.0):
+    """Start points, unit normals and amplitudes of `nrays` rays spread over the seven
+    upward-pointing beams, equidistant in arc length along the (spherical) wavefront at
+    DIST from the focus -- the analytic stand-in for Beam.rays (beam.py:278-331).
+    Returns (x, y, kx, ky, amp) in lab coordinates."""
+    lam = const.speed_of_light * 100 / freq
+    y_r = np.pi * WAIST ** 2 * n_edge / lam                # beam.py:134
+    wa = WAIST * np.sqrt(1 + DIST ** 2 / y_r ** 2)         # beam.py:183
+    rc = DIST * (1 + y_r ** 2 / DIST ** 2)                 # beam.py:185 curvature radius
+    xmax = np.sqrt(-wa ** 2 * np.log(AMPBND))              # beam.py:218
+    th_max = np.arcsin(min(xmax / rc, 0.999))
+    xa, ya = antenna_positions()
+    per = np.full(7, nrays // 7)
+    per[: nrays % 7] += 1
+    xs, ys, kxs, kys, amps = [], [], [], [], []
+    for a in range(7):
+        th = np.linspace(-th_max, th_max, per[a]) if per[a] > 1 else np.zeros(per[a])
+        xb = rc * np.sin(th)
+        yb = DIST - rc + rc * np.cos(th)                   # along-axis distance from the focus
+        xs.append(xa[a] + xb)
+        ys.append(ya[a] + (yb + FOCUS))                    # beam2lab with k0 = (0, 1) (beam.py:117-131)
+        kxs.append(np.sin(th))
+        kys.append(np.cos(th))
+        amps.append(np.sqrt(WAIST / wa) * np.exp(-xb ** 2 / wa ** 2))   # beam.py:188
+    return tuple(np.concatenate(v) for v in (xs, ys, kxs, kys, amps))
+
+
+@dataclass
+class BeamCase:
+    nfield: Nfield
+    launch: tuple           # (xg0, yg0, kx0, ky0) float64 arrays, kernel units
+    amp: np.ndarray
+    x0: np.ndarray          # physical launch points
+    y0: np.ndarray
+    nrays: int
+    L: int
+    st: float
+    dx: float
+    dy: float
+    freq: float
+    name: str
+
+
+def default_cap(nx: int) -> int:
+    """States per ray for the synthetic beams: 1.5 * nx rounded up to 128.  A vacuum ray
+    crosses the grid in ~nx steps (SURVEY 3.3 i); rays that need more hit the cap exactly
+    like the reference does at Ray.MaxStep."""
+    return int(-(-(3 * nx // 2) // 128) * 128)
+
+
+def beam_case(nx=1001, nrays=1_000_000, *, seed=0, n0=4e13, shift=0.6, elon=1.1, L=None, name=None) -> BeamCase:
+    """BASELINE configs 3/5 shape: shaped density on an nx^2 grid + seven-beam fan of `nrays` rays.
+    `seed` jitters the start angle of every ray by a fraction of the ray spacing so no two
+    rays are identical."""
+    n, x, y = shaped_density(nx, n0=n0, shift=shift, elon=elon)
+    nf = Nfield(n, x=x, y=y)
+    xs, ys, kx, ky, amp = gaussian_fan(nrays)
+    rng = np.random.default_rng(seed)
+    jit = rng.uniform(-1e-4, 1e-4, nrays)
+    kx, ky = kx * np.cos(jit) - ky * np.sin(jit), kx * np.sin(jit) + ky * np.cos(jit)
+    xg, yg, kxs, kys, freq = launch_states(nf, xs, ys, kx, ky, BEAM_FREQ)
+    return BeamCase(nfield=nf, launch=(xg, yg, kxs, kys), amp=amp, x0=xs, y0=ys, nrays=nrays,
+                    L=L or default_cap(nx), st=float(nf.st), dx=float(nf.dx[0]), dy=float(nf.dy[0]), freq=freq,
+                    name=name or f"ft2-7beam-fan-{nrays}rays-{nx}x{nx}")
+
+
+def sweep_case(nx=201, nrays=100_000, *, seed=0, L=None) -> BeamCase:
+    """BASELINE config 4 shape: launch-angle / density-regime sweep with cutoff-heavy
+    trajectories: an OVER-dense core (n0 = 1.3 n_c) reflects head-on rays, grazing rays
+    skim it, and launch angles span +-0.3 rad (Beam.k0 rotation, beam.py:96-100)."""
+    n, x, y = shaped_density(nx, n0=3.0e14, shift=0.3, elon=1.05)
+    nf = Nfield(n, x=x, y=y)
+    rng = np.random.default_rng(seed)
+    xs = rng.uniform(-7.5, 7.5, nrays)
+    ys = np.full(nrays, -9.5)
+    ang = rng.uniform(-0.3, 0.3, nrays)
+    xg, yg, kxs, kys, freq = launch_states(nf, xs, ys, np.sin(ang), np.cos(ang), BEAM_FREQ)
+    return BeamCase(nfield=nf, launch=(xg, yg, kxs, kys), amp=np.ones(nrays), x0=xs, y0=ys, nrays=nrays,
+                    L=L or 4 * default_cap(nx), st=float(nf.st), dx=float(nf.dx[0]), dy=float(nf.dy[0]), freq=freq,
+                    name=f"cutoff-sweep-{nrays}rays-{nx}x{nx}")

@@ -1,0 +1,301 @@
+"""Parity of the CUDA path against the oracle, through the C ABI.
+
+Bar: BIT-EXACT on trajectories, step counts, end states, turning indices and
+the lax/ph running sums (all IEEE +, *, /, sqrt in the reference's order);
+the deposition histogram (extension) within 1e-6 relative L1, the tolerance
+BASELINE.json's north_star states (FP64 atomics make its summation order
+schedule-dependent).
+"""
+import numpy as np
+import pytest
+
+from _util import KAT_NAMES, ft2_density, random_field, random_launch, traj_digest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def st():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from rayrtrace_b200 import sidtrace
+    return sidtrace
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    return torch
+
+
+# ---------------------------------------------------------------- legacy surface
+@pytest.mark.parametrize("name", KAT_NAMES)
+def test_legacy_trace_kat_bitwise(st, kat, name):
+    L, nx, ny, stp, dx, dy, x0, y0, kx0, ky0 = kat[f"{name}_params"]
+    L, nx, ny = int(L), int(nx), int(ny)
+    x = np.zeros(L); y = np.zeros(L); kx = np.zeros(L); ky = np.zeros(L)
+    x[0], y[0], kx[0], ky[0] = x0, y0, kx0, ky0
+    ax = np.ascontiguousarray(kat[f"{name}_ax"]); ay = np.ascontiguousarray(kat[f"{name}_ay"])
+    n = st.trace(x, y, kx, ky, stp, dx, dy, nx, ny, ax, ay)
+    assert isinstance(n, int) and n == int(kat[f"{name}_n"])
+    keep = len(kat[f"{name}_x"])
+    for got, want in ((x, "x"), (y, "y"), (kx, "kx"), (ky, "ky")):
+        assert got[:keep].tobytes() == kat[f"{name}_{want}"].tobytes()
+    assert not x[n + 1:].any()          # entries beyond state n stay untouched (sidtracemodule.c:36-48)
+
+
+def test_legacy_check_and_device_layout(st):
+    a = np.arange(24.0).reshape(4, 6)
+    assert st.check(6, 4, 2, 3, a) == a[2, 3]
+    f = st.Field(a, -a, 7, 5)           # (ny-1, nx-1) = (4, 6)
+    assert f.peek(2, 3, 0) == a[2, 3] and f.peek(3, 5, 1) == -a[3, 5]
+    f.close()
+
+
+def test_reference_ray_fixture_through_product_ray(st, ft2_ray):
+    """BASELINE config 1: one ray through the FT-2 parabolic density via the
+    product's Ray (reference constructor, ray.py:15-111)."""
+    from rayrtrace_b200.nfield import Nfield
+    from rayrtrace_b200.ray import Ray
+    n, x, y = ft2_density(int(ft2_ray["nx"]), float(ft2_ray["n0"]))
+    nf = Nfield(n, x=x, y=y)
+    r = Ray(float(ft2_ray["x0"]), float(ft2_ray["y0"]), 0, 1, float(ft2_ray["freq"]), 1, n_field=nf)
+    assert len(r.x) == int(ft2_ray["nsteps"]) == 204
+    # the launch refractive index goes through SciPy's spline on both sides: 1e-12, see test_nfield
+    np.testing.assert_allclose(r.kx, ft2_ray["ray_kx"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(r.x, ft2_ray["ray_x"], rtol=1e-9)
+    np.testing.assert_allclose(r.y, ft2_ray["ray_y"], rtol=1e-9)
+    np.testing.assert_allclose(r.ph, ft2_ray["ray_ph"], rtol=1e-9)
+    assert r.st[-1] == 0 and r.st[0] == float(ft2_ray["st"])
+
+
+def test_reference_ray_fixture_exact_launch_bitwise(st, ft2_ray):
+    """Same ray fed the reference's exact launch state: the whole trajectory is bit-identical."""
+    from rayrtrace_b200.nfield import Nfield
+    n, x, y = ft2_density(int(ft2_ray["nx"]), float(ft2_ray["n0"]))
+    nf = Nfield(n, x=x, y=y)
+    L = 100000                                           # Ray.MaxStep (ray.py:11)
+    xs = [np.zeros(L) for _ in range(4)]
+    for a, v in zip(xs, ft2_ray["launch"]):
+        a[0] = v
+    i = st.trace(*xs, float(ft2_ray["st"]), float(ft2_ray["dx0"]), float(ft2_ray["dy0"]), nf.nx, nf.ny, nf.ax, nf.ay)
+    assert i == 204
+    got = np.stack([a[:i + 1] for a in xs], 1)
+    assert got.tobytes() == ft2_ray["grid_traj"].tobytes()
+
+
+# ---------------------------------------------------------------- batched surface
+def _fan_inputs(ft2_fan, tag):
+    from rayrtrace_b200.nfield import Nfield
+    n, x, y = ft2_density(int(ft2_fan[f"{tag}_nx"]), float(ft2_fan[f"{tag}_n0"]))
+    nf = Nfield(n, x=x, y=y)
+    ins = [np.ascontiguousarray(ft2_fan[f"{tag}_{k}"]) for k in ("xg0", "yg0", "kx0", "ky0")]
+    return nf, ins
+
+
+@pytest.mark.parametrize("tag", ["under", "over"])
+@pytest.mark.parametrize("div_ieee", [False, True])
+@pytest.mark.parametrize("refill", [True, False])
+@pytest.mark.parametrize("device_io", [False, True])
+def test_fan_fixture_bitwise(st, torch_mod, ft2_fan, tag, div_ieee, refill, device_io):
+    nf, ins = _fan_inputs(ft2_fan, tag)
+    L = int(ft2_fan["L"])
+    f = nf.device_field()
+    if device_io:
+        ins = [torch_mod.from_numpy(a).cuda() for a in ins]
+    res = st.trace_batch(f, *ins, L=L, st=nf.st, dx=nf.dx[0], dy=nf.dy[0], traj=True,
+                         div_ieee=div_ieee, refill=refill)
+    torch_mod.cuda.synchronize()
+    nsteps = res.nsteps.cpu().numpy() if device_io else res.nsteps
+    end = res.end_state.cpu().numpy() if device_io else res.end_state
+    traj = res.traj.cpu().numpy()
+    assert np.array_equal(nsteps, ft2_fan[f"{tag}_nsteps"])
+    assert end.tobytes() == ft2_fan[f"{tag}_end"].tobytes()
+    assert np.array_equal(traj_digest(traj, nsteps), ft2_fan[f"{tag}_traj_sha"])
+    # untouched beyond the last written state
+    for r in (0, 17, 95):
+        assert not traj[r, nsteps[r] + 1:].any()
+
+
+def _oracle_vs_gpu(st, oracle, rng, nx, ny, nrays, L, *, stp=0.37, dx=0.8, dy=1.3, st_ray=None, **kw):
+    ax, ay = random_field(rng, nx, ny)
+    x0, y0, kx0, ky0 = random_launch(rng, nrays, nx, ny)
+    if nrays >= 8:   # bad starts and edge starts
+        x0[0] = -0.5; y0[1] = np.nan; x0[2] = nx - 1.0; y0[3] = 0.0; x0[4] = np.inf; kx0[5] = np.nan
+        x0[6] = nx - 1 - 1e-12; kx0[7] = 0.0
+    want = oracle.trace_batch(x0, y0, kx0, ky0, L, stp, dx, dy, nx, ny, ax, ay, st_ray=st_ray)
+    f = st.Field(ax, ay, nx, ny)
+    res = st.trace_batch(f, x0, y0, kx0, ky0, L=L, st=stp, dx=dx, dy=dy, st_ray=st_ray, traj=True, **kw)
+    traj = res.traj.cpu().numpy()
+    assert np.array_equal(res.nsteps, want["nsteps"])
+    assert res.end_state.tobytes() == want["end"].tobytes()
+    assert traj.tobytes() == want["traj"].tobytes()
+    f.close()
+    return res, want, (ax, ay, x0, y0, kx0, ky0)
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 1, 4), (5, 3, 33, 16), (64, 80, 1000, 300), (201, 201, 4097, 700),
+                                   (33, 17, 31, 1), (33, 17, 32, 2), (1001, 777, 3000, 64)])
+@pytest.mark.parametrize("div_ieee", [False, True])
+def test_random_fields_bitwise_vs_oracle(st, oracle_mod, shape, div_ieee):
+    nx, ny, nrays, L = shape
+    rng = np.random.default_rng(nx * 1000 + nrays)
+    _oracle_vs_gpu(st, oracle_mod, rng, nx, ny, nrays, L, div_ieee=div_ieee)
+
+
+def test_empty_batch(st):
+    f = st.Field(np.zeros((3, 3)), np.zeros((3, 3)))
+    z = np.zeros(0)
+    res = st.trace_batch(f, z, z, z, z, L=8, st=0.1, dx=1, dy=1)
+    assert res.nsteps.shape == (0,) and res.end_state.shape == (4, 0)
+
+
+def test_awkward_divisors_bitwise(st, oracle_mod):
+    """dx, dy whose reciprocals are inexact / near a binade edge: the constant-divisor
+    sequence must still equal the IEEE quotient the reference computes."""
+    rng = np.random.default_rng(11)
+    for dx, dy in ((0.1, 0.3), (np.nextafter(2.0, 0), np.nextafter(1.0, 2)), (1e-3, 7.0), (20.0 / 2000, 20.0 / 1000),
+                   (3.0, 1 / 3), (2.0 ** -20, 2.0 ** 20)):
+        _oracle_vs_gpu(st, oracle_mod, rng, 40, 30, 500, 120, stp=0.21, dx=dx, dy=dy)
+    # divisors outside the guarded range fall back to div.rn.f64
+    _oracle_vs_gpu(st, oracle_mod, rng, 40, 30, 100, 50, stp=1e-300, dx=1e-290, dy=1e300)
+
+
+def test_tiny_and_huge_magnitudes_bitwise(st, oracle_mod):
+    """Subnormal / overflowing intermediates take the guarded fallback and still match."""
+    rng = np.random.default_rng(5)
+    nx, ny, n, L = 20, 20, 256, 40
+    ax, ay = random_field(rng, nx, ny, scale=1e-300)
+    x0, y0, kx0, ky0 = random_launch(rng, n, nx, ny, kmag=1e-308)
+    kx0[::3] = 0.0
+    ky0[::5] *= 1e300 * 1e308
+    for stp in (1e-3, 1.0, 1e150):
+        want = oracle_mod.trace_batch(x0, y0, kx0, ky0, L, stp, 0.7, 0.9, nx, ny, ax, ay)
+        f = st.Field(ax, ay, nx, ny)
+        res = st.trace_batch(f, x0, y0, kx0, ky0, L=L, st=stp, dx=0.7, dy=0.9, traj=True)
+        assert np.array_equal(res.nsteps, want["nsteps"])
+        assert res.traj.cpu().numpy().tobytes() == want["traj"].tobytes()
+        f.close()
+
+
+def test_per_ray_step_bitwise(st, oracle_mod):
+    """Frequency sweeps give every ray its own st (SURVEY 3.3 iii)."""
+    rng = np.random.default_rng(9)
+    st_ray = rng.uniform(0.1, 0.6, 700)
+    _oracle_vs_gpu(st, oracle_mod, rng, 64, 64, 700, 200, st_ray=st_ray)
+
+
+def test_heavy_tail_refill_equals_static(st, oracle_mod, torch_mod):
+    """A few trapped rays (closed orbits in a focusing well) run to the cap while the
+    rest leave early: the persistent refill schedule must give the same bits."""
+    nx = ny = 65
+    yy, xx = np.meshgrid(np.arange(ny - 1) + 0.5 - 32, np.arange(nx - 1) + 0.5 - 32, indexing="ij")
+    ax = np.ascontiguousarray(-0.02 * xx); ay = np.ascontiguousarray(-0.02 * yy)   # harmonic well
+    rng = np.random.default_rng(1)
+    n = 3000
+    x0, y0, kx0, ky0 = random_launch(rng, n, nx, ny, kmag=3.0)
+    kx0[::50] *= 0.05; ky0[::50] *= 0.05          # slow rays stay trapped
+    L = 6000
+    want = oracle_mod.trace_batch(x0, y0, kx0, ky0, L, 0.25, 1.0, 1.0, nx, ny, ax, ay, want_traj=False, nthreads=4)
+    assert (want["nsteps"] == L - 1).sum() > 10 and np.median(want["nsteps"]) < 200
+    f = st.Field(ax, ay, nx, ny)
+    for refill in (True, False):
+        res = st.trace_batch(f, x0, y0, kx0, ky0, L=L, st=0.25, dx=1.0, dy=1.0, refill=refill, want_extras=True)
+        assert np.array_equal(res.nsteps, want["nsteps"])
+        assert res.end_state.tobytes() == want["end"].tobytes()
+    f.close()
+
+
+# ---------------------------------------------------------------- fused reductions
+def test_extras_bitwise_vs_oracle(st, oracle_mod):
+    rng = np.random.default_rng(21)
+    nx, ny, n, L = 90, 70, 800, 400
+    res, want, _ = _oracle_vs_gpu(st, oracle_mod, rng, nx, ny, n, L, want_extras=True)
+    for r in range(n):
+        k = int(want["nsteps"][r])
+        assert int(res.turn_index[r]) == oracle_mod.turning_point(want["traj"][r], k)
+        if k >= 1:
+            lax, ph = oracle_mod.lax_ph(want["traj"][r, :k], 0.37)
+            assert float(res.lax_end[r]).hex() == float(lax[-1]).hex()
+            assert float(res.ph_end[r]).hex() == float(ph[-1]).hex()
+        else:
+            assert res.lax_end[r] == 0.0 and res.ph_end[r] == 0.0
+
+
+def test_extras_match_reference_ray_properties(st, ft2_ray):
+    """lax[-1], ph[-1] of the reference Ray (ray.py:117-126) for BASELINE config 1."""
+    from rayrtrace_b200.nfield import Nfield
+    n, x, y = ft2_density(int(ft2_ray["nx"]), float(ft2_ray["n0"]))
+    nf = Nfield(n, x=x, y=y)
+    a = [np.array([v]) for v in ft2_ray["launch"]]
+    res = st.trace_batch(nf.device_field(), *a, L=1000, st=float(ft2_ray["st"]), dx=float(ft2_ray["dx0"]),
+                         dy=float(ft2_ray["dy0"]), want_extras=True)
+    assert float(res.lax_end[0]).hex() == float(ft2_ray["ray_lax"][-1]).hex()
+    assert float(res.ph_end[0]).hex() == float(ft2_ray["ray_ph"][-1]).hex()
+
+
+def test_deposition_histogram_vs_oracle(st, oracle_mod, ft2_fan):
+    """Extension (no reference code): histogram of amp^2*dl over rho bins, oracle = the same
+    definition evaluated on reference-identical trajectories.  Tolerance 1e-6 relative L1
+    (north_star); summation order differs (warp aggregation + FP64 atomics)."""
+    nf, ins = _fan_inputs(ft2_fan, "over")
+    L = int(ft2_fan["L"])
+    nb = 48
+    rng = np.random.default_rng(2)
+    amp = rng.uniform(0.1, 1.0, len(ins[0]))
+    want_t = oracle_mod.trace_batch(*ins, L, nf.st, nf.dx[0], nf.dy[0], nf.nx, nf.ny, nf.ax, nf.ay)
+    hist = np.zeros(nb)
+    for r in range(len(amp)):
+        k = int(want_t["nsteps"][r])
+        oracle_mod.deposit(want_t["traj"][r, :k], nf.st, amp[r], nf.x[0], nf.y[0], nf.dx[0], nf.dy[0], 7.85, 1.2, nb, hist)
+    res = st.trace_batch(nf.device_field(), *ins, L=L, st=nf.st, dx=nf.dx[0], dy=nf.dy[0], nbins=nb, amp=amp,
+                         xorg=nf.x[0], yorg=nf.y[0], r_lcs=7.85, rho_max=1.2)
+    assert hist.sum() > 0
+    assert np.abs(res.hist - hist).sum() / np.abs(hist).sum() < 1e-6
+    # accumulates into a caller-provided histogram (not cleared)
+    res2 = st.trace_batch(nf.device_field(), *ins, L=L, st=nf.st, dx=nf.dx[0], dy=nf.dy[0], hist=res.hist.copy(), amp=amp,
+                          xorg=nf.x[0], yorg=nf.y[0], r_lcs=7.85, rho_max=1.2)
+    assert np.abs(res2.hist - 2 * hist).sum() / np.abs(hist).sum() < 2e-6
+
+
+# ---------------------------------------------------------------- size-independent properties at full size
+def test_full_size_invariants(st, oracle_mod, torch_mod):
+    """BASELINE config 3 shape (1001^2 grid, 10^6 rays): results are independent of the
+    schedule and of how the ray set is sharded; a 2000-ray subsample equals the oracle."""
+    from rayrtrace_b200 import synth
+    case = synth.beam_case(nx=1001, nrays=1_000_000, seed=0)
+    f = case.nfield.device_field()
+    dev = [torch_mod.from_numpy(a).cuda() for a in case.launch]
+    kw = dict(L=case.L, st=case.st, dx=case.dx, dy=case.dy)
+    a = st.trace_batch(f, *dev, **kw)
+    b = st.trace_batch(f, *dev, refill=False, div_ieee=True, **kw)
+    torch_mod.cuda.synchronize()
+    assert torch_mod.equal(a.nsteps, b.nsteps) and torch_mod.equal(a.end_state, b.end_state)
+    # shard invariance: 4 contiguous shards traced separately == one launch
+    n = case.nrays
+    for s in range(4):
+        lo, hi = s * n // 4, (s + 1) * n // 4
+        part = st.trace_batch(f, *[d[lo:hi].contiguous() for d in dev], **kw)
+        assert torch_mod.equal(part.nsteps, a.nsteps[lo:hi])
+        assert torch_mod.equal(part.end_state, a.end_state[:, lo:hi])
+    # checksum of step counts is the total work
+    total = int(a.nsteps.sum().item())
+    assert total > 500 * n
+    # oracle on a subsample
+    idx = np.random.default_rng(0).choice(n, 2000, replace=False)
+    sub = [x[idx] for x in case.launch]
+    want = oracle_mod.trace_batch(*sub, case.L, case.st, case.dx, case.dy, case.nfield.nx, case.nfield.ny,
+                                  case.nfield.ax, case.nfield.ay, want_traj=False, nthreads=4)
+    assert np.array_equal(a.nsteps.cpu().numpy()[idx], want["nsteps"])
+    assert a.end_state.cpu().numpy()[:, idx].tobytes() == want["end"].tobytes()
+
+
+def test_vacuum_step_count_property(st):
+    """Vacuum: a ray advances k0*st/dx cells per step, so n = ceil(distance / advance)."""
+    nx = ny = 257
+    f = st.Field(np.zeros((ny - 1, nx - 1)), np.zeros((ny - 1, nx - 1)))
+    x0 = np.linspace(5, 250, 4000); y0 = np.zeros(4000)
+    adv = 0.4375                              # exactly representable -> no rounding drift
+    res = st.trace_batch(f, x0, y0, np.zeros(4000), np.full(4000, adv), L=2000, st=1.0, dx=1.0, dy=1.0)
+    assert (res.nsteps == int(np.ceil((ny - 1) / adv))).all()
+    assert np.array_equal(res.end_state[0], x0) and (res.end_state[1] == adv * res.nsteps).all()
