@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
     ap.add_argument("--extra", action="store_true", help="also time endpoint-only mode and the FP64 peak")
+    ap.add_argument("--layout", default="tiled", choices=["tiled", "ray"],
+                    help="trajectory layout: tiled [tile][step][32][4] (default) or ray-major [ray][step][4]")
     return ap.parse_args()
 
 
@@ -193,7 +195,7 @@ def load_traffic():
 
 def workload_name(args):
     return (f"config3: {args.nrays}-ray seven-beam FT-2 fan per GPU, {args.nx}x{args.nx} shaped-density grid, "
-            f"full trajectories [ray][step][4] f64 in HBM")
+            f"full trajectories f64 in HBM, layout {'[tile][step][32][4]' if args.layout == 'tiled' else '[ray][step][4]'}")
 
 
 # --------------------------------------------------------------------------
@@ -271,10 +273,11 @@ def run_b200(args):
     field = sidtrace.Field(np.ascontiguousarray(nf.ax), np.ascontiguousarray(nf.ay), nf.nx, nf.ny)
     n, L = case.nrays, case.L
     d_in = [torch.from_numpy(a).to(dev) for a in case.launch]
-    traj = torch.empty((n, L, 4), dtype=torch.float64, device=dev)
+    tiled = args.layout == "tiled"
+    traj = torch.empty(((n + 31) // 32, L, 32, 4) if tiled else (n, L, 4), dtype=torch.float64, device=dev)
     out = sidtrace.BatchResult(nsteps=torch.empty(n, dtype=torch.int32, device=dev),
                                end_state=torch.empty((4, n), dtype=torch.float64, device=dev), traj=traj)
-    kw = dict(L=L, st=case.st, dx=case.dx, dy=case.dy)
+    kw = dict(L=L, st=case.st, dx=case.dx, dy=case.dy, tiled=tiled)
 
     def step():
         sidtrace.trace_batch(field, *d_in, traj=traj, out=out, **kw)
@@ -349,12 +352,13 @@ def run_b200(args):
         bw = ctypes.c_double()
         _cabi.check(_cabi.lib.stb_measure_store_bw(8 << 30, ctypes.byref(bw)))
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        kw0 = dict(kw, tiled=False)
         for _ in range(3):
-            sidtrace.trace_batch(field, *d_in, out=sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state), **kw)
+            sidtrace.trace_batch(field, *d_in, out=sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state), **kw0)
         torch.cuda.synchronize()
         e0.record()
         for _ in range(args.steps):
-            sidtrace.trace_batch(field, *d_in, out=sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state), **kw)
+            sidtrace.trace_batch(field, *d_in, out=sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state), **kw0)
         e1.record()
         torch.cuda.synchronize()
         ep = steps_per_launch * args.steps / (e0.elapsed_time(e1) * 1e-3)
@@ -382,7 +386,7 @@ def run_b200(args):
                    "parallelism": f"rays interleaved over {world} rank(s), field replicated, no data-path collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (tr or {}).get("dram_bytes_per_launch"),
-                     "kernel": "stb::trace_kernel<TRAJ=1,EXTRAS=0,HIST=0,DIVC=1,REFILL=1>",
+                     "kernel": "stb::trace_kernel<TRAJ=1,EXTRAS=0,HIST=0,DIVC=1,REFILL=1,TILED=%d>" % int(tiled),
                      "algorithmic_bytes_per_launch": BYTES_PER_RAY_STEP * steps_per_launch,
                      "avg_launch_ms": avg_kernel_ms, "peak_source": peak_src},
         "cpu_baseline": cpu,

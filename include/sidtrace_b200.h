@@ -81,6 +81,9 @@ int stb_check(int nx, int ny, int i, int j, const double *a, double *out);
 #define STB_F_NO_REFILL    (1u << 2)  /* static one-thread-per-ray grid instead of the persistent
                                          warp-refill scheduler */
 #define STB_F_TRAJ_HOST    (1u << 3)  /* traj is a HOST pointer (copied back after the launch) */
+#define STB_F_TRAJ_TILED   (1u << 4)  /* traj layout [tile][step][32][4]: tile = ray/32, lane = ray%32;
+                                         ceil(nrays/32)*L*128 doubles; every warp-step is one coalesced
+                                         1 KB row (the HBM-friendly layout); traj_ray_stride is ignored */
 
 typedef struct stb_batch_s {
     size_t   struct_size;     /* = sizeof(stb_batch_t); ABI evolution guard                     */

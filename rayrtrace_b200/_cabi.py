@@ -20,6 +20,7 @@ F_HOST_IO = 1 << 0
 F_DIV_IEEE = 1 << 1
 F_NO_REFILL = 1 << 2
 F_TRAJ_HOST = 1 << 3
+F_TRAJ_TILED = 1 << 4
 
 # every symbol include/sidtrace_b200.h declares (tests check the .so exports them all)
 EXPORTS = (

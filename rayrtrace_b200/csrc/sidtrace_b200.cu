@@ -203,14 +203,14 @@ namespace {
 
 using stb::KParams;
 
-template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC>
+template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool TILED = false>
 int launch_variant(const KParams &p, bool refill, int num_sms, cudaStream_t s)
 {
     const size_t smem = HIST ? (size_t)p.nbins * sizeof(double) : 0;
     if (p.nrays <= 0) return STB_OK;
     long long blocks_all = (p.nrays + stb::kBlock - 1) / stb::kBlock;
     if (refill) {
-        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, true>;
+        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, true, TILED>;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, stb::kBlock, smem));
@@ -220,7 +220,7 @@ int launch_variant(const KParams &p, bool refill, int num_sms, cudaStream_t s)
         CU(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), s));
         kern<<<(unsigned)blocks, stb::kBlock, smem, s>>>(p);
     } else {
-        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, false>;
+        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, false, TILED>;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (blocks_all > 0x7fffffffLL) return fail(STB_ERR_ARG, "too many rays for a static grid");
         kern<<<(unsigned)blocks_all, stb::kBlock, smem, s>>>(p);
@@ -237,8 +237,18 @@ int launch_div(const KParams &p, bool divc, bool refill, int num_sms, cudaStream
                 : launch_variant<TRAJ, EXTRAS, HIST, false>(p, refill, num_sms, s);
 }
 
-int launch_trace(const KParams &p, bool divc, bool refill, int num_sms, cudaStream_t s)
+int launch_trace(const KParams &p, bool divc, bool refill, bool tiled, int num_sms, cudaStream_t s)
 {
+    if (tiled && p.traj) {
+        // tiled layout: plain trajectories (+ fused running sums); the histogram keeps the ray-major kernels
+        const bool extras = p.turn || p.lax_end || p.ph_end;
+        if (p.hist) return fail(STB_ERR_ARG, "STB_F_TRAJ_TILED cannot be combined with the histogram output");
+        if (extras)
+            return divc ? launch_variant<true, true, false, true, true>(p, refill, num_sms, s)
+                        : launch_variant<true, true, false, false, true>(p, refill, num_sms, s);
+        return divc ? launch_variant<true, false, false, true, true>(p, refill, num_sms, s)
+                    : launch_variant<true, false, false, false, true>(p, refill, num_sms, s);
+    }
     const bool traj = p.traj != nullptr;
     const bool extras = p.turn || p.lax_end || p.ph_end;
     const bool hist = p.hist != nullptr;
@@ -311,11 +321,13 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
     const bool refill = !(b->flags & STB_F_NO_REFILL);
     const bool host_io = b->flags & STB_F_HOST_IO;
     const bool traj_host = b->flags & STB_F_TRAJ_HOST;
+    const bool tiled = b->flags & STB_F_TRAJ_TILED;
+    if (tiled && traj_host) return fail(STB_ERR_ARG, "STB_F_TRAJ_TILED and STB_F_TRAJ_HOST are mutually exclusive");
 
     if (!host_io && !traj_host) {
         // the counter is per field: serialise launches that share it on different streams
         std::lock_guard<std::mutex> lk(f->mu);
-        return launch_trace(p, divc, refill, f->num_sms, s);
+        return launch_trace(p, divc, refill, tiled, f->num_sms, s);
     }
 
     std::lock_guard<std::mutex> lk(f->mu);
@@ -365,7 +377,7 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
         p.traj = (double *)f->ws_traj.p;
     }
 
-    rc = launch_trace(p, divc, refill, f->num_sms, s);
+    rc = launch_trace(p, divc, refill, tiled, f->num_sms, s);
     if (rc != STB_OK) return rc;
 
     if (host_io && n) {
@@ -414,7 +426,7 @@ int stb_trace(stb_field_t f, double *x, double *y, double *kx, double *ky, int64
     bool divc = false;
     rc = fill_params(f, &b, p, divc);
     if (rc != STB_OK) return rc;
-    rc = launch_trace(p, divc, /*refill=*/false, f->num_sms, 0);
+    rc = launch_trace(p, divc, /*refill=*/false, /*tiled=*/false, f->num_sms, 0);
     if (rc != STB_OK) return rc;
     int32_t n = 0;
     CU(cudaMemcpy(&n, b.nsteps, sizeof(n), cudaMemcpyDeviceToHost));

@@ -102,7 +102,12 @@ __device__ __forceinline__ void hist_add(double *sh, int b, double w)
     if (lane == leader && b >= 0) atomicAdd(&sh[b], sum);
 }
 
-template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool REFILL>
+// TILED (trajectory layout [tile][step][32 rays][4]): a warp owns one tile of 32
+// consecutive rays; its lanes step in lock-step, so every step is ONE fully coalesced
+// 1 KB row store and consecutive steps are consecutive rows -- sequential DRAM pages
+// instead of 32 scattered sectors.  Rays are then claimed a whole tile at a time
+// (the lane-granular refill would scatter a new ray's rows).
+template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool REFILL, bool TILED = false>
 __global__ void __launch_bounds__(kBlock)
 trace_kernel(const KParams p)
 {
@@ -134,7 +139,8 @@ trace_kernel(const KParams p)
         if (p.st_ray) { st = p.st_ray[r]; sst = __dmul_rn(st, st); }
         i = 0;
         if (TRAJ) {
-            tp = p.traj + r * p.stride;
+            tp = TILED ? p.traj + ((r >> 5) * (long long)p.L * 32 + (r & 31)) * 4
+                       : p.traj + r * p.stride;
             st_state(tp, x, y, kx, ky);
         }
         if (EXTRAS) { turn = -1; lax = 0; ph = 0; }
@@ -150,7 +156,7 @@ trace_kernel(const KParams p)
 
     for (;;) {
         unsigned act = __ballot_sync(FULL, active);
-        if (REFILL && more && act != FULL) {
+        if (REFILL && more && (TILED ? act == 0 : act != FULL)) {
             const unsigned idle = ~act;
             const int leader = __ffs(idle) - 1;
             const int want = __popc(idle);
@@ -217,7 +223,7 @@ trace_kernel(const KParams p)
                 x = x1; y = y1; kx = kx1; ky = ky1;
                 ++i;
                 if (TRAJ) {
-                    tp += 4;
+                    tp += TILED ? 128 : 4;
                     st_state(tp, x, y, kx, ky);
                 }
             } else {

@@ -27,7 +27,7 @@ from typing import Optional
 import numpy as np
 
 from . import _cabi
-from ._cabi import (F_DIV_IEEE, F_HOST_IO, F_NO_REFILL, F_TRAJ_HOST, SidtraceError, StbBatch, lib)
+from ._cabi import (F_DIV_IEEE, F_HOST_IO, F_NO_REFILL, F_TRAJ_HOST, F_TRAJ_TILED, SidtraceError, StbBatch, lib)
 
 __all__ = ["trace", "check", "trace_batch", "Field", "BatchResult", "invalidate", "SidtraceError"]
 
@@ -217,13 +217,29 @@ class BatchResult:
     lax_end: object = None      # float64 [nrays]
     ph_end: object = None       # float64 [nrays]
     hist: object = None         # float64 [nbins]
+    tiled: bool = False         # traj is [ntiles, L, 32, 4] (tile = ray // 32, lane = ray % 32)
+
+    def ray_states(self, r: int, n: Optional[int] = None):
+        """View [n, 4] of the first n states (default nsteps[r], the part the reference's
+        Ray keeps, ray.py:99-102) of ray r, whatever the layout -- no copy."""
+        if n is None:
+            n = int(self.nsteps[r])
+        if self.tiled:
+            return self.traj[r >> 5, :n, r & 31, :]
+        return self.traj[r, :n]
 
     def ray(self, r: int):
-        """Kept part of ray r as the reference's Ray holds it (ray.py:99-102):
-        four views x, y, kx, ky of length nsteps[r] (grid units)."""
-        n = int(self.nsteps[r])
-        t = self.traj[r, :n]
+        """Four views x, y, kx, ky of the kept part of ray r (grid units)."""
+        t = self.ray_states(r)
         return t[:, 0], t[:, 1], t[:, 2], t[:, 3]
+
+    def traj_ray_major(self):
+        """The trajectories as a [nrays, L, 4] tensor (a copy when the layout is tiled)."""
+        if not self.tiled:
+            return self.traj
+        nt, L = self.traj.shape[0], self.traj.shape[1]
+        n = int(self.nsteps.shape[0])
+        return self.traj.permute(0, 2, 1, 3).reshape(nt * 32, L, 4)[:n]
 
 
 def _ptr(a):
@@ -238,8 +254,8 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
                 st_ray=None, traj=None, want_end: bool = True, want_extras: bool = False,
                 hist=None, nbins: int = 0, amp=None, xorg: float = 0.0, yorg: float = 0.0,
                 r_lcs: float = 1.0, rho_max: float = 1.0, traj_host: bool = False,
-                div_ieee: bool = False, refill: bool = True, out: Optional[BatchResult] = None,
-                stream=None) -> BatchResult:
+                div_ieee: bool = False, refill: bool = True, tiled: bool = False,
+                out: Optional[BatchResult] = None, stream=None) -> BatchResult:
     """Trace ``len(x0)`` rays in one launch.
 
     x0, y0, kx0, ky0: launch states (grid units / cm^-1, ray.py:62-68), all numpy
@@ -250,6 +266,9 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     traj: None -> no trajectories; True -> allocate a zeroed [nrays, L, 4] CUDA
     tensor; or a preallocated CUDA tensor of that shape (32-byte aligned).
     With ``traj_host=True`` and host I/O, a numpy [nrays, L, 4] array.
+    tiled: trajectory layout [ceil(nrays/32), L, 32, 4] instead of [nrays, L, 4]: every
+    warp-step becomes one coalesced 1 KB row store (the fast layout; read rays back
+    with ``BatchResult.ray_states``).
     """
     torch = _torch()
     dev_io = _is_tensor(x0)
@@ -300,22 +319,28 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     if not refill:
         flags |= F_NO_REFILL
 
+    tshape = ((n + 31) // 32, L, 32, 4) if tiled else (n, L, 4)
+    if tiled:
+        flags |= F_TRAJ_TILED
+        if traj_host:
+            raise ValueError("tiled trajectories live in HBM: traj_host is not supported with tiled=True")
     if traj is True:
         if traj_host and not dev_io:
             traj = np.zeros((n, L, 4), np.float64)
         else:
-            traj = torch.zeros((n, L, 4), dtype=torch.float64, device=device)
+            traj = torch.zeros(tshape, dtype=torch.float64, device=device)
     if traj is not None:
         if _is_tensor(traj):
             if traj.dtype != torch.float64 or not traj.is_cuda or not traj.is_contiguous() \
-                    or tuple(traj.shape) != (n, L, 4):
-                raise TypeError(f"traj must be a contiguous float64 CUDA tensor of shape ({n}, {L}, 4)")
+                    or tuple(traj.shape) != tshape:
+                raise TypeError(f"traj must be a contiguous float64 CUDA tensor of shape {tshape}")
         else:
             _f64_host(traj, "traj", 3)
             if traj.shape != (n, L, 4):
                 raise ValueError(f"traj must have shape ({n}, {L}, 4)")
             flags |= F_TRAJ_HOST
         res.traj = traj
+        res.tiled = bool(tiled)
 
     if hist is None and nbins:
         hist = torch.zeros(nbins, dtype=torch.float64, device=device) if dev_io else np.zeros(nbins)

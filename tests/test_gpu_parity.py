@@ -97,18 +97,20 @@ def _fan_inputs(ft2_fan, tag):
 @pytest.mark.parametrize("div_ieee", [False, True])
 @pytest.mark.parametrize("refill", [True, False])
 @pytest.mark.parametrize("device_io", [False, True])
-def test_fan_fixture_bitwise(st, torch_mod, ft2_fan, tag, div_ieee, refill, device_io):
+@pytest.mark.parametrize("tiled", [False, True])
+def test_fan_fixture_bitwise(st, torch_mod, ft2_fan, tag, div_ieee, refill, device_io, tiled):
     nf, ins = _fan_inputs(ft2_fan, tag)
     L = int(ft2_fan["L"])
     f = nf.device_field()
     if device_io:
         ins = [torch_mod.from_numpy(a).cuda() for a in ins]
     res = st.trace_batch(f, *ins, L=L, st=nf.st, dx=nf.dx[0], dy=nf.dy[0], traj=True,
-                         div_ieee=div_ieee, refill=refill)
+                         div_ieee=div_ieee, refill=refill, tiled=tiled)
     torch_mod.cuda.synchronize()
     nsteps = res.nsteps.cpu().numpy() if device_io else res.nsteps
     end = res.end_state.cpu().numpy() if device_io else res.end_state
-    traj = res.traj.cpu().numpy()
+    traj = res.traj_ray_major().cpu().numpy()
+    assert res.ray_states(17).cpu().numpy().tobytes() == traj[17, :nsteps[17]].tobytes()
     assert np.array_equal(nsteps, ft2_fan[f"{tag}_nsteps"])
     assert end.tobytes() == ft2_fan[f"{tag}_end"].tobytes()
     assert np.array_equal(traj_digest(traj, nsteps), ft2_fan[f"{tag}_traj_sha"])
@@ -126,7 +128,7 @@ def _oracle_vs_gpu(st, oracle, rng, nx, ny, nrays, L, *, stp=0.37, dx=0.8, dy=1.
     want = oracle.trace_batch(x0, y0, kx0, ky0, L, stp, dx, dy, nx, ny, ax, ay, st_ray=st_ray)
     f = st.Field(ax, ay, nx, ny)
     res = st.trace_batch(f, x0, y0, kx0, ky0, L=L, st=stp, dx=dx, dy=dy, st_ray=st_ray, traj=True, **kw)
-    traj = res.traj.cpu().numpy()
+    traj = res.traj_ray_major().cpu().numpy()
     assert np.array_equal(res.nsteps, want["nsteps"])
     assert res.end_state.tobytes() == want["end"].tobytes()
     assert traj.tobytes() == want["traj"].tobytes()
@@ -137,10 +139,12 @@ def _oracle_vs_gpu(st, oracle, rng, nx, ny, nrays, L, *, stp=0.37, dx=0.8, dy=1.
 @pytest.mark.parametrize("shape", [(2, 2, 1, 4), (5, 3, 33, 16), (64, 80, 1000, 300), (201, 201, 4097, 700),
                                    (33, 17, 31, 1), (33, 17, 32, 2), (1001, 777, 3000, 64)])
 @pytest.mark.parametrize("div_ieee", [False, True])
-def test_random_fields_bitwise_vs_oracle(st, oracle_mod, shape, div_ieee):
+@pytest.mark.parametrize("tiled", [False, True])
+def test_random_fields_bitwise_vs_oracle(st, oracle_mod, shape, div_ieee, tiled):
     nx, ny, nrays, L = shape
     rng = np.random.default_rng(nx * 1000 + nrays)
-    _oracle_vs_gpu(st, oracle_mod, rng, nx, ny, nrays, L, div_ieee=div_ieee)
+    _oracle_vs_gpu(st, oracle_mod, rng, nx, ny, nrays, L, div_ieee=div_ieee, tiled=tiled)
+    _oracle_vs_gpu(st, oracle_mod, rng, nx, ny, nrays, L, div_ieee=div_ieee, tiled=tiled, refill=False)
 
 
 def test_empty_batch(st):
@@ -183,6 +187,7 @@ def test_per_ray_step_bitwise(st, oracle_mod):
     rng = np.random.default_rng(9)
     st_ray = rng.uniform(0.1, 0.6, 700)
     _oracle_vs_gpu(st, oracle_mod, rng, 64, 64, 700, 200, st_ray=st_ray)
+    _oracle_vs_gpu(st, oracle_mod, rng, 64, 64, 700, 200, st_ray=st_ray, tiled=True)
 
 
 def test_heavy_tail_refill_equals_static(st, oracle_mod, torch_mod):
@@ -195,14 +200,18 @@ def test_heavy_tail_refill_equals_static(st, oracle_mod, torch_mod):
     n = 3000
     x0, y0, kx0, ky0 = random_launch(rng, n, nx, ny, kmag=3.0)
     kx0[::50] *= 0.05; ky0[::50] *= 0.05          # slow rays stay trapped
-    L = 6000
-    want = oracle_mod.trace_batch(x0, y0, kx0, ky0, L, 0.25, 1.0, 1.0, nx, ny, ax, ay, want_traj=False, nthreads=4)
-    assert (want["nsteps"] == L - 1).sum() > 10 and np.median(want["nsteps"]) < 200
+    L = 2500
+    want = oracle_mod.trace_batch(x0, y0, kx0, ky0, L, 0.25, 1.0, 1.0, nx, ny, ax, ay, want_traj=True, nthreads=4)
+    assert (want["nsteps"] == L - 1).sum() > 50 and np.median(want["nsteps"]) < L / 4 and want["nsteps"].min() == 0
     f = st.Field(ax, ay, nx, ny)
     for refill in (True, False):
         res = st.trace_batch(f, x0, y0, kx0, ky0, L=L, st=0.25, dx=1.0, dy=1.0, refill=refill, want_extras=True)
         assert np.array_equal(res.nsteps, want["nsteps"])
         assert res.end_state.tobytes() == want["end"].tobytes()
+        for tiled in (False, True):
+            res = st.trace_batch(f, x0, y0, kx0, ky0, L=L, st=0.25, dx=1.0, dy=1.0, refill=refill, traj=True, tiled=tiled)
+            assert np.array_equal(res.nsteps, want["nsteps"])
+            assert res.traj_ray_major().cpu().numpy().tobytes() == want["traj"].tobytes()
     f.close()
 
 

@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Times the trace kernel variants on one GPU (CUDA events, device-resident inputs).
+
+    python tools/kernel_sweep.py [--nrays 1000000] [--nx 1001] [--reps 5]
+
+One line per variant: layout x schedule x division x output mode, with ray-steps/s and the
+HBM-roofline fraction (32 B per ray-step over MEASURED_PEAKS.json's copy bandwidth)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rayrtrace_b200 import sidtrace, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nrays", type=int, default=1_000_000)
+    ap.add_argument("--nx", type=int, default=1001)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--case", default="beam", choices=["beam", "sweep"])
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    peak = 6533.5
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak = float(json.load(open(p))["hbm_gbs"])
+    case = synth.beam_case(nx=args.nx, nrays=args.nrays) if args.case == "beam" else synth.sweep_case(nx=args.nx, nrays=args.nrays)
+    dev = torch.device("cuda", 0)
+    nf = case.nfield
+    field = sidtrace.Field(np.ascontiguousarray(nf.ax), np.ascontiguousarray(nf.ay), nf.nx, nf.ny)
+    d_in = [torch.from_numpy(a).to(dev) for a in case.launch]
+    n, L = case.nrays, case.L
+    nt = (n + 31) // 32
+    buf = torch.empty(nt * 32 * L * 4, dtype=torch.float64, device=dev)
+    kw = dict(L=L, st=case.st, dx=case.dx, dy=case.dy)
+    out = sidtrace.BatchResult(nsteps=torch.empty(n, dtype=torch.int32, device=dev),
+                               end_state=torch.empty((4, n), dtype=torch.float64, device=dev))
+    variants = []
+    for mode in ("traj-tiled", "traj-ray", "endpoints", "extras"):
+        for refill in (True, False):
+            for div_ieee in (False, True):
+                variants.append((mode, refill, div_ieee))
+    print(f"# case {case.name} L={L} peak={peak} GB/s")
+    for mode, refill, div_ieee in variants:
+        tag = f"{mode}/{'refill' if refill else 'static'}/{'ieee' if div_ieee else 'divc'}"
+        if args.only and args.only not in tag:
+            continue
+        o = sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state)
+        k = dict(kw, refill=refill, div_ieee=div_ieee)
+        if mode == "traj-tiled":
+            k.update(traj=buf[: nt * L * 128].view(nt, L, 32, 4), tiled=True)
+        elif mode == "traj-ray":
+            k.update(traj=buf[: n * L * 4].view(n, L, 4))
+        elif mode == "extras":
+            k.update(want_extras=True)
+        for _ in range(2):
+            sidtrace.trace_batch(field, *d_in, out=o, **k)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(args.reps):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sidtrace.trace_batch(field, *d_in, out=o, **k)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        steps = int(o.nsteps.sum().item())
+        ms = float(np.median(ts))
+        rate = steps / (ms * 1e-3)
+        frac = rate * 32 / 1e9 / peak
+        print(f"{tag:32s} {ms:9.3f} ms  {rate:11.4e} ray-steps/s  {rate * 32 / 1e9:8.1f} GB/s-equiv  frac {frac:5.3f}  (min {min(ts):.3f} ms)", flush=True)
+
+
+if __name__ == "__main__":
+    main()
