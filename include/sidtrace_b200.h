@@ -81,9 +81,12 @@ int stb_check(int nx, int ny, int i, int j, const double *a, double *out);
 #define STB_F_NO_REFILL    (1u << 2)  /* static one-thread-per-ray grid instead of the persistent
                                          warp-refill scheduler */
 #define STB_F_TRAJ_HOST    (1u << 3)  /* traj is a HOST pointer (copied back after the launch) */
-#define STB_F_TRAJ_TILED   (1u << 4)  /* traj layout [tile][step][32][4]: tile = ray/32, lane = ray%32;
-                                         ceil(nrays/32)*L*128 doubles; every warp-step is one coalesced
-                                         1 KB row (the HBM-friendly layout); traj_ray_stride is ignored */
+#define STB_F_TRAJ_TILED   (1u << 4)  /* warp-tile schedule: a warp owns tile = ray/32 (lane = ray%32) until all
+                                         32 rays ended.  traj (if any) is laid out [tile][step][32][4],
+                                         ceil(nrays/32)*L*128 doubles: every warp-step is one coalesced 1 KB
+                                         row (the HBM-friendly layout; traj_ray_stride is ignored).  Per-ray
+                                         results leave as coalesced rows too, so with STB_F_HOST_IO and PINNED
+                                         host buffers the kernel reads/writes them in place (zero-copy) */
 
 typedef struct stb_batch_s {
     size_t   struct_size;     /* = sizeof(stb_batch_t); ABI evolution guard                     */

@@ -239,15 +239,22 @@ int launch_div(const KParams &p, bool divc, bool refill, int num_sms, cudaStream
 
 int launch_trace(const KParams &p, bool divc, bool refill, bool tiled, int num_sms, cudaStream_t s)
 {
-    if (tiled && p.traj) {
-        // tiled layout: plain trajectories (+ fused running sums); the histogram keeps the ray-major kernels
+    if (tiled) {
+        // warp-tile schedule: plain trajectories and/or fused running sums; the histogram keeps
+        // the ray-granular kernels
         const bool extras = p.turn || p.lax_end || p.ph_end;
         if (p.hist) return fail(STB_ERR_ARG, "STB_F_TRAJ_TILED cannot be combined with the histogram output");
-        if (extras)
-            return divc ? launch_variant<true, true, false, true, true>(p, refill, num_sms, s)
-                        : launch_variant<true, true, false, false, true>(p, refill, num_sms, s);
-        return divc ? launch_variant<true, false, false, true, true>(p, refill, num_sms, s)
-                    : launch_variant<true, false, false, false, true>(p, refill, num_sms, s);
+        const int key = (p.traj ? 4 : 0) | (extras ? 2 : 0) | (divc ? 1 : 0);
+        switch (key) {
+            case 0: return launch_variant<false, false, false, false, true>(p, refill, num_sms, s);
+            case 1: return launch_variant<false, false, false, true, true>(p, refill, num_sms, s);
+            case 2: return launch_variant<false, true, false, false, true>(p, refill, num_sms, s);
+            case 3: return launch_variant<false, true, false, true, true>(p, refill, num_sms, s);
+            case 4: return launch_variant<true, false, false, false, true>(p, refill, num_sms, s);
+            case 5: return launch_variant<true, false, false, true, true>(p, refill, num_sms, s);
+            case 6: return launch_variant<true, true, false, false, true>(p, refill, num_sms, s);
+            default: return launch_variant<true, true, false, true, true>(p, refill, num_sms, s);
+        }
     }
     const bool traj = p.traj != nullptr;
     const bool extras = p.turn || p.lax_end || p.ph_end;
@@ -263,6 +270,17 @@ int launch_trace(const KParams &p, bool divc, bool refill, bool tiled, int num_s
         case 6: return launch_div<true, true, false>(p, divc, refill, num_sms, s);
         default: return launch_div<true, true, true>(p, divc, refill, num_sms, s);
     }
+}
+
+// Device alias of a pinned (page-locked, mapped) host pointer, or nullptr when the memory is
+// pageable / unknown to CUDA.  With unified addressing the alias equals the host pointer.
+void *mapped_alias(const void *host)
+{
+    if (!host) return nullptr;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost) return nullptr;
+    return a.devicePointer;
 }
 
 // the constant-divisor sequence is exact only while nothing under/overflows
@@ -334,6 +352,33 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
     const size_t n = (size_t)b->nrays;
     const size_t nb = n * sizeof(double);
     const bool extras = b->turn_index || b->lax_end || b->ph_end;
+
+    // ---- zero-copy host I/O -------------------------------------------------------------
+    // With the warp-tile schedule every launch-state read and every per-ray result write is a
+    // coalesced 128-256 B row, so when the caller's buffers are pinned the kernel reads and
+    // writes them in place over PCIe, overlapped with the tracing itself: no staging copies,
+    // no serial H2D -> kernel -> D2H chain.  Pageable buffers take the staged path below.
+    if (host_io && tiled && !traj_host && !b->hist && n) {
+        const void *hp[11] = {b->x0, b->y0, b->kx0, b->ky0, b->st_ray, b->amp,
+                              b->nsteps, b->end_state, b->turn_index, b->lax_end, b->ph_end};
+        void *dp[11];
+        bool all = true;
+        for (int k = 0; k < 11; ++k) {
+            dp[k] = mapped_alias(hp[k]);
+            if (hp[k] && !dp[k]) all = false;
+        }
+        if (all) {
+            p.x0 = (const double *)dp[0]; p.y0 = (const double *)dp[1];
+            p.kx0 = (const double *)dp[2]; p.ky0 = (const double *)dp[3];
+            p.st_ray = (const double *)dp[4]; p.amp = (const double *)dp[5];
+            p.nsteps = (int *)dp[6]; p.endst = (double *)dp[7];
+            p.turn = (int *)dp[8]; p.lax_end = (double *)dp[9]; p.ph_end = (double *)dp[10];
+            rc = launch_trace(p, divc, refill, tiled, f->num_sms, s);
+            if (rc != STB_OK) return rc;
+            CU(cudaStreamSynchronize(s));
+            return STB_OK;
+        }
+    }
 
     if (host_io) {
         // ---- inputs: [x0 | y0 | kx0 | ky0 | st_ray? | amp?] ----

@@ -148,6 +148,26 @@ trace_kernel(const KParams p)
         active = true;
     };
 
+    // per-ray results: state i is the first out-of-domain state or the cap (sidtracemodule.c:50).
+    // Ray-granular schedules retire a ray the moment it ends; the TILED schedule retires the
+    // whole tile at once, so nsteps / end states leave the warp as coalesced 128 B / 256 B rows
+    // (which is what makes writing them straight into mapped host memory cheap).
+    auto retire = [&]() {
+        if (p.nsteps) p.nsteps[ray] = i;
+        if (p.endst) {
+            p.endst[0 * p.nrays + ray] = x;
+            p.endst[1 * p.nrays + ray] = y;
+            p.endst[2 * p.nrays + ray] = kx;
+            p.endst[3 * p.nrays + ray] = ky;
+        }
+        if (EXTRAS) {
+            if (p.turn) p.turn[ray] = turn;
+            if (p.lax_end) p.lax_end[ray] = lax;
+            if (p.ph_end) p.ph_end[ray] = ph;
+        }
+        ray = -1;
+    };
+
     bool more = REFILL;   // warp-uniform: the queue may still hold rays
     if (!REFILL) {
         const long long r = (long long)blockIdx.x * kBlock + threadIdx.x;
@@ -156,6 +176,7 @@ trace_kernel(const KParams p)
 
     for (;;) {
         unsigned act = __ballot_sync(FULL, active);
+        if (TILED && act == 0 && ray >= 0) retire();
         if (REFILL && more && (TILED ? act == 0 : act != FULL)) {
             const unsigned idle = ~act;
             const int leader = __ffs(idle) - 1;
@@ -227,19 +248,7 @@ trace_kernel(const KParams p)
                     st_state(tp, x, y, kx, ky);
                 }
             } else {
-                // retire: state i is the first out-of-domain state or the cap (sidtracemodule.c:50)
-                if (p.nsteps) p.nsteps[ray] = i;
-                if (p.endst) {
-                    p.endst[0 * p.nrays + ray] = x;
-                    p.endst[1 * p.nrays + ray] = y;
-                    p.endst[2 * p.nrays + ray] = kx;
-                    p.endst[3 * p.nrays + ray] = ky;
-                }
-                if (EXTRAS) {
-                    if (p.turn) p.turn[ray] = turn;
-                    if (p.lax_end) p.lax_end[ray] = lax;
-                    if (p.ph_end) p.ph_end[ray] = ph;
-                }
+                if (!TILED) retire();
                 active = false;
             }
         }

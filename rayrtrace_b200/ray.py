@@ -142,8 +142,8 @@ class RayBundle:
         if self.result is None or self.result.traj is None:
             raise RuntimeError("trace_rays(..., keep_traj=False) kept no trajectories")
         n = int(self.nsteps[r])
-        t = self.result.traj[r, :n].cpu().numpy() if hasattr(self.result.traj, "cpu") \
-            else np.asarray(self.result.traj[r, :n])
+        t = self.result.ray_states(r, n)
+        t = t.cpu().numpy() if hasattr(t, "cpu") else np.ascontiguousarray(t)
         out = Ray.__new__(Ray)
         out.len_unit = "cm"
         out.freq = self.freq
@@ -158,6 +158,19 @@ class RayBundle:
         if n:
             out.st[-1] = 0
         return out
+
+
+def _device_field(n_field):
+    """HBM-resident field of an Nfield-like object: this repo's Nfield has device_field();
+    the reference's own den.Nfield (duck-typed: ax, ay, nx, ny) gets one attached."""
+    if hasattr(n_field, "device_field"):
+        return n_field.device_field()
+    f = getattr(n_field, "_stb_device_field", None)
+    if f is None:
+        f = _st.Field(np.ascontiguousarray(n_field.ax, np.float64), np.ascontiguousarray(n_field.ay, np.float64),
+                      n_field.nx, n_field.ny)
+        n_field._stb_device_field = f
+    return f
 
 
 def launch_states(n_field, x0, y0, kx0, ky0, freq):
@@ -179,7 +192,7 @@ def launch_states(n_field, x0, y0, kx0, ky0, freq):
     den = n_field.n_interpolant_points(x0, y0) if hasattr(n_field, "n_interpolant_points") else \
         np.array([np.asarray(n_field.n_interpolant(a, b)).reshape(-1)[0] for a, b in zip(x0, y0)])
     from .nfield import critical_den
-    refr = np.sqrt(1 - den / critical_den(freq, den_unit=n_field.den_unit))
+    refr = np.sqrt(1 - den / critical_den(freq, den_unit=getattr(n_field, "den_unit", "cm^-3")))
     kx = kx * refr
     ky = ky * refr
     xg = np.ascontiguousarray(n_field.x2grid(x0), np.float64)
@@ -188,7 +201,7 @@ def launch_states(n_field, x0, y0, kx0, ky0, freq):
 
 
 def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional[int] = None,
-               keep_traj: bool = True, want_extras: bool = False) -> RayBundle:
+               keep_traj: bool = True, want_extras: bool = False, tiled: bool = True) -> RayBundle:
     """Trace a whole fan of rays in one kernel launch (replaces beam.py:340-342).
 
     max_steps: array length per ray (the reference's Ray.MaxStep = 100000 would
@@ -202,9 +215,10 @@ def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional
     amp = np.broadcast_to(np.asarray(amp, np.float64), (n,)).copy()
     L = int(max_steps) if max_steps else min(int(Ray.MaxStep), 4 * (n_field.nx + n_field.ny))
     st = float(n_field.st * Ray.kStep)
-    f = n_field.device_field()
+    f = _device_field(n_field)
     res = _st.trace_batch(f, xg, yg, kx, ky, L=L, st=st, dx=float(n_field.dx[0]), dy=float(n_field.dy[0]),
-                          traj=True if keep_traj else None, want_end=True, want_extras=want_extras)
+                          traj=True if keep_traj else None, want_end=True, want_extras=want_extras,
+                          tiled=bool(tiled and keep_traj))
     return RayBundle(n_field=n_field, x0=np.atleast_1d(np.asarray(x0, np.float64)),
                      y0=np.atleast_1d(np.asarray(y0, np.float64)), freq=freq, st=st, amp=amp,
                      xg0=xg, yg0=yg, kx0=kx, ky0=ky, nsteps=res.nsteps, end_state=res.end_state, result=res)

@@ -29,7 +29,8 @@ import numpy as np
 from . import _cabi
 from ._cabi import (F_DIV_IEEE, F_HOST_IO, F_NO_REFILL, F_TRAJ_HOST, F_TRAJ_TILED, SidtraceError, StbBatch, lib)
 
-__all__ = ["trace", "check", "trace_batch", "Field", "BatchResult", "invalidate", "SidtraceError"]
+__all__ = ["trace", "check", "trace_batch", "Field", "BatchResult", "invalidate", "pinned_empty", "pinned_copy",
+           "SidtraceError"]
 
 
 def _torch():
@@ -51,6 +52,21 @@ def _f64_host(a, name: str, ndim: Optional[int] = None) -> np.ndarray:
     if ndim is not None and a.ndim != ndim:
         raise ValueError(f"{name} must be {ndim}-D, got {a.ndim}-D")
     return a
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """A numpy array backed by page-locked (pinned, device-mapped) host memory.  Launch states
+    and result buffers allocated this way are read / written IN PLACE by the kernels of the
+    tiled schedule (zero-copy), instead of being staged through HBM."""
+    torch = _torch()
+    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+    return torch.empty(shape, dtype=tdt).pin_memory().numpy()
+
+
+def pinned_copy(a) -> np.ndarray:
+    out = pinned_empty(np.shape(a), np.asarray(a).dtype)
+    out[...] = a
+    return out
 
 
 class Field:

@@ -202,7 +202,7 @@ def test_heavy_tail_refill_equals_static(st, oracle_mod, torch_mod):
     kx0[::50] *= 0.05; ky0[::50] *= 0.05          # slow rays stay trapped
     L = 2500
     want = oracle_mod.trace_batch(x0, y0, kx0, ky0, L, 0.25, 1.0, 1.0, nx, ny, ax, ay, want_traj=True, nthreads=4)
-    assert (want["nsteps"] == L - 1).sum() > 50 and np.median(want["nsteps"]) < L / 4 and want["nsteps"].min() == 0
+    assert (want["nsteps"] == L - 1).sum() > 50 and np.median(want["nsteps"]) < L / 4
     f = st.Field(ax, ay, nx, ny)
     for refill in (True, False):
         res = st.trace_batch(f, x0, y0, kx0, ky0, L=L, st=0.25, dx=1.0, dy=1.0, refill=refill, want_extras=True)
@@ -308,3 +308,65 @@ def test_vacuum_step_count_property(st):
     res = st.trace_batch(f, x0, y0, np.zeros(4000), np.full(4000, adv), L=2000, st=1.0, dx=1.0, dy=1.0)
     assert (res.nsteps == int(np.ceil((ny - 1) / adv))).all()
     assert np.array_equal(res.end_state[0], x0) and (res.end_state[1] == adv * res.nsteps).all()
+
+
+def test_trace_rays_bundle_matches_per_ray_Ray(st, ft2_ray):
+    """The batched launcher (replacement of beam.py:340-342) returns, per ray, exactly what the
+    per-ray Ray constructor returns."""
+    from rayrtrace_b200.nfield import Nfield
+    from rayrtrace_b200.ray import Ray, trace_rays
+    n, x, y = ft2_density(int(ft2_ray["nx"]), float(ft2_ray["n0"]))
+    nf = Nfield(n, x=x, y=y)
+    xs = np.linspace(-5, 5, 9); ys = np.full(9, -9.5)
+    ang = np.linspace(-0.2, 0.2, 9)
+    freq = float(ft2_ray["freq"])
+    b = trace_rays(nf, xs, ys, np.sin(ang), np.cos(ang), freq, amp=np.linspace(0.1, 0.9, 9), want_extras=True)
+    assert len(b) == 9
+    for r in (0, 4, 8):
+        one = Ray(xs[r], ys[r], np.sin(ang[r]), np.cos(ang[r]), freq, 0.5, n_field=nf)
+        got = b.ray(r)
+        assert len(got.x) == len(one.x) == b.nsteps[r]
+        # launch direction normalisation differs by <= 1 ulp (np.linalg.norm vs sqrt), see launch_states
+        np.testing.assert_allclose(got.x, one.x, rtol=1e-9)
+        np.testing.assert_allclose(got.y, one.y, rtol=1e-9)
+        np.testing.assert_allclose(got.ky, one.ky, rtol=1e-9)
+        np.testing.assert_allclose(got.ph, one.ph, rtol=1e-9)
+        np.testing.assert_allclose(b.result.ph_end[r], one.ph[-1], rtol=1e-9)
+        assert got.st[-1] == 0 and got.amp == pytest.approx(0.1 + 0.1 * r)
+
+
+@pytest.mark.parametrize("with_traj", [False, True])
+def test_zero_copy_pinned_host_io_bitwise(st, oracle_mod, with_traj):
+    """Tiled schedule + pinned host buffers: the kernel reads launch states and writes per-ray
+    results directly in host memory (no staging).  Same bits as the oracle; pageable buffers
+    (staged path) give the same bits too."""
+    rng = np.random.default_rng(77)
+    nx, ny, n, L = 120, 90, 5000 + 13, 260
+    ax, ay = random_field(rng, nx, ny)
+    launch = list(random_launch(rng, n, nx, ny))
+    launch[0][:3] = (-1.0, np.nan, nx + 5.0)
+    st_ray = rng.uniform(0.2, 0.5, n)
+    want = oracle_mod.trace_batch(*launch, L, 0.3, 0.8, 1.3, nx, ny, ax, ay, st_ray=st_ray, nthreads=4)
+    f = st.Field(ax, ay, nx, ny)
+    for pin in (True, False):
+        ins = [st.pinned_copy(a) if pin else a for a in launch]
+        sr = st.pinned_copy(st_ray) if pin else st_ray
+        out = st.BatchResult()
+        if pin:
+            out.nsteps = st.pinned_empty(n, np.int32); out.end_state = st.pinned_empty((4, n))
+            out.turn_index = st.pinned_empty(n, np.int32); out.lax_end = st.pinned_empty(n); out.ph_end = st.pinned_empty(n)
+            out.nsteps[:] = -7
+        res = st.trace_batch(f, *ins, L=L, st=0.3, dx=0.8, dy=1.3, st_ray=sr, tiled=True, want_extras=True,
+                             traj=True if with_traj else None, out=out)
+        assert np.array_equal(res.nsteps, want["nsteps"])
+        assert res.end_state.tobytes() == want["end"].tobytes()
+        if with_traj:
+            assert res.traj_ray_major().cpu().numpy().tobytes() == want["traj"].tobytes()
+        for r in range(0, n, 97):
+            k = int(want["nsteps"][r])
+            assert int(res.turn_index[r]) == oracle_mod.turning_point(want["traj"][r], k)
+            if k:
+                lax, ph = oracle_mod.lax_ph(want["traj"][r, :k], st_ray[r])
+                assert float(res.ph_end[r]).hex() == float(ph[-1]).hex()
+                assert float(res.lax_end[r]).hex() == float(lax[-1]).hex()
+    f.close()
