@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define STB_ABI_VERSION 1
+#define STB_ABI_VERSION 2
 
 /* status codes */
 #define STB_OK            0
@@ -118,6 +118,19 @@ typedef struct stb_batch_s {
     const double *amp;        /* [ray] launch amplitude (ray.py:56); NULL -> 1                   */
     double   xorg, yorg;      /* physical coordinates of grid node (0,0)                         */
     double   r_lcs, rho_max;
+
+    /* receiver-line crossing, fused: what the reference's Ray.addpoint(val, axis)
+     * (ray.py:131-224) reports for the FIRST crossing of the line y = cross_val (axis 1) or
+     * x = cross_val (axis 2), in PHYSICAL cm -- the inputs of Beam.field_r (beam.py:359-369).
+     * cross_axis = 0 disables it.  Tolerance-level parity (1e-9), see oracle/crossing.py. */
+    int32_t  cross_axis;
+    double   cross_val;
+    const double *x0_phys, *y0_phys;   /* [ray] physical launch point (ray.py:105-106); required */
+    int32_t *cross_count;     /* [ray] crossing segments found (0: the reference returns nan)      */
+    int32_t *cross_index;     /* [ray] index addpoint returns for the first crossing, -1 if none   */
+    int32_t *cross_flags;     /* [ray] bit 0: exact hit of an existing point; bit 1: extrapolated  */
+                              /*       past the last kept point (ray.py:147-148)                   */
+    double  *cross_state;     /* [6][nrays] x, y (cm), kx, ky, lax, ph at that point; NaN if none  */
 } stb_batch_t;
 
 /* Traces b->nrays rays on `stream` (a cudaStream_t passed as void*; NULL = the

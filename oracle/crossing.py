@@ -1,0 +1,97 @@
+"""Oracle for the receiver-line crossing: what the reference's
+``Ray.addpoint(val, axis)`` (ray.py:131-224) reports for the FIRST crossing of
+the line ``y = val`` (or ``x = val``), as a pure function of a kept trajectory.
+
+TEST INFRASTRUCTURE ONLY.  Pinned by tests/golden/ft2_cross.npz, produced by
+the unmodified reference ``Ray.addpoint`` (tests/golden/make_golden.py).
+
+Restated, not inserted: the reference inserts the crossing point into the ray's
+arrays and returns its index; ``Beam.field_r`` (beam.py:359-369) then reads
+``r.x[ind]`` and ``r.ph[ind]``.  This function returns those values directly.
+
+Two documented deviations from the reference text:
+  * the cell of the segment start is ``trunc`` of the grid coordinate the tracer
+    itself used; the reference maps the physical point back through
+    ``x2grid = interp1d(...)`` (ray.py:166-167), identical unless the state sits
+    within an ulp of a cell edge;
+  * squares are products; the reference's ``ky ** 2`` on NumPy scalars goes
+    through libm ``pow`` (ray.py:177-178), which can differ by one ulp.
+Hence the tolerance for this path is 1e-9 relative (north_star), not bitwise.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def _solve(c0, k, a, val, st1):
+    """ray.py:174-193: smallest non-negative root of k*s + a*s^2/2 = val - c0."""
+    st = st1
+    if a != 0:
+        disc = k * k + 2 * a * (val - c0)
+        if disc < 0:
+            return math.nan                      # reference: empty .min() -> ValueError
+        sq = math.sqrt(disc)
+        roots = [r for r in ((-k - sq) / a, (-k + sq) / a) if r >= 0]
+        if not roots:
+            return math.nan
+        st = min(roots)
+        if st == 0 and val != c0 and k != 0:
+            st = (val - c0) / k
+    elif k != 0:
+        st = (val - c0) / k
+    return st
+
+
+def crossing(traj_kept, x0p, y0p, dx, dy, st, ax, ay, val, axis="y"):
+    """traj_kept: [n, 4] kept states in grid units.  Returns dict(count, index, exact,
+    extrapolated, x, y, kx, ky, lax, ph); count == 0 -> the reference returns nan."""
+    t = np.asarray(traj_kept, np.float64)
+    n = t.shape[0]
+    out = dict(count=0, index=-1, exact=0, extrapolated=0, x=math.nan, y=math.nan, kx=math.nan, ky=math.nan,
+               lax=math.nan, ph=math.nan)
+    if n == 0:
+        return out
+    xs = x0p + (t[:, 0] - t[0, 0]) * dx          # ray.py:105-106
+    ys = y0p + (t[:, 1] - t[0, 1]) * dy
+    kx, ky = t[:, 2], t[:, 3]
+    k = np.sqrt(kx * kx + ky * ky)
+    kavr = (k[:-1] + k[1:]) / 2
+    lax = np.cumsum(np.insert(st * kavr, 0, 0))  # ray.py:117-120 with st[:-1] == st
+    ph = np.cumsum(np.insert(np.diff(lax) * kavr, 0, 0))
+    c = ys if axis == "y" else xs
+    kc = ky if axis == "y" else kx
+    eq = np.where(c == val)[0]
+    if len(eq):                                   # ray.py:142-143
+        i = int(eq[0])
+        out.update(count=len(eq), index=i, exact=1, x=xs[i], y=ys[i], kx=kx[i], ky=ky[i], lax=lax[i], ph=ph[i])
+        return out
+    if np.any(c < val) and np.any(val < c):       # ray.py:144-146
+        i_n = np.where((c - val)[:-1] * (c - val)[1:] < 0)[0]
+        st1 = st
+    elif (val - c[-1]) * kc[-1] > 0:              # ray.py:147-148
+        i_n = np.array([n - 1])
+        st1 = 0.0
+        out["extrapolated"] = 1
+    else:
+        return out
+    if len(i_n) == 0:
+        return out
+    i = int(i_n[0])
+    ix, iy = int(t[i, 0]), int(t[i, 1])           # trunc: states are >= 0 inside the grid
+    a_x, a_y = float(ax[iy, ix]), float(ay[iy, ix])
+    s = _solve(c[i], kc[i], a_y if axis == "y" else a_x, val, st1)
+    if math.isnan(s) or s == 0:
+        out["extrapolated"] = 0
+        return out
+    kxn = kx[i] + a_x * s                         # ray.py:212-216
+    kyn = ky[i] + a_y * s
+    xn = xs[i] + kx[i] * s + a_x / 2 * s * s
+    yn = ys[i] + ky[i] * s + a_y / 2 * s * s
+    kn = math.sqrt(kxn * kxn + kyn * kyn)
+    kav = (k[i] + kn) / 2
+    laxn = lax[i] + s * kav
+    phn = ph[i] + (laxn - lax[i]) * kav
+    out.update(count=len(i_n), index=i + 1, x=xn, y=yn, kx=kxn, ky=kyn, lax=laxn, ph=phn)
+    return out

@@ -12,7 +12,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_in
 
 from . import build as _build
 
-STB_ABI_VERSION = 1
+STB_ABI_VERSION = 2
 STB_OK = 0
 STB_ERR_ARG, STB_ERR_CUDA, STB_ERR_NOMEM, STB_ERR_RANGE = -1, -2, -3, -4
 
@@ -54,6 +54,11 @@ class StbBatch(Structure):
         ("amp", c_void_p),
         ("xorg", c_double), ("yorg", c_double),
         ("r_lcs", c_double), ("rho_max", c_double),
+        ("cross_axis", c_int32),
+        ("cross_val", c_double),
+        ("x0_phys", c_void_p), ("y0_phys", c_void_p),
+        ("cross_count", c_void_p), ("cross_index", c_void_p), ("cross_flags", c_void_p),
+        ("cross_state", c_void_p),
     ]
 
 

@@ -203,14 +203,14 @@ namespace {
 
 using stb::KParams;
 
-template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool TILED = false>
+template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool TILED = false, bool CROSS = false>
 int launch_variant(const KParams &p, bool refill, int num_sms, cudaStream_t s)
 {
     const size_t smem = HIST ? (size_t)p.nbins * sizeof(double) : 0;
     if (p.nrays <= 0) return STB_OK;
     long long blocks_all = (p.nrays + stb::kBlock - 1) / stb::kBlock;
     if (refill) {
-        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, true, TILED>;
+        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, true, TILED, CROSS>;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, stb::kBlock, smem));
@@ -220,7 +220,7 @@ int launch_variant(const KParams &p, bool refill, int num_sms, cudaStream_t s)
         CU(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), s));
         kern<<<(unsigned)blocks, stb::kBlock, smem, s>>>(p);
     } else {
-        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, false, TILED>;
+        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, false, TILED, CROSS>;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (blocks_all > 0x7fffffffLL) return fail(STB_ERR_ARG, "too many rays for a static grid");
         kern<<<(unsigned)blocks_all, stb::kBlock, smem, s>>>(p);
@@ -237,8 +237,22 @@ int launch_div(const KParams &p, bool divc, bool refill, int num_sms, cudaStream
                 : launch_variant<TRAJ, EXTRAS, HIST, false>(p, refill, num_sms, s);
 }
 
+template <bool TRAJ, bool TILED>
+int launch_cross(const KParams &p, bool divc, bool refill, int num_sms, cudaStream_t s)
+{
+    return divc ? launch_variant<TRAJ, true, false, true, TILED, true>(p, refill, num_sms, s)
+                : launch_variant<TRAJ, true, false, false, TILED, true>(p, refill, num_sms, s);
+}
+
 int launch_trace(const KParams &p, bool divc, bool refill, bool tiled, int num_sms, cudaStream_t s)
 {
+    if (p.cross_axis) {
+        if (p.hist) return fail(STB_ERR_ARG, "the crossing output cannot be combined with the histogram output");
+        if (p.traj) return tiled ? launch_cross<true, true>(p, divc, refill, num_sms, s)
+                                 : launch_cross<true, false>(p, divc, refill, num_sms, s);
+        return tiled ? launch_cross<false, true>(p, divc, refill, num_sms, s)
+                     : launch_cross<false, false>(p, divc, refill, num_sms, s);
+    }
     if (tiled) {
         // warp-tile schedule: plain trajectories and/or fused running sums; the histogram keeps
         // the ray-granular kernels
@@ -318,6 +332,15 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     p.hist = b->hist; p.nbins = b->nbins; p.amp = b->amp;
     p.xorg = b->xorg; p.yorg = b->yorg; p.r_lcs = b->r_lcs; p.rho_max = b->rho_max;
     p.counter = f->counter + (f->launch_seq++ % kCounters);
+    p.cross_axis = b->cross_axis; p.cross_val = b->cross_val;
+    p.x0p = b->x0_phys; p.y0p = b->y0_phys;
+    p.cross_count = b->cross_count; p.cross_index = b->cross_index; p.cross_flags = b->cross_flags;
+    p.cross_state = b->cross_state;
+    if (b->cross_axis) {
+        if (b->cross_axis != 1 && b->cross_axis != 2) return fail(STB_ERR_ARG, "stb_trace_batch: cross_axis must be 0, 1 (y) or 2 (x)");
+        if (b->nrays > 0 && (!b->x0_phys || !b->y0_phys))
+            return fail(STB_ERR_ARG, "stb_trace_batch: the crossing output needs x0_phys and y0_phys");
+    }
     divc = !(b->flags & STB_F_DIV_IEEE) && divisor_in_guarded_range(b->dx) && divisor_in_guarded_range(b->dy);
     return STB_OK;
 }
@@ -359,11 +382,12 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
     // writes them in place over PCIe, overlapped with the tracing itself: no staging copies,
     // no serial H2D -> kernel -> D2H chain.  Pageable buffers take the staged path below.
     if (host_io && tiled && !traj_host && !b->hist && n) {
-        const void *hp[11] = {b->x0, b->y0, b->kx0, b->ky0, b->st_ray, b->amp,
-                              b->nsteps, b->end_state, b->turn_index, b->lax_end, b->ph_end};
-        void *dp[11];
+        const void *hp[17] = {b->x0, b->y0, b->kx0, b->ky0, b->st_ray, b->amp,
+                              b->nsteps, b->end_state, b->turn_index, b->lax_end, b->ph_end,
+                              b->x0_phys, b->y0_phys, b->cross_count, b->cross_index, b->cross_flags, b->cross_state};
+        void *dp[17];
         bool all = true;
-        for (int k = 0; k < 11; ++k) {
+        for (int k = 0; k < 17; ++k) {
             dp[k] = mapped_alias(hp[k]);
             if (hp[k] && !dp[k]) all = false;
         }
@@ -373,6 +397,9 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
             p.st_ray = (const double *)dp[4]; p.amp = (const double *)dp[5];
             p.nsteps = (int *)dp[6]; p.endst = (double *)dp[7];
             p.turn = (int *)dp[8]; p.lax_end = (double *)dp[9]; p.ph_end = (double *)dp[10];
+            p.x0p = (const double *)dp[11]; p.y0p = (const double *)dp[12];
+            p.cross_count = (int *)dp[13]; p.cross_index = (int *)dp[14]; p.cross_flags = (int *)dp[15];
+            p.cross_state = (double *)dp[16];
             rc = launch_trace(p, divc, refill, tiled, f->num_sms, s);
             if (rc != STB_OK) return rc;
             CU(cudaStreamSynchronize(s));
@@ -382,30 +409,34 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
 
     if (host_io) {
         // ---- inputs: [x0 | y0 | kx0 | ky0 | st_ray? | amp?] ----
-        const int nin = 4 + (b->st_ray ? 1 : 0) + (b->amp ? 1 : 0);
+        const int nin = 4 + (b->st_ray ? 1 : 0) + (b->amp ? 1 : 0) + (b->x0_phys ? 1 : 0) + (b->y0_phys ? 1 : 0);
         rc = f->ws_in.ensure(nb * nin + 64);
         if (rc != STB_OK) return rc;
         double *din = (double *)f->ws_in.p;
-        const double *src[6] = {b->x0, b->y0, b->kx0, b->ky0, b->st_ray, b->amp};
-        const double **dst[6] = {&p.x0, &p.y0, &p.kx0, &p.ky0, &p.st_ray, &p.amp};
+        const double *src[8] = {b->x0, b->y0, b->kx0, b->ky0, b->st_ray, b->amp, b->x0_phys, b->y0_phys};
+        const double **dst[8] = {&p.x0, &p.y0, &p.kx0, &p.ky0, &p.st_ray, &p.amp, &p.x0p, &p.y0p};
         int slot = 0;
-        for (int k = 0; k < 6; ++k) {
+        for (int k = 0; k < 8; ++k) {
             if (!src[k]) continue;
             double *d = din + (size_t)slot * n;
             if (n) CU(cudaMemcpyAsync(d, src[k], nb, cudaMemcpyHostToDevice, s));
             *dst[k] = d;
             ++slot;
         }
-        // ---- outputs: [end 4n | lax n | ph n | nsteps n(i32) | turn n(i32)] ----
-        rc = f->ws_out.ensure(nb * 6 + 2 * n * sizeof(int32_t) + 64);
+        // ---- outputs: [end 4n | lax n | ph n | cross_state 6n | nsteps, turn, cross_count/index/flags n(i32) each] ----
+        rc = f->ws_out.ensure(nb * 12 + 5 * n * sizeof(int32_t) + 64);
         if (rc != STB_OK) return rc;
         double *dout = (double *)f->ws_out.p;
         p.endst = b->end_state ? dout : nullptr;
         p.lax_end = b->lax_end ? dout + 4 * n : nullptr;
         p.ph_end = b->ph_end ? dout + 5 * n : nullptr;
-        int32_t *iout = (int32_t *)(dout + 6 * n);
+        p.cross_state = b->cross_state ? dout + 6 * n : nullptr;
+        int32_t *iout = (int32_t *)(dout + 12 * n);
         p.nsteps = b->nsteps ? iout : nullptr;
         p.turn = b->turn_index ? iout + n : nullptr;
+        p.cross_count = b->cross_count ? iout + 2 * n : nullptr;
+        p.cross_index = b->cross_index ? iout + 3 * n : nullptr;
+        p.cross_flags = b->cross_flags ? iout + 4 * n : nullptr;
         (void)extras;
         if (b->hist) {
             rc = f->ws_hist.ensure((size_t)b->nbins * sizeof(double));
@@ -431,6 +462,10 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
         if (b->ph_end) CU(cudaMemcpyAsync(b->ph_end, p.ph_end, nb, cudaMemcpyDeviceToHost, s));
         if (b->nsteps) CU(cudaMemcpyAsync(b->nsteps, p.nsteps, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         if (b->turn_index) CU(cudaMemcpyAsync(b->turn_index, p.turn, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (b->cross_state) CU(cudaMemcpyAsync(b->cross_state, p.cross_state, 6 * nb, cudaMemcpyDeviceToHost, s));
+        if (b->cross_count) CU(cudaMemcpyAsync(b->cross_count, p.cross_count, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (b->cross_index) CU(cudaMemcpyAsync(b->cross_index, p.cross_index, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (b->cross_flags) CU(cudaMemcpyAsync(b->cross_flags, p.cross_flags, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
     if (host_io && b->hist)
         CU(cudaMemcpyAsync(b->hist, p.hist, (size_t)b->nbins * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -54,7 +54,32 @@ struct KParams {
     const double *amp;
     double xorg, yorg, r_lcs, rho_max;
     unsigned long long *counter;         // ray queue head (refill schedule)
+    // receiver-line crossing (CROSS)
+    int cross_axis;                      // 1: y = cross_val, 2: x = cross_val (physical cm)
+    double cross_val;
+    const double *x0p, *y0p;             // physical launch points
+    int *cross_count, *cross_index, *cross_flags;
+    double *cross_state;                 // [6][nrays]
 };
+
+// Smallest non-negative root s of k*s + a*s^2/2 = val - c0 (ray.py:174-193); NaN when none.
+__device__ __forceinline__ double cross_solve(double c0, double k, double a, double val, double st1)
+{
+    double st = st1;
+    if (a != 0.0) {
+        const double disc = k * k + 2.0 * a * (val - c0);
+        if (!(disc >= 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
+        const double sq = sqrt(disc);
+        const double r1 = (-k - sq) / a, r2 = (-k + sq) / a;
+        const bool ok1 = r1 >= 0.0, ok2 = r2 >= 0.0;
+        if (!ok1 && !ok2) return __longlong_as_double(0x7ff8000000000000LL);
+        st = ok1 && ok2 ? fmin(r1, r2) : (ok1 ? r1 : r2);
+        if (st == 0.0 && val != c0 && k != 0.0) st = (val - c0) / k;
+    } else if (k != 0.0) {
+        st = (val - c0) / k;
+    }
+    return st;
+}
 
 __device__ __forceinline__ void st_state(double *p, double a, double b, double c, double d)
 {
@@ -107,7 +132,12 @@ __device__ __forceinline__ void hist_add(double *sh, int b, double w)
 // 1 KB row store and consecutive steps are consecutive rows -- sequential DRAM pages
 // instead of 32 scattered sectors.  Rays are then claimed a whole tile at a time
 // (the lane-granular refill would scatter a new ray's rows).
-template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool REFILL, bool TILED = false>
+//
+// CROSS (needs EXTRAS): first crossing of a receiver line y = val / x = val with the semantics of
+// the reference's Ray.addpoint (ray.py:131-224): exact hits, sign-change segments solved with the
+// start cell's constant acceleration, or extrapolation past the last kept point.  Tolerance-level
+// parity (the reference squares through libm pow there), so plain arithmetic is used.
+template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool REFILL, bool TILED = false, bool CROSS = false>
 __global__ void __launch_bounds__(kBlock)
 trace_kernel(const KParams p)
 {
@@ -132,6 +162,13 @@ trace_kernel(const KParams p)
     int turn = -1;
     double kprev = 0, lax = 0, ph = 0, a2 = 1.0;
     int binprev = -1;
+    // crossing: previous kept state, capture of the first crossing / exact hit
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    double xg0 = 0, yg0 = 0, x0p = 0, y0p = 0;
+    double pxg = 0, pyg = 0, pkx = 0, pky = 0, pmx = 0, pmy = 0, plax = 0, pph = 0, dprev = 0;
+    double cx = qnan, cy = qnan, ckx = qnan, cky = qnan, clax = qnan, cph = qnan;
+    int cidx = -1, ncross = 0, neq = 0;
+    bool below = false, above = false;
 
     auto launch = [&](long long r) {
         ray = r;
@@ -144,8 +181,31 @@ trace_kernel(const KParams p)
             st_state(tp, x, y, kx, ky);
         }
         if (EXTRAS) { turn = -1; lax = 0; ph = 0; }
+        if (CROSS) {
+            xg0 = x; yg0 = y; x0p = p.x0p[r]; y0p = p.y0p[r];
+            cx = cy = ckx = cky = clax = cph = qnan;
+            cidx = -1; ncross = 0; neq = 0; below = above = false;
+        }
         if (HIST) { const double a = p.amp ? p.amp[r] : 1.0; a2 = __dmul_rn(a, a); }
         active = true;
+    };
+
+    const bool axis_y = p.cross_axis != 2;
+    // solve from the previous kept state (index i-1) and capture the crossing point (ray.py:212-216)
+    auto capture_from_prev = [&](double st1) -> bool {
+        const double xp = x0p + (pxg - xg0) * p.dx, yp = y0p + (pyg - yg0) * p.dy;   // ray.py:105-106
+        const double s = cross_solve(axis_y ? yp : xp, axis_y ? pky : pkx, axis_y ? pmy : pmx, p.cross_val, st1);
+        if (!(s == s) || s == 0.0) return false;
+        ckx = pkx + pmx * s;
+        cky = pky + pmy * s;
+        cx = xp + pkx * s + pmx / 2 * s * s;
+        cy = yp + pky * s + pmy / 2 * s * s;
+        const double kp = sqrt(pkx * pkx + pky * pky), kn = sqrt(ckx * ckx + cky * cky);
+        const double kav = (kp + kn) / 2;
+        clax = plax + s * kav;
+        cph = pph + (clax - plax) * kav;
+        cidx = i;               // i-1 is the segment start: the reference inserts at (i-1)+1
+        return true;
     };
 
     // per-ray results: state i is the first out-of-domain state or the cap (sidtracemodule.c:50).
@@ -164,6 +224,27 @@ trace_kernel(const KParams p)
             if (p.turn) p.turn[ray] = turn;
             if (p.lax_end) p.lax_end[ray] = lax;
             if (p.ph_end) p.ph_end[ray] = ph;
+        }
+        if (CROSS) {
+            // here i = n (states 0..n-1 are kept) and the "previous kept state" is state n-1
+            int count = 0, flags = 0;
+            if (neq > 0) {                              // ray.py:142-143: exact hit(s), nothing inserted
+                count = neq; flags = 1;
+            } else if (below && above) {                // ray.py:144-146
+                count = cidx >= 0 ? ncross : 0;
+            } else if (i >= 1) {                        // ray.py:147-148: heading for the line past the end
+                const double cl = axis_y ? y0p + (pyg - yg0) * p.dy : x0p + (pxg - xg0) * p.dx;
+                if ((p.cross_val - cl) * (axis_y ? pky : pkx) > 0.0 && capture_from_prev(0.0)) { count = 1; flags = 2; }
+            }
+            if (count == 0) { cx = cy = ckx = cky = clax = cph = qnan; cidx = -1; }
+            if (p.cross_count) p.cross_count[ray] = count;
+            if (p.cross_index) p.cross_index[ray] = cidx;
+            if (p.cross_flags) p.cross_flags[ray] = flags;
+            if (p.cross_state) {
+                p.cross_state[0 * p.nrays + ray] = cx;  p.cross_state[1 * p.nrays + ray] = cy;
+                p.cross_state[2 * p.nrays + ray] = ckx; p.cross_state[3 * p.nrays + ray] = cky;
+                p.cross_state[4 * p.nrays + ray] = clax; p.cross_state[5 * p.nrays + ray] = cph;
+            }
         }
         ray = -1;
     };
@@ -227,6 +308,26 @@ trace_kernel(const KParams p)
                             if (b >= 0 && b < p.nbins) binprev = b;
                         }
                     }
+                }
+
+                if (CROSS) {
+                    // state i is kept; lax, ph are its running sums
+                    const double c = axis_y ? y0p + (y - yg0) * p.dy : x0p + (x - xg0) * p.dx;
+                    const double d = c - p.cross_val;
+                    if (d == 0.0) {
+                        if (neq == 0) {
+                            cx = x0p + (x - xg0) * p.dx; cy = y0p + (y - yg0) * p.dy;
+                            ckx = kx; cky = ky; clax = lax; cph = ph; cidx = i;
+                        }
+                        ++neq;
+                    }
+                    below |= d < 0.0;
+                    above |= d > 0.0;
+                    if (i > 0 && dprev * d < 0.0) {
+                        if (ncross == 0 && neq == 0) capture_from_prev(st);
+                        ++ncross;
+                    }
+                    pxg = x; pyg = y; pkx = kx; pky = ky; pmx = m.x; pmy = m.y; plax = lax; pph = ph; dprev = d;
                 }
 
                 const double tx = __dmul_rn(__dmul_rn(sst, m.x), 0.5);   // ((st*st)*Mx)/2

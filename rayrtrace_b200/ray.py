@@ -201,13 +201,18 @@ def launch_states(n_field, x0, y0, kx0, ky0, freq):
 
 
 def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional[int] = None,
-               keep_traj: bool = True, want_extras: bool = False, tiled: bool = True) -> RayBundle:
+               keep_traj: bool = True, want_extras: bool = False, tiled: bool = True,
+               receiver=None) -> RayBundle:
     """Trace a whole fan of rays in one kernel launch (replaces beam.py:340-342).
 
     max_steps: array length per ray (the reference's Ray.MaxStep = 100000 would
     be 3.2 MB per ray; default here is a bound from the grid size:
     4*(nx+ny) states, enough for any non-trapped ray; rays hitting the cap
-    report nsteps == max_steps-1 exactly like the reference at its cap)."""
+    report nsteps == max_steps-1 exactly like the reference at its cap).
+
+    receiver: (val, axis) -- also report, per ray, what ``Ray.addpoint(val, axis)`` would
+    (ray.py:131-224): first crossing of the receiver line, its phase and wave vector
+    (``bundle.result.cross_*``), i.e. the per-ray inputs of ``Beam.field_r`` (beam.py:359-369)."""
     xg, yg, kx, ky, freq = launch_states(n_field, x0, y0, kx0, ky0, freq)
     n = len(xg)
     if amp is None:
@@ -218,7 +223,9 @@ def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional
     f = _device_field(n_field)
     res = _st.trace_batch(f, xg, yg, kx, ky, L=L, st=st, dx=float(n_field.dx[0]), dy=float(n_field.dy[0]),
                           traj=True if keep_traj else None, want_end=True, want_extras=want_extras,
-                          tiled=bool(tiled and keep_traj))
+                          tiled=bool(tiled and keep_traj), cross=receiver,
+                          x0_phys=np.ascontiguousarray(np.atleast_1d(np.asarray(x0, np.float64))) if receiver else None,
+                          y0_phys=np.ascontiguousarray(np.atleast_1d(np.asarray(y0, np.float64))) if receiver else None)
     return RayBundle(n_field=n_field, x0=np.atleast_1d(np.asarray(x0, np.float64)),
                      y0=np.atleast_1d(np.asarray(y0, np.float64)), freq=freq, st=st, amp=amp,
                      xg0=xg, yg0=yg, kx0=kx, ky0=ky, nsteps=res.nsteps, end_state=res.end_state, result=res)

@@ -233,6 +233,10 @@ class BatchResult:
     lax_end: object = None      # float64 [nrays]
     ph_end: object = None       # float64 [nrays]
     hist: object = None         # float64 [nbins]
+    cross_count: object = None  # int32 [nrays]   crossing segments of the receiver line (0: none)
+    cross_index: object = None  # int32 [nrays]   index Ray.addpoint would return for the first one
+    cross_flags: object = None  # int32 [nrays]   bit 0 exact hit, bit 1 extrapolated past the end
+    cross_state: object = None  # float64 [6, nrays]  x, y (cm), kx, ky, lax, ph at the first crossing
     tiled: bool = False         # traj is [ntiles, L, 32, 4] (tile = ray // 32, lane = ray % 32)
 
     def ray_states(self, r: int, n: Optional[int] = None):
@@ -271,6 +275,7 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
                 hist=None, nbins: int = 0, amp=None, xorg: float = 0.0, yorg: float = 0.0,
                 r_lcs: float = 1.0, rho_max: float = 1.0, traj_host: bool = False,
                 div_ieee: bool = False, refill: bool = True, tiled: bool = False,
+                cross=None, x0_phys=None, y0_phys=None,
                 out: Optional[BatchResult] = None, stream=None) -> BatchResult:
     """Trace ``len(x0)`` rays in one launch.
 
@@ -282,6 +287,9 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     traj: None -> no trajectories; True -> allocate a zeroed [nrays, L, 4] CUDA
     tensor; or a preallocated CUDA tensor of that shape (32-byte aligned).
     With ``traj_host=True`` and host I/O, a numpy [nrays, L, 4] array.
+    cross: (val, axis) with axis 'y' or 'x' -- fused receiver-line crossing with the semantics of
+    the reference's Ray.addpoint (ray.py:131-224); needs the physical launch points
+    x0_phys, y0_phys; fills cross_count / cross_index / cross_flags / cross_state.
     tiled: trajectory layout [ceil(nrays/32), L, 32, 4] instead of [nrays, L, 4]: every
     warp-step becomes one coalesced 1 KB row store (the fast layout; read rays back
     with ``BatchResult.ray_states``).
@@ -293,6 +301,14 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
         ins["st_ray"] = st_ray
     if amp is not None:
         ins["amp"] = amp
+    if cross is not None:
+        if x0_phys is None or y0_phys is None:
+            raise ValueError("cross=(val, axis) needs x0_phys and y0_phys (physical launch points)")
+        if cross[1] not in ("x", "y"):
+            raise ValueError("cross axis must be 'x' or 'y'")
+        ins["x0_phys"] = x0_phys
+        ins["y0_phys"] = y0_phys
+        want_extras = True
     n = int(x0.shape[0])
     for name, a in ins.items():
         if dev_io:
@@ -326,6 +342,16 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
             res.lax_end = alloc((n,), np.float64, torch.float64)
         if res.ph_end is None:
             res.ph_end = alloc((n,), np.float64, torch.float64)
+
+    if cross is not None:
+        if res.cross_count is None:
+            res.cross_count = alloc((n,), np.int32, torch.int32)
+        if res.cross_index is None:
+            res.cross_index = alloc((n,), np.int32, torch.int32)
+        if res.cross_flags is None:
+            res.cross_flags = alloc((n,), np.int32, torch.int32)
+        if res.cross_state is None:
+            res.cross_state = alloc((6, n), np.float64, torch.float64)
 
     flags = 0
     if not dev_io:
@@ -386,6 +412,13 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
         b.nbins = nbins
         b.amp = _ptr(amp)
         b.xorg, b.yorg, b.r_lcs, b.rho_max = float(xorg), float(yorg), float(r_lcs), float(rho_max)
+
+    if cross is not None:
+        b.cross_axis = 1 if cross[1] == "y" else 2
+        b.cross_val = float(cross[0])
+        b.x0_phys, b.y0_phys = _ptr(x0_phys), _ptr(y0_phys)
+        b.cross_count, b.cross_index = _ptr(res.cross_count), _ptr(res.cross_index)
+        b.cross_flags, b.cross_state = _ptr(res.cross_flags), _ptr(res.cross_state)
 
     if stream is None:
         stream = torch.cuda.current_stream(device)

@@ -35,3 +35,8 @@ def oracle_mod():
     import oracle
     oracle.port()   # builds libsidtrace_oracle.so on demand (gcc only)
     return oracle
+
+
+@pytest.fixture(scope="session")
+def ft2_cross():
+    return np.load(os.path.join(GOLDEN, "ft2_cross.npz"))

@@ -165,6 +165,46 @@ def make_ft2_fan(den):
     np.savez_compressed(os.path.join(HERE, "ft2_fan.npz"), **out)
 
 
+def make_ft2_cross(den, ray):
+    """Reference Ray.addpoint (ray.py:131-224) on a 40-ray fan through the over-dense profile:
+    what it returns for receiver lines y = 9, -2, -9 and x = 5 (first crossing)."""
+    nx, n0 = 129, 3.0e14
+    n, x, y = ft2_density(nx, n0)
+    nf = den.Nfield(n, x=x, y=y)
+    freq = 136.268e9
+    rng = np.random.default_rng(77)
+    nray = 40
+    xs = rng.uniform(-6.0, 6.0, nray)
+    ang = rng.uniform(-0.35, 0.35, nray)
+    ray.Ray.MaxStep = 4096
+    lines = [(9.0, "y"), (-2.0, "y"), (-9.0, "y"), (5.0, "x")]
+    launch = np.zeros((nray, 4))
+    nkept = np.zeros(nray, np.int64)
+    res = np.full((len(lines), nray, 9), np.nan)      # count, index, x, y, kx, ky, lax, ph, raised
+    for r in range(nray):
+        for li, (val, axis) in enumerate(lines):
+            rr = ray.Ray(xs[r], -9.5, np.sin(ang[r]), np.cos(ang[r]), freq, 1, n_field=nf)
+            launch[r] = float(nf.x2grid(xs[r])), float(nf.y2grid(-9.5)), rr.kx[0], rr.ky[0]
+            nkept[r] = len(rr.x)
+            try:
+                ind = rr.addpoint(val, axis=axis)
+            except ValueError:                        # empty .min(): no non-negative root
+                res[li, r, 0] = 0; res[li, r, 8] = 1
+                continue
+            if not hasattr(ind, "__len__") or len(ind) == 0:
+                res[li, r, 0] = 0; res[li, r, 8] = 0
+                continue
+            i = int(ind[0])
+            res[li, r] = len(ind), i, rr.x[i], rr.y[i], rr.kx[i], rr.ky[i], rr.lax[i], rr.ph[i], 0
+    ray.Ray.MaxStep = 100000
+    np.savez_compressed(os.path.join(HERE, "ft2_cross.npz"), nx=np.int64(nx), n0=n0, freq=freq, x0=xs, y0=np.full(nray, -9.5),
+                        launch=launch, nkept=nkept, st=np.float64(nf.st), dx0=np.float64(nf.dx[0]), dy0=np.float64(nf.dy[0]),
+                        line_val=np.array([l[0] for l in lines]), line_axis=np.array([l[1] for l in lines]), res=res)
+    print("ft2_cross: counts per line", [(res[li, :, 0]).astype(int).tolist().count(1) for li in range(len(lines))],
+          "none", [int((res[li, :, 0] == 0).sum()) for li in range(len(lines))],
+          "multi", [int((res[li, :, 0] > 1).sum()) for li in range(len(lines))])
+
+
 if __name__ == "__main__":
     if not oracle.have_ref():
         oracle.build(ref=True)
@@ -172,5 +212,6 @@ if __name__ == "__main__":
     make_kat(oracle.ref())
     make_ft2_ray(den, ray)
     make_ft2_fan(den)
-    for f in ("kat.npz", "ft2_ray.npz", "ft2_fan.npz"):
+    make_ft2_cross(den, ray)
+    for f in ("kat.npz", "ft2_ray.npz", "ft2_fan.npz", "ft2_cross.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -370,3 +370,60 @@ def test_zero_copy_pinned_host_io_bitwise(st, oracle_mod, with_traj):
                 assert float(res.ph_end[r]).hex() == float(ph[-1]).hex()
                 assert float(res.lax_end[r]).hex() == float(lax[-1]).hex()
     f.close()
+
+
+@pytest.mark.parametrize("tiled", [False, True])
+@pytest.mark.parametrize("device_io", [False, True])
+def test_receiver_crossing_matches_reference_addpoint(st, torch_mod, ft2_cross, tiled, device_io):
+    """Fused receiver-line crossing against what the reference's own Ray.addpoint
+    returned (tests/golden/ft2_cross.npz).  Tolerance 1e-9 relative (north_star): the reference
+    squares through libm pow there (oracle/crossing.py), so this path is not bitwise."""
+    from test_oracle_crossing import cross_case
+    nf = cross_case(ft2_cross)
+    la = ft2_cross["launch"]
+    ins = [np.ascontiguousarray(la[:, k]) for k in range(4)]
+    xp, yp = np.ascontiguousarray(ft2_cross["x0"]), np.ascontiguousarray(ft2_cross["y0"])
+    if device_io:
+        ins = [torch_mod.from_numpy(a).cuda() for a in ins]
+        xp, yp = torch_mod.from_numpy(xp).cuda(), torch_mod.from_numpy(yp).cuda()
+    res_all = ft2_cross["res"]
+    for li, (val, axis) in enumerate(zip(ft2_cross["line_val"], ft2_cross["line_axis"])):
+        res = st.trace_batch(nf.device_field(), *ins, L=4096, st=nf.st, dx=nf.dx[0], dy=nf.dy[0], tiled=tiled,
+                             traj=True if tiled else None, cross=(float(val), str(axis)), x0_phys=xp, y0_phys=yp)
+        get = (lambda a: a.cpu().numpy()) if device_io else (lambda a: a)
+        cnt, idx, cs = get(res.cross_count), get(res.cross_index), get(res.cross_state)
+        assert np.array_equal(get(res.nsteps), ft2_cross["nkept"])
+        want = res_all[li]
+        assert np.array_equal(cnt, want[:, 0].astype(int)), (li, cnt, want[:, 0])
+        hit = want[:, 0] > 0
+        assert np.array_equal(idx[hit], want[hit, 1].astype(int))
+        assert (idx[~hit] == -1).all() and np.isnan(cs[:, ~hit]).all()
+        np.testing.assert_allclose(cs[:, hit].T, want[hit, 2:8], rtol=1e-9, atol=1e-9)
+
+
+def test_receiver_crossing_vs_oracle_random(st, oracle_mod):
+    """Same, against oracle/crossing.py on a random field (exact hits, both axes, extrapolation)."""
+    from oracle.crossing import crossing
+    rng = np.random.default_rng(31)
+    nx, ny, n, L = 60, 50, 400, 300
+    ax, ay = random_field(rng, nx, ny, scale=0.05)
+    x0, y0, kx0, ky0 = random_launch(rng, n, nx, ny)
+    y0[:50] = 10.0                                   # exact hits of the line y = 2.0 (phys) below
+    want = oracle_mod.trace_batch(x0, y0, kx0, ky0, L, 0.4, 0.5, 0.25, nx, ny, ax, ay)
+    xp = -3.0 + x0 * 0.5; yp = -0.5 + y0 * 0.25       # physical launch points of an equidistant grid
+    f = st.Field(ax, ay, nx, ny)
+    for val, axis in ((2.0, "y"), (6.0, "y"), (9.5, "x"), (100.0, "x")):
+        res = st.trace_batch(f, x0, y0, kx0, ky0, L=L, st=0.4, dx=0.5, dy=0.25, cross=(val, axis), x0_phys=xp, y0_phys=yp)
+        nhit = 0
+        for r in range(n):
+            k = int(want["nsteps"][r])
+            o = crossing(want["traj"][r, :k], xp[r], yp[r], 0.5, 0.25, 0.4, ax, ay, val, axis)
+            assert int(res.cross_count[r]) == o["count"], (val, axis, r)
+            if o["count"]:
+                nhit += 1
+                assert int(res.cross_index[r]) == o["index"]
+                assert int(res.cross_flags[r]) == o["exact"] + 2 * o["extrapolated"]
+                np.testing.assert_allclose(res.cross_state[:, r], [o[q] for q in ("x", "y", "kx", "ky", "lax", "ph")],
+                                           rtol=1e-9, atol=1e-9)
+        assert nhit > 20 or val == 100.0
+    f.close()
