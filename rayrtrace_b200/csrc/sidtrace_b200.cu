@@ -203,14 +203,18 @@ namespace {
 
 using stb::KParams;
 
-template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool TILED = false, bool CROSS = false>
+template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool TILED = false, bool CROSS = false, bool STRAY = true>
 int launch_variant(const KParams &p, bool refill, int num_sms, cudaStream_t s)
 {
+    // lean variants (no fused outputs) with one global step keep st in the constant bank
+    if constexpr (STRAY && !EXTRAS && !HIST && !CROSS) {
+        if (!p.st_ray) return launch_variant<TRAJ, EXTRAS, HIST, DIVC, TILED, CROSS, false>(p, refill, num_sms, s);
+    }
     const size_t smem = HIST ? (size_t)p.nbins * sizeof(double) : 0;
     if (p.nrays <= 0) return STB_OK;
     long long blocks_all = (p.nrays + stb::kBlock - 1) / stb::kBlock;
     if (refill) {
-        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, true, TILED, CROSS>;
+        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, true, TILED, CROSS, STRAY>;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, stb::kBlock, smem));
@@ -220,7 +224,7 @@ int launch_variant(const KParams &p, bool refill, int num_sms, cudaStream_t s)
         CU(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), s));
         kern<<<(unsigned)blocks, stb::kBlock, smem, s>>>(p);
     } else {
-        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, false, TILED, CROSS>;
+        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, false, TILED, CROSS, STRAY>;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (blocks_all > 0x7fffffffLL) return fail(STB_ERR_ARG, "too many rays for a static grid");
         kern<<<(unsigned)blocks_all, stb::kBlock, smem, s>>>(p);
@@ -324,7 +328,7 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     p.fx = (double)(f->nx - 1); p.fy = (double)(f->ny - 1);
     p.nrays = b->nrays; p.L = (int)b->L;
     p.x0 = b->x0; p.y0 = b->y0; p.kx0 = b->kx0; p.ky0 = b->ky0;
-    p.st = b->st; p.st_ray = b->st_ray;
+    p.st = b->st; p.sst = b->st * b->st; p.st_ray = b->st_ray;
     p.dx = b->dx; p.dy = b->dy; p.rdx = 1.0 / b->dx; p.rdy = 1.0 / b->dy;
     p.traj = b->traj; p.stride = stride;
     p.nsteps = b->nsteps; p.endst = b->end_state;

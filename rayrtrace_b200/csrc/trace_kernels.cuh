@@ -32,6 +32,10 @@
 namespace stb {
 
 constexpr int kBlock = 128;   // threads per CTA (4 warps)
+#ifndef STB_MINB
+#define STB_MINB 12           // min resident CTAs/SM asked of ptxas for the lean variants: 40 registers,
+#endif                        // 48 warps/SM (measured: +4..7 % in endpoint mode, neutral for trajectories;
+                              // 16 -> 32 registers spills and loses 20 %, profiles/r01/occupancy_layout_sweep.txt)
 
 struct KParams {
     const double2 *field;   // {ax, ay} per cell, row stride nxm1
@@ -40,7 +44,7 @@ struct KParams {
     long long nrays;
     int L;
     const double *x0, *y0, *kx0, *ky0;
-    double st;
+    double st, sst;                      // sst = RN(st*st), computed once on the host
     const double *st_ray;
     double dx, dy, rdx, rdy;
     double *traj;
@@ -104,6 +108,28 @@ __device__ __forceinline__ double div_const(double v, double d, double rd)
     return __ddiv_rn(v, d);                  // subnormal, huge, inf, nan: generic path
 }
 
+// Both quotients of a step.  One combined exponent test sends the (overwhelmingly common) case
+// "vx and vy both in the guarded range" down a branch-free path where the two 3-instruction
+// sequences interleave; anything else (a zero, a subnormal, inf, nan) takes the per-quotient path.
+template <bool DIVC>
+__device__ __forceinline__ void div_pair(double vx, double vy, double dx, double dy, double rdx, double rdy,
+                                         double &wx, double &wy)
+{
+    if (DIVC) {
+        const unsigned ex = ((unsigned)__double2hiint(vx) & 0x7ff00000u) - (623u << 20);
+        const unsigned ey = ((unsigned)__double2hiint(vy) & 0x7ff00000u) - (623u << 20);
+        if (max(ex, ey) <= (800u << 20)) {
+            const double qx = __dmul_rn(vx, rdx), qy = __dmul_rn(vy, rdy);
+            const double rx = __fma_rn(-qx, dx, vx), ry = __fma_rn(-qy, dy, vy);
+            wx = __fma_rn(rx, rdx, qx);
+            wy = __fma_rn(ry, rdy, qy);
+            return;
+        }
+    }
+    wx = div_const<DIVC>(vx, dx, rdx);
+    wy = div_const<DIVC>(vy, dy, rdy);
+}
+
 __device__ __forceinline__ double kmod(double kx, double ky)
 {   // ray.py:115  np.sqrt(kx**2 + ky**2)
     return __dsqrt_rn(__dadd_rn(__dmul_rn(kx, kx), __dmul_rn(ky, ky)));
@@ -137,8 +163,11 @@ __device__ __forceinline__ void hist_add(double *sh, int b, double w)
 // the reference's Ray.addpoint (ray.py:131-224): exact hits, sign-change segments solved with the
 // start cell's constant acceleration, or extrapolation past the last kept point.  Tolerance-level
 // parity (the reference squares through libm pow there), so plain arithmetic is used.
-template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool REFILL, bool TILED = false, bool CROSS = false>
-__global__ void __launch_bounds__(kBlock)
+// STRAY = false: one global step for the whole launch (the reference's case, den.py:107): st and
+// st*st stay in the constant bank instead of four registers per thread.
+template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool REFILL, bool TILED = false, bool CROSS = false,
+          bool STRAY = true>
+__global__ void __launch_bounds__(kBlock, (CROSS || HIST || EXTRAS) ? 1 : STB_MINB)
 trace_kernel(const KParams p)
 {
     extern __shared__ double sh_hist[];
@@ -153,10 +182,9 @@ trace_kernel(const KParams p)
 
     // per-ray state
     long long ray = -1;
-    bool active = false;
     int i = 0;
     double x = 0, y = 0, kx = 0, ky = 0;
-    double st = p.st, sst = __dmul_rn(p.st, p.st);
+    double st_r = p.st, sst_r = p.sst;      // per-ray step (STRAY)
     double *tp = nullptr;
     // extras
     int turn = -1;
@@ -169,11 +197,12 @@ trace_kernel(const KParams p)
     double cx = qnan, cy = qnan, ckx = qnan, cky = qnan, clax = qnan, cph = qnan;
     int cidx = -1, ncross = 0, neq = 0;
     bool below = false, above = false;
+    const bool axis_y = p.cross_axis != 2;
 
     auto launch = [&](long long r) {
         ray = r;
         x = p.x0[r]; y = p.y0[r]; kx = p.kx0[r]; ky = p.ky0[r];
-        if (p.st_ray) { st = p.st_ray[r]; sst = __dmul_rn(st, st); }
+        if (STRAY && p.st_ray) { st_r = p.st_ray[r]; sst_r = __dmul_rn(st_r, st_r); }
         i = 0;
         if (TRAJ) {
             tp = TILED ? p.traj + ((r >> 5) * (long long)p.L * 32 + (r & 31)) * 4
@@ -187,10 +216,8 @@ trace_kernel(const KParams p)
             cidx = -1; ncross = 0; neq = 0; below = above = false;
         }
         if (HIST) { const double a = p.amp ? p.amp[r] : 1.0; a2 = __dmul_rn(a, a); }
-        active = true;
     };
 
-    const bool axis_y = p.cross_axis != 2;
     // solve from the previous kept state (index i-1) and capture the crossing point (ray.py:212-216)
     auto capture_from_prev = [&](double st1) -> bool {
         const double xp = x0p + (pxg - xg0) * p.dx, yp = y0p + (pyg - yg0) * p.dy;   // ray.py:105-106
@@ -246,111 +273,137 @@ trace_kernel(const KParams p)
                 p.cross_state[4 * p.nrays + ray] = clax; p.cross_state[5 * p.nrays + ray] = cph;
             }
         }
-        ray = -1;
     };
 
-    bool more = REFILL;   // warp-uniform: the queue may still hold rays
-    if (!REFILL) {
-        const long long r = (long long)blockIdx.x * kBlock + threadIdx.x;
-        if (r < p.nrays) launch(r);
-    }
+    // One step of the reference loop; false when the guard on state i fails (the ray has ended).
+    auto step = [&]() -> bool {
+        // sidtracemodule.c:36 -- guard on state i (NaN fails every comparison)
+        if (!((i < Lm1) & (x >= 0.0) & (x < p.fx) & (y >= 0.0) & (y < p.fy))) return false;
+        const double st = STRAY ? st_r : p.st, sst = STRAY ? sst_r : p.sst;
+        // :38  nearest lower-left cell, no interpolation
+        const int ind = __double2int_rz(y) * p.nxm1 + __double2int_rz(x);
+        const double2 m = __ldg(&p.field[ind]);
 
-    for (;;) {
-        unsigned act = __ballot_sync(FULL, active);
-        if (TILED && act == 0 && ray >= 0) retire();
-        if (REFILL && more && (TILED ? act == 0 : act != FULL)) {
-            const unsigned idle = ~act;
-            const int leader = __ffs(idle) - 1;
-            const int want = __popc(idle);
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(p.counter, (unsigned long long)want);
-            base = __shfl_sync(FULL, base, leader);
-            if (!active) {
-                const long long r = (long long)base + __popc(idle & ((1u << lane) - 1u));
-                if (r < p.nrays) launch(r);
-            }
-            more = (long long)(base + want) < p.nrays;
-            act = __ballot_sync(FULL, active);
-        }
-        if (act == 0) break;
-
-        if (active) {
-            // sidtracemodule.c:36 -- guard on state i (NaN fails every comparison)
-            const bool in = (i < Lm1) & (x >= 0.0) & (x < p.fx) & (y >= 0.0) & (y < p.fy);
-            if (in) {
-                // :38  nearest lower-left cell, no interpolation
-                const int ind = __double2int_rz(y) * p.nxm1 + __double2int_rz(x);
-                const double2 m = __ldg(&p.field[ind]);
-
-                if (EXTRAS || HIST) {
-                    // state i is a KEPT state (ray.py:99-102 keeps [:n]); close segment (i-1, i)
-                    const double kcur = kmod(kx, ky);
-                    if (i > 0) {
-                        const double kavr = __dmul_rn(__dadd_rn(kprev, kcur), 0.5);   // ray.py:118
-                        const double sk = __dmul_rn(st, kavr);
-                        if (EXTRAS) {
-                            const double lnew = __dadd_rn(lax, sk);                  // :120 cumsum
-                            const double dl = __dsub_rn(lnew, lax);                  // :124 diff
-                            ph = __dadd_rn(ph, __dmul_rn(dl, kavr));                 // :125
-                            lax = lnew;
-                        }
-                        if (HIST) hist_add(sh_hist, binprev, __dmul_rn(a2, sk));
-                    }
-                    kprev = kcur;
-                    if (HIST) {
-                        // flux label of the segment START (oracle_deposit)
-                        const double xp = __dadd_rn(p.xorg, __dmul_rn(x, p.dx));
-                        const double yp = __dadd_rn(p.yorg, __dmul_rn(y, p.dy));
-                        const double rho = __ddiv_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(xp, xp), __dmul_rn(yp, yp))), p.r_lcs);
-                        binprev = -1;
-                        if (rho < p.rho_max) {
-                            const int b = __double2int_rz(__ddiv_rn(__dmul_rn(rho, (double)p.nbins), p.rho_max));
-                            if (b >= 0 && b < p.nbins) binprev = b;
-                        }
-                    }
-                }
-
-                if (CROSS) {
-                    // state i is kept; lax, ph are its running sums
-                    const double c = axis_y ? y0p + (y - yg0) * p.dy : x0p + (x - xg0) * p.dx;
-                    const double d = c - p.cross_val;
-                    if (d == 0.0) {
-                        if (neq == 0) {
-                            cx = x0p + (x - xg0) * p.dx; cy = y0p + (y - yg0) * p.dy;
-                            ckx = kx; cky = ky; clax = lax; cph = ph; cidx = i;
-                        }
-                        ++neq;
-                    }
-                    below |= d < 0.0;
-                    above |= d > 0.0;
-                    if (i > 0 && dprev * d < 0.0) {
-                        if (ncross == 0 && neq == 0) capture_from_prev(st);
-                        ++ncross;
-                    }
-                    pxg = x; pyg = y; pkx = kx; pky = ky; pmx = m.x; pmy = m.y; plax = lax; pph = ph; dprev = d;
-                }
-
-                const double tx = __dmul_rn(__dmul_rn(sst, m.x), 0.5);   // ((st*st)*Mx)/2
-                const double ty = __dmul_rn(__dmul_rn(sst, m.y), 0.5);
-                const double vx = __dadd_rn(tx, __dmul_rn(kx, st));
-                const double vy = __dadd_rn(ty, __dmul_rn(ky, st));
-                const double x1 = __dadd_rn(x, div_const<DIVC>(vx, p.dx, p.rdx));   // :41
-                const double y1 = __dadd_rn(y, div_const<DIVC>(vy, p.dy, p.rdy));   // :42
-                const double kx1 = __dadd_rn(kx, __dmul_rn(st, m.x));               // :44
-                const double ky1 = __dadd_rn(ky, __dmul_rn(st, m.y));               // :45
-
+        if (EXTRAS || HIST) {
+            // state i is a KEPT state (ray.py:99-102 keeps [:n]); close segment (i-1, i)
+            const double kcur = kmod(kx, ky);
+            if (i > 0) {
+                const double kavr = __dmul_rn(__dadd_rn(kprev, kcur), 0.5);   // ray.py:118
+                const double sk = __dmul_rn(st, kavr);
                 if (EXTRAS) {
-                    if (turn < 0 && ((ky > 0.0 && ky1 <= 0.0) || (ky < 0.0 && ky1 >= 0.0))) turn = i + 1;
+                    const double lnew = __dadd_rn(lax, sk);                  // :120 cumsum
+                    const double dl = __dsub_rn(lnew, lax);                  // :124 diff
+                    ph = __dadd_rn(ph, __dmul_rn(dl, kavr));                 // :125
+                    lax = lnew;
                 }
-                x = x1; y = y1; kx = kx1; ky = ky1;
-                ++i;
-                if (TRAJ) {
-                    tp += TILED ? 128 : 4;
-                    st_state(tp, x, y, kx, ky);
+                if (HIST) hist_add(sh_hist, binprev, __dmul_rn(a2, sk));
+            }
+            kprev = kcur;
+            if (HIST) {
+                // flux label of the segment START (oracle_deposit)
+                const double xp = __dadd_rn(p.xorg, __dmul_rn(x, p.dx));
+                const double yp = __dadd_rn(p.yorg, __dmul_rn(y, p.dy));
+                const double rho = __ddiv_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(xp, xp), __dmul_rn(yp, yp))), p.r_lcs);
+                binprev = -1;
+                if (rho < p.rho_max) {
+                    const int b = __double2int_rz(__ddiv_rn(__dmul_rn(rho, (double)p.nbins), p.rho_max));
+                    if (b >= 0 && b < p.nbins) binprev = b;
                 }
-            } else {
-                if (!TILED) retire();
-                active = false;
+            }
+        }
+
+        if (CROSS) {
+            // state i is kept; lax, ph are its running sums
+            const double c = axis_y ? y0p + (y - yg0) * p.dy : x0p + (x - xg0) * p.dx;
+            const double d = c - p.cross_val;
+            if (d == 0.0) {
+                if (neq == 0) {
+                    cx = x0p + (x - xg0) * p.dx; cy = y0p + (y - yg0) * p.dy;
+                    ckx = kx; cky = ky; clax = lax; cph = ph; cidx = i;
+                }
+                ++neq;
+            }
+            below |= d < 0.0;
+            above |= d > 0.0;
+            if (i > 0 && dprev * d < 0.0) {
+                if (ncross == 0 && neq == 0) capture_from_prev(st);
+                ++ncross;
+            }
+            pxg = x; pyg = y; pkx = kx; pky = ky; pmx = m.x; pmy = m.y; plax = lax; pph = ph; dprev = d;
+        }
+
+        const double tx = __dmul_rn(__dmul_rn(sst, m.x), 0.5);   // ((st*st)*Mx)/2
+        const double ty = __dmul_rn(__dmul_rn(sst, m.y), 0.5);
+        const double vx = __dadd_rn(tx, __dmul_rn(kx, st));
+        const double vy = __dadd_rn(ty, __dmul_rn(ky, st));
+        double wx, wy;
+        div_pair<DIVC>(vx, vy, p.dx, p.dy, p.rdx, p.rdy, wx, wy);
+        const double x1 = __dadd_rn(x, wx);                       // :41
+        const double y1 = __dadd_rn(y, wy);                       // :42
+        const double kx1 = __dadd_rn(kx, __dmul_rn(st, m.x));     // :44
+        const double ky1 = __dadd_rn(ky, __dmul_rn(st, m.y));     // :45
+
+        if (EXTRAS) {
+            if (turn < 0 && ((ky > 0.0 && ky1 <= 0.0) || (ky < 0.0 && ky1 >= 0.0))) turn = i + 1;
+        }
+        x = x1; y = y1; kx = kx1; ky = ky1;
+        ++i;
+        if (TRAJ) {
+            tp += TILED ? 128 : 4;
+            st_state(tp, x, y, kx, ky);
+        }
+        return true;
+    };
+
+    if (TILED || !REFILL) {
+        // ---- whole-ray schedules: claim, trace to the end in a plain per-thread loop, retire.
+        // No vote per step: lanes that finish early wait at the reconvergence point after the
+        // inner loop, which for a tile of neighbouring rays costs a few steps.
+        long long r = REFILL ? 0 : (long long)blockIdx.x * kBlock + threadIdx.x;
+        for (;;) {
+            if (REFILL) {   // TILED: one aggregated claim of 32 consecutive rays per warp
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(p.counter, 32ull);
+                base = __shfl_sync(FULL, base, 0);
+                if ((long long)base >= p.nrays) break;
+                r = (long long)base + lane;
+            }
+            const bool has = r < p.nrays;
+            if (has) {
+                launch(r);
+                while (step()) { }
+            }
+            if (TILED) __syncwarp();
+            if (has) retire();
+            if (!REFILL) break;
+        }
+    } else {
+        // ---- ray-granular refill: a lane whose ray ended claims the next one.  The warp votes
+        // once per kBatch steps; idle lanes are refilled with ONE aggregated atomic.
+        constexpr int kBatch = 8;
+        bool active = false, more = true;
+        for (;;) {
+            unsigned act = __ballot_sync(FULL, active);
+            if (more && act != FULL) {
+                const unsigned idle = ~act;
+                const int leader = __ffs(idle) - 1;
+                const int want = __popc(idle);
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(p.counter, (unsigned long long)want);
+                base = __shfl_sync(FULL, base, leader);
+                if (!active) {
+                    const long long r = (long long)base + __popc(idle & ((1u << lane) - 1u));
+                    if (r < p.nrays) { launch(r); active = true; }
+                }
+                more = (long long)(base + want) < p.nrays;
+                act = __ballot_sync(FULL, active);
+            }
+            if (act == 0) break;
+            if (active) {
+#pragma unroll 1
+                for (int s = 0; s < kBatch; ++s) {
+                    if (!step()) { retire(); active = false; break; }
+                }
             }
         }
     }
@@ -364,7 +417,8 @@ trace_kernel(const KParams p)
     }
 }
 
-// {ax, ay} -> interleaved double2 per cell
+// {ax, ay} -> interleaved double2 per cell.  (A 2x4-cell blocked layout was measured and dropped:
+// it did not beat row-major in any mode, profiles/r01/occupancy_layout_sweep.txt.)
 __global__ void interleave_kernel(const double *__restrict__ ax, const double *__restrict__ ay,
                                   double2 *__restrict__ out, long long n)
 {

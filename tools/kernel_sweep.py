@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--nx", type=int, default=1001)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--case", default="beam", choices=["beam", "sweep"])
-    ap.add_argument("--only", default="")
+    ap.add_argument("--only", default="", help="comma-separated substrings; a variant runs if any matches")
     args = ap.parse_args()
     peak = 6533.5
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -42,14 +42,14 @@ def main():
     out = sidtrace.BatchResult(nsteps=torch.empty(n, dtype=torch.int32, device=dev),
                                end_state=torch.empty((4, n), dtype=torch.float64, device=dev))
     variants = []
-    for mode in ("traj-tiled", "traj-ray", "endpoints", "extras"):
+    for mode in ("traj-tiled", "traj-ray", "endpoints", "endpoints-tiled", "extras", "extras-tiled"):
         for refill in (True, False):
             for div_ieee in (False, True):
                 variants.append((mode, refill, div_ieee))
-    print(f"# case {case.name} L={L} peak={peak} GB/s")
+    print(f"# case {case.name} L={L} peak={peak} GB/s lib={os.path.basename(sidtrace._cabi.LIB_PATH)}")
     for mode, refill, div_ieee in variants:
         tag = f"{mode}/{'refill' if refill else 'static'}/{'ieee' if div_ieee else 'divc'}"
-        if args.only and args.only not in tag:
+        if args.only and not any(o in tag for o in args.only.split(",")):
             continue
         o = sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state)
         k = dict(kw, refill=refill, div_ieee=div_ieee)
@@ -59,6 +59,10 @@ def main():
             k.update(traj=buf[: n * L * 4].view(n, L, 4))
         elif mode == "extras":
             k.update(want_extras=True)
+        elif mode == "endpoints-tiled":
+            k.update(tiled=True)
+        elif mode == "extras-tiled":
+            k.update(want_extras=True, tiled=True)
         for _ in range(2):
             sidtrace.trace_batch(field, *d_in, out=o, **k)
         torch.cuda.synchronize()
