@@ -78,8 +78,11 @@ int stb_check(int nx, int ny, int i, int j, const double *a, double *out);
                                          (staged through pinned/HBM workspaces; traj stays a DEVICE pointer) */
 #define STB_F_DIV_IEEE     (1u << 1)  /* use the generic IEEE division (div.rn.f64) instead of the
                                          constant-divisor correctly-rounded sequence; both are bit-exact */
-#define STB_F_NO_REFILL    (1u << 2)  /* static one-thread-per-ray grid instead of the persistent
-                                         warp-refill scheduler */
+#define STB_F_REFILL        (1u << 2)  /* persistent grid: warps claim rays from a global queue (a lane whose
+                                         ray ended is refilled; with STB_F_TRAJ_TILED a whole 32-ray tile at a
+                                         time) instead of the static one-thread-per-ray grid.  Pays off when a
+                                         few rays run 10-100x longer than the rest (trapped rays); for beams
+                                         and moderate cutoff sweeps the static grid measured faster */
 #define STB_F_TRAJ_HOST    (1u << 3)  /* traj is a HOST pointer (copied back after the launch) */
 #define STB_F_TRAJ_TILED   (1u << 4)  /* warp-tile schedule: a warp owns tile = ray/32 (lane = ray%32) until all
                                          32 rays ended.  traj (if any) is laid out [tile][step][32][4],

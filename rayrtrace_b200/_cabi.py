@@ -18,7 +18,7 @@ STB_ERR_ARG, STB_ERR_CUDA, STB_ERR_NOMEM, STB_ERR_RANGE = -1, -2, -3, -4
 
 F_HOST_IO = 1 << 0
 F_DIV_IEEE = 1 << 1
-F_NO_REFILL = 1 << 2
+F_REFILL = 1 << 2
 F_TRAJ_HOST = 1 << 3
 F_TRAJ_TILED = 1 << 4
 

@@ -363,7 +363,7 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
     bool divc = false;
     int rc = fill_params(f, b, p, divc);
     if (rc != STB_OK) return rc;
-    const bool refill = !(b->flags & STB_F_NO_REFILL);
+    const bool refill = b->flags & STB_F_REFILL;
     const bool host_io = b->flags & STB_F_HOST_IO;
     const bool traj_host = b->flags & STB_F_TRAJ_HOST;
     const bool tiled = b->flags & STB_F_TRAJ_TILED;

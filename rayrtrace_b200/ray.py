@@ -114,6 +114,64 @@ class Ray:
         return np.cumsum(np.insert(dl * kavr, 0, 0))
 
 
+    # ray.py:131-224
+    def addpoint(self, val, axis="y"):
+        """Insert the exact point(s) where the ray crosses the line ``y = val`` (or ``x = val``)
+        and return their indices, with the reference's semantics (ray.py:131-224):
+
+        * ``val`` already among the coordinates -> indices of those points, nothing inserted;
+        * sign changes of ``coord - val`` -> one inserted point per crossing segment, found by
+          solving ``k*s + a*s**2/2 = val - coord`` with the constant acceleration of the
+          segment's start cell (smallest non-negative root, small-``a`` fallback);
+        * no crossing but the last point is heading for the line -> extrapolated point appended;
+        * otherwise ``nan``.
+        The arrays ``x, y, kx, ky, st`` are updated in place of the old ones.  (The fused device
+        version, ``trace_batch(cross=...)``, reports the first crossing without materialising rays.)"""
+        c = self.y if axis == "y" else self.x
+        kc_end = self.ky[-1] if axis == "y" else self.kx[-1]
+        d = c - val
+        if np.any(d == 0):
+            return np.flatnonzero(d == 0)
+        if np.any(d < 0) and np.any(d > 0):
+            seg = np.flatnonzero(d[:-1] * d[1:] < 0)
+        elif (val - c[-1]) * kc_end > 0:
+            seg = np.array([len(c) - 1])
+        else:
+            return np.nan
+
+        nf = self.n_field
+        xi = np.trunc(nf.x2grid(self.x[seg])).astype(int)
+        yi = np.trunc(nf.y2grid(self.y[seg])).astype(int)
+        acc_x, acc_y = nf.ax[yi, xi], nf.ay[yi, xi]
+        start = [np.array(a[seg]) for a in (self.x, self.y, self.kx, self.ky, self.st)]
+        inserted = []
+        shift = 0
+        for xx, yy, kx, ky, st1, ax, ay, ind in zip(*start, acc_x, acc_y, seg):
+            c0, k, a = (yy, ky, ay) if axis == "y" else (xx, kx, ax)
+            s = st1
+            if a != 0:
+                sq = np.sqrt(k ** 2 + 2 * a * (val - c0))
+                roots = np.array(((-k - sq) / a, (-k + sq) / a))
+                s = roots[roots >= 0].min()
+                if s == 0 and val != c0 and k != 0:     # tiny |a|: the non-zero root can be lost
+                    s = (val - c0) / k
+            elif k != 0:
+                s = (val - c0) / k
+            if s == 0:
+                continue
+            at = ind + shift + 1
+            inserted.append(at)
+            if s != st1:
+                self.st[at - 1] = s
+                self.st = np.insert(self.st, at, st1 - s if at != len(self.x) else 0)
+                self.kx = np.insert(self.kx, at, kx + ax * s)
+                self.ky = np.insert(self.ky, at, ky + ay * s)
+                self.x = np.insert(self.x, at, xx + kx * s + ax / 2 * s ** 2)
+                self.y = np.insert(self.y, at, yy + ky * s + ay / 2 * s ** 2)
+                shift += 1
+        return np.array(inserted, dtype=int)
+
+
 # --------------------------------------------------------------------------
 @dataclass
 class RayBundle:

@@ -27,7 +27,7 @@ from typing import Optional
 import numpy as np
 
 from . import _cabi
-from ._cabi import (F_DIV_IEEE, F_HOST_IO, F_NO_REFILL, F_TRAJ_HOST, F_TRAJ_TILED, SidtraceError, StbBatch, lib)
+from ._cabi import (F_DIV_IEEE, F_HOST_IO, F_REFILL, F_TRAJ_HOST, F_TRAJ_TILED, SidtraceError, StbBatch, lib)
 
 __all__ = ["trace", "check", "trace_batch", "Field", "BatchResult", "invalidate", "pinned_empty", "pinned_copy",
            "SidtraceError"]
@@ -274,7 +274,7 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
                 st_ray=None, traj=None, want_end: bool = True, want_extras: bool = False,
                 hist=None, nbins: int = 0, amp=None, xorg: float = 0.0, yorg: float = 0.0,
                 r_lcs: float = 1.0, rho_max: float = 1.0, traj_host: bool = False,
-                div_ieee: bool = False, refill: bool = True, tiled: bool = False,
+                div_ieee: bool = False, refill: bool = False, tiled: bool = False,
                 cross=None, x0_phys=None, y0_phys=None,
                 out: Optional[BatchResult] = None, stream=None) -> BatchResult:
     """Trace ``len(x0)`` rays in one launch.
@@ -287,6 +287,9 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     traj: None -> no trajectories; True -> allocate a zeroed [nrays, L, 4] CUDA
     tensor; or a preallocated CUDA tensor of that shape (32-byte aligned).
     With ``traj_host=True`` and host I/O, a numpy [nrays, L, 4] array.
+    refill: persistent grid whose warps claim rays from a global queue (lane-granular, or
+    tile-granular with ``tiled``) instead of the static one-thread-per-ray grid; worth it when a
+    few rays run 10-100x longer than the rest (trapped rays).
     cross: (val, axis) with axis 'y' or 'x' -- fused receiver-line crossing with the semantics of
     the reference's Ray.addpoint (ray.py:131-224); needs the physical launch points
     x0_phys, y0_phys; fills cross_count / cross_index / cross_flags / cross_state.
@@ -358,8 +361,8 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
         flags |= F_HOST_IO
     if div_ieee:
         flags |= F_DIV_IEEE
-    if not refill:
-        flags |= F_NO_REFILL
+    if refill:
+        flags |= F_REFILL
 
     tshape = ((n + 31) // 32, L, 32, 4) if tiled else (n, L, 4)
     if tiled:

@@ -40,3 +40,8 @@ def oracle_mod():
 @pytest.fixture(scope="session")
 def ft2_cross():
     return np.load(os.path.join(GOLDEN, "ft2_cross.npz"))
+
+
+@pytest.fixture(scope="session")
+def beam_fix():
+    return np.load(os.path.join(GOLDEN, "beam.npz"))

@@ -205,6 +205,42 @@ def make_ft2_cross(den, ray):
           "multi", [int((res[li, :, 0] > 1).sum()) for li in range(len(lines))])
 
 
+def make_beam(den):
+    """Reference Beam (beam.py) on the FT-2 profile: launch conditions (Beam.rays, beam.py:278-344),
+    field on the receiver line (Beam.field_r, beam.py:347-444) and the interferometer signal
+    (field_result, beam.py:447-472).  The wavefront interpolant is handed to the reference
+    explicitly (its own finder needs skimage): it is the product's Newton-solved iso-phase line,
+    stored here so the test rebuilds the identical interp1d."""
+    import beam as refbeam
+    from scipy.interpolate import interp1d
+    from rayrtrace_b200.beam import Beam as PBeam
+    from rayrtrace_b200.nfield import Nfield as PNfield
+    nx, n0 = 201, 4e13
+    n, x, y = ft2_density(nx, n0)
+    nf = den.Nfield(n, x=x, y=y)
+    x0 = 2.3
+    y0 = -np.sqrt(100 - x0 ** 2)                      # antenna on the r = 10 cm circle (ft2.py:12-16)
+    pb = PBeam(x0=x0, y0=y0, kx0=0, ky0=1)
+    wf = pb.wavefront_r(dist=3, ampbnd=1e-3, n_field=PNfield(n, x=x, y=y))
+    rnum = 101
+    tx = refbeam.Beam(x0=x0, y0=y0, kx0=0, ky0=1)
+    rx = refbeam.Beam(x0=x0, y0=-y0, kx0=0, ky0=-1)
+    lx, ly, lkx, lky, amps, phase, dist = tx.rays(rnum=rnum, wave_front=interp1d(wf.x, wf.y, kind="cubic"),
+                                                  dist=3, ampbnd=1e-3, n_field=nf)
+    nkept = np.array([len(r.x) for r in tx._rays])
+    field, xo, x_max, ph_max, signal, props = refbeam.field_result(tx, rx)
+    # analytic pieces at a few points
+    px = np.linspace(-1.5, 4.0, 7); py = np.linspace(-9.0, -4.0, 7)
+    fs = tx.field(x=px, y=py, n=0.97, outfmt="dict")
+    np.savez_compressed(os.path.join(HERE, "beam.npz"), nx=np.int64(nx), n0=n0, x0=x0, y0=y0, rnum=np.int64(rnum),
+                        wf_x=wf.x, wf_y=wf.y, launch=np.stack([lx, ly, lkx, lky, amps, phase]), nkept=nkept,
+                        field=field, xout=xo, x_max=x_max, ph_max=np.float64(ph_max), signal=np.complex128(signal),
+                        props=np.array(props if props is not None else [np.nan] * 3),
+                        probe_x=px, probe_y=py, probe_field=fs["field"], probe_amp=fs["amp"], probe_phase=fs["phase"],
+                        wave_len=tx.wave_len, rayleigh=tx.rayleigh_len(n=0.97))
+    print("beam: rays kept", len(tx._rays), "of", rnum, "signal", signal, "ph_max", float(ph_max))
+
+
 if __name__ == "__main__":
     if not oracle.have_ref():
         oracle.build(ref=True)
@@ -213,5 +249,6 @@ if __name__ == "__main__":
     make_ft2_ray(den, ray)
     make_ft2_fan(den)
     make_ft2_cross(den, ray)
-    for f in ("kat.npz", "ft2_ray.npz", "ft2_fan.npz", "ft2_cross.npz"):
+    make_beam(den)
+    for f in ("kat.npz", "ft2_ray.npz", "ft2_fan.npz", "ft2_cross.npz", "beam.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

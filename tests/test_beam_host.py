@@ -1,0 +1,98 @@
+"""Host-side mirror of the reference's Beam / Ray.addpoint against fixtures
+produced by the unmodified beam.py / ray.py (tests/golden/beam.npz, ft2_cross.npz).  No GPU."""
+import numpy as np
+import pytest
+from scipy.interpolate import interp1d
+
+from _util import ft2_density
+from rayrtrace_b200.nfield import Nfield
+
+
+def _beam(beam_fix, **kw):
+    from rayrtrace_b200.beam import Beam
+    return Beam(x0=float(beam_fix["x0"]), y0=float(beam_fix["y0"]), kx0=0, ky0=1, **kw)
+
+
+def test_analytic_gaussian_beam_matches_reference(beam_fix):
+    b = _beam(beam_fix)
+    assert b.wave_len == float(beam_fix["wave_len"])
+    assert b.rayleigh_len(n=0.97) == float(beam_fix["rayleigh"])
+    fs = b.field(x=beam_fix["probe_x"], y=beam_fix["probe_y"], n=0.97, outfmt="dict")
+    assert fs["amp"].tobytes() == beam_fix["probe_amp"].tobytes()
+    assert fs["phase"].tobytes() == beam_fix["probe_phase"].tobytes()
+    assert fs["field"].tobytes() == beam_fix["probe_field"].tobytes()
+    xb, yb = b.lab2beam(1.0, -7.0)
+    xl, yl = b.beam2lab(xb, yb)
+    assert (xl, yl) == pytest.approx((1.0, -7.0), abs=1e-15)
+
+
+def test_wavefront_is_an_iso_phase_line(beam_fix):
+    """The Newton-solved front (replacement of skimage.find_contours, beam.py:238) has constant
+    phase to 1e-9 rad, passes through (0, dist) and reproduces the stored samples."""
+    n, x, y = ft2_density(int(beam_fix["nx"]), float(beam_fix["n0"]))
+    nf = Nfield(n, x=x, y=y)
+    b = _beam(beam_fix)
+    wf = b.wavefront_r(dist=3, ampbnd=1e-3, n_field=nf)
+    np.testing.assert_allclose(wf.x, beam_fix["wf_x"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(wf.y, beam_fix["wf_y"], rtol=0, atol=1e-12)
+    ne = nf.refractive_index(freq=b.freq)
+    ph = b._field(wf.x, wf.y, n=ne, outfmt="dict")["phase"]
+    assert np.ptp(ph) < 1e-9
+    mid = len(wf.x) // 2
+    assert abs(wf.y[mid] - 3) < b.wave_len          # nearest whole-period front to dist = 3 (beam.py:263-272)
+    assert abs(ph[mid] / 2 / np.pi - round(ph[mid] / 2 / np.pi)) < 1e-6
+
+
+def test_launch_conditions_match_reference_beam_rays(beam_fix):
+    n, x, y = ft2_density(int(beam_fix["nx"]), float(beam_fix["n0"]))
+    nf = Nfield(n, x=x, y=y)
+    b = _beam(beam_fix)
+    wf = interp1d(beam_fix["wf_x"], beam_fix["wf_y"], kind="cubic")
+    got = b.launch_conditions(int(beam_fix["rnum"]), wf, nf.refractive_index(freq=b.freq))
+    want = beam_fix["launch"]
+    for g, w, name in zip(got, want, ("x", "y", "kx", "ky", "amp", "phase")):
+        np.testing.assert_allclose(g, w, rtol=1e-13, atol=1e-13, err_msg=name)
+
+
+def _host_ray(oracle_mod, nf, launch, x0, y0, L=4096):
+    """A product Ray filled from an ORACLE trajectory (test only: no GPU here)."""
+    from rayrtrace_b200.ray import Ray
+    tr = oracle_mod.trace_batch(*[np.array([v]) for v in launch], L, nf.st, nf.dx[0], nf.dy[0], nf.nx, nf.ny, nf.ax, nf.ay)
+    k = int(tr["nsteps"][0])
+    t = tr["traj"][0, :k]
+    r = Ray.__new__(Ray)
+    r.n_field, r.amp, r.freq = nf, 1.0, 136.268e9
+    r.x = x0 + (t[:, 0] - t[0, 0]) * nf.dx[0]
+    r.y = y0 + (t[:, 1] - t[0, 1]) * nf.dy[0]
+    r.kx, r.ky = t[:, 2].copy(), t[:, 3].copy()
+    r.st = np.full_like(r.x, nf.st)
+    r.st[-1] = 0
+    return r
+
+
+def test_ray_addpoint_matches_reference(oracle_mod, ft2_cross):
+    """rayrtrace_b200.ray.Ray.addpoint against what the reference's Ray.addpoint returned."""
+    n, x, y = ft2_density(int(ft2_cross["nx"]), float(ft2_cross["n0"]))
+    nf = Nfield(n, x=x, y=y)
+    res = ft2_cross["res"]
+    checked = 0
+    for li, (val, axis) in enumerate(zip(ft2_cross["line_val"], ft2_cross["line_axis"])):
+        for r in range(0, ft2_cross["launch"].shape[0], 2):
+            ray = _host_ray(oracle_mod, nf, ft2_cross["launch"][r], ft2_cross["x0"][r], ft2_cross["y0"][r])
+            n0 = len(ray.x)
+            want = res[li, r]
+            if want[8] == 1:                             # the reference raised (no non-negative root)
+                with pytest.raises(ValueError):
+                    ray.addpoint(float(val), axis=str(axis))
+                continue
+            ind = ray.addpoint(float(val), axis=str(axis))
+            if want[0] == 0:
+                assert not hasattr(ind, "__len__") or len(ind) == 0
+                continue
+            assert len(ind) == int(want[0]) and int(ind[0]) == int(want[1])
+            assert len(ray.x) == n0 + len(ind) == len(ray.st) == len(ray.kx)
+            i = int(ind[0])
+            np.testing.assert_allclose([ray.x[i], ray.y[i], ray.kx[i], ray.ky[i], ray.lax[i], ray.ph[i]], want[2:8],
+                                       rtol=1e-11, atol=1e-11)
+            checked += 1
+    assert checked > 40

@@ -427,3 +427,33 @@ def test_receiver_crossing_vs_oracle_random(st, oracle_mod):
                                            rtol=1e-9, atol=1e-9)
         assert nhit > 20 or val == 100.0
     f.close()
+
+
+def test_beam_field_result_matches_reference(st, beam_fix):
+    """the product's Beam (one batched launch instead of the serial Ray loop,
+    beam.py:340-342) followed by field_r / field_result reproduces the reference's interferometer
+    signal for a TX/RX antenna pair on the FT-2 profile.  Tolerance 1e-9 relative: the launch
+    refractive index and addpoint's squares are tolerance-level paths (see test_nfield, oracle/crossing.py)."""
+    from scipy.interpolate import interp1d
+    from rayrtrace_b200.beam import Beam, field_result
+    from rayrtrace_b200.nfield import Nfield
+    n, x, y = ft2_density(int(beam_fix["nx"]), float(beam_fix["n0"]))
+    nf = Nfield(n, x=x, y=y)
+    x0, y0 = float(beam_fix["x0"]), float(beam_fix["y0"])
+    tx = Beam(x0=x0, y0=y0, kx0=0, ky0=1)
+    rx = Beam(x0=x0, y0=-y0, kx0=0, ky0=-1)
+    wf = interp1d(beam_fix["wf_x"], beam_fix["wf_y"], kind="cubic")
+    out = tx.rays(rnum=int(beam_fix["rnum"]), wave_front=wf, dist=3, ampbnd=1e-3, n_field=nf)
+    np.testing.assert_allclose(np.stack(out[:6]), beam_fix["launch"], rtol=1e-13, atol=1e-13)
+    assert np.array_equal(tx.bundle.nsteps, beam_fix["nkept"])
+    # the fused device crossing agrees with the host addpoint on the receiver line
+    b2 = Beam(x0=x0, y0=y0, kx0=0, ky0=1)
+    b2.rays(rnum=int(beam_fix["rnum"]), wave_front=wf, dist=3, ampbnd=1e-3, n_field=nf, receiver=(-y0, "y"))
+    field, xo, x_max, ph_max, signal, props = field_result(tx, rx)
+    hit = b2.bundle.result.cross_count == 1
+    np.testing.assert_allclose(np.sort(b2.bundle.result.cross_state[0][hit]), xo, rtol=1e-9)
+    np.testing.assert_allclose(xo, beam_fix["xout"], rtol=1e-9)
+    np.testing.assert_allclose(field, beam_fix["field"], rtol=1e-7, atol=1e-9)
+    assert abs(signal - complex(beam_fix["signal"])) < 1e-7 * abs(complex(beam_fix["signal"]))
+    assert float(ph_max) == pytest.approx(float(beam_fix["ph_max"]), rel=1e-9)
+    assert x_max == pytest.approx(float(beam_fix["x_max"]), rel=1e-8, abs=1e-9)
