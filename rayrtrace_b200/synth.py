@@ -131,3 +131,33 @@ def sweep_case(nx=201, nrays=100_000, *, seed=0, L=None) -> BeamCase:
     return BeamCase(nfield=nf, launch=(xg, yg, kxs, kys), amp=np.ones(nrays), x0=xs, y0=ys, nrays=nrays,
                     L=L or 4 * default_cap(nx), st=float(nf.st), dx=float(nf.dx[0]), dy=float(nf.dy[0]), freq=freq,
                     name=f"cutoff-sweep-{nrays}rays-{nx}x{nx}")
+
+
+def trapped_case(nx=257, nrays=500_000, *, seed=0, L=8192, trapped_frac=0.03) -> BeamCase:
+    """Heavy-tailed step counts (the stand-in for north_star's "resonance-heavy" rays):
+    an over-dense ring around a hollow core is a closed cavity.  Most rays are launched outside
+    and leave after ~nx steps; a few per cent start inside the cavity and bounce between its
+    walls for thousands of steps (until the scheme's numerical heating lets them over the
+    barrier, ~15-20x the typical ray)."""
+    half = 10.0
+    x = np.linspace(-half, half, nx)
+    y = np.linspace(-half, half, nx)
+    X, Y = np.meshgrid(x, y)
+    r = np.sqrt(X ** 2 + Y ** 2)
+    n = 4.0e14 * np.exp(-((r - 6.0) / 2.5) ** 2) + 1e12     # over-dense ring (n_c = 2.3e14), hollow core: a closed cavity
+    nf = Nfield(n, x=x, y=y)
+    rng = np.random.default_rng(seed)
+    ntr = int(nrays * trapped_frac)
+    xs = rng.uniform(-7.5, 7.5, nrays)
+    ys = np.full(nrays, -9.5)
+    ang = rng.uniform(-0.3, 0.3, nrays)
+    # trapped population: start near the axis of the hollow, any direction
+    idx = rng.choice(nrays, ntr, replace=False)
+    rr = rng.uniform(0.0, 2.5, ntr)
+    th = rng.uniform(0, 2 * np.pi, ntr)
+    xs[idx], ys[idx] = rr * np.cos(th), rr * np.sin(th)
+    ang[idx] = rng.uniform(0, 2 * np.pi, ntr)
+    xg, yg, kxs, kys, freq = launch_states(nf, xs, ys, np.sin(ang), np.cos(ang), BEAM_FREQ)
+    return BeamCase(nfield=nf, launch=(xg, yg, kxs, kys), amp=np.ones(nrays), x0=xs, y0=ys, nrays=nrays,
+                    L=L, st=float(nf.st), dx=float(nf.dx[0]), dy=float(nf.dy[0]), freq=freq,
+                    name=f"trapped-{nrays}rays-{nx}x{nx}")

@@ -23,14 +23,14 @@ def main():
     ap.add_argument("--nrays", type=int, default=1_000_000)
     ap.add_argument("--nx", type=int, default=1001)
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--case", default="beam", choices=["beam", "sweep"])
+    ap.add_argument("--case", default="beam", choices=["beam", "sweep", "trapped"])
     ap.add_argument("--only", default="", help="comma-separated substrings; a variant runs if any matches")
     args = ap.parse_args()
     peak = 6533.5
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         peak = float(json.load(open(p))["hbm_gbs"])
-    case = synth.beam_case(nx=args.nx, nrays=args.nrays) if args.case == "beam" else synth.sweep_case(nx=args.nx, nrays=args.nrays)
+    case = {"beam": synth.beam_case, "sweep": synth.sweep_case, "trapped": synth.trapped_case}[args.case](nx=args.nx, nrays=args.nrays)
     dev = torch.device("cuda", 0)
     nf = case.nfield
     field = sidtrace.Field(np.ascontiguousarray(nf.ax), np.ascontiguousarray(nf.ay), nf.nx, nf.ny)
@@ -47,6 +47,7 @@ def main():
             for div_ieee in (False, True):
                 variants.append((mode, refill, div_ieee))
     print(f"# case {case.name} L={L} peak={peak} GB/s lib={os.path.basename(sidtrace._cabi.LIB_PATH)}")
+    first = True
     for mode, refill, div_ieee in variants:
         tag = f"{mode}/{'refill' if refill else 'static'}/{'ieee' if div_ieee else 'divc'}"
         if args.only and not any(o in tag for o in args.only.split(",")):
@@ -75,6 +76,10 @@ def main():
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         steps = int(o.nsteps.sum().item())
+        if first:
+            ns = o.nsteps.cpu().numpy()
+            print(f"# steps/ray: median {int(np.median(ns))} mean {ns.mean():.0f} p99 {int(np.percentile(ns, 99))} max {ns.max()} capped {(ns == L - 1).mean():.4f}")
+            first = False
         ms = float(np.median(ts))
         rate = steps / (ms * 1e-3)
         frac = rate * 32 / 1e9 / peak
