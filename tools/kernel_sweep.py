@@ -37,7 +37,7 @@ def main():
     d_in = [torch.from_numpy(a).to(dev) for a in case.launch]
     n, L = case.nrays, case.L
     nt = (n + 31) // 32
-    buf = torch.empty(nt * 32 * L * 4, dtype=torch.float64, device=dev)
+    buf = None   # trajectory arena, allocated when a trajectory variant is selected
     kw = dict(L=L, st=case.st, dx=case.dx, dy=case.dy)
     out = sidtrace.BatchResult(nsteps=torch.empty(n, dtype=torch.int32, device=dev),
                                end_state=torch.empty((4, n), dtype=torch.float64, device=dev))
@@ -54,6 +54,8 @@ def main():
             continue
         o = sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state)
         k = dict(kw, refill=refill, div_ieee=div_ieee)
+        if mode.startswith("traj") and buf is None:
+            buf = torch.empty(nt * 32 * L * 4, dtype=torch.float64, device=dev)
         if mode == "traj-tiled":
             k.update(traj=buf[: nt * L * 128].view(nt, L, 32, 4), tiled=True)
         elif mode == "traj-ray":
