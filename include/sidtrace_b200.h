@@ -78,11 +78,14 @@ int stb_check(int nx, int ny, int i, int j, const double *a, double *out);
                                          (staged through pinned/HBM workspaces; traj stays a DEVICE pointer) */
 #define STB_F_DIV_IEEE     (1u << 1)  /* use the generic IEEE division (div.rn.f64) instead of the
                                          constant-divisor correctly-rounded sequence; both are bit-exact */
-#define STB_F_REFILL        (1u << 2)  /* persistent grid: warps claim rays from a global queue (a lane whose
-                                         ray ended is refilled; with STB_F_TRAJ_TILED a whole 32-ray tile at a
-                                         time) instead of the static one-thread-per-ray grid.  Pays off when a
-                                         few rays run 10-100x longer than the rest (trapped rays); for beams
-                                         and moderate cutoff sweeps the static grid measured faster */
+#define STB_F_REFILL        (1u << 2)  /* force the persistent grid: warps claim rays from a global queue (a lane
+                                         whose ray ended is refilled at once; with STB_F_TRAJ_TILED a whole
+                                         32-ray tile at a time) */
+#define STB_F_STATIC        (1u << 5)  /* force the static one-thread-per-ray grid.  With neither flag the
+                                         library picks: static for tiled trajectories (lock-step rows), lane
+                                         refill otherwise -- refill costs <= 20 % on a clean beam but is 3-5x
+                                         faster when a few rays run 10-100x longer than the rest (trapped
+                                         rays; profiles/r01/kernel_sweep_trapped.txt) */
 #define STB_F_TRAJ_HOST    (1u << 3)  /* traj is a HOST pointer (copied back after the launch) */
 #define STB_F_TRAJ_TILED   (1u << 4)  /* warp-tile schedule: a warp owns tile = ray/32 (lane = ray%32) until all
                                          32 rays ended.  traj (if any) is laid out [tile][step][32][4],
@@ -107,6 +110,8 @@ typedef struct stb_batch_s {
     double  *traj;            /* [ray][step][4] = (x, y, kx, ky); states 0..i written, rest      */
                               /* untouched (sidtracemodule.c:36-48)                              */
     int64_t  traj_ray_stride; /* in doubles, >= 4*L, multiple of 4 (0 -> 4*L)                    */
+    int32_t  traj_tile;       /* STB_F_TRAJ_TILED: rays per tile, 32 / 64 / 128 (0 -> 32): layout    */
+                              /* [ray/tile][step][ray%tile][4]; a 128-ray tile = one CTA = 4 KB rows */
     int32_t *nsteps;          /* [ray] i = steps taken = index of last written state            */
     double  *end_state;       /* [4][nrays] state at index i                                     */
 

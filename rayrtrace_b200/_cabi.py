@@ -21,6 +21,7 @@ F_DIV_IEEE = 1 << 1
 F_REFILL = 1 << 2
 F_TRAJ_HOST = 1 << 3
 F_TRAJ_TILED = 1 << 4
+F_STATIC = 1 << 5
 
 # every symbol include/sidtrace_b200.h declares (tests check the .so exports them all)
 EXPORTS = (
@@ -44,6 +45,7 @@ class StbBatch(Structure):
         ("dx", c_double), ("dy", c_double),
         ("traj", c_void_p),
         ("traj_ray_stride", c_int64),
+        ("traj_tile", c_int32),
         ("nsteps", c_void_p),
         ("end_state", c_void_p),
         ("turn_index", c_void_p),

@@ -331,6 +331,9 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     p.st = b->st; p.sst = b->st * b->st; p.st_ray = b->st_ray;
     p.dx = b->dx; p.dy = b->dy; p.rdx = 1.0 / b->dx; p.rdy = 1.0 / b->dy;
     p.traj = b->traj; p.stride = stride;
+    p.tile = b->traj_tile ? b->traj_tile : 32;
+    if (p.tile != 32 && p.tile != 64 && p.tile != 128)
+        return fail(STB_ERR_ARG, "stb_trace_batch: traj_tile must be 32, 64 or 128 (got %d)", b->traj_tile);
     p.nsteps = b->nsteps; p.endst = b->end_state;
     p.turn = b->turn_index; p.lax_end = b->lax_end; p.ph_end = b->ph_end;
     p.hist = b->hist; p.nbins = b->nbins; p.amp = b->amp;
@@ -363,7 +366,9 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
     bool divc = false;
     int rc = fill_params(f, b, p, divc);
     if (rc != STB_OK) return rc;
-    const bool refill = b->flags & STB_F_REFILL;
+    const bool tiled_ = b->flags & STB_F_TRAJ_TILED;
+    if ((b->flags & STB_F_REFILL) && (b->flags & STB_F_STATIC)) return fail(STB_ERR_ARG, "STB_F_REFILL and STB_F_STATIC are mutually exclusive");
+    const bool refill = (b->flags & STB_F_REFILL) ? true : (b->flags & STB_F_STATIC) ? false : !tiled_;
     const bool host_io = b->flags & STB_F_HOST_IO;
     const bool traj_host = b->flags & STB_F_TRAJ_HOST;
     const bool tiled = b->flags & STB_F_TRAJ_TILED;

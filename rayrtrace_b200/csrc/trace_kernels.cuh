@@ -48,7 +48,8 @@ struct KParams {
     const double *st_ray;
     double dx, dy, rdx, rdy;
     double *traj;
-    long long stride;                    // doubles per ray
+    long long stride;                    // doubles per ray (ray-major layout)
+    int tile;                            // rays per tile (tiled layout): 32, 64 or 128
     int *nsteps;
     double *endst;
     int *turn;
@@ -205,7 +206,7 @@ trace_kernel(const KParams p)
         if (STRAY && p.st_ray) { st_r = p.st_ray[r]; sst_r = __dmul_rn(st_r, st_r); }
         i = 0;
         if (TRAJ) {
-            tp = TILED ? p.traj + ((r >> 5) * (long long)p.L * 32 + (r & 31)) * 4
+            tp = TILED ? p.traj + ((r / p.tile) * (long long)p.L * p.tile + (r % p.tile)) * 4
                        : p.traj + r * p.stride;
             st_state(tp, x, y, kx, ky);
         }
@@ -349,7 +350,7 @@ trace_kernel(const KParams p)
         x = x1; y = y1; kx = kx1; ky = ky1;
         ++i;
         if (TRAJ) {
-            tp += TILED ? 128 : 4;
+            tp += TILED ? 4 * p.tile : 4;
             st_state(tp, x, y, kx, ky);
         }
         return true;

@@ -27,7 +27,7 @@ from typing import Optional
 import numpy as np
 
 from . import _cabi
-from ._cabi import (F_DIV_IEEE, F_HOST_IO, F_REFILL, F_TRAJ_HOST, F_TRAJ_TILED, SidtraceError, StbBatch, lib)
+from ._cabi import (F_DIV_IEEE, F_HOST_IO, F_REFILL, F_STATIC, F_TRAJ_HOST, F_TRAJ_TILED, SidtraceError, StbBatch, lib)
 
 __all__ = ["trace", "check", "trace_batch", "Field", "BatchResult", "invalidate", "pinned_empty", "pinned_copy",
            "SidtraceError"]
@@ -237,7 +237,7 @@ class BatchResult:
     cross_index: object = None  # int32 [nrays]   index Ray.addpoint would return for the first one
     cross_flags: object = None  # int32 [nrays]   bit 0 exact hit, bit 1 extrapolated past the end
     cross_state: object = None  # float64 [6, nrays]  x, y (cm), kx, ky, lax, ph at the first crossing
-    tiled: bool = False         # traj is [ntiles, L, 32, 4] (tile = ray // 32, lane = ray % 32)
+    tiled: bool = False         # traj is [ntiles, L, T, 4] (tile = ray // T, slot = ray % T; T = 32, 64 or 128)
 
     def ray_states(self, r: int, n: Optional[int] = None):
         """View [n, 4] of the first n states (default nsteps[r], the part the reference's
@@ -245,7 +245,8 @@ class BatchResult:
         if n is None:
             n = int(self.nsteps[r])
         if self.tiled:
-            return self.traj[r >> 5, :n, r & 31, :]
+            t = self.traj.shape[2]
+            return self.traj[r // t, :n, r % t, :]
         return self.traj[r, :n]
 
     def ray(self, r: int):
@@ -257,9 +258,9 @@ class BatchResult:
         """The trajectories as a [nrays, L, 4] tensor (a copy when the layout is tiled)."""
         if not self.tiled:
             return self.traj
-        nt, L = self.traj.shape[0], self.traj.shape[1]
+        nt, L, t = self.traj.shape[0], self.traj.shape[1], self.traj.shape[2]
         n = int(self.nsteps.shape[0])
-        return self.traj.permute(0, 2, 1, 3).reshape(nt * 32, L, 4)[:n]
+        return self.traj.permute(0, 2, 1, 3).reshape(nt * t, L, 4)[:n]
 
 
 def _ptr(a):
@@ -274,7 +275,7 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
                 st_ray=None, traj=None, want_end: bool = True, want_extras: bool = False,
                 hist=None, nbins: int = 0, amp=None, xorg: float = 0.0, yorg: float = 0.0,
                 r_lcs: float = 1.0, rho_max: float = 1.0, traj_host: bool = False,
-                div_ieee: bool = False, refill: bool = False, tiled: bool = False,
+                div_ieee: bool = False, refill: Optional[bool] = None, tiled: bool = False, tile: int = 32,
                 cross=None, x0_phys=None, y0_phys=None,
                 out: Optional[BatchResult] = None, stream=None) -> BatchResult:
     """Trace ``len(x0)`` rays in one launch.
@@ -287,9 +288,10 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     traj: None -> no trajectories; True -> allocate a zeroed [nrays, L, 4] CUDA
     tensor; or a preallocated CUDA tensor of that shape (32-byte aligned).
     With ``traj_host=True`` and host I/O, a numpy [nrays, L, 4] array.
-    refill: persistent grid whose warps claim rays from a global queue (lane-granular, or
-    tile-granular with ``tiled``) instead of the static one-thread-per-ray grid; worth it when a
-    few rays run 10-100x longer than the rest (trapped rays).
+    refill: True -> persistent grid whose warps claim rays from a global queue (lane-granular, or
+    tile-granular with ``tiled``); False -> static one-thread-per-ray grid; None -> the library
+    picks (static for tiled trajectories, lane refill otherwise: refill costs <= 20 % on a clean
+    beam and wins 3-5x when a few rays run 10-100x longer than the rest).
     cross: (val, axis) with axis 'y' or 'x' -- fused receiver-line crossing with the semantics of
     the reference's Ray.addpoint (ray.py:131-224); needs the physical launch points
     x0_phys, y0_phys; fills cross_count / cross_index / cross_flags / cross_state.
@@ -361,10 +363,13 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
         flags |= F_HOST_IO
     if div_ieee:
         flags |= F_DIV_IEEE
-    if refill:
-        flags |= F_REFILL
+    if refill is not None:
+        flags |= F_REFILL if refill else F_STATIC
 
-    tshape = ((n + 31) // 32, L, 32, 4) if tiled else (n, L, 4)
+    tile = int(tile)
+    if tile not in (32, 64, 128):
+        raise ValueError('tile must be 32, 64 or 128')
+    tshape = ((n + tile - 1) // tile, L, tile, 4) if tiled else (n, L, 4)
     if tiled:
         flags |= F_TRAJ_TILED
         if traj_host:
@@ -406,6 +411,7 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     b.dx, b.dy = float(dx), float(dy)
     b.traj = _ptr(res.traj) if traj is not None else None
     b.traj_ray_stride = 4 * L
+    b.traj_tile = tile
     b.nsteps = _ptr(res.nsteps)
     b.end_state = _ptr(res.end_state) if want_end else None
     if want_extras:

@@ -457,3 +457,84 @@ def test_beam_field_result_matches_reference(st, beam_fix):
     assert abs(signal - complex(beam_fix["signal"])) < 1e-7 * abs(complex(beam_fix["signal"]))
     assert float(ph_max) == pytest.approx(float(beam_fix["ph_max"]), rel=1e-9)
     assert x_max == pytest.approx(float(beam_fix["x_max"]), rel=1e-8, abs=1e-9)
+
+
+def test_config2_thousand_ray_beam_deposition(st, oracle_mod):
+    """BASELINE config 2: a 10^3-ray Gaussian beam launched by Beam.rays (restated, beam.py:278-344)
+    from an FT-2 antenna; trajectories bit-identical to the oracle and the deposition profile
+    (extension) within 1e-6 L1 of the oracle's."""
+    from rayrtrace_b200.beam import Beam
+    from rayrtrace_b200.nfield import Nfield
+    n, x, y = ft2_density(201, 4e13)
+    nf = Nfield(n, x=x, y=y)
+    xa = 2.3
+    b = Beam(x0=xa, y0=-np.sqrt(100 - xa ** 2), kx0=0, ky0=1)
+    b.rays(rnum=1000, dist=3, ampbnd=1e-3, n_field=nf, tiled=False)
+    bun = b.bundle
+    assert len(bun) == 1000 and bun.nsteps.min() > 150
+    L = bun.result.traj.shape[1]
+    want = oracle_mod.trace_batch(bun.xg0, bun.yg0, bun.kx0, bun.ky0, L, bun.st, nf.dx[0], nf.dy[0], nf.nx, nf.ny, nf.ax, nf.ay,
+                                  nthreads=4)
+    assert np.array_equal(bun.nsteps, want["nsteps"])
+    assert bun.result.traj.cpu().numpy().tobytes() == want["traj"].tobytes()
+    nb = 40
+    hist = np.zeros(nb)
+    for r in range(1000):
+        oracle_mod.deposit(want["traj"][r, :want["nsteps"][r]], bun.st, bun.amp[r], nf.x[0], nf.y[0], nf.dx[0], nf.dy[0],
+                           7.85, 1.3, nb, hist)
+    res = st.trace_batch(nf.device_field(), bun.xg0, bun.yg0, bun.kx0, bun.ky0, L=L, st=bun.st, dx=nf.dx[0], dy=nf.dy[0],
+                         nbins=nb, amp=bun.amp, xorg=nf.x[0], yorg=nf.y[0], r_lcs=7.85, rho_max=1.3)
+    assert np.abs(res.hist - hist).sum() / hist.sum() < 1e-6
+
+
+def test_config4_sweep_invariants(st, oracle_mod, torch_mod):
+    """BASELINE config 4 shape: launch-angle x frequency sweep over an over-dense (reflecting)
+    profile, 2*10^6 rays with per-ray step (frequency) -- a cutoff-heavy, ragged workload.
+    Schedules agree bit for bit; a 3000-ray subsample equals the oracle; a third of the rays reflect."""
+    from rayrtrace_b200 import synth
+    case = synth.sweep_case(nx=201, nrays=2_000_000, seed=4)
+    rng = np.random.default_rng(4)
+    fscale = rng.uniform(100e9, 160e9, case.nrays) / case.freq          # per-ray frequency, 100-160 GHz
+    st_ray = case.st / fscale                                           # st ~ 1/w (den.py:107); k0 ~ w
+    launch = [case.launch[0], case.launch[1], case.launch[2] * fscale, case.launch[3] * fscale]
+    f = case.nfield.device_field()
+    dev = [torch_mod.from_numpy(np.ascontiguousarray(a)).cuda() for a in launch]
+    dst = torch_mod.from_numpy(st_ray).cuda()
+    kw = dict(L=case.L, st=case.st, dx=case.dx, dy=case.dy, st_ray=dst, want_extras=True)
+    a = st.trace_batch(f, *dev, **kw)
+    b = st.trace_batch(f, *dev, refill=True, **kw)
+    c = st.trace_batch(f, *dev, tiled=True, div_ieee=True, **kw)
+    torch_mod.cuda.synchronize()
+    for o in (b, c):
+        assert torch_mod.equal(a.nsteps, o.nsteps) and torch_mod.equal(a.end_state, o.end_state)
+        assert torch_mod.equal(a.ph_end, o.ph_end) and torch_mod.equal(a.turn_index, o.turn_index)
+    refl = float((a.end_state[3] < 0).double().mean().item())
+    assert 0.2 < refl < 0.6
+    idx = rng.choice(case.nrays, 3000, replace=False)
+    want = oracle_mod.trace_batch(*[x[idx] for x in launch], case.L, case.st, case.dx, case.dy, case.nfield.nx, case.nfield.ny,
+                                  case.nfield.ax, case.nfield.ay, st_ray=st_ray[idx], nthreads=4)
+    assert np.array_equal(a.nsteps.cpu().numpy()[idx], want["nsteps"])
+    assert a.end_state.cpu().numpy()[:, idx].tobytes() == want["end"].tobytes()
+    ph = a.ph_end.cpu().numpy()[idx]
+    for j in range(0, 3000, 150):
+        k = int(want["nsteps"][j])
+        assert float(ph[j]).hex() == float(oracle_mod.lax_ph(want["traj"][j, :k], st_ray[idx][j])[1][-1]).hex()
+
+
+@pytest.mark.parametrize("tile", [64, 128])
+@pytest.mark.parametrize("refill", [None, True, False])
+def test_tile_sizes_bitwise(st, oracle_mod, tile, refill):
+    """Tiled trajectory layout with 64- and 128-ray tiles ([ray/T][step][ray%T][4]): same bits."""
+    rng = np.random.default_rng(tile)
+    nx, ny, n, L = 70, 60, 1000 + 37, 220
+    ax, ay = random_field(rng, nx, ny)
+    launch = random_launch(rng, n, nx, ny)
+    want = oracle_mod.trace_batch(*launch, L, 0.37, 0.8, 1.3, nx, ny, ax, ay)
+    f = st.Field(ax, ay, nx, ny)
+    res = st.trace_batch(f, *launch, L=L, st=0.37, dx=0.8, dy=1.3, traj=True, tiled=True, tile=tile, refill=refill)
+    assert tuple(res.traj.shape) == ((n + tile - 1) // tile, L, tile, 4)
+    assert np.array_equal(res.nsteps, want["nsteps"])
+    assert res.traj_ray_major().cpu().numpy().tobytes() == want["traj"].tobytes()
+    r = n - 3
+    assert res.ray_states(r).cpu().numpy().tobytes() == want["traj"][r, :want["nsteps"][r]].tobytes()
+    f.close()

@@ -36,13 +36,13 @@ def main():
     field = sidtrace.Field(np.ascontiguousarray(nf.ax), np.ascontiguousarray(nf.ay), nf.nx, nf.ny)
     d_in = [torch.from_numpy(a).to(dev) for a in case.launch]
     n, L = case.nrays, case.L
-    nt = (n + 31) // 32
+    nt = (n + 127) // 128 * 4
     buf = None   # trajectory arena, allocated when a trajectory variant is selected
     kw = dict(L=L, st=case.st, dx=case.dx, dy=case.dy)
     out = sidtrace.BatchResult(nsteps=torch.empty(n, dtype=torch.int32, device=dev),
                                end_state=torch.empty((4, n), dtype=torch.float64, device=dev))
     variants = []
-    for mode in ("traj-tiled", "traj-ray", "endpoints", "endpoints-tiled", "extras", "extras-tiled"):
+    for mode in ("traj-tiled", "traj-tiled64", "traj-tiled128", "traj-ray", "endpoints", "endpoints-tiled", "extras", "extras-tiled"):
         for refill in (True, False):
             for div_ieee in (False, True):
                 variants.append((mode, refill, div_ieee))
@@ -56,8 +56,10 @@ def main():
         k = dict(kw, refill=refill, div_ieee=div_ieee)
         if mode.startswith("traj") and buf is None:
             buf = torch.empty(nt * 32 * L * 4, dtype=torch.float64, device=dev)
-        if mode == "traj-tiled":
-            k.update(traj=buf[: nt * L * 128].view(nt, L, 32, 4), tiled=True)
+        if mode in ("traj-tiled", "traj-tiled64", "traj-tiled128"):
+            T = {"traj-tiled": 32, "traj-tiled64": 64, "traj-tiled128": 128}[mode]
+            ntt = (n + T - 1) // T
+            k.update(traj=buf[: ntt * L * T * 4].view(ntt, L, T, 4), tiled=True, tile=T)
         elif mode == "traj-ray":
             k.update(traj=buf[: n * L * 4].view(n, L, 4))
         elif mode == "extras":
