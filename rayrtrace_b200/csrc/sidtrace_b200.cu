@@ -331,7 +331,7 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     p.st = b->st; p.sst = b->st * b->st; p.st_ray = b->st_ray;
     p.dx = b->dx; p.dy = b->dy; p.rdx = 1.0 / b->dx; p.rdy = 1.0 / b->dy;
     p.traj = b->traj; p.stride = stride;
-    p.tile = b->traj_tile ? b->traj_tile : 32;
+    p.tile = b->traj_tile ? b->traj_tile : 128;
     if (p.tile != 32 && p.tile != 64 && p.tile != 128)
         return fail(STB_ERR_ARG, "stb_trace_batch: traj_tile must be 32, 64 or 128 (got %d)", b->traj_tile);
     p.nsteps = b->nsteps; p.endst = b->end_state;

@@ -1,0 +1,57 @@
+"""FT-2 interferometer geometry and the density-scan driver (the reference's ft2.py:1-71),
+on top of the batched Beam.  Host-side O(beams) orchestration; every ray is traced on the GPU.
+
+Only what sits on the path from a density grid to interferometer phases is mirrored
+(``ants``, ``limiter``, ``phases``); the CX / TS chord helpers (ft2.py:74-90) never touch the
+tracer and are out of scope.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .beam import Beam, field_result
+from .nfield import Nfield
+
+r_dia = 7.85     # limiter radius, cm (ft2.py:6)
+r_ant = 10       # antenna radius, cm (ft2.py:7)
+
+
+def ants():
+    """Seven antennas on the r = 10 cm circle, x from -6.9 to 6.9 cm (ft2.py:12-16)."""
+    x = np.linspace(-6.9, 6.9, 7)
+    return np.vstack((x, np.sqrt(r_ant ** 2 - x ** 2))).T
+
+
+def limiter(r_dia=r_dia, theta=360):
+    if isinstance(theta, (int, np.integer)):
+        theta = np.linspace(0, 2 * np.pi, theta, endpoint=False)
+    return r_dia * np.cos(theta), r_dia * np.sin(theta)
+
+
+def phases(den, x, y, *, ant_tx=None, ant_rx=None, a_set=None, nst=-1, nray=251):
+    """Interferometer phase of every TX/RX antenna pair for the density ``den * a`` with ``a`` in
+    ``a_set`` (or ``nst + 1`` values from 0 to 1): ``(ph_by_max, ph_by_sig)``, each
+    ``[len(a_set), n_antennas]`` (ft2.py:25-71).  Per density scale: one field upload and one
+    kernel launch per TX beam instead of ``nray`` Python-level ``Ray`` constructions."""
+    Beam._nray = nray
+    if ant_tx is None:
+        ant_tx = ants()
+        ant_tx[:, 1] *= -1.
+    if ant_rx is None:
+        ant_rx = ant_tx.copy()
+        ant_rx[:, 1] *= -1.
+    if nst > 0:
+        a_set = np.linspace(0, 1, nst + 1)
+    a_set = np.atleast_1d(a_set)
+    ph_by_max, ph_by_sig = [], []
+    for a in a_set:
+        nfield = Nfield(den * a, x=x, y=y)
+        for tx, rx in zip(ant_tx, ant_rx):
+            beam_tx = Beam(x0=tx[0], y0=tx[1], kx0=0, ky0=1, n_field=nfield)
+            beam_rx = Beam(x0=rx[0], y0=rx[1], kx0=0, ky0=-1, n_field=None)
+            _, _, _, ph_max, signal, *_ = field_result(beam_tx, beam_rx)
+            ph_by_max.append(ph_max)
+            ph_by_sig.append(np.angle(signal))
+        nfield.close()
+    n_ant = len(ant_tx)
+    return np.array(ph_by_max, float).reshape((-1, n_ant)), np.array(ph_by_sig, float).reshape((-1, n_ant))

@@ -140,6 +140,12 @@ class Nfield:
         self.st = min(st_grad, self.min_dxy * c / w)
         self._device_field = None
 
+    def close(self):
+        """Release the HBM copy of the field (it is re-uploaded on next use)."""
+        if self._device_field is not None:
+            self._device_field.close()
+            self._device_field = None
+
     # ---- B200 side -------------------------------------------------------
     def device_field(self):
         """The HBM-resident copy of (ax, ay) the kernels gather from (uploaded once)."""

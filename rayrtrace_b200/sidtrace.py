@@ -275,7 +275,7 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
                 st_ray=None, traj=None, want_end: bool = True, want_extras: bool = False,
                 hist=None, nbins: int = 0, amp=None, xorg: float = 0.0, yorg: float = 0.0,
                 r_lcs: float = 1.0, rho_max: float = 1.0, traj_host: bool = False,
-                div_ieee: bool = False, refill: Optional[bool] = None, tiled: bool = False, tile: int = 32,
+                div_ieee: bool = False, refill: Optional[bool] = None, tiled: bool = False, tile: int = 128,
                 cross=None, x0_phys=None, y0_phys=None,
                 out: Optional[BatchResult] = None, stream=None) -> BatchResult:
     """Trace ``len(x0)`` rays in one launch.
@@ -295,9 +295,9 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     cross: (val, axis) with axis 'y' or 'x' -- fused receiver-line crossing with the semantics of
     the reference's Ray.addpoint (ray.py:131-224); needs the physical launch points
     x0_phys, y0_phys; fills cross_count / cross_index / cross_flags / cross_state.
-    tiled: trajectory layout [ceil(nrays/32), L, 32, 4] instead of [nrays, L, 4]: every
-    warp-step becomes one coalesced 1 KB row store (the fast layout; read rays back
-    with ``BatchResult.ray_states``).
+    tiled: trajectory layout [ceil(nrays/T), L, T, 4] (T = ``tile`` = 128, 64 or 32 rays) instead
+    of [nrays, L, 4]: every warp-step becomes one coalesced 1 KB row store and a 128-thread CTA
+    writes 4 KB contiguous rows (the fast layout; read rays back with ``BatchResult.ray_states``).
     """
     torch = _torch()
     dev_io = _is_tensor(x0)

@@ -45,3 +45,8 @@ def ft2_cross():
 @pytest.fixture(scope="session")
 def beam_fix():
     return np.load(os.path.join(GOLDEN, "beam.npz"))
+
+
+@pytest.fixture(scope="session")
+def ft2_phases_fix():
+    return np.load(os.path.join(GOLDEN, "ft2_phases.npz"))

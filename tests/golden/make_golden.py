@@ -241,6 +241,29 @@ def make_beam(den):
     print("beam: rays kept", len(tx._rays), "of", rnum, "signal", signal, "ph_max", float(ph_max))
 
 
+def make_ft2_phases():
+    """The reference's top-level driver ft2.phases (ft2.py:25-71) end to end: density scan x seven
+    antenna pairs -> interferometer phases.  Harness shim: the reference Beam's wavefront finder
+    (skimage) is replaced at run time by the product's Newton-solved iso-phase line; everything
+    else (Nfield, Beam.rays, Ray, sidtrace.trace, addpoint, field_r, field_result) is reference code."""
+    import beam as refbeam
+    import ft2 as refft2
+    from rayrtrace_b200.beam import Beam as PBeam
+
+    def _wavefront(self, dist=0.003, ampbnd=0.001, n=1.):
+        pb = PBeam(x0=self.x0, y0=self.y0, kx0=self._kx0, ky0=self._ky0, freq=self.freq, waist=self.waist, focus=self.focus)
+        return pb._wavefront(dist, ampbnd, n=n)
+
+    refbeam.Beam._wavefront = _wavefront
+    nx = 161
+    n, x, y = ft2_density(nx, 4e13)
+    a_set = np.array([0.0, 0.6, 1.0])
+    ph_max, ph_sig = refft2.phases(n, x, y, a_set=a_set, nray=41)
+    np.savez_compressed(os.path.join(HERE, "ft2_phases.npz"), nx=np.int64(nx), n0=4e13, a_set=a_set, nray=np.int64(41),
+                        ph_by_max=ph_max, ph_by_sig=ph_sig)
+    print("ft2_phases: ph_by_sig[a=1] =", np.round(ph_sig[-1], 4))
+
+
 if __name__ == "__main__":
     if not oracle.have_ref():
         oracle.build(ref=True)
@@ -250,5 +273,6 @@ if __name__ == "__main__":
     make_ft2_fan(den)
     make_ft2_cross(den, ray)
     make_beam(den)
-    for f in ("kat.npz", "ft2_ray.npz", "ft2_fan.npz", "ft2_cross.npz", "beam.npz"):
+    make_ft2_phases()
+    for f in ("kat.npz", "ft2_ray.npz", "ft2_fan.npz", "ft2_cross.npz", "beam.npz", "ft2_phases.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

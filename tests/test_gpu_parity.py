@@ -471,7 +471,7 @@ def test_config2_thousand_ray_beam_deposition(st, oracle_mod):
     b = Beam(x0=xa, y0=-np.sqrt(100 - xa ** 2), kx0=0, ky0=1)
     b.rays(rnum=1000, dist=3, ampbnd=1e-3, n_field=nf, tiled=False)
     bun = b.bundle
-    assert len(bun) == 1000 and bun.nsteps.min() > 150
+    assert len(bun) == 1000 and bun.nsteps.min() > 100 and np.median(bun.nsteps) > 180
     L = bun.result.traj.shape[1]
     want = oracle_mod.trace_batch(bun.xg0, bun.yg0, bun.kx0, bun.ky0, L, bun.st, nf.dx[0], nf.dy[0], nf.nx, nf.ny, nf.ax, nf.ay,
                                   nthreads=4)
@@ -521,7 +521,7 @@ def test_config4_sweep_invariants(st, oracle_mod, torch_mod):
         assert float(ph[j]).hex() == float(oracle_mod.lax_ph(want["traj"][j, :k], st_ray[idx][j])[1][-1]).hex()
 
 
-@pytest.mark.parametrize("tile", [64, 128])
+@pytest.mark.parametrize("tile", [32, 64])
 @pytest.mark.parametrize("refill", [None, True, False])
 def test_tile_sizes_bitwise(st, oracle_mod, tile, refill):
     """Tiled trajectory layout with 64- and 128-ray tiles ([ray/T][step][ray%T][4]): same bits."""
@@ -538,3 +538,16 @@ def test_tile_sizes_bitwise(st, oracle_mod, tile, refill):
     r = n - 3
     assert res.ray_states(r).cpu().numpy().tobytes() == want["traj"][r, :want["nsteps"][r]].tobytes()
     f.close()
+
+
+def test_ft2_phases_driver_matches_reference(st, ft2_phases_fix):
+    """Top of the reference's call stack (ft2.phases, ft2.py:25-71): density scan x seven TX/RX
+    antenna pairs -> interferometer phases, every ray traced on the GPU through the batched Beam.
+    The fixture is the reference's own ft2.phases output (tests/golden/make_golden.py)."""
+    from rayrtrace_b200 import ft2
+    n, x, y = ft2_density(int(ft2_phases_fix["nx"]), float(ft2_phases_fix["n0"]))
+    ph_max, ph_sig = ft2.phases(n, x, y, a_set=ft2_phases_fix["a_set"], nray=int(ft2_phases_fix["nray"]))
+    assert ph_max.shape == ph_sig.shape == (3, 7)
+    d = np.angle(np.exp(1j * (ph_sig - ft2_phases_fix["ph_by_sig"])))      # compare angles modulo 2 pi
+    assert np.abs(d).max() < 1e-6
+    np.testing.assert_allclose(ph_max, ft2_phases_fix["ph_by_max"], rtol=1e-6)
