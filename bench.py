@@ -386,7 +386,7 @@ def run_b200(args):
                    "parallelism": f"rays interleaved over {world} rank(s), field replicated, no data-path collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (tr or {}).get("dram_bytes_per_launch"),
-                     "kernel": "stb::trace_kernel<TRAJ=1,EXTRAS=0,HIST=0,DIVC=1,REFILL=1,TILED=%d>" % int(tiled),
+                     "kernel": "stb::trace_kernel<TRAJ=1,EXTRAS=0,HIST=0,DIVC=1,REFILL=0,TILED=%d,CROSS=0,STRAY=0>" % int(tiled),
                      "algorithmic_bytes_per_launch": BYTES_PER_RAY_STEP * steps_per_launch,
                      "avg_launch_ms": avg_kernel_ms, "peak_source": peak_src},
         "cpu_baseline": cpu,

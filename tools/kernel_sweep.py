@@ -35,6 +35,9 @@ def main():
     nf = case.nfield
     field = sidtrace.Field(np.ascontiguousarray(nf.ax), np.ascontiguousarray(nf.ay), nf.nx, nf.ny)
     d_in = [torch.from_numpy(a).to(dev) for a in case.launch]
+    d_amp = torch.from_numpy(np.ascontiguousarray(case.amp)).to(dev)
+    d_xp = torch.from_numpy(np.ascontiguousarray(case.x0)).to(dev)
+    d_yp = torch.from_numpy(np.ascontiguousarray(case.y0)).to(dev)
     n, L = case.nrays, case.L
     nt = (n + 127) // 128 * 4
     buf = None   # trajectory arena, allocated when a trajectory variant is selected
@@ -42,7 +45,7 @@ def main():
     out = sidtrace.BatchResult(nsteps=torch.empty(n, dtype=torch.int32, device=dev),
                                end_state=torch.empty((4, n), dtype=torch.float64, device=dev))
     variants = []
-    for mode in ("traj-tiled", "traj-tiled64", "traj-tiled128", "traj-ray", "endpoints", "endpoints-tiled", "extras", "extras-tiled"):
+    for mode in ("traj-tiled", "traj-tiled64", "traj-tiled128", "traj-ray", "endpoints", "endpoints-tiled", "extras", "extras-tiled", "hist64", "hist1024", "cross"):
         for refill in (True, False):
             for div_ieee in (False, True):
                 variants.append((mode, refill, div_ieee))
@@ -64,6 +67,12 @@ def main():
             k.update(traj=buf[: n * L * 4].view(n, L, 4))
         elif mode == "extras":
             k.update(want_extras=True)
+        elif mode in ("hist64", "hist1024"):
+            nb = int(mode[4:])
+            k.update(hist=torch.zeros(nb, dtype=torch.float64, device=dev), amp=d_amp, xorg=float(nf.x[0]), yorg=float(nf.y[0]),
+                     r_lcs=synth.R_DIA, rho_max=1.3)
+        elif mode == "cross":
+            k.update(cross=(9.0, "y"), x0_phys=d_xp, y0_phys=d_yp)
         elif mode == "endpoints-tiled":
             k.update(tiled=True)
         elif mode == "extras-tiled":
