@@ -338,6 +338,7 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     p.turn = b->turn_index; p.lax_end = b->lax_end; p.ph_end = b->ph_end;
     p.hist = b->hist; p.nbins = b->nbins; p.amp = b->amp;
     p.xorg = b->xorg; p.yorg = b->yorg; p.r_lcs = b->r_lcs; p.rho_max = b->rho_max;
+    p.r_rlcs = 1.0 / b->r_lcs; p.r_rhomax = 1.0 / b->rho_max;
     p.counter = f->counter + (f->launch_seq++ % kCounters);
     p.cross_axis = b->cross_axis; p.cross_val = b->cross_val;
     p.x0p = b->x0_phys; p.y0p = b->y0_phys;
@@ -349,6 +350,7 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
             return fail(STB_ERR_ARG, "stb_trace_batch: the crossing output needs x0_phys and y0_phys");
     }
     divc = !(b->flags & STB_F_DIV_IEEE) && divisor_in_guarded_range(b->dx) && divisor_in_guarded_range(b->dy);
+    if (b->hist) divc = divc && divisor_in_guarded_range(b->r_lcs) && divisor_in_guarded_range(b->rho_max);
     return STB_OK;
 }
 

@@ -58,6 +58,7 @@ struct KParams {
     int nbins;
     const double *amp;
     double xorg, yorg, r_lcs, rho_max;
+    double r_rlcs, r_rhomax;             // RN(1/r_lcs), RN(1/rho_max) for the constant-divisor quotients
     unsigned long long *counter;         // ray queue head (refill schedule)
     // receiver-line crossing (CROSS)
     int cross_axis;                      // 1: y = cross_val, 2: x = cross_val (physical cm)
@@ -190,7 +191,8 @@ trace_kernel(const KParams p)
     // extras
     int turn = -1;
     double kprev = 0, lax = 0, ph = 0, a2 = 1.0;
-    int binprev = -1;
+    int binprev = -1;        // HIST: flux bin of the previous kept state = bin of the current run
+    double binacc = 0.0;     // HIST: weight gathered for that bin since the ray entered it
     // crossing: previous kept state, capture of the first crossing / exact hit
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     double xg0 = 0, yg0 = 0, x0p = 0, y0p = 0;
@@ -216,7 +218,7 @@ trace_kernel(const KParams p)
             cx = cy = ckx = cky = clax = cph = qnan;
             cidx = -1; ncross = 0; neq = 0; below = above = false;
         }
-        if (HIST) { const double a = p.amp ? p.amp[r] : 1.0; a2 = __dmul_rn(a, a); }
+        if (HIST) { const double a = p.amp ? p.amp[r] : 1.0; a2 = __dmul_rn(a, a); binprev = -1; binacc = 0.0; }
     };
 
     // solve from the previous kept state (index i-1) and capture the crossing point (ray.py:212-216)
@@ -241,6 +243,10 @@ trace_kernel(const KParams p)
     // whole tile at once, so nsteps / end states leave the warp as coalesced 128 B / 256 B rows
     // (which is what makes writing them straight into mapped host memory cheap).
     auto retire = [&]() {
+        if (HIST) {
+            if (binacc != 0.0) hist_add(sh_hist, binprev, binacc);
+            binacc = 0.0;
+        }
         if (p.nsteps) p.nsteps[ray] = i;
         if (p.endst) {
             p.endst[0 * p.nrays + ray] = x;
@@ -297,18 +303,26 @@ trace_kernel(const KParams p)
                     ph = __dadd_rn(ph, __dmul_rn(dl, kavr));                 // :125
                     lax = lnew;
                 }
-                if (HIST) hist_add(sh_hist, binprev, __dmul_rn(a2, sk));
+                // a ray stays in one flux bin for many consecutive steps: gather the run in a
+                // register and touch shared memory only when the bin changes
+                if (HIST) binacc = __dadd_rn(binacc, __dmul_rn(a2, sk));
             }
             kprev = kcur;
             if (HIST) {
                 // flux label of the segment START (oracle_deposit)
                 const double xp = __dadd_rn(p.xorg, __dmul_rn(x, p.dx));
                 const double yp = __dadd_rn(p.yorg, __dmul_rn(y, p.dy));
-                const double rho = __ddiv_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(xp, xp), __dmul_rn(yp, yp))), p.r_lcs);
-                binprev = -1;
+                const double rho = div_const<DIVC>(__dsqrt_rn(__dadd_rn(__dmul_rn(xp, xp), __dmul_rn(yp, yp))),
+                                                   p.r_lcs, p.r_rlcs);
+                int bnew = -1;
                 if (rho < p.rho_max) {
-                    const int b = __double2int_rz(__ddiv_rn(__dmul_rn(rho, (double)p.nbins), p.rho_max));
-                    if (b >= 0 && b < p.nbins) binprev = b;
+                    const int b = __double2int_rz(div_const<DIVC>(__dmul_rn(rho, (double)p.nbins), p.rho_max, p.r_rhomax));
+                    if (b >= 0 && b < p.nbins) bnew = b;
+                }
+                if (bnew != binprev) {
+                    if (binacc != 0.0) hist_add(sh_hist, binprev, binacc);
+                    binprev = bnew;
+                    binacc = 0.0;
                 }
             }
         }

@@ -551,3 +551,25 @@ def test_ft2_phases_driver_matches_reference(st, ft2_phases_fix):
     d = np.angle(np.exp(1j * (ph_sig - ft2_phases_fix["ph_by_sig"])))      # compare angles modulo 2 pi
     assert np.abs(d).max() < 1e-6
     np.testing.assert_allclose(ph_max, ft2_phases_fix["ph_by_max"], rtol=1e-6)
+
+
+def test_cap_at_reference_maxstep(st, oracle_mod):
+    """A ray that never leaves the grid stops at the cap exactly like the reference at
+    Ray.MaxStep = 100000 (ray.py:11, sidtracemodule.c:36): i = L-1 = 99999, state L-1 written."""
+    nx = ny = 9
+    ax = np.zeros((ny - 1, nx - 1)); ay = np.zeros((ny - 1, nx - 1))
+    L = 100000
+    xs = [np.zeros(L) for _ in range(4)]
+    xs[0][0], xs[1][0] = 4.5, 4.5                      # k = 0: stands still forever
+    n = st.trace(*xs, 0.1, 1.0, 1.0, nx, ny, ax, ay)
+    assert n == L - 1 and xs[0][L - 1] == 4.5 and xs[1][L - 1] == 4.5
+    # batch: one standing ray among moving ones, both schedules, cap reported per ray
+    x0 = np.array([4.5, 1.0, 2.0, 7.9]); y0 = np.array([4.5, 1.0, 2.0, 0.1])
+    kx0 = np.array([0.0, 1.0, -1.0, 0.5]); ky0 = np.array([0.0, 0.5, 2.0, -1.0])
+    want = oracle_mod.trace_batch(x0, y0, kx0, ky0, L, 0.1, 1.0, 1.0, nx, ny, ax, ay, want_traj=False)
+    f = st.Field(ax, ay, nx, ny)
+    for refill in (True, False):
+        res = st.trace_batch(f, x0, y0, kx0, ky0, L=L, st=0.1, dx=1.0, dy=1.0, refill=refill)
+        assert np.array_equal(res.nsteps, want["nsteps"]) and res.nsteps[0] == L - 1
+        assert res.end_state.tobytes() == want["end"].tobytes()
+    f.close()
