@@ -140,6 +140,14 @@ typedef struct stb_batch_s {
     int32_t *cross_flags;     /* [ray] bit 0: exact hit of an existing point; bit 1: extrapolated  */
                               /*       past the last kept point (ray.py:147-148)                   */
     double  *cross_state;     /* [6][nrays] x, y (cm), kx, ky, lax, ph at that point; NaN if none  */
+
+    /* equal-phase lookup (needs cross_axis != 0): the neighbour-ray step of Beam.field_r
+     * (beam.py:404-425).  Each ray -- as it stands after addpoint inserted its crossing point and
+     * its phase was recomputed (ray.py:205-216, 122-126) -- is sampled at two target phases with
+     * the linear interpolation / end-segment extrapolation of scipy's interp1d.  The rays are
+     * traced again; no stored trajectory is needed. */
+    const double *lookup_ph;  /* [2][nrays] target phases A, B per ray; NULL disables             */
+    double  *lookup_xy;       /* [4][nrays] xA, yA, xB, yB (cm); NaN if the ray has < 2 points     */
 } stb_batch_t;
 
 /* Traces b->nrays rays on `stream` (a cudaStream_t passed as void*; NULL = the

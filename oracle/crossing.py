@@ -95,3 +95,53 @@ def crossing(traj_kept, x0p, y0p, dx, dy, st, ax, ay, val, axis="y"):
     phn = ph[i] + (laxn - lax[i]) * kav
     out.update(count=len(i_n), index=i + 1, x=xn, y=yn, kx=kxn, ky=kyn, lax=laxn, ph=phn)
     return out
+
+
+def ray_after_addpoint(traj_kept, x0p, y0p, dx, dy, st, ax, ay, val, axis="y"):
+    """Arrays (x, y, ph) of the ray as the reference holds them after ``addpoint(val, axis)``
+    inserted the FIRST crossing point (ray.py:198-216) and ``ph`` was recomputed from the modified
+    ``st`` (ray.py:117-126).  Rays without a crossing (or with an exact hit) are returned unchanged."""
+    t = np.asarray(traj_kept, np.float64)
+    n = t.shape[0]
+    xs = x0p + (t[:, 0] - t[0, 0]) * dx
+    ys = y0p + (t[:, 1] - t[0, 1]) * dy
+    kx, ky = t[:, 2].copy(), t[:, 3].copy()
+    sts = np.full(n, float(st))
+    sts[-1] = 0.0
+    c = crossing(t, x0p, y0p, dx, dy, st, ax, ay, val, axis)
+    if c["count"] and not c["exact"]:
+        i = c["index"]                    # insertion index; segment start is i-1
+        s_old = sts[i - 1]
+        kav = (math.hypot(kx[i - 1], ky[i - 1]) + math.hypot(c["kx"], c["ky"])) / 2
+        s = (c["lax"] - _lax_at(kx, ky, sts, i - 1)) / kav if kav else 0.0
+        sts[i - 1] = s
+        sts = np.insert(sts, i, s_old - s if i != n else 0.0)
+        xs = np.insert(xs, i, c["x"]); ys = np.insert(ys, i, c["y"])
+        kx = np.insert(kx, i, c["kx"]); ky = np.insert(ky, i, c["ky"])
+    k = np.sqrt(kx * kx + ky * ky)
+    kavr = (k[:-1] + k[1:]) / 2
+    lax = np.cumsum(np.insert(sts[:-1] * kavr, 0, 0))
+    ph = np.cumsum(np.insert(np.diff(lax) * kavr, 0, 0))
+    return xs, ys, ph
+
+
+def _lax_at(kx, ky, sts, j):
+    k = np.sqrt(kx * kx + ky * ky)
+    kavr = (k[:-1] + k[1:]) / 2
+    return float(np.cumsum(np.insert(sts[:-1] * kavr, 0, 0))[j])
+
+
+def interp_extrap(xn, yn, t):
+    """scipy interp1d(kind='linear', fill_value='extrapolate') at one point: node b is the first
+    with t <= xn[b] (clipped to [1, n-1]); y = slope*(t - x_lo) + y_lo."""
+    b = int(np.clip(np.searchsorted(xn, t), 1, len(xn) - 1))
+    slope = (yn[b] - yn[b - 1]) / (xn[b] - xn[b - 1])
+    return slope * (t - xn[b - 1]) + yn[b - 1]
+
+
+def phase_lookup(traj_kept, x0p, y0p, dx, dy, st, ax, ay, val, axis, targets):
+    """Points of the (post-addpoint) ray at the target phases: [(x, y), ...] (beam.py:410-413)."""
+    xs, ys, ph = ray_after_addpoint(traj_kept, x0p, y0p, dx, dy, st, ax, ay, val, axis)
+    if len(ph) < 2:
+        return [(math.nan, math.nan) for _ in targets]
+    return [(interp_extrap(ph, xs, t), interp_extrap(ph, ys, t)) for t in targets]

@@ -61,6 +61,7 @@ class StbBatch(Structure):
         ("x0_phys", c_void_p), ("y0_phys", c_void_p),
         ("cross_count", c_void_p), ("cross_index", c_void_p), ("cross_flags", c_void_p),
         ("cross_state", c_void_p),
+        ("lookup_ph", c_void_p), ("lookup_xy", c_void_p),
     ]
 
 

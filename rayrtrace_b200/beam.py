@@ -261,20 +261,7 @@ class Beam:
         n = len(rays)
 
         # sort the rays into "pages" of monotonically increasing receiver x (caustics fold the beam)
-        pages = [[0]] if n else []
-        cur = 0
-        used = {0}
-        while cur < len(pages):
-            for j in range(pages[cur][-1] + 1, n):
-                if xout[j] > xout[pages[cur][-1]]:
-                    if j not in used:
-                        pages[cur].append(j)
-                        used.add(j)
-                elif cur + 1 == len(pages):
-                    pages.append([j])
-                    used.add(j)
-            cur += 1
-        pages = [np.array(pg) for pg in pages if len(pg) >= 2]
+        pages = _pages(xout)
 
         field = np.zeros(n, dtype=complex)
         for pg in pages:
@@ -309,10 +296,95 @@ class Beam:
         return field, xout, amp0, amp1, ph, pnt
 
 
-def field_result(beam_tx: Beam, beam_rx: Beam):
+def _pages(xout):
+    """Split ray indices into "pages" of increasing receiver coordinate (beam.py:374-398)."""
+    n = len(xout)
+    pages = [[0]] if n else []
+    cur = 0
+    used = {0}
+    while cur < len(pages):
+        for j in range(pages[cur][-1] + 1, n):
+            if xout[j] > xout[pages[cur][-1]]:
+                if j not in used:
+                    pages[cur].append(j)
+                    used.add(j)
+            elif cur + 1 == len(pages):
+                pages.append([j])
+                used.add(j)
+        cur += 1
+    return [np.array(pg) for pg in pages if len(pg) >= 2]
+
+
+def field_r_device(beam: Beam, y, axis="y"):
+    """``Beam.field_r`` (beam.py:347-444) without materialising a single Ray: the crossing of the
+    receiver line comes from the fused ``cross`` output of the trace, the neighbour rays' points at
+    equal eikonal phase from one more launch (``lookup_ph``); only O(rays) numbers reach the host.
+    Returns the same tuple as ``field_r``."""
+    from . import sidtrace as _st
+    from .ray import _device_field
+    if beam.length_unit == "m":
+        y = y * 100
+    bun = beam.bundle
+    nf = bun.n_field
+    fld = _device_field(nf)
+    kw = dict(L=int(bun.L), st=bun.st, dx=float(nf.dx[0]), dy=float(nf.dy[0]))
+    res = bun.result
+    if res is None or res.cross_count is None or bun.receiver != (float(y), axis):
+        res = _st.trace_batch(fld, bun.xg0, bun.yg0, bun.kx0, bun.ky0, cross=(float(y), axis),
+                              x0_phys=bun.x0, y0_phys=bun.y0, **kw)
+    keep = np.flatnonzero(np.asarray(res.cross_count) == 1)     # exactly one crossing (beam.py:361-364)
+    cs = np.asarray(res.cross_state)[:, keep]
+    xc, yc, ph = cs[0], cs[1], cs[5]
+    xout = xc.copy()                                             # the reference reads r.x[ind] for either axis
+    amp0 = np.asarray(bun.amp, float)[keep]
+    amp1 = amp0.copy()
+    pnt = np.asarray(res.cross_index)[keep]
+    x0, y0 = bun.x0[keep], bun.y0[keep]
+    n = len(keep)
+    pages = _pages(xout)
+
+    # every ray of a page is asked for its point at the phase of its right-hand (A) and
+    # left-hand (B) page neighbour's crossing
+    targets = np.full((2, n), np.nan)
+    for pg in pages:
+        targets[0, pg] = ph[np.roll(pg, -1)]
+        targets[1, pg] = ph[np.roll(pg, 1)]
+    sub = [np.ascontiguousarray(a[keep]) for a in (bun.xg0, bun.yg0, bun.kx0, bun.ky0)]
+    look = _st.trace_batch(fld, *sub, cross=(float(y), axis), x0_phys=np.ascontiguousarray(x0),
+                           y0_phys=np.ascontiguousarray(y0), lookup_ph=np.ascontiguousarray(targets), **kw)
+    lx = np.asarray(look.lookup_xy)
+
+    field = np.zeros(n, dtype=complex)
+    for pg in pages:
+        left, right = np.roll(pg, 1), np.roll(pg, -1)
+        d0 = np.stack([np.hypot(x0[pg] - x0[left], y0[pg] - y0[left]),
+                       np.hypot(x0[pg] - x0[right], y0[pg] - y0[right])], 1).reshape(-1)
+        # left neighbour sampled at MY phase = its A target; right neighbour = its B target
+        d1 = np.stack([np.hypot(lx[0, left] - xc[pg], lx[1, left] - yc[pg]),
+                       np.hypot(lx[2, right] - xc[pg], lx[3, right] - yc[pg])], 1).reshape(-1)
+        d0[0], d0[-1] = d0[1], d0[-2]
+        d1[0], d1[-1] = d1[1], d1[-2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            a1 = np.sqrt(d0.reshape(-1, 2).sum(1) / d1.reshape(-1, 2).sum(1))
+        a1[np.isnan(a1)] = amp0[pg][np.isnan(a1)]
+        amp1[pg] = a1
+        field[pg] += amp0[pg] * a1 * np.exp(-1j * ph[pg])
+
+    order = np.argsort(xout)
+    xout, field, amp0, amp1, ph, pnt = xout[order], field[order], amp0[order], amp1[order], ph[order], pnt[order]
+    hole = np.where(field == 0)[0]
+    if len(hole):
+        amp1[hole] = (np.roll(amp1, -1) + np.roll(amp1, 1))[hole] / 2
+        amp1[np.isnan(amp1)] = amp0[np.isnan(amp1)]
+        field[hole] = amp0[hole] * amp1[hole] * np.exp(-1j * ph[hole])
+    return field, xout, amp0, amp1, ph, pnt
+
+
+def field_result(beam_tx: Beam, beam_rx: Beam, device: bool = False):
     """Overlap of the traced TX field with the analytic RX pattern on the receiver line:
-    complex interferometer signal and phase at the maximum (beam.py:447-472)."""
-    field_tx, x, _, _, ph, pnt = beam_tx.field_r(beam_rx.y0)
+    complex interferometer signal and phase at the maximum (beam.py:447-472).  ``device=True``
+    takes the receiver-line field from ``field_r_device`` (no Ray objects)."""
+    field_tx, x, _, _, ph, pnt = field_r_device(beam_tx, beam_rx.y0) if device else beam_tx.field_r(beam_rx.y0)
     field = field_tx * beam_rx.field(x=x, y=beam_rx.y0)
     x_max = np.sum(np.abs(field) * x) / np.sum(np.abs(field))
     x2ph = interp1d(x, ph, kind="cubic")

@@ -203,7 +203,8 @@ namespace {
 
 using stb::KParams;
 
-template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool TILED = false, bool CROSS = false, bool STRAY = true>
+template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool TILED = false, bool CROSS = false, bool STRAY = true,
+          bool LOOKUP = false>
 int launch_variant(const KParams &p, bool refill, int num_sms, cudaStream_t s)
 {
     // lean variants (no fused outputs) with one global step keep st in the constant bank
@@ -214,7 +215,7 @@ int launch_variant(const KParams &p, bool refill, int num_sms, cudaStream_t s)
     if (p.nrays <= 0) return STB_OK;
     long long blocks_all = (p.nrays + stb::kBlock - 1) / stb::kBlock;
     if (refill) {
-        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, true, TILED, CROSS, STRAY>;
+        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, true, TILED, CROSS, STRAY, LOOKUP>;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, stb::kBlock, smem));
@@ -224,7 +225,7 @@ int launch_variant(const KParams &p, bool refill, int num_sms, cudaStream_t s)
         CU(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), s));
         kern<<<(unsigned)blocks, stb::kBlock, smem, s>>>(p);
     } else {
-        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, false, TILED, CROSS, STRAY>;
+        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, false, TILED, CROSS, STRAY, LOOKUP>;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (blocks_all > 0x7fffffffLL) return fail(STB_ERR_ARG, "too many rays for a static grid");
         kern<<<(unsigned)blocks_all, stb::kBlock, smem, s>>>(p);
@@ -252,6 +253,11 @@ int launch_trace(const KParams &p, bool divc, bool refill, bool tiled, int num_s
 {
     if (p.cross_axis) {
         if (p.hist) return fail(STB_ERR_ARG, "the crossing output cannot be combined with the histogram output");
+        if (p.lookup_ph) {
+            if (p.traj || tiled) return fail(STB_ERR_ARG, "the equal-phase lookup pass takes no trajectory output and no tiled schedule");
+            return divc ? launch_variant<false, true, false, true, false, true, true, true>(p, refill, num_sms, s)
+                        : launch_variant<false, true, false, false, false, true, true, true>(p, refill, num_sms, s);
+        }
         if (p.traj) return tiled ? launch_cross<true, true>(p, divc, refill, num_sms, s)
                                  : launch_cross<true, false>(p, divc, refill, num_sms, s);
         return tiled ? launch_cross<false, true>(p, divc, refill, num_sms, s)
@@ -344,6 +350,9 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     p.x0p = b->x0_phys; p.y0p = b->y0_phys;
     p.cross_count = b->cross_count; p.cross_index = b->cross_index; p.cross_flags = b->cross_flags;
     p.cross_state = b->cross_state;
+    p.lookup_ph = b->lookup_ph; p.lookup_xy = b->lookup_xy;
+    if (b->lookup_ph && (!b->cross_axis || !b->lookup_xy))
+        return fail(STB_ERR_ARG, "stb_trace_batch: lookup_ph needs cross_axis != 0 and lookup_xy");
     if (b->cross_axis) {
         if (b->cross_axis != 1 && b->cross_axis != 2) return fail(STB_ERR_ARG, "stb_trace_batch: cross_axis must be 0, 1 (y) or 2 (x)");
         if (b->nrays > 0 && (!b->x0_phys || !b->y0_phys))
@@ -420,7 +429,8 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
 
     if (host_io) {
         // ---- inputs: [x0 | y0 | kx0 | ky0 | st_ray? | amp?] ----
-        const int nin = 4 + (b->st_ray ? 1 : 0) + (b->amp ? 1 : 0) + (b->x0_phys ? 1 : 0) + (b->y0_phys ? 1 : 0);
+        const int nin = 4 + (b->st_ray ? 1 : 0) + (b->amp ? 1 : 0) + (b->x0_phys ? 1 : 0) + (b->y0_phys ? 1 : 0)
+                        + (b->lookup_ph ? 2 : 0);
         rc = f->ws_in.ensure(nb * nin + 64);
         if (rc != STB_OK) return rc;
         double *din = (double *)f->ws_in.p;
@@ -434,15 +444,21 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
             *dst[k] = d;
             ++slot;
         }
+        if (b->lookup_ph) {
+            double *d = din + (size_t)slot * n;
+            if (n) CU(cudaMemcpyAsync(d, b->lookup_ph, 2 * nb, cudaMemcpyHostToDevice, s));
+            p.lookup_ph = d;
+        }
         // ---- outputs: [end 4n | lax n | ph n | cross_state 6n | nsteps, turn, cross_count/index/flags n(i32) each] ----
-        rc = f->ws_out.ensure(nb * 12 + 5 * n * sizeof(int32_t) + 64);
+        rc = f->ws_out.ensure(nb * 16 + 5 * n * sizeof(int32_t) + 64);
         if (rc != STB_OK) return rc;
         double *dout = (double *)f->ws_out.p;
         p.endst = b->end_state ? dout : nullptr;
         p.lax_end = b->lax_end ? dout + 4 * n : nullptr;
         p.ph_end = b->ph_end ? dout + 5 * n : nullptr;
         p.cross_state = b->cross_state ? dout + 6 * n : nullptr;
-        int32_t *iout = (int32_t *)(dout + 12 * n);
+        p.lookup_xy = b->lookup_xy ? dout + 12 * n : nullptr;
+        int32_t *iout = (int32_t *)(dout + 16 * n);
         p.nsteps = b->nsteps ? iout : nullptr;
         p.turn = b->turn_index ? iout + n : nullptr;
         p.cross_count = b->cross_count ? iout + 2 * n : nullptr;
@@ -474,6 +490,7 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
         if (b->nsteps) CU(cudaMemcpyAsync(b->nsteps, p.nsteps, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         if (b->turn_index) CU(cudaMemcpyAsync(b->turn_index, p.turn, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         if (b->cross_state) CU(cudaMemcpyAsync(b->cross_state, p.cross_state, 6 * nb, cudaMemcpyDeviceToHost, s));
+        if (b->lookup_xy) CU(cudaMemcpyAsync(b->lookup_xy, p.lookup_xy, 4 * nb, cudaMemcpyDeviceToHost, s));
         if (b->cross_count) CU(cudaMemcpyAsync(b->cross_count, p.cross_count, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         if (b->cross_index) CU(cudaMemcpyAsync(b->cross_index, p.cross_index, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         if (b->cross_flags) CU(cudaMemcpyAsync(b->cross_flags, p.cross_flags, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));

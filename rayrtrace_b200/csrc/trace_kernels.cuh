@@ -66,6 +66,9 @@ struct KParams {
     const double *x0p, *y0p;             // physical launch points
     int *cross_count, *cross_index, *cross_flags;
     double *cross_state;                 // [6][nrays]
+    // equal-phase lookup (LOOKUP): two target phases per ray -> point of the ray at that phase
+    const double *lookup_ph;             // [2][nrays]
+    double *lookup_xy;                   // [4][nrays]  xA, yA, xB, yB (physical)
 };
 
 // Smallest non-negative root s of k*s + a*s^2/2 = val - c0 (ray.py:174-193); NaN when none.
@@ -167,8 +170,13 @@ __device__ __forceinline__ void hist_add(double *sh, int b, double w)
 // parity (the reference squares through libm pow there), so plain arithmetic is used.
 // STRAY = false: one global step for the whole launch (the reference's case, den.py:107): st and
 // st*st stay in the constant bank instead of four registers per thread.
+// LOOKUP (needs CROSS): the ray as Beam.field_r sees it after addpoint -- the polyline of kept
+// states with the crossing point inserted and the eikonal phase recomputed (ray.py:205-216,
+// 122-126) -- is sampled at two target phases by linear interpolation / end-segment
+// extrapolation, exactly what interp1d(r.ph, r.x, fill_value='extrapolate') does in
+// beam.py:410-413.  Nothing is stored: the ray is simply traced again.
 template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool REFILL, bool TILED = false, bool CROSS = false,
-          bool STRAY = true>
+          bool STRAY = true, bool LOOKUP = false>
 __global__ void __launch_bounds__(kBlock, (CROSS || HIST || EXTRAS) ? 1 : STB_MINB)
 trace_kernel(const KParams p)
 {
@@ -201,6 +209,13 @@ trace_kernel(const KParams p)
     int cidx = -1, ncross = 0, neq = 0;
     bool below = false, above = false;
     const bool axis_y = p.cross_axis != 2;
+    // lookup: capture extras, post-insertion running sums, last two polyline points, targets
+    double cs = 0, ckn = 0;
+    double lax2 = 0, ph2 = 0;
+    double sa_ph = 0, sa_x = 0, sa_y = 0, sb_ph = 0, sb_x = 0, sb_y = 0;
+    int npts = 0;
+    double tA = 0, tB = 0, oxA = qnan, oyA = qnan, oxB = qnan, oyB = qnan;
+    bool doneA = false, doneB = false, inserted = false;
 
     auto launch = [&](long long r) {
         ray = r;
@@ -217,6 +232,12 @@ trace_kernel(const KParams p)
             xg0 = x; yg0 = y; x0p = p.x0p[r]; y0p = p.y0p[r];
             cx = cy = ckx = cky = clax = cph = qnan;
             cidx = -1; ncross = 0; neq = 0; below = above = false;
+            if (LOOKUP) {
+                tA = p.lookup_ph[r]; tB = p.lookup_ph[p.nrays + r];
+                oxA = oyA = oxB = oyB = qnan;
+                doneA = doneB = inserted = false;
+                npts = 0; lax2 = ph2 = 0;
+            }
         }
         if (HIST) { const double a = p.amp ? p.amp[r] : 1.0; a2 = __dmul_rn(a, a); binprev = -1; binacc = 0.0; }
     };
@@ -235,7 +256,24 @@ trace_kernel(const KParams p)
         clax = plax + s * kav;
         cph = pph + (clax - plax) * kav;
         cidx = i;               // i-1 is the segment start: the reference inserts at (i-1)+1
+        cs = s; ckn = kn;
         return true;
+    };
+
+    // append a point (phase, x, y) to the ray's polyline and resolve the targets it brackets:
+    // interp1d picks the first node b >= 1 with t <= ph[b] and interpolates on (b-1, b)
+    auto interp_seg = [&](double t, double &ox, double &oy) {
+        const double dph = sb_ph - sa_ph;
+        ox = (sb_x - sa_x) / dph * (t - sa_ph) + sa_x;
+        oy = (sb_y - sa_y) / dph * (t - sa_ph) + sa_y;
+    };
+    auto add_point = [&](double phq, double xq, double yq) {
+        sa_ph = sb_ph; sa_x = sb_x; sa_y = sb_y;
+        sb_ph = phq; sb_x = xq; sb_y = yq;
+        if (++npts >= 2) {
+            if (!doneA && tA <= phq) { interp_seg(tA, oxA, oyA); doneA = true; }
+            if (!doneB && tB <= phq) { interp_seg(tB, oxB, oyB); doneB = true; }
+        }
     };
 
     // per-ray results: state i is the first out-of-domain state or the cap (sidtracemodule.c:50).
@@ -269,6 +307,17 @@ trace_kernel(const KParams p)
             } else if (i >= 1) {                        // ray.py:147-148: heading for the line past the end
                 const double cl = axis_y ? y0p + (pyg - yg0) * p.dy : x0p + (pxg - xg0) * p.dx;
                 if ((p.cross_val - cl) * (axis_y ? pky : pkx) > 0.0 && capture_from_prev(0.0)) { count = 1; flags = 2; }
+            }
+            if (LOOKUP) {
+                if (flags == 2) add_point(cph, cx, cy);            // point appended past the last kept state
+                if (npts >= 2) {                                    // beyond the last node: last segment extrapolates
+                    if (!doneA) interp_seg(tA, oxA, oyA);
+                    if (!doneB) interp_seg(tB, oxB, oyB);
+                }
+                if (p.lookup_xy) {
+                    p.lookup_xy[0 * p.nrays + ray] = oxA; p.lookup_xy[1 * p.nrays + ray] = oyA;
+                    p.lookup_xy[2 * p.nrays + ray] = oxB; p.lookup_xy[3 * p.nrays + ray] = oyB;
+                }
             }
             if (count == 0) { cx = cy = ckx = cky = clax = cph = qnan; cidx = -1; }
             if (p.cross_count) p.cross_count[ray] = count;
@@ -340,9 +389,32 @@ trace_kernel(const KParams p)
             }
             below |= d < 0.0;
             above |= d > 0.0;
+            bool captured_now = false;
             if (i > 0 && dprev * d < 0.0) {
-                if (ncross == 0 && neq == 0) capture_from_prev(st);
+                if (ncross == 0 && neq == 0) captured_now = capture_from_prev(st);
                 ++ncross;
+            }
+            if (LOOKUP) {
+                const double xpi = x0p + (x - xg0) * p.dx, ypi = y0p + (y - yg0) * p.dy;
+                const double ki = sqrt(kx * kx + ky * ky);
+                if (i > 0) {
+                    if (captured_now && !inserted) {
+                        // the crossing point splits segment (i-1, i): st[i-1] = s, st[new] = st - s (ray.py:205-210)
+                        add_point(cph, cx, cy);
+                        const double kav2 = (ckn + ki) / 2;
+                        const double l2 = clax + (st - cs) * kav2;
+                        ph2 = cph + (l2 - clax) * kav2;
+                        lax2 = l2;
+                        inserted = true;
+                    } else {
+                        const double kpv = sqrt(pkx * pkx + pky * pky);
+                        const double kav = (kpv + ki) / 2;
+                        const double l2 = lax2 + st * kav;
+                        ph2 = ph2 + (l2 - lax2) * kav;
+                        lax2 = l2;
+                    }
+                }
+                add_point(ph2, xpi, ypi);
             }
             pxg = x; pyg = y; pkx = kx; pky = ky; pmx = m.x; pmy = m.y; plax = lax; pph = ph; dprev = d;
         }

@@ -189,6 +189,8 @@ class RayBundle:
     nsteps: np.ndarray        # int32, = len(Ray.x) of the reference
     end_state: np.ndarray     # [4, n] first out-of-domain state (grid units), dropped by Ray
     result: object = None     # sidtrace.BatchResult (traj is a CUDA tensor or None)
+    L: int = 0                # states per ray the launch was sized for
+    receiver: object = None   # (val, axis) of the fused crossing output, if any
     _cache: dict = _dc_field(default_factory=dict)
 
     def __len__(self):
@@ -286,4 +288,5 @@ def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional
                           y0_phys=np.ascontiguousarray(np.atleast_1d(np.asarray(y0, np.float64))) if receiver else None)
     return RayBundle(n_field=n_field, x0=np.atleast_1d(np.asarray(x0, np.float64)),
                      y0=np.atleast_1d(np.asarray(y0, np.float64)), freq=freq, st=st, amp=amp,
-                     xg0=xg, yg0=yg, kx0=kx, ky0=ky, nsteps=res.nsteps, end_state=res.end_state, result=res)
+                     xg0=xg, yg0=yg, kx0=kx, ky0=ky, nsteps=res.nsteps, end_state=res.end_state, result=res, L=L,
+                     receiver=(float(receiver[0]), receiver[1]) if receiver else None)

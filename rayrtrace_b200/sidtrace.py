@@ -237,6 +237,7 @@ class BatchResult:
     cross_index: object = None  # int32 [nrays]   index Ray.addpoint would return for the first one
     cross_flags: object = None  # int32 [nrays]   bit 0 exact hit, bit 1 extrapolated past the end
     cross_state: object = None  # float64 [6, nrays]  x, y (cm), kx, ky, lax, ph at the first crossing
+    lookup_xy: object = None    # float64 [4, nrays]  points of the ray at the two target phases (xA, yA, xB, yB)
     tiled: bool = False         # traj is [ntiles, L, T, 4] (tile = ray // T, slot = ray % T; T = 32, 64 or 128)
 
     def ray_states(self, r: int, n: Optional[int] = None):
@@ -276,7 +277,7 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
                 hist=None, nbins: int = 0, amp=None, xorg: float = 0.0, yorg: float = 0.0,
                 r_lcs: float = 1.0, rho_max: float = 1.0, traj_host: bool = False,
                 div_ieee: bool = False, refill: Optional[bool] = None, tiled: bool = False, tile: int = 128,
-                cross=None, x0_phys=None, y0_phys=None,
+                cross=None, x0_phys=None, y0_phys=None, lookup_ph=None,
                 out: Optional[BatchResult] = None, stream=None) -> BatchResult:
     """Trace ``len(x0)`` rays in one launch.
 
@@ -295,6 +296,9 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     cross: (val, axis) with axis 'y' or 'x' -- fused receiver-line crossing with the semantics of
     the reference's Ray.addpoint (ray.py:131-224); needs the physical launch points
     x0_phys, y0_phys; fills cross_count / cross_index / cross_flags / cross_state.
+    lookup_ph: [2, nrays] target phases (needs ``cross``): the rays are traced again and each one --
+    with its crossing point inserted, as after addpoint -- is sampled at its two target phases
+    like ``interp1d(r.ph, r.x, fill_value='extrapolate')`` (beam.py:410-413); fills ``lookup_xy``.
     tiled: trajectory layout [ceil(nrays/T), L, T, 4] (T = ``tile`` = 128, 64 or 32 rays) instead
     of [nrays, L, 4]: every warp-step becomes one coalesced 1 KB row store and a 128-thread CTA
     writes 4 KB contiguous rows (the fast layout; read rays back with ``BatchResult.ray_states``).
@@ -357,6 +361,18 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
             res.cross_flags = alloc((n,), np.int32, torch.int32)
         if res.cross_state is None:
             res.cross_state = alloc((6, n), np.float64, torch.float64)
+
+    if lookup_ph is not None:
+        if cross is None:
+            raise ValueError("lookup_ph needs cross=(val, axis)")
+        if dev_io:
+            ok = _is_tensor(lookup_ph) and lookup_ph.dtype == torch.float64 and lookup_ph.is_cuda and lookup_ph.is_contiguous()
+        else:
+            ok = isinstance(lookup_ph, np.ndarray) and lookup_ph.dtype == np.float64 and lookup_ph.flags.c_contiguous
+        if not ok or tuple(lookup_ph.shape) != (2, n):
+            raise TypeError(f"lookup_ph must be a contiguous float64 [2, {n}] array living where the launch states live")
+        if res.lookup_xy is None:
+            res.lookup_xy = alloc((4, n), np.float64, torch.float64)
 
     flags = 0
     if not dev_io:
@@ -428,6 +444,8 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
         b.x0_phys, b.y0_phys = _ptr(x0_phys), _ptr(y0_phys)
         b.cross_count, b.cross_index = _ptr(res.cross_count), _ptr(res.cross_index)
         b.cross_flags, b.cross_state = _ptr(res.cross_flags), _ptr(res.cross_state)
+        if lookup_ph is not None:
+            b.lookup_ph, b.lookup_xy = _ptr(lookup_ph), _ptr(res.lookup_xy)
 
     if stream is None:
         stream = torch.cuda.current_stream(device)

@@ -181,6 +181,9 @@ def make_ft2_cross(den, ray):
     launch = np.zeros((nray, 4))
     nkept = np.zeros(nray, np.int64)
     res = np.full((len(lines), nray, 9), np.nan)      # count, index, x, y, kx, ky, lax, ph, raised
+    from scipy.interpolate import interp1d
+    look_t = np.full((len(lines), nray, 2), np.nan)   # target phases handed to the equal-phase lookup
+    look_xy = np.full((len(lines), nray, 4), np.nan)  # interp1d(r.ph, r.x / r.y, extrapolate)(t) AFTER addpoint (beam.py:410-413)
     for r in range(nray):
         for li, (val, axis) in enumerate(lines):
             rr = ray.Ray(xs[r], -9.5, np.sin(ang[r]), np.cos(ang[r]), freq, 1, n_field=nf)
@@ -196,10 +199,19 @@ def make_ft2_cross(den, ray):
                 continue
             i = int(ind[0])
             res[li, r] = len(ind), i, rr.x[i], rr.y[i], rr.kx[i], rr.ky[i], rr.lax[i], rr.ph[i], 0
+            if len(ind) == 1:
+                ph = rr.ph
+                t = np.array([(0.35 + 0.6 * rng.random()) * ph[i], (1.0 + 0.3 * rng.random()) * ph[i] + 1.0])
+                if r % 7 == 0:
+                    t[0] = -2.0                       # before the first node: first-segment extrapolation
+                look_t[li, r] = t
+                look_xy[li, r] = (interp1d(ph, rr.x, fill_value="extrapolate")(t[0]), interp1d(ph, rr.y, fill_value="extrapolate")(t[0]),
+                                  interp1d(ph, rr.x, fill_value="extrapolate")(t[1]), interp1d(ph, rr.y, fill_value="extrapolate")(t[1]))
     ray.Ray.MaxStep = 100000
     np.savez_compressed(os.path.join(HERE, "ft2_cross.npz"), nx=np.int64(nx), n0=n0, freq=freq, x0=xs, y0=np.full(nray, -9.5),
                         launch=launch, nkept=nkept, st=np.float64(nf.st), dx0=np.float64(nf.dx[0]), dy0=np.float64(nf.dy[0]),
-                        line_val=np.array([l[0] for l in lines]), line_axis=np.array([l[1] for l in lines]), res=res)
+                        line_val=np.array([l[0] for l in lines]), line_axis=np.array([l[1] for l in lines]), res=res,
+                        look_t=look_t, look_xy=look_xy)
     print("ft2_cross: counts per line", [(res[li, :, 0]).astype(int).tolist().count(1) for li in range(len(lines))],
           "none", [int((res[li, :, 0] == 0).sum()) for li in range(len(lines))],
           "multi", [int((res[li, :, 0] > 1).sum()) for li in range(len(lines))])

@@ -573,3 +573,53 @@ def test_cap_at_reference_maxstep(st, oracle_mod):
         assert np.array_equal(res.nsteps, want["nsteps"]) and res.nsteps[0] == L - 1
         assert res.end_state.tobytes() == want["end"].tobytes()
     f.close()
+
+
+def test_equal_phase_lookup_matches_reference_interp1d(st, ft2_cross):
+    """LOOKUP pass (second launch of Beam.field_r's device path): each ray, with its crossing point
+    inserted as after the reference's addpoint, sampled at two target phases == the reference's
+    interp1d(r.ph, r.x / r.y, fill_value='extrapolate') (beam.py:410-413).  Tolerance 1e-9."""
+    from test_oracle_crossing import cross_case
+    nf = cross_case(ft2_cross)
+    la = ft2_cross["launch"]
+    ins = [np.ascontiguousarray(la[:, k]) for k in range(4)]
+    xp, yp = np.ascontiguousarray(ft2_cross["x0"]), np.ascontiguousarray(ft2_cross["y0"])
+    checked = 0
+    for li, (val, axis) in enumerate(zip(ft2_cross["line_val"], ft2_cross["line_axis"])):
+        t = ft2_cross["look_t"][li]                       # [nray, 2], NaN where the reference had no single crossing
+        ok = ~np.isnan(t[:, 0])
+        targets = np.ascontiguousarray(np.where(ok[:, None], t, 0.0).T)
+        for refill in (True, False):
+            res = st.trace_batch(nf.device_field(), *ins, L=4096, st=nf.st, dx=nf.dx[0], dy=nf.dy[0],
+                                 cross=(float(val), str(axis)), x0_phys=xp, y0_phys=yp, lookup_ph=targets, refill=refill)
+            assert np.array_equal(res.cross_count, ft2_cross["res"][li][:, 0].astype(int))
+            np.testing.assert_allclose(res.lookup_xy[:, ok].T, ft2_cross["look_xy"][li][ok], rtol=1e-9, atol=1e-9)
+        checked += int(ok.sum())
+    assert checked > 60
+
+
+def test_field_r_device_matches_reference(st, beam_fix):
+    """Beam.field_r without Ray objects (fused crossing + equal-phase lookup launch) reproduces the
+    reference's field on the receiver line and the interferometer signal (beam.py:347-472)."""
+    from scipy.interpolate import interp1d
+    from rayrtrace_b200.beam import Beam, field_r_device, field_result
+    from rayrtrace_b200.nfield import Nfield
+    n, x, y = ft2_density(int(beam_fix["nx"]), float(beam_fix["n0"]))
+    nf = Nfield(n, x=x, y=y)
+    x0, y0 = float(beam_fix["x0"]), float(beam_fix["y0"])
+    wf = interp1d(beam_fix["wf_x"], beam_fix["wf_y"], kind="cubic")
+    tx = Beam(x0=x0, y0=y0, kx0=0, ky0=1)
+    rx = Beam(x0=x0, y0=-y0, kx0=0, ky0=-1)
+    tx.rays(rnum=int(beam_fix["rnum"]), wave_front=wf, dist=3, ampbnd=1e-3, n_field=nf, keep_traj=False, receiver=(-y0, "y"))
+    field, xo, amp0, amp1, ph, pnt = field_r_device(tx, -y0)
+    np.testing.assert_allclose(xo, beam_fix["xout"], rtol=1e-9)
+    np.testing.assert_allclose(field, beam_fix["field"], rtol=1e-7, atol=1e-9)
+    f2, x2, x_max, ph_max, signal, props = field_result(tx, rx, device=True)
+    assert abs(signal - complex(beam_fix["signal"])) < 1e-7 * abs(complex(beam_fix["signal"]))
+    assert float(ph_max) == pytest.approx(float(beam_fix["ph_max"]), rel=1e-9)
+    # and equals the host path (Ray objects + addpoint + interp1d) on the same beam
+    tx2 = Beam(x0=x0, y0=y0, kx0=0, ky0=1)
+    tx2.rays(rnum=int(beam_fix["rnum"]), wave_front=wf, dist=3, ampbnd=1e-3, n_field=nf)
+    fh = tx2.field_r(-y0)
+    np.testing.assert_allclose(field, fh[0], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(amp1, fh[3], rtol=1e-7)
