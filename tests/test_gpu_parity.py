@@ -623,3 +623,49 @@ def test_field_r_device_matches_reference(st, beam_fix):
     fh = tx2.field_r(-y0)
     np.testing.assert_allclose(field, fh[0], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(amp1, fh[3], rtol=1e-7)
+
+
+@pytest.mark.parametrize("refill", [True, False])
+@pytest.mark.parametrize("tiled", [False, True])
+def test_no_out_of_bounds_writes_canaries(st, torch_mod, oracle_mod, refill, tiled):
+    """Own bounds check (compute-sanitizer is closed on this pool): every output buffer sits inside
+    a larger arena filled with a canary; after the launch the canaries are intact and the payload
+    equals the oracle.  Ray count deliberately not a multiple of 32 / 128."""
+    rng = np.random.default_rng(123)
+    nx, ny, n, L = 50, 40, 1000 + 77, 90
+    ax, ay = random_field(rng, nx, ny)
+    launch = random_launch(rng, n, nx, ny)
+    want = oracle_mod.trace_batch(*launch, L, 0.37, 0.8, 1.3, nx, ny, ax, ay)
+    f = st.Field(ax, ay, nx, ny)
+    dev = [torch_mod.from_numpy(a).cuda() for a in launch]
+    pad = 4096
+    CAN = -7.25e300
+
+    def arena(numel, dtype):
+        buf = torch_mod.full((numel + 2 * pad,), CAN if dtype == torch_mod.float64 else -77777, dtype=dtype, device="cuda")
+        return buf, buf[pad:pad + numel]
+
+    T = 128
+    nt = (n + T - 1) // T
+    tshape = (nt, L, T, 4) if tiled else (n, L, 4)
+    bufs = {k: arena(int(np.prod(shp)), dt) for k, (shp, dt) in {
+        "traj": (tshape, torch_mod.float64), "nsteps": ((n,), torch_mod.int32), "end": ((4, n), torch_mod.float64),
+        "turn": ((n,), torch_mod.int32), "lax": ((n,), torch_mod.float64), "ph": ((n,), torch_mod.float64)}.items()}
+    out = st.BatchResult(nsteps=bufs["nsteps"][1], end_state=bufs["end"][1].view(4, n), turn_index=bufs["turn"][1],
+                         lax_end=bufs["lax"][1], ph_end=bufs["ph"][1])
+    res = st.trace_batch(f, *dev, L=L, st=0.37, dx=0.8, dy=1.3, traj=bufs["traj"][1].view(*tshape), tiled=tiled, tile=T,
+                         refill=refill, want_extras=True, out=out)
+    torch_mod.cuda.synchronize()
+    for k, (buf, _) in bufs.items():
+        can = CAN if buf.dtype == torch_mod.float64 else -77777
+        assert bool((buf[:pad] == can).all()) and bool((buf[-pad:] == can).all()), f"canary of {k} overwritten"
+    assert np.array_equal(res.nsteps.cpu().numpy(), want["nsteps"])
+    assert res.end_state.cpu().numpy().tobytes() == want["end"].tobytes()
+    traj = res.traj_ray_major().cpu().numpy()
+    for r in range(n):
+        k = int(want["nsteps"][r])
+        assert traj[r, :k + 1].tobytes() == want["traj"][r, :k + 1].tobytes()
+        assert (traj[r, k + 1:] == CAN).all()          # never written beyond state i
+    if tiled:                                          # slots of the partial last tile stay untouched
+        assert bool((res.traj[-1, :, n % T:, :] == CAN).all())
+    f.close()
