@@ -28,30 +28,30 @@ def limiter(r_dia=r_dia, theta=360):
     return r_dia * np.cos(theta), r_dia * np.sin(theta)
 
 
+def _pair_phases(nfield, tx, rx):
+    """One TX/RX antenna pair: trace the TX beam through ``nfield`` (one launch), overlap its field
+    on the receiver line with the RX antenna pattern (beam.py:447-472)."""
+    beam_tx = Beam(x0=tx[0], y0=tx[1], kx0=0, ky0=1, n_field=nfield)
+    beam_rx = Beam(x0=rx[0], y0=rx[1], kx0=0, ky0=-1)
+    _, _, _, ph_at_max, signal, *_ = field_result(beam_tx, beam_rx)
+    return ph_at_max, np.angle(signal)
+
+
 def phases(den, x, y, *, ant_tx=None, ant_rx=None, a_set=None, nst=-1, nray=251):
     """Interferometer phase of every TX/RX antenna pair for the density ``den * a`` with ``a`` in
     ``a_set`` (or ``nst + 1`` values from 0 to 1): ``(ph_by_max, ph_by_sig)``, each
     ``[len(a_set), n_antennas]`` (ft2.py:25-71).  Per density scale: one field upload and one
     kernel launch per TX beam instead of ``nray`` Python-level ``Ray`` constructions."""
-    Beam._nray = nray
-    if ant_tx is None:
-        ant_tx = ants()
-        ant_tx[:, 1] *= -1.
-    if ant_rx is None:
-        ant_rx = ant_tx.copy()
-        ant_rx[:, 1] *= -1.
-    if nst > 0:
-        a_set = np.linspace(0, 1, nst + 1)
-    a_set = np.atleast_1d(a_set)
-    ph_by_max, ph_by_sig = [], []
-    for a in a_set:
-        nfield = Nfield(den * a, x=x, y=y)
-        for tx, rx in zip(ant_tx, ant_rx):
-            beam_tx = Beam(x0=tx[0], y0=tx[1], kx0=0, ky0=1, n_field=nfield)
-            beam_rx = Beam(x0=rx[0], y0=rx[1], kx0=0, ky0=-1, n_field=None)
-            _, _, _, ph_max, signal, *_ = field_result(beam_tx, beam_rx)
-            ph_by_max.append(ph_max)
-            ph_by_sig.append(np.angle(signal))
+    Beam._nray = nray                                   # the reference sets the class default too (ft2.py:26)
+    if ant_tx is None:                                  # transmitters on the lower half of the antenna circle
+        ant_tx = ants() * np.array([1., -1.])
+    if ant_rx is None:                                  # receivers mirrored to the upper half
+        ant_rx = ant_tx * np.array([1., -1.])
+    scales = np.linspace(0, 1, nst + 1) if nst > 0 else np.atleast_1d(a_set)
+    rows = []
+    for scale in scales:
+        nfield = Nfield(den * scale, x=x, y=y)
+        rows.append([_pair_phases(nfield, tx, rx) for tx, rx in zip(ant_tx, ant_rx)])
         nfield.close()
-    n_ant = len(ant_tx)
-    return np.array(ph_by_max, float).reshape((-1, n_ant)), np.array(ph_by_sig, float).reshape((-1, n_ant))
+    out = np.array(rows, float)                         # [scale, antenna, (ph_max, ph_sig)]
+    return out[:, :, 0], out[:, :, 1]
