@@ -373,28 +373,28 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
     if (b->struct_size != sizeof(stb_batch_t))
         return fail(STB_ERR_ARG, "stb_trace_batch: struct_size %zu != %zu (ABI mismatch)", b->struct_size, sizeof(stb_batch_t));
     cudaStream_t s = (cudaStream_t)stream;
+    const bool host_io = b->flags & STB_F_HOST_IO;
+    const bool traj_host = b->flags & STB_F_TRAJ_HOST;
+    const bool tiled = b->flags & STB_F_TRAJ_TILED;
+    if ((b->flags & STB_F_REFILL) && (b->flags & STB_F_STATIC)) return fail(STB_ERR_ARG, "STB_F_REFILL and STB_F_STATIC are mutually exclusive");
+    if (tiled && traj_host) return fail(STB_ERR_ARG, "STB_F_TRAJ_TILED and STB_F_TRAJ_HOST are mutually exclusive");
+    const bool refill = (b->flags & STB_F_REFILL) ? true : (b->flags & STB_F_STATIC) ? false : !tiled;
+    int dev = -1;
+    CU(cudaGetDevice(&dev));
+    if (dev != f->device)
+        return fail(STB_ERR_ARG, "stb_trace_batch: the field lives on device %d but the current device is %d", f->device, dev);
+
+    // one lock per field: the queue heads and the staging workspaces belong to it
+    std::lock_guard<std::mutex> lk(f->mu);
     KParams p{};
     bool divc = false;
     int rc = fill_params(f, b, p, divc);
     if (rc != STB_OK) return rc;
-    const bool tiled_ = b->flags & STB_F_TRAJ_TILED;
-    if ((b->flags & STB_F_REFILL) && (b->flags & STB_F_STATIC)) return fail(STB_ERR_ARG, "STB_F_REFILL and STB_F_STATIC are mutually exclusive");
-    const bool refill = (b->flags & STB_F_REFILL) ? true : (b->flags & STB_F_STATIC) ? false : !tiled_;
-    const bool host_io = b->flags & STB_F_HOST_IO;
-    const bool traj_host = b->flags & STB_F_TRAJ_HOST;
-    const bool tiled = b->flags & STB_F_TRAJ_TILED;
-    if (tiled && traj_host) return fail(STB_ERR_ARG, "STB_F_TRAJ_TILED and STB_F_TRAJ_HOST are mutually exclusive");
 
-    if (!host_io && !traj_host) {
-        // the counter is per field: serialise launches that share it on different streams
-        std::lock_guard<std::mutex> lk(f->mu);
-        return launch_trace(p, divc, refill, tiled, f->num_sms, s);
-    }
+    if (!host_io && !traj_host) return launch_trace(p, divc, refill, tiled, f->num_sms, s);
 
-    std::lock_guard<std::mutex> lk(f->mu);
     const size_t n = (size_t)b->nrays;
     const size_t nb = n * sizeof(double);
-    const bool extras = b->turn_index || b->lax_end || b->ph_end;
 
     // ---- zero-copy host I/O -------------------------------------------------------------
     // With the warp-tile schedule every launch-state read and every per-ray result write is a
@@ -464,7 +464,6 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
         p.cross_count = b->cross_count ? iout + 2 * n : nullptr;
         p.cross_index = b->cross_index ? iout + 3 * n : nullptr;
         p.cross_flags = b->cross_flags ? iout + 4 * n : nullptr;
-        (void)extras;
         if (b->hist) {
             rc = f->ws_hist.ensure((size_t)b->nbins * sizeof(double));
             if (rc != STB_OK) return rc;
@@ -508,6 +507,10 @@ int stb_trace(stb_field_t f, double *x, double *y, double *kx, double *ky, int64
 {
     if (!f || !x || !y || !kx || !ky || !nsteps) return fail(STB_ERR_ARG, "stb_trace: NULL argument");
     if (L < 1 || L > 0x7fffffffLL) return fail(STB_ERR_ARG, "stb_trace: L = %lld out of range", (long long)L);
+    int dev = -1;
+    CU(cudaGetDevice(&dev));
+    if (dev != f->device)
+        return fail(STB_ERR_ARG, "stb_trace: the field lives on device %d but the current device is %d", f->device, dev);
     std::lock_guard<std::mutex> lk(f->mu);
     // workspace: launch state (4 doubles) | nsteps (i32) ; trajectory [L][4]
     int rc = f->ws_in.ensure(64);
