@@ -63,3 +63,21 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "sidtrace_oracle" not in text, f
+
+
+def test_compute_entry_points_fail_loudly_without_a_device():
+    """No CPU fallback: on a box without a GPU the field upload returns STB_ERR_CUDA with a message
+    (and the Python surface raises) instead of computing anything on the host."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from rayrtrace_b200 import _cabi, sidtrace
+    a = np.zeros((4, 6))
+    h = ctypes.c_void_p()
+    rc = _cabi.lib.stb_field_create(a.ctypes.data, a.ctypes.data, 7, 5, 0, ctypes.byref(h))
+    assert rc == _cabi.STB_ERR_CUDA and not h.value
+    assert b"cuda" in _cabi.lib.stb_last_error().lower()
+    x = [np.zeros(8) for _ in range(4)]
+    with pytest.raises(_cabi.SidtraceError):
+        sidtrace.trace(*x, 0.1, 1.0, 1.0, 7, 5, a, a.copy())

@@ -669,3 +669,19 @@ def test_no_out_of_bounds_writes_canaries(st, torch_mod, oracle_mod, refill, til
     if tiled:                                          # slots of the partial last tile stay untouched
         assert bool((res.traj[-1, :, n % T:, :] == CAN).all())
     f.close()
+
+
+def test_plain_c_caller_of_the_abi(st, tmp_path):
+    """The boundary is a C ABI: a C program (no Python, no torch) binds include/sidtrace_b200.h,
+    traces KAT G1 through stb_trace and stb_trace_batch and compares with the published bits."""
+    import os
+    import subprocess
+    from rayrtrace_b200 import _cabi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "abi_kat"
+    lib = _cabi.LIB_PATH
+    subprocess.check_call([os.environ.get("CC", "gcc"), "-O1", "-std=c11", os.path.join(root, "tests", "c", "abi_kat.c"),
+                           lib, "-lm", "-Wl,-rpath," + os.path.dirname(lib), "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "MISMATCH" not in r.stdout
