@@ -28,16 +28,23 @@ def limiter(r_dia=r_dia, theta=360):
     return r_dia * np.cos(theta), r_dia * np.sin(theta)
 
 
-def _pair_phases(nfield, tx, rx):
-    """One TX/RX antenna pair: trace the TX beam through ``nfield`` (one launch), overlap its field
-    on the receiver line with the RX antenna pattern (beam.py:447-472)."""
-    beam_tx = Beam(x0=tx[0], y0=tx[1], kx0=0, ky0=1, n_field=nfield)
+def _pair_phases(nfield, tx, rx, device=True):
+    """One TX/RX antenna pair: trace the TX beam through ``nfield``, overlap its field on the
+    receiver line with the RX antenna pattern (beam.py:447-472).  ``device=True``: the crossing of
+    the receiver line is fused into the trace and the neighbour-ray lookup is one more launch --
+    no trajectories kept, no Ray objects; ``device=False``: the reference's flow on materialised
+    rays (Ray.addpoint + interp1d on the host)."""
     beam_rx = Beam(x0=rx[0], y0=rx[1], kx0=0, ky0=-1)
-    _, _, _, ph_at_max, signal, *_ = field_result(beam_tx, beam_rx)
+    if device:
+        beam_tx = Beam(x0=tx[0], y0=tx[1], kx0=0, ky0=1)
+        beam_tx.rays(n_field=nfield, keep_traj=False, receiver=(float(rx[1]), "y"))
+    else:
+        beam_tx = Beam(x0=tx[0], y0=tx[1], kx0=0, ky0=1, n_field=nfield)
+    _, _, _, ph_at_max, signal, *_ = field_result(beam_tx, beam_rx, device=device)
     return ph_at_max, np.angle(signal)
 
 
-def phases(den, x, y, *, ant_tx=None, ant_rx=None, a_set=None, nst=-1, nray=251):
+def phases(den, x, y, *, ant_tx=None, ant_rx=None, a_set=None, nst=-1, nray=251, device=True):
     """Interferometer phase of every TX/RX antenna pair for the density ``den * a`` with ``a`` in
     ``a_set`` (or ``nst + 1`` values from 0 to 1): ``(ph_by_max, ph_by_sig)``, each
     ``[len(a_set), n_antennas]`` (ft2.py:25-71).  Per density scale: one field upload and one
@@ -51,7 +58,7 @@ def phases(den, x, y, *, ant_tx=None, ant_rx=None, a_set=None, nst=-1, nray=251)
     rows = []
     for scale in scales:
         nfield = Nfield(den * scale, x=x, y=y)
-        rows.append([_pair_phases(nfield, tx, rx) for tx, rx in zip(ant_tx, ant_rx)])
+        rows.append([_pair_phases(nfield, tx, rx, device) for tx, rx in zip(ant_tx, ant_rx)])
         nfield.close()
     out = np.array(rows, float)                         # [scale, antenna, (ph_max, ph_sig)]
     return out[:, :, 0], out[:, :, 1]

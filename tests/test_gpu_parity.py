@@ -546,11 +546,12 @@ def test_ft2_phases_driver_matches_reference(st, ft2_phases_fix):
     The fixture is the reference's own ft2.phases output (tests/golden/make_golden.py)."""
     from rayrtrace_b200 import ft2
     n, x, y = ft2_density(int(ft2_phases_fix["nx"]), float(ft2_phases_fix["n0"]))
-    ph_max, ph_sig = ft2.phases(n, x, y, a_set=ft2_phases_fix["a_set"], nray=int(ft2_phases_fix["nray"]))
-    assert ph_max.shape == ph_sig.shape == (3, 7)
-    d = np.angle(np.exp(1j * (ph_sig - ft2_phases_fix["ph_by_sig"])))      # compare angles modulo 2 pi
-    assert np.abs(d).max() < 1e-6
-    np.testing.assert_allclose(ph_max, ft2_phases_fix["ph_by_max"], rtol=1e-6)
+    for device in (True, False):       # fused crossing + lookup launches / materialised Ray objects
+        ph_max, ph_sig = ft2.phases(n, x, y, a_set=ft2_phases_fix["a_set"], nray=int(ft2_phases_fix["nray"]), device=device)
+        assert ph_max.shape == ph_sig.shape == (3, 7)
+        d = np.angle(np.exp(1j * (ph_sig - ft2_phases_fix["ph_by_sig"])))      # compare angles modulo 2 pi
+        assert np.abs(d).max() < 1e-6
+        np.testing.assert_allclose(ph_max, ft2_phases_fix["ph_by_max"], rtol=1e-6)
 
 
 def test_cap_at_reference_maxstep(st, oracle_mod):
