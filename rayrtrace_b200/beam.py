@@ -197,16 +197,28 @@ class Beam:
         l2x = interp1d(lax, wave_front.x)
         x = l2x(np.linspace(0, lax[-1], rnum))
         y = wave_front(x)
-        # normals from finite differences on a fine arc-length-equidistant grid
-        xg = l2x(np.linspace(0, lax[-1], np.lcm(rnum, Beam._nfront)))
-        yg = wave_front(xg)
+        # Normals: the reference differentiates the front on a fine grid of M = lcm(rnum, _nfront)
+        # arc-length-equidistant points with np.gradient and keeps every (M/rnum)-th value
+        # (beam.py:306-326).  Only the kept nodes and their two neighbours enter the result, so just
+        # those 3*rnum points are evaluated -- same values bit for bit, O(rnum) instead of O(lcm).
+        m_fine = int(np.lcm(rnum, Beam._nfront))
+        stride = int(m_fine / rnum)
+        keep = np.arange(0, m_fine, stride)
+        lo, hi = np.maximum(keep - 1, 0), np.minimum(keep + 1, m_fine - 1)
+        step = lax[-1] / (m_fine - 1)                       # np.linspace: arange(M) * step + start, last = stop
+
+        def fine(idx):
+            t = idx * step + 0.0
+            t[idx == m_fine - 1] = lax[-1]
+            xb = l2x(t)
+            return self.beam2lab(xb, wave_front(xb))
+
         x, y = self.beam2lab(x, y)
-        xg, yg = self.beam2lab(xg, yg)
-        kx, ky = -np.gradient(yg), np.gradient(xg)
+        (x_lo, y_lo), (x_hi, y_hi) = fine(lo), fine(hi)
+        width = np.where((keep == 0) | (keep == m_fine - 1), 1.0, 2.0)   # one-sided at the ends, central inside
+        kx, ky = -((y_hi - y_lo) / width), (x_hi - x_lo) / width
         nrm = np.sqrt(kx ** 2 + ky ** 2)
         kx, ky = kx / nrm, ky / nrm
-        kx = kx[::int(len(kx) / rnum)]
-        ky = ky[::int(len(ky) / rnum)]
         fs = self.field(x=x, y=y, n=n_edge, outfmt="dict")
         return x, y, kx, ky, fs["amp"], fs["phase"]
 
