@@ -311,6 +311,8 @@ class Beam:
 def _pages(xout):
     """Split ray indices into "pages" of increasing receiver coordinate (beam.py:374-398)."""
     n = len(xout)
+    if n >= 2 and bool(np.all(xout[1:] > xout[:-1])):
+        return [np.arange(n)]                  # no caustic: the whole beam is one page
     pages = [[0]] if n else []
     cur = 0
     used = {0}

@@ -265,10 +265,11 @@ def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional
                receiver=None) -> RayBundle:
     """Trace a whole fan of rays in one kernel launch (replaces beam.py:340-342).
 
-    max_steps: array length per ray (the reference's Ray.MaxStep = 100000 would
-    be 3.2 MB per ray; default here is a bound from the grid size:
-    4*(nx+ny) states, enough for any non-trapped ray; rays hitting the cap
-    report nsteps == max_steps-1 exactly like the reference at its cap).
+    max_steps: array length per ray.  The reference's Ray.MaxStep = 100000 would be 3.2 MB per
+    ray; the default here is 2*max(nx, ny) rounded up to 128 states -- a vacuum ray crosses the
+    grid in ~max(nx, ny) steps (SURVEY 3.3 i).  Rays that hit the cap report
+    nsteps == max_steps-1 exactly like the reference does at its cap, and a RuntimeWarning says
+    how many did so they can be re-traced with a larger cap (or refill=True, keep_traj=False).
 
     receiver: (val, axis) -- also report, per ray, what ``Ray.addpoint(val, axis)`` would
     (ray.py:131-224): first crossing of the receiver line, its phase and wave vector
@@ -278,7 +279,15 @@ def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional
     if amp is None:
         amp = np.ones(n)
     amp = np.broadcast_to(np.asarray(amp, np.float64), (n,)).copy()
-    L = int(max_steps) if max_steps else min(int(Ray.MaxStep), 4 * (n_field.nx + n_field.ny))
+    L = int(max_steps) if max_steps else min(int(Ray.MaxStep), -(-2 * max(n_field.nx, n_field.ny) // 128) * 128)
+    if keep_traj:
+        import torch
+        free, _total = torch.cuda.mem_get_info()
+        need = -(-n // 128) * 128 * L * 32
+        if need > 0.9 * free:
+            raise MemoryError(f"{n} rays x {L} states x 32 B = {need / 1e9:.1f} GB of trajectories exceed the free HBM "
+                              f"({free / 1e9:.1f} GB): pass keep_traj=False (per-ray outputs only), a smaller max_steps, "
+                              f"or trace the beam in chunks")
     st = float(n_field.st * Ray.kStep)
     f = _device_field(n_field)
     res = _st.trace_batch(f, xg, yg, kx, ky, L=L, st=st, dx=float(n_field.dx[0]), dy=float(n_field.dy[0]),
@@ -286,6 +295,11 @@ def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional
                           tiled=bool(tiled and keep_traj), cross=receiver,
                           x0_phys=np.ascontiguousarray(np.atleast_1d(np.asarray(x0, np.float64))) if receiver else None,
                           y0_phys=np.ascontiguousarray(np.atleast_1d(np.asarray(y0, np.float64))) if receiver else None)
+    capped = int(np.count_nonzero(np.asarray(res.nsteps) == L - 1))
+    if capped:
+        import warnings
+        warnings.warn(f"{capped} of {n} rays hit the cap of {L - 1} steps (max_steps={L}); the reference's cap is "
+                      f"Ray.MaxStep = {Ray.MaxStep}", RuntimeWarning, stacklevel=2)
     return RayBundle(n_field=n_field, x0=np.atleast_1d(np.asarray(x0, np.float64)),
                      y0=np.atleast_1d(np.asarray(y0, np.float64)), freq=freq, st=st, amp=amp,
                      xg0=xg, yg0=yg, kx0=kx, ky0=ky, nsteps=res.nsteps, end_state=res.end_state, result=res, L=L,
