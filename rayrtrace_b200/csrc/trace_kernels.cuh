@@ -135,6 +135,14 @@ __device__ __forceinline__ void div_pair(double vx, double vy, double dx, double
     wy = div_const<DIVC>(vy, dy, rdy);
 }
 
+// 0 <= v < n evaluated on the integer pipe; c = __double2int_rz(v).  See the guard in step().
+__device__ __forceinline__ bool in_range(double v, int c, int n)
+{
+    const unsigned hi = (unsigned)__double2hiint(v);
+    const bool nonneg = (hi < 0x7ff00000u) | ((hi == 0x80000000u) & (__double2loint(v) == 0));
+    return nonneg & ((unsigned)c < (unsigned)n);
+}
+
 __device__ __forceinline__ double kmod(double kx, double ky)
 {   // ray.py:115  np.sqrt(kx**2 + ky**2)
     return __dsqrt_rn(__dadd_rn(__dmul_rn(kx, kx), __dmul_rn(ky, ky)));
@@ -333,11 +341,17 @@ trace_kernel(const KParams p)
 
     // One step of the reference loop; false when the guard on state i fails (the ray has ended).
     auto step = [&]() -> bool {
-        // sidtracemodule.c:36 -- guard on state i (NaN fails every comparison)
-        if (!((i < Lm1) & (x >= 0.0) & (x < p.fx) & (y >= 0.0) & (y < p.fy))) return false;
+        // sidtracemodule.c:36 -- guard on state i:  0 <= x < nx-1  and  0 <= y < ny-1  (false for NaN).
+        // The O(rays)-output modes are bound by FP64-pipe issue, so the four FP64 compares are done
+        // on the integer pipe instead, exactly: with c = trunc(v) (saturating, NaN -> 0),
+        //   0 <= v < n   <=>   v is +finite (or -0.0)  and  (unsigned)c < n        (n integer < 2^31)
+        // "+finite": high word, read as unsigned, below 0x7ff00000 (excludes negatives, inf, NaN);
+        // -0.0 (which compares >= 0 in the reference) is admitted explicitly.
+        const int ix = __double2int_rz(x), iy = __double2int_rz(y);
+        if (!((i < Lm1) & in_range(x, ix, p.nxm1) & in_range(y, iy, p.nym1))) return false;
         const double st = STRAY ? st_r : p.st, sst = STRAY ? sst_r : p.sst;
         // :38  nearest lower-left cell, no interpolation
-        const int ind = __double2int_rz(y) * p.nxm1 + __double2int_rz(x);
+        const int ind = iy * p.nxm1 + ix;
         const double2 m = __ldg(&p.field[ind]);
 
         if (EXTRAS || HIST) {

@@ -686,3 +686,34 @@ def test_plain_c_caller_of_the_abi(st, tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "MISMATCH" not in r.stdout
+
+
+def test_guard_special_values_bitwise(st, oracle_mod):
+    """The loop guard `0 <= x < nx-1 and 0 <= y < ny-1` (sidtracemodule.c:36) is evaluated with
+    integer compares on the device: -0.0 (passes: -0.0 >= 0), tiny negatives in (-1, 0), +-inf,
+    NaN payloads, subnormals, values at and next to the upper bound, and values >= 2^31 must
+    all decide exactly as the FP64 compares of the reference do."""
+    nx, ny, L = 12, 9, 40
+    rng = np.random.default_rng(8)
+    ax, ay = random_field(rng, nx, ny, scale=0.05)
+    ax[0, :] = -0.0; ay[0, :] = -0.0                     # a -0.0 field row keeps -0.0 states alive
+    nan2 = np.frombuffer(np.uint64(0x7ff0000000000001).tobytes(), np.float64)[0]     # NaN with hi word 0x7ff00000
+    nan3 = np.frombuffer(np.uint64(0xfff8000000000000).tobytes(), np.float64)[0]
+    specials = [-0.0, 0.0, 5e-324, -5e-324, -1e-300, -0.5, -0.999999, -1.0, np.nextafter(nx - 1.0, 0), nx - 1.0,
+                np.nextafter(nx - 1.0, 99), 2.0 ** 31, 2.0 ** 31 - 0.5, 2.0 ** 40, 1e300, np.inf, -np.inf, np.nan, nan2, nan3,
+                np.nextafter(ny - 1.0, 0), ny - 1.0]
+    x0, y0, kx0, ky0 = [], [], [], []
+    for v in specials:
+        for w in (0.25, -0.0):
+            x0 += [v, w]; y0 += [w, v]
+            kx0 += [-0.0, 0.3]; ky0 += [0.2, -0.0]
+    x0, y0, kx0, ky0 = (np.array(a, np.float64) for a in (x0, y0, kx0, ky0))
+    want = oracle_mod.trace_batch(x0, y0, kx0, ky0, L, 0.5, 1.0, 1.0, nx, ny, ax, ay)
+    assert 0 < (want["nsteps"] > 0).sum() < len(x0)
+    f = st.Field(ax, ay, nx, ny)
+    for kw in (dict(), dict(refill=True), dict(tiled=True), dict(div_ieee=True), dict(want_extras=True)):
+        res = st.trace_batch(f, x0, y0, kx0, ky0, L=L, st=0.5, dx=1.0, dy=1.0, traj=True, **kw)
+        assert np.array_equal(res.nsteps, want["nsteps"]), kw
+        assert res.end_state.tobytes() == want["end"].tobytes(), kw
+        assert res.traj_ray_major().cpu().numpy().tobytes() == want["traj"].tobytes(), kw
+    f.close()
