@@ -118,6 +118,8 @@ typedef struct stb_batch_s {
 
     /* fused per-ray reductions (ray.py:113-126 and SURVEY 8c extensions); may be NULL */
     int32_t *turn_index;      /* [ray] first index j in [1,i] where ky changes sign, else -1     */
+    double  *turn_state;      /* [4][nrays] (x, y, kx, ky) of state turn_index (grid units), NaN  */
+                              /* when the ray has no turning point                               */
     double  *lax_end;         /* [ray] lax[i-1]: path-length integral over the kept states       */
     double  *ph_end;          /* [ray] ph[i-1]:  eikonal phase over the kept states              */
 
@@ -155,6 +157,13 @@ typedef struct stb_batch_s {
  * with STB_F_HOST_IO / STB_F_TRAJ_HOST it returns after the results are in
  * host memory. */
 int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream);
+
+/* Trajectory export: packs the KEPT states 0..nsteps[r]-1 of every ray (what the reference's Ray keeps,
+ * ray.py:99-102) from a trajectory arena -- ray-major (tile = 0, ray_stride doubles per ray, 0 -> 4*L) or
+ * tiled (tile = 32 / 64 / 128) -- into out[offsets[r] .. offsets[r] + nsteps[r]][4].  All pointers are
+ * DEVICE pointers; offsets is an exclusive prefix sum of nsteps (int64).  Asynchronous on `stream`. */
+int stb_pack_traj(const double *traj, int tile, int64_t ray_stride, int64_t L, int64_t nrays,
+                  const int32_t *nsteps, const int64_t *offsets, double *out, void *stream);
 
 /* number of kernel launches issued by this library so far (all threads) */
 int64_t stb_launch_count(void);

@@ -27,7 +27,7 @@ F_STATIC = 1 << 5
 EXPORTS = (
     "stb_abi_version", "stb_last_error", "stb_device_count", "stb_set_device",
     "stb_field_create", "stb_field_destroy", "stb_field_shape", "stb_field_peek",
-    "stb_trace", "stb_check", "stb_trace_batch", "stb_launch_count",
+    "stb_trace", "stb_check", "stb_trace_batch", "stb_pack_traj", "stb_launch_count",
     "stb_measure_fp64_peak", "stb_measure_store_bw",
 )
 
@@ -49,6 +49,7 @@ class StbBatch(Structure):
         ("nsteps", c_void_p),
         ("end_state", c_void_p),
         ("turn_index", c_void_p),
+        ("turn_state", c_void_p),
         ("lax_end", c_void_p),
         ("ph_end", c_void_p),
         ("hist", c_void_p),
@@ -92,6 +93,8 @@ def _load() -> ctypes.CDLL:
                               c_double, c_double, c_double, POINTER(c_int64)]
     lib.stb_check.argtypes = [c_int, c_int, c_int, c_int, c_void_p, POINTER(c_double)]
     lib.stb_trace_batch.argtypes = [c_void_p, POINTER(StbBatch), c_void_p]
+    lib.stb_pack_traj.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.stb_pack_traj.restype = c_int
     lib.stb_launch_count.restype = c_int64
     lib.stb_launch_count.argtypes = []
     lib.stb_measure_fp64_peak.argtypes = [POINTER(c_double)]

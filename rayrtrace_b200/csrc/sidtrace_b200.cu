@@ -266,7 +266,7 @@ int launch_trace(const KParams &p, bool divc, bool refill, bool tiled, int num_s
     if (tiled) {
         // warp-tile schedule: plain trajectories and/or fused running sums; the histogram keeps
         // the ray-granular kernels
-        const bool extras = p.turn || p.lax_end || p.ph_end;
+        const bool extras = p.turn || p.turn_state || p.lax_end || p.ph_end;
         if (p.hist) return fail(STB_ERR_ARG, "STB_F_TRAJ_TILED cannot be combined with the histogram output");
         const int key = (p.traj ? 4 : 0) | (extras ? 2 : 0) | (divc ? 1 : 0);
         switch (key) {
@@ -281,7 +281,7 @@ int launch_trace(const KParams &p, bool divc, bool refill, bool tiled, int num_s
         }
     }
     const bool traj = p.traj != nullptr;
-    const bool extras = p.turn || p.lax_end || p.ph_end;
+    const bool extras = p.turn || p.turn_state || p.lax_end || p.ph_end;
     const bool hist = p.hist != nullptr;
     const int key = (traj ? 4 : 0) | (extras ? 2 : 0) | (hist ? 1 : 0);
     switch (key) {
@@ -341,7 +341,7 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     if (p.tile != 32 && p.tile != 64 && p.tile != 128)
         return fail(STB_ERR_ARG, "stb_trace_batch: traj_tile must be 32, 64 or 128 (got %d)", b->traj_tile);
     p.nsteps = b->nsteps; p.endst = b->end_state;
-    p.turn = b->turn_index; p.lax_end = b->lax_end; p.ph_end = b->ph_end;
+    p.turn = b->turn_index; p.turn_state = b->turn_state; p.lax_end = b->lax_end; p.ph_end = b->ph_end;
     p.hist = b->hist; p.nbins = b->nbins; p.amp = b->amp;
     p.xorg = b->xorg; p.yorg = b->yorg; p.r_lcs = b->r_lcs; p.rho_max = b->rho_max;
     p.r_rlcs = 1.0 / b->r_lcs; p.r_rhomax = 1.0 / b->rho_max;
@@ -402,12 +402,13 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
     // writes them in place over PCIe, overlapped with the tracing itself: no staging copies,
     // no serial H2D -> kernel -> D2H chain.  Pageable buffers take the staged path below.
     if (host_io && tiled && !traj_host && !b->hist && n) {
-        const void *hp[17] = {b->x0, b->y0, b->kx0, b->ky0, b->st_ray, b->amp,
+        const void *hp[18] = {b->x0, b->y0, b->kx0, b->ky0, b->st_ray, b->amp,
                               b->nsteps, b->end_state, b->turn_index, b->lax_end, b->ph_end,
-                              b->x0_phys, b->y0_phys, b->cross_count, b->cross_index, b->cross_flags, b->cross_state};
-        void *dp[17];
+                              b->x0_phys, b->y0_phys, b->cross_count, b->cross_index, b->cross_flags, b->cross_state,
+                              b->turn_state};
+        void *dp[18];
         bool all = true;
-        for (int k = 0; k < 17; ++k) {
+        for (int k = 0; k < 18; ++k) {
             dp[k] = mapped_alias(hp[k]);
             if (hp[k] && !dp[k]) all = false;
         }
@@ -420,6 +421,7 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
             p.x0p = (const double *)dp[11]; p.y0p = (const double *)dp[12];
             p.cross_count = (int *)dp[13]; p.cross_index = (int *)dp[14]; p.cross_flags = (int *)dp[15];
             p.cross_state = (double *)dp[16];
+            p.turn_state = (double *)dp[17];
             rc = launch_trace(p, divc, refill, tiled, f->num_sms, s);
             if (rc != STB_OK) return rc;
             CU(cudaStreamSynchronize(s));
@@ -450,7 +452,7 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
             p.lookup_ph = d;
         }
         // ---- outputs: [end 4n | lax n | ph n | cross_state 6n | nsteps, turn, cross_count/index/flags n(i32) each] ----
-        rc = f->ws_out.ensure(nb * 16 + 5 * n * sizeof(int32_t) + 64);
+        rc = f->ws_out.ensure(nb * 20 + 5 * n * sizeof(int32_t) + 64);
         if (rc != STB_OK) return rc;
         double *dout = (double *)f->ws_out.p;
         p.endst = b->end_state ? dout : nullptr;
@@ -458,7 +460,8 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
         p.ph_end = b->ph_end ? dout + 5 * n : nullptr;
         p.cross_state = b->cross_state ? dout + 6 * n : nullptr;
         p.lookup_xy = b->lookup_xy ? dout + 12 * n : nullptr;
-        int32_t *iout = (int32_t *)(dout + 16 * n);
+        p.turn_state = b->turn_state ? dout + 16 * n : nullptr;
+        int32_t *iout = (int32_t *)(dout + 20 * n);
         p.nsteps = b->nsteps ? iout : nullptr;
         p.turn = b->turn_index ? iout + n : nullptr;
         p.cross_count = b->cross_count ? iout + 2 * n : nullptr;
@@ -490,6 +493,7 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
         if (b->turn_index) CU(cudaMemcpyAsync(b->turn_index, p.turn, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         if (b->cross_state) CU(cudaMemcpyAsync(b->cross_state, p.cross_state, 6 * nb, cudaMemcpyDeviceToHost, s));
         if (b->lookup_xy) CU(cudaMemcpyAsync(b->lookup_xy, p.lookup_xy, 4 * nb, cudaMemcpyDeviceToHost, s));
+        if (b->turn_state) CU(cudaMemcpyAsync(b->turn_state, p.turn_state, 4 * nb, cudaMemcpyDeviceToHost, s));
         if (b->cross_count) CU(cudaMemcpyAsync(b->cross_count, p.cross_count, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         if (b->cross_index) CU(cudaMemcpyAsync(b->cross_index, p.cross_index, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         if (b->cross_flags) CU(cudaMemcpyAsync(b->cross_flags, p.cross_flags, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -551,6 +555,25 @@ int stb_trace(stb_field_t f, double *x, double *y, double *kx, double *ky, int64
         }
     }
     *nsteps = n;
+    return STB_OK;
+}
+
+int stb_pack_traj(const double *traj, int tile, int64_t ray_stride, int64_t L, int64_t nrays,
+                  const int32_t *nsteps, const int64_t *offsets, double *out, void *stream)
+{
+    if (!traj || !nsteps || !offsets || !out) return fail(STB_ERR_ARG, "stb_pack_traj: NULL argument");
+    if (tile != 0 && tile != 32 && tile != 64 && tile != 128) return fail(STB_ERR_ARG, "stb_pack_traj: tile must be 0, 32, 64 or 128");
+    if (nrays <= 0) return STB_OK;
+    if (!tile && ray_stride == 0) ray_stride = 4 * L;
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long blocks = (nrays * 32 + 255) / 256;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    stb::pack_traj_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        traj, tile, (long long)ray_stride, (long long)L, (long long)nrays, nsteps, (const long long *)offsets, out);
+    g_launches++;
+    CU(cudaGetLastError());
     return STB_OK;
 }
 

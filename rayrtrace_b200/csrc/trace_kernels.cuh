@@ -53,6 +53,7 @@ struct KParams {
     int *nsteps;
     double *endst;
     int *turn;
+    double *turn_state;                  // [4][nrays]
     double *lax_end, *ph_end;
     double *hist;
     int nbins;
@@ -206,6 +207,7 @@ trace_kernel(const KParams p)
     double *tp = nullptr;
     // extras
     int turn = -1;
+    double tsx = 0, tsy = 0, tskx = 0, tsky = 0;   // state at the turning index
     double kprev = 0, lax = 0, ph = 0, a2 = 1.0;
     int binprev = -1;        // HIST: flux bin of the previous kept state = bin of the current run
     double binacc = 0.0;     // HIST: weight gathered for that bin since the ray entered it
@@ -302,6 +304,13 @@ trace_kernel(const KParams p)
         }
         if (EXTRAS) {
             if (p.turn) p.turn[ray] = turn;
+            if (p.turn_state) {
+                const bool has = turn >= 0;
+                p.turn_state[0 * p.nrays + ray] = has ? tsx : qnan;
+                p.turn_state[1 * p.nrays + ray] = has ? tsy : qnan;
+                p.turn_state[2 * p.nrays + ray] = has ? tskx : qnan;
+                p.turn_state[3 * p.nrays + ray] = has ? tsky : qnan;
+            }
             if (p.lax_end) p.lax_end[ray] = lax;
             if (p.ph_end) p.ph_end[ray] = ph;
         }
@@ -445,7 +454,10 @@ trace_kernel(const KParams p)
         const double ky1 = __dadd_rn(ky, __dmul_rn(st, m.y));     // :45
 
         if (EXTRAS) {
-            if (turn < 0 && ((ky > 0.0 && ky1 <= 0.0) || (ky < 0.0 && ky1 >= 0.0))) turn = i + 1;
+            if (turn < 0 && ((ky > 0.0 && ky1 <= 0.0) || (ky < 0.0 && ky1 >= 0.0))) {
+                turn = i + 1;
+                tsx = x1; tsy = y1; tskx = kx1; tsky = ky1;
+            }
         }
         x = x1; y = y1; kx = kx1; ky = ky1;
         ++i;
@@ -526,6 +538,28 @@ __global__ void interleave_kernel(const double *__restrict__ ax, const double *_
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long step = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += step) out[i] = make_double2(ax[i], ay[i]);
+}
+
+// Trajectory export: one warp per ray copies the KEPT states 0..n-1 (ray.py:99-102) of a
+// trajectory arena -- ray-major (tile == 0) or tiled -- into a packed [total][4] buffer at
+// offsets[ray]; 32 B per lane per iteration, coalesced on the packed side.
+__global__ void pack_traj_kernel(const double *__restrict__ traj, int tile, long long ray_stride, long long L,
+                                 long long nrays, const int *__restrict__ nsteps,
+                                 const long long *__restrict__ offsets, double *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < nrays; r += nwarps) {
+        const int n = nsteps[r];
+        const double *src = tile ? traj + ((r / tile) * L * tile + (r % tile)) * 4 : traj + r * ray_stride;
+        const long long step = tile ? 4LL * tile : 4;
+        double *dst = out + offsets[r] * 4;
+        for (int j = lane; j < n; j += 32) {
+            const double4 v = *reinterpret_cast<const double4 *>(src + j * step);
+            st_state(dst + 4LL * j, v.x, v.y, v.z, v.w);
+        }
+    }
 }
 
 // FP64 peak: 8 independent DFMA chains per thread

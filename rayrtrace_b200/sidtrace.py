@@ -230,6 +230,7 @@ class BatchResult:
     end_state: object = None    # float64 [4, nrays]  (x, y, kx, ky) at index nsteps
     traj: object = None         # float64 [nrays, L, 4] CUDA tensor (or numpy with traj_host)
     turn_index: object = None   # int32 [nrays]
+    turn_state: object = None   # float64 [4, nrays] (x, y, kx, ky) at turn_index (grid units), NaN if none
     lax_end: object = None      # float64 [nrays]
     ph_end: object = None       # float64 [nrays]
     hist: object = None         # float64 [nbins]
@@ -347,6 +348,8 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     if want_extras:
         if res.turn_index is None:
             res.turn_index = alloc((n,), np.int32, torch.int32)
+        if res.turn_state is None:
+            res.turn_state = alloc((4, n), np.float64, torch.float64)
         if res.lax_end is None:
             res.lax_end = alloc((n,), np.float64, torch.float64)
         if res.ph_end is None:
@@ -432,6 +435,7 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     b.end_state = _ptr(res.end_state) if want_end else None
     if want_extras:
         b.turn_index, b.lax_end, b.ph_end = _ptr(res.turn_index), _ptr(res.lax_end), _ptr(res.ph_end)
+        b.turn_state = _ptr(res.turn_state)
     if hist is not None:
         b.hist = _ptr(hist)
         b.nbins = nbins

@@ -222,7 +222,12 @@ def test_extras_bitwise_vs_oracle(st, oracle_mod):
     res, want, _ = _oracle_vs_gpu(st, oracle_mod, rng, nx, ny, n, L, want_extras=True)
     for r in range(n):
         k = int(want["nsteps"][r])
-        assert int(res.turn_index[r]) == oracle_mod.turning_point(want["traj"][r], k)
+        tp = oracle_mod.turning_point(want["traj"][r], k)
+        assert int(res.turn_index[r]) == tp
+        if tp >= 0:      # turning point = the reference-identical state at that index, bit for bit
+            assert res.turn_state[:, r].tobytes() == want["traj"][r, tp].tobytes()
+        else:
+            assert np.isnan(res.turn_state[:, r]).all()
         if k >= 1:
             lax, ph = oracle_mod.lax_ph(want["traj"][r, :k], 0.37)
             assert float(res.lax_end[r]).hex() == float(lax[-1]).hex()
@@ -716,4 +721,25 @@ def test_guard_special_values_bitwise(st, oracle_mod):
         assert np.array_equal(res.nsteps, want["nsteps"]), kw
         assert res.end_state.tobytes() == want["end"].tobytes(), kw
         assert res.traj_ray_major().cpu().numpy().tobytes() == want["traj"].tobytes(), kw
+    f.close()
+
+
+def test_trajectory_export_to_host_packed(st, oracle_mod):
+    """export.trace_to_host: chunked trace + pack + device-to-host copy on a second stream; the
+    packed states of every ray equal the oracle's kept trajectory bit for bit."""
+    from rayrtrace_b200 import export
+    rng = np.random.default_rng(55)
+    nx, ny, n, L = 80, 64, 5000 + 9, 200
+    ax, ay = random_field(rng, nx, ny)
+    launch = random_launch(rng, n, nx, ny)
+    launch[0][:2] = (-3.0, np.nan)                                  # rays with zero kept states
+    want = oracle_mod.trace_batch(*launch, L, 0.37, 0.8, 1.3, nx, ny, ax, ay, nthreads=4)
+    f = st.Field(ax, ay, nx, ny)
+    for chunk in (640, 100000):                                      # many chunks (ragged last one) / a single chunk
+        off, states, nsteps, end = export.trace_to_host(f, *launch, L=L, st=0.37, dx=0.8, dy=1.3, chunk_rays=chunk)
+        assert np.array_equal(nsteps, want["nsteps"]) and end.tobytes() == want["end"].tobytes()
+        assert off[-1] == want["nsteps"].sum() == states.shape[0]
+        for r in range(0, n, 7):
+            k = int(want["nsteps"][r])
+            assert states[off[r]:off[r + 1]].tobytes() == want["traj"][r, :k].tobytes()
     f.close()
