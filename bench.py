@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
     ap.add_argument("--extra", action="store_true", help="also time endpoint-only mode and the FP64 peak")
+    ap.add_argument("--no-traj-export", action="store_true", help="skip the trajectories-to-host side measurement")
     ap.add_argument("--layout", default="tiled", choices=["tiled", "ray"],
                     help="trajectory layout: tiled [tile][step][32][4] (default) or ray-major [ray][step][4]")
     return ap.parse_args()
@@ -344,6 +345,25 @@ def run_b200(args):
     h2d = 4 * n * 8
     d2h = n * 4 + 4 * n * 8
 
+    # ---- for transparency: the same metric when EVERY state must reach host memory (packed
+    # export, PCIe-bound at 32 B per ray-step); bounded sample, rank 0 only.
+    traj_host = None
+    if rank == 0 and not args.no_traj_export:
+        from rayrtrace_b200 import export
+        m = min(n, 62_500)
+        sel = np.linspace(0, n - 1, m).astype(np.int64)
+        sub = [np.ascontiguousarray(a[sel]) for a in case.launch]
+        out_pin = sidtrace.pinned_empty((int(m * (steps_per_launch / n) * 1.3) + 1024, 4))
+        export.trace_to_host(field, *sub, L=L, st=case.st, dx=case.dx, dy=case.dy, out=out_pin)     # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        off, _, _, _ = export.trace_to_host(field, *sub, L=L, st=case.st, dx=case.dx, dy=case.dy, out=out_pin)
+        dt = time.perf_counter() - t0
+        traj_host = {"value": float(off[-1]) / dt, "unit": UNIT, "d2h_bytes": int(off[-1]) * 32, "sample_rays": int(m),
+                     "note": "export.trace_to_host: chunked trace, pack, D2H of every kept state into pinned host memory, "
+                             "copies overlapped with tracing on a second stream; PCIe-bound"}
+        del out_pin
+
     extra = {}
     if args.extra and rank == 0:
         import ctypes
@@ -396,6 +416,8 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": clk,
     }
+    if traj_host:
+        line["e2e_traj_to_host"] = traj_host
     if extra:
         line["extra"] = extra
     print(json.dumps(line), flush=True)
