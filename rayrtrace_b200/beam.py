@@ -20,7 +20,7 @@ from scipy import constants as const
 from scipy.interpolate import interp1d
 from scipy.optimize import curve_fit
 
-from .ray import Ray, trace_rays
+from .ray import trace_rays
 
 
 class Beam:

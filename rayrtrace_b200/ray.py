@@ -12,7 +12,7 @@ launch; trajectories stay in HBM and are read back per ray on demand.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field as _dc_field
+from dataclasses import dataclass
 from typing import Optional
 
 import numpy as np
@@ -191,7 +191,6 @@ class RayBundle:
     result: object = None     # sidtrace.BatchResult (traj is a CUDA tensor or None)
     L: int = 0                # states per ray the launch was sized for
     receiver: object = None   # (val, axis) of the fused crossing output, if any
-    _cache: dict = _dc_field(default_factory=dict)
 
     def __len__(self):
         return len(self.nsteps)
