@@ -516,43 +516,42 @@ int stb_trace(stb_field_t f, double *x, double *y, double *kx, double *ky, int64
     if (dev != f->device)
         return fail(STB_ERR_ARG, "stb_trace: the field lives on device %d but the current device is %d", f->device, dev);
     std::lock_guard<std::mutex> lk(f->mu);
-    // workspace: launch state (4 doubles) | nsteps (i32) ; trajectory [L][4]
-    int rc = f->ws_in.ensure(64);
+    // One pinned, device-mapped workspace: [launch state 4 doubles | nsteps | pad] [trajectory L x 4].
+    // The single-ray kernel reads the launch state and writes every state straight into it over
+    // PCIe (posted stores, off the critical path), so a call is one launch + one synchronize:
+    // no cudaMemcpy in either direction.
+    const size_t head = 64;   // bytes
+    int rc = f->pin.ensure(head + (size_t)L * 4 * sizeof(double));
     if (rc != STB_OK) return rc;
-    rc = f->ws_out.ensure(64);
-    if (rc != STB_OK) return rc;
-    rc = f->ws_traj.ensure((size_t)L * 4 * sizeof(double));
-    if (rc != STB_OK) return rc;
-    rc = f->pin.ensure((size_t)L * 4 * sizeof(double));
-    if (rc != STB_OK) return rc;
-
-    double h0[4] = {x[0], y[0], kx[0], ky[0]};
-    double *din = (double *)f->ws_in.p;
-    CU(cudaMemcpyAsync(din, h0, sizeof(h0), cudaMemcpyHostToDevice, 0));
+    double *h = (double *)f->pin.p;
+    void *dptr = nullptr;
+    CU(cudaHostGetDevicePointer(&dptr, h, 0));
+    double *d = (double *)dptr;
+    h[0] = x[0]; h[1] = y[0]; h[2] = kx[0]; h[3] = ky[0];
+    volatile int32_t *hn = (volatile int32_t *)(h + 4);
+    *hn = -1;
 
     stb_batch_t b{};
     b.struct_size = sizeof(b);
     b.nrays = 1; b.L = L;
-    b.x0 = din; b.y0 = din + 1; b.kx0 = din + 2; b.ky0 = din + 3;
+    b.x0 = d; b.y0 = d + 1; b.kx0 = d + 2; b.ky0 = d + 3;
     b.st = st; b.dx = dx; b.dy = dy;
-    b.traj = (double *)f->ws_traj.p;
-    b.nsteps = (int32_t *)f->ws_out.p;
+    b.traj = d + head / sizeof(double);
+    b.nsteps = (int32_t *)(d + 4);
     KParams p{};
     bool divc = false;
     rc = fill_params(f, &b, p, divc);
     if (rc != STB_OK) return rc;
     rc = launch_trace(p, divc, /*refill=*/false, /*tiled=*/false, f->num_sms, 0);
     if (rc != STB_OK) return rc;
-    int32_t n = 0;
-    CU(cudaMemcpy(&n, b.nsteps, sizeof(n), cudaMemcpyDeviceToHost));
-    if (n > 0) {
-        double *h = (double *)f->pin.p;
-        CU(cudaMemcpy(h, b.traj, (size_t)(n + 1) * 4 * sizeof(double), cudaMemcpyDeviceToHost));
-        // scatter the interleaved states 1..n into the caller's four arrays
-        // (sidtracemodule.c:41-45 writes xx[i+1], yy[i+1], kxx[i+1], kyy[i+1]); data marshalling only
-        for (int32_t j = 1; j <= n; ++j) {
-            x[j] = h[4 * j + 0]; y[j] = h[4 * j + 1]; kx[j] = h[4 * j + 2]; ky[j] = h[4 * j + 3];
-        }
+    CU(cudaStreamSynchronize(0));
+    const int32_t n = *hn;
+    if (n < 0 || n > L - 1) return fail(STB_ERR_CUDA, "stb_trace: kernel reported %d steps", (int)n);
+    // scatter the interleaved states 1..n into the caller's four arrays
+    // (sidtracemodule.c:41-45 writes xx[i+1], yy[i+1], kxx[i+1], kyy[i+1]); data marshalling only
+    const double *t = h + head / sizeof(double);
+    for (int32_t j = 1; j <= n; ++j) {
+        x[j] = t[4 * j + 0]; y[j] = t[4 * j + 1]; kx[j] = t[4 * j + 2]; ky[j] = t[4 * j + 3];
     }
     *nsteps = n;
     return STB_OK;
