@@ -230,7 +230,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -419,11 +419,28 @@ def run_b200(args):
         line["e2e_traj_to_host"] = traj_host
     if extra:
         line["extra"] = extra
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's original stdout; everything else any library prints
+    to fd 1 (e.g. NCCL's version banner) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
