@@ -195,7 +195,7 @@ def load_traffic():
 
 def workload_name(args):
     return (f"config3: {args.nrays}-ray seven-beam FT-2 fan per GPU, {args.nx}x{args.nx} shaped-density grid, "
-            f"full trajectories f64 in HBM, layout {'[ray/128][step][ray%128][4]' if args.layout == 'tiled' else '[ray][step][4]'}")
+            f"full trajectories f64 in HBM, layout {'[ray/256][step][ray%256][4]' if args.layout == 'tiled' else '[ray][step][4]'}")
 
 
 # --------------------------------------------------------------------------
@@ -274,7 +274,7 @@ def run_b200(args):
     n, L = case.nrays, case.L
     d_in = [torch.from_numpy(a).to(dev) for a in case.launch]
     tiled = args.layout == "tiled"
-    traj = torch.empty(((n + 127) // 128, L, 128, 4) if tiled else (n, L, 4), dtype=torch.float64, device=dev)
+    traj = torch.empty(((n + 255) // 256, L, 256, 4) if tiled else (n, L, 4), dtype=torch.float64, device=dev)
     out = sidtrace.BatchResult(nsteps=torch.empty(n, dtype=torch.int32, device=dev),
                                end_state=torch.empty((4, n), dtype=torch.float64, device=dev), traj=traj)
     kw = dict(L=L, st=case.st, dx=case.dx, dy=case.dy, tiled=tiled)
@@ -405,7 +405,7 @@ def run_b200(args):
                    "parallelism": f"rays interleaved over {world} rank(s), field replicated, no data-path collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (tr or {}).get("dram_bytes_per_launch"),
-                     "kernel": "stb::trace_kernel<TRAJ=1,EXTRAS=0,HIST=0,DIVC=1,REFILL=0,TILED=%d,CROSS=0,STRAY=0>" % int(tiled),
+                     "kernel": "stb::trace_kernel<TRAJ=1,EXTRAS=0,HIST=0,DIVC=1,REFILL=0,TILED=%d,CROSS=0,STRAY=0,LOOKUP=0,BLOCK=%d>" % (int(tiled), 256 if tiled else 128),
                      "algorithmic_bytes_per_launch": BYTES_PER_RAY_STEP * steps_per_launch,
                      "avg_launch_ms": avg_kernel_ms, "peak_source": peak_src},
         "cpu_baseline": cpu,

@@ -110,9 +110,9 @@ typedef struct stb_batch_s {
     double  *traj;            /* [ray][step][4] = (x, y, kx, ky); states 0..i written, rest      */
                               /* untouched (sidtracemodule.c:36-48)                              */
     int64_t  traj_ray_stride; /* in doubles, >= 4*L, multiple of 4 (0 -> 4*L)                    */
-    int32_t  traj_tile;       /* STB_F_TRAJ_TILED: rays per tile T = 32 / 64 / 128 (0 -> 128): layout   */
-                              /* [ray/T][step][ray%T][4], ceil(nrays/T)*L*T*4 doubles; T = 128 = one    */
-                              /* CTA = 4 KB contiguous rows (measured best: 0.97 of the HBM copy peak) */
+    int32_t  traj_tile;       /* STB_F_TRAJ_TILED: rays per tile T = 32 / 64 / 128 / 256 (0 -> 256):    */
+                              /* layout [ray/T][step][ray%T][4], ceil(nrays/T)*L*T*4 doubles; T = 256 = */
+                              /* one 256-thread CTA = 8 KB contiguous rows (0.98 of the HBM copy peak)  */
     int32_t *nsteps;          /* [ray] i = steps taken = index of last written state            */
     double  *end_state;       /* [4][nrays] state at index i                                     */
 

@@ -211,6 +211,17 @@ int launch_variant(const KParams &p, bool refill, int num_sms, cudaStream_t s)
     if constexpr (STRAY && !EXTRAS && !HIST && !CROSS) {
         if (!p.st_ray) return launch_variant<TRAJ, EXTRAS, HIST, DIVC, TILED, CROSS, false>(p, refill, num_sms, s);
     }
+    // static tiled trajectories over 256-ray tiles: 256-thread CTAs, one 8 KB row per CTA-step
+    if constexpr (TRAJ && TILED && !EXTRAS && !HIST && !CROSS) {
+        if (!refill && p.tile == 256 && p.nrays > 0) {
+            const long long blocks = (p.nrays + 255) / 256;
+            if (blocks > 0x7fffffffLL) return fail(STB_ERR_ARG, "too many rays for a static grid");
+            stb::trace_kernel<true, false, false, DIVC, false, true, false, STRAY, false, 256><<<(unsigned)blocks, 256, 0, s>>>(p);
+            g_launches++;
+            CU(cudaGetLastError());
+            return STB_OK;
+        }
+    }
     const size_t smem = HIST ? (size_t)p.nbins * sizeof(double) : 0;
     if (p.nrays <= 0) return STB_OK;
     long long blocks_all = (p.nrays + stb::kBlock - 1) / stb::kBlock;
@@ -337,9 +348,9 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     p.st = b->st; p.sst = b->st * b->st; p.st_ray = b->st_ray;
     p.dx = b->dx; p.dy = b->dy; p.rdx = 1.0 / b->dx; p.rdy = 1.0 / b->dy;
     p.traj = b->traj; p.stride = stride;
-    p.tile = b->traj_tile ? b->traj_tile : 128;
-    if (p.tile != 32 && p.tile != 64 && p.tile != 128)
-        return fail(STB_ERR_ARG, "stb_trace_batch: traj_tile must be 32, 64 or 128 (got %d)", b->traj_tile);
+    p.tile = b->traj_tile ? b->traj_tile : 256;
+    if (p.tile != 32 && p.tile != 64 && p.tile != 128 && p.tile != 256)
+        return fail(STB_ERR_ARG, "stb_trace_batch: traj_tile must be 32, 64, 128 or 256 (got %d)", b->traj_tile);
     p.nsteps = b->nsteps; p.endst = b->end_state;
     p.turn = b->turn_index; p.turn_state = b->turn_state; p.lax_end = b->lax_end; p.ph_end = b->ph_end;
     p.hist = b->hist; p.nbins = b->nbins; p.amp = b->amp;
@@ -561,7 +572,8 @@ int stb_pack_traj(const double *traj, int tile, int64_t ray_stride, int64_t L, i
                   const int32_t *nsteps, const int64_t *offsets, double *out, void *stream)
 {
     if (!traj || !nsteps || !offsets || !out) return fail(STB_ERR_ARG, "stb_pack_traj: NULL argument");
-    if (tile != 0 && tile != 32 && tile != 64 && tile != 128) return fail(STB_ERR_ARG, "stb_pack_traj: tile must be 0, 32, 64 or 128");
+    if (tile != 0 && tile != 32 && tile != 64 && tile != 128 && tile != 256)
+        return fail(STB_ERR_ARG, "stb_pack_traj: tile must be 0, 32, 64, 128 or 256");
     if (nrays <= 0) return STB_OK;
     if (!tile && ray_stride == 0) ray_stride = 4 * L;
     int dev = 0, sms = 0;

@@ -31,7 +31,7 @@
 
 namespace stb {
 
-constexpr int kBlock = 128;   // threads per CTA (4 warps)
+constexpr int kBlock = 128;   // threads per CTA (4 warps); the tiled trajectory kernel also runs with 256
 #ifndef STB_MINB
 #define STB_MINB 12           // min resident CTAs/SM asked of ptxas for the lean variants: 40 registers,
 #endif                        // 48 warps/SM (measured: +4..7 % in endpoint mode, neutral for trajectories;
@@ -94,6 +94,7 @@ __device__ __forceinline__ double cross_solve(double c0, double k, double a, dou
 __device__ __forceinline__ void st_state(double *p, double a, double b, double c, double d)
 {
     // one ray-step = one 32-byte sector = one STG.E.ENL2.256
+    // (st.global.cs -- evict-first -- measured the same within noise; plain stores kept)
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
                  :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
@@ -184,14 +185,18 @@ __device__ __forceinline__ void hist_add(double *sh, int b, double w)
 // 122-126) -- is sampled at two target phases by linear interpolation / end-segment
 // extrapolation, exactly what interp1d(r.ph, r.x, fill_value='extrapolate') does in
 // beam.py:410-413.  Nothing is stored: the ray is simply traced again.
+//
+// BLOCK: threads per CTA.  128 everywhere except the static tiled trajectory kernel, which runs
+// 256-thread CTAs over 256-ray tiles: a CTA-step is then one contiguous 8 KB row (+1.3 % over 4 KB
+// rows, profiles/r01/kernel_sweep_block256_cs.txt; the O(rays)-output modes lose 0.5-3 % with 256).
 template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool REFILL, bool TILED = false, bool CROSS = false,
-          bool STRAY = true, bool LOOKUP = false>
-__global__ void __launch_bounds__(kBlock, (CROSS || HIST || EXTRAS) ? 1 : STB_MINB)
+          bool STRAY = true, bool LOOKUP = false, int BLOCK = kBlock>
+__global__ void __launch_bounds__(BLOCK, (CROSS || HIST || EXTRAS) ? 1 : STB_MINB * kBlock / BLOCK)
 trace_kernel(const KParams p)
 {
     extern __shared__ double sh_hist[];
     if (HIST) {
-        for (int b = threadIdx.x; b < p.nbins; b += kBlock) sh_hist[b] = 0.0;
+        for (int b = threadIdx.x; b < p.nbins; b += BLOCK) sh_hist[b] = 0.0;
         __syncthreads();
     }
 
@@ -472,7 +477,7 @@ trace_kernel(const KParams p)
         // ---- whole-ray schedules: claim, trace to the end in a plain per-thread loop, retire.
         // No vote per step: lanes that finish early wait at the reconvergence point after the
         // inner loop, which for a tile of neighbouring rays costs a few steps.
-        long long r = REFILL ? 0 : (long long)blockIdx.x * kBlock + threadIdx.x;
+        long long r = REFILL ? 0 : (long long)blockIdx.x * BLOCK + threadIdx.x;
         for (;;) {
             if (REFILL) {   // TILED: one aggregated claim of 32 consecutive rays per warp
                 unsigned long long base = 0;
@@ -523,7 +528,7 @@ trace_kernel(const KParams p)
 
     if (HIST) {
         __syncthreads();
-        for (int b = threadIdx.x; b < p.nbins; b += kBlock) {
+        for (int b = threadIdx.x; b < p.nbins; b += BLOCK) {
             const double v = sh_hist[b];
             if (v != 0.0) atomicAdd(&p.hist[b], v);
         }

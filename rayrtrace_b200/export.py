@@ -43,9 +43,9 @@ def trace_to_host(field, x0, y0, kx0, ky0, *, L, st, dx, dy, chunk_rays=131072, 
         raise ValueError(f"out must be a C-contiguous float64 array of shape [>= {total}, 4]")
 
     chunk = int(min(max(chunk_rays, 128), max(n, 1)))
-    chunk = -(-chunk // 128) * 128
+    chunk = -(-chunk // 256) * 256
     s_trace, s_copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    arenas = [torch.empty((chunk // 128, L, 128, 4), dtype=torch.float64, device=dev) for _ in range(2)]
+    arenas = [torch.empty((chunk // 256, L, 256, 4), dtype=torch.float64, device=dev) for _ in range(2)]
     max_steps_chunk = int(max((offsets[min(i + chunk, n)] - offsets[i]) for i in range(0, n, chunk))) if n else 0
     packed = [torch.empty((max(max_steps_chunk, 1), 4), dtype=torch.float64, device=dev) for _ in range(2)]
     free = [torch.cuda.Event(), torch.cuda.Event()]        # arena/packed slot k is free again
@@ -63,15 +63,15 @@ def trace_to_host(field, x0, y0, kx0, ky0, *, L, st, dx, dy, chunk_rays=131072, 
             d_in = [torch.from_numpy(a[lo:hi]).to(dev, non_blocking=True) for a in ins]
             d_sr = torch.from_numpy(st_ray[lo:hi]).to(dev, non_blocking=True) if st_ray is not None else None
             s_trace.wait_event(free[slot])
-            traj = arenas[slot][: -(-m // 128)]
-            sidtrace.trace_batch(field, *d_in, traj=traj, tiled=True, tile=128, st_ray=d_sr, want_end=False, stream=s_trace, **kw)
+            traj = arenas[slot][: -(-m // 256)]
+            sidtrace.trace_batch(field, *d_in, traj=traj, tiled=True, tile=256, st_ray=d_sr, want_end=False, stream=s_trace, **kw)
             done = torch.cuda.Event()
             done.record(s_trace)
         with torch.cuda.stream(s_copy):
             s_copy.wait_event(done)
             nst = int(offsets[hi] - offsets[lo])
             local_off = d_off[lo:hi] - int(offsets[lo])
-            _cabi.check(_cabi.lib.stb_pack_traj(traj.data_ptr(), 128, 0, int(L), m, d_ns[lo:hi].data_ptr(),
+            _cabi.check(_cabi.lib.stb_pack_traj(traj.data_ptr(), 256, 0, int(L), m, d_ns[lo:hi].data_ptr(),
                                                 local_off.data_ptr(), packed[slot].data_ptr(),
                                                 ctypes.c_void_p(s_copy.cuda_stream)))
             if nst:

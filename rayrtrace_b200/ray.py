@@ -282,7 +282,7 @@ def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional
     if keep_traj:
         import torch
         free, _total = torch.cuda.mem_get_info()
-        need = -(-n // 128) * 128 * L * 32
+        need = -(-n // 256) * 256 * L * 32
         if need > 0.9 * free:
             raise MemoryError(f"{n} rays x {L} states x 32 B = {need / 1e9:.1f} GB of trajectories exceed the free HBM "
                               f"({free / 1e9:.1f} GB): pass keep_traj=False (per-ray outputs only), a smaller max_steps, "

@@ -239,7 +239,7 @@ class BatchResult:
     cross_flags: object = None  # int32 [nrays]   bit 0 exact hit, bit 1 extrapolated past the end
     cross_state: object = None  # float64 [6, nrays]  x, y (cm), kx, ky, lax, ph at the first crossing
     lookup_xy: object = None    # float64 [4, nrays]  points of the ray at the two target phases (xA, yA, xB, yB)
-    tiled: bool = False         # traj is [ntiles, L, T, 4] (tile = ray // T, slot = ray % T; T = 32, 64 or 128)
+    tiled: bool = False         # traj is [ntiles, L, T, 4] (tile = ray // T, slot = ray % T; T = 32 ... 256)
 
     def ray_states(self, r: int, n: Optional[int] = None):
         """View [n, 4] of the first n states (default nsteps[r], the part the reference's
@@ -277,7 +277,7 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
                 st_ray=None, traj=None, want_end: bool = True, want_extras: bool = False,
                 hist=None, nbins: int = 0, amp=None, xorg: float = 0.0, yorg: float = 0.0,
                 r_lcs: float = 1.0, rho_max: float = 1.0, traj_host: bool = False,
-                div_ieee: bool = False, refill: Optional[bool] = None, tiled: bool = False, tile: int = 128,
+                div_ieee: bool = False, refill: Optional[bool] = None, tiled: bool = False, tile: int = 256,
                 cross=None, x0_phys=None, y0_phys=None, lookup_ph=None,
                 out: Optional[BatchResult] = None, stream=None) -> BatchResult:
     """Trace ``len(x0)`` rays in one launch.
@@ -300,9 +300,9 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     lookup_ph: [2, nrays] target phases (needs ``cross``): the rays are traced again and each one --
     with its crossing point inserted, as after addpoint -- is sampled at its two target phases
     like ``interp1d(r.ph, r.x, fill_value='extrapolate')`` (beam.py:410-413); fills ``lookup_xy``.
-    tiled: trajectory layout [ceil(nrays/T), L, T, 4] (T = ``tile`` = 128, 64 or 32 rays) instead
-    of [nrays, L, 4]: every warp-step becomes one coalesced 1 KB row store and a 128-thread CTA
-    writes 4 KB contiguous rows (the fast layout; read rays back with ``BatchResult.ray_states``).
+    tiled: trajectory layout [ceil(nrays/T), L, T, 4] (T = ``tile`` = 256, 128, 64 or 32 rays)
+    instead of [nrays, L, 4]: every warp-step becomes one coalesced 1 KB row store and a 256-thread
+    CTA writes 8 KB contiguous rows (the fast layout; read rays back with ``BatchResult.ray_states``).
     """
     torch = _torch()
     dev_io = _is_tensor(x0)
@@ -386,8 +386,8 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
         flags |= F_REFILL if refill else F_STATIC
 
     tile = int(tile)
-    if tile not in (32, 64, 128):
-        raise ValueError('tile must be 32, 64 or 128')
+    if tile not in (32, 64, 128, 256):
+        raise ValueError('tile must be 32, 64, 128 or 256')
     tshape = ((n + tile - 1) // tile, L, tile, 4) if tiled else (n, L, 4)
     if tiled:
         flags |= F_TRAJ_TILED

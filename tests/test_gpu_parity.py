@@ -526,7 +526,7 @@ def test_config4_sweep_invariants(st, oracle_mod, torch_mod):
         assert float(ph[j]).hex() == float(oracle_mod.lax_ph(want["traj"][j, :k], st_ray[idx][j])[1][-1]).hex()
 
 
-@pytest.mark.parametrize("tile", [32, 64])
+@pytest.mark.parametrize("tile", [32, 64, 128])
 @pytest.mark.parametrize("refill", [None, True, False])
 def test_tile_sizes_bitwise(st, oracle_mod, tile, refill):
     """Tiled trajectory layout with 64- and 128-ray tiles ([ray/T][step][ray%T][4]): same bits."""

@@ -39,13 +39,13 @@ def main():
     d_xp = torch.from_numpy(np.ascontiguousarray(case.x0)).to(dev)
     d_yp = torch.from_numpy(np.ascontiguousarray(case.y0)).to(dev)
     n, L = case.nrays, case.L
-    nt = (n + 127) // 128 * 4
+    nt = (n + 255) // 256 * 8
     buf = None   # trajectory arena, allocated when a trajectory variant is selected
     kw = dict(L=L, st=case.st, dx=case.dx, dy=case.dy)
     out = sidtrace.BatchResult(nsteps=torch.empty(n, dtype=torch.int32, device=dev),
                                end_state=torch.empty((4, n), dtype=torch.float64, device=dev))
     variants = []
-    for mode in ("traj-tiled", "traj-tiled64", "traj-tiled128", "traj-ray", "endpoints", "endpoints-tiled", "extras", "extras-tiled", "hist64", "hist1024", "cross"):
+    for mode in ("traj-tiled", "traj-tiled64", "traj-tiled128", "traj-tiled256", "traj-ray", "endpoints", "endpoints-tiled", "extras", "extras-tiled", "hist64", "hist1024", "cross"):
         for refill in (True, False):
             for div_ieee in (False, True):
                 variants.append((mode, refill, div_ieee))
@@ -59,8 +59,8 @@ def main():
         k = dict(kw, refill=refill, div_ieee=div_ieee)
         if mode.startswith("traj") and buf is None:
             buf = torch.empty(nt * 32 * L * 4, dtype=torch.float64, device=dev)
-        if mode in ("traj-tiled", "traj-tiled64", "traj-tiled128"):
-            T = {"traj-tiled": 32, "traj-tiled64": 64, "traj-tiled128": 128}[mode]
+        if mode in ("traj-tiled", "traj-tiled64", "traj-tiled128", "traj-tiled256"):
+            T = {"traj-tiled": 32, "traj-tiled64": 64, "traj-tiled128": 128, "traj-tiled256": 256}[mode]
             ntt = (n + T - 1) // T
             k.update(traj=buf[: ntt * L * T * 4].view(ntt, L, T, 4), tiled=True, tile=T)
         elif mode == "traj-ray":
