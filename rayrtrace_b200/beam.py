@@ -309,10 +309,46 @@ class Beam:
 
 
 def _pages(xout):
-    """Split ray indices into "pages" of increasing receiver coordinate (beam.py:374-398)."""
+    """Split ray indices into "pages" of increasing receiver coordinate (beam.py:374-398).
+
+    The reference walks the rays once per page: a page starts at a seed; a later ray joins it when
+    it lies beyond the page's current last member and belongs to no page yet; the first ray that
+    does NOT lie beyond it seeds the next page.  Pages with fewer than two rays are dropped.
+    Same result, but each page is one vectorised pass: the members are the running-maximum records
+    over the still-unused rays after the seed."""
+    xout = np.asarray(xout, float)
     n = len(xout)
     if n >= 2 and bool(np.all(xout[1:] > xout[:-1])):
         return [np.arange(n)]                  # no caustic: the whole beam is one page
+    if n == 0:
+        return []
+    used = np.zeros(n, dtype=bool)
+    used[0] = True
+    seeds = [0]
+    pages = []
+    cur = 0
+    while cur < len(seeds):
+        s = seeds[cur]
+        idx = np.arange(s + 1, n)
+        free = ~used[idx]
+        vals = np.where(free, xout[idx], -np.inf)            # rays already in a page never move the front
+        front = np.maximum.accumulate(np.concatenate(([xout[s]], vals)))[:-1]
+        beyond = xout[idx] > front
+        members = idx[free & beyond]
+        used[members] = True
+        if cur + 1 == len(seeds):                             # the first ray not beyond the front seeds the next page
+            stop = np.flatnonzero(~beyond)
+            if len(stop):
+                seeds.append(int(idx[stop[0]]))
+                used[idx[stop[0]]] = True
+        pages.append(np.concatenate(([s], members)))
+        cur += 1
+    return [pg for pg in pages if len(pg) >= 2]
+
+
+def _pages_loop(xout):
+    """Literal restatement of beam.py:374-398 (kept as the checker of ``_pages`` in the tests)."""
+    n = len(xout)
     pages = [[0]] if n else []
     cur = 0
     used = {0}

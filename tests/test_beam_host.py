@@ -96,3 +96,25 @@ def test_ray_addpoint_matches_reference(oracle_mod, ft2_cross):
                                        rtol=1e-11, atol=1e-11)
             checked += 1
     assert checked > 40
+
+
+def test_pages_vectorised_equals_reference_loop():
+    """beam._pages (one vectorised pass per page) == the literal loop of beam.py:374-398 on random
+    receiver coordinates: folded beams, ties, duplicates, reversed halves, empty and tiny inputs."""
+    from rayrtrace_b200.beam import _pages, _pages_loop
+    rng = np.random.default_rng(0)
+    for trial in range(1500):
+        n = int(rng.integers(0, 70))
+        kind = trial % 5
+        if kind == 0:
+            x = rng.normal(size=n)
+        elif kind == 1:
+            x = np.sort(rng.normal(size=n)) + rng.normal(size=n) * 0.2
+        elif kind == 2:
+            x = rng.integers(0, 6, size=n).astype(float)
+        elif kind == 3:
+            x = np.concatenate([np.sort(rng.normal(size=n // 2)), np.sort(rng.normal(size=n - n // 2))[::-1]])
+        else:
+            x = np.sort(rng.normal(size=n))
+        a, b = _pages(x), _pages_loop(x)
+        assert len(a) == len(b) and all(np.array_equal(p, q) for p, q in zip(a, b)), (trial, x)
