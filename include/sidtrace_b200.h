@@ -158,6 +158,26 @@ typedef struct stb_batch_s {
  * host memory. */
 int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream);
 
+/* ---- launch states on the device (ray.py:34-68 for a whole beam) ------------------------------- */
+/* From physical start points and directions to what stb_trace_batch takes: direction normalised to
+ * w/c and scaled by the local refractive index N = sqrt(1 - n/n_c) (n from the bicubic B-spline
+ * (tx, ty, coef) SciPy fitted to the density grid, evaluated like FITPACK fpbisp), start points
+ * mapped to grid units with the piecewise-linear x2grid / y2grid of den.py:69-70 (bit-identical to
+ * scipy's interp1d).  All pointers are DEVICE pointers; asynchronous on `stream`. */
+typedef struct stb_launch_s {
+    size_t   struct_size;
+    int64_t  n;
+    const double *x0_phys, *y0_phys;   /* [n] start points, cm                                    */
+    const double *kx_dir, *ky_dir;     /* [n] direction (any non-zero length)                     */
+    const double *x_nodes, *y_nodes;   /* [nx], [ny] grid node coordinates (Nfield.x, Nfield.y)   */
+    int32_t  nx, ny;
+    const double *tx, *ty, *coef;      /* knots [ntx], [nty] and coefficients [(ntx-4)*(nty-4)]   */
+    int32_t  ntx, nty;
+    double   w, c, n_crit;             /* angular frequency, speed of light (cm/s), critical density */
+    double  *x0, *y0, *kx0, *ky0;      /* [n] outputs: grid units / cm^-1                         */
+} stb_launch_t;
+int stb_launch_states(const stb_launch_t *a, void *stream);
+
 /* Trajectory export: packs the KEPT states 0..nsteps[r]-1 of every ray (what the reference's Ray keeps,
  * ray.py:99-102) from a trajectory arena -- ray-major (tile = 0, ray_stride doubles per ray, 0 -> 4*L) or
  * tiled (tile = 32 / 64 / 128) -- into out[offsets[r] .. offsets[r] + nsteps[r]][4].  All pointers are

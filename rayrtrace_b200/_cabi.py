@@ -27,7 +27,7 @@ F_STATIC = 1 << 5
 EXPORTS = (
     "stb_abi_version", "stb_last_error", "stb_device_count", "stb_set_device",
     "stb_field_create", "stb_field_destroy", "stb_field_shape", "stb_field_peek",
-    "stb_trace", "stb_check", "stb_trace_batch", "stb_pack_traj", "stb_launch_count",
+    "stb_trace", "stb_check", "stb_trace_batch", "stb_launch_states", "stb_pack_traj", "stb_launch_count",
     "stb_measure_fp64_peak", "stb_measure_store_bw",
 )
 
@@ -66,6 +66,22 @@ class StbBatch(Structure):
     ]
 
 
+class StbLaunch(Structure):
+    """Mirror of ``stb_launch_t``."""
+    _fields_ = [
+        ("struct_size", c_size_t),
+        ("n", c_int64),
+        ("x0_phys", c_void_p), ("y0_phys", c_void_p),
+        ("kx_dir", c_void_p), ("ky_dir", c_void_p),
+        ("x_nodes", c_void_p), ("y_nodes", c_void_p),
+        ("nx", c_int32), ("ny", c_int32),
+        ("tx", c_void_p), ("ty", c_void_p), ("coef", c_void_p),
+        ("ntx", c_int32), ("nty", c_int32),
+        ("w", c_double), ("c", c_double), ("n_crit", c_double),
+        ("x0", c_void_p), ("y0", c_void_p), ("kx0", c_void_p), ("ky0", c_void_p),
+    ]
+
+
 class SidtraceError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"sidtrace_b200 error {code}: {msg}")
@@ -93,6 +109,8 @@ def _load() -> ctypes.CDLL:
                               c_double, c_double, c_double, POINTER(c_int64)]
     lib.stb_check.argtypes = [c_int, c_int, c_int, c_int, c_void_p, POINTER(c_double)]
     lib.stb_trace_batch.argtypes = [c_void_p, POINTER(StbBatch), c_void_p]
+    lib.stb_launch_states.argtypes = [POINTER(StbLaunch), c_void_p]
+    lib.stb_launch_states.restype = c_int
     lib.stb_pack_traj.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.stb_pack_traj.restype = c_int
     lib.stb_launch_count.restype = c_int64

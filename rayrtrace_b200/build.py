@@ -14,7 +14,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "sidtrace_b200.cu")
-DEPS = [SRC, os.path.join(_HERE, "csrc", "trace_kernels.cuh"),
+DEPS = [SRC, os.path.join(_HERE, "csrc", "trace_kernels.cuh"), os.path.join(_HERE, "csrc", "launch_kernels.cuh"),
         os.path.join(os.path.dirname(_HERE), "include", "sidtrace_b200.h")]
 LIB_DIR = os.path.join(_HERE, "_lib")
 LIB = os.path.join(LIB_DIR, "libsidtrace_b200.so")

@@ -1,0 +1,112 @@
+// launch_kernels.cuh -- launch-state preparation on the device: what the
+// reference's Ray.__init__ does per ray before calling trace (ray.py:34-68), for a whole beam.
+//
+//   k  = (kx0, ky0) / |k0| * w / c                       ray.py:38-45   normalise to the vacuum wave number
+//   N  = sqrt(1 - n(x0, y0) / n_c)                        ray.py:62, den.py:76-82 with the cubic spline of n
+//   k *= N                                               ray.py:63-64
+//   xg = x2grid(x0), yg = y2grid(y0)                     ray.py:67-68, den.py:69-70 (piecewise-linear
+//                                                        interp1d with extrapolation)
+//
+// The grid coordinates decide which cell a ray starts in, so x2grid/y2grid follow scipy's interp1d
+// arithmetic operation for operation (bit-identical to the host path).  n(x0, y0) evaluates the
+// bicubic B-spline that SciPy's RectBivariateSpline fitted on the host (FITPACK fpbisp/fpbspl
+// restated); it agrees with SciPy's own evaluation to rounding (tolerance-level path, like the
+// reference's interp2d it replaces).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace stb {
+
+struct LaunchParams {
+    long long n;
+    const double *x0p, *y0p, *kxd, *kyd;          // physical start points, direction (any length)
+    const double *xn, *yn;                          // grid node coordinates
+    int nx, ny;
+    const double *tx, *ty, *coef;                   // spline knots and coefficients (degree 3 x 3)
+    int ntx, nty;
+    double w, c, nc;
+    double *xg, *yg, *kx, *ky;                      // outputs
+};
+
+// interp1d(x, arange(n), fill_value='extrapolate')(v): node hi = searchsorted(x, v) clipped to
+// [1, n-1]; slope = (hi - lo) / (x[hi] - x[lo]); result = slope * (v - x[lo]) + lo.
+__device__ __forceinline__ double to_grid(const double *__restrict__ x, int n, double v)
+{
+    int lo = 0, hi = n;                             // first index with x[idx] >= v  (searchsorted 'left')
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (x[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    int b = lo < 1 ? 1 : (lo > n - 1 ? n - 1 : lo);
+    const int a = b - 1;
+    const double slope = __ddiv_rn(__dsub_rn((double)b, (double)a), __dsub_rn(x[b], x[a]));
+    return __dadd_rn(__dmul_rn(slope, __dsub_rn(v, x[a])), (double)a);
+}
+
+// FITPACK fpbspl for degree 3: the four non-zero B-splines at x, knot interval l (t[l] <= x < t[l+1]).
+__device__ __forceinline__ void bspl3(const double *__restrict__ t, double x, int l, double h[4])
+{
+    double hh[3];
+    h[0] = 1.0;
+    for (int j = 1; j <= 3; ++j) {
+        for (int i = 0; i < j; ++i) hh[i] = h[i];
+        h[0] = 0.0;
+        for (int i = 0; i < j; ++i) {
+            const int li = l + i + 1, lj = li - j;
+            if (t[li] != t[lj]) {
+                const double f = hh[i] / (t[li] - t[lj]);
+                h[i] = h[i] + f * (t[li] - x);
+                h[i + 1] = f * (x - t[lj]);
+            } else {
+                h[i + 1] = 0.0;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int knot_interval(const double *__restrict__ t, int nt, double x)
+{
+    // largest l in [3, nt-5] with t[l] <= x  (FITPACK fpbisp; x already clamped to [t[3], t[nt-4]])
+    int lo = 3, hi = nt - 5;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (t[mid] <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void launch_states_kernel(const LaunchParams p)
+{
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (; r < p.n; r += step) {
+        const double x0 = p.x0p[r], y0 = p.y0p[r];
+        // density at the start point: clamp to the spline's domain like fpbisp does
+        double xs = x0, ys = y0;
+        const double xb = p.tx[3], xe = p.tx[p.ntx - 4], yb = p.ty[3], ye = p.ty[p.nty - 4];
+        xs = xs < xb ? xb : (xs > xe ? xe : xs);
+        ys = ys < yb ? yb : (ys > ye ? ye : ys);
+        const int lx = knot_interval(p.tx, p.ntx, xs), ly = knot_interval(p.ty, p.nty, ys);
+        double hx[4], hy[4];
+        bspl3(p.tx, xs, lx, hx);
+        bspl3(p.ty, ys, ly, hy);
+        const int ncy = p.nty - 4;
+        double den = 0.0;
+        for (int i = 0; i < 4; ++i) {
+            const double *row = p.coef + (long long)(lx - 3 + i) * ncy + (ly - 3);
+            double s = 0.0;
+            for (int j = 0; j < 4; ++j) s += row[j] * hy[j];
+            den += hx[i] * s;
+        }
+        const double refr = sqrt(1.0 - den / p.nc);
+        // direction -> vacuum wave vector -> local wave vector (same operation order as launch_states)
+        const double kxd = p.kxd[r], kyd = p.kyd[r];
+        const double kn = sqrt(kxd * kxd + kyd * kyd);
+        p.kx[r] = kxd / kn * p.w / p.c * refr;
+        p.ky[r] = kyd / kn * p.w / p.c * refr;
+        p.xg[r] = to_grid(p.xn, p.nx, x0);
+        p.yg[r] = to_grid(p.yn, p.ny, y0);
+    }
+}
+
+}  // namespace stb

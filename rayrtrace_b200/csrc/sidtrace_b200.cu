@@ -6,6 +6,7 @@
 //        -Xcompiler -fPIC -shared -o libsidtrace_b200.so sidtrace_b200.cu
 #include "../../include/sidtrace_b200.h"
 #include "trace_kernels.cuh"
+#include "launch_kernels.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -565,6 +566,35 @@ int stb_trace(stb_field_t f, double *x, double *y, double *kx, double *ky, int64
         x[j] = t[4 * j + 0]; y[j] = t[4 * j + 1]; kx[j] = t[4 * j + 2]; ky[j] = t[4 * j + 3];
     }
     *nsteps = n;
+    return STB_OK;
+}
+
+int stb_launch_states(const stb_launch_t *a, void *stream)
+{
+    if (!a) return fail(STB_ERR_ARG, "stb_launch_states: NULL argument");
+    if (a->struct_size != sizeof(stb_launch_t))
+        return fail(STB_ERR_ARG, "stb_launch_states: struct_size %zu != %zu (ABI mismatch)", a->struct_size, sizeof(stb_launch_t));
+    if (a->n < 0 || a->nx < 2 || a->ny < 2 || a->ntx < 8 || a->nty < 8)
+        return fail(STB_ERR_ARG, "stb_launch_states: bad sizes (n=%lld nx=%d ny=%d ntx=%d nty=%d)", (long long)a->n, a->nx, a->ny, a->ntx, a->nty);
+    const void *ptrs[] = {a->x0_phys, a->y0_phys, a->kx_dir, a->ky_dir, a->x_nodes, a->y_nodes, a->tx, a->ty, a->coef,
+                          a->x0, a->y0, a->kx0, a->ky0};
+    for (const void *q : ptrs) if (!q) return fail(STB_ERR_ARG, "stb_launch_states: NULL pointer");
+    if (a->n == 0) return STB_OK;
+    stb::LaunchParams p{};
+    p.n = a->n;
+    p.x0p = a->x0_phys; p.y0p = a->y0_phys; p.kxd = a->kx_dir; p.kyd = a->ky_dir;
+    p.xn = a->x_nodes; p.yn = a->y_nodes; p.nx = a->nx; p.ny = a->ny;
+    p.tx = a->tx; p.ty = a->ty; p.coef = a->coef; p.ntx = a->ntx; p.nty = a->nty;
+    p.w = a->w; p.c = a->c; p.nc = a->n_crit;
+    p.xg = a->x0; p.yg = a->y0; p.kx = a->kx0; p.ky = a->ky0;
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long blocks = (a->n + 255) / 256;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    stb::launch_states_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    g_launches++;
+    CU(cudaGetLastError());
     return STB_OK;
 }
 

@@ -145,6 +145,21 @@ class Nfield:
         if self._device_field is not None:
             self._device_field.close()
             self._device_field = None
+        self._device_launch = None
+
+    def device_launch_tables(self):
+        """CUDA copies of what the device launcher needs: node coordinates and the bicubic spline of
+        n (knots, coefficients) fitted once on the host."""
+        tabs = getattr(self, "_device_launch", None)
+        if tabs is None:
+            import torch
+            self.n_interpolant(self.x[0], self.y[0])     # builds the spline
+            tx, ty, c = self._spline.tck
+            dev = torch.device("cuda", torch.cuda.current_device())
+            tabs = {k: torch.from_numpy(np.ascontiguousarray(v, np.float64)).to(dev)
+                    for k, v in (("x", self.x), ("y", self.y), ("tx", tx), ("ty", ty), ("c", c))}
+            self._device_launch = tabs
+        return tabs
 
     # ---- B200 side -------------------------------------------------------
     def device_field(self):

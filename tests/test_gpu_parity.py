@@ -743,3 +743,31 @@ def test_trajectory_export_to_host_packed(st, oracle_mod):
             k = int(want["nsteps"][r])
             assert states[off[r]:off[r + 1]].tobytes() == want["traj"][r, :k].tobytes()
     f.close()
+
+
+def test_device_launch_states_match_host(st, torch_mod, ft2_ray):
+    """stb_launch_states (ray.py:34-68 for a whole beam, on the GPU) against the host restatement:
+    grid coordinates bit-identical (scipy interp1d arithmetic, incl. extrapolation outside the grid),
+    wave vectors to 1e-13 (same spline coefficients, FITPACK evaluation restated on the device)."""
+    from rayrtrace_b200.nfield import Nfield
+    from rayrtrace_b200.ray import launch_states, launch_states_device
+    rng = np.random.default_rng(17)
+    for nx, n0 in ((201, 4e13), (129, 3.0e14)):
+        n, x, y = ft2_density(nx, n0)
+        nf = Nfield(n, x=x, y=y)
+        m = 20000
+        x0 = rng.uniform(-10.5, 10.5, m); y0 = rng.uniform(-10.5, 10.5, m)     # some points outside the grid
+        x0[:4] = (x[0], x[-1], x[5], -10.0); y0[:4] = (y[0], y[-1], y[7], 10.0)  # exactly on nodes / edges
+        ang = rng.uniform(0, 2 * np.pi, m)
+        kx0 = np.cos(ang) * rng.uniform(0.1, 3, m); ky0 = np.sin(ang) * rng.uniform(0.1, 3, m)
+        inside = (np.abs(x0) < 7.5) & (np.abs(y0) < 7.5) if n0 > 2e14 else np.ones(m, bool)   # avoid n > n_c (NaN index)
+        freq = float(ft2_ray["freq"])
+        hx, hy, hkx, hky, _ = launch_states(nf, x0, y0, kx0, ky0, freq)
+        dx_, dy_, dkx, dky, _ = launch_states_device(nf, x0, y0, kx0, ky0, freq)
+        torch_mod.cuda.synchronize()
+        assert dx_.cpu().numpy().tobytes() == hx.tobytes() and dy_.cpu().numpy().tobytes() == hy.tobytes()
+        ok = ~np.isnan(hkx)
+        assert ok.mean() > 0.5
+        np.testing.assert_allclose(dkx.cpu().numpy()[ok], hkx[ok], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(dky.cpu().numpy()[ok], hky[ok], rtol=1e-12, atol=1e-12)
+        assert np.array_equal(np.isnan(dkx.cpu().numpy()), np.isnan(hkx)) or (~ok).sum() < 5
