@@ -28,8 +28,9 @@ struct LaunchParams {
     double *xg, *yg, *kx, *ky;                      // outputs
 };
 
-// interp1d(x, arange(n), fill_value='extrapolate')(v): node hi = searchsorted(x, v) clipped to
-// [1, n-1]; slope = (hi - lo) / (x[hi] - x[lo]); result = slope * (v - x[lo]) + lo.
+// interp1d(x, arange(n), fill_value='extrapolate')(v) as SciPy >= 1.12 evaluates it
+// (interp1d._call_linear): node hi = searchsorted(x, v) clipped to [1, n-1], lo = hi - 1,
+//   ((v - x[lo]) / (x[hi] - x[lo])) * hi  +  ((x[hi] - v) / (x[hi] - x[lo])) * lo.
 __device__ __forceinline__ double to_grid(const double *__restrict__ x, int n, double v)
 {
     int lo = 0, hi = n;                             // first index with x[idx] >= v  (searchsorted 'left')
@@ -39,8 +40,10 @@ __device__ __forceinline__ double to_grid(const double *__restrict__ x, int n, d
     }
     int b = lo < 1 ? 1 : (lo > n - 1 ? n - 1 : lo);
     const int a = b - 1;
-    const double slope = __ddiv_rn(__dsub_rn((double)b, (double)a), __dsub_rn(x[b], x[a]));
-    return __dadd_rn(__dmul_rn(slope, __dsub_rn(v, x[a])), (double)a);
+    const double w = __dsub_rn(x[b], x[a]);
+    const double up = __dmul_rn(__ddiv_rn(__dsub_rn(v, x[a]), w), (double)b);
+    const double dn = __dmul_rn(__ddiv_rn(__dsub_rn(x[b], v), w), (double)a);
+    return __dadd_rn(up, dn);
 }
 
 // FITPACK fpbspl for degree 3: the four non-zero B-splines at x, knot interval l (t[l] <= x < t[l+1]).
