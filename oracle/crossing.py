@@ -132,11 +132,12 @@ def _lax_at(kx, ky, sts, j):
 
 
 def interp_extrap(xn, yn, t):
-    """scipy interp1d(kind='linear', fill_value='extrapolate') at one point: node b is the first
-    with t <= xn[b] (clipped to [1, n-1]); y = slope*(t - x_lo) + y_lo."""
+    """scipy interp1d(kind='linear', fill_value='extrapolate') at one point (interp1d._call_linear,
+    SciPy >= 1.12): node b is the first with t <= xn[b] (clipped to [1, n-1]);
+    y = ((t - x_lo)/(x_hi - x_lo))*y_hi + ((x_hi - t)/(x_hi - x_lo))*y_lo."""
     b = int(np.clip(np.searchsorted(xn, t), 1, len(xn) - 1))
-    slope = (yn[b] - yn[b - 1]) / (xn[b] - xn[b - 1])
-    return slope * (t - xn[b - 1]) + yn[b - 1]
+    w = xn[b] - xn[b - 1]
+    return ((t - xn[b - 1]) / w) * yn[b] + ((xn[b] - t) / w) * yn[b - 1]
 
 
 def phase_lookup(traj_kept, x0p, y0p, dx, dy, st, ax, ay, val, axis, targets):

@@ -278,9 +278,11 @@ trace_kernel(const KParams p)
     // append a point (phase, x, y) to the ray's polyline and resolve the targets it brackets:
     // interp1d picks the first node b >= 1 with t <= ph[b] and interpolates on (b-1, b)
     auto interp_seg = [&](double t, double &ox, double &oy) {
+        // interp1d._call_linear (SciPy >= 1.12): ((t - lo)/(hi - lo))*y_hi + ((hi - t)/(hi - lo))*y_lo
         const double dph = sb_ph - sa_ph;
-        ox = (sb_x - sa_x) / dph * (t - sa_ph) + sa_x;
-        oy = (sb_y - sa_y) / dph * (t - sa_ph) + sa_y;
+        const double wa = (t - sa_ph) / dph, wb = (sb_ph - t) / dph;
+        ox = wa * sb_x + wb * sa_x;
+        oy = wa * sb_y + wb * sa_y;
     };
     auto add_point = [&](double phq, double xq, double yq) {
         sa_ph = sb_ph; sa_x = sb_x; sa_y = sb_y;

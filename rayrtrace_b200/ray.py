@@ -278,8 +278,8 @@ def launch_states_device(n_field, x0, y0, kx0, ky0, freq):
         if type(a).__module__.startswith("torch"):
             return a.to(dev, torch.float64).contiguous()
         a = np.asarray(a, np.float64)
-        if n is not None:
-            a = np.broadcast_to(a, (n,))
+        if n is not None and a.shape != (n,):
+            a = np.broadcast_to(a, (n,)).copy()
         return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
     x0d = up(np.atleast_1d(x0) if not type(x0).__module__.startswith("torch") else x0)
@@ -305,7 +305,7 @@ def launch_states_device(n_field, x0, y0, kx0, ky0, freq):
 
 def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional[int] = None,
                keep_traj: bool = True, want_extras: bool = False, tiled: bool = True,
-               receiver=None) -> RayBundle:
+               receiver=None, device_launch: Optional[bool] = None) -> RayBundle:
     """Trace a whole fan of rays in one kernel launch (replaces beam.py:340-342).
 
     max_steps: array length per ray.  The reference's Ray.MaxStep = 100000 would be 3.2 MB per
@@ -314,10 +314,19 @@ def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional
     nsteps == max_steps-1 exactly like the reference does at its cap, and a RuntimeWarning says
     how many did so they can be re-traced with a larger cap (or refill=True, keep_traj=False).
 
+    device_launch: prepare the launch states (ray.py:34-68) on the GPU (``launch_states_device``)
+    instead of on the host; default: on for >= 65536 rays, where SciPy's point-wise spline
+    evaluation would take longer than the trace.
     receiver: (val, axis) -- also report, per ray, what ``Ray.addpoint(val, axis)`` would
     (ray.py:131-224): first crossing of the receiver line, its phase and wave vector
     (``bundle.result.cross_*``), i.e. the per-ray inputs of ``Beam.field_r`` (beam.py:359-369)."""
-    xg, yg, kx, ky, freq = launch_states(n_field, x0, y0, kx0, ky0, freq)
+    if device_launch is None:
+        device_launch = np.size(x0) >= 65536 and hasattr(n_field, "device_launch_tables")
+    if device_launch:
+        xg, yg, kx, ky, freq = (t.cpu().numpy() if hasattr(t, "cpu") else t
+                                for t in launch_states_device(n_field, x0, y0, kx0, ky0, freq))
+    else:
+        xg, yg, kx, ky, freq = launch_states(n_field, x0, y0, kx0, ky0, freq)
     n = len(xg)
     if amp is None:
         amp = np.ones(n)
