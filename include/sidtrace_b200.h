@@ -178,6 +178,12 @@ typedef struct stb_launch_s {
 } stb_launch_t;
 int stb_launch_states(const stb_launch_t *a, void *stream);
 
+/* Host helper (no device work): the "pages" of Beam.field_r (beam.py:374-398) -- the rays, in launch
+ * order with receiver coordinate xout[n], split into runs of increasing xout; pages of fewer than two
+ * rays are dropped.  members needs room for 2*n entries, offsets for n+2; page k is
+ * members[offsets[k] .. offsets[k+1]). */
+int stb_field_pages(const double *xout, int64_t n, int64_t *offsets, int64_t *members, int64_t *npages);
+
 /* Trajectory export: packs the KEPT states 0..nsteps[r]-1 of every ray (what the reference's Ray keeps,
  * ray.py:99-102) from a trajectory arena -- ray-major (tile = 0, ray_stride doubles per ray, 0 -> 4*L) or
  * tiled (tile = 32 / 64 / 128) -- into out[offsets[r] .. offsets[r] + nsteps[r]][4].  All pointers are

@@ -27,7 +27,7 @@ F_STATIC = 1 << 5
 EXPORTS = (
     "stb_abi_version", "stb_last_error", "stb_device_count", "stb_set_device",
     "stb_field_create", "stb_field_destroy", "stb_field_shape", "stb_field_peek",
-    "stb_trace", "stb_check", "stb_trace_batch", "stb_launch_states", "stb_pack_traj", "stb_launch_count",
+    "stb_trace", "stb_check", "stb_trace_batch", "stb_launch_states", "stb_field_pages", "stb_pack_traj", "stb_launch_count",
     "stb_measure_fp64_peak", "stb_measure_store_bw",
 )
 
@@ -111,6 +111,8 @@ def _load() -> ctypes.CDLL:
     lib.stb_trace_batch.argtypes = [c_void_p, POINTER(StbBatch), c_void_p]
     lib.stb_launch_states.argtypes = [POINTER(StbLaunch), c_void_p]
     lib.stb_launch_states.restype = c_int
+    lib.stb_field_pages.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, POINTER(c_int64)]
+    lib.stb_field_pages.restype = c_int
     lib.stb_pack_traj.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.stb_pack_traj.restype = c_int
     lib.stb_launch_count.restype = c_int64

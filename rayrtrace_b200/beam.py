@@ -314,36 +314,20 @@ def _pages(xout):
     The reference walks the rays once per page: a page starts at a seed; a later ray joins it when
     it lies beyond the page's current last member and belongs to no page yet; the first ray that
     does NOT lie beyond it seeds the next page.  Pages with fewer than two rays are dropped.
-    Same result, but each page is one vectorised pass: the members are the running-maximum records
-    over the still-unused rays after the seed."""
-    xout = np.asarray(xout, float)
+    The nearest-cell scheme makes the launch -> receiver map jump at cell edges, so dense beams
+    have hundreds of tiny pages and the walk is O(rays x pages): it runs natively
+    (``stb_field_pages``, host code of the C library)."""
+    import ctypes
+    from . import _cabi
+    xout = np.ascontiguousarray(xout, np.float64)
     n = len(xout)
     if n >= 2 and bool(np.all(xout[1:] > xout[:-1])):
-        return [np.arange(n)]                  # no caustic: the whole beam is one page
-    if n == 0:
-        return []
-    used = np.zeros(n, dtype=bool)
-    used[0] = True
-    seeds = [0]
-    pages = []
-    cur = 0
-    while cur < len(seeds):
-        s = seeds[cur]
-        idx = np.arange(s + 1, n)
-        free = ~used[idx]
-        vals = np.where(free, xout[idx], -np.inf)            # rays already in a page never move the front
-        front = np.maximum.accumulate(np.concatenate(([xout[s]], vals)))[:-1]
-        beyond = xout[idx] > front
-        members = idx[free & beyond]
-        used[members] = True
-        if cur + 1 == len(seeds):                             # the first ray not beyond the front seeds the next page
-            stop = np.flatnonzero(~beyond)
-            if len(stop):
-                seeds.append(int(idx[stop[0]]))
-                used[idx[stop[0]]] = True
-        pages.append(np.concatenate(([s], members)))
-        cur += 1
-    return [pg for pg in pages if len(pg) >= 2]
+        return [np.arange(n)]                  # no caustic, no jumps: the whole beam is one page
+    offsets = np.zeros(n + 2, np.int64)
+    members = np.zeros(2 * n + 2, np.int64)
+    npages = ctypes.c_int64()
+    _cabi.check(_cabi.lib.stb_field_pages(xout.ctypes.data, n, offsets.ctypes.data, members.ctypes.data, ctypes.byref(npages)))
+    return [members[offsets[k]:offsets[k + 1]].copy() for k in range(npages.value)]
 
 
 def _pages_loop(xout):

@@ -569,6 +569,39 @@ int stb_trace(stb_field_t f, double *x, double *y, double *kx, double *ky, int64
     return STB_OK;
 }
 
+int stb_field_pages(const double *xout, int64_t n, int64_t *offsets, int64_t *members, int64_t *npages)
+{
+    // Host helper, no device work: the page construction of Beam.field_r (beam.py:374-398), kept
+    // native because folded beams of 10^4..10^6 rays make it O(rays x pages).
+    if (!xout || !offsets || !members || !npages || n < 0) return fail(STB_ERR_ARG, "stb_field_pages: bad argument");
+    *npages = 0;
+    offsets[0] = 0;
+    if (n == 0) return STB_OK;
+    std::vector<char> used((size_t)n, 0);
+    std::vector<std::vector<int64_t>> pages;
+    pages.push_back({0});
+    used[0] = 1;
+    for (size_t cur = 0; cur < pages.size(); ++cur) {
+        const int64_t start = pages[cur].back() + 1;
+        for (int64_t j = start; j < n; ++j) {
+            if (xout[j] > xout[pages[cur].back()]) {
+                if (!used[(size_t)j]) { pages[cur].push_back(j); used[(size_t)j] = 1; }
+            } else if (cur + 1 == pages.size()) {
+                pages.push_back({j});
+                used[(size_t)j] = 1;
+            }
+        }
+    }
+    int64_t np = 0, pos = 0;
+    for (const auto &pg : pages) {
+        if (pg.size() < 2) continue;                 // single-ray pages are dropped (beam.py:392-398)
+        for (int64_t v : pg) members[pos++] = v;
+        offsets[++np] = pos;
+    }
+    *npages = np;
+    return STB_OK;
+}
+
 int stb_launch_states(const stb_launch_t *a, void *stream)
 {
     if (!a) return fail(STB_ERR_ARG, "stb_launch_states: NULL argument");
