@@ -1,12 +1,15 @@
 // trace_kernels.cuh -- sm_100a kernels of the sidtrace hot path.
 //
-// One thread owns one ray at a time.  A warp runs a flat step loop: every
-// iteration it votes (ballot) on which lanes still own a live ray; lanes whose
-// ray left the grid or hit the cap retire it (write the per-ray results) and,
-// in the persistent "refill" schedule, the warp claims the next rays from a
-// global queue with ONE aggregated atomic and hands them out by lane rank, so
-// a reflected or trapped ray (up to MaxStep = 100000 steps, ray.py:11) never
-// holds 31 idle lanes hostage.
+// One thread owns one ray at a time and steps it in a plain per-thread loop (no
+// vote per step).  Three schedules hand rays to threads:
+//   static       one thread per ray; the hardware CTA scheduler balances the load;
+//   tile refill  persistent warps claim 32 consecutive rays at a time (TILED);
+//   lane refill  persistent warps vote (ballot) once every few steps on which lanes
+//                still own a live ray; lanes whose ray left the grid or hit the cap
+//                have retired it (written the per-ray results), and the warp claims
+//                replacements from a global queue with ONE aggregated atomic, handed
+//                out by lane rank -- a reflected or trapped ray (up to MaxStep =
+//                100000 steps, ray.py:11) never holds 31 idle lanes hostage.
 //
 // Arithmetic contract (bit-exact with sidtracemodule.c:36-48 as gcc -O2
 // compiles it: no FMA, left-to-right):
@@ -49,7 +52,7 @@ struct KParams {
     double dx, dy, rdx, rdy;
     double *traj;
     long long stride;                    // doubles per ray (ray-major layout)
-    int tile;                            // rays per tile (tiled layout): 32, 64 or 128
+    int tile;                            // rays per tile (tiled layout): 32, 64, 128 or 256
     int *nsteps;
     double *endst;
     int *turn;
@@ -168,11 +171,12 @@ __device__ __forceinline__ void hist_add(double *sh, int b, double w)
     if (lane == leader && b >= 0) atomicAdd(&sh[b], sum);
 }
 
-// TILED (trajectory layout [tile][step][32 rays][4]): a warp owns one tile of 32
-// consecutive rays; its lanes step in lock-step, so every step is ONE fully coalesced
-// 1 KB row store and consecutive steps are consecutive rows -- sequential DRAM pages
-// instead of 32 scattered sectors.  Rays are then claimed a whole tile at a time
-// (the lane-granular refill would scatter a new ray's rows).
+// TILED (trajectory layout [ray/T][step][ray%T][4], T = p.tile): a warp owns 32 consecutive
+// rays; its lanes step in lock-step, so every warp-step is ONE fully coalesced 1 KB row store,
+// the warps of a CTA write adjacent rows, and consecutive steps are consecutive rows --
+// sequential DRAM pages instead of 32 scattered sectors.  Rays are claimed 32 at a time
+// (a lane-granular refill would scatter a new ray's rows); per-ray results are retired when
+// the whole warp is done, as coalesced rows.
 //
 // CROSS (needs EXTRAS): first crossing of a receiver line y = val / x = val with the semantics of
 // the reference's Ray.addpoint (ray.py:131-224): exact hits, sign-change segments solved with the
