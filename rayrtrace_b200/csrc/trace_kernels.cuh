@@ -220,6 +220,7 @@ trace_kernel(const KParams p)
     double kprev = 0, lax = 0, ph = 0, a2 = 1.0;
     int binprev = -1;        // HIST: flux bin of the previous kept state = bin of the current run
     double binacc = 0.0;     // HIST: weight gathered for that bin since the ray entered it
+    double r2lo = 1.0, r2hi = 0.0;   // HIST: squared-radius annulus of that bin (empty = unknown)
     // crossing: previous kept state, capture of the first crossing / exact hit
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     double xg0 = 0, yg0 = 0, x0p = 0, y0p = 0;
@@ -258,7 +259,11 @@ trace_kernel(const KParams p)
                 npts = 0; lax2 = ph2 = 0;
             }
         }
-        if (HIST) { const double a = p.amp ? p.amp[r] : 1.0; a2 = __dmul_rn(a, a); binprev = -1; binacc = 0.0; }
+        if (HIST) {
+            const double a = p.amp ? p.amp[r] : 1.0;
+            a2 = __dmul_rn(a, a);
+            binprev = -1; binacc = 0.0; r2lo = 1.0; r2hi = 0.0;
+        }
     };
 
     // solve from the previous kept state (index i-1) and capture the crossing point (ray.py:212-216)
@@ -392,20 +397,37 @@ trace_kernel(const KParams p)
             }
             kprev = kcur;
             if (HIST) {
-                // flux label of the segment START (oracle_deposit)
+                // flux label of the segment START (oracle_deposit).  While the squared radius stays
+                // strictly inside the current bin's annulus (shrunk by 1e-12, far more than the
+                // rounding of the exact formula) the bin cannot have changed: no sqrt, no division.
                 const double xp = __dadd_rn(p.xorg, __dmul_rn(x, p.dx));
                 const double yp = __dadd_rn(p.yorg, __dmul_rn(y, p.dy));
-                const double rho = div_const<DIVC>(__dsqrt_rn(__dadd_rn(__dmul_rn(xp, xp), __dmul_rn(yp, yp))),
-                                                   p.r_lcs, p.r_rlcs);
-                int bnew = -1;
-                if (rho < p.rho_max) {
-                    const int b = __double2int_rz(div_const<DIVC>(__dmul_rn(rho, (double)p.nbins), p.rho_max, p.r_rhomax));
-                    if (b >= 0 && b < p.nbins) bnew = b;
-                }
-                if (bnew != binprev) {
-                    if (binacc != 0.0) hist_add(sh_hist, binprev, binacc);
-                    binprev = bnew;
-                    binacc = 0.0;
+                const double r2 = __dadd_rn(__dmul_rn(xp, xp), __dmul_rn(yp, yp));
+                if (!(r2 > r2lo && r2 < r2hi)) {
+                    const double rho = div_const<DIVC>(__dsqrt_rn(r2), p.r_lcs, p.r_rlcs);
+                    int bnew = -1;
+                    if (rho < p.rho_max) {
+                        const int b = __double2int_rz(div_const<DIVC>(__dmul_rn(rho, (double)p.nbins), p.rho_max, p.r_rhomax));
+                        if (b >= 0 && b < p.nbins) bnew = b;
+                    }
+                    if (bnew != binprev) {
+                        if (binacc != 0.0) hist_add(sh_hist, binprev, binacc);
+                        binprev = bnew;
+                        binacc = 0.0;
+                    }
+                    // annulus of the bin just found, in squared physical radius
+                    const double dr = p.rho_max * p.r_lcs / (double)p.nbins;
+                    if (bnew >= 0) {
+                        const double a = dr * (double)bnew, b2 = dr * (double)(bnew + 1);
+                        r2lo = a * a * (1.0 + 1e-12);
+                        r2hi = b2 * b2 * (1.0 - 1e-12);
+                    } else if (rho >= p.rho_max) {
+                        const double a = p.rho_max * p.r_lcs;
+                        r2lo = a * a * (1.0 + 1e-12);
+                        r2hi = __longlong_as_double(0x7ff0000000000000LL);
+                    } else {
+                        r2lo = 1.0; r2hi = 0.0;       // NaN / odd cases: always take the exact path
+                    }
                 }
             }
         }
