@@ -63,6 +63,8 @@ struct KParams {
     const double *amp;
     double xorg, yorg, r_lcs, rho_max;
     double r_rlcs, r_rhomax;             // RN(1/r_lcs), RN(1/rho_max) for the constant-divisor quotients
+    double hist_dr;                      // radial bin width in cm
+    int hist_annulus;                    // bins span >= 4 steps: use the squared-radius annulus test
     unsigned long long *counter;         // ray queue head (refill schedule)
     // receiver-line crossing (CROSS)
     int cross_axis;                      // 1: y = cross_val, 2: x = cross_val (physical cm)
@@ -403,7 +405,7 @@ trace_kernel(const KParams p)
                 const double xp = __dadd_rn(p.xorg, __dmul_rn(x, p.dx));
                 const double yp = __dadd_rn(p.yorg, __dmul_rn(y, p.dy));
                 const double r2 = __dadd_rn(__dmul_rn(xp, xp), __dmul_rn(yp, yp));
-                if (!(r2 > r2lo && r2 < r2hi)) {
+                if (!p.hist_annulus || !(r2 > r2lo && r2 < r2hi)) {
                     const double rho = div_const<DIVC>(__dsqrt_rn(r2), p.r_lcs, p.r_rlcs);
                     int bnew = -1;
                     if (rho < p.rho_max) {
@@ -416,8 +418,10 @@ trace_kernel(const KParams p)
                         binacc = 0.0;
                     }
                     // annulus of the bin just found, in squared physical radius
-                    const double dr = p.rho_max * p.r_lcs / (double)p.nbins;
-                    if (bnew >= 0) {
+                    const double dr = p.hist_dr;
+                    if (!p.hist_annulus) {
+                        // bins narrower than a few steps: the test would fail most of the time
+                    } else if (bnew >= 0) {
                         const double a = dr * (double)bnew, b2 = dr * (double)(bnew + 1);
                         r2lo = a * a * (1.0 + 1e-12);
                         r2hi = b2 * b2 * (1.0 - 1e-12);
