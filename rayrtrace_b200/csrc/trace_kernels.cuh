@@ -35,6 +35,12 @@
 namespace stb {
 
 constexpr int kBlock = 128;   // threads per CTA (4 warps); the tiled trajectory kernel also runs with 256
+#ifndef STB_MINB_CROSS
+#define STB_MINB_CROSS 1      // crossing / lookup passes
+#endif
+#ifndef STB_MINB_EXTRAS
+#define STB_MINB_EXTRAS 1     // fused sums / histogram
+#endif
 #ifndef STB_MINB
 #define STB_MINB 12           // min resident CTAs/SM asked of ptxas for the lean variants: 40 registers,
 #endif                        // 48 warps/SM (measured: +4..7 % in endpoint mode, neutral for trajectories;
@@ -197,7 +203,7 @@ __device__ __forceinline__ void hist_add(double *sh, int b, double w)
 // rows, profiles/r01/kernel_sweep_block256_cs.txt; the O(rays)-output modes lose 0.5-3 % with 256).
 template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool REFILL, bool TILED = false, bool CROSS = false,
           bool STRAY = true, bool LOOKUP = false, int BLOCK = kBlock>
-__global__ void __launch_bounds__(BLOCK, (CROSS || HIST || EXTRAS) ? 1 : STB_MINB * kBlock / BLOCK)
+__global__ void __launch_bounds__(BLOCK, CROSS ? STB_MINB_CROSS : (HIST || EXTRAS) ? STB_MINB_EXTRAS : STB_MINB * kBlock / BLOCK)
 trace_kernel(const KParams p)
 {
     extern __shared__ double sh_hist[];

@@ -771,3 +771,48 @@ def test_device_launch_states_match_host(st, torch_mod, ft2_ray):
         np.testing.assert_allclose(dkx.cpu().numpy()[ok], hkx[ok], rtol=1e-12, atol=1e-12)
         np.testing.assert_allclose(dky.cpu().numpy()[ok], hky[ok], rtol=1e-12, atol=1e-12)
         assert np.array_equal(np.isnan(dkx.cpu().numpy()), np.isnan(hkx)) or (~ok).sum() < 5
+
+
+def test_fuzz_random_configurations_bitwise(st, oracle_mod, torch_mod):
+    """80 random configurations (grid shape, ray count, cap, step, cell sizes, per-ray steps, schedule,
+    layout, tile, division mode, host/device/pinned I/O, fused outputs): everything bit-identical
+    to the oracle."""
+    rng = np.random.default_rng(2026)
+    for it in range(80):
+        nx, ny = int(rng.integers(2, 90)), int(rng.integers(2, 90))
+        n = int(rng.choice([1, 2, 31, 32, 33, 127, 129, 255, 257, 700, 2049]))
+        L = int(rng.choice([1, 2, 3, 17, 64, 300]))
+        stp = float(rng.uniform(0.05, 1.5)); dx = float(rng.uniform(0.1, 3.0)); dy = float(rng.uniform(0.1, 3.0))
+        ax, ay = random_field(rng, nx, ny, scale=float(rng.choice([0.0, 0.01, 0.5])))
+        launch = random_launch(rng, n, nx, ny, kmag=float(rng.uniform(0.2, 3)))
+        if n > 4:
+            launch[0][rng.integers(0, n)] = rng.choice([-0.0, -1e-9, np.nan, nx - 1.0, 1e20])
+        st_ray = rng.uniform(0.05, 1.0, n) if rng.random() < 0.3 else None
+        tiled = bool(rng.random() < 0.5)
+        kw = dict(refill=[None, True, False][int(rng.integers(0, 3))], div_ieee=bool(rng.random() < 0.3),
+                  tiled=tiled, tile=int(rng.choice([32, 64, 128, 256])), want_extras=bool(rng.random() < 0.5))
+        mode = int(rng.integers(0, 3))          # 0 host pageable, 1 host pinned, 2 device
+        want = oracle_mod.trace_batch(*launch, L, stp, dx, dy, nx, ny, ax, ay, st_ray=st_ray)
+        f = st.Field(ax, ay, nx, ny)
+        ins, sr = list(launch), st_ray
+        if mode == 1:
+            ins = [st.pinned_copy(a) for a in launch]
+            sr = st.pinned_copy(st_ray) if st_ray is not None else None
+        elif mode == 2:
+            ins = [torch_mod.from_numpy(a).cuda() for a in launch]
+            sr = torch_mod.from_numpy(st_ray).cuda() if st_ray is not None else None
+        res = st.trace_batch(f, *ins, L=L, st=stp, dx=dx, dy=dy, st_ray=sr, traj=True, **kw)
+        get = (lambda a: a.cpu().numpy()) if mode == 2 else (lambda a: np.asarray(a))
+        ctx = (it, nx, ny, n, L, kw, mode)
+        assert np.array_equal(get(res.nsteps), want["nsteps"]), ctx
+        assert get(res.end_state).tobytes() == want["end"].tobytes(), ctx
+        assert res.traj_ray_major().cpu().numpy().tobytes() == want["traj"].tobytes(), ctx
+        if kw["want_extras"]:
+            ti = get(res.turn_index)
+            r = int(rng.integers(0, n))
+            k = int(want["nsteps"][r])
+            assert int(ti[r]) == oracle_mod.turning_point(want["traj"][r], k), ctx
+            if k >= 1:
+                s_r = stp if st_ray is None else st_ray[r]
+                assert float(get(res.ph_end)[r]).hex() == float(oracle_mod.lax_ph(want["traj"][r, :k], s_r)[1][-1]).hex(), ctx
+        f.close()
