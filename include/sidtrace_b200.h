@@ -184,6 +184,27 @@ int stb_launch_states(const stb_launch_t *a, void *stream);
  * members[offsets[k] .. offsets[k+1]). */
 int stb_field_pages(const double *xout, int64_t n, int64_t *offsets, int64_t *members, int64_t *npages);
 
+/* ---- beam launch conditions on the device (Beam.rays, beam.py:293-331) -------------------------- */
+/* n start points equidistant in arc length along a wavefront given by nw nodes (arc length lax[],
+ * beam-frame x wf_x[]) and the cubic B-spline (t, c) of its y(x); unit normals from the reference's
+ * central differences on the lcm(n, nfront)-point fine grid; Gaussian amplitudes.  Outputs are lab-
+ * frame start points, unit directions and amplitudes -- the inputs of stb_launch_states.
+ * All pointers are DEVICE pointers; asynchronous on `stream`.  Tolerance-level (1e-12) agreement with
+ * the host restatement (SciPy evaluates the same spline). */
+typedef struct stb_beam_s {
+    size_t   struct_size;
+    int64_t  n;                 /* rays (rnum)                                              */
+    int32_t  nfront;            /* Beam._nfront (1000): the fine grid has lcm(n, nfront) points */
+    const double *lax, *wf_x;   /* [nw]                                                      */
+    int32_t  nw;
+    const double *t, *c;        /* knots [nt] and coefficients [nt-4] of the cubic y(x)      */
+    int32_t  nt;
+    double   x0, y0, kx0, ky0, focus;   /* antenna position, unit direction, focus offset    */
+    double   waist, rayleigh;           /* w0 and the Rayleigh length at the edge index      */
+    double  *x, *y, *kx, *ky, *amp;     /* [n] outputs                                       */
+} stb_beam_t;
+int stb_beam_launch(const stb_beam_t *a, void *stream);
+
 /* Trajectory export: packs the KEPT states 0..nsteps[r]-1 of every ray (what the reference's Ray keeps,
  * ray.py:99-102) from a trajectory arena -- ray-major (tile = 0, ray_stride doubles per ray, 0 -> 4*L) or
  * tiled (tile = 32 / 64 / 128) -- into out[offsets[r] .. offsets[r] + nsteps[r]][4].  All pointers are

@@ -27,7 +27,7 @@ F_STATIC = 1 << 5
 EXPORTS = (
     "stb_abi_version", "stb_last_error", "stb_device_count", "stb_set_device",
     "stb_field_create", "stb_field_destroy", "stb_field_shape", "stb_field_peek",
-    "stb_trace", "stb_check", "stb_trace_batch", "stb_launch_states", "stb_field_pages", "stb_pack_traj", "stb_launch_count",
+    "stb_trace", "stb_check", "stb_trace_batch", "stb_launch_states", "stb_beam_launch", "stb_field_pages", "stb_pack_traj", "stb_launch_count",
     "stb_measure_fp64_peak", "stb_measure_store_bw",
 )
 
@@ -82,6 +82,22 @@ class StbLaunch(Structure):
     ]
 
 
+class StbBeam(Structure):
+    """Mirror of ``stb_beam_t``."""
+    _fields_ = [
+        ("struct_size", c_size_t),
+        ("n", c_int64),
+        ("nfront", c_int32),
+        ("lax", c_void_p), ("wf_x", c_void_p),
+        ("nw", c_int32),
+        ("t", c_void_p), ("c", c_void_p),
+        ("nt", c_int32),
+        ("x0", c_double), ("y0", c_double), ("kx0", c_double), ("ky0", c_double), ("focus", c_double),
+        ("waist", c_double), ("rayleigh", c_double),
+        ("x", c_void_p), ("y", c_void_p), ("kx", c_void_p), ("ky", c_void_p), ("amp", c_void_p),
+    ]
+
+
 class SidtraceError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"sidtrace_b200 error {code}: {msg}")
@@ -111,6 +127,8 @@ def _load() -> ctypes.CDLL:
     lib.stb_trace_batch.argtypes = [c_void_p, POINTER(StbBatch), c_void_p]
     lib.stb_launch_states.argtypes = [POINTER(StbLaunch), c_void_p]
     lib.stb_launch_states.restype = c_int
+    lib.stb_beam_launch.argtypes = [POINTER(StbBeam), c_void_p]
+    lib.stb_beam_launch.restype = c_int
     lib.stb_field_pages.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, POINTER(c_int64)]
     lib.stb_field_pages.restype = c_int
     lib.stb_pack_traj.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]

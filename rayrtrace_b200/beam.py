@@ -222,8 +222,36 @@ class Beam:
         fs = self.field(x=x, y=y, n=n_edge, outfmt="dict")
         return x, y, kx, ky, fs["amp"], fs["phase"]
 
-    def rays(self, rnum=None, wave_front=None, dist=None, ampbnd=None, n_field=None, **trace_kw):
-        """Generate and trace the beam's rays: one kernel launch for the whole fan."""
+    def launch_conditions_device(self, rnum, wave_front, n_edge):
+        """``launch_conditions`` on the GPU (``stb_beam_launch``): everything is a function of the ray
+        index and the 1000-node wavefront tables.  Returns CUDA tensors (x, y, kx, ky, amp); agrees
+        with the host version to ~1e-12 (SciPy evaluates the same spline)."""
+        import ctypes
+        import torch
+        from . import _cabi
+        seg = np.sqrt(np.diff(wave_front.x) ** 2 + np.diff(wave_front.y) ** 2)
+        lax = np.cumsum(np.insert(seg, 0, 0))
+        spl = wave_front._spline                      # interp1d(kind='cubic') keeps a BSpline
+        dev = torch.device("cuda", torch.cuda.current_device())
+        tabs = [torch.from_numpy(np.ascontiguousarray(v, np.float64).ravel()).to(dev)
+                for v in (lax, wave_front.x, spl.t, spl.c)]
+        out = [torch.empty(int(rnum), dtype=torch.float64, device=dev) for _ in range(5)]
+        a = _cabi.StbBeam()
+        a.struct_size = ctypes.sizeof(_cabi.StbBeam)
+        a.n, a.nfront = int(rnum), int(Beam._nfront)
+        a.lax, a.wf_x, a.nw = tabs[0].data_ptr(), tabs[1].data_ptr(), int(tabs[0].shape[0])
+        a.t, a.c, a.nt = tabs[2].data_ptr(), tabs[3].data_ptr(), int(tabs[2].shape[0])
+        a.x0, a.y0, a.kx0, a.ky0, a.focus = float(self.x0), float(self.y0), float(self._kx0), float(self._ky0), float(self.focus)
+        a.waist, a.rayleigh = float(self.waist), float(self.rayleigh_len(n=n_edge))
+        a.x, a.y, a.kx, a.ky, a.amp = (t.data_ptr() for t in out)
+        _cabi.check(_cabi.lib.stb_set_device(dev.index or 0))
+        _cabi.check(_cabi.lib.stb_beam_launch(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        torch.cuda.current_stream(dev).synchronize()      # the tables go out of scope here
+        return tuple(out)
+
+    def rays(self, rnum=None, wave_front=None, dist=None, ampbnd=None, n_field=None, device_launch=None, **trace_kw):
+        """Generate and trace the beam's rays: one kernel launch for the whole fan.  For >= 65536
+        rays (or ``device_launch=True``) the launch conditions are generated on the GPU as well."""
         rnum = Beam._nray if rnum is None else rnum
         dist = Beam._dist if dist is None else dist
         ampbnd = Beam._ampbnd if ampbnd is None else ampbnd
@@ -231,7 +259,14 @@ class Beam:
             raise ValueError("rays() needs a density field (the reference dereferences it too, beam.py:328)")
         if wave_front is None:
             wave_front = self.wavefront_r(dist=dist, ampbnd=ampbnd, n_field=n_field)
-        x, y, kx, ky, amps, phase = self.launch_conditions(rnum, wave_front, n_field.refractive_index(freq=self.freq))
+        n_edge = n_field.refractive_index(freq=self.freq)
+        if device_launch is None:
+            device_launch = rnum >= 65536
+        if device_launch:
+            x, y, kx, ky, amps = (t.cpu().numpy() for t in self.launch_conditions_device(rnum, wave_front, n_edge))
+            phase = None                                # returned "for check" only by the reference (beam.py:331)
+        else:
+            x, y, kx, ky, amps, phase = self.launch_conditions(rnum, wave_front, n_edge)
         k = 100 if self.length_unit == "m" else 1     # tracing works in CGS (beam.py:335-338)
         self.bundle = trace_rays(n_field, x * k, y * k, kx, ky, self.freq, amp=amps, want_extras=True, **trace_kw)
         self._ray_cache = None

@@ -112,4 +112,88 @@ __global__ void launch_states_kernel(const LaunchParams p)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Beam.rays on the device (beam.py:293-331): start points equidistant in arc length along the
+// wavefront, unit normals from the reference's fine-grid central differences, Gaussian amplitudes.
+// Everything is a function of the ray index and a few 1000-node tables, so 10^8 rays cost
+// milliseconds instead of minutes of NumPy.
+struct BeamLaunchParams {
+    long long n;            // rnum
+    long long m_fine;       // lcm(rnum, nfront)
+    long long stride;       // m_fine / rnum
+    const double *lax, *wfx;        // [nw] arc length at the wavefront nodes, their beam-frame x
+    int nw;
+    const double *t, *c;            // cubic B-spline of the wavefront y(x): knots [nt], coefficients [nt-4]
+    int nt;
+    double bx0, by0, bkx, bky, focus;     // beam frame (beam.py:103-131)
+    double w0, y_r;                       // waist, Rayleigh length at the edge index (beam.py:176-188)
+    double *x, *y, *kx, *ky, *amp;        // outputs (lab frame)
+};
+
+// np.interp / interp1d(kind='linear') inside the table range
+__device__ __forceinline__ double lin_interp(const double *__restrict__ xp, const double *__restrict__ fp, int n, double v)
+{
+    int lo = 0, hi = n - 1;                         // largest j with xp[j] <= v, clipped to [0, n-2]
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (xp[mid] <= v) lo = mid; else hi = mid - 1;
+    }
+    if (lo > n - 2) return fp[n - 1];
+    const double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
+    return slope * (v - xp[lo]) + fp[lo];
+}
+
+__device__ __forceinline__ double spl1(const double *__restrict__ t, const double *__restrict__ c, int nt, double x)
+{
+    const double xb = t[3], xe = t[nt - 4];
+    x = x < xb ? xb : (x > xe ? xe : x);
+    const int l = knot_interval(t, nt, x);
+    double h[4];
+    bspl3(t, x, l, h);
+    double s = 0.0;
+    for (int i = 0; i < 4; ++i) s += c[l - 3 + i] * h[i];
+    return s;
+}
+
+__global__ void beam_launch_kernel(const BeamLaunchParams p)
+{
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    const double ltot = p.lax[p.nw - 1];
+    const double step_r = p.n > 1 ? ltot / (double)(p.n - 1) : 0.0;        // np.linspace(0, ltot, n)
+    const double step_f = p.m_fine > 1 ? ltot / (double)(p.m_fine - 1) : 0.0;
+    auto lab = [&](double xb, double yb, double &xl, double &yl) {            // beam2lab
+        const double yf = yb + p.focus;
+        xl = p.bky * xb + p.bkx * yf + p.bx0;
+        yl = -p.bkx * xb + p.bky * yf + p.by0;
+    };
+    auto fine = [&](long long j, double &xl, double &yl) {
+        const double tt = j == p.m_fine - 1 ? ltot : (double)j * step_f + 0.0;
+        const double xb = lin_interp(p.lax, p.wfx, p.nw, tt);
+        lab(xb, spl1(p.t, p.c, p.nt, xb), xl, yl);
+    };
+    for (; r < p.n; r += step) {
+        const double tt = r == p.n - 1 ? ltot : (double)r * step_r;
+        const double xb = lin_interp(p.lax, p.wfx, p.nw, tt);
+        const double yb = spl1(p.t, p.c, p.nt, xb);
+        double xl, yl;
+        lab(xb, yb, xl, yl);
+        const long long j = r * p.stride;
+        const long long jlo = j > 0 ? j - 1 : 0, jhi = j < p.m_fine - 1 ? j + 1 : p.m_fine - 1;
+        double xlo, ylo, xhi, yhi;
+        fine(jlo, xlo, ylo);
+        fine(jhi, xhi, yhi);
+        const double width = (j == 0 || j == p.m_fine - 1) ? 1.0 : 2.0;       // np.gradient: one-sided at the ends
+        double kx = -((yhi - ylo) / width), ky = (xhi - xlo) / width;
+        const double nrm = sqrt(kx * kx + ky * ky);
+        kx /= nrm; ky /= nrm;
+        // Gaussian amplitude at the start point (beam.py:183-188), beam frame of the lab point
+        const double xx = p.bky * (xl - p.bx0) - p.bkx * (yl - p.by0);
+        const double yy = p.bkx * (xl - p.bx0) + p.bky * (yl - p.by0) - p.focus;
+        const double wa = p.w0 * sqrt(1.0 + yy * yy / (p.y_r * p.y_r));
+        p.x[r] = xl; p.y[r] = yl; p.kx[r] = kx; p.ky[r] = ky;
+        p.amp[r] = sqrt(p.w0 / wa) * exp(-(xx * xx) / (wa * wa));
+    }
+}
+
 }  // namespace stb

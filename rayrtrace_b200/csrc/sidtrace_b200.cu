@@ -606,6 +606,39 @@ int stb_field_pages(const double *xout, int64_t n, int64_t *offsets, int64_t *me
     return STB_OK;
 }
 
+int stb_beam_launch(const stb_beam_t *a, void *stream)
+{
+    if (!a) return fail(STB_ERR_ARG, "stb_beam_launch: NULL argument");
+    if (a->struct_size != sizeof(stb_beam_t))
+        return fail(STB_ERR_ARG, "stb_beam_launch: struct_size %zu != %zu (ABI mismatch)", a->struct_size, sizeof(stb_beam_t));
+    if (a->n < 0 || a->nfront < 2 || a->nw < 2 || a->nt < 8)
+        return fail(STB_ERR_ARG, "stb_beam_launch: bad sizes");
+    const void *ptrs[] = {a->lax, a->wf_x, a->t, a->c, a->x, a->y, a->kx, a->ky, a->amp};
+    for (const void *q : ptrs) if (!q) return fail(STB_ERR_ARG, "stb_beam_launch: NULL pointer");
+    if (a->n == 0) return STB_OK;
+    // m_fine = lcm(n, nfront)
+    long long g = a->n, h = a->nfront;
+    while (h) { const long long tmp = g % h; g = h; h = tmp; }
+    stb::BeamLaunchParams p{};
+    p.n = a->n;
+    p.m_fine = a->n / g * (long long)a->nfront;
+    p.stride = p.m_fine / a->n;
+    p.lax = a->lax; p.wfx = a->wf_x; p.nw = a->nw;
+    p.t = a->t; p.c = a->c; p.nt = a->nt;
+    p.bx0 = a->x0; p.by0 = a->y0; p.bkx = a->kx0; p.bky = a->ky0; p.focus = a->focus;
+    p.w0 = a->waist; p.y_r = a->rayleigh;
+    p.x = a->x; p.y = a->y; p.kx = a->kx; p.ky = a->ky; p.amp = a->amp;
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long blocks = (a->n + 255) / 256;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    stb::beam_launch_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    g_launches++;
+    CU(cudaGetLastError());
+    return STB_OK;
+}
+
 int stb_launch_states(const stb_launch_t *a, void *stream)
 {
     if (!a) return fail(STB_ERR_ARG, "stb_launch_states: NULL argument");

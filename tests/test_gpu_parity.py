@@ -816,3 +816,18 @@ def test_fuzz_random_configurations_bitwise(st, oracle_mod, torch_mod):
                 s_r = stp if st_ray is None else st_ray[r]
                 assert float(get(res.ph_end)[r]).hex() == float(oracle_mod.lax_ph(want["traj"][r, :k], s_r)[1][-1]).hex(), ctx
         f.close()
+
+
+@pytest.mark.parametrize("rnum", [7, 251, 1000, 70001])
+def test_beam_launch_conditions_device_match_host(st, beam_fix, rnum):
+    """stb_beam_launch (Beam.rays launch conditions, beam.py:293-331, on the GPU) against the host
+    restatement, which is itself pinned bit for bit to the reference's Beam.rays: 1e-11."""
+    from scipy.interpolate import interp1d
+    from rayrtrace_b200.beam import Beam
+    b = Beam(x0=float(beam_fix["x0"]), y0=float(beam_fix["y0"]), kx0=0.05, ky0=1)
+    b.k0 = (0.05, 1.0)                                  # slightly tilted beam: exercises the frame rotation
+    wf = interp1d(beam_fix["wf_x"], beam_fix["wf_y"], kind="cubic")
+    host = b.launch_conditions(rnum, wf, 0.998)
+    devo = [t.cpu().numpy() for t in b.launch_conditions_device(rnum, wf, 0.998)]
+    for h, d, name in zip(host[:5], devo, ("x", "y", "kx", "ky", "amp")):
+        np.testing.assert_allclose(d, h, rtol=1e-11, atol=1e-11, err_msg=name)
