@@ -128,11 +128,10 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.path = tempfile.mktemp(suffix=".csv")
+        fd, self.path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
         self.proc = None
         self.gpu = gpu_index
-        self.t_start = None
-        self.t_stop = None
 
     def start(self):
         try:
