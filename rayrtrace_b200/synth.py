@@ -51,11 +51,12 @@ def antenna_positions():
     return xa, -np.sqrt(R_ANT ** 2 - xa ** 2)
 
 
-def gaussian_fan(nrays, *, freq=BEAM_FREQ, n_edge=1.0):
+def gaussian_fan(nrays, *, freq=BEAM_FREQ, n_edge=1.0, index=None):
     """Start points, unit normals and amplitudes of `nrays` rays spread over the seven
     upward-pointing beams, equidistant in arc length along the (spherical) wavefront at
     DIST from the focus -- the analytic stand-in for Beam.rays (beam.py:278-331).
-    Returns (x, y, kx, ky, amp) in lab coordinates."""
+    Returns (x, y, kx, ky, amp) in lab coordinates; `index` (global ray indices) restricts
+    the result to a shard without materialising the whole fan."""
     lam = const.speed_of_light * 100 / freq
     y_r = np.pi * WAIST ** 2 * n_edge / lam                # beam.py:134
     wa = WAIST * np.sqrt(1 + DIST ** 2 / y_r ** 2)         # beam.py:183
@@ -65,17 +66,21 @@ def gaussian_fan(nrays, *, freq=BEAM_FREQ, n_edge=1.0):
     xa, ya = antenna_positions()
     per = np.full(7, nrays // 7)
     per[: nrays % 7] += 1
-    xs, ys, kxs, kys, amps = [], [], [], [], []
-    for a in range(7):
-        th = np.linspace(-th_max, th_max, per[a]) if per[a] > 1 else np.zeros(per[a])
-        xb = rc * np.sin(th)
-        yb = DIST - rc + rc * np.cos(th)                   # along-axis distance from the focus
-        xs.append(xa[a] + xb)
-        ys.append(ya[a] + (yb + FOCUS))                    # beam2lab with k0 = (0, 1) (beam.py:117-131)
-        kxs.append(np.sin(th))
-        kys.append(np.cos(th))
-        amps.append(np.sqrt(WAIST / wa) * np.exp(-xb ** 2 / wa ** 2))   # beam.py:188
-    return tuple(np.concatenate(v) for v in (xs, ys, kxs, kys, amps))
+    first = np.concatenate(([0], np.cumsum(per)))          # ray index where each antenna's fan starts
+    idx = np.arange(nrays, dtype=np.int64) if index is None else np.asarray(index, np.int64)
+    ant = np.searchsorted(first, idx, side="right") - 1
+    loc = idx - first[ant]
+    cnt = per[ant]
+    # np.linspace(-th_max, th_max, cnt)[loc], element for element
+    step = np.where(cnt > 1, (2 * th_max) / np.maximum(cnt - 1, 1), 0.0)
+    th = np.where(cnt > 1, loc * step + (-th_max), 0.0)
+    th = np.where((cnt > 1) & (loc == cnt - 1), th_max, th)
+    xb = rc * np.sin(th)
+    yb = DIST - rc + rc * np.cos(th)                       # along-axis distance from the focus
+    x = xa[ant] + xb
+    y = ya[ant] + (yb + FOCUS)                             # beam2lab with k0 = (0, 1) (beam.py:117-131)
+    amp = np.sqrt(WAIST / wa) * np.exp(-xb ** 2 / wa ** 2)  # beam.py:188
+    return x, y, np.sin(th), np.cos(th), amp
 
 
 @dataclass
@@ -101,17 +106,30 @@ def default_cap(nx: int) -> int:
     return int(-(-(3 * nx // 2) // 128) * 128)
 
 
-def beam_case(nx=1001, nrays=1_000_000, *, seed=0, n0=4e13, shift=0.6, elon=1.1, L=None, name=None) -> BeamCase:
+def beam_case(nx=1001, nrays=1_000_000, *, seed=0, n0=4e13, shift=0.6, elon=1.1, L=None, name=None,
+              index=None, device_launch=False) -> BeamCase:
     """BASELINE configs 3/5 shape: shaped density on an nx^2 grid + seven-beam fan of `nrays` rays.
     `seed` jitters the start angle of every ray by a fraction of the ray spacing so no two
-    rays are identical."""
+    rays are identical.  `index` (global ray indices) builds only that shard of the fan (the jitter
+    is a hash of the global index then, so shards of different ranks are consistent);
+    `device_launch` prepares the launch states on the GPU (`launch_states_device`)."""
     n, x, y = shaped_density(nx, n0=n0, shift=shift, elon=elon)
     nf = Nfield(n, x=x, y=y)
-    xs, ys, kx, ky, amp = gaussian_fan(nrays)
-    rng = np.random.default_rng(seed)
-    jit = rng.uniform(-1e-4, 1e-4, nrays)
+    xs, ys, kx, ky, amp = gaussian_fan(nrays, index=index)
+    if index is None:
+        jit = np.random.default_rng(seed).uniform(-1e-4, 1e-4, nrays)
+    else:   # counter-based jitter: a function of (seed, global ray index) only
+        h = (np.asarray(index, np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)) * np.uint64(0xBF58476D1CE4E5B9)
+        h ^= h >> np.uint64(31)
+        jit = ((h >> np.uint64(11)).astype(np.float64) / 2.0 ** 53 * 2 - 1) * 1e-4
     kx, ky = kx * np.cos(jit) - ky * np.sin(jit), kx * np.sin(jit) + ky * np.cos(jit)
-    xg, yg, kxs, kys, freq = launch_states(nf, xs, ys, kx, ky, BEAM_FREQ)
+    if device_launch:
+        from .ray import launch_states_device
+        xg, yg, kxs, kys, freq = launch_states_device(nf, xs, ys, kx, ky, BEAM_FREQ)
+        xg, yg, kxs, kys = (t.cpu().numpy() for t in (xg, yg, kxs, kys))
+    else:
+        xg, yg, kxs, kys, freq = launch_states(nf, xs, ys, kx, ky, BEAM_FREQ)
+    nrays = len(xs)
     return BeamCase(nfield=nf, launch=(xg, yg, kxs, kys), amp=amp, x0=xs, y0=ys, nrays=nrays,
                     L=L or default_cap(nx), st=float(nf.st), dx=float(nf.dx[0]), dy=float(nf.dy[0]), freq=freq,
                     name=name or f"ft2-7beam-fan-{nrays}rays-{nx}x{nx}")

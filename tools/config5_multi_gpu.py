@@ -34,13 +34,15 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    case = synth.beam_case(nx=args.nx, nrays=args.nrays, seed=0)
+    # every rank builds ONLY its interleaved shard of the fan, launch states prepared on the device
+    idx = np.arange(rank, args.nrays, world, dtype=np.int64)
+    case = synth.beam_case(nx=args.nx, nrays=args.nrays, seed=0, index=idx, device_launch=True)
     nf = case.nfield
     field = sidtrace.Field(np.ascontiguousarray(nf.ax), np.ascontiguousarray(nf.ay), nf.nx, nf.ny)
     hist_kw = dict(xorg=float(nf.x[0]), yorg=float(nf.y[0]), r_lcs=synth.R_DIA, rho_max=1.2)
     kw = dict(L=case.L, st=case.st, dx=case.dx, dy=case.dy)
 
-    staged = rd.stage_shard(case.launch, case.amp)        # this rank's rays, resident in HBM
+    staged = ([torch.from_numpy(a).to(dev) for a in case.launch], torch.from_numpy(case.amp).to(dev), args.nrays)
 
     def run(gather=True):
         return rd.trace_sharded(field, None, staged=staged, nbins=args.nbins, hist_kw=hist_kw, gather=gather, **kw)
@@ -63,8 +65,10 @@ def main():
         dist.all_reduce(steps, op=dist.ReduceOp.SUM)
     ok = None
     if args.check and rank == 0:
-        d_in = [torch.from_numpy(a).to(dev) for a in case.launch]
-        one = sidtrace.trace_batch(field, *d_in, amp=torch.from_numpy(case.amp).to(dev), nbins=args.nbins, **hist_kw, **kw)
+        whole = synth.beam_case(nx=args.nx, nrays=args.nrays, seed=0, index=np.arange(args.nrays, dtype=np.int64),
+                                device_launch=True)
+        d_in = [torch.from_numpy(a).to(dev) for a in whole.launch]
+        one = sidtrace.trace_batch(field, *d_in, amp=torch.from_numpy(whole.amp).to(dev), nbins=args.nbins, **hist_kw, **kw)
         torch.cuda.synchronize()
         same_steps = bool(torch.equal(one.nsteps, gathered[0]))
         same_end = bool(torch.equal(one.end_state, gathered[1]))
