@@ -135,7 +135,7 @@ def beam_case(nx=1001, nrays=1_000_000, *, seed=0, n0=4e13, shift=0.6, elon=1.1,
                     name=name or f"ft2-7beam-fan-{nrays}rays-{nx}x{nx}")
 
 
-def sweep_case(nx=201, nrays=100_000, *, seed=0, L=None) -> BeamCase:
+def sweep_case(nx=201, nrays=100_000, *, seed=0, L=None, device_launch=False) -> BeamCase:
     """BASELINE config 4 shape: launch-angle / density-regime sweep with cutoff-heavy
     trajectories: an OVER-dense core (n0 = 1.3 n_c) reflects head-on rays, grazing rays
     skim it, and launch angles span +-0.3 rad (Beam.k0 rotation, beam.py:96-100)."""
@@ -145,7 +145,12 @@ def sweep_case(nx=201, nrays=100_000, *, seed=0, L=None) -> BeamCase:
     xs = rng.uniform(-7.5, 7.5, nrays)
     ys = np.full(nrays, -9.5)
     ang = rng.uniform(-0.3, 0.3, nrays)
-    xg, yg, kxs, kys, freq = launch_states(nf, xs, ys, np.sin(ang), np.cos(ang), BEAM_FREQ)
+    if device_launch:
+        from .ray import launch_states_device
+        xg, yg, kxs, kys, freq = launch_states_device(nf, xs, ys, np.sin(ang), np.cos(ang), BEAM_FREQ)
+        xg, yg, kxs, kys = (t.cpu().numpy() for t in (xg, yg, kxs, kys))
+    else:
+        xg, yg, kxs, kys, freq = launch_states(nf, xs, ys, np.sin(ang), np.cos(ang), BEAM_FREQ)
     return BeamCase(nfield=nf, launch=(xg, yg, kxs, kys), amp=np.ones(nrays), x0=xs, y0=ys, nrays=nrays,
                     L=L or 4 * default_cap(nx), st=float(nf.st), dx=float(nf.dx[0]), dy=float(nf.dy[0]), freq=freq,
                     name=f"cutoff-sweep-{nrays}rays-{nx}x{nx}")

@@ -493,11 +493,12 @@ def test_config2_thousand_ray_beam_deposition(st, oracle_mod):
 
 
 def test_config4_sweep_invariants(st, oracle_mod, torch_mod):
-    """BASELINE config 4 shape: launch-angle x frequency sweep over an over-dense (reflecting)
-    profile, 2*10^6 rays with per-ray step (frequency) -- a cutoff-heavy, ragged workload.
-    Schedules agree bit for bit; a 3000-ray subsample equals the oracle; a third of the rays reflect."""
+    """BASELINE config 4: launch-angle x frequency sweep over an over-dense (reflecting) profile,
+    10^7 rays with per-ray step (frequency) -- a cutoff-heavy, ragged workload (launch states
+    prepared on the device).  Schedules agree bit for bit; a 3000-ray subsample equals the oracle;
+    a third of the rays reflect."""
     from rayrtrace_b200 import synth
-    case = synth.sweep_case(nx=201, nrays=2_000_000, seed=4)
+    case = synth.sweep_case(nx=201, nrays=10_000_000, seed=4, device_launch=True)
     rng = np.random.default_rng(4)
     fscale = rng.uniform(100e9, 160e9, case.nrays) / case.freq          # per-ray frequency, 100-160 GHz
     st_ray = case.st / fscale                                           # st ~ 1/w (den.py:107); k0 ~ w
