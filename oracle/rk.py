@@ -1,0 +1,126 @@
+"""ctypes wrapper of oracle/rk_oracle.c -- TEST INFRASTRUCTURE ONLY, PARITY UNPINNED.
+
+The checker of the adaptive-RK extension (include/sidtrace_b200_rk.h).  The reference has no
+counterpart; see the header of rk_oracle.c.  Never imported by ``rayrtrace_b200``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "librk_oracle.so")
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+
+LEFT_DOMAIN, TAU_MAX, MAX_STEPS, STEP_UNDERFLOW, START_OUTSIDE = range(5)
+
+
+class _Medium(ctypes.Structure):
+    _fields_ = [("X", _dp), ("alpha", _dp), ("nx", ctypes.c_int), ("ny", ctypes.c_int),
+                ("xorg", ctypes.c_double), ("yorg", ctypes.c_double), ("rdx", ctypes.c_double), ("rdy", ctypes.c_double),
+                ("Y0R0", ctypes.c_double), ("R0", ctypes.c_double), ("xmode", ctypes.c_int), ("interp", ctypes.c_int)]
+
+
+class _Ctl(ctypes.Structure):
+    _fields_ = [("rtol", ctypes.c_double), ("atol_r", ctypes.c_double), ("atol_p", ctypes.c_double),
+                ("h0", ctypes.c_double), ("hmin", ctypes.c_double), ("hmax", ctypes.c_double), ("tau_max", ctypes.c_double),
+                ("max_steps", ctypes.c_int), ("hist", _dp), ("nbins", ctypes.c_int),
+                ("xaxis", ctypes.c_double), ("yaxis", ctypes.c_double), ("r_rlcs", ctypes.c_double),
+                ("bins_per_rho", ctypes.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
+        L = ctypes.CDLL(_SO)
+        L.rk_oracle_eval.restype = None
+        L.rk_oracle_eval.argtypes = [ctypes.POINTER(_Medium)] + [ctypes.c_double] * 4 + [_dp] * 4
+        L.rk_oracle_prefilter.restype = None
+        L.rk_oracle_prefilter.argtypes = [_dp, ctypes.c_int, ctypes.c_int, _dp]
+        L.rk_oracle_batch.restype = ctypes.c_int
+        L.rk_oracle_batch.argtypes = [ctypes.POINTER(_Medium), ctypes.POINTER(_Ctl), ctypes.c_longlong] + [_dp] * 7 + \
+            [_dp] * 6 + [_ip] * 3 + [_dp, _dp, ctypes.c_longlong, ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _pi(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def _f64(a, n=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if n is not None and a.shape != (n,):
+        a = np.ascontiguousarray(np.broadcast_to(a, (n,)))
+    return a
+
+
+BILINEAR, CATMULL_ROM, BSPLINE = 0, 1, 2
+
+
+def prefilter(nodes):
+    """[ny, nx] node values -> [ny+2, nx+2] natural cubic B-spline coefficients."""
+    nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+    ny, nx = nodes.shape
+    coef = np.empty((ny + 2, nx + 2))
+    lib().rk_oracle_prefilter(_p(nodes), nx, ny, _p(coef))
+    return coef
+
+
+class Medium:
+    """Host copy of the medium the kernel reads (stb_medium_desc_t)."""
+
+    def __init__(self, X, xorg, yorg, dx, dy, *, alpha=None, mode="O", Y0=0.0, R0=55.0, interp=BSPLINE):
+        """X, alpha: [ny, nx] NODE values; for interp = BSPLINE they are prefiltered here."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        ny, nx = X.shape
+        if interp == BSPLINE:
+            X = prefilter(X)
+            alpha = None if alpha is None else prefilter(alpha)
+        self.X = X
+        self.alpha = None if alpha is None else np.ascontiguousarray(alpha, dtype=np.float64)
+        self.c = _Medium(_p(self.X), _p(self.alpha), nx, ny, float(xorg), float(yorg), 1.0 / float(dx), 1.0 / float(dy),
+                         float(Y0) * float(R0), float(R0), 1 if mode == "X" else 0, int(interp))
+
+    def eval(self, x, y, xs=1.0, ys=1.0):
+        """(fx, fy, alpha, N^2) at one point."""
+        out = [ctypes.c_double() for _ in range(4)]
+        lib().rk_oracle_eval(ctypes.byref(self.c), xs, ys, float(x), float(y), *[ctypes.byref(o) for o in out])
+        return tuple(o.value for o in out)
+
+
+def trace(med: Medium, x0, y0, px0, py0, *, rtol=1e-9, atol_r=1e-9, atol_p=1e-9, h0=0.05, hmin=1e-12, hmax=1e30,
+          tau_max=float("inf"), max_steps=100000, xscale=None, yscale=None, amp=None, nbins=0, xaxis=0.0, yaxis=0.0,
+          r_lcs=1.0, rho_max=1.0, L=0, aux=False, threads=1):
+    x0 = _f64(np.atleast_1d(x0))
+    n = x0.shape[0]
+    y0, px0, py0 = _f64(y0, n), _f64(px0, n), _f64(py0, n)
+    xscale, yscale, amp = _f64(xscale, n), _f64(yscale, n), _f64(amp, n)
+    hist = np.zeros(nbins) if nbins else None
+    ctl = _Ctl(rtol, atol_r, atol_p, h0, hmin, hmax, tau_max, int(max_steps), _p(hist), int(nbins), xaxis, yaxis,
+               1.0 / r_lcs, (nbins / rho_max) if nbins else 0.0)
+    end = np.empty((4, n))
+    tau, phi, sig, n2min, ham = (np.empty(n) for _ in range(5))
+    nacc, nrej, status = (np.empty(n, dtype=np.int32) for _ in range(3))
+    traj = np.full((n, L, 4), np.nan) if L else None
+    auxa = np.full((n, L, 2), np.nan) if (L and aux) else None
+    lib().rk_oracle_batch(ctypes.byref(med.c), ctypes.byref(ctl), n, _p(x0), _p(y0), _p(px0), _p(py0), _p(xscale),
+                          _p(yscale), _p(amp), _p(end), _p(tau), _p(phi), _p(sig), _p(n2min), _p(ham), _pi(nacc), _pi(nrej),
+                          _pi(status), _p(traj), _p(auxa), int(L), int(threads))
+    return dict(end_state=end, tau=tau, phi=phi, sig=sig, n2_min=n2min, ham=ham, nacc=nacc, nrej=nrej, status=status,
+                traj=traj, aux=auxa, hist=hist)

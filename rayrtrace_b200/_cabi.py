@@ -29,6 +29,8 @@ EXPORTS = (
     "stb_field_create", "stb_field_destroy", "stb_field_shape", "stb_field_peek",
     "stb_trace", "stb_check", "stb_trace_batch", "stb_launch_states", "stb_beam_launch", "stb_field_pages", "stb_pack_traj", "stb_launch_count",
     "stb_measure_fp64_peak", "stb_measure_store_bw",
+    # include/sidtrace_b200_rk.h (adaptive-RK extension)
+    "stb_medium_create", "stb_medium_destroy", "stb_medium_table", "stb_trace_rk",
 )
 
 
@@ -98,6 +100,43 @@ class StbBeam(Structure):
     ]
 
 
+class StbMediumDesc(Structure):
+    """Mirror of ``stb_medium_desc_t`` (include/sidtrace_b200_rk.h)."""
+    _fields_ = [
+        ("struct_size", c_size_t),
+        ("nx", c_int32), ("ny", c_int32),
+        ("xorg", c_double), ("yorg", c_double),
+        ("dx", c_double), ("dy", c_double),
+        ("X", c_void_p), ("alpha", c_void_p),
+        ("on_device", c_int32), ("mode", c_int32), ("interp", c_int32),
+        ("Y0", c_double), ("R0", c_double),
+    ]
+
+
+class StbRk(Structure):
+    """Mirror of ``stb_rk_t`` (include/sidtrace_b200_rk.h)."""
+    _fields_ = [
+        ("struct_size", c_size_t),
+        ("flags", c_uint32),
+        ("nrays", c_int64),
+        ("x0", c_void_p), ("y0", c_void_p), ("px0", c_void_p), ("py0", c_void_p),
+        ("xscale", c_void_p), ("yscale", c_void_p), ("amp", c_void_p),
+        ("rtol", c_double), ("atol_r", c_double), ("atol_p", c_double),
+        ("h0", c_double), ("hmin", c_double), ("hmax", c_double),
+        ("tau_max", c_double),
+        ("max_steps", c_int32),
+        ("end_state", c_void_p),
+        ("tau_end", c_void_p), ("phi_end", c_void_p), ("sig_end", c_void_p), ("n2_min", c_void_p), ("ham_end", c_void_p),
+        ("nacc", c_void_p), ("nrej", c_void_p), ("status", c_void_p),
+        ("traj", c_void_p), ("traj_aux", c_void_p),
+        ("L", c_int64),
+        ("hist", c_void_p),
+        ("nbins", c_int32),
+        ("xaxis", c_double), ("yaxis", c_double),
+        ("r_lcs", c_double), ("rho_max", c_double),
+    ]
+
+
 class SidtraceError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"sidtrace_b200 error {code}: {msg}")
@@ -137,6 +176,14 @@ def _load() -> ctypes.CDLL:
     lib.stb_launch_count.argtypes = []
     lib.stb_measure_fp64_peak.argtypes = [POINTER(c_double)]
     lib.stb_measure_store_bw.argtypes = [c_size_t, POINTER(c_double)]
+    lib.stb_medium_create.argtypes = [POINTER(StbMediumDesc), POINTER(c_void_p)]
+    lib.stb_medium_create.restype = c_int
+    lib.stb_medium_destroy.argtypes = [c_void_p]
+    lib.stb_medium_destroy.restype = c_int
+    lib.stb_medium_table.argtypes = [c_void_p, c_int, c_void_p, c_size_t]
+    lib.stb_medium_table.restype = c_int
+    lib.stb_trace_rk.argtypes = [c_void_p, POINTER(StbRk), c_void_p]
+    lib.stb_trace_rk.restype = c_int
     for name in ("stb_device_count", "stb_set_device", "stb_field_create", "stb_field_destroy",
                  "stb_field_shape", "stb_field_peek", "stb_trace", "stb_check", "stb_trace_batch",
                  "stb_measure_fp64_peak", "stb_measure_store_bw"):

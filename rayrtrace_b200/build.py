@@ -14,8 +14,10 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "sidtrace_b200.cu")
-DEPS = [SRC, os.path.join(_HERE, "csrc", "trace_kernels.cuh"), os.path.join(_HERE, "csrc", "launch_kernels.cuh"),
-        os.path.join(os.path.dirname(_HERE), "include", "sidtrace_b200.h")]
+SRC_RK = os.path.join(_HERE, "csrc", "rk_b200.cu")      # adaptive-RK physics mode (extension)
+SOURCES = [SRC, SRC_RK]
+DEPS = SOURCES + [os.path.join(_HERE, "csrc", h) for h in ("trace_kernels.cuh", "launch_kernels.cuh", "rk_kernels.cuh")] + [
+    os.path.join(os.path.dirname(_HERE), "include", h) for h in ("sidtrace_b200.h", "sidtrace_b200_rk.h")]
 LIB_DIR = os.path.join(_HERE, "_lib")
 LIB = os.path.join(LIB_DIR, "libsidtrace_b200.so")
 
@@ -25,6 +27,7 @@ NVCC_FLAGS = [
     "-fmad=false",                 # parity: no FMA contraction anywhere (kernels use explicit _rn intrinsics too)
     "-Xcompiler", "-fPIC", "-shared",
     "-cudart", "static",
+    "--threads", "2",
 ]
 
 
@@ -46,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     # the image exports CC=/opt/gcc/bin/gcc; nvcc picks its host compiler from PATH
     subprocess.check_call(cmd)
     return LIB

@@ -1,0 +1,234 @@
+// rk_b200.cu -- C ABI of the adaptive-RK physics mode (include/sidtrace_b200_rk.h) over
+// rk_kernels.cuh.  Linked into the same libsidtrace_b200.so as sidtrace_b200.cu.
+#include "../../include/sidtrace_b200_rk.h"
+#include "rk_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <new>
+#include <vector>
+
+extern "C" int stb_internal_fail(int code, const char *msg);
+extern "C" void stb_internal_count_launch(void);
+
+namespace {
+
+constexpr int kCounters = 64;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    return stb_internal_fail(code, buf);
+}
+
+#define CU(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? STB_ERR_NOMEM : STB_ERR_CUDA,  \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+}  // namespace
+
+struct stb_medium_s {
+    int device = 0;
+    int num_sms = 0;
+    stbrk::Medium m{};
+    int mode = 0, interp = 2;
+    double *X = nullptr, *alpha = nullptr;
+    unsigned long long *counter = nullptr;   // kCounters queue heads used round-robin
+    unsigned launch_seq = 0;
+};
+
+namespace {
+
+template <int INTERP, bool XMODE, bool ABSORB>
+int launch_rk(const stbrk::Params &p, int num_sms, cudaStream_t s)
+{
+    auto kern = stbrk::rk_kernel<INTERP, XMODE, ABSORB>;
+    const size_t smem = (ABSORB && p.hist) ? (size_t)p.nbins * sizeof(double) : 0;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, stbrk::kBlock, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (long long)num_sms * per_sm;
+    const long long blocks_all = (p.nrays + stbrk::kBlock - 1) / stbrk::kBlock;
+    if (blocks > blocks_all) blocks = blocks_all;
+    CU(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), s));
+    kern<<<(unsigned)blocks, stbrk::kBlock, smem, s>>>(p);
+    stb_internal_count_launch();
+    CU(cudaGetLastError());
+    return STB_OK;
+}
+
+template <int INTERP>
+int launch_mode(const stbrk::Params &p, bool xmode, bool absorb, int num_sms, cudaStream_t s)
+{
+    if (xmode) return absorb ? launch_rk<INTERP, true, true>(p, num_sms, s) : launch_rk<INTERP, true, false>(p, num_sms, s);
+    return absorb ? launch_rk<INTERP, false, true>(p, num_sms, s) : launch_rk<INTERP, false, false>(p, num_sms, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int stb_medium_create(const stb_medium_desc_t *d, stb_medium_t *out)
+{
+    if (!d || !out) return fail(STB_ERR_ARG, "stb_medium_create: NULL argument");
+    if (d->struct_size != sizeof(stb_medium_desc_t))
+        return fail(STB_ERR_ARG, "stb_medium_create: struct_size %zu != %zu (header/library mismatch)", d->struct_size,
+                    sizeof(stb_medium_desc_t));
+    if (!d->X) return fail(STB_ERR_ARG, "stb_medium_create: X is NULL");
+    if (d->nx < 2 || d->ny < 2) return fail(STB_ERR_ARG, "stb_medium_create: nx, ny must be >= 2 (got %d, %d)", d->nx, d->ny);
+    if ((long long)d->nx * d->ny > 0x7fffffffLL) return fail(STB_ERR_RANGE, "stb_medium_create: nx*ny exceeds int32");
+    if (!(d->dx > 0.0) || !(d->dy > 0.0) || !std::isfinite(d->dx) || !std::isfinite(d->dy))
+        return fail(STB_ERR_ARG, "stb_medium_create: dx, dy must be positive and finite");
+    if (d->mode != STB_RK_MODE_O && d->mode != STB_RK_MODE_X) return fail(STB_ERR_ARG, "stb_medium_create: unknown mode %d", d->mode);
+    if (d->mode == STB_RK_MODE_X && !(d->R0 > 0.0)) return fail(STB_ERR_ARG, "stb_medium_create: the X mode needs R0 > 0");
+
+    if (d->interp != STB_RK_INTERP_BILINEAR && d->interp != STB_RK_INTERP_CATMULL_ROM && d->interp != STB_RK_INTERP_BSPLINE)
+        return fail(STB_ERR_ARG, "stb_medium_create: unknown interpolation %d", d->interp);
+
+    stb_medium_s *m = new (std::nothrow) stb_medium_s;
+    if (!m) return fail(STB_ERR_NOMEM, "stb_medium_create: host allocation failed");
+    cudaError_t e = cudaGetDevice(&m->device);
+    const int nx = d->nx, ny = d->ny;
+    const bool spline = d->interp == STB_RK_INTERP_BSPLINE;
+    const size_t bytes = (size_t)nx * ny * sizeof(double);
+    const size_t tbytes = spline ? (size_t)(nx + 2) * (ny + 2) * sizeof(double) : bytes;
+    const cudaMemcpyKind kind = d->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    double *nodes = nullptr, *half = nullptr, *piv = nullptr;   // B-spline prefilter scratch
+    do {
+        if (e != cudaSuccess) break;
+        cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device);
+        if ((e = cudaMalloc(&m->X, tbytes)) != cudaSuccess) break;
+        if (d->alpha && (e = cudaMalloc(&m->alpha, tbytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&m->counter, kCounters * sizeof(unsigned long long))) != cudaSuccess) break;
+        if (!spline) {
+            if ((e = cudaMemcpy(m->X, d->X, bytes, kind)) != cudaSuccess) break;
+            if (d->alpha && (e = cudaMemcpy(m->alpha, d->alpha, bytes, kind)) != cudaSuccess) break;
+            break;
+        }
+        // reciprocal pivots of the tridiagonal (1, 4, 1) system: data-independent
+        const int nmax = nx > ny ? nx : ny;
+        std::vector<double> R((size_t)nmax + 1, 0.0);
+        R[1] = 0.25;
+        for (int i = 2; i <= nmax; ++i) R[i] = 1.0 / (4.0 - R[i - 1]);
+        if ((e = cudaMalloc(&piv, R.size() * sizeof(double))) != cudaSuccess) break;
+        if ((e = cudaMemcpy(piv, R.data(), R.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&nodes, bytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&half, (size_t)(nx + 2) * ny * sizeof(double))) != cudaSuccess) break;
+        for (int which = 0; which < 2 && e == cudaSuccess; ++which) {
+            const double *src = which ? d->alpha : d->X;
+            double *dst = which ? m->alpha : m->X;
+            if (!src) continue;
+            if ((e = cudaMemcpy(nodes, src, bytes, kind)) != cudaSuccess) break;
+            // rows: [ny][nx] -> [ny][nx+2]; columns: [ny][nx+2] -> [ny+2][nx+2]
+            stbrk::bspline_prefilter_kernel<<<(ny + 127) / 128, 128>>>(nodes, nx, 1, half, nx + 2, 1, piv, nx, ny);
+            stbrk::bspline_prefilter_kernel<<<(nx + 2 + 127) / 128, 128>>>(half, 1, nx + 2, dst, 1, nx + 2, piv, ny, nx + 2);
+            stb_internal_count_launch(); stb_internal_count_launch();
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    } while (0);
+    cudaFree(nodes); cudaFree(half); cudaFree(piv);
+    if (e != cudaSuccess) {
+        const int rc = fail(e == cudaErrorMemoryAllocation ? STB_ERR_NOMEM : STB_ERR_CUDA, "stb_medium_create: %s",
+                            cudaGetErrorString(e));
+        cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->counter);
+        delete m;
+        return rc;
+    }
+    m->mode = d->mode;
+    m->interp = d->interp;
+    m->m.X = m->X; m->m.alpha = m->alpha;
+    m->m.nx = d->nx; m->m.ny = d->ny;
+    m->m.xorg = d->xorg; m->m.yorg = d->yorg;
+    m->m.rdx = 1.0 / d->dx; m->m.rdy = 1.0 / d->dy;
+    m->m.Y0R0 = d->Y0 * d->R0; m->m.R0 = d->R0;
+    *out = m;
+    return STB_OK;
+}
+
+int stb_medium_table(stb_medium_t m, int which, double *host_out, size_t count)
+{
+    if (!m || !host_out) return fail(STB_ERR_ARG, "stb_medium_table: NULL argument");
+    const double *src = which ? m->alpha : m->X;
+    if (!src) return fail(STB_ERR_ARG, "stb_medium_table: the medium has no absorption table");
+    const int pad = m->interp == STB_RK_INTERP_BSPLINE ? 2 : 0;
+    const size_t have = (size_t)(m->m.nx + pad) * (size_t)(m->m.ny + pad);
+    if (count != have) return fail(STB_ERR_ARG, "stb_medium_table: the table holds %zu doubles, not %zu", have, count);
+    CU(cudaMemcpy(host_out, src, have * sizeof(double), cudaMemcpyDeviceToHost));
+    return STB_OK;
+}
+
+int stb_medium_destroy(stb_medium_t m)
+{
+    if (!m) return STB_OK;
+    cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->counter);
+    delete m;
+    return STB_OK;
+}
+
+int stb_trace_rk(stb_medium_t m, const stb_rk_t *rk, void *stream)
+{
+    if (!m || !rk) return fail(STB_ERR_ARG, "stb_trace_rk: NULL argument");
+    if (rk->struct_size != sizeof(stb_rk_t))
+        return fail(STB_ERR_ARG, "stb_trace_rk: struct_size %zu != %zu (header/library mismatch)", rk->struct_size, sizeof(stb_rk_t));
+    if (rk->nrays < 0) return fail(STB_ERR_ARG, "stb_trace_rk: nrays < 0");
+    if (rk->nrays == 0) return STB_OK;
+    if (!rk->x0 || !rk->y0 || !rk->px0 || !rk->py0) return fail(STB_ERR_ARG, "stb_trace_rk: launch state pointers must not be NULL");
+    if (!(rk->rtol >= 0.0) || !(rk->atol_r > 0.0) || !(rk->atol_p > 0.0))
+        return fail(STB_ERR_ARG, "stb_trace_rk: need rtol >= 0 and atol_r, atol_p > 0");
+    if (!(rk->h0 > 0.0) || !(rk->hmin > 0.0) || !(rk->hmax >= rk->h0) || !(rk->h0 >= rk->hmin))
+        return fail(STB_ERR_ARG, "stb_trace_rk: need 0 < hmin <= h0 <= hmax");
+    if (!(rk->tau_max > 0.0)) return fail(STB_ERR_ARG, "stb_trace_rk: tau_max must be positive");
+    if (rk->traj && rk->L < 1) return fail(STB_ERR_ARG, "stb_trace_rk: traj needs L >= 1");
+    if (rk->traj_aux && !rk->traj) return fail(STB_ERR_ARG, "stb_trace_rk: traj_aux needs traj");
+    if (rk->hist) {
+        if (!m->alpha) return fail(STB_ERR_ARG, "stb_trace_rk: the deposition histogram needs a medium with an absorption table");
+        if (rk->nbins < 1 || rk->nbins > 28000) return fail(STB_ERR_ARG, "stb_trace_rk: nbins must be in [1, 28000]");
+        if (!(rk->r_lcs > 0.0) || !(rk->rho_max > 0.0)) return fail(STB_ERR_ARG, "stb_trace_rk: r_lcs and rho_max must be positive");
+    }
+    int dev = -1;
+    CU(cudaGetDevice(&dev));
+    if (dev != m->device)
+        return fail(STB_ERR_ARG, "stb_trace_rk: the medium lives on device %d but the current device is %d", m->device, dev);
+
+    stbrk::Params p{};
+    p.m = m->m;
+    p.nrays = rk->nrays;
+    p.x0 = rk->x0; p.y0 = rk->y0; p.px0 = rk->px0; p.py0 = rk->py0;
+    p.xscale = rk->xscale; p.yscale = rk->yscale; p.amp = rk->amp;
+    p.rtol = rk->rtol; p.atol_r = rk->atol_r; p.atol_p = rk->atol_p;
+    p.h0 = rk->h0; p.hmin = rk->hmin; p.hmax = rk->hmax; p.tau_max = rk->tau_max;
+    p.max_steps = rk->max_steps;
+    p.end_state = rk->end_state; p.tau_end = rk->tau_end; p.phi_end = rk->phi_end; p.sig_end = rk->sig_end;
+    p.n2_min = rk->n2_min; p.ham_end = rk->ham_end;
+    p.nacc = rk->nacc; p.nrej = rk->nrej; p.status = rk->status;
+    p.traj = rk->traj; p.traj_aux = rk->traj_aux; p.L = rk->L;
+    p.hist = rk->hist; p.nbins = rk->nbins;
+    p.xaxis = rk->xaxis; p.yaxis = rk->yaxis;
+    if (rk->hist) {
+        p.r_rlcs = 1.0 / rk->r_lcs;
+        p.bins_per_rho = (double)rk->nbins / rk->rho_max;
+    }
+    p.counter = m->counter + (m->launch_seq++ % kCounters);
+
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool xmode = m->mode == STB_RK_MODE_X;
+    const bool absorb = m->alpha != nullptr;
+    switch (m->interp) {
+        case STB_RK_INTERP_BILINEAR: return launch_mode<0>(p, xmode, absorb, m->num_sms, s);
+        case STB_RK_INTERP_CATMULL_ROM: return launch_mode<1>(p, xmode, absorb, m->num_sms, s);
+        default: return launch_mode<2>(p, xmode, absorb, m->num_sms, s);
+    }
+}
+
+}  // extern "C"

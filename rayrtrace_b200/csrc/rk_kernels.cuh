@@ -1,0 +1,451 @@
+// rk_kernels.cuh -- beyond-reference physics mode: adaptive Dormand-Prince 5(4)
+// integration of the Hamiltonian ray equations
+//
+//     dr/dtau = p,   dp/dtau = (1/2) grad N^2(r),   p = k / k0,  H = |p|^2 - N^2(r) = 0
+//
+// through a density table X = n/n_c interpolated by a cubic B-spline (C2, prefiltered on the device),
+// Catmull-Rom patches (C1, local) or bilinearly,
+// with the cold-plasma O-mode (N^2 = 1 - X) or X-mode (N^2 = 1 - X(1-X)/(1-X-Y^2), toroidal
+// Y = Y0 R0/(R0+x)) dispersion and its analytic derivatives fused into the field evaluation,
+// an optional absorption table integrated as optical depth, and absorbed power deposited into
+// flux-coordinate bins.  The reference has NO counterpart of this (its only integrator is the
+// fixed-step loop of sidtracemodule.c:36-48, which trace_kernels.cuh reproduces bit for bit):
+// this file is an extension and is never reported as parity.  Its checker is oracle/rk_oracle.c
+// (same operation order, explicit fma -> bit-identical) plus analytic solutions in the tests.
+//
+// One thread per ray; rays take different numbers of (accepted + rejected) steps, so warps are
+// persistent and refill idle lanes from a global queue after a vote, like trace_kernels.cuh.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace stbrk {
+
+constexpr int kBlock = 128;
+constexpr unsigned FULL = 0xffffffffu;
+
+enum Status : int { LEFT_DOMAIN = 0, TAU_MAX = 1, MAX_STEPS = 2, STEP_UNDERFLOW = 3, START_OUTSIDE = 4 };
+
+struct Medium {
+    const double *X;       // n/n_c at the reference frequency: [ny][nx] nodes, or [ny+2][nx+2] B-spline coefficients
+    const double *alpha;   // power absorption coefficient per unit tau (same layout), or nullptr
+    int nx, ny;
+    double xorg, yorg;     // physical position of node (0, 0)
+    double rdx, rdy;       // 1/dx, 1/dy
+    double Y0R0, R0;       // X-mode: Y(x) = Y0R0 / (R0 + x)
+};
+
+struct Params {
+    Medium m;
+    long long nrays;
+    const double *x0, *y0, *px0, *py0;   // launch position (cm) and refractive-index vector
+    const double *xscale, *yscale;       // per-ray multipliers of X and Y (sweeps) or nullptr
+    const double *amp;                   // launch amplitude or nullptr (-> 1)
+    double rtol, atol_r, atol_p;
+    double h0, hmin, hmax, tau_max;
+    int max_steps;
+    // outputs (any may be nullptr)
+    double *end_state;                   // [4][nrays]
+    double *tau_end, *phi_end, *sig_end, *n2_min, *ham_end;
+    int *nacc, *nrej, *status;
+    double *traj;                        // [ray][L][4] accepted states (state 0 = launch)
+    double *traj_aux;                    // [ray][L][2] (tau, sigma)
+    long long L;
+    double *hist;
+    int nbins;
+    double xaxis, yaxis, r_rlcs, bins_per_rho;
+    unsigned long long *counter;
+};
+
+// Dormand-Prince 5(4) tableau.  cA[i][j] = a_{i+2, j+1}; row 5 is also the 5th-order weights
+// (FSAL); cE = b - b* (error estimate).
+__constant__ double cA[6][6] = {
+    {1.0 / 5.0, 0, 0, 0, 0, 0},
+    {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0},
+    {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0, 0},
+    {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0, 0},
+    {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, 0},
+    {35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0},
+};
+__constant__ double cE[7] = {71.0 / 57600.0, 0.0, -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0, 22.0 / 525.0,
+                             -1.0 / 40.0};
+
+// Catmull-Rom weights and their derivatives at fractional position t (Horner, explicit fma)
+__device__ __forceinline__ void cr_weights(double t, double (&w)[4], double (&d)[4])
+{
+    const double tt = t * t;
+    w[0] = t * fma(t, fma(t, -0.5, 1.0), -0.5);
+    w[1] = fma(tt, fma(t, 1.5, -2.5), 1.0);
+    w[2] = t * fma(t, fma(t, -1.5, 2.0), 0.5);
+    w[3] = tt * fma(t, 0.5, -0.5);
+    d[0] = fma(t, fma(t, -1.5, 2.0), -0.5);
+    d[1] = t * fma(t, 4.5, -5.0);
+    d[2] = fma(t, fma(t, -4.5, 4.0), 0.5);
+    d[3] = t * fma(t, 1.5, -1.0);
+}
+
+// uniform cubic B-spline weights: a C2 interpolant once the table is prefiltered
+__device__ __forceinline__ void bs_weights(double t, double (&w)[4], double (&d)[4])
+{
+    const double tt = t * t, a = 1.0 - t;
+    w[0] = ((a * a) * a) * (1.0 / 6.0);
+    w[1] = fma(tt, fma(t, 0.5, -1.0), 2.0 / 3.0);
+    w[2] = fma(t, fma(t, fma(t, -0.5, 0.5), 0.5), 1.0 / 6.0);
+    w[3] = (tt * t) * (1.0 / 6.0);
+    d[0] = -0.5 * (a * a);
+    d[1] = t * fma(t, 1.5, -2.0);
+    d[2] = fma(t, fma(t, -1.5, 1.0), 0.5);
+    d[3] = 0.5 * tt;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Table value and grid-unit gradient at grid position (u, v).  INTERP 0: bilinear, 1: Catmull-Rom on
+// the node table, 2: cubic B-spline on the prefiltered (ny+2) x (nx+2) coefficient table (element
+// (0, 0) is coefficient (-1, -1), so the 4 x 4 stencil never leaves it).
+// The cell index is clamped to the table, the fractional part is not: outside the table the
+// edge cell's polynomial is continued (stage points of the last step may fall there).
+template <int INTERP, bool GRAD>
+__device__ __forceinline__ void table_eval(const double *__restrict__ T, int nx, int ny, int iu, int iv, double t,
+                                           double s, double &f, double &fu, double &fv)
+{
+    if (INTERP == 0) {
+        const double *r0 = T + (long long)iv * nx + iu;
+        const double a = __ldg(r0), b = __ldg(r0 + 1), c = __ldg(r0 + nx), d = __ldg(r0 + nx + 1);
+        const double ba = b - a, dc = d - c;
+        const double lo = fma(t, ba, a), hi = fma(t, dc, c);
+        f = fma(s, hi - lo, lo);
+        if (GRAD) {
+            fu = fma(s, dc - ba, ba);
+            fv = hi - lo;
+        }
+    } else {
+        double wx[4], dx[4], wy[4], dy[4];
+        if (INTERP == 1) {
+            cr_weights(t, wx, dx);
+            cr_weights(s, wy, dy);
+        } else {
+            bs_weights(t, wx, dx);
+            bs_weights(s, wy, dy);
+        }
+        double rv[4], rd[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double v0, v1, v2, v3;
+            if (INTERP == 1) {
+                const double *row = T + (long long)clampi(iv - 1 + j, 0, ny - 1) * nx;
+                v0 = __ldg(row + clampi(iu - 1, 0, nx - 1)); v1 = __ldg(row + iu); v2 = __ldg(row + iu + 1);
+                v3 = __ldg(row + clampi(iu + 2, 0, nx - 1));
+            } else {
+                const double *row = T + (long long)(iv + j) * (nx + 2) + iu;
+                v0 = __ldg(row); v1 = __ldg(row + 1); v2 = __ldg(row + 2); v3 = __ldg(row + 3);
+            }
+            rv[j] = fma(wx[3], v3, fma(wx[2], v2, fma(wx[1], v1, wx[0] * v0)));
+            if (GRAD) rd[j] = fma(dx[3], v3, fma(dx[2], v2, fma(dx[1], v1, dx[0] * v0)));
+        }
+        f = fma(wy[3], rv[3], fma(wy[2], rv[2], fma(wy[1], rv[1], wy[0] * rv[0])));
+        if (GRAD) {
+            fu = fma(wy[3], rd[3], fma(wy[2], rd[2], fma(wy[1], rd[1], wy[0] * rd[0])));
+            fv = fma(dy[3], rv[3], fma(dy[2], rv[2], fma(dy[1], rv[1], dy[0] * rv[0])));
+        }
+    }
+}
+
+// Right-hand side at (x, y): force = grad(N^2)/2, absorption coefficient, N^2.
+template <int INTERP, bool XMODE, bool ABSORB>
+__device__ __forceinline__ void rk_eval(const Medium &m, double xs, double ys, double x, double y, double &fx,
+                                        double &fy, double &al, double &n2)
+{
+    const double u = (x - m.xorg) * m.rdx, v = (y - m.yorg) * m.rdy;
+    const int iu = (int)fmin(fmax(u, 0.0), (double)(m.nx - 2));
+    const int iv = (int)fmin(fmax(v, 0.0), (double)(m.ny - 2));
+    const double t = u - (double)iu, s = v - (double)iv;
+    double F, Fu, Fv;
+    table_eval<INTERP, true>(m.X, m.nx, m.ny, iu, iv, t, s, F, Fu, Fv);
+    const double Xv = xs * F;
+    const double Xx = xs * (Fu * m.rdx), Xy = xs * (Fv * m.rdy);   // physical gradient of X
+    if (!XMODE) {
+        n2 = 1.0 - Xv;
+        fx = -0.5 * Xx;
+        fy = -0.5 * Xy;
+    } else {
+        const double rR = 1.0 / (m.R0 + x);
+        const double Yv = ys * (m.Y0R0 * rR);
+        const double Y2 = Yv * Yv;
+        const double D = (1.0 - Xv) - Y2;
+        const double rD = 1.0 / D;
+        const double g = Xv * (1.0 - Xv);
+        n2 = 1.0 - g * rD;
+        const double rD2 = rD * rD;
+        const double dX = -(fma(1.0 - 2.0 * Xv, D, g)) * rD2;    // dN^2/dX
+        const double dY2 = -g * rD2;                             // dN^2/d(Y^2)
+        const double Y2x = -2.0 * (Y2 * rR);                     // d(Y^2)/dx
+        fx = 0.5 * fma(dY2, Y2x, dX * Xx);
+        fy = 0.5 * (dX * Xy);
+    }
+    if (ABSORB) {
+        double a, au, av;
+        table_eval<INTERP, false>(m.alpha, m.nx, m.ny, iu, iv, t, s, a, au, av);
+        al = a;
+    } else {
+        al = 0.0;
+    }
+}
+
+// err^(1/5) from IEEE operations only (sqrt + Newton), so that the CPU checker reproduces the
+// step-size sequence bit for bit.  The argument is clamped to the range the controller uses.
+__device__ __forceinline__ double root5(double err)
+{
+    const double e = fmin(fmax(err, 1e-4), 2e3);
+    double g = sqrt(sqrt(e));
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const double g2 = g * g;
+        g = (4.0 * g + e / (g2 * g2)) * 0.2;
+    }
+    return g;
+}
+
+__device__ __forceinline__ void rk_hist_add(double *sh, int b, double w)
+{
+    const unsigned peers = __match_any_sync(__activemask(), b);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    double sum = 0.0;
+    for (unsigned mm = peers; mm; mm &= mm - 1) sum += __shfl_sync(peers, w, __ffs(mm) - 1);
+    if (lane == leader && b >= 0) atomicAdd(&sh[b], sum);
+}
+
+template <int INTERP, bool XMODE, bool ABSORB>
+__global__ void __launch_bounds__(kBlock) rk_kernel(const Params p)
+{
+    extern __shared__ double sh_hist[];
+    const bool hist = ABSORB && p.hist != nullptr;
+    if (hist) {
+        for (int b = threadIdx.x; b < p.nbins; b += kBlock) sh_hist[b] = 0.0;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const Medium &m = p.m;
+    const double umax = (double)(m.nx - 1), vmax = (double)(m.ny - 1);
+
+    long long ray = -1;
+    double x = 0, y = 0, px = 0, py = 0, phi = 0, sig = 0, tau = 0, h = 0, xs = 1, ys = 1, amp2 = 1, P = 1, n2min = 0;
+    double f1x = 0, f1y = 0, a1 = 0;
+    int nacc = 0, nrej = 0, status = 0;
+    bool after_reject = false;
+
+    auto inside = [&](double xx, double yy) -> bool {
+        const double u = (xx - m.xorg) * m.rdx, v = (yy - m.yorg) * m.rdy;
+        return u >= 0.0 && u < umax && v >= 0.0 && v < vmax;
+    };
+    auto store_state = [&]() {
+        if (p.traj && nacc < p.L) {
+            double *tp = p.traj + (ray * p.L + nacc) * 4;
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(tp), "d"(x), "d"(y), "d"(px), "d"(py) : "memory");
+            if (p.traj_aux) {
+                double *ap = p.traj_aux + (ray * p.L + nacc) * 2;
+                asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(ap), "d"(tau), "d"(sig) : "memory");
+            }
+        }
+    };
+    auto retire = [&]() {
+        const long long n = p.nrays;
+        if (p.end_state) {
+            p.end_state[ray] = x; p.end_state[n + ray] = y; p.end_state[2 * n + ray] = px; p.end_state[3 * n + ray] = py;
+        }
+        if (p.tau_end) p.tau_end[ray] = tau;
+        if (p.phi_end) p.phi_end[ray] = phi;
+        if (p.sig_end) p.sig_end[ray] = sig;
+        if (p.n2_min) p.n2_min[ray] = n2min;
+        if (p.ham_end) {
+            double fx, fy, al, n2;
+            rk_eval<INTERP, XMODE, false>(m, xs, ys, x, y, fx, fy, al, n2);
+            p.ham_end[ray] = fma(px, px, py * py) - n2;
+        }
+        if (p.nacc) p.nacc[ray] = nacc;
+        if (p.nrej) p.nrej[ray] = nrej;
+        if (p.status) p.status[ray] = status;
+    };
+    // returns false when the ray is over before its first step
+    auto launch = [&](long long r) -> bool {
+        ray = r;
+        x = p.x0[r]; y = p.y0[r]; px = p.px0[r]; py = p.py0[r];
+        xs = p.xscale ? p.xscale[r] : 1.0;
+        ys = p.yscale ? p.yscale[r] : 1.0;
+        const double a = p.amp ? p.amp[r] : 1.0;
+        amp2 = a * a; P = amp2;
+        phi = 0.0; sig = 0.0; tau = 0.0; h = p.h0;
+        nacc = 0; nrej = 0; after_reject = false;
+        double n2;
+        rk_eval<INTERP, XMODE, ABSORB>(m, xs, ys, x, y, f1x, f1y, a1, n2);
+        n2min = n2;
+        store_state();
+        if (!inside(x, y)) { status = START_OUTSIDE; retire(); return false; }
+        if (p.max_steps <= 0) { status = MAX_STEPS; retire(); return false; }
+        return true;
+    };
+
+    // one step attempt; false when the ray ended (outputs written)
+    auto attempt = [&]() -> bool {
+        double hh = h;
+        bool last = false;
+        if (tau + hh >= p.tau_max) { hh = p.tau_max - tau; last = true; }
+        // stage derivatives: position <- kp (the stage's p), momentum <- kf, sigma <- ka
+        double kpx[7], kpy[7], kfx[7], kfy[7], ka[7];
+        kpx[0] = px; kpy[0] = py; kfx[0] = f1x; kfy[0] = f1y; ka[0] = a1;
+        double xn = x, yn = y, pxn = px, pyn = py, n2n = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double sx = cA[i][0] * kpx[0], sy = cA[i][0] * kpy[0], sfx = cA[i][0] * kfx[0], sfy = cA[i][0] * kfy[0];
+#pragma unroll
+            for (int j = 1; j <= i; ++j) {
+                sx = fma(cA[i][j], kpx[j], sx);
+                sy = fma(cA[i][j], kpy[j], sy);
+                sfx = fma(cA[i][j], kfx[j], sfx);
+                sfy = fma(cA[i][j], kfy[j], sfy);
+            }
+            xn = fma(hh, sx, x); yn = fma(hh, sy, y);
+            pxn = fma(hh, sfx, px); pyn = fma(hh, sfy, py);
+            kpx[i + 1] = pxn; kpy[i + 1] = pyn;
+            rk_eval<INTERP, XMODE, ABSORB>(m, xs, ys, xn, yn, kfx[i + 1], kfy[i + 1], ka[i + 1], n2n);
+        }
+        // (xn, yn, pxn, pyn) is the 5th-order solution (row 5 = b); stage 7 is its derivative
+        double ex = cE[0] * kpx[0], ey = cE[0] * kpy[0], efx = cE[0] * kfx[0], efy = cE[0] * kfy[0];
+#pragma unroll
+        for (int j = 1; j < 7; ++j) {
+            ex = fma(cE[j], kpx[j], ex);
+            ey = fma(cE[j], kpy[j], ey);
+            efx = fma(cE[j], kfx[j], efx);
+            efy = fma(cE[j], kfy[j], efy);
+        }
+        const double ah = fabs(hh);
+        const double scx = fma(p.rtol, fmax(fabs(x), fabs(xn)), p.atol_r);
+        const double scy = fma(p.rtol, fmax(fabs(y), fabs(yn)), p.atol_r);
+        const double scpx = fma(p.rtol, fmax(fabs(px), fabs(pxn)), p.atol_p);
+        const double scpy = fma(p.rtol, fmax(fabs(py), fabs(pyn)), p.atol_p);
+        const double e0 = ah * fabs(ex) / scx, e1 = ah * fabs(ey) / scy;
+        const double e2 = ah * fabs(efx) / scpx, e3 = ah * fabs(efy) / scpy;
+        const double esum = (e0 + e1) + (e2 + e3);   // NaN in any component must not be hidden by fmax
+        const double err = (esum == esum) ? fmax(fmax(e0, e1), fmax(e2, e3)) : esum;
+        if (!(err <= 1.0)) {   // rejected (NaN included)
+            ++nrej;
+            const double fac = (err == err) ? fmax(0.2, 0.9 / root5(err)) : 0.2;
+            h = hh * fac;
+            after_reject = true;
+            if (!(h >= p.hmin)) { status = STEP_UNDERFLOW; retire(); return false; }
+            return true;
+        }
+        // accepted: quadratures with the 5th-order weights
+        double sphi = cA[5][0] * fma(kpx[0], kpx[0], kpy[0] * kpy[0]);
+        double ssig = cA[5][0] * ka[0];
+#pragma unroll
+        for (int j = 1; j < 6; ++j) {
+            sphi = fma(cA[5][j], fma(kpx[j], kpx[j], kpy[j] * kpy[j]), sphi);
+            ssig = fma(cA[5][j], ka[j], ssig);
+        }
+        const double xm = 0.5 * (x + xn), ym = 0.5 * (y + yn);
+        x = xn; y = yn; px = pxn; py = pyn;
+        phi = fma(hh, sphi, phi);
+        sig = fma(hh, ssig, sig);
+        tau = last ? p.tau_max : tau + hh;
+        f1x = kfx[6]; f1y = kfy[6]; a1 = ka[6];
+        n2min = fmin(n2min, n2n);
+        ++nacc;
+        store_state();
+        if (hist) {
+            const double Pn = amp2 * exp(-sig);
+            const double dP = P - Pn;
+            P = Pn;
+            const double rx = xm - p.xaxis, ry = ym - p.yaxis;
+            const double rho = sqrt(fma(rx, rx, ry * ry)) * p.r_rlcs;
+            const double fb = rho * p.bins_per_rho;
+            const int b = (fb < (double)p.nbins) ? (int)fb : -1;
+            rk_hist_add(sh_hist, b, dP);
+        }
+        // no growth right after a rejection: keeps the controller from bouncing at the kinks of the
+        // interpolant (cell edges)
+        const double fmx = after_reject ? 1.0 : 5.0;
+        const double fac = (err > 0.0) ? fmin(fmx, 0.9 / root5(err)) : fmx;
+        after_reject = false;
+        h = fmin(hh * fac, p.hmax);
+        if (!inside(x, y)) { status = LEFT_DOMAIN; retire(); return false; }
+        if (last) { status = TAU_MAX; retire(); return false; }
+        if (nacc >= p.max_steps) { status = MAX_STEPS; retire(); return false; }
+        return true;
+    };
+
+    // persistent warps: vote, refill idle lanes with one aggregated claim, step
+    bool active = false, more = true;
+    for (;;) {
+        unsigned act = __ballot_sync(FULL, active);
+        if (more && act != FULL) {
+            const unsigned idle = ~act;
+            const int leader = __ffs(idle) - 1;
+            const int want = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(p.counter, (unsigned long long)want);
+            base = __shfl_sync(FULL, base, leader);
+            if (!active) {
+                const long long r = (long long)base + __popc(idle & ((1u << lane) - 1u));
+                if (r < p.nrays) active = launch(r);
+            }
+            more = (long long)(base + want) < p.nrays;
+            act = __ballot_sync(FULL, active);
+            if (act == 0 && more) continue;   // every claimed ray ended at launch: claim again
+        }
+        if (act == 0) break;
+        if (active) {
+#pragma unroll 1
+            for (int s = 0; s < 2; ++s) {
+                if (!attempt()) { active = false; break; }
+            }
+        }
+    }
+
+    if (hist) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < p.nbins; b += kBlock) {
+            const double v = sh_hist[b];
+            if (v != 0.0) atomicAdd(&p.hist[b], v);
+        }
+    }
+}
+
+// Cubic B-spline prefilter along one axis: for every line, solve c[i-1] + 4 c[i] + c[i+1] = 6 f[i]
+// with the natural end conditions c[0] = f[0], c[n-1] = f[n-1] and extend by c[-1] = 2c[0] - c[1],
+// c[n] = 2c[n-1] - c[n-2].  One thread per line (Thomas algorithm; R[i] are the data-independent
+// pivots' reciprocals, R[1] = 1/4, R[i] = 1/(4 - R[i-1])).  Output index 0 holds c[-1].
+__global__ void bspline_prefilter_kernel(const double *__restrict__ in, long long in_line, long long in_elem,
+                                         double *__restrict__ out, long long out_line, long long out_elem,
+                                         const double *__restrict__ R, int n, int nlines)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlines) return;
+    const double *f = in + (long long)l * in_line;
+    double *c = out + (long long)l * out_line + out_elem;   // c[i] at c + i*out_elem, i = -1 .. n
+    const double f0 = f[0], fl = f[(long long)(n - 1) * in_elem];
+    c[0] = f0;
+    c[(long long)(n - 1) * out_elem] = fl;
+    if (n > 2) {
+        double dprev = 0.0;
+        for (int i = 1; i <= n - 2; ++i) {
+            double rhs = 6.0 * f[(long long)i * in_elem];
+            if (i == 1) rhs -= f0;
+            if (i == n - 2) rhs -= fl;
+            const double d = (rhs - dprev) * R[i];
+            c[(long long)i * out_elem] = d;
+            dprev = d;
+        }
+        double cnext = c[(long long)(n - 2) * out_elem];
+        for (int i = n - 3; i >= 1; --i) {
+            const double ci = c[(long long)i * out_elem] - R[i] * cnext;
+            c[(long long)i * out_elem] = ci;
+            cnext = ci;
+        }
+    }
+    c[-out_elem] = 2.0 * c[0] - c[out_elem];
+    c[(long long)n * out_elem] = 2.0 * c[(long long)(n - 1) * out_elem] - c[(long long)(n - 2) * out_elem];
+}
+
+}  // namespace stbrk

@@ -89,6 +89,14 @@ struct stb_field_s {
     HostBuf pin;
 };
 
+// shared with rk_b200.cu (same library, not part of the public headers)
+extern "C" int stb_internal_fail(int code, const char *msg)
+{
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+extern "C" void stb_internal_count_launch(void) { g_launches++; }
+
 extern "C" {
 
 int stb_abi_version(void) { return STB_ABI_VERSION; }

@@ -1,0 +1,229 @@
+"""Beyond-reference physics mode: adaptive Runge-Kutta ray tracing through an
+interpolated medium with O/X-mode cold-plasma dispersion, absorption and a deposition profile.
+
+EXTENSION, NOT PARITY: the reference's only integrator is the fixed-step loop of
+sidtracemodule.c:36-48 (``rayrtrace_b200.sidtrace``).  This module is the host side of
+include/sidtrace_b200_rk.h; it is validated against analytic solutions, a SciPy integration and a
+bit-level CPU checker in tests/test_rk_*.py, never against reference output.
+
+    med = Medium.from_density(n, x, y, freq=136.268e9)          # X = n / n_c  (den.py:335-348)
+    res = trace_rk(med, x0, y0, px0, py0)                       # CUDA tensors in, CUDA tensors out
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import StbMediumDesc, StbRk, lib
+from .nfield import critical_den
+
+LEFT_DOMAIN, TAU_MAX, MAX_STEPS, STEP_UNDERFLOW, START_OUTSIDE = range(5)
+INTERP = {"bilinear": 0, "catmull-rom": 1, "bspline": 2}
+
+ELECTRON_CYCLOTRON_HZ_PER_T = 2.799249e10
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Medium:
+    """Device-resident medium: the n/n_c node table (and an optional absorption table) on a
+    uniform grid, plus the dispersion mode.  ``x``/``y`` are the node coordinates (cm, uniform).
+    interp: 'bspline' (C2 natural cubic spline, prefiltered on the device -- the smooth default),
+    'catmull-rom' (C1 local bicubic patches) or 'bilinear'."""
+
+    def __init__(self, X, x, y, *, alpha=None, mode: str = "O", Y0: float = 0.0, R0: float = 55.0,
+                 interp: str = "bspline"):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        x = np.asarray(x, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        if X.ndim != 2 or X.shape != (y.size, x.size):
+            raise ValueError(f"X must have shape (len(y), len(x)) = ({y.size}, {x.size}), got {X.shape}")
+        if x.size < 2 or y.size < 2:
+            raise ValueError("the table needs at least 2 x 2 nodes")
+        dx, dy = (x[-1] - x[0]) / (x.size - 1), (y[-1] - y[0]) / (y.size - 1)
+        if not (dx > 0 and dy > 0):
+            raise ValueError("x and y must be increasing")
+        if np.max(np.abs(np.diff(x) - dx)) > 1e-9 * dx or np.max(np.abs(np.diff(y) - dy)) > 1e-9 * dy:
+            raise ValueError("the adaptive-RK medium needs a uniform grid")
+        if mode not in ("O", "X"):
+            raise ValueError("mode must be 'O' or 'X'")
+        if interp not in INTERP:
+            raise ValueError(f"interp must be one of {sorted(INTERP)}")
+        if alpha is not None:
+            alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+            if alpha.shape != X.shape:
+                raise ValueError("alpha must have the shape of X")
+        self.nx, self.ny = int(x.size), int(y.size)
+        self.xorg, self.yorg, self.dx, self.dy = float(x[0]), float(y[0]), float(dx), float(dy)
+        self.mode, self.Y0, self.R0, self.interp = mode, float(Y0), float(R0), interp
+        self.has_alpha = alpha is not None
+        torch = _torch()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        _cabi.check(lib.stb_set_device(self.device.index or 0))
+        d = StbMediumDesc()
+        d.struct_size = ctypes.sizeof(StbMediumDesc)
+        d.nx, d.ny = self.nx, self.ny
+        d.xorg, d.yorg, d.dx, d.dy = self.xorg, self.yorg, self.dx, self.dy
+        d.X = X.ctypes.data
+        d.alpha = alpha.ctypes.data if alpha is not None else None
+        d.on_device = 0
+        d.mode = 1 if mode == "X" else 0
+        d.interp = INTERP[interp]
+        d.Y0, d.R0 = self.Y0, self.R0
+        h = ctypes.c_void_p()
+        _cabi.check(lib.stb_medium_create(ctypes.byref(d), ctypes.byref(h)))
+        self._h = h
+
+    @classmethod
+    def from_density(cls, n, x, y, *, freq: float = 136.268e9, den_unit="cm^-3", alpha=None, mode: str = "O",
+                     btor: float = 2.2, R0: float = 55.0, interp: str = "bspline") -> "Medium":
+        """n in cm^-3 (times ``den_unit``) on nodes -> X = n / n_c(freq) (den.py:335-348); the
+        X mode's Y0 = f_ce(btor) / freq with the rmain/btor defaults of equilibrium.py:289."""
+        X = np.asarray(n, dtype=np.float64) / critical_den(freq, den_unit=den_unit)
+        Y0 = ELECTRON_CYCLOTRON_HZ_PER_T * btor / freq if mode == "X" else 0.0
+        return cls(X, x, y, alpha=alpha, mode=mode, Y0=Y0, R0=R0, interp=interp)
+
+    def table(self, which: str = "X") -> np.ndarray:
+        """The table the kernel reads, copied back: node values, or for the B-spline the
+        (ny+2, nx+2) coefficients the device prefilter produced."""
+        pad = 2 if self.interp == "bspline" else 0
+        out = np.empty((self.ny + pad, self.nx + pad))
+        _cabi.check(lib.stb_medium_table(self._h, 0 if which == "X" else 1, out.ctypes.data, out.size))
+        return out
+
+    def close(self) -> None:
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.stb_medium_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class RkResult:
+    __slots__ = ("end_state", "tau", "phi", "sig", "n2_min", "ham", "nacc", "nrej", "status", "traj", "aux", "hist")
+
+    def __init__(self):
+        for s in self.__slots__:
+            setattr(self, s, None)
+
+
+def trace_rk(med: Medium, x0, y0, px0, py0, *, rtol: float = 1e-9, atol_r: float = 1e-9, atol_p: float = 1e-9,
+             h0: Optional[float] = None, hmin: float = 1e-12, hmax: Optional[float] = None,
+             tau_max: float = math.inf, max_steps: int = 100000, xscale=None, yscale=None, amp=None,
+             diagnostics: bool = True, L: int = 0, aux: bool = False, hist=None, nbins: int = 0,
+             xaxis: float = 0.0, yaxis: float = 0.0, r_lcs: float = 1.0, rho_max: float = 1.0,
+             out: Optional[RkResult] = None, stream=None) -> RkResult:
+    """Trace ``len(x0)`` rays with the adaptive Dormand-Prince 5(4) kernel, one launch.
+
+    x0, y0 (cm) and px0, py0 (= k/k0) are contiguous float64 CUDA tensors; so are the optional
+    per-ray ``xscale`` / ``yscale`` (multipliers of X and Y: density and frequency sweeps) and
+    ``amp``.  ``h0`` defaults to half a cell and ``hmax`` to four cells, which bounds how far the
+    last step can carry a ray past the table edge.  ``L`` > 0 records the first L accepted states
+    per ray ([nrays, L, 4], NaN-filled) and with ``aux`` their (tau, sigma).  ``nbins`` > 0 (or a
+    preallocated ``hist``) accumulates absorbed power per rho bin; needs a medium with ``alpha``.
+    Asynchronous on ``stream`` (default: the current torch stream).
+    """
+    torch = _torch()
+    n = int(x0.shape[0])
+    ins = {"x0": x0, "y0": y0, "px0": px0, "py0": py0}
+    for name, a in (("xscale", xscale), ("yscale", yscale), ("amp", amp)):
+        if a is not None:
+            ins[name] = a
+    for name, a in ins.items():
+        if not isinstance(a, torch.Tensor) or a.dtype != torch.float64 or not a.is_cuda or not a.is_contiguous():
+            raise TypeError(f"{name} must be a contiguous float64 CUDA tensor")
+        if a.ndim != 1 or int(a.shape[0]) != n:
+            raise ValueError(f"{name} must be 1-D of length {n}")
+        if a.device != med.device:
+            raise ValueError(f"{name} lives on {a.device} but the medium on {med.device}")
+    cell = min(med.dx, med.dy)
+    h0 = 0.5 * cell if h0 is None else float(h0)
+    hmax = 4.0 * cell if hmax is None else float(hmax)
+    res = out if out is not None else RkResult()
+    dev = med.device
+
+    def need(name, shape, dtype):
+        cur = getattr(res, name)
+        if cur is None:
+            cur = torch.empty(shape, dtype=dtype, device=dev)
+            setattr(res, name, cur)
+        return cur
+
+    need("end_state", (4, n), torch.float64)
+    need("nacc", (n,), torch.int32)
+    need("nrej", (n,), torch.int32)
+    need("status", (n,), torch.int32)
+    if diagnostics:
+        for name in ("tau", "phi", "sig", "n2_min", "ham"):
+            need(name, (n,), torch.float64)
+    if L:
+        if res.traj is None:
+            res.traj = torch.full((n, L, 4), math.nan, dtype=torch.float64, device=dev)
+        if aux and res.aux is None:
+            res.aux = torch.full((n, L, 2), math.nan, dtype=torch.float64, device=dev)
+    if hist is None and nbins:
+        hist = torch.zeros(nbins, dtype=torch.float64, device=dev)
+    if hist is not None:
+        if not med.has_alpha:
+            raise ValueError("the deposition histogram needs a medium with an absorption table (alpha)")
+        nbins = int(hist.shape[0])
+        res.hist = hist
+
+    k = StbRk()
+    k.struct_size = ctypes.sizeof(StbRk)
+    k.flags = 0
+    k.nrays = n
+    k.x0, k.y0, k.px0, k.py0 = x0.data_ptr(), y0.data_ptr(), px0.data_ptr(), py0.data_ptr()
+    k.xscale = xscale.data_ptr() if xscale is not None else None
+    k.yscale = yscale.data_ptr() if yscale is not None else None
+    k.amp = amp.data_ptr() if amp is not None else None
+    k.rtol, k.atol_r, k.atol_p = float(rtol), float(atol_r), float(atol_p)
+    k.h0, k.hmin, k.hmax, k.tau_max = h0, float(hmin), hmax, float(tau_max)
+    k.max_steps = int(max_steps)
+    k.end_state = res.end_state.data_ptr()
+    k.nacc, k.nrej, k.status = res.nacc.data_ptr(), res.nrej.data_ptr(), res.status.data_ptr()
+    if diagnostics:
+        k.tau_end, k.phi_end, k.sig_end = res.tau.data_ptr(), res.phi.data_ptr(), res.sig.data_ptr()
+        k.n2_min, k.ham_end = res.n2_min.data_ptr(), res.ham.data_ptr()
+    if L:
+        k.traj = res.traj.data_ptr()
+        k.traj_aux = res.aux.data_ptr() if res.aux is not None else None
+        k.L = int(L)
+    if hist is not None:
+        k.hist, k.nbins = hist.data_ptr(), nbins
+        k.xaxis, k.yaxis, k.r_lcs, k.rho_max = float(xaxis), float(yaxis), float(r_lcs), float(rho_max)
+    if n == 0:
+        return res
+    _cabi.check(lib.stb_set_device(dev.index or 0))
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    sptr = ctypes.c_void_p(stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
+    _cabi.check(lib.stb_trace_rk(med._h, ctypes.byref(k), sptr))
+    return res
+
+
+def refractive_index(med: Medium, x0, y0, xscale=None, yscale=None):
+    """N at the given points (CUDA tensors), evaluated by the kernel itself: a zero-step launch
+    reports N^2 at the launch point.  Scale unit launch directions by it so that H = 0 (the role
+    of ray.py:62-64 for the interpolated medium)."""
+    torch = _torch()
+    z = torch.zeros_like(x0)
+    res = trace_rk(med, x0, y0, z, z, xscale=xscale, yscale=yscale, max_steps=0)
+    return torch.sqrt(torch.clamp(res.n2_min, min=0.0))

@@ -11,12 +11,16 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "sidtrace_b200.h")
+HEADER_RK = os.path.join(ROOT, "include", "sidtrace_b200_rk.h")   # adaptive-RK extension
 
 
 def _declared():
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(stb_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for h in (HEADER, HEADER_RK):
+        src = open(h).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(stb_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_declares_expected_symbols():
@@ -33,19 +37,23 @@ def test_library_exports_every_declared_symbol():
     assert _cabi.lib.stb_last_error() is not None
 
 
-def test_batch_struct_layout_matches_c(tmp_path):
-    from rayrtrace_b200._cabi import StbBatch
-    fields = [f[0] for f in StbBatch._fields_]
+@pytest.mark.parametrize("cname, pyname", [("stb_batch_t", "StbBatch"), ("stb_launch_t", "StbLaunch"),
+                                           ("stb_beam_t", "StbBeam"), ("stb_medium_desc_t", "StbMediumDesc"),
+                                           ("stb_rk_t", "StbRk")])
+def test_struct_layout_matches_c(tmp_path, cname, pyname):
+    from rayrtrace_b200 import _cabi
+    cls = getattr(_cabi, pyname)
+    fields = [f[0] for f in cls._fields_]
     prog = tmp_path / "layout.c"
-    body = "\n".join(f'    printf("{f} %zu\\n", offsetof(stb_batch_t, {f}));' for f in fields)
-    prog.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{HEADER}"\n'
-                    f'int main(void) {{\n    printf("sizeof %zu\\n", sizeof(stb_batch_t));\n{body}\n    return 0;\n}}\n')
+    body = "\n".join(f'    printf("{f} %zu\\n", offsetof({cname}, {f}));' for f in fields)
+    prog.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{HEADER_RK}"\n'
+                    f'int main(void) {{\n    printf("sizeof %zu\\n", sizeof({cname}));\n{body}\n    return 0;\n}}\n')
     exe = tmp_path / "layout"
     subprocess.check_call([os.environ.get("CC", "gcc"), str(prog), "-o", str(exe)])
     out = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
-    assert int(out["sizeof"]) == ctypes.sizeof(StbBatch)
+    assert int(out["sizeof"]) == ctypes.sizeof(cls)
     for f in fields:
-        assert int(out[f]) == getattr(StbBatch, f).offset, f
+        assert int(out[f]) == getattr(cls, f).offset, f
 
 
 def test_missing_library_fails_loudly(tmp_path):

@@ -1,0 +1,229 @@
+"""The adaptive-RK CUDA kernel (include/sidtrace_b200_rk.h) against its CPU checker, through the C ABI.
+
+EXTENSION, PARITY UNPINNED: no reference output exists for this mode; the checker
+(oracle/rk_oracle.c) is pinned by closed forms and SciPy in tests/test_rk_oracle.py.  Bar here:
+BIT-EXACT on everything a ray carries (states, step counts, statuses, tau / phi / sigma, the
+accepted-state trajectories, the prefiltered spline table); the deposition histogram within 1e-9
+relative L1 (FP64 atomics and exp() differ in the last bits).  Plus closed-form and conservation
+properties at sizes the CPU checker does not reach.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+INTERPS = ["bilinear", "catmull-rom", "bspline"]
+
+
+@pytest.fixture(scope="module")
+def ph():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from rayrtrace_b200 import physics
+    return physics
+
+
+@pytest.fixture(scope="module")
+def rk():
+    from oracle import rk
+    rk.lib()
+    return rk
+
+
+def _tables(n=201, peak=0.6, seed=0, with_alpha=False):
+    xs = np.linspace(-10, 10, n)
+    XX, YY = np.meshgrid(xs, xs)
+    rng = np.random.default_rng(seed)
+    X = peak * np.exp(-((XX - 0.4) ** 2 + 1.3 * YY ** 2) / 14.0) * (1 + 0.05 * np.sin(1.7 * XX) * np.cos(1.1 * YY))
+    X += 1e-3 * rng.random(X.shape)          # table noise: exercises every stencil value
+    alpha = 0.02 * np.exp(-(XX ** 2 + YY ** 2) / 9.0) if with_alpha else None
+    return xs, X, alpha
+
+
+def _beam(n, seed=1):
+    rng = np.random.default_rng(seed)
+    x0 = rng.uniform(-6, 6, n)
+    y0 = np.full(n, -9.5) + rng.uniform(0, 0.3, n)
+    th = rng.uniform(-0.5, 0.5, n)
+    return x0, y0, np.sin(th), np.cos(th)
+
+
+def _gpu(ph, med, x0, y0, px, py, **kw):
+    import torch
+    dev = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    for k in ("xscale", "yscale", "amp"):
+        if k in kw:
+            kw[k] = dev(kw[k])
+    res = ph.trace_rk(med, dev(x0), dev(y0), dev(px), dev(py), **kw)
+    torch.cuda.synchronize()
+    return res
+
+
+def _same(res, want, keys=("end_state", "tau", "phi", "sig", "n2_min", "ham", "nacc", "nrej", "status")):
+    for k in keys:
+        got = getattr(res, k).cpu().numpy()
+        assert got.tobytes() == want[k].tobytes(), (k, np.flatnonzero((got != want[k]).reshape(-1))[:5])
+
+
+INTERP_ID = {"bilinear": 0, "catmull-rom": 1, "bspline": 2}
+
+
+def test_device_prefilter_is_bitwise_the_checkers(ph, rk):
+    xs, X, alpha = _tables(151, with_alpha=True)
+    X = X[:, :131].copy()                       # nx != ny
+    alpha = alpha[:, :131].copy()
+    med = ph.Medium(X, xs[:131], xs, alpha=alpha)
+    assert med.table("X").tobytes() == rk.prefilter(X).tobytes()
+    assert med.table("alpha").tobytes() == rk.prefilter(alpha).tobytes()
+    raw = ph.Medium(X, xs[:131], xs, interp="catmull-rom")
+    assert raw.table("X").tobytes() == X.tobytes()
+    for shape in ((2, 2), (2, 5), (3, 2)):
+        G = np.random.default_rng(4).random(shape)
+        t = ph.Medium(G, np.arange(shape[1]) * 1.0, np.arange(shape[0]) * 1.0).table()
+        assert t.tobytes() == rk.prefilter(G).tobytes()
+
+
+@pytest.mark.parametrize("interp", INTERPS)
+@pytest.mark.parametrize("mode", ["O", "X"])
+@pytest.mark.parametrize("absorb", [False, True])
+def test_every_variant_bitwise(ph, rk, interp, mode, absorb):
+    xs, X, alpha = _tables(with_alpha=absorb, peak=0.6 if mode == "O" else 0.3)
+    d = xs[1] - xs[0]
+    n = 3000
+    x0, y0, px, py = _beam(n)
+    rng = np.random.default_rng(7)
+    xscale = rng.uniform(0.2, 2.2, n)           # under-dense ... reflected
+    yscale = rng.uniform(0.8, 1.2, n)
+    amp = rng.uniform(0.5, 1.5, n)
+    kw = dict(rtol=1e-8, atol_r=1e-8, atol_p=1e-8, h0=0.05, hmin=1e-10, hmax=0.4, max_steps=5000)
+    med = ph.Medium(X, xs, xs, alpha=alpha, mode=mode, Y0=0.45, R0=55.0, interp=interp)
+    res = _gpu(ph, med, x0, y0, px, py, xscale=xscale, yscale=yscale, amp=amp, L=48, aux=True,
+               nbins=32 if absorb else 0, r_lcs=7.85, rho_max=1.5, **kw)
+    om = rk.Medium(X, med.xorg, med.yorg, med.dx, med.dy, alpha=alpha, mode=mode, Y0=0.45, R0=55.0, interp=INTERP_ID[interp])
+    want = rk.trace(om, x0, y0, px, py, xscale=xscale, yscale=yscale, amp=amp, L=48, aux=True,
+                    nbins=32 if absorb else 0, r_lcs=7.85, rho_max=1.5, threads=8, **kw)
+    _same(res, want)
+    assert res.traj.cpu().numpy().tobytes() == want["traj"].tobytes()
+    assert res.aux.cpu().numpy().tobytes() == want["aux"].tobytes()
+    assert len(set(want["status"].tolist())) >= 1 and want["nacc"].min() > 3
+    if absorb:
+        got = res.hist.cpu().numpy()
+        assert np.abs(got - want["hist"]).sum() <= 1e-9 * np.abs(want["hist"]).sum()
+        assert want["hist"].sum() > 0
+
+
+def test_sweep_with_cutoffs_resonances_and_caps_bitwise(ph, rk):
+    """2*10^5 rays, X mode, density scale 0..6 and field scale 0.5..1.5: under-dense, reflected at
+    the right-hand cutoff, collapsing on the upper-hybrid layer, capped; every status occurs."""
+    xs, X, _ = _tables(301, peak=0.5, seed=3)
+    d = xs[1] - xs[0]
+    n = 200_000
+    x0, y0, px, py = _beam(n, seed=5)
+    rng = np.random.default_rng(11)
+    xscale = rng.uniform(0.0, 6.0, n)
+    yscale = rng.uniform(0.5, 1.5, n)
+    # a few rays start inside the dense core (beyond the upper-hybrid layer) or outside the table
+    x0[:2000] = rng.uniform(-1, 1, 2000); y0[:2000] = rng.uniform(-1, 1, 2000); xscale[:2000] = rng.uniform(2.0, 3.4, 2000)
+    x0[2000:2100] = 10.5
+    kw = dict(rtol=1e-7, atol_r=1e-7, atol_p=1e-7, h0=0.05, hmin=1e-9, hmax=0.4, max_steps=400, tau_max=60.0)
+    med = ph.Medium(X, xs, xs, mode="X", Y0=0.45, R0=55.0)
+    res = _gpu(ph, med, x0, y0, px, py, xscale=xscale, yscale=yscale, **kw)
+    om = rk.Medium(X, med.xorg, med.yorg, med.dx, med.dy, mode="X", Y0=0.45, R0=55.0)
+    want = rk.trace(om, x0, y0, px, py, xscale=xscale, yscale=yscale, threads=16, **kw)
+    _same(res, want)
+    assert set(want["status"].tolist()) >= {rk.LEFT_DOMAIN, rk.MAX_STEPS, rk.STEP_UNDERFLOW, rk.START_OUTSIDE}
+
+
+def test_whole_warps_ending_at_launch_and_tiny_batches(ph, rk):
+    xs, X, _ = _tables(101)
+    d = xs[1] - xs[0]
+    med = ph.Medium(X, xs, xs)
+    om = rk.Medium(X, med.xorg, med.yorg, med.dx, med.dy)
+    d = med.dx
+    for n in (1, 31, 33, 1000):
+        x0 = np.full(n, 12.0); x0[n // 2:] = -3.0          # first half starts outside the table
+        y0 = np.full(n, -9.0)
+        res = _gpu(ph, med, x0, y0, np.zeros(n), np.ones(n), hmax=0.4)
+        want = rk.trace(om, x0, y0, np.zeros(n), np.ones(n), hmax=0.4, h0=0.5 * d)
+        _same(res, want)
+    # every ray ends at launch (the refill loop must keep claiming)
+    n = 5000
+    res = _gpu(ph, med, np.full(n, 12.0), np.zeros(n), np.ones(n), np.zeros(n))
+    assert (res.status.cpu().numpy() == ph.START_OUTSIDE).all() and (res.nacc.cpu().numpy() == 0).all()
+    import torch
+    e = torch.empty(0, dtype=torch.float64, device="cuda")
+    assert ph.trace_rk(med, e, e, e, e).end_state.shape == (4, 0)
+
+
+def test_refractive_index_helper_and_on_shell_launch(ph, rk):
+    import torch
+    xs, X, _ = _tables(201, peak=0.3)
+    med = ph.Medium(X, xs, xs, mode="X", Y0=0.45, R0=55.0)
+    om = rk.Medium(X, med.xorg, med.yorg, med.dx, med.dy, mode="X", Y0=0.45, R0=55.0)
+    x0 = torch.linspace(-5, 5, 257, dtype=torch.float64, device="cuda")
+    y0 = torch.full_like(x0, -9.5)
+    N = ph.refractive_index(med, x0, y0)
+    want = np.sqrt([om.eval(float(x), -9.5)[3] for x in x0.cpu()])
+    np.testing.assert_array_equal(N.cpu().numpy(), want)
+    res = ph.trace_rk(med, x0, y0, torch.zeros_like(x0), N, rtol=1e-10, atol_r=1e-10, atol_p=1e-10)
+    assert float(res.ham.abs().max()) < 2e-6 and bool((res.status == ph.LEFT_DOMAIN).all())   # noisy table
+
+
+def test_million_ray_properties(ph):
+    """Sizes the CPU checker does not reach: conservation, deposited power, closed-form ramp."""
+    import torch
+    n = 1_000_000
+    xs = np.linspace(-10, 10, 401)
+    XX, YY = np.meshgrid(xs, xs)
+    X = 0.7 * np.exp(-(XX ** 2 + YY ** 2) / 16.0)
+    alpha = np.full_like(X, 0.02)
+    med = ph.Medium(X, xs, xs, alpha=alpha)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x0 = (torch.rand(n, generator=g, dtype=torch.float64, device="cuda") - 0.5) * 12
+    y0 = torch.full_like(x0, -9.5)
+    th = (torch.rand(n, generator=g, dtype=torch.float64, device="cuda") - 0.5) * 0.8
+    N = ph.refractive_index(med, x0, y0)
+    amp = 0.5 + torch.rand(n, generator=g, dtype=torch.float64, device="cuda")
+    res = ph.trace_rk(med, x0, y0, N * torch.sin(th), N * torch.cos(th), amp=amp, rtol=1e-9, atol_r=1e-9, atol_p=1e-9,
+                      nbins=64, r_lcs=7.85, rho_max=2.5)
+    torch.cuda.synchronize()
+    assert bool((res.status == ph.LEFT_DOMAIN).all())
+    assert float(res.ham.abs().max()) < 1e-6
+    torch.testing.assert_close(res.sig, 0.02 * res.tau, rtol=1e-12, atol=0)
+    absorbed = (amp * amp * (1 - torch.exp(-res.sig))).sum()
+    assert float(res.hist.sum()) == pytest.approx(float(absorbed), rel=1e-10)
+
+    # linear ramp: exact parabola for every ray
+    Xr = np.tile(0.4 + 0.04 * xs, (401, 1))
+    ramp = ph.Medium(Xr, xs, xs, interp="catmull-rom")
+    x0 = torch.full((n,), -9.5, dtype=torch.float64, device="cuda")
+    y0 = (torch.rand(n, generator=g, dtype=torch.float64, device="cuda") - 0.5) * 10
+    th = (torch.rand(n, generator=g, dtype=torch.float64, device="cuda") - 0.5) * 1.0
+    N0 = np.sqrt(1 - (0.4 + 0.04 * -9.5))
+    px, py = N0 * torch.cos(th), N0 * torch.sin(th)
+    T = 6.0
+    res = ph.trace_rk(ramp, x0, y0, px, py, tau_max=T, hmax=0.5)
+    torch.cuda.synchronize()
+    assert bool((res.status == ph.TAU_MAX).all())
+    want = torch.stack([x0 + px * T - 0.25 * 0.04 * T * T, y0 + py * T, px - 0.5 * 0.04 * T, py])
+    torch.testing.assert_close(res.end_state, want, rtol=0, atol=5e-12)
+
+
+def test_argument_errors(ph):
+    import torch
+    from rayrtrace_b200._cabi import SidtraceError
+    xs, X, _ = _tables(51)
+    med = ph.Medium(X, xs, xs)
+    z = torch.zeros(4, dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError):
+        ph.trace_rk(med, z, z, z, z, nbins=8)                       # histogram without alpha
+    with pytest.raises(SidtraceError):
+        ph.trace_rk(med, z, z, z, z, atol_r=0.0)
+    with pytest.raises(SidtraceError):
+        ph.trace_rk(med, z, z, z, z, h0=1.0, hmax=0.5)
+    with pytest.raises(TypeError):
+        ph.trace_rk(med, z.cpu(), z, z, z)
+    with pytest.raises(ValueError):
+        ph.Medium(X, xs ** 3, xs)                                   # non-uniform grid
+    with pytest.raises(SidtraceError):
+        ph.Medium(X, xs, xs, mode="X", R0=0.0)
