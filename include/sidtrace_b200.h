@@ -83,7 +83,7 @@ int stb_check(int nx, int ny, int i, int j, const double *a, double *out);
                                          32-ray tile at a time) */
 #define STB_F_STATIC        (1u << 5)  /* force the static one-thread-per-ray grid.  With neither flag the
                                          library picks: static for tiled trajectories (lock-step rows), lane
-                                         refill otherwise -- refill costs <= 20 % on a clean beam but is 3-5x
+                                         refill otherwise -- refill costs <= 15 % on a clean beam but is 3-5x
                                          faster when a few rays run 10-100x longer than the rest (trapped
                                          rays; profiles/r01/kernel_sweep_trapped.txt) */
 #define STB_F_TRAJ_HOST    (1u << 3)  /* traj is a HOST pointer (copied back after the launch) */

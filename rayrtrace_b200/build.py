@@ -49,10 +49,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    # SIDTRACE_B200_NVCC_EXTRA / SIDTRACE_B200_LIB: tuning sweeps build variants (-DSTB_...=...) side by side
+    extra = os.environ.get("SIDTRACE_B200_NVCC_EXTRA", "").split()
+    out = os.environ.get("SIDTRACE_B200_LIB", LIB) if extra else LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
     # the image exports CC=/opt/gcc/bin/gcc; nvcc picks its host compiler from PATH
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -152,13 +152,21 @@ __device__ __forceinline__ void table_eval(const double *__restrict__ T, int nx,
 }
 
 // Right-hand side at (x, y): force = grad(N^2)/2, absorption coefficient, N^2.
+#ifndef STB_RK_EVAL_INLINE
+#define STB_RK_EVAL_INLINE __forceinline__
+#endif
+#ifndef STB_RK_MINB
+#define STB_RK_MINB 3   // <= 170 registers, 3 CTAs per SM: measured best (profiles/r01/rk_occupancy_sweep.txt)
+#endif
 template <int INTERP, bool XMODE, bool ABSORB>
-__device__ __forceinline__ void rk_eval(const Medium &m, double xs, double ys, double x, double y, double &fx,
+__device__ STB_RK_EVAL_INLINE void rk_eval(const Medium &m, double xs, double ys, double x, double y, double &fx,
                                         double &fy, double &al, double &n2)
 {
     const double u = (x - m.xorg) * m.rdx, v = (y - m.yorg) * m.rdy;
-    const int iu = (int)fmin(fmax(u, 0.0), (double)(m.nx - 2));
-    const int iv = (int)fmin(fmax(v, 0.0), (double)(m.ny - 2));
+    // cell index = clamp(floor(u), 0, nx-2): the saturating conversion (NaN -> 0) and integer min/max
+    // give what (int)fmin(fmax(u, 0), nx-2) gives, without the NaN-aware double min/max sequences
+    const int iu = max(0, min(__double2int_rd(u), m.nx - 2));
+    const int iv = max(0, min(__double2int_rd(v), m.ny - 2));
     const double t = u - (double)iu, s = v - (double)iv;
     double F, Fu, Fv;
     table_eval<INTERP, true>(m.X, m.nx, m.ny, iu, iv, t, s, F, Fu, Fv);
@@ -217,7 +225,7 @@ __device__ __forceinline__ void rk_hist_add(double *sh, int b, double w)
 }
 
 template <int INTERP, bool XMODE, bool ABSORB>
-__global__ void __launch_bounds__(kBlock) rk_kernel(const Params p)
+__global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
 {
     extern __shared__ double sh_hist[];
     const bool hist = ABSORB && p.hist != nullptr;
