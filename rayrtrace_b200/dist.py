@@ -106,3 +106,24 @@ def trace_sharded(field, launch, *, L, st, dx, dy, amp=None, nbins=0, hist_kw=No
     if gather:
         gathered = (gather_sharded(res.nsteps, n_global, mode), gather_sharded(res.end_state, n_global, mode, dim=1))
     return res, hist, gathered
+
+
+def trace_rk_sharded(medium, launch, *, amp=None, xscale=None, yscale=None, gather=False, mode="interleave", **kw):
+    """The adaptive-RK extension (physics.trace_rk) over this rank's shard: ``launch`` = global host
+    arrays (x0, y0, px0, py0), identical on every rank; ``medium`` is this rank's replica.  The
+    deposition histogram is all-reduced; with ``gather`` the per-ray (status, end_state) come back
+    in global ray order.  Returns (RkResult of the local shard, global hist or None, gathered or None)."""
+    from . import physics
+    per_ray = [a for a in (amp, xscale, yscale)]
+    d_in, _, n_global = stage_shard(launch, mode=mode)
+    rank, world, _ = env_world()
+    sl = shard_slice(n_global, rank, world, mode)
+    import torch
+    dev = d_in[0].device
+    d_amp, d_xs, d_ys = (None if a is None else torch.from_numpy(np.ascontiguousarray(a[sl])).to(dev) for a in per_ray)
+    res = physics.trace_rk(medium, *d_in, amp=d_amp, xscale=d_xs, yscale=d_ys, **kw)
+    hist = allreduce_hist(res.hist) if res.hist is not None else None
+    gathered = None
+    if gather:
+        gathered = (gather_sharded(res.status, n_global, mode), gather_sharded(res.end_state, n_global, mode, dim=1))
+    return res, hist, gathered
