@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 #include <new>
 #include <vector>
 
@@ -43,7 +44,7 @@ struct stb_medium_s {
     int mode = 0, interp = 2;
     double *X = nullptr, *alpha = nullptr;
     unsigned long long *counter = nullptr;   // kCounters queue heads used round-robin
-    unsigned launch_seq = 0;
+    std::atomic<unsigned> launch_seq{0};   // host threads may launch concurrently on their own streams
 };
 
 namespace {
@@ -219,7 +220,7 @@ int stb_trace_rk(stb_medium_t m, const stb_rk_t *rk, void *stream)
         p.r_rlcs = 1.0 / rk->r_lcs;
         p.bins_per_rho = (double)rk->nbins / rk->rho_max;
     }
-    p.counter = m->counter + (m->launch_seq++ % kCounters);
+    p.counter = m->counter + (m->launch_seq.fetch_add(1) % kCounters);
 
     cudaStream_t s = (cudaStream_t)stream;
     const bool xmode = m->mode == STB_RK_MODE_X;

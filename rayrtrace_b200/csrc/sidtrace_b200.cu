@@ -82,7 +82,7 @@ struct stb_field_s {
     double2 *cells = nullptr;             // interleaved {ax, ay}, (ny-1)*(nx-1)
     unsigned long long *counter = nullptr;   // kCounters queue heads, used round-robin so that
                                              // launches in flight on different streams never share one
-    unsigned launch_seq = 0;
+    std::atomic<unsigned> launch_seq{0};   // host threads may launch concurrently on their own streams
     int num_sms = 0;
     std::mutex mu;                        // guards the workspaces below
     DevBuf ws_in, ws_out, ws_traj, ws_hist;
@@ -369,7 +369,7 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     // a ray advances about one smallest cell per step (SURVEY 3.3 i): the annulus test pays off when a
     // bin spans several steps, otherwise most steps would fail it and take the exact path anyway
     p.hist_annulus = b->hist && p.hist_dr >= 4.0 * std::fmin(std::fabs(b->dx), std::fabs(b->dy));
-    p.counter = f->counter + (f->launch_seq++ % kCounters);
+    p.counter = f->counter + (f->launch_seq.fetch_add(1) % kCounters);
     p.cross_axis = b->cross_axis; p.cross_val = b->cross_val;
     p.x0p = b->x0_phys; p.y0p = b->y0_phys;
     p.cross_count = b->cross_count; p.cross_index = b->cross_index; p.cross_flags = b->cross_flags;

@@ -44,6 +44,43 @@ def test_legacy_trace_kat_bitwise(st, kat, name):
     assert not x[n + 1:].any()          # entries beyond state n stay untouched (sidtracemodule.c:36-48)
 
 
+def test_legacy_calls_follow_their_field_arrays_and_turning_rays(st, oracle_mod):
+    """The per-ray surface caches the field upload per (ax, ay) pair: new arrays, arrays rescaled in
+    place, and single-element edits followed by invalidate() must all be seen; rays that wander and
+    turn several times stay bit-exact."""
+    rng = np.random.default_rng(21)
+    nx, ny, L = 97, 81, 3000
+
+    def both(ax, ay, launch):
+        got = [np.zeros(L) for _ in range(4)]
+        want = [np.zeros(L) for _ in range(4)]
+        for g, w, v in zip(got, want, launch):
+            g[0] = w[0] = v
+        n = st.trace(*got, 0.35, 1.0, 0.8, nx, ny, ax, ay)
+        m = oracle_mod.trace(*want, 0.35, 1.0, 0.8, nx, ny, ax, ay)
+        assert n == m
+        for g, w in zip(got, want):
+            assert g.tobytes() == w.tobytes()
+        return n
+
+    ax, ay = random_field(rng, nx, ny, scale=0.05)
+    steps = []
+    for _ in range(40):       # strong field: most rays wander and turn several times
+        x0, y0, kx0, ky0 = (float(v[0]) for v in random_launch(rng, 1, nx, ny, kmag=0.6))
+        steps.append(both(ax, ay, (x0, y0, kx0, ky0)))
+    assert max(steps) > 300
+    launch = (40.3, 11.2, 0.1, 0.9)
+    n1 = both(ax, ay, launch)
+    bx, by = random_field(rng, nx, ny, scale=0.05)           # new arrays
+    n2 = both(bx, by, launch)
+    ax *= 1.7; ay *= 0.6                                      # in place, caught by the content sample
+    n3 = both(ax, ay, launch)
+    ax[int(launch[1]), int(launch[0])] += 0.5                 # one cell, in place: needs invalidate()
+    st.invalidate()
+    n4 = both(ax, ay, launch)
+    assert len({n1, n2, n3, n4}) > 1
+
+
 def test_legacy_check_and_device_layout(st):
     a = np.arange(24.0).reshape(4, 6)
     assert st.check(6, 4, 2, 3, a) == a[2, 3]
