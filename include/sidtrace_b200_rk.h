@@ -17,7 +17,7 @@
  * solutions and an independent SciPy integration (tests/test_rk_*.py).
  *
  * Same conventions as sidtrace_b200.h: 0 = success, negative = error, stb_last_error().
- * All array pointers are DEVICE pointers.
+ * Array pointers are DEVICE pointers unless STB_RK_F_HOST_IO is set.
  */
 #ifndef SIDTRACE_B200_RK_H
 #define SIDTRACE_B200_RK_H
@@ -66,9 +66,12 @@ int stb_medium_destroy(stb_medium_t m);
  * the [ny+2][nx+2] spline coefficients for STB_RK_INTERP_BSPLINE (count must match). */
 int stb_medium_table(stb_medium_t m, int which, double *host_out, size_t count);
 
+#define STB_RK_F_HOST_IO (1u << 0)   /* every array pointer of stb_rk_t is a HOST pointer: the call stages them
+                                        through HBM and returns when the results are back (synchronous) */
+
 typedef struct stb_rk_s {
     size_t   struct_size;
-    uint32_t flags;            /* reserved, 0                                                       */
+    uint32_t flags;            /* STB_RK_F_*                                                        */
     int64_t  nrays;
     const double *x0, *y0;     /* launch position, cm                                               */
     const double *px0, *py0;   /* launch refractive-index vector k/k0 (|p| = N on the ray H = 0)    */
@@ -98,7 +101,8 @@ typedef struct stb_rk_s {
     double   r_lcs, rho_max;   /* rho = |r - axis| / r_lcs, bins cover [0, rho_max)                 */
 } stb_rk_t;
 
-/* Traces all rays of `rk` through `m` on `stream` (a cudaStream_t, may be NULL).  Asynchronous. */
+/* Traces all rays of `rk` through `m` on `stream` (a cudaStream_t, may be NULL).  Asynchronous unless
+ * STB_RK_F_HOST_IO is set. */
 int stb_trace_rk(stb_medium_t m, const stb_rk_t *rk, void *stream);
 
 #ifdef __cplusplus

@@ -75,6 +75,8 @@ int launch_mode(const stbrk::Params &p, bool xmode, bool absorb, int num_sms, cu
     return absorb ? launch_rk<INTERP, false, true>(p, num_sms, s) : launch_rk<INTERP, false, false>(p, num_sms, s);
 }
 
+int trace_rk_host_io(stb_medium_t m, const stb_rk_t *rk, cudaStream_t s);
+
 }  // namespace
 
 extern "C" {
@@ -202,6 +204,8 @@ int stb_trace_rk(stb_medium_t m, const stb_rk_t *rk, void *stream)
     if (dev != m->device)
         return fail(STB_ERR_ARG, "stb_trace_rk: the medium lives on device %d but the current device is %d", m->device, dev);
 
+    if (rk->flags & STB_RK_F_HOST_IO) return trace_rk_host_io(m, rk, (cudaStream_t)stream);
+
     stbrk::Params p{};
     p.m = m->m;
     p.nrays = rk->nrays;
@@ -233,3 +237,68 @@ int stb_trace_rk(stb_medium_t m, const stb_rk_t *rk, void *stream)
 }
 
 }  // extern "C"
+
+namespace {
+
+// STB_RK_F_HOST_IO: one device arena for every array of the call, copies in, the ordinary device
+// launch, copies out.  Synchronous; meant for non-CUDA hosts and small batches.
+int trace_rk_host_io(stb_medium_t m, const stb_rk_t *rk, cudaStream_t s)
+{
+    const size_t n = (size_t)rk->nrays;
+    struct Slot { const void *host_in; void *host_out; size_t bytes; size_t off; };
+    std::vector<Slot> slots;
+    size_t total = 0;
+    auto add = [&](const void *in, void *out, size_t bytes) -> size_t {
+        if (!in && !out) return (size_t)-1;
+        const size_t off = total;
+        slots.push_back({in, out, bytes, off});
+        total += (bytes + 255) & ~(size_t)255;
+        return off;
+    };
+    const size_t d8 = sizeof(double), i4 = sizeof(int32_t);
+    const size_t o_x0 = add(rk->x0, nullptr, n * d8), o_y0 = add(rk->y0, nullptr, n * d8);
+    const size_t o_px = add(rk->px0, nullptr, n * d8), o_py = add(rk->py0, nullptr, n * d8);
+    const size_t o_xs = add(rk->xscale, nullptr, n * d8), o_ys = add(rk->yscale, nullptr, n * d8);
+    const size_t o_amp = add(rk->amp, nullptr, n * d8);
+    const size_t o_end = add(nullptr, rk->end_state, 4 * n * d8);
+    const size_t o_tau = add(nullptr, rk->tau_end, n * d8), o_phi = add(nullptr, rk->phi_end, n * d8);
+    const size_t o_sig = add(nullptr, rk->sig_end, n * d8), o_n2 = add(nullptr, rk->n2_min, n * d8);
+    const size_t o_ham = add(nullptr, rk->ham_end, n * d8);
+    const size_t o_nacc = add(nullptr, rk->nacc, n * i4), o_nrej = add(nullptr, rk->nrej, n * i4);
+    const size_t o_stat = add(nullptr, rk->status, n * i4);
+    const size_t L = rk->traj ? (size_t)rk->L : 0;
+    // trajectories and the histogram are read-modify-write for the caller (untouched tail, accumulation)
+    const size_t o_traj = add(rk->traj, rk->traj, n * L * 4 * d8), o_aux = add(rk->traj_aux, rk->traj_aux, n * L * 2 * d8);
+    const size_t o_hist = add(rk->hist, rk->hist, rk->hist ? (size_t)rk->nbins * d8 : 0);
+
+    char *arena = nullptr;
+    CU(cudaMalloc(&arena, total ? total : 256));
+    int rc = STB_OK;
+    cudaError_t e = cudaSuccess;
+    for (const Slot &sl : slots)
+        if (sl.host_in && sl.bytes && (e = cudaMemcpyAsync(arena + sl.off, sl.host_in, sl.bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
+    if (e == cudaSuccess) {
+        stb_rk_t d = *rk;
+        d.flags &= ~STB_RK_F_HOST_IO;
+        auto at = [&](size_t off) -> void * { return off == (size_t)-1 ? nullptr : (void *)(arena + off); };
+        d.x0 = (const double *)at(o_x0); d.y0 = (const double *)at(o_y0);
+        d.px0 = (const double *)at(o_px); d.py0 = (const double *)at(o_py);
+        d.xscale = (const double *)at(o_xs); d.yscale = (const double *)at(o_ys); d.amp = (const double *)at(o_amp);
+        d.end_state = (double *)at(o_end); d.tau_end = (double *)at(o_tau); d.phi_end = (double *)at(o_phi);
+        d.sig_end = (double *)at(o_sig); d.n2_min = (double *)at(o_n2); d.ham_end = (double *)at(o_ham);
+        d.nacc = (int32_t *)at(o_nacc); d.nrej = (int32_t *)at(o_nrej); d.status = (int32_t *)at(o_stat);
+        d.traj = (double *)at(o_traj); d.traj_aux = (double *)at(o_aux); d.hist = (double *)at(o_hist);
+        rc = stb_trace_rk(m, &d, s);
+    }
+    if (e == cudaSuccess && rc == STB_OK)
+        for (const Slot &sl : slots)
+            if (sl.host_out && sl.bytes && (e = cudaMemcpyAsync(sl.host_out, arena + sl.off, sl.bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(arena);
+    if (rc != STB_OK) return rc;
+    if (e != cudaSuccess) return fail(STB_ERR_CUDA, "stb_trace_rk (host I/O): %s", cudaGetErrorString(e));
+    return STB_OK;
+}
+
+}  // namespace
+

@@ -227,3 +227,19 @@ def test_argument_errors(ph):
         ph.Medium(X, xs ** 3, xs)                                   # non-uniform grid
     with pytest.raises(SidtraceError):
         ph.Medium(X, xs, xs, mode="X", R0=0.0)
+
+
+def test_plain_c_caller_with_host_pointers(ph, tmp_path):
+    """tests/c/rk_abi.c: no Python, no torch -- STB_RK_F_HOST_IO, closed-form checks."""
+    import os
+    import subprocess
+    from rayrtrace_b200 import _cabi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "rk_abi"
+    lib = _cabi.LIB_PATH
+    subprocess.check_call([os.environ.get("CC", "gcc"), "-O1", "-std=c11", os.path.join(root, "tests", "c", "rk_abi.c"),
+                           lib, "-lm", "-Wl,-rpath," + os.path.dirname(lib), "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "MISMATCH" not in r.stdout and "all ok" in r.stdout
+
