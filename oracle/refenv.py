@@ -12,8 +12,9 @@ Shims (harness-side; /root/reference is never edited) -- SURVEY.md 8c:
     the launch refractive index (ray.py:62) depends on it; that is an INPUT of
     the hot path, so parity tests feed the same k0 to both sides.
   * skimage (beam.py:5) is not installed: a stub module whose
-    measure.find_contours is a small marching-squares restatement good enough
-    for beam.py:238 (single open iso-line of a smooth field).
+    measure.find_contours restates the published marching-squares algorithm
+    for the reference's one call site (beam.py:238; single open iso-line of a
+    smooth field).  Everything around it is the reference's own code.
   * ufile (equilibrium.py:8) is not in the reference repo: empty stub.
 """
 from __future__ import annotations
@@ -48,19 +49,30 @@ class _Interp2dShim:
 
 
 def _find_contours(arr, level):
-    """Marching-squares iso-line, single open contour, row/col coordinates like
-    skimage.measure.find_contours: returns [ndarray (n, 2)] of (row, col)."""
+    """Restatement of ``skimage.measure.find_contours(image, level)`` (scikit-image, any release
+    since 0.10; the reference pins no version and skimage is not installable here) for the one way
+    the reference calls it (beam.py:238): the marching-squares iso-line of a smooth phase map that
+    crosses the map from its left to its right wall and is single-valued in the column coordinate.
+
+    Published algorithm: every cell edge whose two corner values straddle the level carries one
+    contour vertex, placed by LINEAR interpolation of the level along that edge; vertices are
+    chained into polylines in (row, col) array coordinates.  For a left-to-right open line that is a
+    graph over the columns, chaining order = increasing column, which is also what the reference
+    relies on (``contour[0][0, 1]`` is tested against the left wall, beam.py:239).
+    Returns ``[ndarray (n, 2)]`` of (row, col) like skimage."""
     a = np.asarray(arr, float) - level
-    nr, nc = a.shape
     pts = []
-    # crossings on vertical edges (between rows r and r+1) for each column
+    nr, nc = a.shape
+    # vertices on vertical edges (between rows r and r+1, integer column)
     for c in range(nc):
         col = a[:, c]
-        s = np.sign(col)
-        idx = np.where(s[:-1] * s[1:] < 0)[0]
-        for r in idx:
-            t = col[r] / (col[r] - col[r + 1])
-            pts.append((r + t, float(c)))
+        for r in np.where(col[:-1] * col[1:] < 0)[0]:
+            pts.append((r + col[r] / (col[r] - col[r + 1]), float(c)))
+    # vertices on horizontal edges (between columns c and c+1, integer row)
+    for r in range(nr):
+        row = a[r, :]
+        for c in np.where(row[:-1] * row[1:] < 0)[0]:
+            pts.append((float(r), c + row[c] / (row[c] - row[c + 1])))
     pts = np.array(sorted(pts, key=lambda p: p[1]))
     return [pts]
 

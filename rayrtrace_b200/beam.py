@@ -5,11 +5,17 @@ beam.py:340-342 replaced by ONE batched launch (``trace_rays``).
 SURVEY 8 f-2 / f-3 ("next" rows): everything here is O(rays) host work around the
 O(rays x steps) GPU trace.  What differs from the reference, on purpose:
 
-* The wavefront (beam.py:209-248) is found by solving ``phase(x, y) = ph0`` per column with
-  Newton's method on the analytic Gaussian-beam phase instead of running
-  ``skimage.measure.find_contours`` on a 1000 x 1000 phase map (skimage is not a dependency);
-  agreement is at the 1e-6 cm level, not bitwise ("parity unpinned" for this step: the real
-  skimage is not available to compare with).
+* The wavefront (beam.py:209-248).  The default ``Beam.front_method = "contour"`` follows the
+  reference: the marching-squares iso-line of a 1000 x 1000 phase map
+  (``skimage.measure.find_contours`` in the reference; skimage is not a dependency, so its
+  published algorithm -- one vertex per straddled cell edge, linear interpolation -- is restated
+  in ``_iso_line``) and a cubic interpolant through its ~1 200 vertices.  Only the ~6 000 map nodes
+  next to the front are evaluated (``_iso_line_banded``): same vertices bit for bit, 3 ms instead
+  of 0.1-0.2 s.  ``"newton"`` solves ``phase(x, y) = ph0`` per column on the analytic phase
+  instead: the exact iso-phase line, 1e-6 cm away from the contour one -- but the contour's
+  cell-periodic interpolation error tilts the launch normals by ~1e-4 rad and the interferometer
+  phases by ~1e-3 rad, so parity with the reference needs the contour front.  The fixtures in
+  tests/golden come from the reference's own finder.
 * Rays live in HBM (``self.bundle``); ``self._rays`` materialises reference-shaped ``Ray``
   objects on demand.
 """
@@ -29,6 +35,7 @@ class Beam:
     _dist = 3        # beam.py:25  distance from the focus where rays start
     _ampbnd = 0.001  # beam.py:26  relative amplitude bounding the launch area
     _gouy = 1        # beam.py:27  Gouy phase switch
+    front_method = "contour"  # the reference's marching-squares finder (beam.py:225-247); or "newton"
 
     def __init__(self, x0=0, y0=0, kx0=0, ky0=1, freq=136.268e9, waist=0.35, focus=-1,
                  n_field=None, freq_unit="Hz", length_unit="cm"):
@@ -155,23 +162,118 @@ class Beam:
         dph = 2 * np.pi * n / lw + np.pi * xx ** 2 * (y_r ** 2 - yy ** 2) / (q ** 2 * lw) - y_r / q / 2 * Beam._gouy
         return ph, dph
 
-    def _wavefront(self, dist=0.003, ampbnd=0.001, n=1.):
-        """Interpolant x -> y (beam coordinates) of the iso-phase line through (0, dist), sampled
-        on ``_nfront`` columns out to the ``ampbnd`` amplitude level (beam.py:209-248)."""
+    @staticmethod
+    def _iso_line(a):
+        """Marching-squares vertices of the zero level of ``a`` as (row, col), ordered by column:
+        one vertex on every cell edge whose end values straddle zero, placed by linear
+        interpolation (the published algorithm behind skimage.measure.find_contours, beam.py:238;
+        for a front that is a graph over the columns, chaining order = column order)."""
+        r, c = np.nonzero(a[:-1, :] * a[1:, :] < 0)              # vertical edges
+        t = a[r, c] / (a[r, c] - a[r + 1, c])
+        rows, cols = [r + t], [c.astype(float)]
+        r, c = np.nonzero(a[:, :-1] * a[:, 1:] < 0)              # horizontal edges
+        t = a[r, c] / (a[r, c] - a[r, c + 1])
+        rows.append(r.astype(float)); cols.append(c + t)
+        rows, cols = np.concatenate(rows), np.concatenate(cols)
+        order = np.argsort(cols, kind="stable")
+        return rows[order], cols[order]
+
+    def _iso_line_banded(self, x, y, n, ph0, y_guess):
+        """The vertices ``_iso_line`` finds on the full ``len(y) x len(x)`` phase map, from phase
+        values in a narrow band of rows around the front only (the map is 10^6 nodes, the front
+        touches ~3 000 of them).  The phase grows monotonically along y, so every column has
+        exactly one straddled vertical edge, and a horizontal edge (row r, columns c..c+1) is
+        straddled exactly when r lies between the two columns' crossing rows.  Node values come
+        from the same elementwise formula, so the vertices are bit-identical to the full map's.
+        Returns None when the front is not inside the rows for every column (caller widens)."""
+        ny, nx = len(y), len(x)
+        dy = (y[-1] - y[0]) / (ny - 1)
+        r0 = np.floor((y_guess - y[0]) / dy).astype(np.int64)          # row just below the front, +-1
+        if r0.min() < 2 or r0.max() > ny - 4:
+            return None
+        k = np.arange(-2, 4)                                            # 6 rows per column
+        rr = r0[None, :] + k[:, None]
+        cc = np.broadcast_to(np.arange(nx), rr.shape)
+        a = self._field(x[cc], y[rr], n=n, outfmt="dict")["phase"] - ph0
+        sgn = a[:-1] * a[1:] < 0
+        if not np.all(sgn.sum(axis=0) == 1):
+            return None
+        j = np.argmax(sgn, axis=0)
+        c = np.arange(nx)
+        rv = rr[j, c]                                                   # crossing between rows rv and rv+1
+        t = a[j, c] / (a[j, c] - a[j + 1, c])
+        rows, cols = [rv + t], [c.astype(float)]
+        # horizontal edges between columns c and c+1: rows in (min(rv), max(rv)] of the pair
+        lo, hi = np.minimum(rv[:-1], rv[1:]), np.maximum(rv[:-1], rv[1:])
+        span = int((hi - lo).max())
+        if span > 0:
+            kk = np.arange(1, span + 1)
+            rh = lo[None, :] + kk[:, None]
+            ok = rh <= hi[None, :]
+            ch = np.broadcast_to(np.arange(nx - 1), rh.shape)
+            rh_c = np.minimum(rh, ny - 1)
+            al = self._field(x[ch], y[rh_c], n=n, outfmt="dict")["phase"] - ph0
+            ar = self._field(x[ch + 1], y[rh_c], n=n, outfmt="dict")["phase"] - ph0
+            ok &= al * ar < 0
+            rows.append(rh[ok].astype(float)); cols.append(ch[ok] + al[ok] / (al[ok] - ar[ok]))
+        rows, cols = np.concatenate(rows), np.concatenate(cols)
+        order = np.argsort(cols, kind="stable")
+        return rows[order], cols[order]
+
+    def _wavefront_contour(self, dist, ampbnd, n, banded=True):
+        """The reference's finder, step for step (beam.py:209-247).  ``banded=False`` evaluates the
+        full 1000 x 1000 phase map like the reference does; the default evaluates only the rows
+        the front touches and returns the same vertices bit for bit."""
         w0, lw = self.waist, self.wave_len
         y_r = self.rayleigh_len(n=n)
         xmax = np.sqrt(-w0 ** 2 * (1 + (dist / y_r) ** 2) * np.log(ampbnd))        # beam.py:218
         x = np.linspace(-xmax, xmax, Beam._nfront)
+        r = dist * (1 + (y_r / dist) ** 2)                                          # beam.py:223
         ph0 = 2 * np.pi * dist * n / lw - np.arctan(dist / y_r) / 2 * Beam._gouy   # beam.py:236
-        rc = dist * (1 + (y_r / dist) ** 2)                                         # beam.py:223
-        y = dist - (rc - np.sqrt(np.maximum(rc ** 2 - x ** 2, 0.0)))                # spherical first guess
+        y_guess = self._front_newton(x, dist, n, ph0) if banded else None
+        nl = 1
+        while True:                                                                 # beam.py:228-242
+            y = np.linspace(dist - np.sqrt(r ** 2 - xmax ** 2) - nl * lw, dist + nl * lw, Beam._nfront)
+            ind2x = interp1d(np.arange(len(x)), x)
+            ind2y = interp1d(np.arange(len(y)), y)
+            line = self._iso_line_banded(x, y, n, ph0, y_guess) if banded else None
+            if line is None:
+                xx, yy = np.meshgrid(x, y)
+                line = self._iso_line(self._field(xx, yy, n=n, outfmt="dict")["phase"] - ph0)
+            rows, cols = line
+            if len(cols) and ind2x(cols[0]) <= -xmax:
+                break
+            nl += 1
+            if nl > 64:
+                raise RuntimeError("wavefront finder: the iso-phase line never reaches the left wall")
+        return interp1d(ind2x(cols), ind2y(rows), kind="cubic")                     # beam.py:245
+
+    def _front_newton(self, x, dist, n, ph0):
+        """y(x) with phase(x, y) = ph0, by Newton's method from the spherical first guess."""
+        y_r = self.rayleigh_len(n=n)
+        rc = dist * (1 + (y_r / dist) ** 2)
+        y = dist - (rc - np.sqrt(np.maximum(rc ** 2 - x ** 2, 0.0)))
         for _ in range(50):
             ph, dph = self._phase_and_dy(x, y, n)
             step = (ph - ph0) / dph
             y = y - step
             if np.max(np.abs(step)) < 1e-14 * max(1.0, abs(dist)):
                 break
-        return interp1d(x, y, kind="cubic")
+        return y
+
+    def _wavefront(self, dist=0.003, ampbnd=0.001, n=1.):
+        """Interpolant x -> y (beam coordinates) of the iso-phase line through (0, dist), sampled
+        on ``_nfront`` columns out to the ``ampbnd`` amplitude level (beam.py:209-248)."""
+        if self.front_method == "contour":
+            return self._wavefront_contour(dist, ampbnd, n)
+        if self.front_method != "newton":
+            raise ValueError("Beam.front_method must be 'newton' or 'contour'")
+        w0, lw = self.waist, self.wave_len
+        y_r = self.rayleigh_len(n=n)
+        xmax = np.sqrt(-w0 ** 2 * (1 + (dist / y_r) ** 2) * np.log(ampbnd))        # beam.py:218
+        x = np.linspace(-xmax, xmax, Beam._nfront)
+        ph0 = 2 * np.pi * dist * n / lw - np.arctan(dist / y_r) / 2 * Beam._gouy   # beam.py:236
+        return interp1d(x, self._front_newton(x, dist, n, ph0), kind="cubic")
 
     def wavefront(self, dist=0.02, ampbnd=0.001, n=1.):
         wf = self._wavefront(dist, ampbnd, n=n)
@@ -224,7 +326,7 @@ class Beam:
 
     def launch_conditions_device(self, rnum, wave_front, n_edge):
         """``launch_conditions`` on the GPU (``stb_beam_launch``): everything is a function of the ray
-        index and the 1000-node wavefront tables.  Returns CUDA tensors (x, y, kx, ky, amp); agrees
+        index and the wavefront's node tables.  Returns CUDA tensors (x, y, kx, ky, amp); agrees
         with the host version to ~1e-12 (SciPy evaluates the same spline)."""
         import ctypes
         import torch

@@ -220,25 +220,20 @@ def make_ft2_cross(den, ray):
 def make_beam(den):
     """Reference Beam (beam.py) on the FT-2 profile: launch conditions (Beam.rays, beam.py:278-344),
     field on the receiver line (Beam.field_r, beam.py:347-444) and the interferometer signal
-    (field_result, beam.py:447-472).  The wavefront interpolant is handed to the reference
-    explicitly (its own finder needs skimage): it is the product's Newton-solved iso-phase line,
-    stored here so the test rebuilds the identical interp1d."""
+    (field_result, beam.py:447-472).  All reference code, including its wavefront finder
+    (beam.py:209-276) on top of the restated skimage.measure.find_contours of oracle/refenv.py; the
+    front's nodes are stored so that tests can rebuild the identical interp1d."""
     import beam as refbeam
-    from scipy.interpolate import interp1d
-    from rayrtrace_b200.beam import Beam as PBeam
-    from rayrtrace_b200.nfield import Nfield as PNfield
     nx, n0 = 201, 4e13
     n, x, y = ft2_density(nx, n0)
     nf = den.Nfield(n, x=x, y=y)
     x0 = 2.3
     y0 = -np.sqrt(100 - x0 ** 2)                      # antenna on the r = 10 cm circle (ft2.py:12-16)
-    pb = PBeam(x0=x0, y0=y0, kx0=0, ky0=1)
-    wf = pb.wavefront_r(dist=3, ampbnd=1e-3, n_field=PNfield(n, x=x, y=y))
     rnum = 101
     tx = refbeam.Beam(x0=x0, y0=y0, kx0=0, ky0=1)
     rx = refbeam.Beam(x0=x0, y0=-y0, kx0=0, ky0=-1)
-    lx, ly, lkx, lky, amps, phase, dist = tx.rays(rnum=rnum, wave_front=interp1d(wf.x, wf.y, kind="cubic"),
-                                                  dist=3, ampbnd=1e-3, n_field=nf)
+    wf = tx.wavefront_r(dist=3, ampbnd=1e-3, n_field=nf)          # the reference's own finder
+    lx, ly, lkx, lky, amps, phase, dist = tx.rays(rnum=rnum, dist=3, ampbnd=1e-3, n_field=nf)
     nkept = np.array([len(r.x) for r in tx._rays])
     field, xo, x_max, ph_max, signal, props = refbeam.field_result(tx, rx)
     # analytic pieces at a few points
@@ -255,18 +250,10 @@ def make_beam(den):
 
 def make_ft2_phases():
     """The reference's top-level driver ft2.phases (ft2.py:25-71) end to end: density scan x seven
-    antenna pairs -> interferometer phases.  Harness shim: the reference Beam's wavefront finder
-    (skimage) is replaced at run time by the product's Newton-solved iso-phase line; everything
-    else (Nfield, Beam.rays, Ray, sidtrace.trace, addpoint, field_r, field_result) is reference code."""
-    import beam as refbeam
+    antenna pairs -> interferometer phases.  Everything is reference code (Nfield, Beam incl. its
+    wavefront finder, Ray, sidtrace.trace, addpoint, field_r, field_result); the only stand-in is the
+    restated skimage.measure.find_contours of oracle/refenv.py."""
     import ft2 as refft2
-    from rayrtrace_b200.beam import Beam as PBeam
-
-    def _wavefront(self, dist=0.003, ampbnd=0.001, n=1.):
-        pb = PBeam(x0=self.x0, y0=self.y0, kx0=self._kx0, ky0=self._ky0, freq=self.freq, waist=self.waist, focus=self.focus)
-        return pb._wavefront(dist, ampbnd, n=n)
-
-    refbeam.Beam._wavefront = _wavefront
     nx = 161
     n, x, y = ft2_density(nx, 4e13)
     a_set = np.array([0.0, 0.6, 1.0])

@@ -26,21 +26,45 @@ def test_analytic_gaussian_beam_matches_reference(beam_fix):
     assert (xl, yl) == pytest.approx((1.0, -7.0), abs=1e-15)
 
 
-def test_wavefront_is_an_iso_phase_line(beam_fix):
-    """The Newton-solved front (replacement of skimage.find_contours, beam.py:238) has constant
-    phase to 1e-9 rad, passes through (0, dist) and reproduces the stored samples."""
+def test_wavefront_matches_the_reference_finder(beam_fix):
+    """The reference finds the front with skimage.measure.find_contours on a 1000 x 1000 phase map
+    (beam.py:225-247); the fixture holds the vertices its own code produced (on the restated
+    find_contours of oracle/refenv.py).  The product's default finder must return the same vertices
+    from the narrow band of map nodes it evaluates, and from the full map."""
     n, x, y = ft2_density(int(beam_fix["nx"]), float(beam_fix["n0"]))
     nf = Nfield(n, x=x, y=y)
     b = _beam(beam_fix)
+    assert b.front_method == "contour"
     wf = b.wavefront_r(dist=3, ampbnd=1e-3, n_field=nf)
-    np.testing.assert_allclose(wf.x, beam_fix["wf_x"], rtol=0, atol=1e-12)
-    np.testing.assert_allclose(wf.y, beam_fix["wf_y"], rtol=0, atol=1e-12)
+    assert wf.x.tobytes() == beam_fix["wf_x"].tobytes()
+    assert wf.y.tobytes() == beam_fix["wf_y"].tobytes()
+    rng = np.random.default_rng(0)
+    for _ in range(4):       # band == full map, for other beams too
+        from rayrtrace_b200.beam import Beam
+        bb = Beam(x0=rng.uniform(-4, 4), y0=-9.0, kx0=0, ky0=1, waist=rng.uniform(0.25, 0.6), focus=rng.uniform(-2, 0.5),
+                  freq=rng.uniform(100e9, 160e9))
+        dist, ne = rng.uniform(1.5, 4), rng.uniform(0.9, 1.0)
+        fast, full = bb._wavefront_contour(dist, 1e-3, ne), bb._wavefront_contour(dist, 1e-3, ne, banded=False)
+        assert fast.x.tobytes() == full.x.tobytes() and fast.y.tobytes() == full.y.tobytes()
+
+
+def test_newton_front_is_the_exact_iso_phase_line(beam_fix):
+    """front_method='newton': constant phase to 1e-9 rad, through (0, dist), within the
+    marching-squares interpolation error (~1e-6 cm) of the reference's front."""
+    n, x, y = ft2_density(int(beam_fix["nx"]), float(beam_fix["n0"]))
+    nf = Nfield(n, x=x, y=y)
+    b = _beam(beam_fix)
+    b.front_method = "newton"
+    wf = b.wavefront_r(dist=3, ampbnd=1e-3, n_field=nf)
     ne = nf.refractive_index(freq=b.freq)
     ph = b._field(wf.x, wf.y, n=ne, outfmt="dict")["phase"]
     assert np.ptp(ph) < 1e-9
     mid = len(wf.x) // 2
     assert abs(wf.y[mid] - 3) < b.wave_len          # nearest whole-period front to dist = 3 (beam.py:263-272)
     assert abs(ph[mid] / 2 / np.pi - round(ph[mid] / 2 / np.pi)) < 1e-6
+    ref = interp1d(beam_fix["wf_x"], beam_fix["wf_y"], kind="cubic")
+    xs = np.linspace(wf.x[1], wf.x[-2], 4001)
+    assert 1e-8 < np.abs(wf(xs) - ref(xs)).max() < 3e-6
 
 
 def test_launch_conditions_match_reference_beam_rays(beam_fix):
