@@ -46,6 +46,7 @@ typedef struct stb_medium_s *stb_medium_t;
 #define STB_RK_MAX_STEPS      2
 #define STB_RK_STEP_UNDERFLOW 3   /* step shrank below hmin: resonance (N^2 -> inf) or NaN input */
 #define STB_RK_START_OUTSIDE  4
+#define STB_RK_STOP_LINE      5   /* landed on the stop line (receiver line, cf. Ray.addpoint, ray.py:131-224) */
 
 typedef struct stb_medium_desc_s {
     size_t struct_size;
@@ -82,6 +83,10 @@ typedef struct stb_rk_s {
     double h0, hmin, hmax;     /* first, smallest and largest step in tau (cm)                      */
     double tau_max;            /* stop at this tau (HUGE_VAL: never)                                */
     int32_t max_steps;         /* accepted-step cap                                                 */
+    int32_t stop_axis;         /* 0: none; 1: end the ray ON the line y = stop_val; 2: on x = stop_val. The step  */
+                               /* that crosses the line is repeated with shorter lengths (regula falsi on the   */
+                               /* step length, counted in nrej) until |coordinate - stop_val| <= stop_tol         */
+    double   stop_val, stop_tol;
 
     double  *end_state;        /* [4][nrays] (x, y, px, py)                                         */
     double  *tau_end;          /* [ray] integration variable at the end (path length in vacuum)     */

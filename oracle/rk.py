@@ -16,7 +16,7 @@ _SO = os.path.join(_HERE, "librk_oracle.so")
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int32)
 
-LEFT_DOMAIN, TAU_MAX, MAX_STEPS, STEP_UNDERFLOW, START_OUTSIDE = range(5)
+LEFT_DOMAIN, TAU_MAX, MAX_STEPS, STEP_UNDERFLOW, START_OUTSIDE, STOP_LINE = range(6)
 
 
 class _Medium(ctypes.Structure):
@@ -28,7 +28,8 @@ class _Medium(ctypes.Structure):
 class _Ctl(ctypes.Structure):
     _fields_ = [("rtol", ctypes.c_double), ("atol_r", ctypes.c_double), ("atol_p", ctypes.c_double),
                 ("h0", ctypes.c_double), ("hmin", ctypes.c_double), ("hmax", ctypes.c_double), ("tau_max", ctypes.c_double),
-                ("max_steps", ctypes.c_int), ("hist", _dp), ("nbins", ctypes.c_int),
+                ("max_steps", ctypes.c_int), ("stop_axis", ctypes.c_int), ("stop_val", ctypes.c_double),
+                ("stop_tol", ctypes.c_double), ("hist", _dp), ("nbins", ctypes.c_int),
                 ("xaxis", ctypes.c_double), ("yaxis", ctypes.c_double), ("r_rlcs", ctypes.c_double),
                 ("bins_per_rho", ctypes.c_double)]
 
@@ -106,13 +107,16 @@ class Medium:
 
 def trace(med: Medium, x0, y0, px0, py0, *, rtol=1e-9, atol_r=1e-9, atol_p=1e-9, h0=0.05, hmin=1e-12, hmax=1e30,
           tau_max=float("inf"), max_steps=100000, xscale=None, yscale=None, amp=None, nbins=0, xaxis=0.0, yaxis=0.0,
-          r_lcs=1.0, rho_max=1.0, L=0, aux=False, threads=1):
+          r_lcs=1.0, rho_max=1.0, L=0, aux=False, threads=1, stop=None, stop_tol=1e-12):
+    """stop = (val, 'y' | 'x'): end the ray on that line."""
     x0 = _f64(np.atleast_1d(x0))
     n = x0.shape[0]
     y0, px0, py0 = _f64(y0, n), _f64(px0, n), _f64(py0, n)
     xscale, yscale, amp = _f64(xscale, n), _f64(yscale, n), _f64(amp, n)
     hist = np.zeros(nbins) if nbins else None
-    ctl = _Ctl(rtol, atol_r, atol_p, h0, hmin, hmax, tau_max, int(max_steps), _p(hist), int(nbins), xaxis, yaxis,
+    stop_axis = 0 if stop is None else (1 if stop[1] == "y" else 2)
+    ctl = _Ctl(rtol, atol_r, atol_p, h0, hmin, hmax, tau_max, int(max_steps), stop_axis,
+               0.0 if stop is None else float(stop[0]), float(stop_tol), _p(hist), int(nbins), xaxis, yaxis,
                1.0 / r_lcs, (nbins / rho_max) if nbins else 0.0)
     end = np.empty((4, n))
     tau, phi, sig, n2min, ham = (np.empty(n) for _ in range(5))

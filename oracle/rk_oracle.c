@@ -31,6 +31,8 @@ typedef struct {
 typedef struct {
     double rtol, atol_r, atol_p, h0, hmin, hmax, tau_max;
     int max_steps;
+    int stop_axis;
+    double stop_val, stop_tol;
     /* histogram */
     double *hist;
     int nbins;
@@ -227,6 +229,8 @@ void rk_oracle_ray(const rk_medium *m, const rk_ctl *c, double x, double y, doub
     const double amp2 = amp * amp;
     double P = amp2;
     int nacc = 0, nrej = 0, status, after_reject = 0;
+    int land = 0, side = 0;
+    double hland = 0, hl = 0, dl = 0, hu = 0, du = 0;
     double f1x, f1y, a1, n2, n2min;
     rk_oracle_eval(m, xs, ys, x, y, &f1x, &f1y, &a1, &n2);
     n2min = n2;
@@ -242,7 +246,7 @@ void rk_oracle_ray(const rk_medium *m, const rk_ctl *c, double x, double y, doub
     if (!inside(m, x, y)) { status = 4; goto done; }
     if (c->max_steps <= 0) { status = 2; goto done; }
     for (;;) {
-        double hh = h;
+        double hh = land ? hland : h;
         int last = 0;
         if (tau + hh >= c->tau_max) { hh = c->tau_max - tau; last = 1; }
         double kpx[7], kpy[7], kfx[7], kfy[7], ka[7];
@@ -282,8 +286,42 @@ void rk_oracle_ray(const rk_medium *m, const rk_ctl *c, double x, double y, doub
             const double fac = (err == err) ? fmax(0.2, 0.9 / root5(err)) : 0.2;
             h = hh * fac;
             after_reject = 1;
+            land = 0;
             if (!(h >= c->hmin)) { status = 3; goto done; }
             continue;
+        }
+        int on_line = 0;
+        if (c->stop_axis) {
+            const double d0 = (c->stop_axis == 1 ? y : x) - c->stop_val;
+            const double d1 = (c->stop_axis == 1 ? yn : xn) - c->stop_val;
+            if (!land) {
+                if (d0 != 0.0 && ((d0 < 0.0) != (d1 < 0.0) || d1 == 0.0)) {
+                    if (fabs(d1) <= c->stop_tol) {
+                        on_line = 1;
+                    } else {
+                        land = 1; side = 0;
+                        hl = 0.0; dl = d0; hu = hh; du = d1;
+                        hland = hh * (d0 / (d0 - d1));
+                        ++nrej;
+                        continue;
+                    }
+                }
+            } else if (fabs(d1) <= c->stop_tol || land >= 12) {
+                on_line = 1;
+            } else {
+                if ((d1 < 0.0) == (dl < 0.0)) {
+                    hl = hh; dl = d1;
+                    if (side == -1) du *= 0.5;
+                    side = -1;
+                } else {
+                    hu = hh; du = d1;
+                    if (side == 1) dl *= 0.5;
+                    side = 1;
+                }
+                hland = (hl * du - hu * dl) / (du - dl);
+                ++land; ++nrej;
+                continue;
+            }
         }
         double sphi = A[5][0] * fma(kpx[0], kpx[0], kpy[0] * kpy[0]);
         double ssig = A[5][0] * ka[0];
@@ -315,6 +353,7 @@ void rk_oracle_ray(const rk_medium *m, const rk_ctl *c, double x, double y, doub
         const double fac = (err > 0.0) ? fmin(fmx, 0.9 / root5(err)) : fmx;
         after_reject = 0;
         h = fmin(hh * fac, c->hmax);
+        if (on_line) { status = 5; break; }
         if (!inside(m, x, y)) { status = 0; break; }
         if (last) { status = 1; break; }
         if (nacc >= c->max_steps) { status = 2; break; }

@@ -125,6 +125,8 @@ class StbRk(Structure):
         ("h0", c_double), ("hmin", c_double), ("hmax", c_double),
         ("tau_max", c_double),
         ("max_steps", c_int32),
+        ("stop_axis", c_int32),
+        ("stop_val", c_double), ("stop_tol", c_double),
         ("end_state", c_void_p),
         ("tau_end", c_void_p), ("phi_end", c_void_p), ("sig_end", c_void_p), ("n2_min", c_void_p), ("ham_end", c_void_p),
         ("nacc", c_void_p), ("nrej", c_void_p), ("status", c_void_p),

@@ -24,7 +24,7 @@ namespace stbrk {
 constexpr int kBlock = 128;
 constexpr unsigned FULL = 0xffffffffu;
 
-enum Status : int { LEFT_DOMAIN = 0, TAU_MAX = 1, MAX_STEPS = 2, STEP_UNDERFLOW = 3, START_OUTSIDE = 4 };
+enum Status : int { LEFT_DOMAIN = 0, TAU_MAX = 1, MAX_STEPS = 2, STEP_UNDERFLOW = 3, START_OUTSIDE = 4, STOP_LINE = 5 };
 
 struct Medium {
     const double *X;       // n/n_c at the reference frequency: [ny][nx] nodes, or [ny+2][nx+2] B-spline coefficients
@@ -44,6 +44,8 @@ struct Params {
     double rtol, atol_r, atol_p;
     double h0, hmin, hmax, tau_max;
     int max_steps;
+    int stop_axis;                       // 0: none, 1: stop on the line y = stop_val, 2: x = stop_val
+    double stop_val, stop_tol;
     // outputs (any may be nullptr)
     double *end_state;                   // [4][nrays]
     double *tau_end, *phi_end, *sig_end, *n2_min, *ham_end;
@@ -242,6 +244,14 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
     double f1x = 0, f1y = 0, a1 = 0;
     int nacc = 0, nrej = 0, status = 0;
     bool after_reject = false;
+    // landing on the stop line: the step that crosses it is repeated with shorter lengths
+    // (Illinois regula falsi on the step length) until its end state lies on the line
+    // (the bracket lives in shared memory: it is touched on a handful of attempts per ray and
+    // would otherwise cost ten registers in the hot loop)
+    __shared__ double s_land[5 * kBlock];
+    double &hland = s_land[threadIdx.x], &hl = s_land[kBlock + threadIdx.x], &dl = s_land[2 * kBlock + threadIdx.x];
+    double &hu = s_land[3 * kBlock + threadIdx.x], &du = s_land[4 * kBlock + threadIdx.x];
+    int land = 0, side = 0;
 
     auto inside = [&](double xx, double yy) -> bool {
         const double u = (xx - m.xorg) * m.rdx, v = (yy - m.yorg) * m.rdy;
@@ -284,7 +294,7 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
         const double a = p.amp ? p.amp[r] : 1.0;
         amp2 = a * a; P = amp2;
         phi = 0.0; sig = 0.0; tau = 0.0; h = p.h0;
-        nacc = 0; nrej = 0; after_reject = false;
+        nacc = 0; nrej = 0; after_reject = false; land = 0;
         double n2;
         rk_eval<INTERP, XMODE, ABSORB>(m, xs, ys, x, y, f1x, f1y, a1, n2);
         n2min = n2;
@@ -296,7 +306,7 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
 
     // one step attempt; false when the ray ended (outputs written)
     auto attempt = [&]() -> bool {
-        double hh = h;
+        double hh = land ? hland : h;
         bool last = false;
         if (tau + hh >= p.tau_max) { hh = p.tau_max - tau; last = true; }
         // stage derivatives: position <- kp (the stage's p), momentum <- kf, sigma <- ka
@@ -341,8 +351,42 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
             const double fac = (err == err) ? fmax(0.2, 0.9 / root5(err)) : 0.2;
             h = hh * fac;
             after_reject = true;
+            land = 0;              // a landing trial that fails the error test: resume stepping, re-detect
             if (!(h >= p.hmin)) { status = STEP_UNDERFLOW; retire(); return false; }
             return true;
+        }
+        bool on_line = false;
+        if (p.stop_axis) {
+            const double d0 = (p.stop_axis == 1 ? y : x) - p.stop_val;
+            const double d1 = (p.stop_axis == 1 ? yn : xn) - p.stop_val;
+            if (!land) {
+                if (d0 != 0.0 && ((d0 < 0.0) != (d1 < 0.0) || d1 == 0.0)) {      // the line is crossed in this step
+                    if (fabs(d1) <= p.stop_tol) {
+                        on_line = true;
+                    } else {
+                        land = 1; side = 0;
+                        hl = 0.0; dl = d0; hu = hh; du = d1;
+                        hland = hh * (d0 / (d0 - d1));
+                        ++nrej;
+                        return true;
+                    }
+                }
+            } else if (fabs(d1) <= p.stop_tol || land >= 12) {
+                on_line = true;
+            } else {
+                if ((d1 < 0.0) == (dl < 0.0)) {
+                    hl = hh; dl = d1;
+                    if (side == -1) du *= 0.5;
+                    side = -1;
+                } else {
+                    hu = hh; du = d1;
+                    if (side == 1) dl *= 0.5;
+                    side = 1;
+                }
+                hland = (hl * du - hu * dl) / (du - dl);
+                ++land; ++nrej;
+                return true;
+            }
         }
         // accepted: quadratures with the 5th-order weights
         double sphi = cA[5][0] * fma(kpx[0], kpx[0], kpy[0] * kpy[0]);
@@ -377,6 +421,7 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
         const double fac = (err > 0.0) ? fmin(fmx, 0.9 / root5(err)) : fmx;
         after_reject = false;
         h = fmin(hh * fac, p.hmax);
+        if (on_line) { status = STOP_LINE; retire(); return false; }
         if (!inside(x, y)) { status = LEFT_DOMAIN; retire(); return false; }
         if (last) { status = TAU_MAX; retire(); return false; }
         if (nacc >= p.max_steps) { status = MAX_STEPS; retire(); return false; }

@@ -21,7 +21,7 @@ from . import _cabi
 from ._cabi import StbMediumDesc, StbRk, lib
 from .nfield import critical_den
 
-LEFT_DOMAIN, TAU_MAX, MAX_STEPS, STEP_UNDERFLOW, START_OUTSIDE = range(5)
+LEFT_DOMAIN, TAU_MAX, MAX_STEPS, STEP_UNDERFLOW, START_OUTSIDE, STOP_LINE = range(6)
 INTERP = {"bilinear": 0, "catmull-rom": 1, "bspline": 2}
 
 ELECTRON_CYCLOTRON_HZ_PER_T = 2.799249e10
@@ -129,7 +129,7 @@ def trace_rk(med: Medium, x0, y0, px0, py0, *, rtol: float = 1e-9, atol_r: float
              tau_max: float = math.inf, max_steps: int = 100000, xscale=None, yscale=None, amp=None,
              diagnostics: bool = True, L: int = 0, aux: bool = False, hist=None, nbins: int = 0,
              xaxis: float = 0.0, yaxis: float = 0.0, r_lcs: float = 1.0, rho_max: float = 1.0,
-             out: Optional[RkResult] = None, stream=None) -> RkResult:
+             stop=None, stop_tol: float = 1e-12, out: Optional[RkResult] = None, stream=None) -> RkResult:
     """Trace ``len(x0)`` rays with the adaptive Dormand-Prince 5(4) kernel, one launch.
 
     x0, y0 (cm) and px0, py0 (= k/k0) are contiguous float64 CUDA tensors; so are the optional
@@ -138,6 +138,9 @@ def trace_rk(med: Medium, x0, y0, px0, py0, *, rtol: float = 1e-9, atol_r: float
     last step can carry a ray past the table edge.  ``L`` > 0 records the first L accepted states
     per ray ([nrays, L, 4], NaN-filled) and with ``aux`` their (tau, sigma).  ``nbins`` > 0 (or a
     preallocated ``hist``) accumulates absorbed power per rho bin; needs a medium with ``alpha``.
+    ``stop=(val, 'y')`` (or ``'x'``) ends every ray ON the line y = val (a receiver line, the role of
+    ``Ray.addpoint``, ray.py:131-224): the crossing step is repeated with shorter lengths until
+    ``|y - val| <= stop_tol``; status STOP_LINE, ``res.phi`` is then the optical path to the line.
     Asynchronous on ``stream`` (default: the current torch stream).
     """
     torch = _torch()
@@ -197,6 +200,10 @@ def trace_rk(med: Medium, x0, y0, px0, py0, *, rtol: float = 1e-9, atol_r: float
     k.rtol, k.atol_r, k.atol_p = float(rtol), float(atol_r), float(atol_p)
     k.h0, k.hmin, k.hmax, k.tau_max = h0, float(hmin), hmax, float(tau_max)
     k.max_steps = int(max_steps)
+    if stop is not None:
+        if stop[1] not in ("x", "y"):
+            raise ValueError("stop axis must be 'x' or 'y'")
+        k.stop_axis, k.stop_val, k.stop_tol = (1 if stop[1] == "y" else 2), float(stop[0]), float(stop_tol)
     k.end_state = res.end_state.data_ptr()
     k.nacc, k.nrej, k.status = res.nacc.data_ptr(), res.nrej.data_ptr(), res.status.data_ptr()
     if diagnostics:

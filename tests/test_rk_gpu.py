@@ -134,6 +134,34 @@ def test_sweep_with_cutoffs_resonances_and_caps_bitwise(ph, rk):
     assert set(want["status"].tolist()) >= {rk.LEFT_DOMAIN, rk.MAX_STEPS, rk.STEP_UNDERFLOW, rk.START_OUTSIDE}
 
 
+@pytest.mark.parametrize("stop", [(5.0, "y"), (3.0, "x")])
+@pytest.mark.parametrize("absorb", [False, True])
+def test_stop_line_bitwise_and_on_the_line(ph, rk, stop, absorb):
+    """Receiver line: rays end ON the line (regula falsi on the step length); the landing trials, the
+    landed states and the optical path are the checker's bit for bit; rays that never reach the line
+    end as usual."""
+    xs, X, alpha = _tables(with_alpha=absorb, peak=0.5)
+    n = 4000
+    x0, y0, px, py = _beam(n, seed=9)
+    rng = np.random.default_rng(13)
+    xscale = rng.uniform(0.2, 2.5, n)
+    kw = dict(rtol=1e-9, atol_r=1e-9, atol_p=1e-9, h0=0.05, hmin=1e-10, hmax=0.4, max_steps=5000, stop=stop)
+    med = ph.Medium(X, xs, xs, alpha=alpha)
+    res = _gpu(ph, med, x0, y0, px, py, xscale=xscale, L=32, aux=True, nbins=16 if absorb else 0, r_lcs=7.85, rho_max=1.5, **kw)
+    om = rk.Medium(X, med.xorg, med.yorg, med.dx, med.dy, alpha=alpha)
+    want = rk.trace(om, x0, y0, px, py, xscale=xscale, L=32, aux=True, nbins=16 if absorb else 0, r_lcs=7.85, rho_max=1.5,
+                    threads=8, **kw)
+    _same(res, want)
+    assert res.traj.cpu().numpy().tobytes() == want["traj"].tobytes()
+    landed = want["status"] == rk.STOP_LINE
+    assert 0.3 * n < landed.sum() < n                       # some rays are reflected or leave sideways first
+    coord = want["end_state"][1 if stop[1] == "y" else 0]
+    assert np.abs(coord[landed] - stop[0]).max() <= 1e-12
+    if absorb:
+        got = res.hist.cpu().numpy()
+        assert np.abs(got - want["hist"]).sum() <= 1e-9 * np.abs(want["hist"]).sum()
+
+
 def test_whole_warps_ending_at_launch_and_tiny_batches(ph, rk):
     xs, X, _ = _tables(101)
     d = xs[1] - xs[0]

@@ -302,6 +302,94 @@ def test_threads_do_not_change_results():
     np.testing.assert_allclose(a["hist"], b["hist"], rtol=1e-12)
 
 
+# ---- stop line (receiver) ----------------------------------------------------------------------
+def test_stop_line_lands_on_the_line_closed_forms():
+    xs, d = grid(201)
+    vac = rk.Medium(np.zeros((201, 201)), xs[0], xs[0], d, d)
+    th = np.linspace(-0.4, 0.4, 11)
+    r = rk.trace(vac, np.full(11, 0.5), np.full(11, -9.5), np.sin(th), np.cos(th), hmax=0.4, stop=(8.0, "y"))
+    assert np.all(r["status"] == rk.STOP_LINE)
+    assert np.abs(r["end_state"][1] - 8.0).max() <= 1e-12
+    np.testing.assert_allclose(r["tau"], 17.5 / np.cos(th), rtol=1e-14)
+    np.testing.assert_allclose(r["end_state"][0], 0.5 + 17.5 * np.tan(th), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(r["phi"], r["tau"], rtol=1e-14)
+    # linear ramp: the parabola's crossing of y = 2 and of x = -5
+    X = np.tile(0.4 + 0.04 * xs, (201, 1))
+    ramp = rk.Medium(X, xs[0], xs[0], d, d)
+    N = np.sqrt(1 - (0.4 + 0.04 * -9.5))
+    px, py = N * np.cos(0.5), N * np.sin(0.5)
+    r = rk.trace(ramp, [-9.5], [-3.0], [px], [py], hmax=0.5, stop=(2.0, "y"))
+    T = 5.0 / py
+    assert r["status"][0] == rk.STOP_LINE and abs(r["tau"][0] - T) < 1e-13
+    assert abs(r["end_state"][0, 0] - (-9.5 + px * T - 0.01 * T * T)) < 1e-13
+    r = rk.trace(ramp, [-9.5], [-3.0], [px], [py], hmax=0.5, stop=(-5.0, "x"))
+    T = (px - np.sqrt(px * px - 4 * 0.01 * 4.5)) / 0.02          # -9.5 + px T - 0.01 T^2 = -5, first root
+    assert r["status"][0] == rk.STOP_LINE and abs(r["end_state"][0, 0] + 5.0) <= 1e-12
+    assert abs(r["tau"][0] - T) < 1e-12
+    # a ray that never reaches the line ends as usual; one that starts on it is not stopped there
+    r = rk.trace(vac, [-3.0, -3.0], [-9.5, 8.0], [1.0, 0.0], [0.0, 1.0], hmax=0.4, stop=(8.0, "y"))
+    assert list(r["status"]) == [rk.LEFT_DOMAIN, rk.LEFT_DOMAIN]
+
+
+def test_stop_line_in_a_plasma_agrees_with_scipy_events():
+    m, X, xs, d = gaussian_medium(peak=0.4)
+    ref = _NaturalSpline(X, xs, xs)
+    x0, y0 = -1.0, -9.5
+    N = np.sqrt(1 - ref(x0, y0)[0])
+
+    def rhs(t, z):
+        _, Fx, Fy = ref(z[0], z[1])
+        return [z[2], z[3], -0.5 * Fx, -0.5 * Fy]
+
+    def hit(t, z):
+        return z[1] - 8.0
+    hit.terminal, hit.direction = True, 1
+    sol = solve_ivp(rhs, [0, 60], [x0, y0, 0.1 * N, np.sqrt(1 - 0.01) * N], method="DOP853", rtol=1e-12, atol=1e-13,
+                    max_step=0.1, events=hit)
+    r = rk.trace(m, [x0], [y0], [0.1 * N], [np.sqrt(1 - 0.01) * N], rtol=1e-12, atol_r=1e-12, atol_p=1e-12, hmax=0.4,
+                 stop=(8.0, "y"))
+    assert r["status"][0] == rk.STOP_LINE and abs(r["end_state"][1, 0] - 8.0) <= 1e-12
+    assert r["tau"][0] == pytest.approx(sol.t_events[0][0], abs=2e-8)
+    np.testing.assert_allclose(r["end_state"][:, 0], sol.y_events[0][0], rtol=0, atol=2e-8)
+
+
+def test_reference_receiver_phase_converges_to_the_rk_phase():
+    """The reference's eikonal phase at a receiver line (Ray.ph after Ray.addpoint, ray.py:113-224,
+    on the trajectory of the pinned oracle) approaches k0 * (optical path of the RK ray landed on the
+    same line) at first order in the grid spacing."""
+    from rayrtrace_b200.ray import Ray
+    nc = critical_den(FREQ)
+    k0 = 2 * np.pi * FREQ / (const.speed_of_light * 100)
+    x0, y0, yrx = -3.0, -9.5, 8.0
+    N0 = np.sqrt(1 - 0.5 * np.exp(-(x0 ** 2 + y0 ** 2) / 16))
+    diffs, rk_phase = [], []
+    for n in (201, 401, 801):
+        xs, d = grid(n)
+        XX, YY = np.meshgrid(xs, xs)
+        den = 0.5 * nc * np.exp(-(XX ** 2 + YY ** 2) / 16.0)
+        nf = Nfield(den, x=xs, y=xs, freq=FREQ)
+        L = 40 * n
+        tr = oracle.trace_batch(np.array([(x0 + 10) / d]), np.array([(y0 + 10) / d]), np.array([0.0]), np.array([k0 * N0]),
+                                L, nf.st, nf.dx[0], nf.dy[0], n, n, nf.ax, nf.ay)
+        t = tr["traj"][0, :int(tr["nsteps"][0])]
+        ray = Ray.__new__(Ray)
+        ray.n_field, ray.amp, ray.freq = nf, 1.0, FREQ
+        ray.x = x0 + (t[:, 0] - t[0, 0]) * nf.dx[0]
+        ray.y = y0 + (t[:, 1] - t[0, 1]) * nf.dy[0]
+        ray.kx, ray.ky = t[:, 2].copy(), t[:, 3].copy()
+        ray.st = np.full_like(ray.x, nf.st)
+        ray.st[-1] = 0
+        idx = ray.addpoint(yrx, "y")
+        ph_ref = ray.ph[int(np.atleast_1d(idx)[0])]
+        m = rk.Medium(den / nc, xs[0], xs[0], d, d)
+        q = rk.trace(m, [x0], [y0], [0.0], [N0], rtol=1e-11, atol_r=1e-11, atol_p=1e-11, hmax=0.2, stop=(yrx, "y"))
+        assert q["status"][0] == rk.STOP_LINE
+        rk_phase.append(k0 * q["phi"][0])
+        diffs.append(abs(ph_ref - rk_phase[-1]))
+    assert max(rk_phase) - min(rk_phase) < 2e-3                 # rad, of ~400: the RK phase barely depends on the grid
+    assert diffs[0] < 1.0 and 1.6 < diffs[0] / diffs[1] < 2.6 and 1.6 < diffs[1] / diffs[2] < 2.6
+
+
 # ---- the reference scheme converges to this solution ---------------------------------------
 def _line_crossing(xy, yline):
     x, y = xy[:, 0], xy[:, 1]
