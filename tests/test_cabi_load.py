@@ -89,3 +89,17 @@ def test_compute_entry_points_fail_loudly_without_a_device():
     x = [np.zeros(8) for _ in range(4)]
     with pytest.raises(_cabi.SidtraceError):
         sidtrace.trace(*x, 0.1, 1.0, 1.0, 7, 5, a, a.copy())
+    # the adaptive-RK extension has no host path either
+    from rayrtrace_b200 import physics
+    d = _cabi.StbMediumDesc()
+    d.struct_size = ctypes.sizeof(_cabi.StbMediumDesc)
+    X = np.zeros((4, 4))
+    d.nx = d.ny = 4
+    d.dx = d.dy = 1.0
+    d.X = X.ctypes.data
+    d.interp = 2
+    m = ctypes.c_void_p()
+    assert _cabi.lib.stb_medium_create(ctypes.byref(d), ctypes.byref(m)) == _cabi.STB_ERR_CUDA and not m.value
+    with pytest.raises(Exception):
+        physics.Medium(X, np.arange(4.0), np.arange(4.0))
+
