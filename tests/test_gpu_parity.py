@@ -815,8 +815,9 @@ def test_fuzz_random_configurations_bitwise(st, oracle_mod, torch_mod):
     """80 random configurations (grid shape, ray count, cap, step, cell sizes, per-ray steps, schedule,
     layout, tile, division mode, host/device/pinned I/O, fused outputs): everything bit-identical
     to the oracle."""
-    rng = np.random.default_rng(2026)
-    for it in range(80):
+    import os
+    rng = np.random.default_rng(int(os.environ.get("FUZZ_SEED", "2026")))      # FUZZ_ITERS / FUZZ_SEED: long one-off runs
+    for it in range(int(os.environ.get("FUZZ_ITERS", "80"))):
         nx, ny = int(rng.integers(2, 90)), int(rng.integers(2, 90))
         n = int(rng.choice([1, 2, 31, 32, 33, 127, 129, 255, 257, 700, 2049]))
         L = int(rng.choice([1, 2, 3, 17, 64, 300]))

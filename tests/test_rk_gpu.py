@@ -162,6 +162,63 @@ def test_stop_line_bitwise_and_on_the_line(ph, rk, stop, absorb):
         assert np.abs(got - want["hist"]).sum() <= 1e-9 * np.abs(want["hist"]).sum()
 
 
+def test_fuzz_random_media_and_controls_bitwise(ph, rk):
+    """Random table shapes and spacings, interpolants, modes, tolerances, step limits, scales, stop
+    lines, caps and batch sizes: every per-ray output bit-identical to the checker."""
+    import os
+    rng = np.random.default_rng(int(os.environ.get("FUZZ_SEED", "7")))
+    for it in range(int(os.environ.get("FUZZ_ITERS", "40"))):
+        nx, ny = int(rng.integers(2, 160)), int(rng.integers(2, 160))
+        xs = np.linspace(-rng.uniform(2, 12), rng.uniform(2, 12), nx)
+        ys = np.linspace(-rng.uniform(2, 12), rng.uniform(2, 12), ny)
+        XX, YY = np.meshgrid(xs, ys)
+        X = rng.uniform(0, 1.3) * np.exp(-(XX ** 2 + YY ** 2) / rng.uniform(4, 40)) + 0.02 * rng.random(XX.shape)
+        absorb = bool(rng.random() < 0.4)
+        alpha = 0.05 * rng.random(XX.shape) if absorb else None
+        mode = "X" if rng.random() < 0.5 else "O"
+        interp = INTERPS[int(rng.integers(0, 3))]
+        n = int(rng.choice([1, 2, 31, 33, 100, 257, 1500]))
+        x0 = rng.uniform(xs[0] - 0.5, xs[-1] + 0.5, n)
+        y0 = rng.uniform(ys[0] - 0.5, ys[-1] + 0.5, n)
+        th = rng.uniform(0, 2 * np.pi, n)
+        pm = rng.uniform(0.1, 1.2, n)
+        if n > 4:
+            x0[rng.integers(0, n)] = rng.choice([np.nan, 1e30, -1e30, xs[0], xs[-1]])
+        tol = float(10.0 ** rng.uniform(-11, -4))
+        cell = min(xs[1] - xs[0], ys[1] - ys[0])
+        h0 = float(cell * rng.uniform(0.05, 2.0))
+        kw = dict(rtol=tol, atol_r=tol, atol_p=tol, h0=h0, hmin=float(h0 * 10.0 ** rng.uniform(-9, -2)),
+                  hmax=float(h0 * rng.uniform(1, 20)), max_steps=int(rng.choice([0, 1, 7, 300])),
+                  tau_max=float(rng.choice([np.inf, 0.37, 5.0, 40.0])))
+        if rng.random() < 0.5:
+            kw["stop"] = (float(rng.uniform(ys[0], ys[-1])), "y") if rng.random() < 0.5 else (float(rng.uniform(xs[0], xs[-1])), "x")
+        per_ray = {}
+        if rng.random() < 0.5:
+            per_ray["xscale"] = rng.uniform(0, 3, n)
+        if rng.random() < 0.5:
+            per_ray["yscale"] = rng.uniform(0.3, 2, n)
+        if rng.random() < 0.5:
+            per_ray["amp"] = rng.uniform(0, 2, n)
+        L = int(rng.choice([0, 1, 5, 40]))
+        hist = dict(nbins=int(rng.choice([1, 7, 64])), r_lcs=float(rng.uniform(2, 9)), rho_max=float(rng.uniform(0.5, 2)),
+                    xaxis=float(rng.uniform(-1, 1)), yaxis=float(rng.uniform(-1, 1))) if absorb and rng.random() < 0.7 else {}
+        med = ph.Medium(X, xs, ys, alpha=alpha, mode=mode, Y0=float(rng.uniform(0.2, 0.7)), R0=float(rng.uniform(20, 80)), interp=interp)
+        res = _gpu(ph, med, x0, y0, pm * np.cos(th), pm * np.sin(th), L=L, aux=bool(L and rng.random() < 0.5), **kw, **per_ray, **hist)
+        om = rk.Medium(X, med.xorg, med.yorg, med.dx, med.dy, alpha=alpha, mode=mode, Y0=med.Y0, R0=med.R0, interp=INTERP_ID[interp])
+        want = rk.trace(om, x0, y0, pm * np.cos(th), pm * np.sin(th), L=L, aux=res.aux is not None, threads=4, **kw, **per_ray, **hist)
+        ctx = (it, nx, ny, n, mode, interp, absorb, kw, L)
+        for k in ("nacc", "nrej", "status", "tau", "phi", "sig", "n2_min", "end_state", "ham"):
+            got = getattr(res, k).cpu().numpy()
+            # NaN launch states propagate NaNs whose payload/sign may differ between CPU and GPU: compare as values
+            assert np.array_equal(got, want[k], equal_nan=True), (k, ctx)
+        if L:
+            assert np.array_equal(res.traj.cpu().numpy(), want["traj"], equal_nan=True), ctx
+        if hist:
+            got, w = res.hist.cpu().numpy(), want["hist"]
+            assert np.abs(got - w).sum() <= 1e-9 * max(np.abs(w).sum(), 1e-300), ctx
+        med.close()
+
+
 def test_whole_warps_ending_at_launch_and_tiny_batches(ph, rk):
     xs, X, _ = _tables(101)
     d = xs[1] - xs[0]
