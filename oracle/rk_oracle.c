@@ -12,7 +12,8 @@
  *
  *   dr/dtau = p,  dp/dtau = grad N^2 / 2,  N^2 = 1 - X  (O)  or  1 - X(1-X)/(1-X-Y^2)  (X mode)
  *   X = n/n_c from a node table (the n of den.py:65-66), bicubic Catmull-Rom or bilinear;
- *   Dormand-Prince 5(4), FSAL, max-norm error control, controller 0.9 err^(-1/5) in [0.2, 5].
+ *   Dormand-Prince 5(4), FSAL, max-norm error control, controller 0.9 err^(-1/5) in [0.2, 5]
+ *   (err^(-1/5) by a division-free Newton iteration from an exponent-indexed seed).
  */
 #include <math.h>
 #include <pthread.h>
@@ -204,16 +205,33 @@ void rk_oracle_prefilter(const double *nodes, int nx, int ny, double *coef)
     free(R); free(half);
 }
 
-static double root5(double err)
+/* seeds 2^(-(k + 1/2)/5), k = -14 .. 10 (the bits of the kernel's cR5) */
+static const double R5[25] = {
+    0x1.9fdf8bcce533ep+2, 0x1.6a09e667f3bcdp+2, 0x1.3b2c47bff8328p+2, 0x1.125fbee250664p+2, 0x1.ddb680117ab12p+1,
+    0x1.9fdf8bcce533dp+1, 0x1.6a09e667f3bcdp+1, 0x1.3b2c47bff8329p+1, 0x1.125fbee250664p+1, 0x1.ddb680117ab12p+0,
+    0x1.9fdf8bcce533dp+0, 0x1.6a09e667f3bcdp+0, 0x1.3b2c47bff8329p+0, 0x1.125fbee250664p+0, 0x1.ddb680117ab12p-1,
+    0x1.9fdf8bcce533ep-1, 0x1.6a09e667f3bcdp-1, 0x1.3b2c47bff8329p-1, 0x1.125fbee250664p-1, 0x1.ddb680117ab12p-2,
+    0x1.9fdf8bcce533dp-2, 0x1.6a09e667f3bcdp-2, 0x1.3b2c47bff8329p-2, 0x1.125fbee250664p-2, 0x1.ddb680117ab12p-3};
+
+static double inv_root5(double err)
 {
-    const double e = fmin(fmax(err, 1e-4), 2e3);
-    double g = sqrt(sqrt(e));
+    double e = err > 1e-4 ? err : 1e-4;
+    e = e < 2e3 ? e : 2e3;
+    uint64_t bits;
+    memcpy(&bits, &e, sizeof bits);
+    const int k = (int)((bits >> 52) & 0x7ff) - 1023 + 14;
+    double r = R5[k];
+    const double t = 0.2 * e;
     for (int it = 0; it < 4; ++it) {
-        const double g2 = g * g;
-        g = (4.0 * g + e / (g2 * g2)) * 0.2;
+        const double r2 = r * r;
+        const double r5 = (r2 * r2) * r;
+        r = r * fma(-t, r5, 1.2);
     }
-    return g;
+    return r;
 }
+
+static double max2(double a, double b) { return a > b ? a : b; }
+static double min2(double a, double b) { return a < b ? a : b; }
 
 static int inside(const rk_medium *m, double x, double y)
 {
@@ -273,17 +291,20 @@ void rk_oracle_ray(const rk_medium *m, const rk_ctl *c, double x, double y, doub
             efy = fma(E[j], kfy[j], efy);
         }
         const double ah = fabs(hh);
-        const double scx = fma(c->rtol, fmax(fabs(x), fabs(xn)), c->atol_r);
-        const double scy = fma(c->rtol, fmax(fabs(y), fabs(yn)), c->atol_r);
-        const double scpx = fma(c->rtol, fmax(fabs(px), fabs(pxn)), c->atol_p);
-        const double scpy = fma(c->rtol, fmax(fabs(py), fabs(pyn)), c->atol_p);
-        const double e0 = ah * fabs(ex) / scx, e1 = ah * fabs(ey) / scy;
-        const double e2 = ah * fabs(efx) / scpx, e3 = ah * fabs(efy) / scpy;
-        const double esum = (e0 + e1) + (e2 + e3);
-        const double err = (esum == esum) ? fmax(fmax(e0, e1), fmax(e2, e3)) : esum;
+        const double scx = fma(c->rtol, max2(fabs(x), fabs(xn)), c->atol_r);
+        const double scy = fma(c->rtol, max2(fabs(y), fabs(yn)), c->atol_r);
+        const double scpx = fma(c->rtol, max2(fabs(px), fabs(pxn)), c->atol_p);
+        const double scpy = fma(c->rtol, max2(fabs(py), fabs(pyn)), c->atol_p);
+        const double q0 = ah * fabs(ex), q1 = ah * fabs(ey), q2 = ah * fabs(efx), q3 = ah * fabs(efy);
+        const double esum = (q0 + q1) + (q2 + q3);
+        double en = q0, ed = scx;
+        if (q1 * ed > en * scy) { en = q1; ed = scy; }
+        if (q2 * ed > en * scpx) { en = q2; ed = scpx; }
+        if (q3 * ed > en * scpy) { en = q3; ed = scpy; }
+        const double err = (esum == esum) ? en / ed : esum;
         if (!(err <= 1.0)) {
             ++nrej;
-            const double fac = (err == err) ? fmax(0.2, 0.9 / root5(err)) : 0.2;
+            const double fac = (err == err) ? max2(0.2, 0.9 * inv_root5(err)) : 0.2;
             h = hh * fac;
             after_reject = 1;
             land = 0;
@@ -335,7 +356,7 @@ void rk_oracle_ray(const rk_medium *m, const rk_ctl *c, double x, double y, doub
         sig = fma(hh, ssig, sig);
         tau = last ? c->tau_max : tau + hh;
         f1x = kfx[6]; f1y = kfy[6]; a1 = ka[6];
-        n2min = fmin(n2min, n2n);
+        n2min = min2(n2n, n2min);
         ++nacc;
         STORE();
         if (c->hist && m->alpha) {
@@ -350,9 +371,9 @@ void rk_oracle_ray(const rk_medium *m, const rk_ctl *c, double x, double y, doub
         /* no growth right after a rejection: keeps the controller from bouncing at the kinks of
          * the interpolant (cell edges) */
         const double fmx = after_reject ? 1.0 : 5.0;
-        const double fac = (err > 0.0) ? fmin(fmx, 0.9 / root5(err)) : fmx;
+        const double fac = min2(0.9 * inv_root5(err), fmx);
         after_reject = 0;
-        h = fmin(hh * fac, c->hmax);
+        h = min2(hh * fac, c->hmax);
         if (on_line) { status = 5; break; }
         if (!inside(m, x, y)) { status = 0; break; }
         if (last) { status = 1; break; }

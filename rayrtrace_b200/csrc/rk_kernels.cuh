@@ -202,19 +202,38 @@ __device__ STB_RK_EVAL_INLINE void rk_eval(const Medium &m, double xs, double ys
     }
 }
 
-// err^(1/5) from IEEE operations only (sqrt + Newton), so that the CPU checker reproduces the
-// step-size sequence bit for bit.  The argument is clamped to the range the controller uses.
-__device__ __forceinline__ double root5(double err)
+// Seeds 2^(-(k + 1/2)/5), k = -14 .. 10, of the inverse fifth root (hex literals: the CPU checker holds
+// the same bits).
+__constant__ double cR5[25] = {
+    0x1.9fdf8bcce533ep+2, 0x1.6a09e667f3bcdp+2, 0x1.3b2c47bff8328p+2, 0x1.125fbee250664p+2, 0x1.ddb680117ab12p+1,
+    0x1.9fdf8bcce533dp+1, 0x1.6a09e667f3bcdp+1, 0x1.3b2c47bff8329p+1, 0x1.125fbee250664p+1, 0x1.ddb680117ab12p+0,
+    0x1.9fdf8bcce533dp+0, 0x1.6a09e667f3bcdp+0, 0x1.3b2c47bff8329p+0, 0x1.125fbee250664p+0, 0x1.ddb680117ab12p-1,
+    0x1.9fdf8bcce533ep-1, 0x1.6a09e667f3bcdp-1, 0x1.3b2c47bff8329p-1, 0x1.125fbee250664p-1, 0x1.ddb680117ab12p-2,
+    0x1.9fdf8bcce533dp-2, 0x1.6a09e667f3bcdp-2, 0x1.3b2c47bff8329p-2, 0x1.125fbee250664p-2, 0x1.ddb680117ab12p-3};
+
+// err^(-1/5) for the step-size controller, from IEEE operations only so that the CPU checker reproduces
+// the step-size sequence bit for bit: seed from the binary exponent, then four division-free Newton
+// steps r <- r (1.2 - 0.2 e r^5) (relative error ~1e-11; the controller needs far less).  The argument
+// is clamped to the range the controller's [0.2, 5] limits can distinguish.
+__device__ __forceinline__ double inv_root5(double err)
 {
-    const double e = fmin(fmax(err, 1e-4), 2e3);
-    double g = sqrt(sqrt(e));
+    double e = err > 1e-4 ? err : 1e-4;
+    e = e < 2e3 ? e : 2e3;
+    const int k = ((__double2hiint(e) >> 20) & 0x7ff) - 1023 + 14;
+    double r = cR5[k];
+    const double t = 0.2 * e;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-        const double g2 = g * g;
-        g = (4.0 * g + e / (g2 * g2)) * 0.2;
+        const double r2 = r * r;
+        const double r5 = (r2 * r2) * r;
+        r = r * fma(-t, r5, 1.2);
     }
-    return g;
+    return r;
 }
+
+// compare-select max / min (no NaN special-casing: NaNs are caught separately)
+__device__ __forceinline__ double max2(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double min2(double a, double b) { return a < b ? a : b; }
 
 __device__ __forceinline__ void rk_hist_add(double *sh, int b, double w)
 {
@@ -337,18 +356,23 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
             efx = fma(cE[j], kfx[j], efx);
             efy = fma(cE[j], kfy[j], efy);
         }
+        // err = max_i |e_i| / sc_i, sc_i = atol + rtol max(|y_i|, |ynew_i|): the largest ratio is found
+        // by cross-multiplication (the scales are positive), so the step costs one division, not four
         const double ah = fabs(hh);
-        const double scx = fma(p.rtol, fmax(fabs(x), fabs(xn)), p.atol_r);
-        const double scy = fma(p.rtol, fmax(fabs(y), fabs(yn)), p.atol_r);
-        const double scpx = fma(p.rtol, fmax(fabs(px), fabs(pxn)), p.atol_p);
-        const double scpy = fma(p.rtol, fmax(fabs(py), fabs(pyn)), p.atol_p);
-        const double e0 = ah * fabs(ex) / scx, e1 = ah * fabs(ey) / scy;
-        const double e2 = ah * fabs(efx) / scpx, e3 = ah * fabs(efy) / scpy;
-        const double esum = (e0 + e1) + (e2 + e3);   // NaN in any component must not be hidden by fmax
-        const double err = (esum == esum) ? fmax(fmax(e0, e1), fmax(e2, e3)) : esum;
+        const double scx = fma(p.rtol, max2(fabs(x), fabs(xn)), p.atol_r);
+        const double scy = fma(p.rtol, max2(fabs(y), fabs(yn)), p.atol_r);
+        const double scpx = fma(p.rtol, max2(fabs(px), fabs(pxn)), p.atol_p);
+        const double scpy = fma(p.rtol, max2(fabs(py), fabs(pyn)), p.atol_p);
+        const double q0 = ah * fabs(ex), q1 = ah * fabs(ey), q2 = ah * fabs(efx), q3 = ah * fabs(efy);
+        const double esum = (q0 + q1) + (q2 + q3);   // a NaN anywhere must reject the step
+        double en = q0, ed = scx;
+        if (q1 * ed > en * scy) { en = q1; ed = scy; }
+        if (q2 * ed > en * scpx) { en = q2; ed = scpx; }
+        if (q3 * ed > en * scpy) { en = q3; ed = scpy; }
+        const double err = (esum == esum) ? en / ed : esum;
         if (!(err <= 1.0)) {   // rejected (NaN included)
             ++nrej;
-            const double fac = (err == err) ? fmax(0.2, 0.9 / root5(err)) : 0.2;
+            const double fac = (err == err) ? max2(0.2, 0.9 * inv_root5(err)) : 0.2;
             h = hh * fac;
             after_reject = true;
             land = 0;              // a landing trial that fails the error test: resume stepping, re-detect
@@ -402,7 +426,7 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
         sig = fma(hh, ssig, sig);
         tau = last ? p.tau_max : tau + hh;
         f1x = kfx[6]; f1y = kfy[6]; a1 = ka[6];
-        n2min = fmin(n2min, n2n);
+        n2min = min2(n2n, n2min);
         ++nacc;
         store_state();
         if (hist) {
@@ -418,9 +442,9 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
         // no growth right after a rejection: keeps the controller from bouncing at the kinks of the
         // interpolant (cell edges)
         const double fmx = after_reject ? 1.0 : 5.0;
-        const double fac = (err > 0.0) ? fmin(fmx, 0.9 / root5(err)) : fmx;
+        const double fac = min2(0.9 * inv_root5(err), fmx);
         after_reject = false;
-        h = fmin(hh * fac, p.hmax);
+        h = min2(hh * fac, p.hmax);
         if (on_line) { status = STOP_LINE; retire(); return false; }
         if (!inside(x, y)) { status = LEFT_DOMAIN; retire(); return false; }
         if (last) { status = TAU_MAX; retire(); return false; }
