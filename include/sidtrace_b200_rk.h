@@ -67,6 +67,10 @@ int stb_medium_destroy(stb_medium_t m);
  * the [ny+2][nx+2] spline coefficients for STB_RK_INTERP_BSPLINE (count must match). */
 int stb_medium_table(stb_medium_t m, int which, double *host_out, size_t count);
 
+#define STB_RK_F_LANE_REFILL (1u << 1) /* schedule: by default a warp owns 32 CONSECUTIVE rays at a time (neighbouring
+                                        rays of a beam share cells, so the warp's stencil loads coalesce); with
+                                        this flag every lane whose ray ended is refilled at once instead -- better
+                                        when ray order is random or a few rays take 10x the steps of the rest */
 #define STB_RK_F_HOST_IO (1u << 0)   /* every array pointer of stb_rk_t is a HOST pointer: the call stages them
                                         through HBM and returns when the results are back (synchronous) */
 

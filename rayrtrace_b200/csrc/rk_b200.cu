@@ -43,6 +43,7 @@ struct stb_medium_s {
     stbrk::Medium m{};
     int mode = 0, interp = 2;
     double *X = nullptr, *alpha = nullptr;
+    double2 *XA = nullptr;                   // {X, alpha} interleaved (only with an absorption table)
     unsigned long long *counter = nullptr;   // kCounters queue heads used round-robin
     std::atomic<unsigned> launch_seq{0};   // host threads may launch concurrently on their own streams
 };
@@ -140,17 +141,25 @@ int stb_medium_create(const stb_medium_desc_t *d, stb_medium_t *out)
         }
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
     } while (0);
+    if (e == cudaSuccess && m->alpha) {
+        const long long nt = (long long)(tbytes / sizeof(double));
+        if ((e = cudaMalloc(&m->XA, (size_t)nt * sizeof(double2))) == cudaSuccess) {
+            stbrk::interleave2_kernel<<<148 * 8, 256>>>(m->X, m->alpha, m->XA, nt);
+            stb_internal_count_launch();
+            if ((e = cudaGetLastError()) == cudaSuccess) e = cudaDeviceSynchronize();
+        }
+    }
     cudaFree(nodes); cudaFree(half); cudaFree(piv);
     if (e != cudaSuccess) {
         const int rc = fail(e == cudaErrorMemoryAllocation ? STB_ERR_NOMEM : STB_ERR_CUDA, "stb_medium_create: %s",
                             cudaGetErrorString(e));
-        cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->counter);
+        cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->XA); cudaFree(m->counter);
         delete m;
         return rc;
     }
     m->mode = d->mode;
     m->interp = d->interp;
-    m->m.X = m->X; m->m.alpha = m->alpha;
+    m->m.X = m->X; m->m.alpha = m->alpha; m->m.XA = m->XA;
     m->m.nx = d->nx; m->m.ny = d->ny;
     m->m.xorg = d->xorg; m->m.yorg = d->yorg;
     m->m.rdx = 1.0 / d->dx; m->m.rdy = 1.0 / d->dy;
@@ -174,7 +183,7 @@ int stb_medium_table(stb_medium_t m, int which, double *host_out, size_t count)
 int stb_medium_destroy(stb_medium_t m)
 {
     if (!m) return STB_OK;
-    cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->counter);
+    cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->XA); cudaFree(m->counter);
     delete m;
     return STB_OK;
 }
@@ -216,6 +225,7 @@ int stb_trace_rk(stb_medium_t m, const stb_rk_t *rk, void *stream)
     p.rtol = rk->rtol; p.atol_r = rk->atol_r; p.atol_p = rk->atol_p;
     p.h0 = rk->h0; p.hmin = rk->hmin; p.hmax = rk->hmax; p.tau_max = rk->tau_max;
     p.max_steps = rk->max_steps;
+    p.tile_sched = (rk->flags & STB_RK_F_LANE_REFILL) ? 0 : 1;
     p.stop_axis = rk->stop_axis; p.stop_val = rk->stop_val; p.stop_tol = rk->stop_tol;
     p.end_state = rk->end_state; p.tau_end = rk->tau_end; p.phi_end = rk->phi_end; p.sig_end = rk->sig_end;
     p.n2_min = rk->n2_min; p.ham_end = rk->ham_end;
