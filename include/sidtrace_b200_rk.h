@@ -67,10 +67,7 @@ int stb_medium_destroy(stb_medium_t m);
  * the [ny+2][nx+2] spline coefficients for STB_RK_INTERP_BSPLINE (count must match). */
 int stb_medium_table(stb_medium_t m, int which, double *host_out, size_t count);
 
-#define STB_RK_F_LANE_REFILL (1u << 1) /* schedule: by default a warp owns 32 CONSECUTIVE rays at a time (neighbouring
-                                        rays of a beam share cells, so the warp's stencil loads coalesce); with
-                                        this flag every lane whose ray ended is refilled at once instead -- better
-                                        when ray order is random or a few rays take 10x the steps of the rest */
+#define STB_RK_F_LANE_REFILL (1u << 1) /* same as refill_min = 1 */
 #define STB_RK_F_HOST_IO (1u << 0)   /* every array pointer of stb_rk_t is a HOST pointer: the call stages them
                                         through HBM and returns when the results are back (synchronous) */
 
@@ -87,6 +84,12 @@ typedef struct stb_rk_s {
     double h0, hmin, hmax;     /* first, smallest and largest step in tau (cm)                      */
     double tau_max;            /* stop at this tau (HUGE_VAL: never)                                */
     int32_t max_steps;         /* accepted-step cap                                                 */
+    int32_t refill_min;        /* schedule: a warp claims new rays (consecutive indices, one atomic) once this many of its */
+                               /* lanes are idle.  32 = "warp tiles": the warp owns 32 consecutive rays at a time --       */
+                               /* neighbouring rays of a beam share cells, so its stencil loads coalesce (fastest on a     */
+                               /* clean, ordered beam: 3.7 ms per 10^6 rays); 1 = lane refill (4.2 ms; best for random ray  */
+                               /* order or when a few rays take 10-100x the steps of the rest); 0 -> 24, which costs 4 %   */
+                               /* on the clean beam and never leaves more than 23 lanes waiting for a straggler            */
     int32_t stop_axis;         /* 0: none; 1: end the ray ON the line y = stop_val; 2: on x = stop_val. The step  */
                                /* that crosses the line is repeated with shorter lengths (regula falsi on the   */
                                /* step length, counted in nrej) until |coordinate - stop_val| <= stop_tol         */

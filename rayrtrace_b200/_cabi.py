@@ -125,6 +125,7 @@ class StbRk(Structure):
         ("h0", c_double), ("hmin", c_double), ("hmax", c_double),
         ("tau_max", c_double),
         ("max_steps", c_int32),
+        ("refill_min", c_int32),
         ("stop_axis", c_int32),
         ("stop_val", c_double), ("stop_tol", c_double),
         ("end_state", c_void_p),

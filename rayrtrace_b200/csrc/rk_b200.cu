@@ -201,6 +201,7 @@ int stb_trace_rk(stb_medium_t m, const stb_rk_t *rk, void *stream)
     if (!(rk->h0 > 0.0) || !(rk->hmin > 0.0) || !(rk->hmax >= rk->h0) || !(rk->h0 >= rk->hmin))
         return fail(STB_ERR_ARG, "stb_trace_rk: need 0 < hmin <= h0 <= hmax");
     if (!(rk->tau_max > 0.0)) return fail(STB_ERR_ARG, "stb_trace_rk: tau_max must be positive");
+    if (rk->refill_min < 0 || rk->refill_min > 32) return fail(STB_ERR_ARG, "stb_trace_rk: refill_min must be in [0, 32]");
     if (rk->stop_axis < 0 || rk->stop_axis > 2) return fail(STB_ERR_ARG, "stb_trace_rk: stop_axis must be 0, 1 or 2");
     if (rk->stop_axis && !(rk->stop_tol > 0.0)) return fail(STB_ERR_ARG, "stb_trace_rk: stop_tol must be positive");
     if (rk->traj && rk->L < 1) return fail(STB_ERR_ARG, "stb_trace_rk: traj needs L >= 1");
@@ -225,7 +226,7 @@ int stb_trace_rk(stb_medium_t m, const stb_rk_t *rk, void *stream)
     p.rtol = rk->rtol; p.atol_r = rk->atol_r; p.atol_p = rk->atol_p;
     p.h0 = rk->h0; p.hmin = rk->hmin; p.hmax = rk->hmax; p.tau_max = rk->tau_max;
     p.max_steps = rk->max_steps;
-    p.tile_sched = (rk->flags & STB_RK_F_LANE_REFILL) ? 0 : 1;
+    p.refill_min = (rk->flags & STB_RK_F_LANE_REFILL) ? 1 : (rk->refill_min > 0 ? rk->refill_min : 24);
     p.stop_axis = rk->stop_axis; p.stop_val = rk->stop_val; p.stop_tol = rk->stop_tol;
     p.end_state = rk->end_state; p.tau_end = rk->tau_end; p.phi_end = rk->phi_end; p.sig_end = rk->sig_end;
     p.n2_min = rk->n2_min; p.ham_end = rk->ham_end;

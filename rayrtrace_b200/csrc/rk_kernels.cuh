@@ -45,7 +45,7 @@ struct Params {
     double rtol, atol_r, atol_p;
     double h0, hmin, hmax, tau_max;
     int max_steps;
-    int tile_sched;                      // 1: a warp owns 32 consecutive rays at a time; 0: lane-granular refill
+    int refill_min;                      // idle lanes that trigger a refill: 32 = warp tiles ... 1 = lane refill
     int stop_axis;                       // 0: none, 1: stop on the line y = stop_val, 2: x = stop_val
     double stop_val, stop_tol;
     // outputs (any may be nullptr)
@@ -508,16 +508,16 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
         return true;
     };
 
-    // Persistent warps: vote, refill with one aggregated claim, step.  Two refill policies:
-    //  * warp tiles (default): refill only when every lane is idle, i.e. the warp owns 32 CONSECUTIVE rays
-    //    at a time.  Neighbouring rays of a beam sit in the same or adjacent cells, so each stencil load of
-    //    the warp touches one or two sectors instead of up to 32 (the L1 data pipe is the co-limiter of this
-    //    kernel); the price is idle lanes while the slowest ray of the tile finishes.
-    //  * lane refill: refill as soon as any lane is idle (random ray order, heavy-tailed step counts).
+    // Persistent warps: vote, claim rays for the idle lanes with one aggregated atomic once refill_min lanes are
+    // idle, step.  refill_min = 32 ("warp tiles"): the warp owns 32 CONSECUTIVE rays at a time; neighbouring rays
+    // of a beam sit in the same or adjacent cells, so each stencil load of the warp touches 4 sectors instead of 16
+    // (the L1 data pipe is the co-limiter of this kernel) -- at the price of idle lanes while the slowest ray of the
+    // tile finishes.  refill_min = 1: lane refill.  In between (default 24): most of the locality, and a straggler
+    // never holds more than refill_min - 1 lanes idle.
     bool active = false, more = true;
     for (;;) {
         unsigned act = __ballot_sync(FULL, active);
-        if (more && (p.tile_sched ? act == 0 : act != FULL)) {
+        if (more && __popc(~act) >= p.refill_min) {
             const unsigned idle = ~act;
             const int leader = __ffs(idle) - 1;
             const int want = __popc(idle);

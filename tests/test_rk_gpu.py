@@ -219,6 +219,28 @@ def test_fuzz_random_media_and_controls_bitwise(ph, rk):
         med.close()
 
 
+def test_results_do_not_depend_on_the_schedule(ph):
+    """Warp tiles (32), the default (24), lane refill (1): which warp traces a ray, and next to which
+    other rays, must not change a bit of its result -- including stragglers 40x longer than the rest."""
+    import torch
+    xs, X, alpha = _tables(with_alpha=True)
+    X[:60] = 0.0                                          # a vacuum strip along the launch line
+    n = 50_000
+    x0, y0, px, py = _beam(n, seed=3)
+    px[::97] = 0.0; py[::97] = 0.0                        # these never move: they run into the step cap
+    med = ph.Medium(X, xs, xs, alpha=alpha, interp="catmull-rom")   # local interpolant: the strip stays exactly 0
+    outs = []
+    for kw in (dict(refill_min=32), dict(), dict(lane_refill=True), dict(refill_min=7)):
+        r = _gpu(ph, med, x0, y0, px, py, rtol=1e-8, atol_r=1e-8, atol_p=1e-8, hmax=0.4, max_steps=4000, nbins=32,
+                 r_lcs=7.85, rho_max=1.5, **kw)
+        outs.append(r)
+    assert int((outs[0].status == ph.MAX_STEPS).sum()) == len(range(0, n, 97))
+    for r in outs[1:]:
+        for k in ("end_state", "tau", "phi", "sig", "n2_min", "ham", "nacc", "nrej", "status"):
+            assert torch.equal(getattr(r, k), getattr(outs[0], k)), k
+        torch.testing.assert_close(r.hist, outs[0].hist, rtol=1e-11, atol=0)
+
+
 def test_whole_warps_ending_at_launch_and_tiny_batches(ph, rk):
     xs, X, _ = _tables(101)
     d = xs[1] - xs[0]
