@@ -240,3 +240,32 @@ def refractive_index(med: Medium, x0, y0, xscale=None, yscale=None):
     z = torch.zeros_like(x0)
     res = trace_rk(med, x0, y0, z, z, xscale=xscale, yscale=yscale, max_steps=0)
     return torch.sqrt(torch.clamp(res.n2_min, min=0.0))
+
+
+def beam_to_receiver(beam, med: Medium, n_field, receiver, rnum=None, dist=None, ampbnd=None, **rk_kw):
+    """A ``rayrtrace_b200.beam.Beam`` traced with the adaptive-RK integrator instead of the reference
+    scheme: the same launch set as ``Beam.rays`` (beam.py:278-331: wavefront, equidistant start points,
+    normals, amplitudes), each ray ended ON the receiver line ``receiver = (val, 'y' | 'x')``.
+
+    Returns a dict of CUDA tensors: ``x``, ``y`` (where the ray meets the line), ``phase`` (eikonal
+    phase from the launch point, rad: the quantity ``Ray.ph`` holds at the point ``Ray.addpoint``
+    inserts, ray.py:113-224), ``amp`` (launch amplitude), ``status``.  The reference scheme's phases
+    converge to these at first order in the grid spacing."""
+    from scipy import constants as const
+    torch = _torch()
+    rnum = type(beam)._nray if rnum is None else rnum
+    dist = type(beam)._dist if dist is None else dist
+    ampbnd = type(beam)._ampbnd if ampbnd is None else ampbnd
+    wave_front = beam.wavefront_r(dist=dist, ampbnd=ampbnd, n_field=n_field)
+    n_edge = n_field.refractive_index(freq=beam.freq)
+    x, y, kx, ky, amps, _ = beam.launch_conditions(rnum, wave_front, n_edge)
+    scale = 100 if beam.length_unit == "m" else 1
+    dev = med.device
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    x0, y0, dx, dy = t(x * scale), t(y * scale), t(kx), t(ky)
+    n_loc = refractive_index(med, x0, y0)
+    res = trace_rk(med, x0, y0, (n_loc * dx).contiguous(), (n_loc * dy).contiguous(), stop=receiver, **rk_kw)
+    k0 = 2 * math.pi * beam.freq / (const.speed_of_light * 100)
+    return {"x": res.end_state[0], "y": res.end_state[1], "phase": k0 * res.phi, "amp": t(amps), "status": res.status,
+            "result": res}
+

@@ -350,3 +350,41 @@ def test_plain_c_caller_with_host_pointers(ph, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "MISMATCH" not in r.stdout and "all ok" in r.stdout
 
+
+def test_beam_receiver_phases_parity_path_converges_to_rk(ph):
+    """Closing the loop with the reference's workflow: one FT-2 beam, launch set of Beam.rays
+    (beam.py:278-331), receiver line on the far side.  Per ray, the parity path's eikonal phase at the
+    line (fused crossing output = Ray.addpoint + Ray.ph, ray.py:113-224) approaches the RK phase at
+    first order in the grid spacing; the RK phases themselves move several times less between the grids."""
+    import torch
+    from _util import ft2_density
+    from rayrtrace_b200.beam import Beam
+    from rayrtrace_b200.nfield import Nfield
+    x_ant = 2.3
+    y_ant = -float(np.sqrt(100 - x_ant ** 2))
+    worst, rk_phase, masks = [], [], []
+    for nx in (201, 401):
+        n, x, y = ft2_density(nx, 4e13)
+        nf = Nfield(n, x=x, y=y, freq=136.268e9)
+        b = Beam(x0=x_ant, y0=y_ant, kx0=0, ky0=1)
+        b.rays(rnum=101, dist=3, ampbnd=1e-3, n_field=nf, receiver=(-y_ant, "y"))
+        cs = b.bundle.result.cross_state
+        cs = cs.cpu().numpy() if hasattr(cs, "cpu") else np.asarray(cs)
+        cnt = b.bundle.result.cross_count
+        cnt = cnt.cpu().numpy() if hasattr(cnt, "cpu") else np.asarray(cnt)
+        med = ph.Medium.from_density(n, x, y, freq=136.268e9)
+        out = ph.beam_to_receiver(Beam(x0=x_ant, y0=y_ant, kx0=0, ky0=1), med, nf, (-y_ant, "y"), rnum=101, dist=3,
+                                  ampbnd=1e-3, rtol=1e-10, atol_r=1e-10, atol_p=1e-10)
+        torch.cuda.synchronize()
+        ok = (cnt == 1) & (out["status"].cpu().numpy() == ph.STOP_LINE)
+        assert ok.sum() > 60                                     # the outer rays are refracted out sideways first
+        rk_ph = out["phase"].cpu().numpy()
+        worst.append(np.abs(cs[5] - rk_ph)[ok].max())
+        assert np.abs(cs[0] - out["x"].cpu().numpy())[ok].max() < 0.1 * (201 / nx)      # crossing points, cm
+        rk_phase.append(rk_ph)
+        masks.append(ok)
+    both = masks[0] & masks[1]
+    # the FT-2 profile has a slope discontinuity at the plasma edge, which the two grids sample differently
+    print("rk phase, 201 vs 401:", np.abs(rk_phase[0] - rk_phase[1])[both].max(), "parity - rk:", worst)
+    assert np.abs(rk_phase[0] - rk_phase[1])[both].max() < 0.15
+    assert worst[0] < 2.0 and 1.35 < worst[0] / worst[1] < 2.7      # 0.69 -> 0.44 rad measured (kinked profile: below 2x)
