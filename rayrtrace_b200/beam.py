@@ -36,6 +36,7 @@ class Beam:
     _ampbnd = 0.001  # beam.py:26  relative amplitude bounding the launch area
     _gouy = 1        # beam.py:27  Gouy phase switch
     front_method = "contour"  # the reference's marching-squares finder (beam.py:225-247); or "newton"
+    _front_cache = {}         # wavefront interpolants by beam shape (see _wavefront)
 
     def __init__(self, x0=0, y0=0, kx0=0, ky0=1, freq=136.268e9, waist=0.35, focus=-1,
                  n_field=None, freq_unit="Hz", length_unit="cm"):
@@ -264,6 +265,20 @@ class Beam:
     def _wavefront(self, dist=0.003, ampbnd=0.001, n=1.):
         """Interpolant x -> y (beam coordinates) of the iso-phase line through (0, dist), sampled
         on ``_nfront`` columns out to the ``ampbnd`` amplitude level (beam.py:209-248)."""
+        # In beam coordinates the front depends on the beam's shape only, not on where the antenna
+        # stands: the 14 beams of one ft2.phases density step share it.
+        key = (self.front_method, Beam._nfront, Beam._gouy, float(self.waist), float(self.wave_len), float(dist),
+               float(ampbnd), float(np.asarray(n).reshape(-1)[0]))
+        hit = Beam._front_cache.get(key)
+        if hit is not None:
+            return hit
+        if len(Beam._front_cache) > 64:
+            Beam._front_cache.clear()
+        wf = self._wavefront_uncached(dist, ampbnd, n)
+        Beam._front_cache[key] = wf
+        return wf
+
+    def _wavefront_uncached(self, dist, ampbnd, n):
         if self.front_method == "contour":
             return self._wavefront_contour(dist, ampbnd, n)
         if self.front_method != "newton":
