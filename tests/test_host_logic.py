@@ -63,3 +63,25 @@ def test_vacuum_k_rules():
     assert kx == 0.0 and ky == pytest.approx(2 * np.pi * 136e9 / c, rel=1e-15) and f == 136e9
     kx, ky, f = _vacuum_k(3.0, 4.0, 135e9)
     assert (kx, ky) == (3.0, 4.0) and f == pytest.approx(5.0 * c / 2 / np.pi, rel=1e-15)
+
+
+def test_rk_medium_argument_validation_needs_no_device():
+    """physics.Medium rejects bad tables before any CUDA call (shape, grid uniformity, mode, interpolant)."""
+    from rayrtrace_b200 import physics
+    x = np.linspace(-1, 1, 9)
+    X = np.zeros((9, 9))
+    with pytest.raises(ValueError, match="shape"):
+        physics.Medium(np.zeros((9, 8)), x, x)
+    with pytest.raises(ValueError, match="uniform"):
+        physics.Medium(X, x ** 3, x)
+    with pytest.raises(ValueError, match="increasing"):
+        physics.Medium(X, x[::-1], x)
+    with pytest.raises(ValueError, match="mode"):
+        physics.Medium(X, x, x, mode="Z")
+    with pytest.raises(ValueError, match="interp"):
+        physics.Medium(X, x, x, interp="quintic")
+    with pytest.raises(ValueError, match="alpha"):
+        physics.Medium(X, x, x, alpha=np.zeros((3, 3)))
+    with pytest.raises(ValueError, match="2 x 2"):
+        physics.Medium(np.zeros((1, 9)), x, x[:1])
+
