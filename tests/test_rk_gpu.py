@@ -241,6 +241,23 @@ def test_results_do_not_depend_on_the_schedule(ph):
         torch.testing.assert_close(r.hist, outs[0].hist, rtol=1e-11, atol=0)
 
 
+def test_sorted_tracing_returns_the_same_results_in_the_callers_order(ph):
+    import torch
+    xs, X, alpha = _tables(with_alpha=True)
+    n = 30_000
+    x0, y0, px, py = _beam(n, seed=17)                    # random positions and angles: an incoherent set
+    x0[5] = np.nan
+    med = ph.Medium(X, xs, xs, alpha=alpha)
+    kw = dict(rtol=1e-8, atol_r=1e-8, atol_p=1e-8, hmax=0.4, L=8, aux=True, nbins=16, r_lcs=7.85, rho_max=1.5)
+    a = _gpu(ph, med, x0, y0, px, py, **kw)
+    b = _gpu(ph, med, x0, y0, px, py, sort_rays=True, **kw)
+    for k in ("end_state", "tau", "phi", "sig", "n2_min", "ham", "nacc", "nrej", "status", "traj", "aux"):
+        assert torch.equal(torch.nan_to_num(getattr(a, k).double(), nan=-7.0), torch.nan_to_num(getattr(b, k).double(), nan=-7.0)), k
+    torch.testing.assert_close(a.hist, b.hist, rtol=1e-11, atol=0)
+    order = ph.coherent_order(med, *[torch.from_numpy(v).cuda() for v in (x0, y0, px, py)])
+    assert sorted(order.tolist()) == list(range(n))
+
+
 def test_whole_warps_ending_at_launch_and_tiny_batches(ph, rk):
     xs, X, _ = _tables(101)
     d = xs[1] - xs[0]

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--lane-refill", action="store_true", help="lane-granular refill (refill_min = 1)")
     ap.add_argument("--refill-min", type=int, default=None, help="idle lanes that trigger a refill (32 = warp tiles; default 24)")
+    ap.add_argument("--sort-rays", action="store_true", help="trace in Morton order of launch cell and direction")
     ap.add_argument("--shuffled", action="store_true", help="random launch order and angles: lanes of a warp touch unrelated cells")
     args = ap.parse_args()
 
@@ -62,7 +63,7 @@ def main():
         th = th + 0.03 * x0                   # a diverging fan with a little jitter
     N = ph.refractive_index(med, x0, y0)
     px, py = (N * torch.sin(th)).contiguous(), (N * torch.cos(th)).contiguous()
-    kw = dict(rtol=args.rtol, atol_r=args.rtol, atol_p=args.rtol, hmax=0.4, lane_refill=args.lane_refill, refill_min=args.refill_min)
+    kw = dict(rtol=args.rtol, atol_r=args.rtol, atol_p=args.rtol, hmax=0.4, lane_refill=args.lane_refill, refill_min=args.refill_min, sort_rays=args.sort_rays)
     if args.absorb:
         kw.update(nbins=64, r_lcs=7.85, rho_max=2.0)
     res = ph.RkResult()
@@ -85,6 +86,7 @@ def main():
         "workload": f"{n} rays, {args.nx}^2 {args.interp} medium, {args.mode} mode, rtol {args.rtol:g}"
                     + (", absorption + 64-bin deposition" if args.absorb else "")
                     + (", shuffled launch order" if args.shuffled else ", rays ordered along the launch line")
+                    + (", traced in Morton order" if args.sort_rays else "")
                     + (", lane refill" if args.lane_refill else ", refill_min %s" % (args.refill_min or "24 (default)")),
         "ms_per_launch": ms, "accepted": acc, "rejected": rej,
         "attempts_per_s": attempts / (ms * 1e-3), "accepted_steps_per_s": acc / (ms * 1e-3),
@@ -100,7 +102,7 @@ def main():
         h = [a[:m].cpu().numpy() for a in (x0, y0, px, py)]
         cores = os.cpu_count() or 1
         ckw = dict(kw, h0=0.5 * min(med.dx, med.dy), threads=cores)
-        ckw.pop("lane_refill"); ckw.pop("refill_min")
+        ckw.pop("lane_refill"); ckw.pop("refill_min"); ckw.pop("sort_rays")
         rk.trace(om, *[a[:256] for a in h], **ckw)
         t0 = time.perf_counter()
         w = rk.trace(om, *h, **ckw)
