@@ -383,6 +383,29 @@ def run_b200(args):
         extra = {"fp64_peak_tflops_measured": tf.value, "store_bw_gbs_measured": bw.value,
                  "endpoint_mode_ray_steps_per_s": ep,
                  "endpoint_mode_fp64_frac": ep * FLOPS_PER_RAY_STEP / (tf.value * 1e12) if tf.value else None}
+        # the adaptive-RK extension (never part of the headline): 10^6 ordered rays, 1001^2 spline medium
+        from rayrtrace_b200 import physics
+        xs_m = np.linspace(-10, 10, 1001)
+        XX, YY = np.meshgrid(xs_m, xs_m)
+        med = physics.Medium(0.6 * np.exp(-2.5 * (XX ** 2 + YY ** 2) / 7.85 ** 2), xs_m, xs_m)
+        rx0 = torch.linspace(-5, 5, 1_000_000, dtype=torch.float64, device=dev)
+        ry0 = torch.full_like(rx0, -9.5)
+        rn = physics.refractive_index(med, rx0, ry0)
+        rpx, rpy = (rn * torch.sin(0.03 * rx0)).contiguous(), (rn * torch.cos(0.03 * rx0)).contiguous()
+        rres = physics.RkResult()
+        for _ in range(3):
+            physics.trace_rk(med, rx0, ry0, rpx, rpy, rtol=1e-8, atol_r=1e-8, atol_p=1e-8, hmax=0.4, out=rres)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            physics.trace_rk(med, rx0, ry0, rpx, rpy, rtol=1e-8, atol_r=1e-8, atol_p=1e-8, hmax=0.4, out=rres)
+        e1.record()
+        torch.cuda.synchronize()
+        att = int(rres.nacc.sum() + rres.nrej.sum())
+        extra["rk_extension"] = {"attempts_per_s": att * 5 / (e0.elapsed_time(e1) * 1e-3), "ms_per_launch": e0.elapsed_time(e1) / 5,
+                                 "workload": "1e6 ordered rays, 1001^2 B-spline medium, O mode, Dormand-Prince 5(4), rtol 1e-8",
+                                 "note": "extension beyond the reference (SURVEY 8 f-4); not parity, not the headline"}
+        med.close()
 
     if world > 1:
         dist.barrier()
