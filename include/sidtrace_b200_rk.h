@@ -103,6 +103,9 @@ typedef struct stb_rk_s {
     double  *ham_end;          /* [ray] H = |p|^2 - N^2 at the end state (conservation diagnostic)  */
     int32_t *nacc, *nrej;      /* [ray] accepted / rejected steps                                   */
     int32_t *status;           /* [ray] STB_RK_*                                                    */
+    int32_t *turn_index;       /* [ray] first accepted step at which p_y changed sign (turning point, the  */
+                               /* definition of stb_batch_t.turn_index), or -1                             */
+    double  *turn_state;       /* [4][nrays] (x, y, px, py) there; NaN when the ray has no turning point    */
     double  *traj;             /* [ray][L][4] accepted states, state 0 = launch; states >= L dropped*/
     double  *traj_aux;         /* [ray][L][2] (tau, sigma) of the same states                       */
     int64_t  L;

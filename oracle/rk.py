@@ -49,7 +49,7 @@ def lib():
         L.rk_oracle_prefilter.argtypes = [_dp, ctypes.c_int, ctypes.c_int, _dp]
         L.rk_oracle_batch.restype = ctypes.c_int
         L.rk_oracle_batch.argtypes = [ctypes.POINTER(_Medium), ctypes.POINTER(_Ctl), ctypes.c_longlong] + [_dp] * 7 + \
-            [_dp] * 6 + [_ip] * 3 + [_dp, _dp, ctypes.c_longlong, ctypes.c_int]
+            [_dp] * 6 + [_ip] * 3 + [_dp, _dp, ctypes.c_longlong, ctypes.c_int, _ip, _dp]
         _lib = L
     return _lib
 
@@ -120,11 +120,12 @@ def trace(med: Medium, x0, y0, px0, py0, *, rtol=1e-9, atol_r=1e-9, atol_p=1e-9,
                1.0 / r_lcs, (nbins / rho_max) if nbins else 0.0)
     end = np.empty((4, n))
     tau, phi, sig, n2min, ham = (np.empty(n) for _ in range(5))
-    nacc, nrej, status = (np.empty(n, dtype=np.int32) for _ in range(3))
+    nacc, nrej, status, turn = (np.empty(n, dtype=np.int32) for _ in range(4))
+    turn_state = np.empty((4, n))
     traj = np.full((n, L, 4), np.nan) if L else None
     auxa = np.full((n, L, 2), np.nan) if (L and aux) else None
     lib().rk_oracle_batch(ctypes.byref(med.c), ctypes.byref(ctl), n, _p(x0), _p(y0), _p(px0), _p(py0), _p(xscale),
                           _p(yscale), _p(amp), _p(end), _p(tau), _p(phi), _p(sig), _p(n2min), _p(ham), _pi(nacc), _pi(nrej),
-                          _pi(status), _p(traj), _p(auxa), int(L), int(threads))
+                          _pi(status), _p(traj), _p(auxa), int(L), int(threads), _pi(turn), _p(turn_state))
     return dict(end_state=end, tau=tau, phi=phi, sig=sig, n2_min=n2min, ham=ham, nacc=nacc, nrej=nrej, status=status,
-                traj=traj, aux=auxa, hist=hist)
+                turn_index=turn, turn_state=turn_state, traj=traj, aux=auxa, hist=hist)

@@ -43,6 +43,8 @@ typedef struct {
 typedef struct {
     double x, y, px, py, tau, phi, sig, n2min, ham;
     int nacc, nrej, status;
+    int turn;
+    double tx, ty, tpx, tpy;
 } rk_out;
 
 static const double A[6][6] = {
@@ -247,6 +249,8 @@ void rk_oracle_ray(const rk_medium *m, const rk_ctl *c, double x, double y, doub
     const double amp2 = amp * amp;
     double P = amp2;
     int nacc = 0, nrej = 0, status, after_reject = 0;
+    int turn = -1;
+    double tx = NAN, ty = NAN, tpx = NAN, tpy = NAN;
     int land = 0, side = 0;
     double hland = 0, hl = 0, dl = 0, hu = 0, du = 0;
     double f1x, f1y, a1, n2, n2min;
@@ -351,6 +355,10 @@ void rk_oracle_ray(const rk_medium *m, const rk_ctl *c, double x, double y, doub
             ssig = fma(A[5][j], ka[j], ssig);
         }
         const double xm = 0.5 * (x + xn), ym = 0.5 * (y + yn);
+        if (turn < 0 && ((py > 0.0 && pyn <= 0.0) || (py < 0.0 && pyn >= 0.0))) {
+            turn = nacc + 1;
+            tx = xn; ty = yn; tpx = pxn; tpy = pyn;
+        }
         x = xn; y = yn; px = pxn; py = pyn;
         phi = fma(hh, sphi, phi);
         sig = fma(hh, ssig, sig);
@@ -391,6 +399,7 @@ done:
         o->ham = fma(px, px, py * py) - n2e;
     }
     o->nacc = nacc; o->nrej = nrej; o->status = status;
+    o->turn = turn; o->tx = tx; o->ty = ty; o->tpx = tpx; o->tpy = tpy;
 }
 
 /* ---- batch driver (pthreads; per-thread histograms summed in thread order) ---- */
@@ -400,7 +409,8 @@ typedef struct {
     long long lo, hi, n, L;
     const double *x0, *y0, *px0, *py0, *xscale, *yscale, *amp;
     double *end_state, *tau, *phi, *sig, *n2min, *ham, *traj, *aux;
-    int32_t *nacc, *nrej, *status;
+    int32_t *nacc, *nrej, *status, *turn;
+    double *turn_state;
 } rk_job;
 
 static void *rk_worker(void *arg)
@@ -423,6 +433,11 @@ static void *rk_worker(void *arg)
         if (j->nacc) j->nacc[r] = o.nacc;
         if (j->nrej) j->nrej[r] = o.nrej;
         if (j->status) j->status[r] = o.status;
+        if (j->turn) j->turn[r] = o.turn;
+        if (j->turn_state) {
+            j->turn_state[r] = o.tx; j->turn_state[j->n + r] = o.ty;
+            j->turn_state[2 * j->n + r] = o.tpx; j->turn_state[3 * j->n + r] = o.tpy;
+        }
     }
     return NULL;
 }
@@ -430,7 +445,8 @@ static void *rk_worker(void *arg)
 int rk_oracle_batch(const rk_medium *m, const rk_ctl *c, long long n, const double *x0, const double *y0,
                     const double *px0, const double *py0, const double *xscale, const double *yscale, const double *amp,
                     double *end_state, double *tau, double *phi, double *sig, double *n2min, double *ham, int32_t *nacc,
-                    int32_t *nrej, int32_t *status, double *traj, double *aux, long long L, int nthreads)
+                    int32_t *nrej, int32_t *status, double *traj, double *aux, long long L, int nthreads, int32_t *turn,
+                    double *turn_state)
 {
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
@@ -447,6 +463,7 @@ int rk_oracle_batch(const rk_medium *m, const rk_ctl *c, long long n, const doub
         j->x0 = x0; j->y0 = y0; j->px0 = px0; j->py0 = py0; j->xscale = xscale; j->yscale = yscale; j->amp = amp;
         j->end_state = end_state; j->tau = tau; j->phi = phi; j->sig = sig; j->n2min = n2min; j->ham = ham;
         j->nacc = nacc; j->nrej = nrej; j->status = status; j->traj = traj; j->aux = aux;
+        j->turn = turn; j->turn_state = turn_state;
         if (nthreads == 1) rk_worker(j);
         else pthread_create(&th[t], NULL, rk_worker, j);
     }

@@ -131,6 +131,7 @@ class StbRk(Structure):
         ("end_state", c_void_p),
         ("tau_end", c_void_p), ("phi_end", c_void_p), ("sig_end", c_void_p), ("n2_min", c_void_p), ("ham_end", c_void_p),
         ("nacc", c_void_p), ("nrej", c_void_p), ("status", c_void_p),
+        ("turn_index", c_void_p), ("turn_state", c_void_p),
         ("traj", c_void_p), ("traj_aux", c_void_p),
         ("L", c_int64),
         ("hist", c_void_p),

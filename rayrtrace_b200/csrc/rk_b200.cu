@@ -231,6 +231,7 @@ int stb_trace_rk(stb_medium_t m, const stb_rk_t *rk, void *stream)
     p.end_state = rk->end_state; p.tau_end = rk->tau_end; p.phi_end = rk->phi_end; p.sig_end = rk->sig_end;
     p.n2_min = rk->n2_min; p.ham_end = rk->ham_end;
     p.nacc = rk->nacc; p.nrej = rk->nrej; p.status = rk->status;
+    p.turn_index = rk->turn_index; p.turn_state = rk->turn_state;
     p.traj = rk->traj; p.traj_aux = rk->traj_aux; p.L = rk->L;
     p.hist = rk->hist; p.nbins = rk->nbins;
     p.xaxis = rk->xaxis; p.yaxis = rk->yaxis;
@@ -280,6 +281,7 @@ int trace_rk_host_io(stb_medium_t m, const stb_rk_t *rk, cudaStream_t s)
     const size_t o_ham = add(nullptr, rk->ham_end, n * d8);
     const size_t o_nacc = add(nullptr, rk->nacc, n * i4), o_nrej = add(nullptr, rk->nrej, n * i4);
     const size_t o_stat = add(nullptr, rk->status, n * i4);
+    const size_t o_turn = add(nullptr, rk->turn_index, n * i4), o_tst = add(nullptr, rk->turn_state, 4 * n * d8);
     const size_t L = rk->traj ? (size_t)rk->L : 0;
     // trajectories and the histogram are read-modify-write for the caller (untouched tail, accumulation)
     const size_t o_traj = add(rk->traj, rk->traj, n * L * 4 * d8), o_aux = add(rk->traj_aux, rk->traj_aux, n * L * 2 * d8);
@@ -301,6 +303,7 @@ int trace_rk_host_io(stb_medium_t m, const stb_rk_t *rk, cudaStream_t s)
         d.end_state = (double *)at(o_end); d.tau_end = (double *)at(o_tau); d.phi_end = (double *)at(o_phi);
         d.sig_end = (double *)at(o_sig); d.n2_min = (double *)at(o_n2); d.ham_end = (double *)at(o_ham);
         d.nacc = (int32_t *)at(o_nacc); d.nrej = (int32_t *)at(o_nrej); d.status = (int32_t *)at(o_stat);
+        d.turn_index = (int32_t *)at(o_turn); d.turn_state = (double *)at(o_tst);
         d.traj = (double *)at(o_traj); d.traj_aux = (double *)at(o_aux); d.hist = (double *)at(o_hist);
         rc = stb_trace_rk(m, &d, s);
     }

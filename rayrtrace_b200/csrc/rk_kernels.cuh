@@ -52,6 +52,8 @@ struct Params {
     double *end_state;                   // [4][nrays]
     double *tau_end, *phi_end, *sig_end, *n2_min, *ham_end;
     int *nacc, *nrej, *status;
+    int *turn_index;                     // first accepted step at which p_y changed sign, or -1
+    double *turn_state;                  // [4][nrays] the state there (NaN when none)
     double *traj;                        // [ray][L][4] accepted states (state 0 = launch)
     double *traj_aux;                    // [ray][L][2] (tau, sigma)
     long long L;
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
     double &hland = s_land[threadIdx.x], &hl = s_land[kBlock + threadIdx.x], &dl = s_land[2 * kBlock + threadIdx.x];
     double &hu = s_land[3 * kBlock + threadIdx.x], &du = s_land[4 * kBlock + threadIdx.x];
     int land = 0, side = 0;
+    int turn = -1;
 
     auto inside = [&](double xx, double yy) -> bool {
         const double u = (xx - m.xorg) * m.rdx, v = (yy - m.yorg) * m.rdy;
@@ -356,6 +359,11 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
             rk_eval<INTERP, XMODE, false>(m, xs, ys, x, y, fx, fy, al, n2);
             p.ham_end[ray] = fma(px, px, py * py) - n2;
         }
+        if (p.turn_index) p.turn_index[ray] = turn;
+        if (p.turn_state && turn < 0) {
+            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+            p.turn_state[ray] = qnan; p.turn_state[n + ray] = qnan; p.turn_state[2 * n + ray] = qnan; p.turn_state[3 * n + ray] = qnan;
+        }
         if (p.nacc) p.nacc[ray] = nacc;
         if (p.nrej) p.nrej[ray] = nrej;
         if (p.status) p.status[ray] = status;
@@ -369,7 +377,7 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
         const double a = p.amp ? p.amp[r] : 1.0;
         amp2 = a * a; P = amp2;
         phi = 0.0; sig = 0.0; tau = 0.0; h = p.h0;
-        nacc = 0; nrej = 0; after_reject = false; land = 0;
+        nacc = 0; nrej = 0; after_reject = false; land = 0; turn = -1;
         double n2;
         rk_eval<INTERP, XMODE, ABSORB>(m, xs, ys, x, y, f1x, f1y, a1, n2);
         n2min = n2;
@@ -477,6 +485,15 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
 #pragma unroll
         for (int j = 1; j < 6; ++j) sphi = fma(cA[5][j], fma(kpx[j], kpx[j], kpy[j] * kpy[j]), sphi);
         const double xm = 0.5 * (x + xn), ym = 0.5 * (y + yn);
+        // turning point (the parity kernel's definition, sidtrace_b200.h turn_index): first accepted state at
+        // which p_y has changed sign; written straight to memory, it costs no register in the loop
+        if (turn < 0 && ((py > 0.0 && pyn <= 0.0) || (py < 0.0 && pyn >= 0.0))) {
+            turn = nacc + 1;
+            if (p.turn_state) {
+                const long long nn = p.nrays;
+                p.turn_state[ray] = xn; p.turn_state[nn + ray] = yn; p.turn_state[2 * nn + ray] = pxn; p.turn_state[3 * nn + ray] = pyn;
+            }
+        }
         x = xn; y = yn; px = pxn; py = pyn;
         phi = fma(hh, sphi, phi);
         sig = fma(hh, ssig, sig);

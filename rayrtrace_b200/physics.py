@@ -117,7 +117,8 @@ class Medium:
 
 
 class RkResult:
-    __slots__ = ("end_state", "tau", "phi", "sig", "n2_min", "ham", "nacc", "nrej", "status", "traj", "aux", "hist")
+    __slots__ = ("end_state", "tau", "phi", "sig", "n2_min", "ham", "nacc", "nrej", "status", "turn_index",
+                 "turn_state", "traj", "aux", "hist")
 
     def __init__(self):
         for s in self.__slots__:
@@ -169,7 +170,7 @@ def trace_rk(med: Medium, x0, y0, px0, py0, *, rtol: float = 1e-9, atol_r: float
             if v is None or name == "hist":
                 setattr(res, name, v if getattr(res, name) is None or name == "hist" else getattr(res, name))
                 continue
-            v = v.index_select(1 if name == "end_state" else 0, inv)
+            v = v.index_select(1 if name in ("end_state", "turn_state") else 0, inv)
             cur = getattr(res, name)
             if cur is not None and cur.shape == v.shape:
                 cur.copy_(v)
@@ -207,6 +208,8 @@ def trace_rk(med: Medium, x0, y0, px0, py0, *, rtol: float = 1e-9, atol_r: float
     if diagnostics:
         for name in ("tau", "phi", "sig", "n2_min", "ham"):
             need(name, (n,), torch.float64)
+        need("turn_index", (n,), torch.int32)
+        need("turn_state", (4, n), torch.float64)
     if L:
         if res.traj is None:
             res.traj = torch.full((n, L, 4), math.nan, dtype=torch.float64, device=dev)
@@ -241,6 +244,7 @@ def trace_rk(med: Medium, x0, y0, px0, py0, *, rtol: float = 1e-9, atol_r: float
     if diagnostics:
         k.tau_end, k.phi_end, k.sig_end = res.tau.data_ptr(), res.phi.data_ptr(), res.sig.data_ptr()
         k.n2_min, k.ham_end = res.n2_min.data_ptr(), res.ham.data_ptr()
+        k.turn_index, k.turn_state = res.turn_index.data_ptr(), res.turn_state.data_ptr()
     if L:
         k.traj = res.traj.data_ptr()
         k.traj_aux = res.aux.data_ptr() if res.aux is not None else None

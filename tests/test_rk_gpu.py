@@ -59,10 +59,11 @@ def _gpu(ph, med, x0, y0, px, py, **kw):
     return res
 
 
-def _same(res, want, keys=("end_state", "tau", "phi", "sig", "n2_min", "ham", "nacc", "nrej", "status")):
+def _same(res, want, keys=("end_state", "tau", "phi", "sig", "n2_min", "ham", "nacc", "nrej", "status", "turn_index")):
     for k in keys:
         got = getattr(res, k).cpu().numpy()
         assert got.tobytes() == want[k].tobytes(), (k, np.flatnonzero((got != want[k]).reshape(-1))[:5])
+    assert np.array_equal(res.turn_state.cpu().numpy(), want["turn_state"], equal_nan=True)
 
 
 INTERP_ID = {"bilinear": 0, "catmull-rom": 1, "bspline": 2}
@@ -207,7 +208,7 @@ def test_fuzz_random_media_and_controls_bitwise(ph, rk):
         om = rk.Medium(X, med.xorg, med.yorg, med.dx, med.dy, alpha=alpha, mode=mode, Y0=med.Y0, R0=med.R0, interp=INTERP_ID[interp])
         want = rk.trace(om, x0, y0, pm * np.cos(th), pm * np.sin(th), L=L, aux=res.aux is not None, threads=4, **kw, **per_ray, **hist)
         ctx = (it, nx, ny, n, mode, interp, absorb, kw, L)
-        for k in ("nacc", "nrej", "status", "tau", "phi", "sig", "n2_min", "end_state", "ham"):
+        for k in ("nacc", "nrej", "status", "tau", "phi", "sig", "n2_min", "end_state", "ham", "turn_index", "turn_state"):
             got = getattr(res, k).cpu().numpy()
             # NaN launch states propagate NaNs whose payload/sign may differ between CPU and GPU: compare as values
             assert np.array_equal(got, want[k], equal_nan=True), (k, ctx)
@@ -236,8 +237,9 @@ def test_results_do_not_depend_on_the_schedule(ph):
         outs.append(r)
     assert int((outs[0].status == ph.MAX_STEPS).sum()) == len(range(0, n, 97))
     for r in outs[1:]:
-        for k in ("end_state", "tau", "phi", "sig", "n2_min", "ham", "nacc", "nrej", "status"):
+        for k in ("end_state", "tau", "phi", "sig", "n2_min", "ham", "nacc", "nrej", "status", "turn_index"):
             assert torch.equal(getattr(r, k), getattr(outs[0], k)), k
+        assert torch.equal(torch.nan_to_num(r.turn_state, nan=-7.0), torch.nan_to_num(outs[0].turn_state, nan=-7.0))
         torch.testing.assert_close(r.hist, outs[0].hist, rtol=1e-11, atol=0)
 
 
@@ -251,7 +253,7 @@ def test_sorted_tracing_returns_the_same_results_in_the_callers_order(ph):
     kw = dict(rtol=1e-8, atol_r=1e-8, atol_p=1e-8, hmax=0.4, L=8, aux=True, nbins=16, r_lcs=7.85, rho_max=1.5)
     a = _gpu(ph, med, x0, y0, px, py, **kw)
     b = _gpu(ph, med, x0, y0, px, py, sort_rays=True, **kw)
-    for k in ("end_state", "tau", "phi", "sig", "n2_min", "ham", "nacc", "nrej", "status", "traj", "aux"):
+    for k in ("end_state", "tau", "phi", "sig", "n2_min", "ham", "nacc", "nrej", "status", "traj", "aux", "turn_index", "turn_state"):
         assert torch.equal(torch.nan_to_num(getattr(a, k).double(), nan=-7.0), torch.nan_to_num(getattr(b, k).double(), nan=-7.0)), k
     torch.testing.assert_close(a.hist, b.hist, rtol=1e-11, atol=0)
     order = ph.coherent_order(med, *[torch.from_numpy(v).cuda() for v in (x0, y0, px, py)])

@@ -268,6 +268,31 @@ def test_upper_hybrid_resonance_retires_with_step_underflow():
     assert abs(r["end_state"][2, 0]) > 30          # |p| = N blows up
 
 
+def test_turning_point_of_a_reflected_ray():
+    """X = 0.2 + 0.08 (y + 10): p_y falls linearly, the ray turns at y0 + p_y0^2 / b; turn_index is the
+    first accepted state with p_y <= 0 (the parity kernel's definition), turn_state that state."""
+    xs, d = grid(201)
+    b = 0.08
+    X = np.tile((0.2 + b * (xs + 10))[:, None], (1, 201))
+    m = rk.Medium(X, xs[0], xs[0], d, d)
+    y0 = -9.0
+    N = np.sqrt(1 - (0.2 + b * (y0 + 10)))
+    th = np.array([0.0, 0.3, 0.6])
+    r = rk.trace(m, np.full(3, -2.0), np.full(3, y0), N * np.sin(th), N * np.cos(th), hmax=0.2, L=2000)
+    y_turn = y0 + (N * np.cos(th)) ** 2 / b
+    assert np.all(r["turn_index"] > 0) and np.all(r["status"] == rk.LEFT_DOMAIN)
+    for i in range(3):
+        k = r["turn_index"][i]
+        np.testing.assert_array_equal(r["turn_state"][:, i], r["traj"][i, k])
+        assert r["traj"][i, k - 1, 3] > 0 >= r["traj"][i, k, 3]
+        assert abs(r["turn_state"][1, i] - y_turn[i]) < 0.02
+        assert r["traj"][i, :r["nacc"][i] + 1, 1].max() == pytest.approx(y_turn[i], abs=0.01)
+    # a ray through vacuum never turns
+    vac = rk.Medium(np.zeros((201, 201)), xs[0], xs[0], d, d)
+    r = rk.trace(vac, [0.0], [-9.0], [0.1], [0.9])
+    assert r["turn_index"][0] == -1 and np.all(np.isnan(r["turn_state"][:, 0]))
+
+
 def test_status_codes():
     m, X, xs, d = gaussian_medium()
     r = rk.trace(m, [-3.0, -3.0, 11.0, -3.0], [-9.5, -9.5, 0.0, -9.5], [0, 0, 1.0, 0], [1.0, 1.0, 0, 1.0],
