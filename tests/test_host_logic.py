@@ -85,3 +85,25 @@ def test_rk_medium_argument_validation_needs_no_device():
     with pytest.raises(ValueError, match="2 x 2"):
         physics.Medium(np.zeros((1, 9)), x, x[:1])
 
+
+def test_coherent_order_groups_neighbouring_rays():
+    """physics.coherent_order (host logic, plain torch): a permutation; rays that share launch cell and
+    direction end up next to each other; NaN / out-of-table launches do not break it."""
+    import types
+    import torch
+    from rayrtrace_b200 import physics
+    med = types.SimpleNamespace(xorg=-10.0, yorg=-10.0, dx=0.02, dy=0.02, nx=1001, ny=1001)
+    g = torch.Generator().manual_seed(0)
+    n = 20000
+    x0 = (torch.rand(n, generator=g, dtype=torch.float64) - 0.5) * 10
+    y0 = torch.full_like(x0, -9.5)
+    th = (torch.rand(n, generator=g, dtype=torch.float64) - 0.5) * 0.6
+    x0[3] = float("nan"); x0[4] = 1e30; y0[5] = -1e30
+    perm = physics.coherent_order(med, x0, y0, torch.sin(th), torch.cos(th))
+    assert sorted(perm.tolist()) == list(range(n))
+    keep = torch.isfinite(x0[perm]) & (x0[perm].abs() < 100) & (y0[perm].abs() < 100)
+    xs, ts = x0[perm][keep], th[perm][keep]
+    jump = ((xs[1:] - xs[:-1]).abs() / 10 + (ts[1:] - ts[:-1]).abs() / 0.6)
+    rnd = ((x0[1:] - x0[:-1]).abs() / 10 + (th[1:] - th[:-1]).abs() / 0.6)[torch.isfinite(x0[1:]) & torch.isfinite(x0[:-1])]
+    assert jump.median() < 0.05 * rnd.median()
+
