@@ -31,6 +31,11 @@ def ft2_fan():
 
 
 @pytest.fixture(scope="session")
+def rxyten_fan():
+    return np.load(os.path.join(GOLDEN, "rxyten_fan.npz"))
+
+
+@pytest.fixture(scope="session")
 def oracle_mod():
     import oracle
     oracle.port()   # builds libsidtrace_oracle.so on demand (gcc only)

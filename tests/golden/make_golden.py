@@ -165,6 +165,46 @@ def make_ft2_fan(den):
     np.savez_compressed(os.path.join(HERE, "ft2_fan.npz"), **out)
 
 
+def make_rxyten_fan(den):
+    """BASELINE config 3's density kind: shaped flux surfaces from the reference's own parameterisation
+    (rxyten_from_params, den.py:458-485: Shafranov shift, triangularity, elongation), mapped to a
+    Cartesian grid by RXYTEN.on_grid with 2-D meshgrids (den.py:169-230), NaNs outside the last surface
+    filled with the edge density, then den.Nfield and a 64-ray fan through the compiled reference.
+    The density grid itself is stored (97^2): the parameterisation is host prep outside the hot path."""
+    ref = oracle.ref()
+    rx, rlcs, _ = den.rxyten_from_params(shifx=0.3, delta=0.5, trian=0.1, elon=1.2, num=60)
+    rx.den = 2.6e14 * np.maximum(0.0, 1 - (rx.r / abs(rlcs)) ** 2) + 1e12
+    nx = 97
+    x = np.linspace(-10, 10, nx)
+    XX, YY = np.meshgrid(x, x)
+    n = np.array(rx.on_grid(x=XX, y=YY)[0], dtype=np.float64)
+    n[np.isnan(n)] = 1e12
+    nf = den.Nfield(n, x=x, y=x)
+    rng = np.random.default_rng(77)
+    nray, L = 64, 4096
+    freq = 136.268e9
+    k0 = 2 * np.pi * freq / (299792458.0 * 100) * float(nf.refractive_index(freq=freq))
+    xs = rng.uniform(-5.0, 5.0, nray)
+    ang = rng.uniform(-0.3, 0.3, nray)
+    xg0 = np.asarray(nf.x2grid(xs), np.float64)
+    yg0 = np.full(nray, float(nf.y2grid(-9.5)))
+    kx0, ky0 = k0 * np.sin(ang), k0 * np.cos(ang)
+    nst = np.zeros(nray, np.int64)
+    end = np.zeros((4, nray))
+    dig = []
+    for r in range(nray):
+        i, gx, gy, gkx, gky = run_ref_trace(ref, L, xg0[r], yg0[r], kx0[r], ky0[r], nf.st, nf.dx[0], nf.dy[0],
+                                            nf.nx, nf.ny, nf.ax, nf.ay)
+        nst[r] = i
+        end[:, r] = gx[i], gy[i], gkx[i], gky[i]
+        dig.append(sha(np.stack([gx[:i + 1], gy[:i + 1], gkx[:i + 1], gky[:i + 1]], 1)))
+    np.savez_compressed(os.path.join(HERE, "rxyten_fan.npz"), nx=np.int64(nx), density=n, x=x, rlcs=np.float64(rlcs),
+                        st=np.float64(nf.st), ax_sha=sha(nf.ax), ay_sha=sha(nf.ay), xg0=xg0, yg0=yg0, kx0=kx0, ky0=ky0,
+                        nsteps=nst, end=end, traj_sha=np.array(dig), L=np.int64(L))
+    print("rxyten_fan: rlcs", float(rlcs), "steps min/median/max", nst.min(), int(np.median(nst)), nst.max(),
+          "reflected", int((end[3] < 0).sum()), "density asymmetry", float(np.abs(n - n[:, ::-1]).max() / n.max()))
+
+
 def make_ft2_cross(den, ray):
     """Reference Ray.addpoint (ray.py:131-224) on a 40-ray fan through the over-dense profile:
     what it returns for receiver lines y = 9, -2, -9 and x = 5 (first crossing)."""
@@ -270,8 +310,9 @@ if __name__ == "__main__":
     make_kat(oracle.ref())
     make_ft2_ray(den, ray)
     make_ft2_fan(den)
+    make_rxyten_fan(den)
     make_ft2_cross(den, ray)
     make_beam(den)
     make_ft2_phases()
-    for f in ("kat.npz", "ft2_ray.npz", "ft2_fan.npz", "ft2_cross.npz", "beam.npz", "ft2_phases.npz"):
+    for f in ("kat.npz", "ft2_ray.npz", "ft2_fan.npz", "rxyten_fan.npz", "ft2_cross.npz", "beam.npz", "ft2_phases.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

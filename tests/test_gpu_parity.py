@@ -156,6 +156,24 @@ def test_fan_fixture_bitwise(st, torch_mod, ft2_fan, tag, div_ieee, refill, devi
         assert not traj[r, nsteps[r] + 1:].any()
 
 
+@pytest.mark.parametrize("tiled", [False, True])
+def test_shaped_density_fan_bitwise(st, torch_mod, rxyten_fan, tiled):
+    """The fan through the shaped (shifted / elongated / triangular) density that the reference's own
+    rxyten_from_params + on_grid produced (tests/golden/make_golden.py): step counts, end states and
+    every trajectory equal to the compiled reference's."""
+    from rayrtrace_b200.nfield import Nfield
+    x = rxyten_fan["x"]
+    nf = Nfield(np.ascontiguousarray(rxyten_fan["density"]), x=x, y=x)
+    ins = [np.ascontiguousarray(rxyten_fan[k]) for k in ("xg0", "yg0", "kx0", "ky0")]
+    res = st.trace_batch(nf.device_field(), *ins, L=int(rxyten_fan["L"]), st=nf.st, dx=nf.dx[0], dy=nf.dy[0], traj=True,
+                         want_extras=True, tiled=tiled)
+    torch_mod.cuda.synchronize()
+    assert np.array_equal(res.nsteps, rxyten_fan["nsteps"])
+    assert res.end_state.tobytes() == rxyten_fan["end"].tobytes()
+    assert np.array_equal(traj_digest(res.traj_ray_major().cpu().numpy(), res.nsteps), rxyten_fan["traj_sha"])
+    assert int((np.asarray(res.turn_index) >= 0).sum()) >= 16          # the reflected rays have a turning point
+
+
 def _oracle_vs_gpu(st, oracle, rng, nx, ny, nrays, L, *, stp=0.37, dx=0.8, dy=1.3, st_ray=None, **kw):
     ax, ay = random_field(rng, nx, ny)
     x0, y0, kx0, ky0 = random_launch(rng, nrays, nx, ny)
