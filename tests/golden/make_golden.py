@@ -298,9 +298,14 @@ def make_ft2_phases():
     n, x, y = ft2_density(nx, 4e13)
     a_set = np.array([0.0, 0.6, 1.0])
     ph_max, ph_sig = refft2.phases(n, x, y, a_set=a_set, nray=41)
+    # strongly refracting plasmas (peak density 0.52 and 0.78 of critical): bent, partly folded beams.
+    # (At a = 5.5 the reference itself fails with an IndexError in field_r; not a fixture.)
+    dense = np.array([3.0, 4.5])
+    dph_max, dph_sig = refft2.phases(n, x, y, a_set=dense, nray=41)
     np.savez_compressed(os.path.join(HERE, "ft2_phases.npz"), nx=np.int64(nx), n0=4e13, a_set=a_set, nray=np.int64(41),
-                        ph_by_max=ph_max, ph_by_sig=ph_sig)
-    print("ft2_phases: ph_by_sig[a=1] =", np.round(ph_sig[-1], 4))
+                        ph_by_max=ph_max, ph_by_sig=ph_sig, dense_a_set=dense, dense_ph_by_max=dph_max,
+                        dense_ph_by_sig=dph_sig)
+    print("ft2_phases: ph_by_sig[a=1] =", np.round(ph_sig[-1], 4), " dense[a=4.5] =", np.round(dph_sig[-1], 4))
 
 
 if __name__ == "__main__":

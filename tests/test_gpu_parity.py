@@ -615,6 +615,18 @@ def test_ft2_phases_driver_matches_reference(st, ft2_phases_fix):
         np.testing.assert_allclose(ph_max, ft2_phases_fix["ph_by_max"], rtol=1e-6)
 
 
+def test_ft2_phases_driver_matches_reference_in_dense_plasmas(st, ft2_phases_fix):
+    """The same driver at peak densities of 0.52 and 0.78 of critical: strongly bent, partly folded
+    beams (several 'pages' in field_r, rays missing the receiver)."""
+    from rayrtrace_b200 import ft2
+    n, x, y = ft2_density(int(ft2_phases_fix["nx"]), float(ft2_phases_fix["n0"]))
+    for device in (True, False):
+        ph_max, ph_sig = ft2.phases(n, x, y, a_set=ft2_phases_fix["dense_a_set"], nray=int(ft2_phases_fix["nray"]), device=device)
+        d = np.angle(np.exp(1j * (ph_sig - ft2_phases_fix["dense_ph_by_sig"])))
+        assert np.abs(d).max() < 1e-5, (device, d)
+        np.testing.assert_allclose(ph_max, ft2_phases_fix["dense_ph_by_max"], rtol=1e-6)
+
+
 def test_cap_at_reference_maxstep(st, oracle_mod):
     """A ray that never leaves the grid stops at the cap exactly like the reference at
     Ray.MaxStep = 100000 (ray.py:11, sidtracemodule.c:36): i = L-1 = 99999, state L-1 written."""
