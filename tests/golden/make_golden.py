@@ -279,7 +279,19 @@ def make_beam(den):
     # analytic pieces at a few points
     px = np.linspace(-1.5, 4.0, 7); py = np.linspace(-9.0, -4.0, 7)
     fs = tx.field(x=px, y=py, n=0.97, outfmt="dict")
-    np.savez_compressed(os.path.join(HERE, "beam.npz"), nx=np.int64(nx), n0=n0, x0=x0, y0=y0, rnum=np.int64(rnum),
+    # tilted launches (the launch-angle axis of BASELINE config 4, Beam.k0 setter beam.py:96-100)
+    tilt = {}
+    for tag, th in (("tiltp", 0.12), ("tiltm", -0.2)):
+        t2 = refbeam.Beam(x0=x0, y0=y0, kx0=0, ky0=1)
+        t2.k0 = (np.sin(th), np.cos(th))
+        r2 = refbeam.Beam(x0=x0, y0=-y0, kx0=0, ky0=-1)
+        l2 = t2.rays(rnum=61, dist=3, ampbnd=1e-3, n_field=nf)
+        nk2 = np.array([len(r.x) for r in t2._rays])          # before field_r inserts the receiver points
+        f2, xo2, xm2, pm2, sg2, _ = refbeam.field_result(t2, r2)
+        tilt.update({f"{tag}_angle": th, f"{tag}_launch": np.stack(l2[:6]), f"{tag}_nkept": nk2,
+                     f"{tag}_field": f2, f"{tag}_xout": xo2, f"{tag}_x_max": xm2, f"{tag}_ph_max": np.float64(pm2),
+                     f"{tag}_signal": np.complex128(sg2)})
+    np.savez_compressed(os.path.join(HERE, "beam.npz"), nx=np.int64(nx), n0=n0, x0=x0, y0=y0, rnum=np.int64(rnum), **tilt,
                         wf_x=wf.x, wf_y=wf.y, launch=np.stack([lx, ly, lkx, lky, amps, phase]), nkept=nkept,
                         field=field, xout=xo, x_max=x_max, ph_max=np.float64(ph_max), signal=np.complex128(signal),
                         props=np.array(props if props is not None else [np.nan] * 3),
