@@ -291,6 +291,16 @@ def make_beam(den):
         tilt.update({f"{tag}_angle": th, f"{tag}_launch": np.stack(l2[:6]), f"{tag}_nkept": nk2,
                      f"{tag}_field": f2, f"{tag}_xout": xo2, f"{tag}_x_max": xm2, f"{tag}_ph_max": np.float64(pm2),
                      f"{tag}_signal": np.complex128(sg2)})
+    # other probing frequencies (the frequency axis of BASELINE config 4): field, step and beam all at f
+    for tag, f in (("f100", 100e9), ("f160", 160e9)):
+        nff = den.Nfield(n, x=x, y=y, freq=f)
+        t2 = refbeam.Beam(x0=x0, y0=y0, kx0=0, ky0=1, freq=f)
+        r2 = refbeam.Beam(x0=x0, y0=-y0, kx0=0, ky0=-1, freq=f)
+        l2 = t2.rays(rnum=61, dist=3, ampbnd=1e-3, n_field=nff)
+        nk2 = np.array([len(r.x) for r in t2._rays])
+        f2, xo2, xm2, pm2, sg2, _ = refbeam.field_result(t2, r2)
+        tilt.update({f"{tag}_freq": f, f"{tag}_st": np.float64(nff.st), f"{tag}_launch": np.stack(l2[:6]), f"{tag}_nkept": nk2,
+                     f"{tag}_x_max": xm2, f"{tag}_ph_max": np.float64(pm2), f"{tag}_signal": np.complex128(sg2)})
     np.savez_compressed(os.path.join(HERE, "beam.npz"), nx=np.int64(nx), n0=n0, x0=x0, y0=y0, rnum=np.int64(rnum), **tilt,
                         wf_x=wf.x, wf_y=wf.y, launch=np.stack([lx, ly, lkx, lky, amps, phase]), nkept=nkept,
                         field=field, xout=xo, x_max=x_max, ph_max=np.float64(ph_max), signal=np.complex128(signal),

@@ -624,6 +624,28 @@ def test_tilted_beam_matches_reference(st, beam_fix, tag):
         assert x_max == pytest.approx(float(beam_fix[f"{tag}_x_max"]), rel=1e-6, abs=1e-8)
 
 
+@pytest.mark.parametrize("tag", ["f100", "f160"])
+def test_other_probing_frequencies_match_reference(st, beam_fix, tag):
+    """Frequency axis of BASELINE config 4: field (den.py:84-107), step and beam at 100 and 160 GHz."""
+    from rayrtrace_b200.beam import Beam, field_result
+    from rayrtrace_b200.nfield import Nfield
+    n, x, y = ft2_density(int(beam_fix["nx"]), float(beam_fix["n0"]))
+    f = float(beam_fix[f"{tag}_freq"])
+    nf = Nfield(n, x=x, y=y, freq=f)
+    assert float(nf.st) == float(beam_fix[f"{tag}_st"])
+    x0, y0 = float(beam_fix["x0"]), float(beam_fix["y0"])
+    for device in (False, True):
+        tx = Beam(x0=x0, y0=y0, kx0=0, ky0=1, freq=f)
+        rx = Beam(x0=x0, y0=-y0, kx0=0, ky0=-1, freq=f)
+        out = tx.rays(rnum=61, dist=3, ampbnd=1e-3, n_field=nf, receiver=(-y0, "y") if device else None)
+        np.testing.assert_allclose(np.stack(out[:6]), beam_fix[f"{tag}_launch"], rtol=1e-12, atol=1e-12)
+        assert np.array_equal(tx.bundle.nsteps, beam_fix[f"{tag}_nkept"])
+        _, _, x_max, ph_max, signal, _ = field_result(tx, rx, device=device)
+        want = complex(beam_fix[f"{tag}_signal"])
+        assert abs(signal - want) < 1e-6 * abs(want), device
+        assert float(ph_max) == pytest.approx(float(beam_fix[f"{tag}_ph_max"]), rel=1e-8)
+
+
 def test_ft2_phases_driver_matches_reference(st, ft2_phases_fix):
     """Top of the reference's call stack (ft2.phases, ft2.py:25-71): density scan x seven TX/RX
     antenna pairs -> interferometer phases, every ray traced on the GPU through the batched Beam.
