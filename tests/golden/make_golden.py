@@ -107,8 +107,16 @@ def make_ft2_ray(den, ray):
     i, gx, gy, gkx, gky = run_ref_trace(ref, L, xg0, yg0, kx0, ky0, nf.st, nf.dx[0], nf.dy[0], nf.nx, nf.ny, nf.ax, nf.ay)
     assert i == len(rc.x)
     assert np.array_equal(gkx[:i], rc.kx) and np.array_equal(gky[:i], rc.ky), "launch-state restatement differs from Ray"
+    # the class-level step multiplier (ray.py:12, :75): the same ray with Ray.kStep = 2 and 0.5
+    ks = {}
+    for tag, kstep in (("k2", 2), ("khalf", 0.5)):
+        ray.Ray.kStep = kstep
+        rk = ray.Ray(-3.0, -9.5, 0, 1, freq, 1, n_field=nf)
+        ks.update({f"{tag}_kstep": np.float64(kstep), f"{tag}_n": np.int64(len(rk.x)), f"{tag}_x": rk.x, f"{tag}_y": rk.y,
+                   f"{tag}_ph_end": np.float64(rk.ph[-1]), f"{tag}_st0": np.float64(rk.st[0])})
+    ray.Ray.kStep = 1
     np.savez_compressed(
-        os.path.join(HERE, "ft2_ray.npz"),
+        os.path.join(HERE, "ft2_ray.npz"), **ks,
         nx=np.int64(nx), n0=4e13, edge=1e12, r_dia=7.85, half=10.0,
         field_freq=136.26e9, freq=freq, x0=-3.0, y0=-9.5,
         st=np.float64(nf.st), dx0=np.float64(nf.dx[0]), dy0=np.float64(nf.dy[0]),

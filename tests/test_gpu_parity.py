@@ -106,6 +106,28 @@ def test_reference_ray_fixture_through_product_ray(st, ft2_ray):
     assert r.st[-1] == 0 and r.st[0] == float(ft2_ray["st"])
 
 
+@pytest.mark.parametrize("tag", ["k2", "khalf"])
+def test_class_level_step_multiplier(st, ft2_ray, tag):
+    """Ray.kStep (ray.py:12, :75: st = n_field.st * Ray.kStep) is honoured by Ray and by trace_rays."""
+    from rayrtrace_b200.nfield import Nfield
+    from rayrtrace_b200.ray import Ray, trace_rays
+    n, x, y = ft2_density(int(ft2_ray["nx"]), float(ft2_ray["n0"]))
+    nf = Nfield(n, x=x, y=y)
+    Ray.kStep = float(ft2_ray[f"{tag}_kstep"])
+    try:
+        r = Ray(float(ft2_ray["x0"]), float(ft2_ray["y0"]), 0, 1, float(ft2_ray["freq"]), 1, n_field=nf)
+        b = trace_rays(nf, [float(ft2_ray["x0"])], [float(ft2_ray["y0"])], [0.0], [1.0], float(ft2_ray["freq"]))
+    finally:
+        Ray.kStep = 1
+    assert len(r.x) == int(ft2_ray[f"{tag}_n"]) == int(b.nsteps[0])
+    assert r.st[0] == float(ft2_ray[f"{tag}_st0"])
+    np.testing.assert_allclose(r.x, ft2_ray[f"{tag}_x"], rtol=1e-9)
+    np.testing.assert_allclose(r.y, ft2_ray[f"{tag}_y"], rtol=1e-9)
+    assert r.ph[-1] == pytest.approx(float(ft2_ray[f"{tag}_ph_end"]), rel=1e-9)
+    rb = b.ray(0)
+    np.testing.assert_allclose(rb.x, ft2_ray[f"{tag}_x"], rtol=1e-9)
+
+
 def test_reference_ray_fixture_exact_launch_bitwise(st, ft2_ray):
     """Same ray fed the reference's exact launch state: the whole trajectory is bit-identical."""
     from rayrtrace_b200.nfield import Nfield
