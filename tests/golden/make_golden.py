@@ -299,6 +299,12 @@ def make_beam(den):
         tilt.update({f"{tag}_angle": th, f"{tag}_launch": np.stack(l2[:6]), f"{tag}_nkept": nk2,
                      f"{tag}_field": f2, f"{tag}_xout": xo2, f"{tag}_x_max": xm2, f"{tag}_ph_max": np.float64(pm2),
                      f"{tag}_signal": np.complex128(sg2)})
+    # class-level switches of the wavefront finder (beam.py:23, :27): no Gouy phase, a coarser phase map
+    for tag, gouy, nfront in (("gouy0", 0, 1000), ("nfront500", 1, 500)):
+        refbeam.Beam._gouy, refbeam.Beam._nfront = gouy, nfront
+        w2 = refbeam.Beam(x0=x0, y0=y0, kx0=0, ky0=1).wavefront_r(dist=3, ampbnd=1e-3, n_field=nf)
+        tilt.update({f"{tag}_wf_x": w2.x, f"{tag}_wf_y": w2.y})
+    refbeam.Beam._gouy, refbeam.Beam._nfront = 1, 1000
     # other probing frequencies (the frequency axis of BASELINE config 4): field, step and beam all at f
     for tag, f in (("f100", 100e9), ("f160", 160e9)):
         nff = den.Nfield(n, x=x, y=y, freq=f)

@@ -48,6 +48,21 @@ def test_wavefront_matches_the_reference_finder(beam_fix):
         assert fast.x.tobytes() == full.x.tobytes() and fast.y.tobytes() == full.y.tobytes()
 
 
+@pytest.mark.parametrize("tag, gouy, nfront", [("gouy0", 0, 1000), ("nfront500", 1, 500)])
+def test_wavefront_class_switches_match_reference(beam_fix, tag, gouy, nfront):
+    """Beam._gouy and Beam._nfront (beam.py:23, :27) are class-level settings the finder must honour."""
+    from rayrtrace_b200.beam import Beam
+    n, x, y = ft2_density(int(beam_fix["nx"]), float(beam_fix["n0"]))
+    nf = Nfield(n, x=x, y=y)
+    Beam._gouy, Beam._nfront = gouy, nfront
+    try:
+        wf = _beam(beam_fix).wavefront_r(dist=3, ampbnd=1e-3, n_field=nf)
+    finally:
+        Beam._gouy, Beam._nfront = 1, 1000
+    assert wf.x.tobytes() == beam_fix[f"{tag}_wf_x"].tobytes()
+    assert wf.y.tobytes() == beam_fix[f"{tag}_wf_y"].tobytes()
+
+
 def test_newton_front_is_the_exact_iso_phase_line(beam_fix):
     """front_method='newton': constant phase to 1e-9 rad, through (0, dist), within the
     marching-squares interpolation error (~1e-6 cm) of the reference's front."""
