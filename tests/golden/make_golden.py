@@ -299,6 +299,11 @@ def make_beam(den):
         tilt.update({f"{tag}_angle": th, f"{tag}_launch": np.stack(l2[:6]), f"{tag}_nkept": nk2,
                      f"{tag}_field": f2, f"{tag}_xout": xo2, f"{tag}_x_max": xm2, f"{tag}_ph_max": np.float64(pm2),
                      f"{tag}_signal": np.complex128(sg2)})
+    # ray counts that exercise the fine-grid normals of Beam.rays (beam.py:306-326, M = lcm(rnum, 1000)):
+    # coprime (7 -> M = 7000), a divisor (250 -> stride 4), equal (1000 -> stride 1)
+    for rn in (7, 250, 1000):
+        t3 = refbeam.Beam(x0=x0, y0=y0, kx0=0, ky0=1)
+        tilt[f"launch_r{rn}"] = np.stack(t3.rays(rnum=rn, dist=3, ampbnd=1e-3, n_field=nf)[:6])
     # class-level switches of the wavefront finder (beam.py:23, :27): no Gouy phase, a coarser phase map
     for tag, gouy, nfront in (("gouy0", 0, 1000), ("nfront500", 1, 500)):
         refbeam.Beam._gouy, refbeam.Beam._nfront = gouy, nfront

@@ -93,6 +93,20 @@ def test_launch_conditions_match_reference_beam_rays(beam_fix):
         np.testing.assert_allclose(g, w, rtol=1e-13, atol=1e-13, err_msg=name)
 
 
+@pytest.mark.parametrize("rnum", [7, 250, 1000])
+def test_launch_conditions_for_other_ray_counts(beam_fix, rnum):
+    """The reference takes the launch normals from np.gradient on a fine grid of lcm(rnum, 1000) points
+    (beam.py:306-326); the product evaluates only the 3 * rnum nodes that enter.  Coprime, divisor
+    and equal ray counts all reproduce the reference's launch set."""
+    n, x, y = ft2_density(int(beam_fix["nx"]), float(beam_fix["n0"]))
+    nf = Nfield(n, x=x, y=y)
+    b = _beam(beam_fix)
+    wf = b.wavefront_r(dist=3, ampbnd=1e-3, n_field=nf)
+    got = b.launch_conditions(rnum, wf, nf.refractive_index(freq=b.freq))
+    for g, w, name in zip(got, beam_fix[f"launch_r{rnum}"], ("x", "y", "kx", "ky", "amp", "phase")):
+        np.testing.assert_allclose(g, w, rtol=1e-12, atol=1e-12, err_msg=name)
+
+
 def _host_ray(oracle_mod, nf, launch, x0, y0, L=4096):
     """A product Ray filled from an ORACLE trajectory (test only: no GPU here)."""
     from rayrtrace_b200.ray import Ray
