@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define STB_ABI_VERSION 2
+#define STB_ABI_VERSION 3
 
 /* status codes */
 #define STB_OK            0
@@ -86,6 +86,11 @@ int stb_check(int nx, int ny, int i, int j, const double *a, double *out);
                                          refill otherwise -- refill costs <= 15 % on a clean beam but is 3-5x
                                          faster when a few rays run 10-100x longer than the rest (trapped
                                          rays; profiles/r01/kernel_sweep_trapped.txt) */
+#define STB_F_NO_HOIST     (1u << 6)  /* keep the 16-byte {ax, ay} cells even when the launch has one global step.
+                                         By default such launches read a per-(field, st) table of the four
+                                         cell-only products of sidtracemodule.c:41-45 (32 B per cell, built once
+                                         and cached on the field; bit-identical results, 14 instead of 20 FP64
+                                         instructions per step); tables over 64 MB (STB_HOIST_MAX_MB) are not built */
 #define STB_F_TRAJ_HOST    (1u << 3)  /* traj is a HOST pointer (copied back after the launch) */
 #define STB_F_TRAJ_TILED   (1u << 4)  /* warp-tile schedule: a warp owns 32 consecutive rays until all of them
                                          ended.  traj (if any) is laid out [ray/T][step][ray%T][4] (T =
@@ -150,6 +155,15 @@ typedef struct stb_batch_s {
      * traced again; no stored trajectory is needed. */
     const double *lookup_ph;  /* [2][nrays] target phases A, B per ray; NULL disables             */
     double  *lookup_xy;       /* [4][nrays] xA, yA, xB, yB (cm); NaN if the ray has < 2 points     */
+
+    /* packed tiled trajectories (with STB_F_TRAJ_TILED; NULL -> the [ray/T][step][ray%T][4] layout with
+     * L rows per tile): the plan stb_traj_plan made from the step counts of a first pass.  Slot s of
+     * the plan holds ray traj_perm[s] (-1: empty); tile t = slots [t*T, (t+1)*T) owns rows
+     * traj_tile_off[t] .. traj_tile_off[t+1] of T x 4 doubles; state j of the ray in slot s is at
+     * traj[((traj_tile_off[s/T] + j)*T + s%T)*4].  No ray steps past the rows of its tile. */
+    const int32_t *traj_perm;      /* [traj_nslots]                                              */
+    const int64_t *traj_tile_off;  /* [traj_nslots/T + 1]                                        */
+    int64_t  traj_nslots;          /* ceil(nrays/T)*T                                            */
 } stb_batch_t;
 
 /* Traces b->nrays rays on `stream` (a cudaStream_t passed as void*; NULL = the
@@ -205,12 +219,26 @@ typedef struct stb_beam_s {
 } stb_beam_t;
 int stb_beam_launch(const stb_beam_t *a, void *stream);
 
+/* ---- exactly-sized trajectory arenas -------------------------------------------------------------- */
+/* The reference gives every ray MaxStep-long arrays and keeps [:i] (ray.py:19-22, 99-102).  Here a first
+ * pass without trajectory output (step counts only) is followed by this plan: rays sorted by step count,
+ * longest first, ties in launch order (stable radix sort); T = `tile` consecutive ones share a tile; a tile
+ * owns (step count of its longest ray + 1) rows.  Outputs (DEVICE): perm[ceil(nrays/T)*T] slot -> ray
+ * (-1 = empty), slot_of[nrays] ray -> slot, tile_off[ceil(nrays/T)+1] first row of every tile; *total_rows
+ * (HOST) = rows of the whole arena, i.e. it needs total_rows*T*32 bytes.  L > 0 tells the sort how many
+ * key bits matter (nsteps < L).  Synchronises `stream` before returning. */
+int stb_traj_plan(const int32_t *nsteps, int64_t nrays, int32_t tile, int64_t L,
+                  int32_t *perm, int32_t *slot_of, int64_t *tile_off, int64_t *total_rows, void *stream);
+
 /* Trajectory export: packs the KEPT states 0..nsteps[r]-1 of every ray (what the reference's Ray keeps,
  * ray.py:99-102) from a trajectory arena -- ray-major (tile = 0, ray_stride doubles per ray, 0 -> 4*L) or
  * tiled (tile = 32 / 64 / 128) -- into out[offsets[r] .. offsets[r] + nsteps[r]][4].  All pointers are
  * DEVICE pointers; offsets is an exclusive prefix sum of nsteps (int64).  Asynchronous on `stream`. */
 int stb_pack_traj(const double *traj, int tile, int64_t ray_stride, int64_t L, int64_t nrays,
                   const int32_t *nsteps, const int64_t *offsets, double *out, void *stream);
+/* The same from a packed tiled arena (stb_traj_plan): slot_of, tile_off as the plan wrote them. */
+int stb_pack_traj_plan(const double *traj, int tile, const int32_t *slot_of, const int64_t *tile_off, int64_t nrays,
+                       const int32_t *nsteps, const int64_t *offsets, double *out, void *stream);
 
 /* number of kernel launches issued by this library so far (all threads) */
 int64_t stb_launch_count(void);

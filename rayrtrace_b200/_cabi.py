@@ -12,7 +12,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_in
 
 from . import build as _build
 
-STB_ABI_VERSION = 2
+STB_ABI_VERSION = 3
 STB_OK = 0
 STB_ERR_ARG, STB_ERR_CUDA, STB_ERR_NOMEM, STB_ERR_RANGE = -1, -2, -3, -4
 
@@ -22,12 +22,13 @@ F_REFILL = 1 << 2
 F_TRAJ_HOST = 1 << 3
 F_TRAJ_TILED = 1 << 4
 F_STATIC = 1 << 5
+F_NO_HOIST = 1 << 6
 
 # every symbol include/sidtrace_b200.h declares (tests check the .so exports them all)
 EXPORTS = (
     "stb_abi_version", "stb_last_error", "stb_device_count", "stb_set_device",
     "stb_field_create", "stb_field_destroy", "stb_field_shape", "stb_field_peek",
-    "stb_trace", "stb_check", "stb_trace_batch", "stb_launch_states", "stb_beam_launch", "stb_field_pages", "stb_pack_traj", "stb_launch_count",
+    "stb_trace", "stb_check", "stb_trace_batch", "stb_launch_states", "stb_beam_launch", "stb_field_pages", "stb_pack_traj", "stb_pack_traj_plan", "stb_traj_plan", "stb_launch_count",
     "stb_measure_fp64_peak", "stb_measure_store_bw",
     # include/sidtrace_b200_rk.h (adaptive-RK extension)
     "stb_medium_create", "stb_medium_destroy", "stb_medium_table", "stb_trace_rk",
@@ -65,6 +66,7 @@ class StbBatch(Structure):
         ("cross_count", c_void_p), ("cross_index", c_void_p), ("cross_flags", c_void_p),
         ("cross_state", c_void_p),
         ("lookup_ph", c_void_p), ("lookup_xy", c_void_p),
+        ("traj_perm", c_void_p), ("traj_tile_off", c_void_p), ("traj_nslots", c_int64),
     ]
 
 
@@ -176,6 +178,10 @@ def _load() -> ctypes.CDLL:
     lib.stb_field_pages.restype = c_int
     lib.stb_pack_traj.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.stb_pack_traj.restype = c_int
+    lib.stb_pack_traj_plan.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.stb_pack_traj_plan.restype = c_int
+    lib.stb_traj_plan.argtypes = [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_void_p]
+    lib.stb_traj_plan.restype = c_int
     lib.stb_launch_count.restype = c_int64
     lib.stb_launch_count.argtypes = []
     lib.stb_measure_fp64_peak.argtypes = [POINTER(c_double)]

@@ -348,7 +348,10 @@ class Beam:
         from . import _cabi
         seg = np.sqrt(np.diff(wave_front.x) ** 2 + np.diff(wave_front.y) ** 2)
         lax = np.cumsum(np.insert(seg, 0, 0))
-        spl = wave_front._spline                      # interp1d(kind='cubic') keeps a BSpline
+        # the cubic interp1d of the wavefront is a not-a-knot B-spline; build it through the public API
+        # (bit-identical knots and coefficients to the interp1d object's own)
+        from scipy.interpolate import make_interp_spline
+        spl = make_interp_spline(np.asarray(wave_front.x, float), np.asarray(wave_front.y, float), k=3, check_finite=False)
         dev = torch.device("cuda", torch.cuda.current_device())
         tabs = [torch.from_numpy(np.ascontiguousarray(v, np.float64).ravel()).to(dev)
                 for v in (lax, wave_front.x, spl.t, spl.c)]

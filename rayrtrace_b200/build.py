@@ -15,7 +15,8 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "sidtrace_b200.cu")
 SRC_RK = os.path.join(_HERE, "csrc", "rk_b200.cu")      # adaptive-RK physics mode (extension)
-SOURCES = [SRC, SRC_RK]
+SRC_PLAN = os.path.join(_HERE, "csrc", "plan_b200.cu")  # exactly-sized trajectory arenas (CUB sort + scan)
+SOURCES = [SRC, SRC_RK, SRC_PLAN]
 DEPS = SOURCES + [os.path.join(_HERE, "csrc", h) for h in ("trace_kernels.cuh", "launch_kernels.cuh", "rk_kernels.cuh")] + [
     os.path.join(os.path.dirname(_HERE), "include", h) for h in ("sidtrace_b200.h", "sidtrace_b200_rk.h")]
 LIB_DIR = os.path.join(_HERE, "_lib")
@@ -27,7 +28,7 @@ NVCC_FLAGS = [
     "-fmad=false",                 # parity: no FMA contraction anywhere (kernels use explicit _rn intrinsics too)
     "-Xcompiler", "-fPIC", "-shared",
     "-cudart", "static",
-    "--threads", "2",
+    "--threads", "3",
 ]
 
 

@@ -101,6 +101,8 @@ __global__ void launch_states_kernel(const LaunchParams p)
             for (int j = 0; j < 4; ++j) s += row[j] * hy[j];
             den += hx[i] * s;
         }
+        // den.py:71: interp2d(..., fill_value=1e12) -- outside the grid the reference reads 1e12
+        if (x0 < xb || x0 > xe || y0 < yb || y0 > ye) den = 1e12;
         const double refr = sqrt(1.0 - den / p.nc);
         // direction -> vacuum wave vector -> local wave vector (same operation order as launch_states)
         const double kxd = p.kxd[r], kyd = p.kyd[r];

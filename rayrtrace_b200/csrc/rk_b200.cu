@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <atomic>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -44,14 +45,17 @@ struct stb_medium_s {
     int mode = 0, interp = 2;
     double *X = nullptr, *alpha = nullptr;
     double2 *XA = nullptr;                   // {X, alpha} interleaved (only with an absorption table)
-    unsigned long long *counter = nullptr;   // kCounters queue heads used round-robin
+    unsigned long long *counter = nullptr;   // kCounters queue heads used round-robin; a slot is handed out again
+                                             // only after the launch that used it last has finished (counter_ev)
+    cudaEvent_t counter_ev[64] = {};
     std::atomic<unsigned> launch_seq{0};   // host threads may launch concurrently on their own streams
+    std::mutex mu;                           // guards counter_ev
 };
 
 namespace {
 
 template <int INTERP, bool XMODE, bool ABSORB>
-int launch_rk(const stbrk::Params &p, int num_sms, cudaStream_t s)
+int launch_rk(const stbrk::Params &p, int num_sms, cudaStream_t s, cudaEvent_t ev)
 {
     auto kern = stbrk::rk_kernel<INTERP, XMODE, ABSORB>;
     const size_t smem = (ABSORB && p.hist) ? (size_t)p.nbins * sizeof(double) : 0;
@@ -66,14 +70,15 @@ int launch_rk(const stbrk::Params &p, int num_sms, cudaStream_t s)
     kern<<<(unsigned)blocks, stbrk::kBlock, smem, s>>>(p);
     stb_internal_count_launch();
     CU(cudaGetLastError());
+    if (ev) CU(cudaEventRecord(ev, s));
     return STB_OK;
 }
 
 template <int INTERP>
-int launch_mode(const stbrk::Params &p, bool xmode, bool absorb, int num_sms, cudaStream_t s)
+int launch_mode(const stbrk::Params &p, bool xmode, bool absorb, int num_sms, cudaStream_t s, cudaEvent_t ev)
 {
-    if (xmode) return absorb ? launch_rk<INTERP, true, true>(p, num_sms, s) : launch_rk<INTERP, true, false>(p, num_sms, s);
-    return absorb ? launch_rk<INTERP, false, true>(p, num_sms, s) : launch_rk<INTERP, false, false>(p, num_sms, s);
+    if (xmode) return absorb ? launch_rk<INTERP, true, true>(p, num_sms, s, ev) : launch_rk<INTERP, true, false>(p, num_sms, s, ev);
+    return absorb ? launch_rk<INTERP, false, true>(p, num_sms, s, ev) : launch_rk<INTERP, false, false>(p, num_sms, s, ev);
 }
 
 int trace_rk_host_io(stb_medium_t m, const stb_rk_t *rk, cudaStream_t s);
@@ -184,6 +189,7 @@ int stb_medium_destroy(stb_medium_t m)
 {
     if (!m) return STB_OK;
     cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->XA); cudaFree(m->counter);
+    for (auto &e : m->counter_ev) if (e) cudaEventDestroy(e);
     delete m;
     return STB_OK;
 }
@@ -239,15 +245,20 @@ int stb_trace_rk(stb_medium_t m, const stb_rk_t *rk, void *stream)
         p.r_rlcs = 1.0 / rk->r_lcs;
         p.bins_per_rho = (double)rk->nbins / rk->rho_max;
     }
-    p.counter = m->counter + (m->launch_seq.fetch_add(1) % kCounters);
+    std::lock_guard<std::mutex> lk(m->mu);
+    const unsigned slot = m->launch_seq.fetch_add(1) % kCounters;
+    p.counter = m->counter + slot;
+    if (m->counter_ev[slot]) CU(cudaEventSynchronize(m->counter_ev[slot]));
+    else CU(cudaEventCreateWithFlags(&m->counter_ev[slot], cudaEventDisableTiming));
+    cudaEvent_t ev = m->counter_ev[slot];
 
     cudaStream_t s = (cudaStream_t)stream;
     const bool xmode = m->mode == STB_RK_MODE_X;
     const bool absorb = m->alpha != nullptr;
     switch (m->interp) {
-        case STB_RK_INTERP_BILINEAR: return launch_mode<0>(p, xmode, absorb, m->num_sms, s);
-        case STB_RK_INTERP_CATMULL_ROM: return launch_mode<1>(p, xmode, absorb, m->num_sms, s);
-        default: return launch_mode<2>(p, xmode, absorb, m->num_sms, s);
+        case STB_RK_INTERP_BILINEAR: return launch_mode<0>(p, xmode, absorb, m->num_sms, s, ev);
+        case STB_RK_INTERP_CATMULL_ROM: return launch_mode<1>(p, xmode, absorb, m->num_sms, s, ev);
+        default: return launch_mode<2>(p, xmode, absorb, m->num_sms, s, ev);
     }
 }
 

@@ -76,13 +76,27 @@ struct HostBuf {   // pinned
 
 }  // namespace
 
+// One hoisted table (trace_kernels.cuh, HOIST) per global step value the field has been traced with.
+struct HoistEntry {
+    uint64_t st_bits = 0;
+    double4 *tab = nullptr;
+    cudaEvent_t ready = nullptr;          // recorded on the building stream after hoist_kernel
+    uint64_t last_use = 0;
+};
+constexpr int kHoistSlots = 4;
+
 struct stb_field_s {
     int device = 0;
     int nx = 0, ny = 0;
     double2 *cells = nullptr;             // interleaved {ax, ay}, (ny-1)*(nx-1)
-    unsigned long long *counter = nullptr;   // kCounters queue heads, used round-robin so that
-                                             // launches in flight on different streams never share one
-    std::atomic<unsigned> launch_seq{0};   // host threads may launch concurrently on their own streams
+    unsigned long long *counter = nullptr;   // kCounters queue heads, used round-robin; a slot is handed out
+                                             // again only after the launch that used it last has finished
+                                             // (counter_ev), so launches in flight never share one
+    cudaEvent_t counter_ev[kCounters] = {};
+    unsigned launch_seq = 0;              // guarded by mu
+    HoistEntry hoist[kHoistSlots];
+    uint64_t hoist_clock = 0;
+    size_t hoist_max_bytes = 64u << 20;   // larger tables would fall out of L2: keep the 16-byte cells
     int num_sms = 0;
     std::mutex mu;                        // guards the workspaces below
     DevBuf ws_in, ws_out, ws_traj, ws_hist;
@@ -131,6 +145,7 @@ int stb_field_create(const double *ax, const double *ay, int nx, int ny, int on_
     cudaError_t e = cudaGetDevice(&f->device);
     if (e != cudaSuccess) { delete f; return fail(STB_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e)); }
     cudaDeviceGetAttribute(&f->num_sms, cudaDevAttrMultiProcessorCount, f->device);
+    if (const char *e = getenv("STB_HOIST_MAX_MB")) f->hoist_max_bytes = (size_t)atoll(e) << 20;
 
     const size_t bytes = (size_t)ncell * sizeof(double);
     double *tmp = nullptr;   // staging for host input: [ax | ay]
@@ -171,6 +186,11 @@ int stb_field_destroy(stb_field_t f)
     if (!f) return STB_OK;
     cudaFree(f->cells);
     cudaFree(f->counter);
+    for (auto &h : f->hoist) {
+        if (h.tab) cudaFree(h.tab);
+        if (h.ready) cudaEventDestroy(h.ready);
+    }
+    for (auto &e : f->counter_ev) if (e) cudaEventDestroy(e);
     f->ws_in.release(); f->ws_out.release(); f->ws_traj.release(); f->ws_hist.release();
     f->pin.release();
     delete f;
@@ -212,76 +232,140 @@ namespace {
 
 using stb::KParams;
 
-template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool TILED = false, bool CROSS = false, bool STRAY = true,
-          bool LOOKUP = false>
-int launch_variant(const KParams &p, bool refill, int num_sms, cudaStream_t s)
+struct LaunchCtx {
+    stb_field_s *f;
+    bool refill;
+    cudaStream_t s;
+};
+
+// The actual launch of one kernel instantiation.
+template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool TILED, bool CROSS, bool LOOKUP, bool STRAY, bool HOIST>
+int launch_one(const KParams &p0, const LaunchCtx &c)
 {
-    // lean variants (no fused outputs) with one global step keep st in the constant bank
-    if constexpr (STRAY && !EXTRAS && !HIST && !CROSS) {
-        if (!p.st_ray) return launch_variant<TRAJ, EXTRAS, HIST, DIVC, TILED, CROSS, false>(p, refill, num_sms, s);
-    }
+    cudaStream_t s = c.s;
     // static tiled trajectories over 256-ray tiles: 256-thread CTAs, one 8 KB row per CTA-step
-    if constexpr (TRAJ && TILED && !EXTRAS && !HIST && !CROSS) {
-        if (!refill && p.tile == 256 && p.nrays > 0) {
-            const long long blocks = (p.nrays + 255) / 256;
+    if constexpr (TRAJ && TILED && !EXTRAS && !HIST && !CROSS && !STRAY) {
+        if (!c.refill && p0.tile == 256 && p0.nrays > 0) {
+            const long long blocks = (p0.nrays + 255) / 256;
             if (blocks > 0x7fffffffLL) return fail(STB_ERR_ARG, "too many rays for a static grid");
-            stb::trace_kernel<true, false, false, DIVC, false, true, false, STRAY, false, 256><<<(unsigned)blocks, 256, 0, s>>>(p);
+            stb::trace_kernel<true, false, false, DIVC, false, true, false, false, false, 256, HOIST><<<(unsigned)blocks, 256, 0, s>>>(p0);
             g_launches++;
             CU(cudaGetLastError());
             return STB_OK;
         }
     }
-    const size_t smem = HIST ? (size_t)p.nbins * sizeof(double) : 0;
-    if (p.nrays <= 0) return STB_OK;
-    long long blocks_all = (p.nrays + stb::kBlock - 1) / stb::kBlock;
-    if (refill) {
-        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, true, TILED, CROSS, STRAY, LOOKUP>;
+    const size_t smem = HIST ? (size_t)p0.nbins * sizeof(double) : 0;
+    if (p0.nrays <= 0) return STB_OK;
+    long long blocks_all = (p0.nrays + stb::kBlock - 1) / stb::kBlock;
+    if (c.refill) {
+        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, true, TILED, CROSS, STRAY, LOOKUP, stb::kBlock, HOIST>;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, stb::kBlock, smem));
         if (per_sm < 1) per_sm = 1;
-        long long blocks = (long long)num_sms * per_sm;
+        long long blocks = (long long)c.f->num_sms * per_sm;
         if (blocks > blocks_all) blocks = blocks_all;
+        // queue head: one of kCounters slots; a slot is reused only after the launch that used it last
+        // has finished, so launches in flight (other streams, other host threads) never share one
+        stb_field_s *f = c.f;
+        const int k = (int)(f->launch_seq++ % kCounters);
+        if (f->counter_ev[k]) CU(cudaEventSynchronize(f->counter_ev[k]));
+        else CU(cudaEventCreateWithFlags(&f->counter_ev[k], cudaEventDisableTiming));
+        KParams p = p0;
+        p.counter = f->counter + k;
         CU(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), s));
         kern<<<(unsigned)blocks, stb::kBlock, smem, s>>>(p);
+        CU(cudaEventRecord(f->counter_ev[k], s));
     } else {
-        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, false, TILED, CROSS, STRAY, LOOKUP>;
+        auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, false, TILED, CROSS, STRAY, LOOKUP, stb::kBlock, HOIST>;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (blocks_all > 0x7fffffffLL) return fail(STB_ERR_ARG, "too many rays for a static grid");
-        kern<<<(unsigned)blocks_all, stb::kBlock, smem, s>>>(p);
+        kern<<<(unsigned)blocks_all, stb::kBlock, smem, s>>>(p0);
     }
     g_launches++;
     CU(cudaGetLastError());
     return STB_OK;
 }
 
-template <bool TRAJ, bool EXTRAS, bool HIST>
-int launch_div(const KParams &p, bool divc, bool refill, int num_sms, cudaStream_t s)
+// Step flavour: per-ray steps (STRAY); one global step with the hoisted per-cell products (HOIST);
+// or one global step read from the constant bank (lean variants only, when hoisting is off).
+template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool TILED = false, bool CROSS = false, bool LOOKUP = false>
+int launch_variant(const KParams &p, const LaunchCtx &c)
 {
-    return divc ? launch_variant<TRAJ, EXTRAS, HIST, true>(p, refill, num_sms, s)
-                : launch_variant<TRAJ, EXTRAS, HIST, false>(p, refill, num_sms, s);
+    if (!p.st_ray) {
+        if (p.field4) return launch_one<TRAJ, EXTRAS, HIST, DIVC, TILED, CROSS, LOOKUP, false, true>(p, c);
+        if constexpr (!EXTRAS && !HIST && !CROSS)
+            return launch_one<TRAJ, EXTRAS, HIST, DIVC, TILED, CROSS, LOOKUP, false, false>(p, c);
+    }
+    return launch_one<TRAJ, EXTRAS, HIST, DIVC, TILED, CROSS, LOOKUP, true, false>(p, c);
+}
+
+template <bool TRAJ, bool EXTRAS, bool HIST>
+int launch_div(const KParams &p, bool divc, const LaunchCtx &c)
+{
+    return divc ? launch_variant<TRAJ, EXTRAS, HIST, true>(p, c)
+                : launch_variant<TRAJ, EXTRAS, HIST, false>(p, c);
 }
 
 template <bool TRAJ, bool TILED>
-int launch_cross(const KParams &p, bool divc, bool refill, int num_sms, cudaStream_t s)
+int launch_cross(const KParams &p, bool divc, const LaunchCtx &c)
 {
-    return divc ? launch_variant<TRAJ, true, false, true, TILED, true>(p, refill, num_sms, s)
-                : launch_variant<TRAJ, true, false, false, TILED, true>(p, refill, num_sms, s);
+    return divc ? launch_variant<TRAJ, true, false, true, TILED, true>(p, c)
+                : launch_variant<TRAJ, true, false, false, TILED, true>(p, c);
 }
 
-int launch_trace(const KParams &p, bool divc, bool refill, bool tiled, int num_sms, cudaStream_t s)
+// Table of the cell-only products for the launch's global step: built once per (field, st) on the
+// launching stream, kept in a small LRU cache on the field.  Caller holds f->mu.
+int ensure_hoist(stb_field_s *f, double st, cudaStream_t s, const double4 **out)
 {
+    uint64_t bits;
+    memcpy(&bits, &st, sizeof(bits));
+    HoistEntry *e = nullptr, *victim = nullptr;
+    for (auto &h : f->hoist) {
+        if (h.tab && h.st_bits == bits) { e = &h; break; }
+        if (!victim || (victim->tab && (!h.tab || h.last_use < victim->last_use))) victim = &h;
+    }
+    if (!e) {
+        e = victim;
+        const long long ncell = (long long)(f->nx - 1) * (long long)(f->ny - 1);
+        if (e->tab) CU(cudaDeviceSynchronize());        // kernels that still read the evicted table
+        else CU(cudaMalloc(&e->tab, (size_t)ncell * sizeof(double4)));
+        if (!e->ready) CU(cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming));
+        long long blocks = (ncell + 255) / 256;
+        if (blocks > (long long)f->num_sms * 16) blocks = (long long)f->num_sms * 16;
+        stb::hoist_kernel<<<(unsigned)blocks, 256, 0, s>>>(f->cells, st, st * st, e->tab, ncell);
+        g_launches++;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(e->ready, s));
+        e->st_bits = bits;
+    } else {
+        CU(cudaStreamWaitEvent(s, e->ready, 0));         // built on another stream, perhaps
+    }
+    e->last_use = ++f->hoist_clock;
+    *out = e->tab;
+    return STB_OK;
+}
+
+int launch_trace(stb_field_s *f, KParams &p, bool divc, bool refill, bool tiled, bool hoist, cudaStream_t s)
+{
+    const LaunchCtx c{f, refill, s};
+    p.field4 = nullptr;
+    if (hoist && !p.st_ray && p.nrays > 0) {
+        const size_t bytes = (size_t)(f->nx - 1) * (size_t)(f->ny - 1) * sizeof(double4);
+        if (bytes <= f->hoist_max_bytes) {
+            int rc = ensure_hoist(f, p.st, s, &p.field4);
+            if (rc != STB_OK) return rc;
+        }
+    }
     if (p.cross_axis) {
         if (p.hist) return fail(STB_ERR_ARG, "the crossing output cannot be combined with the histogram output");
         if (p.lookup_ph) {
             if (p.traj || tiled) return fail(STB_ERR_ARG, "the equal-phase lookup pass takes no trajectory output and no tiled schedule");
-            return divc ? launch_variant<false, true, false, true, false, true, true, true>(p, refill, num_sms, s)
-                        : launch_variant<false, true, false, false, false, true, true, true>(p, refill, num_sms, s);
+            return divc ? launch_variant<false, true, false, true, false, true, true>(p, c)
+                        : launch_variant<false, true, false, false, false, true, true>(p, c);
         }
-        if (p.traj) return tiled ? launch_cross<true, true>(p, divc, refill, num_sms, s)
-                                 : launch_cross<true, false>(p, divc, refill, num_sms, s);
-        return tiled ? launch_cross<false, true>(p, divc, refill, num_sms, s)
-                     : launch_cross<false, false>(p, divc, refill, num_sms, s);
+        if (p.traj) return tiled ? launch_cross<true, true>(p, divc, c) : launch_cross<true, false>(p, divc, c);
+        return tiled ? launch_cross<false, true>(p, divc, c) : launch_cross<false, false>(p, divc, c);
     }
     if (tiled) {
         // warp-tile schedule: plain trajectories and/or fused running sums; the histogram keeps
@@ -290,14 +374,14 @@ int launch_trace(const KParams &p, bool divc, bool refill, bool tiled, int num_s
         if (p.hist) return fail(STB_ERR_ARG, "STB_F_TRAJ_TILED cannot be combined with the histogram output");
         const int key = (p.traj ? 4 : 0) | (extras ? 2 : 0) | (divc ? 1 : 0);
         switch (key) {
-            case 0: return launch_variant<false, false, false, false, true>(p, refill, num_sms, s);
-            case 1: return launch_variant<false, false, false, true, true>(p, refill, num_sms, s);
-            case 2: return launch_variant<false, true, false, false, true>(p, refill, num_sms, s);
-            case 3: return launch_variant<false, true, false, true, true>(p, refill, num_sms, s);
-            case 4: return launch_variant<true, false, false, false, true>(p, refill, num_sms, s);
-            case 5: return launch_variant<true, false, false, true, true>(p, refill, num_sms, s);
-            case 6: return launch_variant<true, true, false, false, true>(p, refill, num_sms, s);
-            default: return launch_variant<true, true, false, true, true>(p, refill, num_sms, s);
+            case 0: return launch_variant<false, false, false, false, true>(p, c);
+            case 1: return launch_variant<false, false, false, true, true>(p, c);
+            case 2: return launch_variant<false, true, false, false, true>(p, c);
+            case 3: return launch_variant<false, true, false, true, true>(p, c);
+            case 4: return launch_variant<true, false, false, false, true>(p, c);
+            case 5: return launch_variant<true, false, false, true, true>(p, c);
+            case 6: return launch_variant<true, true, false, false, true>(p, c);
+            default: return launch_variant<true, true, false, true, true>(p, c);
         }
     }
     const bool traj = p.traj != nullptr;
@@ -305,14 +389,14 @@ int launch_trace(const KParams &p, bool divc, bool refill, bool tiled, int num_s
     const bool hist = p.hist != nullptr;
     const int key = (traj ? 4 : 0) | (extras ? 2 : 0) | (hist ? 1 : 0);
     switch (key) {
-        case 0: return launch_div<false, false, false>(p, divc, refill, num_sms, s);
-        case 1: return launch_div<false, false, true>(p, divc, refill, num_sms, s);
-        case 2: return launch_div<false, true, false>(p, divc, refill, num_sms, s);
-        case 3: return launch_div<false, true, true>(p, divc, refill, num_sms, s);
-        case 4: return launch_div<true, false, false>(p, divc, refill, num_sms, s);
-        case 5: return launch_div<true, false, true>(p, divc, refill, num_sms, s);
-        case 6: return launch_div<true, true, false>(p, divc, refill, num_sms, s);
-        default: return launch_div<true, true, true>(p, divc, refill, num_sms, s);
+        case 0: return launch_div<false, false, false>(p, divc, c);
+        case 1: return launch_div<false, false, true>(p, divc, c);
+        case 2: return launch_div<false, true, false>(p, divc, c);
+        case 3: return launch_div<false, true, true>(p, divc, c);
+        case 4: return launch_div<true, false, false>(p, divc, c);
+        case 5: return launch_div<true, false, true>(p, divc, c);
+        case 6: return launch_div<true, true, false>(p, divc, c);
+        default: return launch_div<true, true, true>(p, divc, c);
     }
 }
 
@@ -360,6 +444,17 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     p.tile = b->traj_tile ? b->traj_tile : 256;
     if (p.tile != 32 && p.tile != 64 && p.tile != 128 && p.tile != 256)
         return fail(STB_ERR_ARG, "stb_trace_batch: traj_tile must be 32, 64, 128 or 256 (got %d)", b->traj_tile);
+    p.perm = nullptr; p.tile_off = nullptr; p.nslots = 0;
+    if (b->traj_perm || b->traj_tile_off) {
+        if (!(b->flags & STB_F_TRAJ_TILED) || !b->traj_perm || !b->traj_tile_off)
+            return fail(STB_ERR_ARG, "stb_trace_batch: a packed plan needs STB_F_TRAJ_TILED, traj_perm and traj_tile_off");
+        const long long want = (b->nrays + p.tile - 1) / p.tile * p.tile;
+        if (b->traj_nslots != want)
+            return fail(STB_ERR_ARG, "stb_trace_batch: traj_nslots = %lld, expected ceil(nrays/T)*T = %lld", (long long)b->traj_nslots, want);
+        if (b->flags & STB_F_HOST_IO)
+            return fail(STB_ERR_ARG, "stb_trace_batch: a packed plan lives in device memory (no STB_F_HOST_IO)");
+        p.perm = b->traj_perm; p.tile_off = (const long long *)b->traj_tile_off; p.nslots = b->traj_nslots;
+    }
     p.nsteps = b->nsteps; p.endst = b->end_state;
     p.turn = b->turn_index; p.turn_state = b->turn_state; p.lax_end = b->lax_end; p.ph_end = b->ph_end;
     p.hist = b->hist; p.nbins = b->nbins; p.amp = b->amp;
@@ -369,7 +464,7 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     // a ray advances about one smallest cell per step (SURVEY 3.3 i): the annulus test pays off when a
     // bin spans several steps, otherwise most steps would fail it and take the exact path anyway
     p.hist_annulus = b->hist && p.hist_dr >= 4.0 * std::fmin(std::fabs(b->dx), std::fabs(b->dy));
-    p.counter = f->counter + (f->launch_seq.fetch_add(1) % kCounters);
+    p.counter = nullptr;                 // assigned per persistent launch (launch_one)
     p.cross_axis = b->cross_axis; p.cross_val = b->cross_val;
     p.x0p = b->x0_phys; p.y0p = b->y0_phys;
     p.cross_count = b->cross_count; p.cross_index = b->cross_index; p.cross_flags = b->cross_flags;
@@ -415,7 +510,8 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
     int rc = fill_params(f, b, p, divc);
     if (rc != STB_OK) return rc;
 
-    if (!host_io && !traj_host) return launch_trace(p, divc, refill, tiled, f->num_sms, s);
+    const bool hoist = !(b->flags & STB_F_NO_HOIST);
+    if (!host_io && !traj_host) return launch_trace(f, p, divc, refill, tiled, hoist, s);
 
     const size_t n = (size_t)b->nrays;
     const size_t nb = n * sizeof(double);
@@ -446,7 +542,7 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
             p.cross_count = (int *)dp[13]; p.cross_index = (int *)dp[14]; p.cross_flags = (int *)dp[15];
             p.cross_state = (double *)dp[16];
             p.turn_state = (double *)dp[17];
-            rc = launch_trace(p, divc, refill, tiled, f->num_sms, s);
+            rc = launch_trace(f, p, divc, refill, tiled, hoist, s);
             if (rc != STB_OK) return rc;
             CU(cudaStreamSynchronize(s));
             return STB_OK;
@@ -506,7 +602,7 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
         p.traj = (double *)f->ws_traj.p;
     }
 
-    rc = launch_trace(p, divc, refill, tiled, f->num_sms, s);
+    rc = launch_trace(f, p, divc, refill, tiled, hoist, s);
     if (rc != STB_OK) return rc;
 
     if (host_io && n) {
@@ -566,7 +662,7 @@ int stb_trace(stb_field_t f, double *x, double *y, double *kx, double *ky, int64
     bool divc = false;
     rc = fill_params(f, &b, p, divc);
     if (rc != STB_OK) return rc;
-    rc = launch_trace(p, divc, /*refill=*/false, /*tiled=*/false, f->num_sms, 0);
+    rc = launch_trace(f, p, divc, /*refill=*/false, /*tiled=*/false, /*hoist=*/false, 0);
     if (rc != STB_OK) return rc;
     CU(cudaStreamSynchronize(0));
     const int32_t n = *hn;
@@ -691,6 +787,25 @@ int stb_pack_traj(const double *traj, int tile, int64_t ray_stride, int64_t L, i
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
     stb::pack_traj_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         traj, tile, (long long)ray_stride, (long long)L, (long long)nrays, nsteps, (const long long *)offsets, out);
+    g_launches++;
+    CU(cudaGetLastError());
+    return STB_OK;
+}
+
+int stb_pack_traj_plan(const double *traj, int tile, const int32_t *slot_of, const int64_t *tile_off, int64_t nrays,
+                       const int32_t *nsteps, const int64_t *offsets, double *out, void *stream)
+{
+    if (!traj || !slot_of || !tile_off || !nsteps || !offsets || !out) return fail(STB_ERR_ARG, "stb_pack_traj_plan: NULL argument");
+    if (tile != 32 && tile != 64 && tile != 128 && tile != 256)
+        return fail(STB_ERR_ARG, "stb_pack_traj_plan: tile must be 32, 64, 128 or 256");
+    if (nrays <= 0) return STB_OK;
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long blocks = (nrays * 32 + 255) / 256;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    stb::pack_plan_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        traj, tile, slot_of, (const long long *)tile_off, (long long)nrays, nsteps, (const long long *)offsets, out);
     g_launches++;
     CU(cudaGetLastError());
     return STB_OK;

@@ -48,6 +48,8 @@ constexpr int kBlock = 128;   // threads per CTA (4 warps); the tiled trajectory
 
 struct KParams {
     const double2 *field;   // {ax, ay} per cell, row stride nxm1
+    const double4 *field4;  // HOIST: {RN(RN(sst*ax)/2), RN(RN(sst*ay)/2), RN(st*ax), RN(st*ay)} per cell for the
+                            // launch's global step (built once per (field, st) by hoist_kernel)
     int nxm1, nym1;
     double fx, fy;                       // (double)(nx-1), (double)(ny-1)
     long long nrays;
@@ -59,6 +61,10 @@ struct KParams {
     double *traj;
     long long stride;                    // doubles per ray (ray-major layout)
     int tile;                            // rays per tile (tiled layout): 32, 64, 128 or 256
+    // packed tiled layout (stb_traj_plan): slot -> ray, first row of every tile, slots = ntiles * tile
+    const int *perm;
+    const long long *tile_off;
+    long long nslots;
     int *nsteps;
     double *endst;
     int *turn;
@@ -100,6 +106,14 @@ __device__ __forceinline__ double cross_solve(double c0, double k, double a, dou
         st = (val - c0) / k;
     }
     return st;
+}
+
+// one 32-byte cell of the hoisted table = one LDG.E.ENL2.256.CONSTANT
+__device__ __forceinline__ double4 ld_cell4(const double4 *p)
+{
+    double4 v;
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
 }
 
 __device__ __forceinline__ void st_state(double *p, double a, double b, double c, double d)
@@ -201,8 +215,13 @@ __device__ __forceinline__ void hist_add(double *sh, int b, double w)
 // BLOCK: threads per CTA.  128 everywhere except the static tiled trajectory kernel, which runs
 // 256-thread CTAs over 256-ray tiles: a CTA-step is then one contiguous 8 KB row (+1.3 % over 4 KB
 // rows, profiles/r01/kernel_sweep_block256_cs.txt; the O(rays)-output modes lose 0.5-3 % with 256).
+// HOIST (needs STRAY = false): with one global step the four products of a step that depend only
+// on the cell -- RN(RN(sst*Mx)/2), RN(RN(sst*My)/2), RN(st*Mx), RN(st*My), sidtracemodule.c:41-45 --
+// are read from a per-(field, st) table built once by hoist_kernel with the very same operations on
+// the very same operands (bit-exact by construction): one 32-byte gather per step, 14 instead of
+// 20 FP64-pipe instructions.
 template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool REFILL, bool TILED = false, bool CROSS = false,
-          bool STRAY = true, bool LOOKUP = false, int BLOCK = kBlock>
+          bool STRAY = true, bool LOOKUP = false, int BLOCK = kBlock, bool HOIST = false>
 __global__ void __launch_bounds__(BLOCK, CROSS ? STB_MINB_CROSS : (HIST || EXTRAS) ? STB_MINB_EXTRAS : STB_MINB * kBlock / BLOCK)
 trace_kernel(const KParams p)
 {
@@ -214,7 +233,7 @@ trace_kernel(const KParams p)
 
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int Lm1 = p.L - 1;
+    int Lm1 = p.L - 1;
 
     // per-ray state
     long long ray = -1;
@@ -232,7 +251,8 @@ trace_kernel(const KParams p)
     // crossing: previous kept state, capture of the first crossing / exact hit
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     double xg0 = 0, yg0 = 0, x0p = 0, y0p = 0;
-    double pxg = 0, pyg = 0, pkx = 0, pky = 0, pmx = 0, pmy = 0, plax = 0, pph = 0, dprev = 0;
+    double pxg = 0, pyg = 0, pkx = 0, pky = 0, plax = 0, pph = 0, dprev = 0;
+    int pind = 0;            // cell of the previous kept state (its acceleration is re-read at capture time)
     double cx = qnan, cy = qnan, ckx = qnan, cky = qnan, clax = qnan, cph = qnan;
     int cidx = -1, ncross = 0, neq = 0;
     bool below = false, above = false;
@@ -245,14 +265,22 @@ trace_kernel(const KParams p)
     double tA = 0, tB = 0, oxA = qnan, oyA = qnan, oxB = qnan, oyB = qnan;
     bool doneA = false, doneB = false, inserted = false;
 
-    auto launch = [&](long long r) {
+    auto launch = [&](long long r, long long slot) {
         ray = r;
         x = p.x0[r]; y = p.y0[r]; kx = p.kx0[r]; ky = p.ky0[r];
         if (STRAY && p.st_ray) { st_r = p.st_ray[r]; sst_r = __dmul_rn(st_r, st_r); }
         i = 0;
         if (TRAJ) {
-            tp = TILED ? p.traj + ((r / p.tile) * (long long)p.L * p.tile + (r % p.tile)) * 4
-                       : p.traj + r * p.stride;
+            if (TILED && p.perm) {
+                // packed: tile t owns rows tile_off[t] .. tile_off[t+1] (sized for its longest ray); never
+                // step beyond them, whatever the plan was made from
+                const long long t = slot / p.tile, row0 = p.tile_off[t];
+                tp = p.traj + (row0 * p.tile + (slot - t * p.tile)) * 4;
+                Lm1 = min(p.L - 1, (int)(p.tile_off[t + 1] - row0) - 1);
+            } else {
+                tp = TILED ? p.traj + ((r / p.tile) * (long long)p.L * p.tile + (r % p.tile)) * 4
+                           : p.traj + r * p.stride;
+            }
             st_state(tp, x, y, kx, ky);
         }
         if (EXTRAS) { turn = -1; lax = 0; ph = 0; }
@@ -277,6 +305,8 @@ trace_kernel(const KParams p)
     // solve from the previous kept state (index i-1) and capture the crossing point (ray.py:212-216)
     auto capture_from_prev = [&](double st1) -> bool {
         const double xp = x0p + (pxg - xg0) * p.dx, yp = y0p + (pyg - yg0) * p.dy;   // ray.py:105-106
+        const double2 pm = __ldg(&p.field[pind]);
+        const double pmx = pm.x, pmy = pm.y;
         const double s = cross_solve(axis_y ? yp : xp, axis_y ? pky : pkx, axis_y ? pmy : pmx, p.cross_val, st1);
         if (!(s == s) || s == 0.0) return false;
         ckx = pkx + pmx * s;
@@ -385,7 +415,10 @@ trace_kernel(const KParams p)
         const double st = STRAY ? st_r : p.st, sst = STRAY ? sst_r : p.sst;
         // :38  nearest lower-left cell, no interpolation
         const int ind = iy * p.nxm1 + ix;
-        const double2 m = __ldg(&p.field[ind]);
+        double2 m = make_double2(0.0, 0.0);
+        double4 h = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (HOIST) h = ld_cell4(&p.field4[ind]);
+        else m = __ldg(&p.field[ind]);
 
         if (EXTRAS || HIST) {
             // state i is a KEPT state (ray.py:99-102 keeps [:n]); close segment (i-1, i)
@@ -482,19 +515,19 @@ trace_kernel(const KParams p)
                 }
                 add_point(ph2, xpi, ypi);
             }
-            pxg = x; pyg = y; pkx = kx; pky = ky; pmx = m.x; pmy = m.y; plax = lax; pph = ph; dprev = d;
+            pxg = x; pyg = y; pkx = kx; pky = ky; pind = ind; plax = lax; pph = ph; dprev = d;
         }
 
-        const double tx = __dmul_rn(__dmul_rn(sst, m.x), 0.5);   // ((st*st)*Mx)/2
-        const double ty = __dmul_rn(__dmul_rn(sst, m.y), 0.5);
+        const double tx = HOIST ? h.x : __dmul_rn(__dmul_rn(sst, m.x), 0.5);   // ((st*st)*Mx)/2
+        const double ty = HOIST ? h.y : __dmul_rn(__dmul_rn(sst, m.y), 0.5);
         const double vx = __dadd_rn(tx, __dmul_rn(kx, st));
         const double vy = __dadd_rn(ty, __dmul_rn(ky, st));
         double wx, wy;
         div_pair<DIVC>(vx, vy, p.dx, p.dy, p.rdx, p.rdy, wx, wy);
         const double x1 = __dadd_rn(x, wx);                       // :41
         const double y1 = __dadd_rn(y, wy);                       // :42
-        const double kx1 = __dadd_rn(kx, __dmul_rn(st, m.x));     // :44
-        const double ky1 = __dadd_rn(ky, __dmul_rn(st, m.y));     // :45
+        const double kx1 = __dadd_rn(kx, HOIST ? h.z : __dmul_rn(st, m.x));     // :44
+        const double ky1 = __dadd_rn(ky, HOIST ? h.w : __dmul_rn(st, m.y));     // :45
 
         if (EXTRAS) {
             if (turn < 0 && ((ky > 0.0 && ky1 <= 0.0) || (ky < 0.0 && ky1 >= 0.0))) {
@@ -516,17 +549,20 @@ trace_kernel(const KParams p)
         // No vote per step: lanes that finish early wait at the reconvergence point after the
         // inner loop, which for a tile of neighbouring rays costs a few steps.
         long long r = REFILL ? 0 : (long long)blockIdx.x * BLOCK + threadIdx.x;
+        const bool packed = TILED && p.perm != nullptr;
         for (;;) {
-            if (REFILL) {   // TILED: one aggregated claim of 32 consecutive rays per warp
+            if (REFILL) {   // TILED: one aggregated claim of 32 consecutive rays (slots) per warp
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(p.counter, 32ull);
                 base = __shfl_sync(FULL, base, 0);
-                if ((long long)base >= p.nrays) break;
+                if ((long long)base >= (packed ? p.nslots : p.nrays)) break;
                 r = (long long)base + lane;
             }
-            const bool has = r < p.nrays;
+            const long long slot = r;
+            if (packed) r = slot < p.nslots ? (long long)p.perm[slot] : -1;
+            const bool has = r >= 0 && r < p.nrays;
             if (has) {
-                launch(r);
+                launch(r, slot);
                 while (step()) { }
             }
             if (TILED) __syncwarp();
@@ -560,7 +596,7 @@ trace_kernel(const KParams p)
                 base = __shfl_sync(FULL, base, leader);
                 if (!active) {
                     const long long r = (long long)base + __popc(idle & ((1u << lane) - 1u));
-                    if (r < p.nrays) { launch(r); active = true; }
+                    if (r < p.nrays) { launch(r, r); active = true; }
                 }
                 more = (long long)(base + want) < p.nrays;
                 act = __ballot_sync(FULL, active);
@@ -594,6 +630,23 @@ __global__ void interleave_kernel(const double *__restrict__ ax, const double *_
     for (; i < n; i += step) out[i] = make_double2(ax[i], ay[i]);
 }
 
+// Hoisted table of a (field, st) pair: per cell the four products of sidtracemodule.c:41-45 that do
+// not depend on the ray -- the same operations on the same operands the un-hoisted step() performs.
+__global__ void hoist_kernel(const double2 *__restrict__ cells, double st, double sst, double4 *__restrict__ out, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += step) {
+        const double2 m = cells[i];
+        double4 h;
+        h.x = __dmul_rn(__dmul_rn(sst, m.x), 0.5);
+        h.y = __dmul_rn(__dmul_rn(sst, m.y), 0.5);
+        h.z = __dmul_rn(st, m.x);
+        h.w = __dmul_rn(st, m.y);
+        st_state(reinterpret_cast<double *>(out + i), h.x, h.y, h.z, h.w);
+    }
+}
+
 // Trajectory export: one warp per ray copies the KEPT states 0..n-1 (ray.py:99-102) of a
 // trajectory arena -- ray-major (tile == 0) or tiled -- into a packed [total][4] buffer at
 // offsets[ray]; 32 B per lane per iteration, coalesced on the packed side.
@@ -608,6 +661,27 @@ __global__ void pack_traj_kernel(const double *__restrict__ traj, int tile, long
         const int n = nsteps[r];
         const double *src = tile ? traj + ((r / tile) * L * tile + (r % tile)) * 4 : traj + r * ray_stride;
         const long long step = tile ? 4LL * tile : 4;
+        double *dst = out + offsets[r] * 4;
+        for (int j = lane; j < n; j += 32) {
+            const double4 v = *reinterpret_cast<const double4 *>(src + j * step);
+            st_state(dst + 4LL * j, v.x, v.y, v.z, v.w);
+        }
+    }
+}
+
+// The same from a packed tiled arena (stb_traj_plan).
+__global__ void pack_plan_kernel(const double *__restrict__ traj, int tile, const int *__restrict__ slot_of,
+                                 const long long *__restrict__ tile_off, long long nrays, const int *__restrict__ nsteps,
+                                 const long long *__restrict__ offsets, double *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < nrays; r += nwarps) {
+        const int n = nsteps[r];
+        const long long slot = slot_of[r], t = slot / tile;
+        const double *src = traj + (tile_off[t] * tile + (slot - t * tile)) * 4;
+        const long long step = 4LL * tile;
         double *dst = out + offsets[r] * 4;
         for (int j = lane; j < n; j += 32) {
             const double4 v = *reinterpret_cast<const double4 *>(src + j * step);

@@ -19,6 +19,7 @@ from scipy.interpolate import RectBivariateSpline, interp1d
 
 # CGS electron charge as the reference hard-codes it (den.py:340)
 _E_CGS = 4.8032e-10
+FILL_VALUE = 1e12     # den.py:71: density the reference's interpolant returns outside the grid
 
 
 def critical_den(freq=136.29e9, den_unit="cm^-3"):
@@ -100,6 +101,12 @@ class Nfield:
         xa = np.atleast_1d(np.asarray(x, float))
         ya = np.atleast_1d(np.asarray(y, float))
         out = self._spline(xa, ya).T
+        # den.py:71: interp2d(..., fill_value=1e12) -- outside the grid the reference reads 1e12
+        # (RectBivariateSpline would clamp to the boundary)
+        xo = (xa < self.x.min()) | (xa > self.x.max())
+        yo = (ya < self.y.min()) | (ya > self.y.max())
+        if xo.any() or yo.any():
+            out = np.where(yo[:, None] | xo[None, :], FILL_VALUE, out)
         if out.shape[0] == 1:
             return out[0]
         if out.shape[1] == 1:
@@ -109,7 +116,10 @@ class Nfield:
     def n_interpolant_points(self, x, y):
         """Cubic interpolation of n at the point pairs (x[i], y[i])."""
         self.n_interpolant(self.x[0], self.y[0])   # builds the spline
-        return self._spline.ev(np.asarray(x, float), np.asarray(y, float))
+        x, y = np.asarray(x, float), np.asarray(y, float)
+        out = self._spline.ev(x, y)
+        outside = (x < self.x.min()) | (x > self.x.max()) | (y < self.y.min()) | (y > self.y.max())
+        return np.where(outside, FILL_VALUE, out) if np.any(outside) else out
 
     def refractive_index(self, freq=136.26e9, x=None, y=None):
         """N = sqrt(1 - n/n_c) (den.py:76-82); boundary density when x or y is None."""

@@ -23,6 +23,12 @@ from . import sidtrace as _st
 _DEFAULT_FREQ = 135e9   # ray.py:15 -- also the sentinel of the "infer freq from |k|" rule (ray.py:34,47)
 
 
+class RayOutsideGrid(IndexError, ValueError):
+    """A ray launched outside the density grid takes no step; the reference then fails with an
+    IndexError at ray.py:105 (``self.x[0]`` of an empty array).  Subclasses ValueError as well, which
+    is what earlier versions of this module raised."""
+
+
 def _vacuum_k(kx0, ky0, freq):
     """ray.py:28-51: normalise the launch direction to w/c, or infer the
     frequency from |k| when |k| > 2 and freq is the default.  Returns
@@ -83,7 +89,7 @@ class Ray:
         i = _st.trace(x, y, kx, ky, st, dx, dy, n_field.nx, n_field.ny,
                       np.ascontiguousarray(n_field.ax), np.ascontiguousarray(n_field.ay))
         if i == 0:
-            raise ValueError(f"ray starts outside the density grid: ({x0}, {y0})")  # reference: IndexError at ray.py:105
+            raise RayOutsideGrid(f"ray starts outside the density grid: ({x0}, {y0})")  # reference: IndexError at ray.py:105
 
         # keep [:i] -- the first out-of-domain state is dropped (ray.py:99-102)
         x, y, kx, ky = x[:i], y[:i], kx[:i], ky[:i]
@@ -270,7 +276,15 @@ def launch_states_device(n_field, x0, y0, kx0, ky0, freq):
     from . import _cabi
     from .nfield import critical_den
     if freq == _DEFAULT_FREQ:
-        raise ValueError("a batch must share one explicit frequency")
+        # same rule as launch_states (ray.py:34-51): the default frequency is a sentinel only for |k| > 2
+        def _kmax(a, b):
+            if type(a).__module__.startswith("torch") or type(b).__module__.startswith("torch"):
+                import torch as _t
+                a, b = (_t.as_tensor(v, dtype=_t.float64) for v in (a, b))
+                return float(_t.sqrt(a.cpu() ** 2 + b.cpu() ** 2).max())
+            return float(np.sqrt(np.asarray(a, np.float64) ** 2 + np.asarray(b, np.float64) ** 2).max())
+        if _kmax(kx0, ky0) > 2:
+            raise ValueError("a batch must share one frequency: pass freq explicitly (ray.py:47-51 infers it per ray)")
     tabs = n_field.device_launch_tables()
     dev = tabs["x"].device
 
@@ -303,16 +317,28 @@ def launch_states_device(n_field, x0, y0, kx0, ky0, freq):
     return out[0], out[1], out[2], out[3], freq
 
 
+def _host_results(res):
+    """Per-ray outputs of a device-I/O BatchResult as numpy arrays (trajectories stay in HBM)."""
+    for name in ("nsteps", "end_state", "turn_index", "turn_state", "lax_end", "ph_end", "cross_count", "cross_index",
+                 "cross_flags", "cross_state", "lookup_xy"):
+        v = getattr(res, name)
+        if v is not None and hasattr(v, "cpu"):
+            setattr(res, name, v.cpu().numpy())
+    return res
+
+
 def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional[int] = None,
                keep_traj: bool = True, want_extras: bool = False, tiled: bool = True,
                receiver=None, device_launch: Optional[bool] = None) -> RayBundle:
-    """Trace a whole fan of rays in one kernel launch (replaces beam.py:340-342).
+    """Trace a whole fan of rays (replaces the serial loop of beam.py:340-342).
 
-    max_steps: array length per ray.  The reference's Ray.MaxStep = 100000 would be 3.2 MB per
-    ray; the default here is 2*max(nx, ny) rounded up to 128 states -- a vacuum ray crosses the
-    grid in ~max(nx, ny) steps (SURVEY 3.3 i).  Rays that hit the cap report
-    nsteps == max_steps-1 exactly like the reference does at its cap, and a RuntimeWarning says
-    how many did so they can be re-traced with a larger cap (or refill=True, keep_traj=False).
+    max_steps: array length per ray, default ``Ray.MaxStep`` (ray.py:11) -- the reference's own cap, so a
+    reflected or trapped ray runs exactly as long as ``Ray(...)`` lets it.  The cap costs no memory:
+    a first pass without trajectory output yields every ray's step count, then the trajectories are
+    written into an arena sized exactly for them (``sidtrace.trace_exact``: rays sorted by length into
+    256-ray tiles; ``tiled=False``: ray-major [n, max(nsteps)+1, 4]).  ``keep_traj=False`` stops after
+    the first pass (per-ray outputs only).  Rays that do hit the cap report nsteps == max_steps-1
+    exactly like the reference.
 
     device_launch: prepare the launch states (ray.py:34-68) on the GPU (``launch_states_device``)
     instead of on the host; default: on for >= 65536 rays, where SciPy's point-wise spline
@@ -320,39 +346,47 @@ def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional
     receiver: (val, axis) -- also report, per ray, what ``Ray.addpoint(val, axis)`` would
     (ray.py:131-224): first crossing of the receiver line, its phase and wave vector
     (``bundle.result.cross_*``), i.e. the per-ray inputs of ``Beam.field_r`` (beam.py:359-369)."""
+    import torch
     if device_launch is None:
         device_launch = np.size(x0) >= 65536 and hasattr(n_field, "device_launch_tables")
     if device_launch:
-        xg, yg, kx, ky, freq = (t.cpu().numpy() if hasattr(t, "cpu") else t
-                                for t in launch_states_device(n_field, x0, y0, kx0, ky0, freq))
+        d_in = list(launch_states_device(n_field, x0, y0, kx0, ky0, freq))
+        freq = d_in.pop()
+        xg, yg, kx, ky = (t.cpu().numpy() for t in d_in)
     else:
         xg, yg, kx, ky, freq = launch_states(n_field, x0, y0, kx0, ky0, freq)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        d_in = [torch.from_numpy(a).to(dev) for a in (xg, yg, kx, ky)]
+    dev = d_in[0].device
     n = len(xg)
+    x0 = np.ascontiguousarray(np.atleast_1d(np.asarray(x0.cpu() if hasattr(x0, "cpu") else x0, np.float64)))
+    y0 = np.ascontiguousarray(np.broadcast_to(np.asarray(y0.cpu() if hasattr(y0, "cpu") else y0, np.float64), x0.shape))
     if amp is None:
         amp = np.ones(n)
     amp = np.broadcast_to(np.asarray(amp, np.float64), (n,)).copy()
-    L = int(max_steps) if max_steps else min(int(Ray.MaxStep), -(-2 * max(n_field.nx, n_field.ny) // 128) * 128)
-    if keep_traj:
-        import torch
-        free, _total = torch.cuda.mem_get_info()
-        need = -(-n // 256) * 256 * L * 32
-        if need > 0.9 * free:
-            raise MemoryError(f"{n} rays x {L} states x 32 B = {need / 1e9:.1f} GB of trajectories exceed the free HBM "
-                              f"({free / 1e9:.1f} GB): pass keep_traj=False (per-ray outputs only), a smaller max_steps, "
-                              f"or trace the beam in chunks")
+    L = int(max_steps) if max_steps else int(Ray.MaxStep)
     st = float(n_field.st * Ray.kStep)
     f = _device_field(n_field)
-    res = _st.trace_batch(f, xg, yg, kx, ky, L=L, st=st, dx=float(n_field.dx[0]), dy=float(n_field.dy[0]),
-                          traj=True if keep_traj else None, want_end=True, want_extras=want_extras,
-                          tiled=bool(tiled and keep_traj), cross=receiver,
-                          x0_phys=np.ascontiguousarray(np.atleast_1d(np.asarray(x0, np.float64))) if receiver else None,
-                          y0_phys=np.ascontiguousarray(np.atleast_1d(np.asarray(y0, np.float64))) if receiver else None)
-    capped = int(np.count_nonzero(np.asarray(res.nsteps) == L - 1))
-    if capped:
-        import warnings
-        warnings.warn(f"{capped} of {n} rays hit the cap of {L - 1} steps (max_steps={L}); the reference's cap is "
-                      f"Ray.MaxStep = {Ray.MaxStep}", RuntimeWarning, stacklevel=2)
-    return RayBundle(n_field=n_field, x0=np.atleast_1d(np.asarray(x0, np.float64)),
-                     y0=np.atleast_1d(np.asarray(y0, np.float64)), freq=freq, st=st, amp=amp,
+    kw = dict(L=L, st=st, dx=float(n_field.dx[0]), dy=float(n_field.dy[0]), want_extras=want_extras, cross=receiver)
+    if receiver:
+        kw.update(x0_phys=torch.from_numpy(x0).to(dev), y0_phys=torch.from_numpy(y0).to(dev))
+    if keep_traj and tiled and n:
+        res = _st.trace_exact(f, *d_in, **kw)
+    else:
+        res = _st.trace_batch(f, *d_in, **kw)          # O(rays) outputs; L only bounds the loop
+        if keep_traj and n:
+            # ray-major trajectories [n, L2, 4], L2 = states of the longest ray: the second pass takes
+            # the same steps (no ray needs more than L2 - 1 <= L - 1)
+            L2 = int(res.nsteps.max().item()) + 1
+            free, _total = torch.cuda.mem_get_info(dev)
+            need = n * L2 * 32
+            if need > 0.9 * free:
+                raise MemoryError(f"{n} rays x {L2} states x 32 B = {need / 1e9:.1f} GB of ray-major trajectories exceed the "
+                                  f"free HBM ({free / 1e9:.1f} GB): use tiled=True (exactly sized), keep_traj=False, or chunks")
+            t = _st.trace_batch(f, *d_in, L=L2, st=st, dx=kw["dx"], dy=kw["dy"], traj=True, want_end=False)
+            res.traj, res.tiled = t.traj, False
+    torch.cuda.current_stream(dev).synchronize()
+    res = _host_results(res)
+    return RayBundle(n_field=n_field, x0=x0, y0=y0, freq=freq, st=st, amp=amp,
                      xg0=xg, yg0=yg, kx0=kx, ky0=ky, nsteps=res.nsteps, end_state=res.end_state, result=res, L=L,
                      receiver=(float(receiver[0]), receiver[1]) if receiver else None)

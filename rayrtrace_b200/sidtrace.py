@@ -27,10 +27,10 @@ from typing import Optional
 import numpy as np
 
 from . import _cabi
-from ._cabi import (F_DIV_IEEE, F_HOST_IO, F_REFILL, F_STATIC, F_TRAJ_HOST, F_TRAJ_TILED, SidtraceError, StbBatch, lib)
+from ._cabi import (F_DIV_IEEE, F_HOST_IO, F_NO_HOIST, F_REFILL, F_STATIC, F_TRAJ_HOST, F_TRAJ_TILED, SidtraceError, StbBatch, lib)
 
-__all__ = ["trace", "check", "trace_batch", "Field", "BatchResult", "invalidate", "pinned_empty", "pinned_copy",
-           "SidtraceError"]
+__all__ = ["trace", "check", "trace_batch", "trace_exact", "plan_trajectories", "TrajPlan", "Field", "BatchResult",
+           "invalidate", "pinned_empty", "pinned_copy", "SidtraceError"]
 
 
 def _torch():
@@ -139,26 +139,40 @@ class Field:
 _field_cache: dict = {}
 
 
-def _fingerprint(a: np.ndarray) -> tuple:
-    # runs on every legacy call: data pointer, shape and a 128-point strided content sample (~2 us)
-    flat = a.reshape(-1)
-    step = max(1, flat.size // 128)
-    return (a.__array_interface__["data"][0], a.shape, hash(flat[::step].tobytes()))
+_EXACT_COMPARE_BYTES = 4 << 20    # per array: below this a host copy is compared element for element
+
+
+def _fingerprint(a: np.ndarray):
+    """What identifies the CONTENT of a legacy-call field array.  Runs on every legacy call, so it has
+    to stay far below the round trip it guards (~80 us): arrays up to 4 MB (a 700^2 grid; the
+    reference's customary 201^2 is 0.3 MB, ~15 us) keep a host copy that is compared element for
+    element -- exact; larger ones a wrap-around sum and an xor over the whole buffer read as uint64
+    (every single-element edit changes both; ~1 ms per 16 MB)."""
+    if a.nbytes <= _EXACT_COMPARE_BYTES:
+        return a.copy()
+    w = a.reshape(-1).view(np.uint64)
+    return (a.__array_interface__["data"][0], a.shape, int(w.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(w)))
+
+
+def _same(fp, a: np.ndarray) -> bool:
+    if isinstance(fp, np.ndarray):      # bit for bit (NaN payloads and -0.0 included)
+        return fp.shape == a.shape and np.array_equal(fp.reshape(-1).view(np.uint64), a.reshape(-1).view(np.uint64))
+    return fp == _fingerprint(a)
 
 
 def _cached_field(ax: np.ndarray, ay: np.ndarray, nx: int, ny: int) -> Field:
-    """The reference re-reads ax/ay from host memory on every call; here the
-    upload is cached per (ax, ay) object pair.  Identity is (id, data pointer,
-    shape, strided content sample); a weakref drops the entry when ax dies.
-    After mutating ax/ay IN PLACE call ``invalidate()``."""
+    """The reference re-reads ax/ay from host memory on every call; here the upload is cached per
+    (ax, ay) object pair and re-done whenever their CONTENT changed since (see ``_fingerprint``), so
+    the unmodified ray.py can edit a field in place between rays and still trace through what it
+    sees.  A weakref drops the entry when ax dies; ``invalidate()`` drops everything."""
     key = (id(ax), id(ay), nx, ny)
-    fp = (_fingerprint(ax), _fingerprint(ay))
     ent = _field_cache.get(key)
-    if ent is not None and ent[1] == fp:
+    if ent is not None and _same(ent[1][0], ax) and _same(ent[1][1], ay):
         return ent[0]
     if ent is not None:
         ent[0].close()
     f = Field(ax, ay, nx, ny)
+    fp = (_fingerprint(ax), _fingerprint(ay))
     try:
         ref = weakref.ref(ax, lambda _r, k=key: _drop(k))
     except TypeError:
@@ -241,12 +255,16 @@ class BatchResult:
     cross_state: object = None  # float64 [6, nrays]  x, y (cm), kx, ky, lax, ph at the first crossing
     lookup_xy: object = None    # float64 [4, nrays]  points of the ray at the two target phases (xA, yA, xB, yB)
     tiled: bool = False         # traj is [ntiles, L, T, 4] (tile = ray // T, slot = ray % T; T = 32 ... 256)
+    plan: object = None         # TrajPlan: traj is a packed arena [total_rows, T, 4] (exactly sized, length-sorted)
 
     def ray_states(self, r: int, n: Optional[int] = None):
         """View [n, 4] of the first n states (default nsteps[r], the part the reference's
         Ray keeps, ray.py:99-102) of ray r, whatever the layout -- no copy."""
         if n is None:
             n = int(self.nsteps[r])
+        if self.plan is not None:
+            row0, _rows, lane = self.plan.locate(r)
+            return self.traj[row0:row0 + n, lane, :]
         if self.tiled:
             t = self.traj.shape[2]
             return self.traj[r // t, :n, r % t, :]
@@ -259,11 +277,67 @@ class BatchResult:
 
     def traj_ray_major(self):
         """The trajectories as a [nrays, L, 4] tensor (a copy when the layout is tiled)."""
+        if self.plan is not None:
+            raise ValueError("a packed arena has no common L: use ray_states(r) or export.pack")
         if not self.tiled:
             return self.traj
         nt, L, t = self.traj.shape[0], self.traj.shape[1], self.traj.shape[2]
         n = int(self.nsteps.shape[0])
         return self.traj.permute(0, 2, 1, 3).reshape(nt * t, L, 4)[:n]
+
+
+@dataclass
+class TrajPlan:
+    """Layout of an exactly-sized, length-sorted trajectory arena (``stb_traj_plan``): rays sorted by
+    step count (longest first, ties in launch order), ``tile`` consecutive ones per tile, a tile owns
+    (step count of its longest ray + 1) rows of ``tile`` x 32 B.  The arena is a [total_rows, tile, 4]
+    float64 CUDA tensor; state j of ray r is ``arena[tile_off[slot_of[r] // tile] + j, slot_of[r] % tile]``."""
+    tile: int
+    nrays: int
+    perm: object          # int32 [ntiles*tile] CUDA: slot -> ray (-1 empty)
+    slot_of: object       # int32 [nrays] CUDA: ray -> slot
+    tile_off: object      # int64 [ntiles+1] CUDA: first row of every tile
+    total_rows: int
+    _host: object = None
+
+    @property
+    def nslots(self) -> int:
+        return int(self.perm.shape[0])
+
+    @property
+    def arena_bytes(self) -> int:
+        return self.total_rows * self.tile * 32
+
+    def locate(self, r: int):
+        """(first row, rows of the tile, lane) of ray r."""
+        if self._host is None:
+            self._host = (self.slot_of.cpu().numpy(), self.tile_off.cpu().numpy())
+        slot_of, tile_off = self._host
+        slot = int(slot_of[r])
+        t = slot // self.tile
+        return int(tile_off[t]), int(tile_off[t + 1] - tile_off[t]), slot % self.tile
+
+
+def plan_trajectories(nsteps, *, tile: int = 256, L: int = 0, stream=None) -> TrajPlan:
+    """Plan an exactly-sized arena from the step counts of a first pass (int32 CUDA tensor)."""
+    torch = _torch()
+    if not _is_tensor(nsteps) or nsteps.dtype != torch.int32 or not nsteps.is_cuda or not nsteps.is_contiguous() or nsteps.ndim != 1:
+        raise TypeError("nsteps must be a contiguous 1-D int32 CUDA tensor")
+    if tile not in (32, 64, 128, 256):
+        raise ValueError("tile must be 32, 64, 128 or 256")
+    dev = nsteps.device
+    n = int(nsteps.shape[0])
+    ntiles = (n + tile - 1) // tile
+    perm = torch.empty(ntiles * tile, dtype=torch.int32, device=dev)
+    slot_of = torch.empty(n, dtype=torch.int32, device=dev)
+    tile_off = torch.zeros(ntiles + 1, dtype=torch.int64, device=dev)
+    total = ctypes.c_int64()
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    _cabi.check(lib.stb_set_device(dev.index or 0))
+    _cabi.check(lib.stb_traj_plan(nsteps.data_ptr(), n, tile, int(L), perm.data_ptr(), slot_of.data_ptr(),
+                                  tile_off.data_ptr(), ctypes.byref(total), ctypes.c_void_p(stream.cuda_stream)))
+    return TrajPlan(tile=tile, nrays=n, perm=perm, slot_of=slot_of, tile_off=tile_off, total_rows=int(total.value))
 
 
 def _ptr(a):
@@ -279,8 +353,8 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
                 hist=None, nbins: int = 0, amp=None, xorg: float = 0.0, yorg: float = 0.0,
                 r_lcs: float = 1.0, rho_max: float = 1.0, traj_host: bool = False,
                 div_ieee: bool = False, refill: Optional[bool] = None, tiled: bool = False, tile: int = 256,
-                cross=None, x0_phys=None, y0_phys=None, lookup_ph=None,
-                out: Optional[BatchResult] = None, stream=None) -> BatchResult:
+                cross=None, x0_phys=None, y0_phys=None, lookup_ph=None, hoist: bool = True,
+                plan: Optional[TrajPlan] = None, out: Optional[BatchResult] = None, stream=None) -> BatchResult:
     """Trace ``len(x0)`` rays in one launch.
 
     x0, y0, kx0, ky0: launch states (grid units / cm^-1, ray.py:62-68), all numpy
@@ -301,6 +375,13 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     lookup_ph: [2, nrays] target phases (needs ``cross``): the rays are traced again and each one --
     with its crossing point inserted, as after addpoint -- is sampled at its two target phases
     like ``interp1d(r.ph, r.x, fill_value='extrapolate')`` (beam.py:410-413); fills ``lookup_xy``.
+    hoist: launches with one global step read the four cell-only products of a step
+    (sidtracemodule.c:41-45) from a per-(field, st) table built once and cached on the field --
+    bit-identical results, 14 instead of 20 FP64 instructions per step; False keeps the 16-byte
+    {ax, ay} cells (A/B measurements).
+    plan: a ``TrajPlan`` (from ``plan_trajectories``): ``traj`` is then the packed arena
+    [plan.total_rows, plan.tile, 4] (``True`` allocates it) and the rays are traced in the plan's
+    length-sorted order on the tiled schedule -- see ``trace_exact`` for the two-pass driver.
     tiled: trajectory layout [ceil(nrays/T), L, T, 4] (T = ``tile`` = 256, 128, 64 or 32 rays)
     instead of [nrays, L, 4]: every warp-step becomes one coalesced 1 KB row store and a 256-thread
     CTA writes 8 KB contiguous rows (the fast layout; read rays back with ``BatchResult.ray_states``).
@@ -385,11 +466,23 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
         flags |= F_DIV_IEEE
     if refill is not None:
         flags |= F_REFILL if refill else F_STATIC
+    if not hoist:
+        flags |= F_NO_HOIST
 
+    if plan is not None:
+        if not dev_io:
+            raise ValueError("a packed plan needs device I/O (CUDA launch states)")
+        if plan.nrays != n:
+            raise ValueError(f"the plan was made for {plan.nrays} rays, not {n}")
+        tiled, tile = True, plan.tile
+        if traj is None:
+            raise ValueError("plan= is a trajectory layout: pass traj=True or the arena")
     tile = int(tile)
     if tile not in (32, 64, 128, 256):
         raise ValueError('tile must be 32, 64, 128 or 256')
     tshape = ((n + tile - 1) // tile, L, tile, 4) if tiled else (n, L, 4)
+    if plan is not None:
+        tshape = (plan.total_rows, tile, 4)
     if tiled:
         flags |= F_TRAJ_TILED
         if traj_host:
@@ -397,6 +490,8 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     if traj is True:
         if traj_host and not dev_io:
             traj = np.zeros((n, L, 4), np.float64)
+        elif plan is not None:
+            traj = torch.empty(tshape, dtype=torch.float64, device=device)   # every row a view can reach is written
         else:
             traj = torch.zeros(tshape, dtype=torch.float64, device=device)
     if traj is not None:
@@ -410,7 +505,8 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
                 raise ValueError(f"traj must have shape ({n}, {L}, 4)")
             flags |= F_TRAJ_HOST
         res.traj = traj
-        res.tiled = bool(tiled)
+        res.tiled = bool(tiled) and plan is None
+        res.plan = plan
 
     if hist is None and nbins:
         hist = torch.zeros(nbins, dtype=torch.float64, device=device) if dev_io else np.zeros(nbins)
@@ -452,8 +548,45 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
         if lookup_ph is not None:
             b.lookup_ph, b.lookup_xy = _ptr(lookup_ph), _ptr(res.lookup_xy)
 
+    if plan is not None:
+        b.traj_perm, b.traj_tile_off, b.traj_nslots = plan.perm.data_ptr(), plan.tile_off.data_ptr(), plan.nslots
+
     if stream is None:
         stream = torch.cuda.current_stream(device)
     sptr = ctypes.c_void_p(stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
     _cabi.check(lib.stb_trace_batch(field._h, ctypes.byref(b), sptr))
+    return res
+
+
+def trace_exact(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float, dy: float, tile: int = 256,
+                want_extras: bool = False, cross=None, x0_phys=None, y0_phys=None, div_ieee: bool = False,
+                max_bytes: Optional[int] = None, out: Optional[BatchResult] = None, **kw) -> BatchResult:
+    """Every kept state of every ray in HBM, in an arena sized exactly for them -- whatever the
+    spread of step counts, with the reference's own cap (``L`` = Ray.MaxStep, ray.py:11) costing nothing.
+
+    Pass 1 traces without trajectory output (lane-refill schedule: a trapped ray never idles a warp)
+    and yields every O(rays) result: step counts, end states, optional fused sums / crossing.
+    ``stb_traj_plan`` sorts the rays by step count (longest first) into tiles and sizes every tile
+    for its longest ray.  Pass 2 traces the rays again in that order on the tiled schedule: the lanes of
+    a warp end within a few steps of each other (no lock-step idling) and every warp-step is one
+    coalesced row of the packed arena.  Device I/O only (CUDA tensors).  Raises MemoryError when the
+    arena would exceed ``max_bytes`` (default: 90 % of the free HBM)."""
+    torch = _torch()
+    if not _is_tensor(x0):
+        raise TypeError("trace_exact takes CUDA tensors (device I/O)")
+    res = trace_batch(field, x0, y0, kx0, ky0, L=L, st=st, dx=dx, dy=dy, want_extras=want_extras, cross=cross,
+                      x0_phys=x0_phys, y0_phys=y0_phys, div_ieee=div_ieee, out=out, **kw)
+    plan = plan_trajectories(res.nsteps, tile=tile, L=L)
+    if max_bytes is None:
+        free, _total = torch.cuda.mem_get_info(x0.device)
+        max_bytes = int(0.9 * free)
+    if plan.arena_bytes > max_bytes:
+        raise MemoryError(f"{plan.nrays} rays keep {plan.total_rows * plan.tile} states = {plan.arena_bytes / 1e9:.1f} GB "
+                          f"of trajectories, more than the {max_bytes / 1e9:.1f} GB allowed: trace the beam in chunks "
+                          f"or keep per-ray outputs only")
+    # pass 2: trajectories only (the per-ray outputs of pass 1 stand; same inputs, same bits)
+    t = BatchResult(nsteps=torch.empty_like(res.nsteps))
+    trace_batch(field, x0, y0, kx0, ky0, L=L, st=st, dx=dx, dy=dy, traj=True, plan=plan, want_end=False,
+                div_ieee=div_ieee, out=t, **{k: v for k, v in kw.items() if k in ("st_ray", "hoist", "stream")})
+    res.traj, res.plan, res.tiled = t.traj, plan, False
     return res

@@ -55,3 +55,8 @@ def beam_fix():
 @pytest.fixture(scope="session")
 def ft2_phases_fix():
     return np.load(os.path.join(GOLDEN, "ft2_phases.npz"))
+
+
+@pytest.fixture(scope="session")
+def long_rays_fix():
+    return np.load(os.path.join(GOLDEN, "long_rays.npz"))

@@ -349,10 +349,53 @@ def make_ft2_phases():
     print("ft2_phases: ph_by_sig[a=1] =", np.round(ph_sig[-1], 4), " dense[a=4.5] =", np.round(dph_sig[-1], 4))
 
 
+def ring_density(nx, half=10.0):
+    """An over-dense ring around a hollow core: a closed cavity for rays launched inside it."""
+    x = np.linspace(-half, half, nx)
+    X, Y = np.meshgrid(x, x)
+    r = np.sqrt(X ** 2 + Y ** 2)
+    return 4.0e14 * np.exp(-((r - 6.0) / 2.5) ** 2) + 1e12, x, x
+
+
+def make_long_rays(den):
+    """Rays that need more than 2*nx steps -- the regime a fixed "a vacuum ray crosses the grid in ~nx
+    steps" cap gets wrong: the reference's Beam.rays (one ray.Ray per start point, cap Ray.MaxStep =
+    100000, ray.py:11) through a 201^2 FT-2 profile whose peak density sits at the cutoff (a narrow fan:
+    the central rays crawl through N -> 0 for 500+ steps) and inside an over-dense ring (a cavity: every
+    ray bounces between the walls for ~2000 steps, 10 x nx).  Stored per ray: launch conditions, number of
+    kept points, last kept point, final eikonal phase and path length, SHA-256 of the four kept arrays."""
+    import beam as refbeam
+    out = {}
+    nx = 201
+    nc = den.critical_den(136.268e9)
+    cases = (("near", ft2_density(nx, 1.001 * nc), (0.0, -10.0), 41, 0.9),
+             ("ring", ring_density(nx), (0.3, -2.0), 21, 1e-3))
+    for tag, (n, x, y), (xa, ya), rnum, ampbnd in cases:
+        nf = den.Nfield(n, x=x, y=y)
+        tx = refbeam.Beam(x0=xa, y0=ya, kx0=0, ky0=1)
+        lx, ly, lkx, lky, amps, phase, dist = tx.rays(rnum=rnum, dist=3, ampbnd=ampbnd, n_field=nf)
+        rays = tx._rays
+        nk = np.array([len(r.x) for r in rays])
+        out.update({f"{tag}_ant": np.array([xa, ya]), f"{tag}_rnum": np.int64(rnum), f"{tag}_ampbnd": np.float64(ampbnd),
+                    f"{tag}_launch": np.stack([lx, ly, lkx, lky, amps]), f"{tag}_nkept": nk,
+                    f"{tag}_last": np.array([[r.x[-1], r.y[-1], r.kx[-1], r.ky[-1]] for r in rays]),
+                    f"{tag}_k0": np.array([[r.kx[0], r.ky[0]] for r in rays]),
+                    f"{tag}_ph_end": np.array([r.ph[-1] for r in rays]), f"{tag}_lax_end": np.array([r.lax[-1] for r in rays]),
+                    f"{tag}_sha": np.array([sha(np.stack([r.x, r.y, r.kx, r.ky], 1)) for r in rays]),
+                    f"{tag}_st": np.float64(nf.st)})
+        print(f"long_rays[{tag}]: kept points min/median/max = {nk.min()}/{int(np.median(nk))}/{nk.max()}, "
+              f"beyond 2*nx = 402: {(nk > 402).sum()} of {len(nk)}, beyond 511: {(nk > 511).sum()}")
+    out["near_n0"] = np.float64(1.001 * nc)
+    np.savez_compressed(os.path.join(HERE, "long_rays.npz"), nx=np.int64(nx), **out)
+
+
 if __name__ == "__main__":
     if not oracle.have_ref():
         oracle.build(ref=True)
     den, ray = refenv.modules()
+    if "--only-long" in sys.argv:
+        make_long_rays(den)
+        sys.exit(0)
     make_kat(oracle.ref())
     make_ft2_ray(den, ray)
     make_ft2_fan(den)
@@ -360,5 +403,6 @@ if __name__ == "__main__":
     make_ft2_cross(den, ray)
     make_beam(den)
     make_ft2_phases()
-    for f in ("kat.npz", "ft2_ray.npz", "ft2_fan.npz", "rxyten_fan.npz", "ft2_cross.npz", "beam.npz", "ft2_phases.npz"):
+    make_long_rays(den)
+    for f in ("kat.npz", "ft2_ray.npz", "ft2_fan.npz", "rxyten_fan.npz", "ft2_cross.npz", "beam.npz", "ft2_phases.npz", "long_rays.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -45,9 +45,10 @@ def test_legacy_trace_kat_bitwise(st, kat, name):
 
 
 def test_legacy_calls_follow_their_field_arrays_and_turning_rays(st, oracle_mod):
-    """The per-ray surface caches the field upload per (ax, ay) pair: new arrays, arrays rescaled in
-    place, and single-element edits followed by invalidate() must all be seen; rays that wander and
-    turn several times stay bit-exact."""
+    """The per-ray surface caches the field upload per (ax, ay) pair and re-uploads whenever the CONTENT
+    changed (exact comparison): new arrays, arrays rescaled in place and single-element edits are all
+    seen without any call from the user -- the unmodified ray.py never calls invalidate(); rays that
+    wander and turn several times stay bit-exact."""
     rng = np.random.default_rng(21)
     nx, ny, L = 97, 81, 3000
 
@@ -75,10 +76,13 @@ def test_legacy_calls_follow_their_field_arrays_and_turning_rays(st, oracle_mod)
     n2 = both(bx, by, launch)
     ax *= 1.7; ay *= 0.6                                      # in place, caught by the content sample
     n3 = both(ax, ay, launch)
-    ax[int(launch[1]), int(launch[0])] += 0.5                 # one cell, in place: needs invalidate()
-    st.invalidate()
+    ax[int(launch[1]), int(launch[0])] += 0.5                 # one cell, in place: seen as well
     n4 = both(ax, ay, launch)
-    assert len({n1, n2, n3, n4}) > 1
+    ay[int(launch[1]) + 1, int(launch[0])] = -ay[int(launch[1]) + 1, int(launch[0])] - 0.3
+    n5 = both(ax, ay, launch)
+    st.invalidate()
+    assert both(ax, ay, launch) == n5
+    assert len({n1, n2, n3, n4, n5}) > 1
 
 
 def test_legacy_check_and_device_layout(st):
@@ -967,3 +971,224 @@ def test_beam_launch_conditions_device_match_host(st, beam_fix, rnum):
     devo = [t.cpu().numpy() for t in b.launch_conditions_device(rnum, wf, 0.998)]
     for h, d, name in zip(host[:5], devo, ("x", "y", "kx", "ky", "amp")):
         np.testing.assert_allclose(d, h, rtol=1e-11, atol=1e-11, err_msg=name)
+
+
+# ---------------------------------------------------------------- round 2: hoisted table, exact arenas, the reference's cap
+@pytest.mark.parametrize("mode", ["endpoints", "traj", "traj-tiled", "extras", "cross", "hist"])
+@pytest.mark.parametrize("refill", [True, False])
+def test_hoisted_table_equals_plain_cells(st, torch_mod, oracle_mod, mode, refill):
+    """Launches with one global step read the four cell-only products of sidtracemodule.c:41-45 from a
+    per-(field, st) table (HOIST kernels); the same launch with hoist=False recomputes them per step.
+    Same operations on the same operands: every output is bit-identical (the histogram to 1e-12: atomics)."""
+    rng = np.random.default_rng(31)
+    nx, ny, n, L = 150, 131, 3001, 500
+    ax, ay = random_field(rng, nx, ny, scale=0.02)
+    x0, y0, kx0, ky0 = random_launch(rng, n, nx, ny)
+    x0[0] = -1.0; y0[1] = np.nan; kx0[2] = 0.0
+    f = st.Field(ax, ay, nx, ny)
+    kw = dict(L=L, st=0.41, dx=0.9, dy=1.1, refill=refill)
+    if mode == "traj":
+        kw.update(traj=True)
+    elif mode == "traj-tiled":
+        kw.update(traj=True, tiled=True)
+    elif mode == "extras":
+        kw.update(want_extras=True)
+    elif mode == "cross":
+        kw.update(cross=(70.0, "y"), x0_phys=x0 * 0.9 - 3.0, y0_phys=y0 * 1.1 + 2.0)
+    elif mode == "hist":
+        kw.update(nbins=32, amp=rng.uniform(0.5, 1, n), xorg=-60.0, yorg=-70.0, r_lcs=50.0, rho_max=1.4)
+    a = st.trace_batch(f, x0, y0, kx0, ky0, hoist=True, **kw)
+    b = st.trace_batch(f, x0, y0, kx0, ky0, hoist=False, **kw)
+    torch_mod.cuda.synchronize()
+    want = oracle_mod.trace_batch(x0, y0, kx0, ky0, L, 0.41, 0.9, 1.1, nx, ny, ax, ay)
+    assert np.array_equal(a.nsteps, want["nsteps"]) and np.array_equal(b.nsteps, want["nsteps"])
+    assert a.end_state.tobytes() == want["end"].tobytes() == b.end_state.tobytes()
+    if mode.startswith("traj"):
+        assert a.traj_ray_major().cpu().numpy().tobytes() == want["traj"].tobytes()
+    for name in ("turn_index", "turn_state", "lax_end", "ph_end", "cross_count", "cross_index", "cross_flags", "cross_state"):
+        va, vb = getattr(a, name), getattr(b, name)
+        if va is not None:
+            assert np.asarray(va).tobytes() == np.asarray(vb).tobytes(), name
+    if mode == "hist":
+        assert np.abs(a.hist - b.hist).sum() <= 1e-12 * np.abs(b.hist).sum()
+    f.close()
+
+
+def test_hoisted_tables_of_many_steps_share_one_field(st, torch_mod, oracle_mod):
+    """The field keeps four hoisted tables (LRU): six step values traced round-robin, on two streams,
+    evict and rebuild them; every launch matches the oracle."""
+    rng = np.random.default_rng(8)
+    nx, ny, n, L = 90, 70, 2000, 260
+    ax, ay = random_field(rng, nx, ny, scale=0.03)
+    launch = random_launch(rng, n, nx, ny)
+    d_in = [torch_mod.from_numpy(a).cuda() for a in launch]
+    f = st.Field(ax, ay, nx, ny)
+    steps = [0.2, 0.25, 0.3, 0.35, 0.4, 0.45]
+    want = {s: oracle_mod.trace_batch(*launch, L, s, 1.0, 1.0, nx, ny, ax, ay) for s in steps}
+    streams = [torch_mod.cuda.Stream(), torch_mod.cuda.Stream()]
+    got = []
+    for rep in range(3):
+        for k, s in enumerate(steps):
+            with torch_mod.cuda.stream(streams[k % 2]):
+                got.append((s, st.trace_batch(f, *d_in, L=L, st=s, dx=1.0, dy=1.0)))
+    torch_mod.cuda.synchronize()
+    for s, r in got:
+        assert np.array_equal(r.nsteps.cpu().numpy(), want[s]["nsteps"])
+        assert r.end_state.cpu().numpy().tobytes() == want[s]["end"].tobytes()
+    f.close()
+
+
+def test_queue_heads_are_not_shared_by_launches_in_flight(st, torch_mod, oracle_mod):
+    """More persistent launches in flight than the field has queue-head slots (64), on several
+    streams: a slot is reused only after the launch that used it last has finished, so no ray is
+    traced twice or skipped (the histogram would show it)."""
+    rng = np.random.default_rng(77)
+    nx, ny, n, L = 64, 64, 20000, 400
+    ax, ay = random_field(rng, nx, ny, scale=0.01)
+    launch = random_launch(rng, n, nx, ny)
+    d_in = [torch_mod.from_numpy(a).cuda() for a in launch]
+    f = st.Field(ax, ay, nx, ny)
+    want = oracle_mod.trace_batch(*launch, L, 0.3, 1.0, 1.0, nx, ny, ax, ay)
+    streams = [torch_mod.cuda.Stream() for _ in range(4)]
+    outs = []
+    for k in range(200):
+        with torch_mod.cuda.stream(streams[k % 4]):
+            outs.append(st.trace_batch(f, *d_in, L=L, st=0.3, dx=1.0, dy=1.0, refill=True, nbins=8, xorg=-32.0, yorg=-32.0,
+                                       r_lcs=30.0, rho_max=1.5))
+    torch_mod.cuda.synchronize()
+    ref_hist = outs[0].hist.cpu().numpy()
+    for r in outs:
+        assert np.array_equal(r.nsteps.cpu().numpy(), want["nsteps"])
+        assert np.abs(r.hist.cpu().numpy() - ref_hist).sum() <= 1e-12 * np.abs(ref_hist).sum()
+    f.close()
+
+
+@pytest.mark.parametrize("tile", [32, 256])
+@pytest.mark.parametrize("nrays", [1, 255, 1000])
+def test_exact_arena_heavy_tailed_bitwise(st, torch_mod, oracle_mod, tile, nrays):
+    """trace_exact: a first pass yields the step counts, stb_traj_plan sorts the rays by length into
+    tiles sized for their longest ray, a second pass writes every kept state into the packed arena.
+    Heavy-tailed lengths (strong random field, a cap that some rays hit, bad starts): every ray's states
+    0..i equal the oracle's, the arena holds exactly sum(rows_t) * T states, and the plan is a permutation."""
+    rng = np.random.default_rng(1000 + nrays)
+    nx, ny, L = 97, 81, 3000
+    ax, ay = random_field(rng, nx, ny, scale=0.05)
+    launch = list(random_launch(rng, nrays, nx, ny, kmag=0.6))
+    if nrays > 8:
+        launch[0][3] = -5.0; launch[1][5] = np.nan
+    d_in = [torch_mod.from_numpy(a).cuda() for a in launch]
+    f = st.Field(ax, ay, nx, ny)
+    res = st.trace_exact(f, *d_in, L=L, st=0.35, dx=1.0, dy=0.8, tile=tile, want_extras=True)
+    torch_mod.cuda.synchronize()
+    want = oracle_mod.trace_batch(*launch, L, 0.35, 1.0, 0.8, nx, ny, ax, ay)
+    ns = res.nsteps.cpu().numpy()
+    assert np.array_equal(ns, want["nsteps"])
+    assert res.end_state.cpu().numpy().tobytes() == want["end"].tobytes()
+    plan = res.plan
+    perm = plan.perm.cpu().numpy()
+    assert sorted(perm[perm >= 0].tolist()) == list(range(nrays))
+    assert np.all(np.diff(ns[perm[perm >= 0]]) <= 0)                        # longest first
+    toff = plan.tile_off.cpu().numpy()
+    rows = np.diff(toff)
+    assert plan.total_rows == toff[-1] == rows.sum()
+    for t in range(len(rows)):
+        members = perm[t * tile:(t + 1) * tile]
+        assert rows[t] == ns[members[members >= 0]].max() + 1
+    assert tuple(res.traj.shape) == (plan.total_rows, tile, 4)
+    assert plan.total_rows * tile <= (ns + 1).sum() + tile * L and plan.arena_bytes == res.traj.numel() * 8
+    step = max(1, nrays // 97)
+    for r in list(range(0, nrays, step)) + [int(np.argmax(ns)), int(np.argmin(ns))]:
+        got = res.ray_states(r, int(ns[r]) + 1).cpu().numpy()
+        assert got.tobytes() == want["traj"][r, :ns[r] + 1].tobytes(), r
+    f.close()
+
+
+def test_exact_arena_export_packs_kept_states(st, torch_mod, oracle_mod):
+    """stb_pack_traj_plan: the packed arena -> [sum(nsteps), 4] in launch order, the kept states the
+    reference's Ray holds (ray.py:99-102)."""
+    import ctypes
+    rng = np.random.default_rng(4)
+    nx, ny, n, L = 60, 50, 700, 900
+    ax, ay = random_field(rng, nx, ny, scale=0.04)
+    launch = random_launch(rng, n, nx, ny, kmag=0.7)
+    d_in = [torch_mod.from_numpy(a).cuda() for a in launch]
+    f = st.Field(ax, ay, nx, ny)
+    res = st.trace_exact(f, *d_in, L=L, st=0.3, dx=1.0, dy=1.0, tile=64)
+    want = oracle_mod.trace_batch(*launch, L, 0.3, 1.0, 1.0, nx, ny, ax, ay)
+    ns = res.nsteps.to(torch_mod.int64)
+    off = torch_mod.zeros(n + 1, dtype=torch_mod.int64, device=ns.device)
+    off[1:] = torch_mod.cumsum(ns, 0)
+    out = torch_mod.empty((int(off[-1]), 4), dtype=torch_mod.float64, device=ns.device)
+    lib = st._cabi.lib
+    st._cabi.check(lib.stb_pack_traj_plan(res.traj.data_ptr(), 64, res.plan.slot_of.data_ptr(), res.plan.tile_off.data_ptr(), n,
+                                          res.nsteps.data_ptr(), off.data_ptr(), out.data_ptr(),
+                                          ctypes.c_void_p(torch_mod.cuda.current_stream().cuda_stream)))
+    torch_mod.cuda.synchronize()
+    exp = np.concatenate([want["traj"][r, :want["nsteps"][r]] for r in range(n)])
+    assert out.cpu().numpy().tobytes() == exp.tobytes()
+    f.close()
+
+
+@pytest.mark.parametrize("tag", ["near", "ring"])
+@pytest.mark.parametrize("tiled", [True, False])
+def test_beam_rays_run_to_the_reference_cap(st, long_rays_fix, tag, tiled):
+    """Beam.rays with NO max_steps equals the reference for rays far beyond 2*nx steps (the reference's
+    cap is Ray.MaxStep = 100000, ray.py:11): a near-cutoff fan whose central rays crawl for 500+ steps
+    and a cavity in which every ray bounces for ~2000 steps on a 201^2 grid.  Fixture: the reference's
+    own Beam.rays / Ray (tests/golden/make_golden.py make_long_rays)."""
+    from rayrtrace_b200.beam import Beam
+    fx = long_rays_fix
+    nf = _long_rays_field(fx, tag)
+    assert float(nf.st) == float(fx[f"{tag}_st"])
+    xa, ya = fx[f"{tag}_ant"]
+    b = Beam(x0=float(xa), y0=float(ya), kx0=0, ky0=1)
+    out = b.rays(rnum=int(fx[f"{tag}_rnum"]), dist=3, ampbnd=float(fx[f"{tag}_ampbnd"]), n_field=nf, tiled=tiled)
+    np.testing.assert_allclose(np.stack(out[:5]), fx[f"{tag}_launch"], rtol=1e-12, atol=1e-13)
+    bun = b.bundle
+    nk = fx[f"{tag}_nkept"]
+    assert nk.max() > 511                                   # beyond the old default cap
+    assert np.array_equal(bun.nsteps, nk)
+    np.testing.assert_allclose(bun.result.ph_end, fx[f"{tag}_ph_end"], rtol=1e-9)
+    np.testing.assert_allclose(bun.result.lax_end, fx[f"{tag}_lax_end"], rtol=1e-9)
+    for r in (0, len(nk) // 2, int(np.argmax(nk))):
+        ray = bun.ray(r)
+        assert len(ray.x) == nk[r]
+        np.testing.assert_allclose([ray.x[-1], ray.y[-1], ray.kx[-1], ray.ky[-1]], fx[f"{tag}_last"][r], rtol=1e-8, atol=1e-9)
+
+
+def _long_rays_field(fx, tag):
+    from rayrtrace_b200.nfield import Nfield
+    nx = int(fx["nx"])
+    if tag == "near":
+        n, x, y = ft2_density(nx, float(fx["near_n0"]))
+    else:
+        x = np.linspace(-10.0, 10.0, nx)
+        X, Y = np.meshgrid(x, x)
+        n, y = 4.0e14 * np.exp(-((np.sqrt(X ** 2 + Y ** 2) - 6.0) / 2.5) ** 2) + 1e12, x
+    return Nfield(n, x=x, y=y)
+
+
+@pytest.mark.parametrize("tag", ["near", "ring"])
+def test_long_reference_rays_exact_launch_bitwise(st, torch_mod, long_rays_fix, tag):
+    """The reference's exact launch state (its own k0 after the refractive-index scaling) through
+    trace_exact with L = Ray.MaxStep: every kept array of every ray -- 500 to 2400 points on a 201^2
+    grid -- hashes to the reference Ray's (physical x, y as ray.py:105-106 forms them)."""
+    from rayrtrace_b200.ray import Ray
+    fx = long_rays_fix
+    nf = _long_rays_field(fx, tag)
+    lx, ly = fx[f"{tag}_launch"][0], fx[f"{tag}_launch"][1]
+    xg = np.ascontiguousarray(nf.x2grid(lx), np.float64)
+    yg = np.ascontiguousarray(nf.y2grid(ly), np.float64)
+    k0 = fx[f"{tag}_k0"]
+    d_in = [torch_mod.from_numpy(np.ascontiguousarray(a)).cuda() for a in (xg, yg, k0[:, 0], k0[:, 1])]
+    res = st.trace_exact(nf.device_field(), *d_in, L=int(Ray.MaxStep), st=float(nf.st), dx=float(nf.dx[0]), dy=float(nf.dy[0]))
+    torch_mod.cuda.synchronize()
+    ns = res.nsteps.cpu().numpy()
+    assert np.array_equal(ns, fx[f"{tag}_nkept"])
+    import hashlib
+    for r in range(len(ns)):
+        t = res.ray_states(r).cpu().numpy()
+        x = lx[r] + (t[:, 0] - t[0, 0]) * nf.dx[0]
+        y = ly[r] + (t[:, 1] - t[0, 1]) * nf.dy[0]
+        got = hashlib.sha256(np.ascontiguousarray(np.stack([x, y, t[:, 2], t[:, 3]], 1)).tobytes()).hexdigest()
+        assert got == str(fx[f"{tag}_sha"][r]), r
