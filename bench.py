@@ -11,6 +11,16 @@ HBM) + per-ray step counts and end states.  Weak scaling: every rank traces
 its own 10^6-ray interleaved shard of an N*10^6-ray fan; no data-path
 collective (rays are independent).
 
+The same line carries, measured in the same invocation:
+  config5   BASELINE config 5 -- an N x 1.25*10^7-ray beam (10^8 rays at N = 8) on a 201^2 grid sharded
+            over the N ranks, endpoints + 64-bin deposition histogram, NCCL all-reduce of the histogram and
+            the per-ray summaries of the whole beam gathered in global ray order on rank 0
+            (rayrtrace_b200.dist.trace_sharded): the sharded path WITH its exchange, max over ranks;
+  endpoint_mode   the O(rays)-output mode of config 3 against the measured FP64 peak;
+  exact_arena     config 3 through the two-pass exactly-sized trajectory arena (trace_exact);
+  parity_check    a >= 10^4-ray subsample of the timed kernel's trajectories, bit for bit against the oracle
+                  (untimed; the oracle is the checker, never the thing measured).
+
 Prints ONE JSON line on rank 0 (contract: task statement / DESIGN.md section 6).
 """
 from __future__ import annotations
@@ -48,6 +58,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
     ap.add_argument("--extra", action="store_true", help="also time endpoint-only mode and the FP64 peak")
     ap.add_argument("--no-traj-export", action="store_true", help="skip the trajectories-to-host side measurement")
+    ap.add_argument("--no-config5", action="store_true", help="skip the sharded config-5 block")
+    ap.add_argument("--config5-rays", type=int, default=12_500_000, help="config-5 rays per GPU (10^8 / 8)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed trajectory digest against the oracle")
     ap.add_argument("--layout", default="tiled", choices=["tiled", "ray"],
                     help="trajectory layout: tiled [tile][step][32][4] (default) or ray-major [ray][step][4]")
     return ap.parse_args()
@@ -182,7 +195,8 @@ def load_peaks():
 
 
 def load_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any: evidence from
+    a profiling run of this command line, NOT a property of this run -- it is tagged with its source."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
@@ -195,6 +209,13 @@ def load_traffic():
 def workload_name(args):
     return (f"config3: {args.nrays}-ray seven-beam FT-2 fan per GPU, {args.nx}x{args.nx} shaped-density grid, "
             f"full trajectories f64 in HBM, layout {'[ray/256][step][ray%256][4]' if args.layout == 'tiled' else '[ray][step][4]'}")
+
+
+def make_config(args, cap_states):
+    """The `config` object of the JSON line -- byte-identical in both arms (--impl b200 / reference)."""
+    return {"workload": workload_name(args), "nx": args.nx, "nrays_per_gpu": args.nrays, "cap_states": int(cap_states),
+            "l2": "no explicit flush: every step streams ~26 GB of trajectory stores per GPU (>> 126 MB L2)",
+            "parallelism": f"rays interleaved over {args.gpus} rank(s), field replicated, no data-path collective"}
 
 
 # --------------------------------------------------------------------------
@@ -222,15 +243,126 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "nx": args.nx, "nrays_per_gpu": args.nrays, "cap_states": case.L,
-                   "note": "reference C extension (sidtracemodule.c, gcc -O2) called per ray as ray.py:80-83 does, "
-                           "one process per host core, prefaulted MaxStep buffers"},
+        "config": make_config(args, case.L),
+        "note": "reference C extension (sidtracemodule.c, gcc -O2) called per ray as ray.py:80-83 does, "
+                "one process per host core, prefaulted MaxStep buffers",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
     return 0
+
+
+def parity_digest(case, traj, nsteps_dev, tiled, sample=10_240):
+    """Untimed: a >= 10^4-ray subsample of the trajectories the timed kernel just wrote, state for state
+    against the oracle (the CPU restatement of sidtracemodule.c:36-48).  The oracle is the checker here,
+    never the thing measured."""
+    import hashlib
+    import oracle
+    import torch
+    n = case.nrays
+    m = min(n, sample)
+    sel = np.unique(np.linspace(0, n - 1, m).astype(np.int64))
+    nf = case.nfield
+    ns_gpu = nsteps_dev.cpu().numpy()[sel]
+    bad = 0
+    h_gpu, h_cpu = hashlib.sha256(), hashlib.sha256()
+    # chunks of 512 rays keep the host copy of the oracle's [rays, L, 4] block small
+    for lo in range(0, len(sel), 512):
+        part = sel[lo:lo + 512]
+        w = oracle.trace_batch(*[np.ascontiguousarray(a[part]) for a in case.launch], case.L, case.st, case.dx, case.dy,
+                               nf.nx, nf.ny, np.ascontiguousarray(nf.ax), np.ascontiguousarray(nf.ay), nthreads=4)
+        if not np.array_equal(w["nsteps"], ns_gpu[lo:lo + 512]):
+            bad += 1
+            continue
+        idx = torch.from_numpy(part).to(traj.device)
+        if tiled:
+            g = traj[idx // 256, :, idx % 256, :]            # [rays, L, 4]
+        else:
+            g = traj[idx]
+        g = g.cpu().numpy()
+        for r in range(len(part)):
+            k = int(w["nsteps"][r]) + 1
+            h_gpu.update(g[r, :k].tobytes())
+            h_cpu.update(w["traj"][r, :k].tobytes())
+    ok = bad == 0 and h_gpu.hexdigest() == h_cpu.hexdigest()
+    return {"result": "ok" if ok else "MISMATCH", "rays": int(len(sel)), "states": int((ns_gpu.astype(np.int64) + 1).sum()),
+            "sha256": h_gpu.hexdigest()[:16], "against": "oracle.trace_batch (CPU restatement of sidtracemodule.c:36-48), untimed"}
+
+
+def run_config5(args, rank, world, local_rank, dev, comm):
+    """BASELINE config 5 under the bench's clock: the ray-sharded beam WITH its exchange."""
+    import torch
+    import torch.distributed as dist
+    from rayrtrace_b200 import dist as rd, sidtrace, synth
+    n_global = args.config5_rays * world
+    idx = rd.shard_index(n_global, rank, world)
+    case = synth.beam_case(nx=201, nrays=n_global, seed=0, index=idx, device_launch=True)
+    nf = case.nfield
+    field = sidtrace.Field(np.ascontiguousarray(nf.ax), np.ascontiguousarray(nf.ay), nf.nx, nf.ny)
+    hist_kw = dict(xorg=float(nf.x[0]), yorg=float(nf.y[0]), r_lcs=synth.R_DIA, rho_max=1.2)
+    kw = dict(L=case.L, st=case.st, dx=case.dx, dy=case.dy)
+    staged = ([torch.from_numpy(a).to(dev) for a in case.launch], torch.from_numpy(case.amp).to(dev), n_global)
+    nbins = 64
+
+    def one():
+        # static grid: a clean beam has no stragglers, and CTAs that retire let the exchange kernels in
+        return rd.trace_sharded(field, None, staged=staged, nbins=nbins, hist_kw=hist_kw, gather="root", comm=comm,
+                                chunks=4, refill=False, timing=True, **kw)
+
+    for _ in range(2):
+        res, hist, gathered, tm = one()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    reps = max(3, min(args.steps, 5))
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    tms = []
+    e0.record()
+    for _ in range(reps):
+        res, hist, gathered, tm = one()
+        tms.append(tm)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    parts = np.array([[t.ms()[k] for k in ("kernel_ms", "total_ms", "exchange_exposed_ms")] for t in tms]).mean(0)
+    v = torch.tensor([e0.elapsed_time(e1) / reps, parts[0], parts[1], parts[2]], dtype=torch.float64, device=dev)
+    work = res.nsteps.sum().to(torch.float64).reshape(1)
+    if world > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    ms_pass, ms_kernel, ms_total, ms_exposed = (float(x) for x in v.tolist())
+    out = None
+    if rank == 0:
+        # spot check of the gathered result (untimed): 4096 global rays, their step counts and end states
+        # in GLOBAL order against the oracle on the same launch states
+        import oracle
+        sel = np.unique(np.linspace(0, n_global - 1, 4096).astype(np.int64))
+        sub = synth.beam_case(nx=201, nrays=n_global, seed=0, index=sel, device_launch=True)
+        w = oracle.trace_batch(*sub.launch, case.L, case.st, case.dx, case.dy, nf.nx, nf.ny, np.ascontiguousarray(nf.ax),
+                               np.ascontiguousarray(nf.ay), nthreads=4)
+        isel = torch.from_numpy(sel).to(dev)
+        same = bool(np.array_equal(gathered.nsteps[isel].cpu().numpy(), w["nsteps"])) and \
+            gathered.end_state[:, isel].cpu().numpy().tobytes() == w["end"].tobytes()
+        out = {
+            "workload": f"config5: {n_global}-ray seven-beam fan on a 201x201 grid sharded over {world} GPU(s) "
+                        f"({args.config5_rays} rays each, 256-ray blocks round-robin), endpoints + {nbins}-bin deposition "
+                        f"histogram; NCCL all-reduce of the histogram; step counts + end states of ALL rays gathered in "
+                        f"global ray order on rank 0 (36 B/ray), exchange of chunk k under the trace of chunk k+1",
+            "value": float(work.item()) / (ms_pass * 1e-3), "unit": UNIT, "ms_per_step": ms_pass, "steps": reps,
+            "ray_steps_per_step": float(work.item()), "kernel_ms": ms_kernel, "exchange_exposed_ms": ms_exposed,
+            "exchange_frac_of_pass": ms_exposed / ms_total if ms_total else None,
+            "gathered_bytes_on_root": int(n_global) * 36, "hist_sum": float(hist.sum().item()),
+            "transport": "stb_comm_* (NCCL via the C ABI)" if comm is not None else "single rank: no exchange",
+            "gathered_spot_check": {"result": "ok" if same else "MISMATCH", "rays": int(len(sel)),
+                                    "against": "oracle.trace_batch on the same launch states, global ray order, untimed"},
+        }
+    field.close()
+    del staged, gathered
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_b200(args):
@@ -262,11 +394,13 @@ def run_b200(args):
 
     import torch
     import torch.distributed as dist
-    from rayrtrace_b200 import _cabi, sidtrace
+    from rayrtrace_b200 import _cabi, dist as rd, sidtrace
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        comm = rd.Comm.from_torch(dev)
 
     nf = case.nfield
     field = sidtrace.Field(np.ascontiguousarray(nf.ax), np.ascontiguousarray(nf.ay), nf.nx, nf.ny)
@@ -286,7 +420,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)          # the contract asks for >= 3 warm-up steps; the line reports what ran
+    for _ in range(warmup):
         step()
     barrier()
     steps_per_launch = int(out.nsteps.sum().item())
@@ -320,6 +455,11 @@ def run_b200(args):
     total_ms = float(tm.item())
     global_steps_per_step = float(work.item())
     value = global_steps_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- untimed: the trajectories the timed kernel wrote, against the oracle ----------------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_digest(case, traj, out.nsteps, tiled)
 
     # ---- end to end through the public API with HOST buffers (pinned): H2D launch states,
     # kernel (full trajectories into HBM, kept resident for the device-side consumers),
@@ -362,29 +502,59 @@ def run_b200(args):
                              "copies overlapped with tracing on a second stream; PCIe-bound"}
         del out_pin
 
-    extra = {}
-    if args.extra and rank == 0:
+    # ---- the O(rays)-output mode of the same workload against the measured FP64 peak, and the
+    # two-pass exactly-sized arena (rank 0; a few ms each)
+    endpoint = exact = None
+    if rank == 0:
         import ctypes
         tf = ctypes.c_double()
         _cabi.check(_cabi.lib.stb_measure_fp64_peak(ctypes.byref(tf)))
         bw = ctypes.c_double()
         _cabi.check(_cabi.lib.stb_measure_store_bw(8 << 30, ctypes.byref(bw)))
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        kw0 = dict(kw, tiled=False)
+        kw0 = dict(kw, tiled=False, refill=False)
+        o0 = sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state)
         for _ in range(3):
-            sidtrace.trace_batch(field, *d_in, out=sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state), **kw0)
+            sidtrace.trace_batch(field, *d_in, out=o0, **kw0)
         torch.cuda.synchronize()
         e0.record()
         for _ in range(args.steps):
-            sidtrace.trace_batch(field, *d_in, out=sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state), **kw0)
+            sidtrace.trace_batch(field, *d_in, out=o0, **kw0)
         e1.record()
         torch.cuda.synchronize()
         ep = steps_per_launch * args.steps / (e0.elapsed_time(e1) * 1e-3)
-        extra = {"fp64_peak_tflops_measured": tf.value, "store_bw_gbs_measured": bw.value,
-                 "endpoint_mode_ray_steps_per_s": ep,
-                 "endpoint_mode_fp64_frac": ep * FLOPS_PER_RAY_STEP / (tf.value * 1e12) if tf.value else None}
+        endpoint = {"value": ep, "unit": UNIT, "ms_per_launch": e0.elapsed_time(e1) / args.steps,
+                    "fp64_peak_tflops_measured": tf.value, "store_bw_gbs_measured": bw.value,
+                    "fp64_frac": ep * FLOPS_PER_RAY_STEP / (tf.value * 1e12) if tf.value else None,
+                    "note": "step counts + end states only (static grid, hoisted per-cell products); 16 algorithmic flops per "
+                            "ray-step (SURVEY 8d) over a dependent-free DFMA peak measured in this run"}
+        del traj
+        out.traj = h_out.traj = None
+        torch.cuda.empty_cache()
+        kx = dict(L=L, st=case.st, dx=case.dx, dy=case.dy)
+        r = None
+        for _ in range(2):
+            r = sidtrace.trace_exact(field, *d_in, **kx)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(max(2, args.steps // 2)):
+            r = sidtrace.trace_exact(field, *d_in, **kx)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / max(2, args.steps // 2)
+        exact = {"value": steps_per_launch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                 "arena_bytes": int(r.plan.arena_bytes), "cap_sized_arena_bytes": int(((n + 255) // 256) * L * 256 * 32),
+                 "frac_of_hbm_peak": steps_per_launch * 32 / (ms * 1e-3) / 1e9 / load_peaks()[0],
+                 "note": "sidtrace.trace_exact: pass 1 (step counts, no trajectories) + stb_traj_plan (sort by length, "
+                         "exact tile sizes) + pass 2 (trajectories into the packed arena); the whole of it timed"}
+        del r
+        torch.cuda.empty_cache()
+
+    extra = {}
+    if args.extra and rank == 0:
         # the adaptive-RK extension (never part of the headline): 10^6 ordered rays, 1001^2 spline medium
         from rayrtrace_b200 import physics
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         xs_m = np.linspace(-10, 10, 1001)
         XX, YY = np.meshgrid(xs_m, xs_m)
         med = physics.Medium(0.6 * np.exp(-2.5 * (XX ** 2 + YY ** 2) / 7.85 ** 2), xs_m, xs_m)
@@ -407,8 +577,19 @@ def run_b200(args):
                                  "note": "extension beyond the reference (SURVEY 8 f-4); not parity, not the headline"}
         med.close()
 
+    # ---- BASELINE config 5: the sharded path with its exchange, every rank ---------------------------
+    field.close()
+    del d_in
+    out.traj = None
+    torch.cuda.empty_cache()
+    config5 = None
+    if not args.no_config5:
+        config5 = run_config5(args, rank, world, local_rank, dev, comm)
+
     if world > 1:
         dist.barrier()
+        if comm is not None:
+            comm.close()
         dist.destroy_process_group()
     if rank != 0:
         return 0
@@ -416,26 +597,32 @@ def run_b200(args):
     peak, peak_src = load_peaks()
     avg_kernel_ms = float(np.mean(kern_ms))
     achieved = BYTES_PER_RAY_STEP * steps_per_launch / (avg_kernel_ms * 1e-3) / 1e9
-    tr = load_traffic()
+    tr = load_traffic() if world == 1 else None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "warmup_requested": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "nx": args.nx, "nrays_per_gpu": n, "cap_states": L,
-                   "ray_steps_per_gpu_per_step": steps_per_launch,
-                   "l2": "no explicit flush: every step streams %.1f GB of trajectory stores (>> 126 MB L2)" % (steps_per_launch * 32 / 1e9),
-                   "parallelism": f"rays interleaved over {world} rank(s), field replicated, no data-path collective"},
+        "config": make_config(args, L),
+        "ray_steps_per_gpu_per_step": steps_per_launch,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (tr or {}).get("dram_bytes_per_launch"),
-                     "kernel": "stb::trace_kernel<TRAJ=1,EXTRAS=0,HIST=0,DIVC=1,REFILL=0,TILED=%d,CROSS=0,STRAY=0,LOOKUP=0,BLOCK=%d>" % (int(tiled), 256 if tiled else 128),
+                     "traffic_source": (tr or {}).get("source") if tr else
+                     ("not attached at N > 1: the ncu capture is a single-GPU profiling run" if world > 1 else None),
+                     "kernel": "stb::trace_kernel<TRAJ=1,EXTRAS=0,HIST=0,DIVC=1,REFILL=0,TILED=%d,CROSS=0,STRAY=0,LOOKUP=0,BLOCK=%d,HOIST=0>" % (int(tiled), 256 if tiled else 128),
                      "algorithmic_bytes_per_launch": BYTES_PER_RAY_STEP * steps_per_launch,
-                     "avg_launch_ms": avg_kernel_ms, "peak_source": peak_src},
+                     "avg_launch_ms": avg_kernel_ms, "peak_source": peak_src,
+                     "frac_vs_store_peak": (achieved / endpoint["store_bw_gbs_measured"]) if endpoint else None},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "host launch states in (pinned) -> kernel -> per-ray step counts + end states out; "
                         "trajectories stay resident in HBM"},
         "gpu_launches": int(launches),
         "clocks": clk,
+        "parity_check": parity,
+        "endpoint_mode": endpoint,
+        "exact_arena": exact,
+        "config5": config5,
     }
     if traj_host:
         line["e2e_traj_to_host"] = traj_host

@@ -249,6 +249,10 @@ int64_t stb_launch_count(void);
 int stb_measure_fp64_peak(double *tflops);
 /* Plain streaming-store bandwidth in GB/s over `bytes` of HBM. */
 int stb_measure_store_bw(size_t bytes, double *gbs);
+/* The store pattern of the static tiled trajectory kernel without its arithmetic: `ntiles` CTAs of `tile`
+ * threads, each thread writes `steps` 32-byte states at stride tile*32 B into its tile of `rows_per_tile`
+ * rows, with `chain` dependent DFMAs between two stores.  GB/s of the best of 4 timed launches. */
+int stb_measure_store_pattern(int64_t ntiles, int32_t tile, int64_t rows_per_tile, int32_t steps, int32_t chain, double *gbs);
 
 #ifdef __cplusplus
 }

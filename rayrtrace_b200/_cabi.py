@@ -14,7 +14,8 @@ from . import build as _build
 
 STB_ABI_VERSION = 3
 STB_OK = 0
-STB_ERR_ARG, STB_ERR_CUDA, STB_ERR_NOMEM, STB_ERR_RANGE = -1, -2, -3, -4
+STB_ERR_ARG, STB_ERR_CUDA, STB_ERR_NOMEM, STB_ERR_RANGE, STB_ERR_COMM = -1, -2, -3, -4, -5
+STB_COMM_ID_BYTES = 128
 
 F_HOST_IO = 1 << 0
 F_DIV_IEEE = 1 << 1
@@ -29,7 +30,11 @@ EXPORTS = (
     "stb_abi_version", "stb_last_error", "stb_device_count", "stb_set_device",
     "stb_field_create", "stb_field_destroy", "stb_field_shape", "stb_field_peek",
     "stb_trace", "stb_check", "stb_trace_batch", "stb_launch_states", "stb_beam_launch", "stb_field_pages", "stb_pack_traj", "stb_pack_traj_plan", "stb_traj_plan", "stb_launch_count",
-    "stb_measure_fp64_peak", "stb_measure_store_bw",
+    "stb_measure_fp64_peak", "stb_measure_store_bw", "stb_measure_store_pattern",
+    # include/sidtrace_b200_comm.h (multi-GPU entry points)
+    "stb_comm_unique_id", "stb_comm_init", "stb_comm_destroy", "stb_comm_rank", "stb_comm_allreduce_f64",
+    "stb_comm_allreduce_max_f64", "stb_comm_gather", "stb_comm_allgather", "stb_shard_local_blocks", "stb_shard_local_rays",
+    "stb_unshuffle_blocks",
     # include/sidtrace_b200_rk.h (adaptive-RK extension)
     "stb_medium_create", "stb_medium_destroy", "stb_medium_table", "stb_trace_rk",
 )
@@ -186,6 +191,24 @@ def _load() -> ctypes.CDLL:
     lib.stb_launch_count.argtypes = []
     lib.stb_measure_fp64_peak.argtypes = [POINTER(c_double)]
     lib.stb_measure_store_bw.argtypes = [c_size_t, POINTER(c_double)]
+    lib.stb_measure_store_pattern.argtypes = [c_int64, c_int32, c_int64, c_int32, c_int32, POINTER(c_double)]
+    lib.stb_measure_store_pattern.restype = c_int
+    lib.stb_comm_unique_id.argtypes = [c_void_p]
+    lib.stb_comm_init.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p)]
+    lib.stb_comm_destroy.argtypes = [c_void_p]
+    lib.stb_comm_rank.argtypes = [c_void_p, POINTER(c_int), POINTER(c_int)]
+    lib.stb_comm_allreduce_f64.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
+    lib.stb_comm_allreduce_max_f64.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
+    lib.stb_comm_gather.argtypes = [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]
+    lib.stb_comm_allgather.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+    lib.stb_shard_local_blocks.argtypes = [c_int64, c_int32, c_int32]
+    lib.stb_shard_local_blocks.restype = c_int64
+    lib.stb_shard_local_rays.argtypes = [c_int64, c_int32, c_int32, c_int32]
+    lib.stb_shard_local_rays.restype = c_int64
+    lib.stb_unshuffle_blocks.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int32, c_int32, c_int64, c_int64, c_int64, c_void_p]
+    for name in ("stb_comm_unique_id", "stb_comm_init", "stb_comm_destroy", "stb_comm_rank", "stb_comm_allreduce_f64",
+                 "stb_comm_allreduce_max_f64", "stb_comm_gather", "stb_comm_allgather", "stb_unshuffle_blocks"):
+        getattr(lib, name).restype = c_int
     lib.stb_medium_create.argtypes = [POINTER(StbMediumDesc), POINTER(c_void_p)]
     lib.stb_medium_create.restype = c_int
     lib.stb_medium_destroy.argtypes = [c_void_p]

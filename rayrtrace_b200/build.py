@@ -16,9 +16,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "sidtrace_b200.cu")
 SRC_RK = os.path.join(_HERE, "csrc", "rk_b200.cu")      # adaptive-RK physics mode (extension)
 SRC_PLAN = os.path.join(_HERE, "csrc", "plan_b200.cu")  # exactly-sized trajectory arenas (CUB sort + scan)
-SOURCES = [SRC, SRC_RK, SRC_PLAN]
+SRC_COMM = os.path.join(_HERE, "csrc", "comm_b200.cu")  # multi-GPU entry points (NCCL via dlopen)
+SOURCES = [SRC, SRC_RK, SRC_PLAN, SRC_COMM]
 DEPS = SOURCES + [os.path.join(_HERE, "csrc", h) for h in ("trace_kernels.cuh", "launch_kernels.cuh", "rk_kernels.cuh")] + [
-    os.path.join(os.path.dirname(_HERE), "include", h) for h in ("sidtrace_b200.h", "sidtrace_b200_rk.h")]
+    os.path.join(os.path.dirname(_HERE), "include", h) for h in ("sidtrace_b200.h", "sidtrace_b200_rk.h", "sidtrace_b200_comm.h")]
 LIB_DIR = os.path.join(_HERE, "_lib")
 LIB = os.path.join(LIB_DIR, "libsidtrace_b200.so")
 
@@ -28,7 +29,7 @@ NVCC_FLAGS = [
     "-fmad=false",                 # parity: no FMA contraction anywhere (kernels use explicit _rn intrinsics too)
     "-Xcompiler", "-fPIC", "-shared",
     "-cudart", "static",
-    "--threads", "3",
+    "--threads", "4",
 ]
 
 

@@ -350,7 +350,10 @@ int launch_trace(stb_field_s *f, KParams &p, bool divc, bool refill, bool tiled,
 {
     const LaunchCtx c{f, refill, s};
     p.field4 = nullptr;
-    if (hoist && !p.st_ray && p.nrays > 0) {
+    // plain trajectory launches are bound by HBM stores, not by FP64 issue: the 32-byte hoisted cells only
+    // add L2 traffic there (6770 vs 6810 GB/s, profiles/r02/l2_policy_sweep.txt) -- they keep the 16-byte cells
+    const bool lean_traj = p.traj && !p.hist && !p.cross_axis && !(p.turn || p.turn_state || p.lax_end || p.ph_end);
+    if (hoist && !lean_traj && !p.st_ray && p.nrays > 0) {
         const size_t bytes = (size_t)(f->nx - 1) * (size_t)(f->ny - 1) * sizeof(double4);
         if (bytes <= f->hoist_max_bytes) {
             int rc = ensure_hoist(f, p.st, s, &p.field4);
@@ -862,6 +865,33 @@ int stb_measure_store_bw(size_t bytes, double *gbs)
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, e0, e1));
         const double g = (double)nvec * 32.0 / (ms * 1e-3) / 1e9;
+        if (rep > 0 && g > best) best = g;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    *gbs = best;
+    return STB_OK;
+}
+
+int stb_measure_store_pattern(int64_t ntiles, int32_t tile, int64_t rows_per_tile, int32_t steps, int32_t chain, double *gbs)
+{
+    if (!gbs || ntiles < 1 || rows_per_tile < steps || steps < 1 || chain < 0 ||
+        (tile != 32 && tile != 64 && tile != 128 && tile != 256))
+        return fail(STB_ERR_ARG, "stb_measure_store_pattern: bad argument");
+    double *out = nullptr;
+    CU(cudaMalloc(&out, (size_t)ntiles * (size_t)rows_per_tile * (size_t)tile * 32));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0));
+        stb::store_pattern_kernel<<<(unsigned)ntiles, tile>>>(out, rows_per_tile, steps, chain, 1.0000001, 1e-9);
+        g_launches++;
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double g = (double)ntiles * tile * steps * 32.0 / (ms * 1e-3) / 1e9;
         if (rep > 0 && g > best) best = g;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -108,20 +108,61 @@ __device__ __forceinline__ double cross_solve(double c0, double k, double a, dou
     return st;
 }
 
+// L2 residency of the field while trajectories stream through the L2.  A 26 GB store stream evicts the
+// 16 MB field: ncu saw 60 % of the field reads miss in L2 and the warps wait on them (long scoreboard,
+// profiles/r01).  In the TRAJ kernels the field gathers therefore carry an L2 evict_last policy and the
+// trajectory stores evict_first: 6436 -> 6810 GB/s on BASELINE config 3 (either hint alone: 6620;
+// a persisting-L2 carve-out of 20 / 40 MB: 6630 / 5060; profiles/r02/l2_policy_sweep.txt).  Kernels
+// without trajectory output keep plain loads (the hinted load costs them 15 %).
+__device__ __forceinline__ unsigned long long l2_policy_evict_last()
+{
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first()
+{
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
 // one 32-byte cell of the hoisted table = one LDG.E.ENL2.256.CONSTANT
+template <bool KEEP>
 __device__ __forceinline__ double4 ld_cell4(const double4 *p)
 {
     double4 v;
-    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    if (KEEP)
+        asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p), "l"(l2_policy_evict_last()));
+    else
+        asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
     return v;
 }
 
+// one 16-byte cell {ax, ay}
+template <bool KEEP>
+__device__ __forceinline__ double2 ld_cell2(const double2 *p)
+{
+    if (KEEP) {
+        double2 v;
+        asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(l2_policy_evict_last()));
+        return v;
+    }
+    return __ldg(p);
+}
+
+// one ray-step = one 32-byte sector = one STG.E.ENL2.256
+// (st.global.cs -- evict-first in L1 -- measured the same within noise in round 1; the L2 policy is what counts)
+template <bool STREAM = false>
 __device__ __forceinline__ void st_state(double *p, double a, double b, double c, double d)
 {
-    // one ray-step = one 32-byte sector = one STG.E.ENL2.256
-    // (st.global.cs -- evict-first -- measured the same within noise; plain stores kept)
-    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
-                 :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+    if (STREAM)
+        asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1, %2, %3, %4}, %5;"
+                     :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d), "l"(l2_policy_evict_first()) : "memory");
+    else
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
+                     :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
 // Correctly rounded v / d for a loop-invariant divisor d with rd = RN(1/d).
@@ -281,7 +322,7 @@ trace_kernel(const KParams p)
                 tp = TILED ? p.traj + ((r / p.tile) * (long long)p.L * p.tile + (r % p.tile)) * 4
                            : p.traj + r * p.stride;
             }
-            st_state(tp, x, y, kx, ky);
+            st_state<true>(tp, x, y, kx, ky);
         }
         if (EXTRAS) { turn = -1; lax = 0; ph = 0; }
         if (CROSS) {
@@ -417,8 +458,8 @@ trace_kernel(const KParams p)
         const int ind = iy * p.nxm1 + ix;
         double2 m = make_double2(0.0, 0.0);
         double4 h = make_double4(0.0, 0.0, 0.0, 0.0);
-        if (HOIST) h = ld_cell4(&p.field4[ind]);
-        else m = __ldg(&p.field[ind]);
+        if (HOIST) h = ld_cell4<TRAJ>(&p.field4[ind]);
+        else m = ld_cell2<TRAJ>(&p.field[ind]);
 
         if (EXTRAS || HIST) {
             // state i is a KEPT state (ray.py:99-102 keeps [:n]); close segment (i-1, i)
@@ -539,7 +580,7 @@ trace_kernel(const KParams p)
         ++i;
         if (TRAJ) {
             tp += TILED ? 4 * p.tile : 4;
-            st_state(tp, x, y, kx, ky);
+            st_state<true>(tp, x, y, kx, ky);
         }
         return true;
     };
@@ -711,6 +752,22 @@ __global__ void store_bw_kernel(double *out, long long nvec)
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long step = (long long)gridDim.x * blockDim.x;
     for (; i < nvec; i += step) st_state(out + 4 * i, 1.0, 2.0, 3.0, (double)i);
+}
+
+// The store pattern of the static tiled trajectory kernel without its arithmetic: CTA b owns tile b,
+// thread t writes `steps` states at stride 4*T doubles (one 8 KB row per CTA-step with T = 256), with
+// `chain` dependent DFMAs between two stores (0 = stores back to back).  Tells apart "the pattern
+// bounds the trajectory kernel" from "its dependency chain does".
+__global__ void store_pattern_kernel(double *out, long long rows_per_tile, int steps, int chain, double a, double b)
+{
+    const int T = blockDim.x;
+    double *tp = out + ((long long)blockIdx.x * rows_per_tile * T + threadIdx.x) * 4;
+    double v = threadIdx.x;
+    for (int i = 0; i < steps; ++i) {
+        for (int c = 0; c < chain; ++c) v = __fma_rn(v, a, b);
+        st_state(tp, v, 2.0, 3.0, (double)i);
+        tp += 4LL * T;
+    }
 }
 
 }  // namespace stb

@@ -20,31 +20,13 @@ from scipy import constants as const
 
 from . import sidtrace as _st
 
-_DEFAULT_FREQ = 135e9   # ray.py:15 -- also the sentinel of the "infer freq from |k|" rule (ray.py:34,47)
+from .launch import _DEFAULT_FREQ, _vacuum_k, launch_states  # noqa: F401  (pure NumPy part, re-exported)
 
 
 class RayOutsideGrid(IndexError, ValueError):
     """A ray launched outside the density grid takes no step; the reference then fails with an
     IndexError at ray.py:105 (``self.x[0]`` of an empty array).  Subclasses ValueError as well, which
     is what earlier versions of this module raised."""
-
-
-def _vacuum_k(kx0, ky0, freq):
-    """ray.py:28-51: normalise the launch direction to w/c, or infer the
-    frequency from |k| when |k| > 2 and freq is the default.  Returns
-    (kx0, ky0, freq).  Scalar inputs use the same numpy calls as the reference."""
-    c = const.speed_of_light * 100
-    w = 2 * np.pi * freq
-    if np.sqrt(kx0 ** 2 + ky0 ** 2) <= 2 or freq != _DEFAULT_FREQ:
-        k = np.linalg.norm((kx0, ky0))
-        kx0 = kx0 / k
-        ky0 = ky0 / k
-        kx0 = kx0 * w / c
-        ky0 = ky0 * w / c
-    elif freq == _DEFAULT_FREQ:
-        w = np.sqrt(kx0 ** 2 + ky0 ** 2) * c
-        freq = w / 2 / np.pi
-    return kx0, ky0, freq
 
 
 class Ray:
@@ -236,33 +218,6 @@ def _device_field(n_field):
                       n_field.nx, n_field.ny)
         n_field._stb_device_field = f
     return f
-
-
-def launch_states(n_field, x0, y0, kx0, ky0, freq):
-    """Vectorised ray.py:28-68: returns (xg0, yg0, kx, ky, freq) as the kernel
-    expects them.  Direction vectors are normalised with sqrt(kx^2+ky^2)
-    (np.linalg.norm per ray in the reference; <= 1 ulp apart)."""
-    x0 = np.atleast_1d(np.asarray(x0, np.float64))
-    y0 = np.atleast_1d(np.asarray(y0, np.float64))
-    kx0 = np.broadcast_to(np.asarray(kx0, np.float64), x0.shape).copy()
-    ky0 = np.broadcast_to(np.asarray(ky0, np.float64), x0.shape).copy()
-    c = const.speed_of_light * 100
-    w = 2 * np.pi * freq
-    kn = np.sqrt(kx0 ** 2 + ky0 ** 2)
-    if freq != _DEFAULT_FREQ or np.all(kn <= 2):
-        kx = kx0 / kn * w / c
-        ky = ky0 / kn * w / c
-    else:
-        raise ValueError("a batch must share one frequency: pass freq explicitly (ray.py:47-51 infers it per ray)")
-    den = n_field.n_interpolant_points(x0, y0) if hasattr(n_field, "n_interpolant_points") else \
-        np.array([np.asarray(n_field.n_interpolant(a, b)).reshape(-1)[0] for a, b in zip(x0, y0)])
-    from .nfield import critical_den
-    refr = np.sqrt(1 - den / critical_den(freq, den_unit=getattr(n_field, "den_unit", "cm^-3")))
-    kx = kx * refr
-    ky = ky * refr
-    xg = np.ascontiguousarray(n_field.x2grid(x0), np.float64)
-    yg = np.ascontiguousarray(n_field.y2grid(y0), np.float64)
-    return xg, yg, np.ascontiguousarray(kx), np.ascontiguousarray(ky), freq
 
 
 def launch_states_device(n_field, x0, y0, kx0, ky0, freq):

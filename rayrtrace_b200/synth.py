@@ -13,7 +13,7 @@ import numpy as np
 from scipy import constants as const
 
 from .nfield import Nfield
-from .ray import launch_states
+from .launch import launch_states
 
 R_DIA = 7.85      # limiter radius, cm (ft2.py:6)
 R_ANT = 10.0      # antenna radius, cm (ft2.py:7)

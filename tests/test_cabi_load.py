@@ -12,11 +12,12 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "sidtrace_b200.h")
 HEADER_RK = os.path.join(ROOT, "include", "sidtrace_b200_rk.h")   # adaptive-RK extension
+HEADER_COMM = os.path.join(ROOT, "include", "sidtrace_b200_comm.h")   # multi-GPU entry points
 
 
 def _declared():
     names = set()
-    for h in (HEADER, HEADER_RK):
+    for h in (HEADER, HEADER_RK, HEADER_COMM):
         src = open(h).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names |= set(re.findall(r"\b(stb_[a-z0-9_]+)\s*\(", src))

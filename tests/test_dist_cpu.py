@@ -27,11 +27,11 @@ def _worker(rank, world, port, mode, q):
     import oracle
     from rayrtrace_b200 import dist as rd
     rng = np.random.default_rng(5)
-    nx, ny, n, L = 40, 30, 101, 80          # odd ray count: ragged shards
+    nx, ny, n, L = 40, 30, (101 if mode != "blocks" else 1337), 80          # odd ray counts: ragged shards / a partial last block
     ax, ay = random_field(rng, nx, ny)
     launch = random_launch(rng, n, nx, ny)
     amp = rng.uniform(0.5, 1, n)
-    sl = rd.shard_slice(n, rank, world, mode)
+    sl = rd.shard_index(n, rank, world) if mode == "blocks" else rd.shard_slice(n, rank, world, mode)
     loc = oracle.trace_batch(*[a[sl] for a in launch], L, 0.3, 1.0, 1.0, nx, ny, ax, ay)
     hist = np.zeros(16)
     for r in range(len(loc["nsteps"])):
@@ -45,7 +45,7 @@ def _worker(rank, world, port, mode, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,mode", [(2, "interleave"), (2, "block"), (3, "interleave")])
+@pytest.mark.parametrize("world,mode", [(2, "interleave"), (2, "block"), (3, "interleave"), (2, "blocks"), (3, "blocks")])
 def test_sharded_equals_single(world, mode):
     import oracle
     oracle.port()
@@ -60,7 +60,7 @@ def test_sharded_equals_single(world, mode):
         p.join(60)
         assert p.exitcode == 0
     rng = np.random.default_rng(5)
-    nx, ny, n, L = 40, 30, 101, 80
+    nx, ny, n, L = 40, 30, (101 if mode != "blocks" else 1337), 80
     ax, ay = random_field(rng, nx, ny)
     launch = random_launch(rng, n, nx, ny)
     amp = rng.uniform(0.5, 1, n)
@@ -85,3 +85,45 @@ def test_shard_slices_partition():
                 assert (seen == 1).all()
     with pytest.raises(ValueError):
         shard_slice(10, 2, 2)
+
+
+def test_block_interleaved_sharding_matches_the_library():
+    """dist.shard_index / local_blocks against the C entry points stb_shard_local_rays / _blocks, and the
+    block-interleaved shards partition the rays."""
+    from rayrtrace_b200 import _cabi
+    from rayrtrace_b200.dist import local_blocks, shard_index
+    lib = _cabi.lib
+    for n in (0, 1, 255, 256, 257, 1000, 4096, 100_003):
+        for world in (1, 2, 3, 8):
+            seen = np.zeros(n, int)
+            for r in range(world):
+                idx = shard_index(n, r, world)
+                seen[idx] += 1
+                assert len(idx) == lib.stb_shard_local_rays(n, r, world, 256)
+                assert len(idx) <= local_blocks(n, world) * 256
+                if len(idx):
+                    b = idx // 256
+                    assert np.all(b % world == r) and np.all(np.diff(idx) > 0)
+            assert (seen == 1).all()
+            assert local_blocks(n, world) == lib.stb_shard_local_blocks(n, world, 256)
+
+
+def test_unshuffle_formula_on_host():
+    """The index map stb_unshuffle_blocks implements (local block lb of rank r -> global block lb*world + r),
+    restated with numpy: gathering every rank's padded shard and unshuffling gives the identity."""
+    from rayrtrace_b200.dist import local_blocks, shard_index
+    B = 256
+    for n, world in ((1000, 3), (5000, 2), (256 * 8 + 5, 8)):
+        lb = local_blocks(n, world)
+        src = np.full((world, lb * B), -1, np.int64)
+        for r in range(world):
+            idx = shard_index(n, r, world)
+            src[r, :len(idx)] = idx                       # each ray carries its own global index
+        dst = np.full(n, -2, np.int64)
+        for r in range(world):
+            for l in range(lb):
+                g0 = (l * world + r) * B
+                for j in range(B):
+                    if g0 + j < n:
+                        dst[g0 + j] = src[r, l * B + j]
+        assert np.array_equal(dst, np.arange(n))

@@ -1192,3 +1192,25 @@ def test_long_reference_rays_exact_launch_bitwise(st, torch_mod, long_rays_fix, 
         y = ly[r] + (t[:, 1] - t[0, 1]) * nf.dy[0]
         got = hashlib.sha256(np.ascontiguousarray(np.stack([x, y, t[:, 2], t[:, 3]], 1)).tobytes()).hexdigest()
         assert got == str(fx[f"{tag}_sha"][r]), r
+
+
+def test_plain_c_two_rank_caller_of_the_comm_abi(st, torch_mod, tmp_path):
+    """The multi-GPU entry points are a C ABI too (include/sidtrace_b200_comm.h): tests/c/comm_2rank.c forks
+    two processes, one GPU each -- NCCL from a unique id over a pipe, block-interleaved shards of one beam,
+    all-reduced histogram, summaries gathered and unshuffled on rank 0 -- and compares with one GPU tracing
+    the whole beam.  Needs two GPUs (gpurun --gpus 2); skipped otherwise."""
+    import os
+    import subprocess
+    from rayrtrace_b200 import _cabi
+    if torch_mod.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "comm_2rank"
+    lib = _cabi.LIB_PATH
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call([os.environ.get("CC", "gcc"), "-O1", os.path.join(root, "tests", "c", "comm_2rank.c"),
+                           "-I" + os.path.join(cuda, "include"), lib, "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+                           "-Wl,-rpath," + os.path.dirname(lib), "-Wl,-rpath," + os.path.join(cuda, "lib64"), "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bit-identical" in r.stdout and "MISMATCH" not in r.stdout

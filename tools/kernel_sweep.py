@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--case", default="beam", choices=["beam", "sweep", "trapped"])
     ap.add_argument("--only", default="", help="comma-separated substrings; a variant runs if any matches")
+    ap.add_argument("--hoist", default="on", choices=["on", "off", "both"], help="hoisted per-cell products (default) or plain cells")
+    ap.add_argument("--L", type=int, default=0, help="states per ray (0 = the case's default cap)")
+    ap.add_argument("--store-pattern", action="store_true", help="only run the store-pattern microbenchmark")
     args = ap.parse_args()
     peak = 6533.5
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -38,25 +41,80 @@ def main():
     d_amp = torch.from_numpy(np.ascontiguousarray(case.amp)).to(dev)
     d_xp = torch.from_numpy(np.ascontiguousarray(case.x0)).to(dev)
     d_yp = torch.from_numpy(np.ascontiguousarray(case.y0)).to(dev)
-    n, L = case.nrays, case.L
+    n, L = case.nrays, (args.L or case.L)
+    if args.store_pattern:
+        import ctypes
+        lib = sidtrace._cabi.lib
+        g = ctypes.c_double()
+        sidtrace._cabi.check(lib.stb_measure_store_bw(8 << 30, ctypes.byref(g)))
+        print(f"# plain grid-stride streaming stores: {g.value:.0f} GB/s")
+        nt = (n + 255) // 256
+        for tile, ntl in ((256, nt), (128, 2 * nt), (32, 8 * nt)):
+            for steps in (820, 1000):
+                for chain in (0, 4, 8, 16, 32):
+                    sidtrace._cabi.check(lib.stb_measure_store_pattern(ntl, tile, steps, steps, chain, ctypes.byref(g)))
+                    print(f"store-pattern tile={tile:3d} ntiles={ntl:6d} rows/tile={steps} chain={chain:2d}: {g.value:8.1f} GB/s  "
+                          f"frac {g.value / peak:5.3f}", flush=True)
+        # rows allocated at the cap (the current bench layout: L rows per tile, ~820 written)
+        for chain in (0, 8):
+            sidtrace._cabi.check(lib.stb_measure_store_pattern(nt, 256, L, 820, chain, ctypes.byref(g)))
+            print(f"store-pattern tile=256 ntiles={nt} rows/tile={L} (820 written) chain={chain}: {g.value:8.1f} GB/s  frac {g.value / peak:5.3f}", flush=True)
+        return
     nt = (n + 255) // 256 * 8
     buf = None   # trajectory arena, allocated when a trajectory variant is selected
     kw = dict(L=L, st=case.st, dx=case.dx, dy=case.dy)
     out = sidtrace.BatchResult(nsteps=torch.empty(n, dtype=torch.int32, device=dev),
                                end_state=torch.empty((4, n), dtype=torch.float64, device=dev))
     variants = []
-    for mode in ("traj-tiled", "traj-tiled64", "traj-tiled128", "traj-tiled256", "traj-ray", "endpoints", "endpoints-tiled", "extras", "extras-tiled", "hist64", "hist1024", "cross"):
+    hoists = {"on": (True,), "off": (False,), "both": (True, False)}[args.hoist]
+    for mode in ("traj-tiled", "traj-tiled64", "traj-tiled128", "traj-tiled256", "traj-ray", "traj-exact", "traj-pass2", "endpoints",
+                 "endpoints-tiled", "extras", "extras-tiled", "hist64", "hist1024", "cross", "lookup"):
         for refill in (True, False):
             for div_ieee in (False, True):
-                variants.append((mode, refill, div_ieee))
+                for hoist in hoists:
+                    variants.append((mode, refill, div_ieee, hoist))
     print(f"# case {case.name} L={L} peak={peak} GB/s lib={os.path.basename(sidtrace._cabi.LIB_PATH)}")
     first = True
-    for mode, refill, div_ieee in variants:
-        tag = f"{mode}/{'refill' if refill else 'static'}/{'ieee' if div_ieee else 'divc'}"
+    plan = None
+    for mode, refill, div_ieee, hoist in variants:
+        tag = f"{mode}/{'refill' if refill else 'static'}/{'ieee' if div_ieee else 'divc'}/{'hoist' if hoist else 'cells'}"
         if args.only and not any(o in tag for o in args.only.split(",")):
             continue
         o = sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state)
-        k = dict(kw, refill=refill, div_ieee=div_ieee)
+        k = dict(kw, refill=refill, div_ieee=div_ieee, hoist=hoist)
+        if mode in ("traj-exact", "traj-pass2"):
+            # two-pass exactly-sized arena: the whole of trace_exact, or its second pass alone (plan given)
+            if refill:
+                continue           # pass 1 picks lane refill itself, pass 2 is static
+            del k["refill"]
+            if plan is None:
+                r0 = sidtrace.trace_batch(field, *d_in, out=sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state), **kw)
+                plan = sidtrace.plan_trajectories(r0.nsteps, tile=256, L=L)
+                arena = torch.empty((plan.total_rows, 256, 4), dtype=torch.float64, device=dev)
+                print(f"# exact arena: {plan.arena_bytes / 1e9:.2f} GB for {int(r0.nsteps.sum())} ray-steps "
+                      f"({plan.arena_bytes / 32 / max(int(r0.nsteps.sum()), 1):.4f} states allocated per ray-step)")
+            if mode == "traj-pass2":
+                fn = lambda: sidtrace.trace_batch(field, *d_in, traj=arena, plan=plan, want_end=False, out=o, **k)
+            else:
+                def fn():
+                    r1 = sidtrace.trace_batch(field, *d_in, out=o, **k)
+                    pl = sidtrace.plan_trajectories(r1.nsteps, tile=256, L=L)
+                    assert pl.total_rows == plan.total_rows
+                    sidtrace.trace_batch(field, *d_in, traj=arena, plan=pl, want_end=False,
+                                         out=sidtrace.BatchResult(nsteps=o.nsteps), **k)
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(args.reps):
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            steps = int(o.nsteps.sum().item())
+            ms = float(np.median(ts)); rate = steps / (ms * 1e-3)
+            print(f"{tag:40s} {ms:9.3f} ms  {rate:11.4e} ray-steps/s  {rate * 32 / 1e9:8.1f} GB/s-equiv  frac {rate * 32 / 1e9 / peak:5.3f}  (min {min(ts):.3f} ms)", flush=True)
+            continue
         if mode.startswith("traj") and buf is None:
             buf = torch.empty(nt * 32 * L * 4, dtype=torch.float64, device=dev)
         if mode in ("traj-tiled", "traj-tiled64", "traj-tiled128", "traj-tiled256"):
@@ -73,6 +131,11 @@ def main():
                      r_lcs=synth.R_DIA, rho_max=1.3)
         elif mode == "cross":
             k.update(cross=(9.0, "y"), x0_phys=d_xp, y0_phys=d_yp)
+        elif mode == "lookup":
+            c0 = sidtrace.trace_batch(field, *d_in, cross=(9.0, "y"), x0_phys=d_xp, y0_phys=d_yp, **kw)
+            ph = c0.cross_state[5]
+            k.update(cross=(9.0, "y"), x0_phys=d_xp, y0_phys=d_yp,
+                     lookup_ph=torch.stack([torch.roll(ph, 1), torch.roll(ph, -1)]).contiguous())
         elif mode == "endpoints-tiled":
             k.update(tiled=True)
         elif mode == "extras-tiled":
@@ -96,7 +159,7 @@ def main():
         ms = float(np.median(ts))
         rate = steps / (ms * 1e-3)
         frac = rate * 32 / 1e9 / peak
-        print(f"{tag:32s} {ms:9.3f} ms  {rate:11.4e} ray-steps/s  {rate * 32 / 1e9:8.1f} GB/s-equiv  frac {frac:5.3f}  (min {min(ts):.3f} ms)", flush=True)
+        print(f"{tag:40s} {ms:9.3f} ms  {rate:11.4e} ray-steps/s  {rate * 32 / 1e9:8.1f} GB/s-equiv  frac {frac:5.3f}  (min {min(ts):.3f} ms)", flush=True)
 
 
 if __name__ == "__main__":
