@@ -464,9 +464,10 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     p.xorg = b->xorg; p.yorg = b->yorg; p.r_lcs = b->r_lcs; p.rho_max = b->rho_max;
     p.r_rlcs = 1.0 / b->r_lcs; p.r_rhomax = 1.0 / b->rho_max;
     p.hist_dr = b->nbins > 0 ? b->rho_max * b->r_lcs / (double)b->nbins : 0.0;
-    // a ray advances about one smallest cell per step (SURVEY 3.3 i): the annulus test pays off when a
-    // bin spans several steps, otherwise most steps would fail it and take the exact path anyway
-    p.hist_annulus = b->hist && p.hist_dr >= 4.0 * std::fmin(std::fabs(b->dx), std::fabs(b->dy));
+    // a ray advances about one smallest cell per step (SURVEY 3.3 i): the annulus test (two compares) saves
+    // the square root and both divisions of the flux label whenever the ray is still inside its bin; it
+    // pays off as soon as a bin is about one step wide (failing it costs 2 of ~60 instructions)
+    p.hist_annulus = b->hist && p.hist_dr >= 1.0 * std::fmin(std::fabs(b->dx), std::fabs(b->dy));
     p.counter = nullptr;                 // assigned per persistent launch (launch_one)
     p.cross_axis = b->cross_axis; p.cross_val = b->cross_val;
     p.x0p = b->x0_phys; p.y0p = b->y0_phys;

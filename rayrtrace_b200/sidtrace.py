@@ -570,23 +570,25 @@ def trace_exact(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
     for its longest ray.  Pass 2 traces the rays again in that order on the tiled schedule: the lanes of
     a warp end within a few steps of each other (no lock-step idling) and every warp-step is one
     coalesced row of the packed arena.  Device I/O only (CUDA tensors).  Raises MemoryError when the
-    arena would exceed ``max_bytes`` (default: 90 % of the free HBM)."""
+    arena does not fit (or exceeds ``max_bytes``)."""
     torch = _torch()
     if not _is_tensor(x0):
         raise TypeError("trace_exact takes CUDA tensors (device I/O)")
     res = trace_batch(field, x0, y0, kx0, ky0, L=L, st=st, dx=dx, dy=dy, want_extras=want_extras, cross=cross,
                       x0_phys=x0_phys, y0_phys=y0_phys, div_ieee=div_ieee, out=out, **kw)
     plan = plan_trajectories(res.nsteps, tile=tile, L=L)
-    if max_bytes is None:
-        free, _total = torch.cuda.mem_get_info(x0.device)
-        max_bytes = int(0.9 * free)
-    if plan.arena_bytes > max_bytes:
+    if max_bytes is not None and plan.arena_bytes > max_bytes:
         raise MemoryError(f"{plan.nrays} rays keep {plan.total_rows * plan.tile} states = {plan.arena_bytes / 1e9:.1f} GB "
-                          f"of trajectories, more than the {max_bytes / 1e9:.1f} GB allowed: trace the beam in chunks "
-                          f"or keep per-ray outputs only")
+                          f"of trajectories, more than the {max_bytes / 1e9:.1f} GB allowed")
+    try:
+        arena = torch.empty((plan.total_rows, plan.tile, 4), dtype=torch.float64, device=x0.device)
+    except torch.cuda.OutOfMemoryError as e:
+        raise MemoryError(f"{plan.nrays} rays keep {plan.total_rows * plan.tile} states = {plan.arena_bytes / 1e9:.1f} GB "
+                          f"of trajectories, more than the free HBM: trace the beam in chunks or keep per-ray "
+                          f"outputs only") from e
     # pass 2: trajectories only (the per-ray outputs of pass 1 stand; same inputs, same bits)
     t = BatchResult(nsteps=torch.empty_like(res.nsteps))
-    trace_batch(field, x0, y0, kx0, ky0, L=L, st=st, dx=dx, dy=dy, traj=True, plan=plan, want_end=False,
+    trace_batch(field, x0, y0, kx0, ky0, L=L, st=st, dx=dx, dy=dy, traj=arena, plan=plan, want_end=False,
                 div_ieee=div_ieee, out=t, **{k: v for k, v in kw.items() if k in ("st_ray", "hoist", "stream")})
     res.traj, res.plan, res.tiled = t.traj, plan, False
     return res
