@@ -36,7 +36,9 @@ namespace stb {
 
 constexpr int kBlock = 128;   // threads per CTA (4 warps); the tiled trajectory kernel also runs with 256
 #ifndef STB_MINB_CROSS
-#define STB_MINB_CROSS 1      // crossing / lookup passes
+#define STB_MINB_CROSS 5      // crossing / lookup passes: 96 registers, 20 warps/SM (1 / 4 / 5 / 6 CTAs per SM measured:
+                              // cross 4.48 / 4.51 / 4.17 / 4.47 ms, lookup 9.99 / 6.94 / 6.64 / 6.81 ms per 10^6 rays,
+                              // profiles/r02/kernel_sweep_restructured.txt)
 #endif
 #ifndef STB_MINB_EXTRAS
 #define STB_MINB_EXTRAS 1     // fused sums / histogram
@@ -234,6 +236,54 @@ __device__ __forceinline__ void hist_add(double *sh, int b, double w)
     if (lane == leader && b >= 0) atomicAdd(&sh[b], sum);
 }
 
+// What a crossing capture needs besides the registers of the segment's start state.  Captures are rare
+// (once per ray), so this code stays out of line: the stepping loop keeps its registers for the steps.
+struct CrossCtx {
+    const double2 *field;
+    const double *x0p, *y0p, *xg0, *yg0;    // physical launch points, launch state (grid units)
+    double *cross_state;                      // [6][nrays] or nullptr
+    long long nrays;
+    double dx, dy, val;
+    bool axis_y;
+};
+struct CrossPoint { double x, y, lax, ph, s, kn; };
+
+// Crossing point inside (or extrapolated beyond) the segment that starts at the kept state
+// (sx, sy, skx, sky) in cell sind with running sums (slax, sph): ray.py:174-216.  Writes the per-ray
+// crossing outputs; false when the segment has no usable root.
+__device__ __noinline__ bool cross_capture(const CrossCtx c, long long ray, double sx, double sy, double skx, double sky,
+                                           int sind, double slax, double sph, double st1, CrossPoint *out)
+{
+    const double xp = c.x0p[ray] + (sx - c.xg0[ray]) * c.dx, yp = c.y0p[ray] + (sy - c.yg0[ray]) * c.dy;   // ray.py:105-106
+    const double2 pm = __ldg(&c.field[sind]);
+    const double s = cross_solve(c.axis_y ? yp : xp, c.axis_y ? sky : skx, c.axis_y ? pm.y : pm.x, c.val, st1);
+    if (!(s == s) || s == 0.0) return false;
+    const double nkx = skx + pm.x * s, nky = sky + pm.y * s;
+    const double nx_ = xp + skx * s + pm.x / 2 * s * s, ny_ = yp + sky * s + pm.y / 2 * s * s;
+    const double kp = sqrt(skx * skx + sky * sky), kn = sqrt(nkx * nkx + nky * nky);
+    const double kav = (kp + kn) / 2;
+    const double nlax = slax + s * kav;
+    const double nph = sph + (nlax - slax) * kav;
+    if (c.cross_state) {
+        c.cross_state[0 * c.nrays + ray] = nx_;  c.cross_state[1 * c.nrays + ray] = ny_;
+        c.cross_state[2 * c.nrays + ray] = nkx;  c.cross_state[3 * c.nrays + ray] = nky;
+        c.cross_state[4 * c.nrays + ray] = nlax; c.cross_state[5 * c.nrays + ray] = nph;
+    }
+    out->x = nx_; out->y = ny_; out->lax = nlax; out->ph = nph; out->s = s; out->kn = kn;
+    return true;
+}
+
+// An existing point lies on the receiver line (ray.py:142-143): it is reported as it stands.
+__device__ __noinline__ void cross_exact_hit(const CrossCtx c, long long ray, double x, double y, double kx, double ky,
+                                             double lax, double ph)
+{
+    if (!c.cross_state) return;
+    c.cross_state[0 * c.nrays + ray] = c.x0p[ray] + (x - c.xg0[ray]) * c.dx;
+    c.cross_state[1 * c.nrays + ray] = c.y0p[ray] + (y - c.yg0[ray]) * c.dy;
+    c.cross_state[2 * c.nrays + ray] = kx;  c.cross_state[3 * c.nrays + ray] = ky;
+    c.cross_state[4 * c.nrays + ray] = lax; c.cross_state[5 * c.nrays + ray] = ph;
+}
+
 // TILED (trajectory layout [ray/T][step][ray%T][4], T = p.tile): a warp owns 32 consecutive
 // rays; its lanes step in lock-step, so every warp-step is ONE fully coalesced 1 KB row store,
 // the warps of a CTA write adjacent rows, and consecutive steps are consecutive rows --
@@ -276,37 +326,58 @@ trace_kernel(const KParams p)
     const int lane = threadIdx.x & 31;
     int Lm1 = p.L - 1;
 
-    // per-ray state
+    // per-ray state: state i of the current ray.  Inside the stepping loop state i is always a KEPT state
+    // (it passed the guard of sidtracemodule.c:36; ray.py:99-102 keeps [:n]).
     long long ray = -1;
-    int i = 0;
+    int i = 0, ind = 0;                      // ind: cell of state i (valid while the ray is alive)
     double x = 0, y = 0, kx = 0, ky = 0;
     double st_r = p.st, sst_r = p.sst;      // per-ray step (STRAY)
     double *tp = nullptr;
     // extras
     int turn = -1;
-    double tsx = 0, tsy = 0, tskx = 0, tsky = 0;   // state at the turning index
     double kprev = 0, lax = 0, ph = 0, a2 = 1.0;
     int binprev = -1;        // HIST: flux bin of the previous kept state = bin of the current run
     double binacc = 0.0;     // HIST: weight gathered for that bin since the ray entered it
     double r2lo = 1.0, r2hi = 0.0;   // HIST: squared-radius annulus of that bin (empty = unknown)
-    // crossing: previous kept state, capture of the first crossing / exact hit
+    // crossing.  The receiver coordinate of a state is c = c0p + (g - g0) * dg with g = y or x (ray.py:105-106).
+    // Per step only its offset d = c - val is carried; everything a capture needs beyond the registers of
+    // the segment's start state is re-read from global memory at capture time (once per ray), and what a
+    // capture produces goes straight to the output arrays (the LOOKUP pass keeps it in registers too).
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    double xg0 = 0, yg0 = 0, x0p = 0, y0p = 0;
-    double pxg = 0, pyg = 0, pkx = 0, pky = 0, plax = 0, pph = 0, dprev = 0;
-    int pind = 0;            // cell of the previous kept state (its acceleration is re-read at capture time)
-    double cx = qnan, cy = qnan, ckx = qnan, cky = qnan, clax = qnan, cph = qnan;
+    const bool axis_y = p.cross_axis != 2;
+    const double dg = axis_y ? p.dy : p.dx;
+    double c0p = 0, g0 = 0, dcur = 0;
     int cidx = -1, ncross = 0, neq = 0;
     bool below = false, above = false;
-    const bool axis_y = p.cross_axis != 2;
-    // lookup: capture extras, post-insertion running sums, last two polyline points, targets
-    double cs = 0, ckn = 0;
+    // state n-1 = the last kept state, assigned once when the ray ends (retire() extrapolates from it)
+    double pxg = 0, pyg = 0, pkx = 0, pky = 0, plax = 0, pph = 0;
+    int pind = 0;
+    // lookup: launch point, the captured crossing (until it is inserted into the polyline), post-insertion
+    // running sums, last two polyline points, targets
+    double x0p = 0, y0p = 0, xg0 = 0, yg0 = 0;
+    double cx = qnan, cy = qnan, clax = qnan, cph = qnan, cs = 0, ckn = 0;
+    bool cap_seg = false;    // a crossing point was captured in the segment that ends at state i
     double lax2 = 0, ph2 = 0;
     double sa_ph = 0, sa_x = 0, sa_y = 0, sb_ph = 0, sb_x = 0, sb_y = 0;
     int npts = 0;
     double tA = 0, tB = 0, oxA = qnan, oyA = qnan, oxB = qnan, oyB = qnan;
-    bool doneA = false, doneB = false, inserted = false;
+    bool doneA = false, doneB = false;
 
-    auto launch = [&](long long r, long long slot) {
+    // sidtracemodule.c:36 -- guard on a state with index j:  j < L-1  and  0 <= x < nx-1  and  0 <= y < ny-1
+    // (false for NaN).  The O(rays)-output modes are bound by instruction issue, so the four FP64 compares
+    // are done on the integer pipe instead, exactly: with c = trunc(v) (saturating, NaN -> 0),
+    //   0 <= v < n   <=>   v is +finite (or -0.0)  and  (unsigned)c < n        (n integer < 2^31)
+    // "+finite": high word, read as unsigned, below 0x7ff00000 (excludes negatives, inf, NaN);
+    // -0.0 (which compares >= 0 in the reference) is admitted explicitly.  Returns the cell (:38).
+    auto guard = [&](double xs, double ys, int j, int &cell) -> bool {
+        const int ix = __double2int_rz(xs), iy = __double2int_rz(ys);
+        cell = iy * p.nxm1 + ix;
+        return (j < Lm1) & in_range(xs, ix, p.nxm1) & in_range(ys, iy, p.nym1);
+    };
+
+    // Take ray r: load its launch state, write state 0, reset the per-ray outputs.  False when the launch
+    // state already fails the guard (the ray takes no step: nsteps = 0, end state = launch state).
+    auto launch = [&](long long r, long long slot) -> bool {
         ray = r;
         x = p.x0[r]; y = p.y0[r]; kx = p.kx0[r]; ky = p.ky0[r];
         if (STRAY && p.st_ray) { st_r = p.st_ray[r]; sst_r = __dmul_rn(st_r, st_r); }
@@ -326,13 +397,16 @@ trace_kernel(const KParams p)
         }
         if (EXTRAS) { turn = -1; lax = 0; ph = 0; }
         if (CROSS) {
-            xg0 = x; yg0 = y; x0p = p.x0p[r]; y0p = p.y0p[r];
-            cx = cy = ckx = cky = clax = cph = qnan;
+            c0p = axis_y ? p.y0p[r] : p.x0p[r];
+            g0 = axis_y ? y : x;
+            dcur = c0p - p.cross_val;            // c0p + (g0 - g0) * dg - val
             cidx = -1; ncross = 0; neq = 0; below = above = false;
             if (LOOKUP) {
+                x0p = p.x0p[r]; y0p = p.y0p[r]; xg0 = x; yg0 = y;
+                cx = cy = clax = cph = qnan;
                 tA = p.lookup_ph[r]; tB = p.lookup_ph[p.nrays + r];
                 oxA = oyA = oxB = oyB = qnan;
-                doneA = doneB = inserted = false;
+                doneA = doneB = cap_seg = false;
                 npts = 0; lax2 = ph2 = 0;
             }
         }
@@ -341,25 +415,16 @@ trace_kernel(const KParams p)
             a2 = __dmul_rn(a, a);
             binprev = -1; binacc = 0.0; r2lo = 1.0; r2hi = 0.0;
         }
+        return guard(x, y, 0, ind);
     };
 
-    // solve from the previous kept state (index i-1) and capture the crossing point (ray.py:212-216)
-    auto capture_from_prev = [&](double st1) -> bool {
-        const double xp = x0p + (pxg - xg0) * p.dx, yp = y0p + (pyg - yg0) * p.dy;   // ray.py:105-106
-        const double2 pm = __ldg(&p.field[pind]);
-        const double pmx = pm.x, pmy = pm.y;
-        const double s = cross_solve(axis_y ? yp : xp, axis_y ? pky : pkx, axis_y ? pmy : pmx, p.cross_val, st1);
-        if (!(s == s) || s == 0.0) return false;
-        ckx = pkx + pmx * s;
-        cky = pky + pmy * s;
-        cx = xp + pkx * s + pmx / 2 * s * s;
-        cy = yp + pky * s + pmy / 2 * s * s;
-        const double kp = sqrt(pkx * pkx + pky * pky), kn = sqrt(ckx * ckx + cky * cky);
-        const double kav = (kp + kn) / 2;
-        clax = plax + s * kav;
-        cph = pph + (clax - plax) * kav;
-        cidx = i;               // i-1 is the segment start: the reference inserts at (i-1)+1
-        cs = s; ckn = kn;
+    // crossing capture (out of line, see cross_capture); `at` is the index Ray.addpoint reports
+    auto capture = [&](double sx, double sy, double skx, double sky, int sind, double slax, double sph, double st1, int at) -> bool {
+        const CrossCtx c{p.field, p.x0p, p.y0p, p.x0, p.y0, p.cross_state, p.nrays, p.dx, p.dy, p.cross_val, axis_y};
+        CrossPoint q;
+        if (!cross_capture(c, ray, sx, sy, skx, sky, sind, slax, sph, st1, &q)) return false;
+        cidx = at;
+        if (LOOKUP) { cx = q.x; cy = q.y; clax = q.lax; cph = q.ph; cs = q.s; ckn = q.kn; }
         return true;
     };
 
@@ -381,7 +446,8 @@ trace_kernel(const KParams p)
         }
     };
 
-    // per-ray results: state i is the first out-of-domain state or the cap (sidtracemodule.c:50).
+    // per-ray results: here i = n, (x, y, kx, ky) = state n -- the first out-of-domain state or the cap
+    // (sidtracemodule.c:50) -- and (pxg, ..., pph) = state n-1 when n >= 1.
     // Ray-granular schedules retire a ray the moment it ends; the TILED schedule retires the
     // whole tile at once, so nsteps / end states leave the warp as coalesced 128 B / 256 B rows
     // (which is what makes writing them straight into mapped host memory cheap).
@@ -399,26 +465,25 @@ trace_kernel(const KParams p)
         }
         if (EXTRAS) {
             if (p.turn) p.turn[ray] = turn;
-            if (p.turn_state) {
-                const bool has = turn >= 0;
-                p.turn_state[0 * p.nrays + ray] = has ? tsx : qnan;
-                p.turn_state[1 * p.nrays + ray] = has ? tsy : qnan;
-                p.turn_state[2 * p.nrays + ray] = has ? tskx : qnan;
-                p.turn_state[3 * p.nrays + ray] = has ? tsky : qnan;
+            if (p.turn_state && turn < 0) {           // a turning point wrote its state when it was found
+                p.turn_state[0 * p.nrays + ray] = qnan; p.turn_state[1 * p.nrays + ray] = qnan;
+                p.turn_state[2 * p.nrays + ray] = qnan; p.turn_state[3 * p.nrays + ray] = qnan;
             }
             if (p.lax_end) p.lax_end[ray] = lax;
             if (p.ph_end) p.ph_end[ray] = ph;
         }
         if (CROSS) {
-            // here i = n (states 0..n-1 are kept) and the "previous kept state" is state n-1
+            // states 0..n-1 are kept
             int count = 0, flags = 0;
             if (neq > 0) {                              // ray.py:142-143: exact hit(s), nothing inserted
                 count = neq; flags = 1;
             } else if (below && above) {                // ray.py:144-146
                 count = cidx >= 0 ? ncross : 0;
             } else if (i >= 1) {                        // ray.py:147-148: heading for the line past the end
-                const double cl = axis_y ? y0p + (pyg - yg0) * p.dy : x0p + (pxg - xg0) * p.dx;
-                if ((p.cross_val - cl) * (axis_y ? pky : pkx) > 0.0 && capture_from_prev(0.0)) { count = 1; flags = 2; }
+                const double cl = c0p + ((axis_y ? pyg : pxg) - g0) * dg;
+                if ((p.cross_val - cl) * (axis_y ? pky : pkx) > 0.0 && capture(pxg, pyg, pkx, pky, pind, plax, pph, 0.0, i)) {
+                    count = 1; flags = 2;
+                }
             }
             if (LOOKUP) {
                 if (flags == 2) add_point(cph, cx, cy);            // point appended past the last kept state
@@ -431,42 +496,35 @@ trace_kernel(const KParams p)
                     p.lookup_xy[2 * p.nrays + ray] = oxB; p.lookup_xy[3 * p.nrays + ray] = oyB;
                 }
             }
-            if (count == 0) { cx = cy = ckx = cky = clax = cph = qnan; cidx = -1; }
+            if (count == 0) {
+                cidx = -1;
+                if (p.cross_state)
+                    for (int k = 0; k < 6; ++k) p.cross_state[k * p.nrays + ray] = qnan;
+            }
             if (p.cross_count) p.cross_count[ray] = count;
             if (p.cross_index) p.cross_index[ray] = cidx;
             if (p.cross_flags) p.cross_flags[ray] = flags;
-            if (p.cross_state) {
-                p.cross_state[0 * p.nrays + ray] = cx;  p.cross_state[1 * p.nrays + ray] = cy;
-                p.cross_state[2 * p.nrays + ray] = ckx; p.cross_state[3 * p.nrays + ray] = cky;
-                p.cross_state[4 * p.nrays + ray] = clax; p.cross_state[5 * p.nrays + ray] = cph;
-            }
         }
     };
 
-    // One step of the reference loop; false when the guard on state i fails (the ray has ended).
+    // One step of the reference loop from the KEPT state i: per-state bookkeeping, state i+1, the
+    // guard on state i+1.  True when state i+1 is kept as well (the registers then hold it); false
+    // when the ray has ended: the registers hold state n = i+1 (written, not kept) and p* state n-1.
     auto step = [&]() -> bool {
-        // sidtracemodule.c:36 -- guard on state i:  0 <= x < nx-1  and  0 <= y < ny-1  (false for NaN).
-        // The O(rays)-output modes are bound by FP64-pipe issue, so the four FP64 compares are done
-        // on the integer pipe instead, exactly: with c = trunc(v) (saturating, NaN -> 0),
-        //   0 <= v < n   <=>   v is +finite (or -0.0)  and  (unsigned)c < n        (n integer < 2^31)
-        // "+finite": high word, read as unsigned, below 0x7ff00000 (excludes negatives, inf, NaN);
-        // -0.0 (which compares >= 0 in the reference) is admitted explicitly.
-        const int ix = __double2int_rz(x), iy = __double2int_rz(y);
-        if (!((i < Lm1) & in_range(x, ix, p.nxm1) & in_range(y, iy, p.nym1))) return false;
         const double st = STRAY ? st_r : p.st, sst = STRAY ? sst_r : p.sst;
         // :38  nearest lower-left cell, no interpolation
-        const int ind = iy * p.nxm1 + ix;
         double2 m = make_double2(0.0, 0.0);
         double4 h = make_double4(0.0, 0.0, 0.0, 0.0);
         if (HOIST) h = ld_cell4<TRAJ>(&p.field4[ind]);
         else m = ld_cell2<TRAJ>(&p.field[ind]);
 
+        double kavr = 0, sk = 0, kcur = 0;
         if (EXTRAS || HIST) {
-            // state i is a KEPT state (ray.py:99-102 keeps [:n]); close segment (i-1, i)
-            const double kcur = kmod(kx, ky);
+            // close segment (i-1, i)
+            kcur = kmod(kx, ky);
             if (i > 0) {
-                const double kavr = __dmul_rn(__dadd_rn(kprev, kcur), 0.5);   // ray.py:118
-                const double sk = __dmul_rn(st, kavr);
+                kavr = __dmul_rn(__dadd_rn(kprev, kcur), 0.5);   // ray.py:118
+                sk = __dmul_rn(st, kavr);
                 if (EXTRAS) {
                     const double lnew = __dadd_rn(lax, sk);                  // :120 cumsum
                     const double dl = __dsub_rn(lnew, lax);                  // :124 diff
@@ -500,7 +558,7 @@ trace_kernel(const KParams p)
                     // annulus of the bin just found, in squared physical radius
                     const double dr = p.hist_dr;
                     if (!p.hist_annulus) {
-                        // bins narrower than a few steps: the test would fail most of the time
+                        // bins narrower than a step: the test would fail most of the time
                     } else if (bnew >= 0) {
                         const double a = dr * (double)bnew, b2 = dr * (double)(bnew + 1);
                         r2lo = a * a * (1.0 + 1e-12);
@@ -517,46 +575,39 @@ trace_kernel(const KParams p)
         }
 
         if (CROSS) {
-            // state i is kept; lax, ph are its running sums
-            const double c = axis_y ? y0p + (y - yg0) * p.dy : x0p + (x - xg0) * p.dx;
-            const double d = c - p.cross_val;
-            if (d == 0.0) {
+            // state i is kept; lax, ph are its running sums; dcur = its receiver coordinate - val
+            if (dcur == 0.0) {                         // ray.py:142-143: an existing point lies on the line
                 if (neq == 0) {
-                    cx = x0p + (x - xg0) * p.dx; cy = y0p + (y - yg0) * p.dy;
-                    ckx = kx; cky = ky; clax = lax; cph = ph; cidx = i;
+                    cidx = i;
+                    const CrossCtx c{p.field, p.x0p, p.y0p, p.x0, p.y0, p.cross_state, p.nrays, p.dx, p.dy, p.cross_val, axis_y};
+                    cross_exact_hit(c, ray, x, y, kx, ky, lax, ph);
                 }
                 ++neq;
             }
-            below |= d < 0.0;
-            above |= d > 0.0;
-            bool captured_now = false;
-            if (i > 0 && dprev * d < 0.0) {
-                if (ncross == 0 && neq == 0) captured_now = capture_from_prev(st);
-                ++ncross;
-            }
+            below |= dcur < 0.0;
+            above |= dcur > 0.0;
             if (LOOKUP) {
+                // the polyline Beam.field_r sees after addpoint: kept states plus the inserted crossing
+                // point, phase recomputed (ray.py:205-216, 122-126).  Before the insertion its sums equal
+                // lax / ph (same operations); the crossing point splits segment (i-1, i): st[i-1] = s,
+                // st[new] = st - s (ray.py:205-210)
                 const double xpi = x0p + (x - xg0) * p.dx, ypi = y0p + (y - yg0) * p.dy;
-                const double ki = sqrt(kx * kx + ky * ky);
                 if (i > 0) {
-                    if (captured_now && !inserted) {
-                        // the crossing point splits segment (i-1, i): st[i-1] = s, st[new] = st - s (ray.py:205-210)
+                    if (cap_seg) {
                         add_point(cph, cx, cy);
-                        const double kav2 = (ckn + ki) / 2;
+                        const double kav2 = (ckn + kcur) / 2;
                         const double l2 = clax + (st - cs) * kav2;
                         ph2 = cph + (l2 - clax) * kav2;
                         lax2 = l2;
-                        inserted = true;
+                        cap_seg = false;
                     } else {
-                        const double kpv = sqrt(pkx * pkx + pky * pky);
-                        const double kav = (kpv + ki) / 2;
-                        const double l2 = lax2 + st * kav;
-                        ph2 = ph2 + (l2 - lax2) * kav;
+                        const double l2 = lax2 + sk;
+                        ph2 = ph2 + (l2 - lax2) * kavr;
                         lax2 = l2;
                     }
                 }
                 add_point(ph2, xpi, ypi);
             }
-            pxg = x; pyg = y; pkx = kx; pky = ky; pind = ind; plax = lax; pph = ph; dprev = d;
         }
 
         const double tx = HOIST ? h.x : __dmul_rn(__dmul_rn(sst, m.x), 0.5);   // ((st*st)*Mx)/2
@@ -573,15 +624,38 @@ trace_kernel(const KParams p)
         if (EXTRAS) {
             if (turn < 0 && ((ky > 0.0 && ky1 <= 0.0) || (ky < 0.0 && ky1 >= 0.0))) {
                 turn = i + 1;
-                tsx = x1; tsy = y1; tskx = kx1; tsky = ky1;
+                if (p.turn_state) {
+                    p.turn_state[0 * p.nrays + ray] = x1;  p.turn_state[1 * p.nrays + ray] = y1;
+                    p.turn_state[2 * p.nrays + ray] = kx1; p.turn_state[3 * p.nrays + ray] = ky1;
+                }
             }
         }
-        x = x1; y = y1; kx = kx1; ky = ky1;
-        ++i;
-        if (TRAJ) {
+        if (TRAJ) {     // states 0..n are written (sidtracemodule.c:41-45), kept or not
             tp += TILED ? 4 * p.tile : 4;
-            st_state<true>(tp, x, y, kx, ky);
+            st_state<true>(tp, x1, y1, kx1, ky1);
         }
+        int ind1;
+        const bool ok1 = guard(x1, y1, i + 1, ind1);              // :36 on state i+1
+        if (CROSS) {
+            const double d1 = (c0p + ((axis_y ? y1 : x1) - g0) * dg) - p.cross_val;
+            // a sign change between two KEPT states (ray.py:144-146); the first one is solved for
+            if (ok1 && dcur * d1 < 0.0) {
+                if (ncross == 0 && neq == 0) {
+                    const bool got = capture(x, y, kx, ky, ind, lax, ph, st, i + 1);
+                    if (LOOKUP) cap_seg = got;
+                }
+                ++ncross;
+            }
+            dcur = d1;
+        }
+        if (!ok1) {
+            if (CROSS) { pxg = x; pyg = y; pkx = kx; pky = ky; pind = ind; plax = lax; pph = ph; }
+            x = x1; y = y1; kx = kx1; ky = ky1;
+            ++i;
+            return false;
+        }
+        x = x1; y = y1; kx = kx1; ky = ky1; ind = ind1;
+        ++i;
         return true;
     };
 
@@ -602,8 +676,7 @@ trace_kernel(const KParams p)
             const long long slot = r;
             if (packed) r = slot < p.nslots ? (long long)p.perm[slot] : -1;
             const bool has = r >= 0 && r < p.nrays;
-            if (has) {
-                launch(r, slot);
+            if (has && launch(r, slot)) {
                 while (step()) { }
             }
             if (TILED) __syncwarp();
@@ -637,12 +710,18 @@ trace_kernel(const KParams p)
                 base = __shfl_sync(FULL, base, leader);
                 if (!active) {
                     const long long r = (long long)base + __popc(idle & ((1u << lane) - 1u));
-                    if (r < p.nrays) { launch(r, r); active = true; }
+                    if (r < p.nrays) {
+                        if (launch(r, r)) active = true;
+                        else retire();                      // a ray that takes no step
+                    }
                 }
                 more = (long long)(base + want) < p.nrays;
                 act = __ballot_sync(FULL, active);
             }
-            if (act == 0) break;
+            if (act == 0) {
+                if (!more) break;
+                continue;                                   // every claimed ray ended at launch: claim again
+            }
             if (active) {
 #pragma unroll 1
                 for (int s = 0; s < kBatch; ++s) {
