@@ -198,6 +198,56 @@ int stb_launch_states(const stb_launch_t *a, void *stream);
  * members[offsets[k] .. offsets[k+1]). */
 int stb_field_pages(const double *xout, int64_t n, int64_t *offsets, int64_t *members, int64_t *npages);
 
+/* ---- the O(rays) tail of Beam.field_r / field_result on the device --------------------- */
+/* The pages again, as per-ray links and in O(n log P) (host, no device work): pred[j] / succ[j] = the ray
+ * before / after ray j in its page (-1 at the page's ends), page_size[j] = rays in ray j's page (pages of
+ * one ray are dropped by the reference, beam.py:392-398), *npages = pages of two or more rays.  The walk of
+ * beam.py:374-398 is first-fit -- a ray joins the first page whose last member it lies beyond -- and the
+ * pages' last members are non-increasing in the page index, so each ray is placed by bisection. */
+int stb_field_pages_links(const double *xout, int64_t n, int32_t *pred, int32_t *succ, int32_t *page_size, int64_t *npages);
+
+/* Ray-tube amplitude and complex field on the receiver line (beam.py:404-427) for the n rays that cross it
+ * exactly once, in launch order: amp1 = sqrt((d0l + d0r)/(d1l + d1r)) with d0 the distance to the page
+ * neighbours at launch and d1 at equal phase (lookup_xy = the lookup pass' output for targets A = phase of
+ * succ, B = phase of pred), NaN -> amp0; field = amp0 * amp1 * exp(-i ph), 0 for rays of dropped pages.
+ * DEVICE pointers; field is interleaved complex [n][2]. */
+typedef struct stb_tube_s {
+    size_t   struct_size;
+    int64_t  n;
+    const int32_t *pred, *succ, *page_size;
+    const double *x0, *y0;          /* launch points, cm                                   */
+    const double *xc, *yc, *ph;     /* crossing point and eikonal phase (cross_state 0, 1, 5) */
+    const double *amp0;
+    const double *lookup_xy;        /* [4][n]                                              */
+    double  *amp1;                  /* [n] out                                             */
+    double  *field;                 /* [n][2] out                                          */
+} stb_tube_t;
+int stb_tube_field(const stb_tube_t *a, void *stream);
+/* beam.py:436-440 on the arrays sorted by receiver coordinate: rays whose field is 0 take the mean of their
+ * two neighbours' amplitude (np.roll: cyclic), NaN -> amp0, and field = amp0 * amp1 * exp(-i ph).
+ * amp1_in != amp1_out (the neighbours' OLD values are read). */
+int stb_hole_fill(int64_t n, const double *amp0, const double *ph, const double *amp1_in, double *amp1_out, double *field, void *stream);
+
+/* field_result, first half (beam.py:448-461): field = field_tx x the analytic pattern of the RX beam at
+ * (x, y_rx) (beam.py:103-131, 176-206, n = 1); sums[0..4] = sum|f|, sum|f| x, Re / Im of sum f dist
+ * (dist = centred spacing of x, beam.py:455-457), max|f|.  sums has room for 8 doubles. */
+typedef struct stb_overlap_s {
+    size_t   struct_size;
+    int64_t  n;
+    const double *x;                /* [n] receiver coordinate, sorted                     */
+    const double *field_tx;         /* [n][2]                                              */
+    double   y_rx;
+    double   bx0, by0, bkx, bky, focus, waist, wave_len, rayleigh, gouy;   /* RX beam      */
+    double  *field;                 /* [n][2] out                                          */
+    double  *absf;                  /* [n] out                                             */
+    double  *sums;                  /* [8] out (zeroed by the call)                        */
+} stb_overlap_t;
+int stb_overlap(const stb_overlap_t *a, void *stream);
+/* field_result, second half (beam.py:463-467): the sums a Gauss-Newton / Levenberg-Marquardt step of the fit
+ * y ~ amp exp(-(x - xc)^2 / (2 sigma^2)) needs at the current parameters: out[0..5] = J^T J (aa ab ac bb bc cc),
+ * out[6..8] = J^T r, out[9] = r^T r (r = model - y).  out (DEVICE, 10 doubles) is zeroed by the call. */
+int stb_gauss_fit_sums(const double *x, const double *y, int64_t n, double amp, double xc, double sigma, double *out, void *stream);
+
 /* ---- beam launch conditions on the device (Beam.rays, beam.py:293-331) -------------------------- */
 /* n start points equidistant in arc length along a wavefront given by nw nodes (arc length lax[],
  * beam-frame x wf_x[]) and the cubic B-spline (t, c) of its y(x); unit normals from the reference's

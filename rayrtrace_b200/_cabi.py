@@ -29,7 +29,7 @@ F_NO_HOIST = 1 << 6
 EXPORTS = (
     "stb_abi_version", "stb_last_error", "stb_device_count", "stb_set_device",
     "stb_field_create", "stb_field_destroy", "stb_field_shape", "stb_field_peek",
-    "stb_trace", "stb_check", "stb_trace_batch", "stb_launch_states", "stb_beam_launch", "stb_field_pages", "stb_pack_traj", "stb_pack_traj_plan", "stb_traj_plan", "stb_launch_count",
+    "stb_trace", "stb_check", "stb_trace_batch", "stb_launch_states", "stb_beam_launch", "stb_field_pages", "stb_field_pages_links", "stb_tube_field", "stb_hole_fill", "stb_overlap", "stb_gauss_fit_sums", "stb_pack_traj", "stb_pack_traj_plan", "stb_traj_plan", "stb_launch_count",
     "stb_measure_fp64_peak", "stb_measure_store_bw", "stb_measure_store_pattern",
     # include/sidtrace_b200_comm.h (multi-GPU entry points)
     "stb_comm_unique_id", "stb_comm_init", "stb_comm_destroy", "stb_comm_rank", "stb_comm_allreduce_f64",
@@ -107,6 +107,37 @@ class StbBeam(Structure):
     ]
 
 
+class StbTube(Structure):
+    """Mirror of ``stb_tube_t``."""
+    _fields_ = [
+        ("struct_size", c_size_t),
+        ("n", c_int64),
+        ("pred", c_void_p), ("succ", c_void_p), ("page_size", c_void_p),
+        ("x0", c_void_p), ("y0", c_void_p),
+        ("xc", c_void_p), ("yc", c_void_p), ("ph", c_void_p),
+        ("amp0", c_void_p),
+        ("lookup_xy", c_void_p),
+        ("amp1", c_void_p),
+        ("field", c_void_p),
+    ]
+
+
+class StbOverlap(Structure):
+    """Mirror of ``stb_overlap_t``."""
+    _fields_ = [
+        ("struct_size", c_size_t),
+        ("n", c_int64),
+        ("x", c_void_p),
+        ("field_tx", c_void_p),
+        ("y_rx", c_double),
+        ("bx0", c_double), ("by0", c_double), ("bkx", c_double), ("bky", c_double), ("focus", c_double),
+        ("waist", c_double), ("wave_len", c_double), ("rayleigh", c_double), ("gouy", c_double),
+        ("field", c_void_p),
+        ("absf", c_void_p),
+        ("sums", c_void_p),
+    ]
+
+
 class StbMediumDesc(Structure):
     """Mirror of ``stb_medium_desc_t`` (include/sidtrace_b200_rk.h)."""
     _fields_ = [
@@ -181,6 +212,16 @@ def _load() -> ctypes.CDLL:
     lib.stb_beam_launch.restype = c_int
     lib.stb_field_pages.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, POINTER(c_int64)]
     lib.stb_field_pages.restype = c_int
+    lib.stb_field_pages_links.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, POINTER(c_int64)]
+    lib.stb_field_pages_links.restype = c_int
+    lib.stb_tube_field.argtypes = [POINTER(StbTube), c_void_p]
+    lib.stb_tube_field.restype = c_int
+    lib.stb_hole_fill.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.stb_hole_fill.restype = c_int
+    lib.stb_overlap.argtypes = [POINTER(StbOverlap), c_void_p]
+    lib.stb_overlap.restype = c_int
+    lib.stb_gauss_fit_sums.argtypes = [c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_void_p, c_void_p]
+    lib.stb_gauss_fit_sums.restype = c_int
     lib.stb_pack_traj.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.stb_pack_traj.restype = c_int
     lib.stb_pack_traj_plan.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]

@@ -569,10 +569,208 @@ def field_r_device(beam: Beam, y, axis="y"):
     return field, xout, amp0, amp1, ph, pnt
 
 
+def receiver_field_device(beam: Beam, y, axis="y"):
+    """``Beam.field_r`` (beam.py:347-444) with every O(rays) array on the GPU: the crossing of the receiver
+    line comes from the fused ``cross`` output of the trace, the page structure from
+    ``stb_field_pages_links`` (first-fit by bisection; skipped when the receiver coordinate is monotonic
+    in the launch order -- one page), the neighbour rays' points at equal eikonal phase from the lookup
+    launch, ray-tube amplitudes and the complex field from ``stb_tube_field``, the rays of dropped pages
+    from ``stb_hole_fill``.  Returns a dict of CUDA tensors sorted by receiver coordinate:
+    field [n, 2] (re, im), xout, amp0, amp1, ph, pnt."""
+    import ctypes
+    import torch
+    from . import _cabi, sidtrace as _st
+    from .ray import _device_field
+    if beam.length_unit == "m":
+        y = y * 100
+    bun = beam.bundle
+    nf = bun.n_field
+    fld = _device_field(nf)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    kw = dict(L=int(bun.L), st=bun.st, dx=float(nf.dx[0]), dy=float(nf.dy[0]))
+
+    def up(a):
+        return a if hasattr(a, "is_cuda") else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    if bun.dev is not None:
+        launch, x0p, y0p, amp = bun.dev["launch"], bun.dev["x0"], bun.dev["y0"], bun.dev["amp"]
+    else:
+        launch = [up(a) for a in (bun.xg0, bun.yg0, bun.kx0, bun.ky0)]
+        x0p, y0p, amp = up(bun.x0), up(bun.y0), up(np.asarray(bun.amp, float))
+    res = bun.result
+    if res is None or res.cross_count is None or bun.receiver != (float(y), axis) or not hasattr(res.cross_count, "is_cuda"):
+        res = _st.trace_batch(fld, *launch, cross=(float(y), axis), x0_phys=x0p, y0_phys=y0p, **kw)
+    keep = torch.nonzero(res.cross_count == 1).squeeze(1)            # exactly one crossing (beam.py:361-364)
+    n = int(keep.numel())
+    cs = res.cross_state.index_select(1, keep)
+    xc, yc, ph = cs[0].contiguous(), cs[1].contiguous(), cs[5].contiguous()
+    amp0 = amp.index_select(0, keep)
+    pnt = res.cross_index.index_select(0, keep)
+    x0k, y0k = x0p.index_select(0, keep), y0p.index_select(0, keep)
+    i32 = dict(dtype=torch.int32, device=dev)
+    if n < 2 or bool((xc[1:] > xc[:-1]).all()):                     # no caustic, no jumps: one page
+        pred = torch.arange(-1, n - 1, **i32)
+        succ = torch.arange(1, n + 1, **i32)
+        if n:
+            succ[-1] = -1
+        page_size = torch.full((n,), n, **i32)
+    else:
+        hx = xc.cpu().numpy()
+        hp, hs, hz = (np.empty(n, np.int32) for _ in range(3))
+        npages = ctypes.c_int64()
+        _cabi.check(_cabi.lib.stb_field_pages_links(hx.ctypes.data, n, hp.ctypes.data, hs.ctypes.data, hz.ctypes.data,
+                                                    ctypes.byref(npages)))
+        pred, succ, page_size = (torch.from_numpy(a).to(dev) for a in (hp, hs, hz))
+    # every ray is asked for its point at the phase of its right-hand (A) and left-hand (B) page
+    # neighbour's crossing (a page end asks for its own phase; that answer is never used)
+    own = torch.arange(n, device=dev)
+    tA = ph[torch.where(succ >= 0, succ.long(), own)]
+    tB = ph[torch.where(pred >= 0, pred.long(), own)]
+    amp1 = torch.empty(n, dtype=torch.float64, device=dev)
+    field = torch.empty((n, 2), dtype=torch.float64, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    if n:
+        look = _st.trace_batch(fld, *[a.index_select(0, keep) for a in launch], cross=(float(y), axis), x0_phys=x0k, y0_phys=y0k,
+                               lookup_ph=torch.stack([tA, tB]).contiguous(), **kw)
+        a = _cabi.StbTube()
+        a.struct_size = ctypes.sizeof(_cabi.StbTube)
+        a.n = n
+        a.pred, a.succ, a.page_size = pred.data_ptr(), succ.data_ptr(), page_size.data_ptr()
+        a.x0, a.y0, a.xc, a.yc, a.ph = x0k.data_ptr(), y0k.data_ptr(), xc.data_ptr(), yc.data_ptr(), ph.data_ptr()
+        a.amp0, a.lookup_xy = amp0.data_ptr(), look.lookup_xy.data_ptr()
+        a.amp1, a.field = amp1.data_ptr(), field.data_ptr()
+        _cabi.check(_cabi.lib.stb_tube_field(ctypes.byref(a), stream))
+    order = torch.argsort(xc)
+    xout, field, amp0, amp1, ph, pnt = (t.index_select(0, order) for t in (xc, field, amp0, amp1, ph, pnt))
+    field = field.contiguous()
+    amp1f = torch.empty_like(amp1)
+    _cabi.check(_cabi.lib.stb_hole_fill(n, amp0.data_ptr(), ph.data_ptr(), amp1.data_ptr(), amp1f.data_ptr(), field.data_ptr(), stream))
+    return {"field": field, "xout": xout, "amp0": amp0, "amp1": amp1f, "ph": ph, "pnt": pnt}
+
+
+def _gauss_fit_device(x, y, p0, stream, max_iter=200):
+    """Least-squares fit of amp * exp(-(x - xc)^2 / (2 sigma^2)) to (x, y) -- what the reference asks of
+    scipy.optimize.curve_fit (beam.py:463-465) -- by Levenberg-Marquardt on the GPU: one reduction launch
+    per trial point (``stb_gauss_fit_sums``), the 3 x 3 solve on the host.  Iterated to the minimum itself
+    (step below 1e-13 relative), which MINPACK's answer approaches to its own tolerance.  None when it
+    does not converge."""
+    import ctypes
+    import torch
+    from . import _cabi
+    n = int(x.shape[0])
+    out = torch.empty(10, dtype=torch.float64, device=x.device)
+
+    def sums(p):
+        _cabi.check(_cabi.lib.stb_gauss_fit_sums(x.data_ptr(), y.data_ptr(), n, float(p[0]), float(p[1]), float(p[2]),
+                                                 out.data_ptr(), stream))
+        s = out.cpu().numpy()
+        A = np.array([[s[0], s[1], s[2]], [s[1], s[3], s[4]], [s[2], s[4], s[5]]])
+        return A, s[6:9].copy(), float(s[9])
+
+    p = np.array(p0, float)
+    A, g, c = sums(p)
+    lam = 1e-3
+    for _ in range(max_iter):
+        if not (np.all(np.isfinite(A)) and np.all(np.isfinite(g))):
+            return None
+        try:
+            d = np.linalg.solve(A + lam * np.diag(np.diag(A)), -g)
+        except np.linalg.LinAlgError:
+            lam *= 10
+            continue
+        q = p + d
+        A2, g2, c2 = sums(q)
+        if np.isfinite(c2) and c2 <= c:
+            small = np.all(np.abs(d) <= 1e-13 * np.maximum(np.abs(q), 1e-300))
+            p, A, g, lam = q, A2, g2, max(lam / 10, 1e-15)
+            stalled = c - c2 <= 1e-16 * c
+            c = c2
+            if small or (stalled and lam <= 1e-12):
+                return p
+        else:
+            lam *= 10
+            if lam > 1e15:
+                # no downhill step left: at the minimum to rounding
+                return p if np.all(np.abs(d) <= 1e-9 * np.maximum(np.abs(p), 1e-300)) else None
+    return None
+
+
+def _cubic_at(x, ph, xt, halfwidth=128):
+    """``interp1d(x, ph, kind='cubic')(xt)`` (beam.py:453) from a window of nodes around ``xt``: the
+    not-a-knot spline's dependence on a node decays by a factor ~(2 - sqrt 3) per node in between, so 128
+    nodes either side leave nothing in double precision -- and an O(n) banded solve for ONE value is
+    avoided.  ``x``, ``ph``: CUDA tensors or arrays, x increasing.  Raises ValueError outside the range."""
+    from scipy.interpolate import make_interp_spline
+    n = int(x.shape[0])
+    if not (float(x[0]) <= xt <= float(x[-1])):
+        raise ValueError("A value in x_new is outside the interpolation range.")
+    if hasattr(x, "is_cuda"):
+        import torch
+        i = int(torch.searchsorted(x, torch.tensor([xt], dtype=x.dtype, device=x.device))[0])
+    else:
+        i = int(np.searchsorted(x, xt))
+    lo, hi = max(0, i - halfwidth), min(n, i + halfwidth)
+    if hi - lo < 8:
+        lo, hi = 0, n
+    xs, ps = x[lo:hi], ph[lo:hi]
+    if hasattr(xs, "is_cuda"):
+        xs, ps = xs.cpu().numpy(), ps.cpu().numpy()
+    return make_interp_spline(np.asarray(xs, float), np.asarray(ps, float), k=3, check_finite=False)(xt)
+
+
+def field_result_device(beam_tx: Beam, beam_rx: Beam, want_arrays: bool = True):
+    """``field_result`` (beam.py:447-472) on the GPU: receiver-line field of the traced TX beam
+    (``receiver_field_device``) times the analytic RX pattern, |f|-weighted centre and the complex signal
+    in one launch (``stb_overlap``), the Gaussian fit by Levenberg-Marquardt over device reductions, the
+    cubic phase at the fitted centre from a window of nodes.  Only O(1) numbers cross PCIe unless
+    ``want_arrays`` (then field and x come back as the reference returns them)."""
+    import ctypes
+    import torch
+    from . import _cabi
+    r = receiver_field_device(beam_tx, beam_rx.y0)
+    x, ph, ftx = r["xout"].contiguous(), r["ph"].contiguous(), r["field"]
+    n = int(x.shape[0])
+    dev = x.device
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    field = torch.empty((n, 2), dtype=torch.float64, device=dev)
+    absf = torch.empty(n, dtype=torch.float64, device=dev)
+    sums = torch.empty(8, dtype=torch.float64, device=dev)
+    a = _cabi.StbOverlap()
+    a.struct_size = ctypes.sizeof(_cabi.StbOverlap)
+    a.n = n
+    a.x, a.field_tx = x.data_ptr(), ftx.data_ptr()
+    k = 100 if beam_rx.length_unit == "m" else 1
+    a.y_rx = float(beam_rx.y0)
+    a.bx0, a.by0, a.bkx, a.bky, a.focus = float(beam_rx.x0), float(beam_rx.y0), float(beam_rx._kx0), float(beam_rx._ky0), float(beam_rx.focus)
+    a.waist, a.wave_len, a.rayleigh, a.gouy = float(beam_rx.waist), float(beam_rx.wave_len), float(beam_rx.rayleigh_len(n=1.)), float(Beam._gouy)
+    a.field, a.absf, a.sums = field.data_ptr(), absf.data_ptr(), sums.data_ptr()
+    del k
+    _cabi.check(_cabi.lib.stb_overlap(ctypes.byref(a), stream))
+    s = sums.cpu().numpy()
+    x_max = s[1] / s[0]
+    signal = complex(s[2], s[3])
+    fmax = float(np.frombuffer(s[4:5].tobytes(), np.float64)[0])
+    props = _gauss_fit_device(x, absf, (fmax, x_max, beam_tx.waist), stream) if n >= 3 else None
+    try:
+        if props is None:
+            raise RuntimeError("the Gaussian fit did not converge")
+        ph_max = _cubic_at(x, ph, float(props[1]))
+    except Exception:
+        ph_max = _cubic_at(x, ph, float(x_max))
+        props = None
+    if want_arrays:
+        f = field.cpu().numpy()
+        return f[:, 0] + 1j * f[:, 1], x.cpu().numpy(), x_max, ph_max, signal, props
+    return None, None, x_max, ph_max, signal, props
+
+
 def field_result(beam_tx: Beam, beam_rx: Beam, device: bool = False):
     """Overlap of the traced TX field with the analytic RX pattern on the receiver line:
     complex interferometer signal and phase at the maximum (beam.py:447-472).  ``device=True``
-    takes the receiver-line field from ``field_r_device`` (no Ray objects)."""
+    takes the receiver-line field from ``field_r_device`` (no Ray objects); ``device="gpu"`` runs the whole
+    of it on the GPU (``field_result_device``)."""
+    if device == "gpu":
+        return field_result_device(beam_tx, beam_rx)
     field_tx, x, _, _, ph, pnt = field_r_device(beam_tx, beam_rx.y0) if device else beam_tx.field_r(beam_rx.y0)
     field = field_tx * beam_rx.field(x=x, y=beam_rx.y0)
     x_max = np.sum(np.abs(field) * x) / np.sum(np.abs(field))

@@ -17,7 +17,8 @@ SRC = os.path.join(_HERE, "csrc", "sidtrace_b200.cu")
 SRC_RK = os.path.join(_HERE, "csrc", "rk_b200.cu")      # adaptive-RK physics mode (extension)
 SRC_PLAN = os.path.join(_HERE, "csrc", "plan_b200.cu")  # exactly-sized trajectory arenas (CUB sort + scan)
 SRC_COMM = os.path.join(_HERE, "csrc", "comm_b200.cu")  # multi-GPU entry points (NCCL via dlopen)
-SOURCES = [SRC, SRC_RK, SRC_PLAN, SRC_COMM]
+SRC_FIELD = os.path.join(_HERE, "csrc", "field_b200.cu")  # O(rays) tail of Beam.field_r / field_result
+SOURCES = [SRC, SRC_RK, SRC_PLAN, SRC_COMM, SRC_FIELD]
 DEPS = SOURCES + [os.path.join(_HERE, "csrc", h) for h in ("trace_kernels.cuh", "launch_kernels.cuh", "rk_kernels.cuh")] + [
     os.path.join(os.path.dirname(_HERE), "include", h) for h in ("sidtrace_b200.h", "sidtrace_b200_rk.h", "sidtrace_b200_comm.h")]
 LIB_DIR = os.path.join(_HERE, "_lib")
@@ -29,7 +30,7 @@ NVCC_FLAGS = [
     "-fmad=false",                 # parity: no FMA contraction anywhere (kernels use explicit _rn intrinsics too)
     "-Xcompiler", "-fPIC", "-shared",
     "-cudart", "static",
-    "--threads", "4",
+    "--threads", "5",
 ]
 
 

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .beam import Beam, field_result
+from .beam import Beam, field_result, field_result_device
 from .nfield import Nfield
 
 r_dia = 7.85     # limiter radius, cm (ft2.py:6)
@@ -32,15 +32,21 @@ def _pair_phases(nfield, tx, rx, device=True):
     """One TX/RX antenna pair: trace the TX beam through ``nfield``, overlap its field on the
     receiver line with the RX antenna pattern (beam.py:447-472).  ``device=True``: the crossing of
     the receiver line is fused into the trace and the neighbour-ray lookup is one more launch --
-    no trajectories kept, no Ray objects; ``device=False``: the reference's flow on materialised
-    rays (Ray.addpoint + interp1d on the host)."""
+    no trajectories kept, no Ray objects, and the O(rays) post-processing (pages, ray-tube amplitudes,
+    overlap with the RX pattern, Gaussian fit) stays on the GPU (``field_result_device``);
+    ``device="host-tail"``: the same two launches with the round-1 NumPy / SciPy post-processing;
+    ``device=False``: the reference's flow on materialised rays (Ray.addpoint + interp1d on the host)."""
     beam_rx = Beam(x0=rx[0], y0=rx[1], kx0=0, ky0=-1)
     if device:
         beam_tx = Beam(x0=tx[0], y0=tx[1], kx0=0, ky0=1)
-        beam_tx.rays(n_field=nfield, keep_traj=False, receiver=(float(rx[1]), "y"))
+        gpu_tail = device != "host-tail"
+        beam_tx.rays(n_field=nfield, keep_traj=False, receiver=(float(rx[1]), "y"), host_results=not gpu_tail)
+        if gpu_tail:
+            _, _, _, ph_at_max, signal, _ = field_result_device(beam_tx, beam_rx, want_arrays=False)
+            return ph_at_max, np.angle(signal)
     else:
         beam_tx = Beam(x0=tx[0], y0=tx[1], kx0=0, ky0=1, n_field=nfield)
-    _, _, _, ph_at_max, signal, *_ = field_result(beam_tx, beam_rx, device=device)
+    _, _, _, ph_at_max, signal, *_ = field_result(beam_tx, beam_rx, device=bool(device))
     return ph_at_max, np.angle(signal)
 
 

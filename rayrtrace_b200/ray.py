@@ -179,6 +179,7 @@ class RayBundle:
     result: object = None     # sidtrace.BatchResult (traj is a CUDA tensor or None)
     L: int = 0                # states per ray the launch was sized for
     receiver: object = None   # (val, axis) of the fused crossing output, if any
+    dev: object = None        # CUDA copies kept for the device-side consumers: launch [4 tensors], x0, y0, amp
 
     def __len__(self):
         return len(self.nsteps)
@@ -284,7 +285,7 @@ def _host_results(res):
 
 def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional[int] = None,
                keep_traj: bool = True, want_extras: bool = False, tiled: bool = True,
-               receiver=None, device_launch: Optional[bool] = None) -> RayBundle:
+               receiver=None, device_launch: Optional[bool] = None, host_results: bool = True) -> RayBundle:
     """Trace a whole fan of rays (replaces the serial loop of beam.py:340-342).
 
     max_steps: array length per ray, default ``Ray.MaxStep`` (ray.py:11) -- the reference's own cap, so a
@@ -300,7 +301,10 @@ def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional
     evaluation would take longer than the trace.
     receiver: (val, axis) -- also report, per ray, what ``Ray.addpoint(val, axis)`` would
     (ray.py:131-224): first crossing of the receiver line, its phase and wave vector
-    (``bundle.result.cross_*``), i.e. the per-ray inputs of ``Beam.field_r`` (beam.py:359-369)."""
+    (``bundle.result.cross_*``), i.e. the per-ray inputs of ``Beam.field_r`` (beam.py:359-369).
+    host_results: False leaves the per-ray outputs on the GPU (CUDA tensors in ``bundle.result`` /
+    ``bundle.nsteps``) for the device-side consumers (``beam.field_result_device``); nothing O(rays) is
+    copied to the host then."""
     import torch
     if device_launch is None:
         device_launch = np.size(x0) >= 65536 and hasattr(n_field, "device_launch_tables")
@@ -323,8 +327,11 @@ def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional
     st = float(n_field.st * Ray.kStep)
     f = _device_field(n_field)
     kw = dict(L=L, st=st, dx=float(n_field.dx[0]), dy=float(n_field.dy[0]), want_extras=want_extras, cross=receiver)
+    d_x0 = d_y0 = None
+    if receiver or not host_results:
+        d_x0, d_y0 = torch.from_numpy(x0.copy()).to(dev), torch.from_numpy(y0.copy()).to(dev)
     if receiver:
-        kw.update(x0_phys=torch.from_numpy(x0).to(dev), y0_phys=torch.from_numpy(y0).to(dev))
+        kw.update(x0_phys=d_x0, y0_phys=d_y0)
     if keep_traj and tiled and n:
         res = _st.trace_exact(f, *d_in, **kw)
     else:
@@ -340,8 +347,12 @@ def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional
                                   f"free HBM ({free / 1e9:.1f} GB): use tiled=True (exactly sized), keep_traj=False, or chunks")
             t = _st.trace_batch(f, *d_in, L=L2, st=st, dx=kw["dx"], dy=kw["dy"], traj=True, want_end=False)
             res.traj, res.tiled = t.traj, False
-    torch.cuda.current_stream(dev).synchronize()
-    res = _host_results(res)
+    keep_dev = None
+    if host_results:
+        torch.cuda.current_stream(dev).synchronize()
+        res = _host_results(res)
+    else:
+        keep_dev = {"launch": d_in, "x0": d_x0, "y0": d_y0, "amp": torch.from_numpy(amp).to(dev)}
     return RayBundle(n_field=n_field, x0=x0, y0=y0, freq=freq, st=st, amp=amp,
                      xg0=xg, yg0=yg, kx0=kx, ky0=ky, nsteps=res.nsteps, end_state=res.end_state, result=res, L=L,
-                     receiver=(float(receiver[0]), receiver[1]) if receiver else None)
+                     receiver=(float(receiver[0]), receiver[1]) if receiver else None, dev=keep_dev)

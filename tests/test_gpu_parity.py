@@ -678,7 +678,8 @@ def test_ft2_phases_driver_matches_reference(st, ft2_phases_fix):
     The fixture is the reference's own ft2.phases output (tests/golden/make_golden.py)."""
     from rayrtrace_b200 import ft2
     n, x, y = ft2_density(int(ft2_phases_fix["nx"]), float(ft2_phases_fix["n0"]))
-    for device in (True, False):       # fused crossing + lookup launches / materialised Ray objects
+    # GPU tail (everything O(rays) on the device) / the two launches + NumPy tail / materialised Ray objects
+    for device in (True, "host-tail", False):
         ph_max, ph_sig = ft2.phases(n, x, y, a_set=ft2_phases_fix["a_set"], nray=int(ft2_phases_fix["nray"]), device=device)
         assert ph_max.shape == ph_sig.shape == (3, 7)
         d = np.angle(np.exp(1j * (ph_sig - ft2_phases_fix["ph_by_sig"])))      # compare angles modulo 2 pi
@@ -691,7 +692,7 @@ def test_ft2_phases_driver_matches_reference_in_dense_plasmas(st, ft2_phases_fix
     beams (several 'pages' in field_r, rays missing the receiver)."""
     from rayrtrace_b200 import ft2
     n, x, y = ft2_density(int(ft2_phases_fix["nx"]), float(ft2_phases_fix["n0"]))
-    for device in (True, False):
+    for device in (True, "host-tail", False):
         ph_max, ph_sig = ft2.phases(n, x, y, a_set=ft2_phases_fix["dense_a_set"], nray=int(ft2_phases_fix["nray"]), device=device)
         d = np.angle(np.exp(1j * (ph_sig - ft2_phases_fix["dense_ph_by_sig"])))
         assert np.abs(d).max() < 1e-5, (device, d)
@@ -762,6 +763,15 @@ def test_field_r_device_matches_reference(st, beam_fix):
     np.testing.assert_allclose(f2, beam_fix["field"], rtol=1e-7, atol=1e-12)      # TX field x RX pattern (beam.py:451)
     assert abs(signal - complex(beam_fix["signal"])) < 1e-7 * abs(complex(beam_fix["signal"]))
     assert float(ph_max) == pytest.approx(float(beam_fix["ph_max"]), rel=1e-9)
+    # the same with every O(rays) array and reduction on the GPU (receiver_field_device, stb_tube_field,
+    # stb_hole_fill, stb_overlap, Levenberg-Marquardt over stb_gauss_fit_sums instead of curve_fit)
+    f3, x3, x_max3, ph_max3, signal3, props3 = field_result(tx, rx, device="gpu")
+    np.testing.assert_allclose(x3, beam_fix["xout"], rtol=1e-9)
+    np.testing.assert_allclose(f3, beam_fix["field"], rtol=1e-7, atol=1e-12)
+    assert abs(signal3 - complex(beam_fix["signal"])) < 1e-7 * abs(complex(beam_fix["signal"]))
+    assert x_max3 == pytest.approx(float(beam_fix["x_max"]), rel=1e-8, abs=1e-9)
+    np.testing.assert_allclose(props3, beam_fix["props"], rtol=1e-7)           # MINPACK stops at its own tolerance
+    assert float(ph_max3) == pytest.approx(float(beam_fix["ph_max"]), rel=1e-9)
     # and equals the host path (Ray objects + addpoint + interp1d) on the same beam
     tx2 = Beam(x0=x0, y0=y0, kx0=0, ky0=1)
     tx2.rays(rnum=int(beam_fix["rnum"]), wave_front=wf, dist=3, ampbnd=1e-3, n_field=nf)
@@ -1214,3 +1224,34 @@ def test_plain_c_two_rank_caller_of_the_comm_abi(st, torch_mod, tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "bit-identical" in r.stdout and "MISMATCH" not in r.stdout
+
+
+def test_gpu_tail_equals_host_tail_on_a_folded_many_page_beam(st, torch_mod):
+    """The device-side O(rays) tail against the NumPy / SciPy one on a beam that needs it all: 20 001 rays
+    through a plasma at 0.8 of critical (hundreds of pages, rays that miss the receiver, holes)."""
+    from rayrtrace_b200.beam import Beam, field_r_device, field_result, receiver_field_device
+    from rayrtrace_b200.nfield import Nfield
+    n, x, y = ft2_density(201, 1.85e14)
+    nf = Nfield(n, x=x, y=y)
+    xa = -2.3
+    ya = -np.sqrt(100 - xa ** 2)
+    tx = Beam(x0=xa, y0=ya, kx0=0, ky0=1)
+    rx = Beam(x0=xa, y0=-ya, kx0=0, ky0=-1)
+    tx.rays(rnum=20001, n_field=nf, keep_traj=False, receiver=(float(-ya), "y"))
+    fh, xh, a0h, a1h, phh, pnth = field_r_device(tx, -ya)
+    d = receiver_field_device(tx, -ya)
+    g = {k: v.cpu().numpy() for k, v in d.items()}
+    assert len(xh) == len(g["xout"]) > 15000
+    np.testing.assert_allclose(g["xout"], xh, rtol=0, atol=0)
+    np.testing.assert_allclose(g["ph"], phh, rtol=0, atol=0)
+    assert np.array_equal(g["pnt"], pnth)
+    np.testing.assert_allclose(g["amp1"], a1h, rtol=1e-9)
+    np.testing.assert_allclose(g["field"][:, 0] + 1j * g["field"][:, 1], fh, rtol=1e-9, atol=1e-13)
+    host = field_result(tx, rx, device=True)
+    gpu = field_result(tx, rx, device="gpu")
+    np.testing.assert_allclose(gpu[0], host[0], rtol=1e-9, atol=1e-13)
+    assert gpu[2] == pytest.approx(host[2], rel=1e-10)
+    assert abs(gpu[4] - host[4]) < 1e-9 * abs(host[4])
+    if host[5] is not None:
+        np.testing.assert_allclose(gpu[5], host[5], rtol=1e-6)
+        assert float(gpu[3]) == pytest.approx(float(host[3]), rel=1e-8)
