@@ -243,10 +243,13 @@ typedef struct stb_overlap_s {
     double  *sums;                  /* [8] out (zeroed by the call)                        */
 } stb_overlap_t;
 int stb_overlap(const stb_overlap_t *a, void *stream);
-/* field_result, second half (beam.py:463-467): the sums a Gauss-Newton / Levenberg-Marquardt step of the fit
+/* field_result, second half (beam.py:463-467): what one Levenberg-Marquardt iteration of the fit
  * y ~ amp exp(-(x - xc)^2 / (2 sigma^2)) needs at the current parameters: out[0..5] = J^T J (aa ab ac bb bc cc),
- * out[6..8] = J^T r, out[9] = r^T r (r = model - y).  out (DEVICE, 10 doubles) is zeroed by the call. */
-int stb_gauss_fit_sums(const double *x, const double *y, int64_t n, double amp, double xc, double sigma, double *out, void *stream);
+ * out[6..8] = J^T r, out[9] = r^T r (r = model - y).  fd_step (HOST, 3 doubles) != NULL: the Jacobian columns
+ * are MINPACK's forward differences with these steps (what scipy.optimize.curve_fit uses without jac=);
+ * NULL: analytic columns.  out (DEVICE, 10 doubles) is zeroed by the call. */
+int stb_gauss_fit_sums(const double *x, const double *y, int64_t n, double amp, double xc, double sigma, const double *fd_step,
+                       double *out, void *stream);
 
 /* ---- beam launch conditions on the device (Beam.rays, beam.py:293-331) -------------------------- */
 /* n start points equidistant in arc length along a wavefront given by nw nodes (arc length lax[],

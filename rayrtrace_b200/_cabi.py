@@ -220,7 +220,7 @@ def _load() -> ctypes.CDLL:
     lib.stb_hole_fill.restype = c_int
     lib.stb_overlap.argtypes = [POINTER(StbOverlap), c_void_p]
     lib.stb_overlap.restype = c_int
-    lib.stb_gauss_fit_sums.argtypes = [c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_void_p, c_void_p]
+    lib.stb_gauss_fit_sums.argtypes = [c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p]
     lib.stb_gauss_fit_sums.restype = c_int
     lib.stb_pack_traj.argtypes = [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.stb_pack_traj.restype = c_int

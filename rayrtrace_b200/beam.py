@@ -648,51 +648,29 @@ def receiver_field_device(beam: Beam, y, axis="y"):
     return {"field": field, "xout": xout, "amp0": amp0, "amp1": amp1f, "ph": ph, "pnt": pnt}
 
 
-def _gauss_fit_device(x, y, p0, stream, max_iter=200):
+def _gauss_fit_device(x, y, p0, stream):
     """Least-squares fit of amp * exp(-(x - xc)^2 / (2 sigma^2)) to (x, y) -- what the reference asks of
-    scipy.optimize.curve_fit (beam.py:463-465) -- by Levenberg-Marquardt on the GPU: one reduction launch
-    per trial point (``stb_gauss_fit_sums``), the 3 x 3 solve on the host.  Iterated to the minimum itself
-    (step below 1e-13 relative), which MINPACK's answer approaches to its own tolerance.  None when it
-    does not converge."""
+    scipy.optimize.curve_fit (beam.py:463-465) -- with the data on the GPU: MINPACK's lmdif restated over
+    reductions (``lmfit.lmdif3``; one ``stb_gauss_fit_sums`` launch per trial point, forward-difference
+    Jacobian with MINPACK's steps, the 3 x 3 algebra on the host), so that it stops where curve_fit stops
+    even on the flat cost surfaces of folded beams.  None when lmdif reports failure (curve_fit raises)."""
     import ctypes
     import torch
     from . import _cabi
+    from .lmfit import lmdif3
     n = int(x.shape[0])
     out = torch.empty(10, dtype=torch.float64, device=x.device)
 
-    def sums(p):
+    def sums(p, h):
+        hs = (ctypes.c_double * 3)(*[float(v) for v in h])
         _cabi.check(_cabi.lib.stb_gauss_fit_sums(x.data_ptr(), y.data_ptr(), n, float(p[0]), float(p[1]), float(p[2]),
-                                                 out.data_ptr(), stream))
+                                                 hs, out.data_ptr(), stream))
         s = out.cpu().numpy()
         A = np.array([[s[0], s[1], s[2]], [s[1], s[3], s[4]], [s[2], s[4], s[5]]])
         return A, s[6:9].copy(), float(s[9])
 
-    p = np.array(p0, float)
-    A, g, c = sums(p)
-    lam = 1e-3
-    for _ in range(max_iter):
-        if not (np.all(np.isfinite(A)) and np.all(np.isfinite(g))):
-            return None
-        try:
-            d = np.linalg.solve(A + lam * np.diag(np.diag(A)), -g)
-        except np.linalg.LinAlgError:
-            lam *= 10
-            continue
-        q = p + d
-        A2, g2, c2 = sums(q)
-        if np.isfinite(c2) and c2 <= c:
-            small = np.all(np.abs(d) <= 1e-13 * np.maximum(np.abs(q), 1e-300))
-            p, A, g, lam = q, A2, g2, max(lam / 10, 1e-15)
-            stalled = c - c2 <= 1e-16 * c
-            c = c2
-            if small or (stalled and lam <= 1e-12):
-                return p
-        else:
-            lam *= 10
-            if lam > 1e15:
-                # no downhill step left: at the minimum to rounding
-                return p if np.all(np.abs(d) <= 1e-9 * np.maximum(np.abs(p), 1e-300)) else None
-    return None
+    p, info = lmdif3(sums, p0)
+    return p if info in (1, 2, 3, 4) and np.all(np.isfinite(p)) else None
 
 
 def _cubic_at(x, ph, xt, halfwidth=128):
@@ -721,7 +699,7 @@ def _cubic_at(x, ph, xt, halfwidth=128):
 def field_result_device(beam_tx: Beam, beam_rx: Beam, want_arrays: bool = True):
     """``field_result`` (beam.py:447-472) on the GPU: receiver-line field of the traced TX beam
     (``receiver_field_device``) times the analytic RX pattern, |f|-weighted centre and the complex signal
-    in one launch (``stb_overlap``), the Gaussian fit by Levenberg-Marquardt over device reductions, the
+    in one launch (``stb_overlap``), the Gaussian fit by MINPACK's lmdif over device reductions, the
     cubic phase at the fitted centre from a window of nodes.  Only O(1) numbers cross PCIe unless
     ``want_arrays`` (then field and x come back as the reference returns them)."""
     import ctypes

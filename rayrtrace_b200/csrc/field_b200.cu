@@ -159,20 +159,33 @@ __global__ void overlap_kernel(const stb_overlap_t a)
     if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long *)&a.sums[4], (unsigned long long)__double_as_longlong(mx));
 }
 
+// h0, h1, h2 != 0: forward-difference Jacobian columns (model(p + h_j e_j) - model(p)) / h_j, the way
+// MINPACK's fdjac2 forms them (curve_fit without jac=); 0: analytic columns.
 __global__ void gauss_sums_kernel(const double *__restrict__ x, const double *__restrict__ y, long long n,
-                                  double amp, double xc, double sigma, double *out)
+                                  double amp, double xc, double sigma, double h0, double h1, double h2, double *out)
 {
     __shared__ double sh[32];
     double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long step = (long long)gridDim.x * blockDim.x;
-    const double is2 = 1.0 / (sigma * sigma);
+    const bool fd = h0 != 0.0;
     for (; i < n; i += step) {
-        const double d = x[i] - xc;
-        const double e = exp(-d * d * 0.5 * is2);
-        const double g = amp * e;
+        const double xi = x[i];
+        const double d = xi - xc;
+        // amp * np.exp(-(xa - xc) ** 2 / 2 / sigma ** 2), operation for operation
+        const double g = amp * exp(-(d * d) / 2 / (sigma * sigma));
         const double r = g - y[i];
-        const double ja = e, jb = g * d * is2, jc = g * d * d * is2 / sigma;
+        double ja, jb, jc;
+        if (fd) {
+            ja = ((amp + h0) * exp(-(d * d) / 2 / (sigma * sigma)) - g) / h0;
+            const double d1 = xi - (xc + h1);
+            jb = (amp * exp(-(d1 * d1) / 2 / (sigma * sigma)) - g) / h1;
+            const double s2 = sigma + h2;
+            jc = (amp * exp(-(d * d) / 2 / (s2 * s2)) - g) / h2;
+        } else {
+            const double is2 = 1.0 / (sigma * sigma);
+            ja = g / amp; jb = g * d * is2; jc = g * d * d * is2 / sigma;
+        }
         s[0] += ja * ja; s[1] += ja * jb; s[2] += ja * jc; s[3] += jb * jb; s[4] += jb * jc; s[5] += jc * jc;
         s[6] += ja * r; s[7] += jb * r; s[8] += jc * r; s[9] += r * r;
     }
@@ -260,14 +273,17 @@ int stb_overlap(const stb_overlap_t *a, void *stream)
     return e == cudaSuccess ? STB_OK : cfail("stb_overlap", e);
 }
 
-int stb_gauss_fit_sums(const double *x, const double *y, int64_t n, double amp, double xc, double sigma, double *out, void *stream)
+int stb_gauss_fit_sums(const double *x, const double *y, int64_t n, double amp, double xc, double sigma, const double *fd_step,
+                       double *out, void *stream)
 {
     if (!out || (n > 0 && (!x || !y))) return stb_internal_fail(STB_ERR_ARG, "stb_gauss_fit_sums: NULL pointer");
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(out, 0, 10 * sizeof(double), s);
     if (e != cudaSuccess) return cfail("stb_gauss_fit_sums", e);
     if (n <= 0) return STB_OK;
-    gauss_sums_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, y, n, amp, xc, sigma, out);
+    const double h0 = fd_step ? fd_step[0] : 0.0, h1 = fd_step ? fd_step[1] : 0.0, h2 = fd_step ? fd_step[2] : 0.0;
+    if (fd_step && (h0 == 0.0 || h1 == 0.0 || h2 == 0.0)) return stb_internal_fail(STB_ERR_ARG, "stb_gauss_fit_sums: zero finite-difference step");
+    gauss_sums_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, y, n, amp, xc, sigma, h0, h1, h2, out);
     stb_internal_count_launch();
     e = cudaGetLastError();
     return e == cudaSuccess ? STB_OK : cfail("stb_gauss_fit_sums", e);
