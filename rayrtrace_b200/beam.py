@@ -653,11 +653,14 @@ def _gauss_fit_device(x, y, p0, stream):
     scipy.optimize.curve_fit (beam.py:463-465) -- with the data on the GPU: MINPACK's lmdif restated over
     reductions (``lmfit.lmdif3``; one ``stb_gauss_fit_sums`` launch per trial point, forward-difference
     Jacobian with MINPACK's steps, the 3 x 3 algebra on the host), so that it stops where curve_fit stops
-    even on the flat cost surfaces of folded beams.  None when lmdif reports failure (curve_fit raises)."""
+    even on the flat cost surfaces of folded beams.  Beams of fewer than 8192 rays, and fits whose Jacobian
+    is nearly rank deficient (few rays inside the Gaussian: the normal equations lose what MINPACK's pivoted
+    QR keeps), go through SciPy's curve_fit on a host copy -- the reference's own call.  None when the fit
+    fails (curve_fit raises)."""
     import ctypes
     import torch
     from . import _cabi
-    from .lmfit import lmdif3
+    from .lmfit import ILL_CONDITIONED, lmdif3
     n = int(x.shape[0])
     out = torch.empty(10, dtype=torch.float64, device=x.device)
 
@@ -669,8 +672,21 @@ def _gauss_fit_device(x, y, p0, stream):
         A = np.array([[s[0], s[1], s[2]], [s[1], s[3], s[4]], [s[2], s[4], s[5]]])
         return A, s[6:9].copy(), float(s[9])
 
-    p, info = lmdif3(sums, p0)
-    return p if info in (1, 2, 3, 4) and np.all(np.isfinite(p)) else None
+    if n > _FIT_ON_HOST_BELOW:
+        p, info = lmdif3(sums, p0)
+        if info != ILL_CONDITIONED:
+            return p if info in (1, 2, 3, 4) and np.all(np.isfinite(p)) else None
+    # a small beam, or one with too few rays inside the fitted Gaussian for the normal equations: the
+    # reference's own routine on a host copy of (x, |field|) -- O(n) bytes once, no device work involved
+    try:
+        p, _ = curve_fit(lambda xa, amp, xc, sigma: amp * np.exp(-(xa - xc) ** 2 / 2 / sigma ** 2),
+                         x.cpu().numpy(), y.cpu().numpy(), p0)
+        return p
+    except Exception:
+        return None
+
+
+_FIT_ON_HOST_BELOW = 8192     # rays: below this the D2H copy + MINPACK cost less than the reduction launches
 
 
 def _cubic_at(x, ph, xt, halfwidth=128):

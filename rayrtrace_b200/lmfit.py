@@ -92,9 +92,25 @@ def _lmpar(A, g, diag, delta, par):
     return par, x
 
 
+ILL_CONDITIONED = -1
+
+
+def _well_conditioned(A, rcond=1e-9):
+    """The normal equations lose what MINPACK's pivoted QR keeps once the Jacobian's columns are nearly
+    dependent (few rays inside the fitted Gaussian): the smallest eigenvalue of the column-scaled
+    J^T J must stand clear of its rounding noise."""
+    d = np.sqrt(np.maximum(np.diag(A), 0.0))
+    if np.any(d == 0) or not np.all(np.isfinite(A)):
+        return False
+    w = np.linalg.eigvalsh(A / np.outer(d, d))
+    return w[0] > rcond * w[-1]
+
+
 def lmdif3(sums, p0, ftol=1.49012e-8, xtol=1.49012e-8, gtol=0.0, maxfev=None, factor=100.0):
     """``sums(p, h)`` -> (A = J^T J [n, n], g = J^T r [n], rr = r^T r) at parameters p with forward-difference
-    steps h.  Returns (p, info) with MINPACK's info codes (1-4: converged, 5: maxfev, ...)."""
+    steps h.  Returns (p, info) with MINPACK's info codes (1-4: converged, 5: maxfev, ...), or
+    ``ILL_CONDITIONED`` as soon as a Jacobian is too close to rank deficient for the normal equations --
+    the caller then runs the QR-based routine on the data itself."""
     x = np.array(p0, float)
     n = len(x)
     if maxfev is None:
@@ -109,6 +125,8 @@ def lmdif3(sums, p0, ftol=1.49012e-8, xtol=1.49012e-8, gtol=0.0, maxfev=None, fa
     delta = xnorm = 0.0
     info = 0
     while True:
+        if not _well_conditioned(A):
+            return x, ILL_CONDITIONED
         acnorm = np.sqrt(np.maximum(np.diag(A), 0.0))
         if it == 1:
             diag = np.where(acnorm == 0, 1.0, acnorm)
