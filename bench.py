@@ -18,6 +18,8 @@ The same line carries, measured in the same invocation:
             (rayrtrace_b200.dist.trace_sharded): the sharded path WITH its exchange, max over ranks;
   endpoint_mode   the O(rays)-output mode of config 3 against the measured FP64 peak;
   exact_arena     config 3 through the two-pass exactly-sized trajectory arena (trace_exact);
+  app             the reference's top-level driver shape (ft2.phases, ft2.py:25-71) end to end, wall clock:
+                  3 density scales x 7 antenna pairs x 251 rays, and one 7 x 10^6-ray antenna scan;
   parity_check    a >= 10^4-ray subsample of the timed kernel's trajectories, bit for bit against the oracle
                   (untimed; the oracle is the checker, never the thing measured).
 
@@ -61,6 +63,7 @@ def parse_args():
     ap.add_argument("--no-config5", action="store_true", help="skip the sharded config-5 block")
     ap.add_argument("--config5-rays", type=int, default=12_500_000, help="config-5 rays per GPU (10^8 / 8)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed trajectory digest against the oracle")
+    ap.add_argument("--no-app", action="store_true", help="skip the application-level (ft2.phases) block")
     ap.add_argument("--layout", default="tiled", choices=["tiled", "ray"],
                     help="trajectory layout: tiled [tile][step][32][4] (default) or ray-major [ray][step][4]")
     return ap.parse_args()
@@ -289,6 +292,33 @@ def parity_digest(case, traj, nsteps_dev, tiled, sample=10_240):
     ok = bad == 0 and h_gpu.hexdigest() == h_cpu.hexdigest()
     return {"result": "ok" if ok else "MISMATCH", "rays": int(len(sel)), "states": int((ns_gpu.astype(np.int64) + 1).sum()),
             "sha256": h_gpu.hexdigest()[:16], "against": "oracle.trace_batch (CPU restatement of sidtracemodule.c:36-48), untimed"}
+
+
+def run_app(_cabi):
+    """ft2.phases (ft2.py:25-71) end to end on one GPU: Nfield per density scale, seven TX beams (wavefront,
+    launch conditions, launch states), trace with fused receiver crossing, equal-phase lookup launch, ray-tube
+    field, overlap with the RX pattern, Gaussian fit, interferometer phases.  Wall clock of the whole call."""
+    import torch
+    from rayrtrace_b200 import ft2, synth
+    n, x, y = synth.shaped_density(201, shift=0.0, elon=1.0)
+    ft2.phases(n, x, y, a_set=[0.5], nray=251)                      # warm-up: allocator, library, SciPy imports
+    out = {}
+    for key, a_set, nray, reps in (("phases_3x7x251", np.linspace(0.2, 1.0, 3), 251, 3), ("scan_7x1e6", [1.0], 1_000_003, 2)):
+        best, launches = None, 0
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            l0 = _cabi.launch_count()
+            t0 = time.perf_counter()
+            ph_max, ph_sig = ft2.phases(n, x, y, a_set=a_set, nray=nray)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            launches = _cabi.launch_count() - l0
+            best = dt if best is None else min(best, dt)
+        out[key] = {"wall_s": best, "beams": 7 * len(a_set), "rays_per_beam": nray, "library_launches": int(launches),
+                    "ph_sig_first": [round(float(v), 6) for v in ph_sig[-1, :3]]}
+    out["note"] = ("rayrtrace_b200.ft2.phases on a 201^2 FT-2 profile, best wall time of a few calls; every O(rays) "
+                   "array stays on the GPU (receiver_field_device / field_result_device)")
+    return out
 
 
 def run_config5(args, rank, world, local_rank, dev, comm):
@@ -577,6 +607,11 @@ def run_b200(args):
                                  "note": "extension beyond the reference (SURVEY 8 f-4); not parity, not the headline"}
         med.close()
 
+    # ---- application level (rank 0): the reference's driver shape, wall clock --------------------------
+    app = None
+    if rank == 0 and not args.no_app:
+        app = run_app(_cabi)
+
     # ---- BASELINE config 5: the sharded path with its exchange, every rank ---------------------------
     field.close()
     del d_in
@@ -623,6 +658,7 @@ def run_b200(args):
         "endpoint_mode": endpoint,
         "exact_arena": exact,
         "config5": config5,
+        "app": app,
     }
     if traj_host:
         line["e2e_traj_to_host"] = traj_host
