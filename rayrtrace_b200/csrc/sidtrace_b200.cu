@@ -437,7 +437,7 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     if (b->hist && !(b->r_lcs > 0 && b->rho_max > 0))
         return fail(STB_ERR_ARG, "stb_trace_batch: r_lcs and rho_max must be > 0 for the histogram");
     p.field = f->cells;
-    p.nxm1 = f->nx - 1; p.nym1 = f->ny - 1;
+    p.nxm1 = f->nx - 1; p.nym1 = f->ny - 1; p.ncell = (f->nx - 1) * (f->ny - 1);
     p.fx = (double)(f->nx - 1); p.fy = (double)(f->ny - 1);
     p.nrays = b->nrays; p.L = (int)b->L;
     p.x0 = b->x0; p.y0 = b->y0; p.kx0 = b->kx0; p.ky0 = b->ky0;

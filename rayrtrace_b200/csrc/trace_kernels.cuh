@@ -52,7 +52,7 @@ struct KParams {
     const double2 *field;   // {ax, ay} per cell, row stride nxm1
     const double4 *field4;  // HOIST: {RN(RN(sst*ax)/2), RN(RN(sst*ay)/2), RN(st*ax), RN(st*ay)} per cell for the
                             // launch's global step (built once per (field, st) by hoist_kernel)
-    int nxm1, nym1;
+    int nxm1, nym1, ncell;
     double fx, fy;                       // (double)(nx-1), (double)(ny-1)
     long long nrays;
     int L;
@@ -654,6 +654,9 @@ trace_kernel(const KParams p)
             ++i;
             return false;
         }
+        // (An L1 prefetch of the cell 1-3 steps further along the last cell-to-cell displacement was measured
+        // for the O(rays)-output modes, whose top stall is the wait for the gather: 13-18 % SLOWER,
+        // profiles/r02/prefetch_dropped.txt.)
         x = x1; y = y1; kx = kx1; ky = ky1; ind = ind1;
         ++i;
         return true;
