@@ -91,6 +91,12 @@ int stb_check(int nx, int ny, int i, int j, const double *a, double *out);
                                          cell-only products of sidtracemodule.c:41-45 (32 B per cell, built once
                                          and cached on the field; bit-identical results, 14 instead of 20 FP64
                                          instructions per step); tables over 64 MB (STB_HOIST_MAX_MB) are not built */
+#define STB_F_YMAJOR       (1u << 7)  /* gather from the y-major copy of the cells (cell (iy, ix) at ix*(ny-1) + iy; built
+                                         on first use and cached on the field, like the hoisted tables).  The reference's
+                                         a[iy*(nx-1) + ix] (sidtracemodule.c:38) puts the next cell of a ray that climbs in y
+                                         one whole row further on -- a new 128-byte line every step; in the y-major copy
+                                         it is the neighbouring 16/32 bytes.  Same cells, same bits; set it when the rays
+                                         of the launch travel mostly along y (the FT-2 antennas shoot upwards) */
 #define STB_F_TRAJ_HOST    (1u << 3)  /* traj is a HOST pointer (copied back after the launch) */
 #define STB_F_TRAJ_TILED   (1u << 4)  /* warp-tile schedule: a warp owns 32 consecutive rays until all of them
                                          ended.  traj (if any) is laid out [ray/T][step][ray%T][4] (T =

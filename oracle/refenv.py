@@ -77,15 +77,19 @@ def _find_contours(arr, level):
     return [pts]
 
 
-def install():
+def install(root=None, sidtrace_module=None):
+    """`root`: where the unmodified reference sources lie (default /root/reference).
+    `sidtrace_module`: what ``import sidtrace`` resolves to for the reference's ray.py:4 -- by default the
+    compiled reference extension; tests/test_dropin_reference.py passes the B200 drop-in instead."""
     global _installed
     if _installed:
         return
+    root = root or REFERENCE_ROOT
     import scipy.interpolate as si
     if not hasattr(si, "_orig_interp2d"):
         si._orig_interp2d = getattr(si, "interp2d", None)
         si.interp2d = _Interp2dShim
-    sys.modules["sidtrace"] = ref()
+    sys.modules["sidtrace"] = sidtrace_module if sidtrace_module is not None else ref()
     if "skimage" not in sys.modules:
         sk = types.ModuleType("skimage")
         me = types.ModuleType("skimage.measure")
@@ -97,8 +101,8 @@ def install():
         uf = types.ModuleType("ufile")
         uf.Ufile = type("Ufile", (), {})
         sys.modules["ufile"] = uf
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     _installed = True
 
 

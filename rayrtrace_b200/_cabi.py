@@ -24,6 +24,7 @@ F_TRAJ_HOST = 1 << 3
 F_TRAJ_TILED = 1 << 4
 F_STATIC = 1 << 5
 F_NO_HOIST = 1 << 6
+F_YMAJOR = 1 << 7
 
 # every symbol include/sidtrace_b200.h declares (tests check the .so exports them all)
 EXPORTS = (

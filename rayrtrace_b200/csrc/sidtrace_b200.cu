@@ -79,7 +79,8 @@ struct HostBuf {   // pinned
 // One hoisted table (trace_kernels.cuh, HOIST) per global step value the field has been traced with.
 struct HoistEntry {
     uint64_t st_bits = 0;
-    double4 *tab = nullptr;
+    bool ymajor = false;                  // layout of the table = layout of the cells it was built from
+    double4 *tab = nullptr, *tab_alloc = nullptr;
     cudaEvent_t ready = nullptr;          // recorded on the building stream after hoist_kernel
     uint64_t last_use = 0;
 };
@@ -88,7 +89,11 @@ constexpr int kHoistSlots = 4;
 struct stb_field_s {
     int device = 0;
     int nx = 0, ny = 0;
-    double2 *cells = nullptr;             // interleaved {ax, ay}, (ny-1)*(nx-1)
+    double2 *cells = nullptr;             // interleaved {ax, ay}, (ny-1)*(nx-1), x-major (the reference's layout)
+    double2 *cells_alloc = nullptr;       // its allocation (padded)
+    double2 *cells_y = nullptr;           // the y-major copy, built on first use (STB_F_YMAJOR)
+    double2 *cells_y_alloc = nullptr;
+    cudaEvent_t cells_y_ready = nullptr;
     unsigned long long *counter = nullptr;   // kCounters queue heads, used round-robin; a slot is handed out
                                              // again only after the launch that used it last has finished
                                              // (counter_ev), so launches in flight never share one
@@ -152,7 +157,9 @@ int stb_field_create(const double *ax, const double *ay, int nx, int ny, int on_
     const double *dax = ax, *day = ay;
     int rc = STB_OK;
     do {
-        if ((e = cudaMalloc(&f->cells, 2 * bytes)) != cudaSuccess) break;
+        // every cell table carries kTablePadCells cells of padding on either side (prefetch_neighbours)
+        if ((e = cudaMalloc(&f->cells_alloc, 2 * bytes + 2 * stb::kTablePadCells * sizeof(double2))) != cudaSuccess) break;
+        f->cells = f->cells_alloc + stb::kTablePadCells;
         if ((e = cudaMalloc(&f->counter, kCounters * sizeof(unsigned long long))) != cudaSuccess) break;
         if (!on_device) {
             if ((e = cudaMalloc(&tmp, 2 * bytes)) != cudaSuccess) break;
@@ -172,7 +179,7 @@ int stb_field_create(const double *ax, const double *ay, int nx, int ny, int on_
     if (e != cudaSuccess) {
         rc = fail(e == cudaErrorMemoryAllocation ? STB_ERR_NOMEM : STB_ERR_CUDA,
                   "stb_field_create: %s", cudaGetErrorString(e));
-        if (f->cells) cudaFree(f->cells);
+        if (f->cells_alloc) cudaFree(f->cells_alloc);
         if (f->counter) cudaFree(f->counter);
         delete f;
         return rc;
@@ -184,10 +191,12 @@ int stb_field_create(const double *ax, const double *ay, int nx, int ny, int on_
 int stb_field_destroy(stb_field_t f)
 {
     if (!f) return STB_OK;
-    cudaFree(f->cells);
+    cudaFree(f->cells_alloc);
+    if (f->cells_y_alloc) cudaFree(f->cells_y_alloc);
+    if (f->cells_y_ready) cudaEventDestroy(f->cells_y_ready);
     cudaFree(f->counter);
     for (auto &h : f->hoist) {
-        if (h.tab) cudaFree(h.tab);
+        if (h.tab_alloc) cudaFree(h.tab_alloc);
         if (h.ready) cudaEventDestroy(h.ready);
     }
     for (auto &e : f->counter_ev) if (e) cudaEventDestroy(e);
@@ -316,28 +325,52 @@ int launch_cross(const KParams &p, bool divc, const LaunchCtx &c)
 
 // Table of the cell-only products for the launch's global step: built once per (field, st) on the
 // launching stream, kept in a small LRU cache on the field.  Caller holds f->mu.
-int ensure_hoist(stb_field_s *f, double st, cudaStream_t s, const double4 **out)
+// The y-major copy of the cells, built once on the launching stream.  Caller holds f->mu.
+int ensure_cells_y(stb_field_s *f, cudaStream_t s, const double2 **out)
+{
+    if (!f->cells_y) {
+        const long long ncell = (long long)(f->nx - 1) * (long long)(f->ny - 1);
+        CU(cudaMalloc(&f->cells_y_alloc, ((size_t)ncell + 2 * stb::kTablePadCells) * sizeof(double2)));
+        f->cells_y = f->cells_y_alloc + stb::kTablePadCells;
+        CU(cudaEventCreateWithFlags(&f->cells_y_ready, cudaEventDisableTiming));
+        const dim3 grid((f->nx - 1 + 31) / 32, (f->ny - 1 + 31) / 32), block(32, 8);
+        stb::transpose_cells_kernel<double2><<<grid, block, 0, s>>>(f->cells, f->cells_y, f->nx - 1, f->ny - 1);
+        g_launches++;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(f->cells_y_ready, s));
+    } else {
+        CU(cudaStreamWaitEvent(s, f->cells_y_ready, 0));
+    }
+    *out = f->cells_y;
+    return STB_OK;
+}
+
+int ensure_hoist(stb_field_s *f, double st, bool ymajor, const double2 *cells, cudaStream_t s, const double4 **out)
 {
     uint64_t bits;
     memcpy(&bits, &st, sizeof(bits));
     HoistEntry *e = nullptr, *victim = nullptr;
     for (auto &h : f->hoist) {
-        if (h.tab && h.st_bits == bits) { e = &h; break; }
+        if (h.tab && h.st_bits == bits && h.ymajor == ymajor) { e = &h; break; }
         if (!victim || (victim->tab && (!h.tab || h.last_use < victim->last_use))) victim = &h;
     }
     if (!e) {
         e = victim;
         const long long ncell = (long long)(f->nx - 1) * (long long)(f->ny - 1);
         if (e->tab) CU(cudaDeviceSynchronize());        // kernels that still read the evicted table
-        else CU(cudaMalloc(&e->tab, (size_t)ncell * sizeof(double4)));
+        else {
+            CU(cudaMalloc(&e->tab_alloc, ((size_t)ncell + 2 * stb::kTablePadCells) * sizeof(double4)));
+            e->tab = e->tab_alloc + stb::kTablePadCells;
+        }
         if (!e->ready) CU(cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming));
         long long blocks = (ncell + 255) / 256;
         if (blocks > (long long)f->num_sms * 16) blocks = (long long)f->num_sms * 16;
-        stb::hoist_kernel<<<(unsigned)blocks, 256, 0, s>>>(f->cells, st, st * st, e->tab, ncell);
+        stb::hoist_kernel<<<(unsigned)blocks, 256, 0, s>>>(cells, st, st * st, e->tab, ncell);
         g_launches++;
         CU(cudaGetLastError());
         CU(cudaEventRecord(e->ready, s));
         e->st_bits = bits;
+        e->ymajor = ymajor;
     } else {
         CU(cudaStreamWaitEvent(s, e->ready, 0));         // built on another stream, perhaps
     }
@@ -346,17 +379,22 @@ int ensure_hoist(stb_field_s *f, double st, cudaStream_t s, const double4 **out)
     return STB_OK;
 }
 
-int launch_trace(stb_field_s *f, KParams &p, bool divc, bool refill, bool tiled, bool hoist, cudaStream_t s)
+int launch_trace(stb_field_s *f, KParams &p, bool divc, bool refill, bool tiled, bool hoist, bool ymajor, cudaStream_t s)
 {
     const LaunchCtx c{f, refill, s};
     p.field4 = nullptr;
+    if (ymajor && p.nrays > 0) {
+        int rc = ensure_cells_y(f, s, &p.field);
+        if (rc != STB_OK) return rc;
+        p.csx = p.nym1; p.csy = 1;
+    }
     // plain trajectory launches are bound by HBM stores, not by FP64 issue: the 32-byte hoisted cells only
     // add L2 traffic there (6770 vs 6810 GB/s, profiles/r02/l2_policy_sweep.txt) -- they keep the 16-byte cells
     const bool lean_traj = p.traj && !p.hist && !p.cross_axis && !(p.turn || p.turn_state || p.lax_end || p.ph_end);
     if (hoist && !lean_traj && !p.st_ray && p.nrays > 0) {
         const size_t bytes = (size_t)(f->nx - 1) * (size_t)(f->ny - 1) * sizeof(double4);
         if (bytes <= f->hoist_max_bytes) {
-            int rc = ensure_hoist(f, p.st, s, &p.field4);
+            int rc = ensure_hoist(f, p.st, ymajor && p.nrays > 0, p.field, s, &p.field4);
             if (rc != STB_OK) return rc;
         }
     }
@@ -438,8 +476,9 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
         return fail(STB_ERR_ARG, "stb_trace_batch: r_lcs and rho_max must be > 0 for the histogram");
     p.field = f->cells;
     p.nxm1 = f->nx - 1; p.nym1 = f->ny - 1; p.ncell = (f->nx - 1) * (f->ny - 1);
+    p.csx = 1; p.csy = f->nx - 1;
     p.fx = (double)(f->nx - 1); p.fy = (double)(f->ny - 1);
-    p.nrays = b->nrays; p.L = (int)b->L;
+    p.nrays = b->nrays; p.L = (int)b->L; p.Lm1 = p.L - 1;
     p.x0 = b->x0; p.y0 = b->y0; p.kx0 = b->kx0; p.ky0 = b->ky0;
     p.st = b->st; p.sst = b->st * b->st; p.st_ray = b->st_ray;
     p.dx = b->dx; p.dy = b->dy; p.rdx = 1.0 / b->dx; p.rdy = 1.0 / b->dy;
@@ -515,7 +554,8 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
     if (rc != STB_OK) return rc;
 
     const bool hoist = !(b->flags & STB_F_NO_HOIST);
-    if (!host_io && !traj_host) return launch_trace(f, p, divc, refill, tiled, hoist, s);
+    const bool ymajor = b->flags & STB_F_YMAJOR;
+    if (!host_io && !traj_host) return launch_trace(f, p, divc, refill, tiled, hoist, ymajor, s);
 
     const size_t n = (size_t)b->nrays;
     const size_t nb = n * sizeof(double);
@@ -546,7 +586,7 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
             p.cross_count = (int *)dp[13]; p.cross_index = (int *)dp[14]; p.cross_flags = (int *)dp[15];
             p.cross_state = (double *)dp[16];
             p.turn_state = (double *)dp[17];
-            rc = launch_trace(f, p, divc, refill, tiled, hoist, s);
+            rc = launch_trace(f, p, divc, refill, tiled, hoist, ymajor, s);
             if (rc != STB_OK) return rc;
             CU(cudaStreamSynchronize(s));
             return STB_OK;
@@ -606,7 +646,7 @@ int stb_trace_batch(stb_field_t f, const stb_batch_t *b, void *stream)
         p.traj = (double *)f->ws_traj.p;
     }
 
-    rc = launch_trace(f, p, divc, refill, tiled, hoist, s);
+    rc = launch_trace(f, p, divc, refill, tiled, hoist, ymajor, s);
     if (rc != STB_OK) return rc;
 
     if (host_io && n) {
@@ -666,7 +706,7 @@ int stb_trace(stb_field_t f, double *x, double *y, double *kx, double *ky, int64
     bool divc = false;
     rc = fill_params(f, &b, p, divc);
     if (rc != STB_OK) return rc;
-    rc = launch_trace(f, p, divc, /*refill=*/false, /*tiled=*/false, /*hoist=*/false, 0);
+    rc = launch_trace(f, p, divc, /*refill=*/false, /*tiled=*/false, /*hoist=*/false, /*ymajor=*/false, 0);
     if (rc != STB_OK) return rc;
     CU(cudaStreamSynchronize(0));
     const int32_t n = *hn;

@@ -49,10 +49,15 @@ constexpr int kBlock = 128;   // threads per CTA (4 warps); the tiled trajectory
                               // 16 -> 32 registers spills and loses 20 %, profiles/r01/occupancy_layout_sweep.txt)
 
 struct KParams {
-    const double2 *field;   // {ax, ay} per cell, row stride nxm1
+    const double2 *field;   // {ax, ay} per cell; cell (iy, ix) sits at iy*csy + ix*csx
     const double4 *field4;  // HOIST: {RN(RN(sst*ax)/2), RN(RN(sst*ay)/2), RN(st*ax), RN(st*ay)} per cell for the
                             // launch's global step (built once per (field, st) by hoist_kernel)
     int nxm1, nym1, ncell;
+    int csx, csy;                        // cell strides: (1, nxm1) = x-major rows, the reference's a[iy*(nx-1) + ix]
+                                         // (sidtracemodule.c:38); (nym1, 1) = the y-major copy (STB_F_YMAJOR): a
+                                         // ray that travels along y then finds its next cells in the SAME 128-byte
+                                         // line instead of one row (nxm1 cells) further on
+    int Lm1;                             // L - 1: the guard compares the state index against it (constant-bank operand)
     double fx, fy;                       // (double)(nx-1), (double)(ny-1)
     long long nrays;
     int L;
@@ -128,6 +133,22 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_first()
     asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+
+// What bounds the kernels WITHOUT trajectory output is the dependent chain of one ray-step, not the FP64 pipe
+// and not instruction issue.  Measured on B200 (tools/probe/latency_probe.cu, profiles/r02/latency_probe.txt,
+// occupancy_curve_endpoints.txt): FP64 operations 8.3 cycles, F2I.F64 ~19, a warp-uniform 32-byte gather 60-70
+// cycles from L1 and 300+ from L2, one ray-step of one warp 437 cycles in isolation and ~570 in the kernel;
+// the kernel's run time does not move between 1 and 8 warps per scheduler and reaches 5.3-6.3e11 ray-steps/s
+// at the 12 the 40-register cap allows (ncu: half of all stall samples sit on the first use of the gathered
+// cell).  A ray enters a new cell -- a new 32-byte sector, whatever the layout -- almost every step, and the
+// four warps of a CTA ride the same cells in convoy, so each of them waits for the same L2 fill.
+// Tried against that, measured, dropped (profiles/r02/prefetch_dropped.txt): `prefetch.global.L1` of the
+// neighbouring cells (CCTL.E.PF1 leaves the probe's chain at 438 cycles: no effect, 2 % slower in the
+// kernel); real 4-byte "touch" loads of the cells 2 ahead and behind along the fast axis of the y-major
+// table (the probe's chain drops to 289 cycles and the kernel's demand-gather stall samples fall 4x, but the
+// two extra LSU instructions per step cost more than they save at full occupancy: 1.28 -> 1.40 ms, and
+// 1.9x slower on rays in random order, where every lane touches a sector of its own).
+constexpr int kTablePadCells = 8;   // cells of padding on either side of every cell table (room for such experiments)
 
 // one 32-byte cell of the hoisted table = one LDG.E.ENL2.256.CONSTANT
 template <bool KEEP>
@@ -324,7 +345,7 @@ trace_kernel(const KParams p)
 
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    int Lm1 = p.L - 1;
+    int Lm1 = p.Lm1;
 
     // per-ray state: state i of the current ray.  Inside the stepping loop state i is always a KEPT state
     // (it passed the guard of sidtracemodule.c:36; ray.py:99-102 keeps [:n]).
@@ -371,7 +392,7 @@ trace_kernel(const KParams p)
     // -0.0 (which compares >= 0 in the reference) is admitted explicitly.  Returns the cell (:38).
     auto guard = [&](double xs, double ys, int j, int &cell) -> bool {
         const int ix = __double2int_rz(xs), iy = __double2int_rz(ys);
-        cell = iy * p.nxm1 + ix;
+        cell = iy * p.csy + ix * p.csx;
         return (j < Lm1) & in_range(xs, ix, p.nxm1) & in_range(ys, iy, p.nym1);
     };
 
@@ -662,6 +683,60 @@ trace_kernel(const KParams p)
         return true;
     };
 
+    // LEAN variants (step counts / end states only: nothing is written per step): the common case of a
+    // step -- both dividends in div_pair's guarded exponent range, the new state +finite and inside the
+    // grid, below the index limit -- runs in a loop of its own.  It leaves the loop in two ways:
+    //   0  a dividend outside the guarded range, seen BEFORE anything is committed: registers still hold the
+    //      kept state i, the general step() takes it from there;
+    //   the new state failed the quick guard (one unsigned compare of the high word per coordinate, which
+    //   also turns away -0.0, next to the cell-range compare) AFTER it was committed: registers hold state
+    //   i (already counted); the exact guard decides between
+    //   1  the ray has ended (registers = state n, sidtracemodule.c:50) and
+    //   2  the state is kept after all (-0.0, or only the caller's index limit was reached).
+    // Same operations on the same operands as step(): the results cannot differ.  One ray-step is
+    // 39 instead of 43 SASS instructions (+3 % in endpoint mode on the static grid; the persistent schedules keep
+    // the plain step() loop).
+    constexpr bool LEAN = !TRAJ && !EXTRAS && !HIST && !CROSS && !STRAY && !REFILL;
+    auto fast_run = [&](int ilim) -> int {
+        if (!LEAN) return 0;
+#pragma unroll 1
+        for (;;) {
+            double tx, ty, sx, sy;
+            if (HOIST) {
+                const double4 h = ld_cell4<false>(&p.field4[ind]);
+                tx = h.x; ty = h.y; sx = h.z; sy = h.w;
+            } else {
+                const double2 m = ld_cell2<false>(&p.field[ind]);
+                tx = __dmul_rn(__dmul_rn(p.sst, m.x), 0.5); ty = __dmul_rn(__dmul_rn(p.sst, m.y), 0.5);
+                sx = __dmul_rn(p.st, m.x); sy = __dmul_rn(p.st, m.y);
+            }
+            const double vx = __dadd_rn(tx, __dmul_rn(kx, p.st));
+            const double vy = __dadd_rn(ty, __dmul_rn(ky, p.st));
+            double wx, wy;
+            if (DIVC) {
+                const unsigned ex = ((unsigned)__double2hiint(vx) & 0x7ff00000u) - (623u << 20);
+                const unsigned ey = ((unsigned)__double2hiint(vy) & 0x7ff00000u) - (623u << 20);
+                if (max(ex, ey) > (800u << 20)) return 0;
+                const double qx = __dmul_rn(vx, p.rdx), qy = __dmul_rn(vy, p.rdy);
+                const double rx = __fma_rn(-qx, p.dx, vx), ry = __fma_rn(-qy, p.dy, vy);
+                wx = __fma_rn(rx, p.rdx, qx);
+                wy = __fma_rn(ry, p.rdy, qy);
+            } else {
+                wx = __ddiv_rn(vx, p.dx);
+                wy = __ddiv_rn(vy, p.dy);
+            }
+            x = __dadd_rn(x, wx); y = __dadd_rn(y, wy);
+            kx = __dadd_rn(kx, sx); ky = __dadd_rn(ky, sy);
+            ++i;
+            const int ix = __double2int_rz(x), iy = __double2int_rz(y);
+            ind = iy * p.csy + ix * p.csx;
+            const bool okx = ((unsigned)__double2hiint(x) < 0x7ff00000u) & ((unsigned)ix < (unsigned)p.nxm1);
+            const bool oky = ((unsigned)__double2hiint(y) < 0x7ff00000u) & ((unsigned)iy < (unsigned)p.nym1);
+            if (!(okx & oky & (i < ilim))) break;
+        }
+        return guard(x, y, i, ind) ? 2 : 1;
+    };
+
     if (TILED || !REFILL) {
         // ---- whole-ray schedules: claim, trace to the end in a plain per-thread loop, retire.
         // No vote per step: lanes that finish early wait at the reconvergence point after the
@@ -680,7 +755,14 @@ trace_kernel(const KParams p)
             if (packed) r = slot < p.nslots ? (long long)p.perm[slot] : -1;
             const bool has = r >= 0 && r < p.nrays;
             if (has && launch(r, slot)) {
-                while (step()) { }
+                if (LEAN) {
+                    for (;;) {
+                        const int why = fast_run(Lm1);
+                        if (why == 1 || (why == 0 && !step())) break;
+                    }
+                } else {
+                    while (step()) { }
+                }
             }
             if (TILED) __syncwarp();
             if (has) retire();
@@ -726,6 +808,8 @@ trace_kernel(const KParams p)
                 continue;                                   // every claimed ray ended at launch: claim again
             }
             if (active) {
+                // (the LEAN loop with a per-batch index limit was measured here too: 10 % slower than plain
+                // step() calls, profiles/r02/lean_sweep_config3.txt)
 #pragma unroll 1
                 for (int s = 0; s < kBatch; ++s) {
                     if (!step()) { retire(); active = false; break; }
@@ -740,6 +824,23 @@ trace_kernel(const KParams p)
             const double v = sh_hist[b];
             if (v != 0.0) atomicAdd(&p.hist[b], v);
         }
+    }
+}
+
+// x-major cells -> y-major copy (out[ix*nym1 + iy] = in[iy*nxm1 + ix]); 32x32 tiles through shared memory
+template <typename T>
+__global__ void transpose_cells_kernel(const T *__restrict__ in, T *__restrict__ out, int nxm1, int nym1)
+{
+    __shared__ T tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int ix = bx + threadIdx.x, iy = by + j;
+        if (ix < nxm1 && iy < nym1) tile[j][threadIdx.x] = in[(long long)iy * nxm1 + ix];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int ix = bx + j, iy = by + threadIdx.x;
+        if (ix < nxm1 && iy < nym1) out[(long long)ix * nym1 + iy] = tile[threadIdx.x][j];
     }
 }
 

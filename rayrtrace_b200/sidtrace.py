@@ -27,9 +27,9 @@ from typing import Optional
 import numpy as np
 
 from . import _cabi
-from ._cabi import (F_DIV_IEEE, F_HOST_IO, F_NO_HOIST, F_REFILL, F_STATIC, F_TRAJ_HOST, F_TRAJ_TILED, SidtraceError, StbBatch, lib)
+from ._cabi import (F_DIV_IEEE, F_HOST_IO, F_NO_HOIST, F_REFILL, F_STATIC, F_TRAJ_HOST, F_TRAJ_TILED, F_YMAJOR, SidtraceError, StbBatch, lib)
 
-__all__ = ["trace", "check", "trace_batch", "trace_exact", "plan_trajectories", "TrajPlan", "Field", "BatchResult",
+__all__ = ["trace", "check", "trace_batch", "pick_cells", "trace_exact", "plan_trajectories", "TrajPlan", "Field", "BatchResult",
            "invalidate", "pinned_empty", "pinned_copy", "SidtraceError"]
 
 
@@ -348,14 +348,34 @@ def _ptr(a):
     return a.ctypes.data
 
 
+def pick_cells(kx0, ky0, sample: int = 4096) -> str:
+    """Cell-table layout for a launch: "y" (y-major copy) when its rays travel mostly along y, else "x" --
+    judged on a strided sample of the launch wave vectors."""
+    n = int(kx0.shape[0])
+    if n == 0:
+        return "x"
+    step = max(1, n // sample)
+    if _is_tensor(kx0):
+        torch = _torch()
+        k = torch.stack([kx0[::step].abs().sum(), ky0[::step].abs().sum()]).cpu()
+        return "y" if float(k[1]) > float(k[0]) else "x"
+    return "y" if float(np.abs(ky0[::step]).sum()) > float(np.abs(kx0[::step]).sum()) else "x"
+
+
 def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float, dy: float,
                 st_ray=None, traj=None, want_end: bool = True, want_extras: bool = False,
                 hist=None, nbins: int = 0, amp=None, xorg: float = 0.0, yorg: float = 0.0,
                 r_lcs: float = 1.0, rho_max: float = 1.0, traj_host: bool = False,
                 div_ieee: bool = False, refill: Optional[bool] = None, tiled: bool = False, tile: int = 256,
                 cross=None, x0_phys=None, y0_phys=None, lookup_ph=None, hoist: bool = True,
-                plan: Optional[TrajPlan] = None, out: Optional[BatchResult] = None, stream=None) -> BatchResult:
+                plan: Optional[TrajPlan] = None, out: Optional[BatchResult] = None, stream=None,
+                cells: str = "x") -> BatchResult:
     """Trace ``len(x0)`` rays in one launch.
+
+    cells: "x" -> gather from the reference's x-major cell table (default), "y" -> from its y-major copy (same
+    cells, same results; a ray that climbs in y then finds its next cells in the same cache line), "auto" ->
+    picked from the launch directions: y-major when sum|ky0| > sum|kx0| over a strided sample of the launch
+    states (device I/O: one small device-to-host copy, i.e. a synchronisation).
 
     x0, y0, kx0, ky0: launch states (grid units / cm^-1, ray.py:62-68), all numpy
     float64 arrays (host I/O: results come back as numpy arrays; pass pinned
@@ -468,6 +488,12 @@ def trace_batch(field: Field, x0, y0, kx0, ky0, *, L: int, st: float, dx: float,
         flags |= F_REFILL if refill else F_STATIC
     if not hoist:
         flags |= F_NO_HOIST
+    if cells == "auto":
+        cells = pick_cells(kx0, ky0)
+    if cells not in ("x", "y"):
+        raise ValueError('cells must be "x", "y" or "auto"')
+    if cells == "y":
+        flags |= F_YMAJOR
 
     if plan is not None:
         if not dev_io:

@@ -1024,6 +1024,57 @@ def test_hoisted_table_equals_plain_cells(st, torch_mod, oracle_mod, mode, refil
     f.close()
 
 
+@pytest.mark.parametrize("mode", ["endpoints", "traj", "traj-tiled", "extras", "cross", "lookup", "hist"])
+@pytest.mark.parametrize("refill", [True, False])
+@pytest.mark.parametrize("hoist", [True, False])
+def test_ymajor_cells_equal_the_reference_layout(st, torch_mod, oracle_mod, mode, refill, hoist):
+    """cells="y" gathers from the y-major copy of the cell table (STB_F_YMAJOR: cell (iy, ix) at ix*(ny-1) + iy)
+    instead of the reference's a[iy*(nx-1) + ix] (sidtracemodule.c:38).  Same cells: every output is
+    bit-identical to the x-major launch and to the oracle, on a non-square grid, hoisted or not."""
+    rng = np.random.default_rng(77)
+    nx, ny, n, L = 97, 161, 3003, 500
+    ax, ay = random_field(rng, nx, ny, scale=0.02)
+    x0, y0, kx0, ky0 = random_launch(rng, n, nx, ny)
+    x0[0] = -1.0; y0[1] = np.nan; kx0[2] = 0.0; x0[3] = -0.0; y0[4] = -0.0
+    f = st.Field(ax, ay, nx, ny)
+    kw = dict(L=L, st=0.41, dx=0.9, dy=1.1, refill=refill, hoist=hoist)
+    xp, yp = x0 * 0.9 - 3.0, y0 * 1.1 + 2.0
+    if mode == "traj":
+        kw.update(traj=True)
+    elif mode == "traj-tiled":
+        kw.update(traj=True, tiled=True)
+    elif mode == "extras":
+        kw.update(want_extras=True)
+    elif mode in ("cross", "lookup"):
+        kw.update(cross=(70.0, "y"), x0_phys=xp, y0_phys=yp)
+        if mode == "lookup":
+            c0 = st.trace_batch(f, x0, y0, kx0, ky0, **kw)
+            ph = np.nan_to_num(c0.cross_state[5], nan=50.0)
+            kw.update(lookup_ph=np.ascontiguousarray(np.stack([0.6 * ph, 1.2 * ph + 1.0])))
+    elif mode == "hist":
+        kw.update(nbins=32, amp=rng.uniform(0.5, 1, n), xorg=-60.0, yorg=-70.0, r_lcs=50.0, rho_max=1.4)
+    a = st.trace_batch(f, x0, y0, kx0, ky0, cells="y", **kw)
+    b = st.trace_batch(f, x0, y0, kx0, ky0, cells="x", **kw)
+    torch_mod.cuda.synchronize()
+    want = oracle_mod.trace_batch(x0, y0, kx0, ky0, L, 0.41, 0.9, 1.1, nx, ny, ax, ay)
+    assert np.array_equal(a.nsteps, want["nsteps"]) and np.array_equal(b.nsteps, want["nsteps"])
+    assert a.end_state.tobytes() == want["end"].tobytes() == b.end_state.tobytes()
+    if mode.startswith("traj"):
+        assert a.traj_ray_major().cpu().numpy().tobytes() == want["traj"].tobytes()
+    for name in ("turn_index", "turn_state", "lax_end", "ph_end", "cross_count", "cross_index", "cross_flags", "cross_state",
+                 "lookup_xy"):
+        va, vb = getattr(a, name), getattr(b, name)
+        if va is not None:
+            assert np.asarray(va).tobytes() == np.asarray(vb).tobytes(), name
+    if mode == "hist":
+        assert np.abs(a.hist - b.hist).sum() <= 1e-12 * np.abs(b.hist).sum()
+    assert st.pick_cells(kx0, ky0) in ("x", "y")
+    up = np.abs(ky0) + 1.0
+    assert st.pick_cells(kx0 * 0.1, up) == "y" and st.pick_cells(up, ky0 * 0.1) == "x"
+    assert st.pick_cells(torch_mod.from_numpy(kx0 * 0.1).cuda(), torch_mod.from_numpy(up).cuda()) == "y"
+    f.close()
+
+
 def test_hoisted_tables_of_many_steps_share_one_field(st, torch_mod, oracle_mod):
     """The field keeps four hoisted tables (LRU): six step values traced round-robin, on two streams,
     evict and rebuild them; every launch matches the oracle."""

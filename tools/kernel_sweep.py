@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--case", default="beam", choices=["beam", "sweep", "trapped"])
     ap.add_argument("--only", default="", help="comma-separated substrings; a variant runs if any matches")
     ap.add_argument("--hoist", default="on", choices=["on", "off", "both"], help="hoisted per-cell products (default) or plain cells")
+    ap.add_argument("--cells", default="x", choices=["x", "y", "both"], help="cell-table layout: the reference's x-major rows, the y-major copy, or both")
     ap.add_argument("--L", type=int, default=0, help="states per ray (0 = the case's default cap)")
     ap.add_argument("--store-pattern", action="store_true", help="only run the store-pattern microbenchmark")
     args = ap.parse_args()
@@ -72,16 +73,17 @@ def main():
         for refill in (True, False):
             for div_ieee in (False, True):
                 for hoist in hoists:
-                    variants.append((mode, refill, div_ieee, hoist))
+                    for cells in {"x": ("x",), "y": ("y",), "both": ("x", "y")}[args.cells]:
+                        variants.append((mode, refill, div_ieee, hoist, cells))
     print(f"# case {case.name} L={L} peak={peak} GB/s lib={os.path.basename(sidtrace._cabi.LIB_PATH)}")
     first = True
     plan = None
-    for mode, refill, div_ieee, hoist in variants:
-        tag = f"{mode}/{'refill' if refill else 'static'}/{'ieee' if div_ieee else 'divc'}/{'hoist' if hoist else 'cells'}"
+    for mode, refill, div_ieee, hoist, cells in variants:
+        tag = f"{mode}/{'refill' if refill else 'static'}/{'ieee' if div_ieee else 'divc'}/{'hoist' if hoist else 'cells'}" + ("/ymajor" if cells == "y" else "")
         if args.only and not any(o in tag for o in args.only.split(",")):
             continue
         o = sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state)
-        k = dict(kw, refill=refill, div_ieee=div_ieee, hoist=hoist)
+        k = dict(kw, refill=refill, div_ieee=div_ieee, hoist=hoist, cells=cells)
         if mode in ("traj-exact", "traj-pass2"):
             # two-pass exactly-sized arena: the whole of trace_exact, or its second pass alone (plan given)
             if refill:
