@@ -10,8 +10,9 @@
  *
  * through an INTERPOLATED medium (cubic-spline, Catmull-Rom or bilinear n/n_c table -- the table the
  * reference differences in den.py:65-66 and splines for its launch index, den.py:71 -- with the cold-plasma O- or X-mode dispersion and its
- * analytic derivatives fused into the evaluation; the X mode's toroidal field B ~ 1/R uses the
- * rmain/btor of equilibrium.py:289), optical-depth integration of an absorption table, and the absorbed
+ * analytic derivatives fused into the evaluation; the X mode's field is the analytic toroidal B ~ 1/R with the
+ * rmain/btor of equilibrium.py:289, or |B| of a tabulated psi(R, Z) + F(psi) in the format of equilibrium.py:11-49),
+ * optical-depth integration of an absorption table, and the absorbed
  * power deposited into flux-coordinate bins.  There is no reference output to compare with: the
  * checker is oracle/rk_oracle.c (same operation order, bit-identical) pinned by analytic
  * solutions and an independent SciPy integration (tests/test_rk_*.py).
@@ -39,6 +40,9 @@ typedef struct stb_medium_s *stb_medium_t;
 
 #define STB_RK_MODE_O 0   /* N^2 = 1 - X                                   */
 #define STB_RK_MODE_X 1   /* N^2 = 1 - X(1-X)/(1-X-Y^2), Y = Y0 R0/(R0+x)  */
+#define STB_RK_MODE_X_TABLE 2   /* the same dispersion with Y^2 = (omega_ce/omega)^2 interpolated from a node table on
+                                   the medium's grid (like X): |B| of a TABULATED equilibrium -- given directly (Y2) or
+                                   built by the library on the device from psi(R, Z) and F(psi) (equilibrium) */
 
 /* per-ray end status */
 #define STB_RK_LEFT_DOMAIN    0   /* accepted state outside the table (the reference's loop exit, sidtracemodule.c:36) */
@@ -47,6 +51,27 @@ typedef struct stb_medium_s *stb_medium_t;
 #define STB_RK_STEP_UNDERFLOW 3   /* step shrank below hmin: resonance (N^2 -> inf) or NaN input */
 #define STB_RK_START_OUTSIDE  4
 #define STB_RK_STOP_LINE      5   /* landed on the stop line (receiver line, cf. Ray.addpoint, ray.py:131-224) */
+
+/* A tabulated axisymmetric equilibrium in the geqdsk-like form of the reference's Equilibrium class
+ * (equilibrium.py:11-49: psi on an nr x nz rectangle [rleft, rleft+rdim] x [zmid-zdim/2, zmid+zdim/2], R-major
+ * "so (x,y) axis order is in geqdsk format", interpolated BILINEARLY -- RectBivariateSpline(kx=1, ky=1),
+ * equilibrium.py:46-49 -- and fpol = R B_phi on a uniform psi grid from simagx to sibdry).  SI units (m, Wb/rad, T m).
+ * From it, at every node (x, y) of the medium's grid (R = (r0_cm + x)/100, Z = (y - z0_cm)/100):
+ *     B_R = -(1/R) dpsi/dZ,  B_Z = (1/R) dpsi/dR,  B_phi = F(psi)/R  (F held at fpol[nf-1] outside the last surface)
+ *     Y^2 = (y_per_tesla)^2 (B_R^2 + B_Z^2 + B_phi^2),   y_per_tesla = e/(m_e omega)
+ * No reference code evaluates B from this table (equilibrium.py is never called by the tracer); this is the
+ * north_star's "psi(R, Z), B components" for the extension's X mode. */
+typedef struct stb_equilibrium_s {
+    size_t struct_size;
+    int32_t nr, nz;
+    double rleft, rdim, zmid, zdim;   /* m */
+    const double *psi;                /* [nr][nz], HOST */
+    const double *fpol;               /* [nf], HOST */
+    int32_t nf;
+    double simagx, sibdry;
+    double r0_cm, z0_cm;              /* where the medium's (x, y) = (0, 0) sits: R = r0_cm, Z = -z0_cm ... see above */
+    double y_per_tesla;
+} stb_equilibrium_t;
 
 typedef struct stb_medium_desc_s {
     size_t struct_size;
@@ -59,11 +84,14 @@ typedef struct stb_medium_desc_s {
     int32_t mode;              /* STB_RK_MODE_*                                                     */
     int32_t interp;            /* STB_RK_INTERP_*                                                   */
     double Y0, R0;             /* X mode: omega_ce/omega on the axis x = 0, major radius (cm)       */
+    const double *Y2;          /* STB_RK_MODE_X_TABLE: (omega_ce/omega)^2 on the nodes, [ny][nx], where X lives;   */
+                               /* or NULL and ...                                                                  */
+    const stb_equilibrium_t *equilibrium;   /* ... the tabulated equilibrium the library builds that table from     */
 } stb_medium_desc_t;
 
 int stb_medium_create(const stb_medium_desc_t *desc, stb_medium_t *out);
 int stb_medium_destroy(stb_medium_t m);
-/* Copies the table the kernel reads back to the host: which = 0 -> X, 1 -> alpha; [ny][nx] doubles, or
+/* Copies the table the kernel reads back to the host: which = 0 -> X, 1 -> alpha, 2 -> Y^2; [ny][nx] doubles, or
  * the [ny+2][nx+2] spline coefficients for STB_RK_INTERP_BSPLINE (count must match). */
 int stb_medium_table(stb_medium_t m, int which, double *host_out, size_t count);
 

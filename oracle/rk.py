@@ -22,7 +22,8 @@ LEFT_DOMAIN, TAU_MAX, MAX_STEPS, STEP_UNDERFLOW, START_OUTSIDE, STOP_LINE = rang
 class _Medium(ctypes.Structure):
     _fields_ = [("X", _dp), ("alpha", _dp), ("nx", ctypes.c_int), ("ny", ctypes.c_int),
                 ("xorg", ctypes.c_double), ("yorg", ctypes.c_double), ("rdx", ctypes.c_double), ("rdy", ctypes.c_double),
-                ("Y0R0", ctypes.c_double), ("R0", ctypes.c_double), ("xmode", ctypes.c_int), ("interp", ctypes.c_int)]
+                ("Y0R0", ctypes.c_double), ("R0", ctypes.c_double), ("xmode", ctypes.c_int), ("interp", ctypes.c_int),
+                ("Y2", _dp)]
 
 
 class _Ctl(ctypes.Structure):
@@ -47,6 +48,9 @@ def lib():
         L.rk_oracle_eval.argtypes = [ctypes.POINTER(_Medium)] + [ctypes.c_double] * 4 + [_dp] * 4
         L.rk_oracle_prefilter.restype = None
         L.rk_oracle_prefilter.argtypes = [_dp, ctypes.c_int, ctypes.c_int, _dp]
+        L.rk_oracle_equilibrium_y2.restype = None
+        L.rk_oracle_equilibrium_y2.argtypes = [_dp, ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 4 + \
+            [_dp, ctypes.c_int] + [ctypes.c_double] * 5 + [ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 4 + [_dp]
         L.rk_oracle_batch.restype = ctypes.c_int
         L.rk_oracle_batch.argtypes = [ctypes.POINTER(_Medium), ctypes.POINTER(_Ctl), ctypes.c_longlong] + [_dp] * 7 + \
             [_dp] * 6 + [_ip] * 3 + [_dp, _dp, ctypes.c_longlong, ctypes.c_int, _ip, _dp]
@@ -83,20 +87,38 @@ def prefilter(nodes):
     return coef
 
 
+def equilibrium_y2(eq, nx, ny, xorg, yorg, dx, dy):
+    """[ny, nx] node table of Y^2 = (omega_ce/omega)^2 from a tabulated equilibrium: ``eq`` carries the fields of
+    stb_equilibrium_t (psi [nr, nz], rleft, rdim, zmid, zdim, fpol, simagx, sibdry, r0_cm, z0_cm, y_per_tesla)."""
+    psi = np.ascontiguousarray(eq["psi"], dtype=np.float64)
+    fpol = np.ascontiguousarray(eq["fpol"], dtype=np.float64)
+    out = np.empty((ny, nx))
+    lib().rk_oracle_equilibrium_y2(_p(psi), psi.shape[0], psi.shape[1], float(eq["rleft"]), float(eq["rdim"]), float(eq["zmid"]),
+                                   float(eq["zdim"]), _p(fpol), fpol.size, float(eq["simagx"]), float(eq["sibdry"]),
+                                   float(eq["r0_cm"]), float(eq["z0_cm"]), float(eq["y_per_tesla"]), int(nx), int(ny),
+                                   float(xorg), float(yorg), float(dx), float(dy), _p(out))
+    return out
+
+
 class Medium:
     """Host copy of the medium the kernel reads (stb_medium_desc_t)."""
 
-    def __init__(self, X, xorg, yorg, dx, dy, *, alpha=None, mode="O", Y0=0.0, R0=55.0, interp=BSPLINE):
-        """X, alpha: [ny, nx] NODE values; for interp = BSPLINE they are prefiltered here."""
+    def __init__(self, X, xorg, yorg, dx, dy, *, alpha=None, mode="O", Y0=0.0, R0=55.0, interp=BSPLINE, Y2=None):
+        """X, alpha, Y2: [ny, nx] NODE values; for interp = BSPLINE they are prefiltered here.
+        mode "XT" = X mode with Y^2 from the node table Y2 (STB_RK_MODE_X_TABLE)."""
         X = np.ascontiguousarray(X, dtype=np.float64)
         ny, nx = X.shape
+        if mode == "XT" and Y2 is None:
+            raise ValueError("mode 'XT' needs the Y2 node table")
         if interp == BSPLINE:
             X = prefilter(X)
             alpha = None if alpha is None else prefilter(alpha)
+            Y2 = None if Y2 is None else prefilter(Y2)
         self.X = X
         self.alpha = None if alpha is None else np.ascontiguousarray(alpha, dtype=np.float64)
+        self.Y2 = None if Y2 is None else np.ascontiguousarray(Y2, dtype=np.float64)
         self.c = _Medium(_p(self.X), _p(self.alpha), nx, ny, float(xorg), float(yorg), 1.0 / float(dx), 1.0 / float(dy),
-                         float(Y0) * float(R0), float(R0), 1 if mode == "X" else 0, int(interp))
+                         float(Y0) * float(R0), float(R0), {"O": 0, "X": 1, "XT": 2}[mode], int(interp), _p(self.Y2))
 
     def eval(self, x, y, xs=1.0, ys=1.0):
         """(fx, fy, alpha, N^2) at one point."""

@@ -25,8 +25,9 @@ typedef struct {
     const double *X, *alpha;
     int nx, ny;
     double xorg, yorg, rdx, rdy, Y0R0, R0;
-    int xmode;
+    int xmode;  /* 0: O mode, 1: X mode with Y = Y0 R0/(R0+x), 2: X mode with Y^2 from the node table Y2 */
     int interp; /* 0 bilinear, 1 Catmull-Rom, 2 cubic B-spline on a prefiltered (ny+2) x (nx+2) table */
+    const double *Y2;
 } rk_medium;
 
 typedef struct {
@@ -141,6 +142,21 @@ void rk_oracle_eval(const rk_medium *m, double xs, double ys, double x, double y
         *n2 = 1.0 - Xv;
         *fx = -0.5 * Xx;
         *fy = -0.5 * Xy;
+    } else if (m->xmode == 2) {
+        double G, Gu, Gv;
+        table_eval(m->Y2, m->nx, m->ny, m->interp, iu, iv, t, s, &G, &Gu, &Gv);
+        const double ys2 = ys * ys;
+        const double Y2 = ys2 * G;
+        const double Y2x = ys2 * (Gu * m->rdx), Y2y = ys2 * (Gv * m->rdy);
+        const double D = (1.0 - Xv) - Y2;
+        const double rD = 1.0 / D;
+        const double g = Xv * (1.0 - Xv);
+        *n2 = 1.0 - g * rD;
+        const double rD2 = rD * rD;
+        const double dX = -(fma(1.0 - 2.0 * Xv, D, g)) * rD2;
+        const double dY2 = -g * rD2;
+        *fx = 0.5 * fma(dY2, Y2x, dX * Xx);
+        *fy = 0.5 * fma(dY2, Y2y, dX * Xy);
     } else {
         const double rR = 1.0 / (m->R0 + x);
         const double Yv = ys * (m->Y0R0 * rR);
@@ -163,6 +179,47 @@ void rk_oracle_eval(const rk_medium *m, double xs, double ys, double x, double y
     } else {
         *al = 0.0;
     }
+}
+
+/* Y^2 = (omega_ce/omega)^2 on the nodes of the medium's grid from a tabulated equilibrium: the arithmetic of
+ * equilibrium_y2_kernel (rk_kernels.cuh), operation for operation.  psi[nr][nz] (R-major, equilibrium.py:34),
+ * bilinear (equilibrium.py:46-49); fpol[nf] on a uniform psi grid from simagx to sibdry. */
+void rk_oracle_equilibrium_y2(const double *psi_tab, int nr, int nz, double rleft, double rdim, double zmid, double zdim,
+                              const double *fpol, int nf, double simagx, double sibdry, double r0_cm, double z0_cm,
+                              double ypt, int nx, int ny, double xorg, double yorg, double dx, double dy, double *y2)
+{
+    const double zlow = zmid - zdim / 2;
+    const double rdr = (double)(nr - 1) / rdim, rdz = (double)(nz - 1) / zdim;
+    const double rdpsi = (double)(nf - 1) / (sibdry - simagx);
+    for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+            const double R = (r0_cm + (xorg + dx * (double)i)) * 0.01;
+            const double Z = ((yorg + dy * (double)j) - z0_cm) * 0.01;
+            const double u = (R - rleft) * rdr, v = (Z - zlow) * rdz;
+            int iu = (int)floor(u), iv = (int)floor(v);
+            iu = iu > nr - 2 ? nr - 2 : iu; iu = iu < 0 ? 0 : iu;
+            iv = iv > nz - 2 ? nz - 2 : iv; iv = iv < 0 ? 0 : iv;
+            const double t = u - (double)iu, s = v - (double)iv;
+            const double *q = psi_tab + (long long)iu * nz + iv;
+            const double p00 = q[0], p01 = q[1], p10 = q[nz], p11 = q[nz + 1];
+            const double dR0 = p10 - p00, dR1 = p11 - p01;
+            const double lo = p00 + t * dR0, hi = p01 + t * dR1;
+            const double psi = lo + s * (hi - lo);
+            const double psiR = (dR0 + s * (dR1 - dR0)) * rdr;
+            const double psiZ = (hi - lo) * rdz;
+            double w = (psi - simagx) * rdpsi;
+            w = w > 0.0 ? w : 0.0;
+            const double wmax = (double)(nf - 1);
+            w = w < wmax ? w : wmax;
+            int iw = (int)floor(w);
+            iw = iw > nf - 2 ? nf - 2 : iw;
+            const double fw = w - (double)iw;
+            const double F = fpol[iw] + fw * (fpol[iw + 1] - fpol[iw]);
+            const double rR = 1.0 / R;
+            const double BR = -(psiZ * rR), BZ = psiR * rR, Bp = F * rR;
+            const double B2 = (BR * BR + BZ * BZ) + Bp * Bp;
+            y2[(long long)j * nx + i] = (ypt * ypt) * B2;
+        }
 }
 
 /* Cubic B-spline prefilter of one line (natural end conditions), the arithmetic of

@@ -149,6 +149,21 @@ class StbMediumDesc(Structure):
         ("X", c_void_p), ("alpha", c_void_p),
         ("on_device", c_int32), ("mode", c_int32), ("interp", c_int32),
         ("Y0", c_double), ("R0", c_double),
+        ("Y2", c_void_p), ("equilibrium", c_void_p),
+    ]
+
+
+class StbEquilibrium(Structure):
+    """Mirror of ``stb_equilibrium_t`` (include/sidtrace_b200_rk.h)."""
+    _fields_ = [
+        ("struct_size", c_size_t),
+        ("nr", c_int32), ("nz", c_int32),
+        ("rleft", c_double), ("rdim", c_double), ("zmid", c_double), ("zdim", c_double),
+        ("psi", c_void_p), ("fpol", c_void_p),
+        ("nf", c_int32),
+        ("simagx", c_double), ("sibdry", c_double),
+        ("r0_cm", c_double), ("z0_cm", c_double),
+        ("y_per_tesla", c_double),
     ]
 
 

@@ -43,7 +43,7 @@ struct stb_medium_s {
     int num_sms = 0;
     stbrk::Medium m{};
     int mode = 0, interp = 2;
-    double *X = nullptr, *alpha = nullptr;
+    double *X = nullptr, *alpha = nullptr, *Y2 = nullptr;
     double2 *XA = nullptr;                   // {X, alpha} interleaved (only with an absorption table)
     unsigned long long *counter = nullptr;   // kCounters queue heads used round-robin; a slot is handed out again
                                              // only after the launch that used it last has finished (counter_ev)
@@ -54,10 +54,10 @@ struct stb_medium_s {
 
 namespace {
 
-template <int INTERP, bool XMODE, bool ABSORB>
+template <int INTERP, int MODE, bool ABSORB>
 int launch_rk(const stbrk::Params &p, int num_sms, cudaStream_t s, cudaEvent_t ev)
 {
-    auto kern = stbrk::rk_kernel<INTERP, XMODE, ABSORB>;
+    auto kern = stbrk::rk_kernel<INTERP, MODE, ABSORB>;
     const size_t smem = (ABSORB && p.hist) ? (size_t)p.nbins * sizeof(double) : 0;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -75,10 +75,11 @@ int launch_rk(const stbrk::Params &p, int num_sms, cudaStream_t s, cudaEvent_t e
 }
 
 template <int INTERP>
-int launch_mode(const stbrk::Params &p, bool xmode, bool absorb, int num_sms, cudaStream_t s, cudaEvent_t ev)
+int launch_mode(const stbrk::Params &p, int mode, bool absorb, int num_sms, cudaStream_t s, cudaEvent_t ev)
 {
-    if (xmode) return absorb ? launch_rk<INTERP, true, true>(p, num_sms, s, ev) : launch_rk<INTERP, true, false>(p, num_sms, s, ev);
-    return absorb ? launch_rk<INTERP, false, true>(p, num_sms, s, ev) : launch_rk<INTERP, false, false>(p, num_sms, s, ev);
+    if (mode == STB_RK_MODE_X_TABLE) return absorb ? launch_rk<INTERP, 2, true>(p, num_sms, s, ev) : launch_rk<INTERP, 2, false>(p, num_sms, s, ev);
+    if (mode == STB_RK_MODE_X) return absorb ? launch_rk<INTERP, 1, true>(p, num_sms, s, ev) : launch_rk<INTERP, 1, false>(p, num_sms, s, ev);
+    return absorb ? launch_rk<INTERP, 0, true>(p, num_sms, s, ev) : launch_rk<INTERP, 0, false>(p, num_sms, s, ev);
 }
 
 int trace_rk_host_io(stb_medium_t m, const stb_rk_t *rk, cudaStream_t s);
@@ -98,8 +99,22 @@ int stb_medium_create(const stb_medium_desc_t *d, stb_medium_t *out)
     if ((long long)d->nx * d->ny > 0x7fffffffLL) return fail(STB_ERR_RANGE, "stb_medium_create: nx*ny exceeds int32");
     if (!(d->dx > 0.0) || !(d->dy > 0.0) || !std::isfinite(d->dx) || !std::isfinite(d->dy))
         return fail(STB_ERR_ARG, "stb_medium_create: dx, dy must be positive and finite");
-    if (d->mode != STB_RK_MODE_O && d->mode != STB_RK_MODE_X) return fail(STB_ERR_ARG, "stb_medium_create: unknown mode %d", d->mode);
+    if (d->mode != STB_RK_MODE_O && d->mode != STB_RK_MODE_X && d->mode != STB_RK_MODE_X_TABLE)
+        return fail(STB_ERR_ARG, "stb_medium_create: unknown mode %d", d->mode);
     if (d->mode == STB_RK_MODE_X && !(d->R0 > 0.0)) return fail(STB_ERR_ARG, "stb_medium_create: the X mode needs R0 > 0");
+    const stb_equilibrium_t *eq = d->mode == STB_RK_MODE_X_TABLE && !d->Y2 ? d->equilibrium : nullptr;
+    if (d->mode == STB_RK_MODE_X_TABLE && !d->Y2 && !eq)
+        return fail(STB_ERR_ARG, "stb_medium_create: STB_RK_MODE_X_TABLE needs the Y2 node table or an equilibrium");
+    if (eq) {
+        if (eq->struct_size != sizeof(stb_equilibrium_t))
+            return fail(STB_ERR_ARG, "stb_medium_create: equilibrium struct_size %zu != %zu", eq->struct_size, sizeof(stb_equilibrium_t));
+        if (eq->nr < 2 || eq->nz < 2 || eq->nf < 2 || !eq->psi || !eq->fpol)
+            return fail(STB_ERR_ARG, "stb_medium_create: the equilibrium needs psi[nr >= 2][nz >= 2] and fpol[nf >= 2]");
+        if (!(eq->rdim > 0.0) || !(eq->zdim > 0.0) || !(eq->rleft > 0.0) || !(eq->sibdry != eq->simagx) || !std::isfinite(eq->y_per_tesla))
+            return fail(STB_ERR_ARG, "stb_medium_create: the equilibrium needs rleft, rdim, zdim > 0, sibdry != simagx, finite y_per_tesla");
+        if (!((eq->r0_cm + d->xorg) * 0.01 > 0.0))
+            return fail(STB_ERR_ARG, "stb_medium_create: the medium's grid reaches R <= 0 (r0_cm = %g, xorg = %g)", eq->r0_cm, d->xorg);
+    }
 
     if (d->interp != STB_RK_INTERP_BILINEAR && d->interp != STB_RK_INTERP_CATMULL_ROM && d->interp != STB_RK_INTERP_BSPLINE)
         return fail(STB_ERR_ARG, "stb_medium_create: unknown interpolation %d", d->interp);
@@ -113,15 +128,41 @@ int stb_medium_create(const stb_medium_desc_t *d, stb_medium_t *out)
     const size_t tbytes = spline ? (size_t)(nx + 2) * (ny + 2) * sizeof(double) : bytes;
     const cudaMemcpyKind kind = d->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     double *nodes = nullptr, *half = nullptr, *piv = nullptr;   // B-spline prefilter scratch
+    double *y2nodes = nullptr, *eq_psi = nullptr, *eq_f = nullptr;
     do {
         if (e != cudaSuccess) break;
         cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device);
         if ((e = cudaMalloc(&m->X, tbytes)) != cudaSuccess) break;
         if (d->alpha && (e = cudaMalloc(&m->alpha, tbytes)) != cudaSuccess) break;
+        if (d->mode == STB_RK_MODE_X_TABLE && (e = cudaMalloc(&m->Y2, tbytes)) != cudaSuccess) break;
+        if (d->mode == STB_RK_MODE_X_TABLE) {
+            // the Y^2 nodes: the caller's table, or |B|^2 of the tabulated equilibrium evaluated on the device
+            if ((e = cudaMalloc(&y2nodes, bytes)) != cudaSuccess) break;
+            if (d->Y2) {
+                if ((e = cudaMemcpy(y2nodes, d->Y2, bytes, kind)) != cudaSuccess) break;
+            } else {
+                const size_t pb = (size_t)eq->nr * eq->nz * sizeof(double), fb = (size_t)eq->nf * sizeof(double);
+                if ((e = cudaMalloc(&eq_psi, pb)) != cudaSuccess) break;
+                if ((e = cudaMalloc(&eq_f, fb)) != cudaSuccess) break;
+                if ((e = cudaMemcpy(eq_psi, eq->psi, pb, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+                if ((e = cudaMemcpy(eq_f, eq->fpol, fb, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+                stbrk::EqTable t{};
+                t.psi = eq_psi; t.fpol = eq_f; t.nr = eq->nr; t.nz = eq->nz; t.nf = eq->nf;
+                t.rleft = eq->rleft; t.zlow = eq->zmid - eq->zdim / 2;
+                t.rdr = (double)(eq->nr - 1) / eq->rdim; t.rdz = (double)(eq->nz - 1) / eq->zdim;
+                t.simagx = eq->simagx; t.rdpsi = (double)(eq->nf - 1) / (eq->sibdry - eq->simagx);
+                t.r0_cm = eq->r0_cm; t.z0_cm = eq->z0_cm; t.ypt = eq->y_per_tesla;
+                stbrk::equilibrium_y2_kernel<<<148 * 4, 256>>>(t, nx, ny, d->xorg, d->yorg, d->dx, d->dy, y2nodes);
+                stb_internal_count_launch();
+                if ((e = cudaGetLastError()) != cudaSuccess) break;
+            }
+        }
         if ((e = cudaMalloc(&m->counter, kCounters * sizeof(unsigned long long))) != cudaSuccess) break;
         if (!spline) {
             if ((e = cudaMemcpy(m->X, d->X, bytes, kind)) != cudaSuccess) break;
             if (d->alpha && (e = cudaMemcpy(m->alpha, d->alpha, bytes, kind)) != cudaSuccess) break;
+            if (m->Y2 && (e = cudaMemcpy(m->Y2, y2nodes, bytes, cudaMemcpyDeviceToDevice)) != cudaSuccess) break;
+            e = cudaDeviceSynchronize();
             break;
         }
         // reciprocal pivots of the tridiagonal (1, 4, 1) system: data-independent
@@ -133,11 +174,11 @@ int stb_medium_create(const stb_medium_desc_t *d, stb_medium_t *out)
         if ((e = cudaMemcpy(piv, R.data(), R.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((e = cudaMalloc(&nodes, bytes)) != cudaSuccess) break;
         if ((e = cudaMalloc(&half, (size_t)(nx + 2) * ny * sizeof(double))) != cudaSuccess) break;
-        for (int which = 0; which < 2 && e == cudaSuccess; ++which) {
-            const double *src = which ? d->alpha : d->X;
-            double *dst = which ? m->alpha : m->X;
+        for (int which = 0; which < 3 && e == cudaSuccess; ++which) {
+            const double *src = which == 2 ? y2nodes : which ? d->alpha : d->X;
+            double *dst = which == 2 ? m->Y2 : which ? m->alpha : m->X;
             if (!src) continue;
-            if ((e = cudaMemcpy(nodes, src, bytes, kind)) != cudaSuccess) break;
+            if ((e = cudaMemcpy(nodes, src, bytes, which == 2 ? cudaMemcpyDeviceToDevice : kind)) != cudaSuccess) break;
             // rows: [ny][nx] -> [ny][nx+2]; columns: [ny][nx+2] -> [ny+2][nx+2]
             stbrk::bspline_prefilter_kernel<<<(ny + 127) / 128, 128>>>(nodes, nx, 1, half, nx + 2, 1, piv, nx, ny);
             stbrk::bspline_prefilter_kernel<<<(nx + 2 + 127) / 128, 128>>>(half, 1, nx + 2, dst, 1, nx + 2, piv, ny, nx + 2);
@@ -154,17 +195,17 @@ int stb_medium_create(const stb_medium_desc_t *d, stb_medium_t *out)
             if ((e = cudaGetLastError()) == cudaSuccess) e = cudaDeviceSynchronize();
         }
     }
-    cudaFree(nodes); cudaFree(half); cudaFree(piv);
+    cudaFree(nodes); cudaFree(half); cudaFree(piv); cudaFree(y2nodes); cudaFree(eq_psi); cudaFree(eq_f);
     if (e != cudaSuccess) {
         const int rc = fail(e == cudaErrorMemoryAllocation ? STB_ERR_NOMEM : STB_ERR_CUDA, "stb_medium_create: %s",
                             cudaGetErrorString(e));
-        cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->XA); cudaFree(m->counter);
+        cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->XA); cudaFree(m->Y2); cudaFree(m->counter);
         delete m;
         return rc;
     }
     m->mode = d->mode;
     m->interp = d->interp;
-    m->m.X = m->X; m->m.alpha = m->alpha; m->m.XA = m->XA;
+    m->m.X = m->X; m->m.alpha = m->alpha; m->m.XA = m->XA; m->m.Y2 = m->Y2;
     m->m.nx = d->nx; m->m.ny = d->ny;
     m->m.xorg = d->xorg; m->m.yorg = d->yorg;
     m->m.rdx = 1.0 / d->dx; m->m.rdy = 1.0 / d->dy;
@@ -176,8 +217,9 @@ int stb_medium_create(const stb_medium_desc_t *d, stb_medium_t *out)
 int stb_medium_table(stb_medium_t m, int which, double *host_out, size_t count)
 {
     if (!m || !host_out) return fail(STB_ERR_ARG, "stb_medium_table: NULL argument");
-    const double *src = which ? m->alpha : m->X;
-    if (!src) return fail(STB_ERR_ARG, "stb_medium_table: the medium has no absorption table");
+    if (which < 0 || which > 2) return fail(STB_ERR_ARG, "stb_medium_table: which must be 0 (X), 1 (alpha) or 2 (Y^2)");
+    const double *src = which == 2 ? m->Y2 : which ? m->alpha : m->X;
+    if (!src) return fail(STB_ERR_ARG, "stb_medium_table: the medium has no %s table", which == 2 ? "Y^2" : "absorption");
     const int pad = m->interp == STB_RK_INTERP_BSPLINE ? 2 : 0;
     const size_t have = (size_t)(m->m.nx + pad) * (size_t)(m->m.ny + pad);
     if (count != have) return fail(STB_ERR_ARG, "stb_medium_table: the table holds %zu doubles, not %zu", have, count);
@@ -188,7 +230,7 @@ int stb_medium_table(stb_medium_t m, int which, double *host_out, size_t count)
 int stb_medium_destroy(stb_medium_t m)
 {
     if (!m) return STB_OK;
-    cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->XA); cudaFree(m->counter);
+    cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->XA); cudaFree(m->Y2); cudaFree(m->counter);
     for (auto &e : m->counter_ev) if (e) cudaEventDestroy(e);
     delete m;
     return STB_OK;
@@ -253,12 +295,11 @@ int stb_trace_rk(stb_medium_t m, const stb_rk_t *rk, void *stream)
     cudaEvent_t ev = m->counter_ev[slot];
 
     cudaStream_t s = (cudaStream_t)stream;
-    const bool xmode = m->mode == STB_RK_MODE_X;
     const bool absorb = m->alpha != nullptr;
     switch (m->interp) {
-        case STB_RK_INTERP_BILINEAR: return launch_mode<0>(p, xmode, absorb, m->num_sms, s, ev);
-        case STB_RK_INTERP_CATMULL_ROM: return launch_mode<1>(p, xmode, absorb, m->num_sms, s, ev);
-        default: return launch_mode<2>(p, xmode, absorb, m->num_sms, s, ev);
+        case STB_RK_INTERP_BILINEAR: return launch_mode<0>(p, m->mode, absorb, m->num_sms, s, ev);
+        case STB_RK_INTERP_CATMULL_ROM: return launch_mode<1>(p, m->mode, absorb, m->num_sms, s, ev);
+        default: return launch_mode<2>(p, m->mode, absorb, m->num_sms, s, ev);
     }
 }
 

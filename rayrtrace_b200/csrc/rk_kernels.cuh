@@ -30,6 +30,7 @@ struct Medium {
     const double *X;       // n/n_c at the reference frequency: [ny][nx] nodes, or [ny+2][nx+2] B-spline coefficients
     const double *alpha;   // power absorption coefficient per unit tau (same layout), or nullptr
     const double2 *XA;     // {X, alpha} interleaved per node (media with absorption), or nullptr
+    const double *Y2;      // MODE 2: (omega_ce/omega)^2 node table (same layout as X), or nullptr
     int nx, ny;
     double xorg, yorg;     // physical position of node (0, 0)
     double rdx, rdy;       // 1/dx, 1/dy
@@ -214,7 +215,9 @@ __device__ __forceinline__ void table_eval2(const double2 *__restrict__ T, int n
 #ifndef STB_RK_MINB
 #define STB_RK_MINB 3   // <= 170 registers, 3 CTAs per SM: measured best (profiles/r01/rk_occupancy_sweep.txt)
 #endif
-template <int INTERP, bool XMODE, bool ABSORB>
+// MODE: 0 = O mode, 1 = X mode with the analytic toroidal field Y = Y0 R0/(R0+x), 2 = X mode with Y^2 from a node
+// table (|B| of a tabulated equilibrium, equilibrium_y2_kernel)
+template <int INTERP, int MODE, bool ABSORB>
 __device__ STB_RK_EVAL_INLINE void rk_eval(const Medium &m, double xs, double ys, double x, double y, double &fx,
                                         double &fy, double &al, double &n2)
 {
@@ -229,10 +232,25 @@ __device__ STB_RK_EVAL_INLINE void rk_eval(const Medium &m, double xs, double ys
     else table_eval<INTERP, true>(m.X, m.nx, m.ny, iu, iv, t, s, F, Fu, Fv);
     const double Xv = xs * F;
     const double Xx = xs * (Fu * m.rdx), Xy = xs * (Fv * m.rdy);   // physical gradient of X
-    if (!XMODE) {
+    if (MODE == 0) {
         n2 = 1.0 - Xv;
         fx = -0.5 * Xx;
         fy = -0.5 * Xy;
+    } else if (MODE == 2) {
+        double G, Gu, Gv;
+        table_eval<INTERP, true>(m.Y2, m.nx, m.ny, iu, iv, t, s, G, Gu, Gv);
+        const double ys2 = ys * ys;
+        const double Y2 = ys2 * G;
+        const double Y2x = ys2 * (Gu * m.rdx), Y2y = ys2 * (Gv * m.rdy);   // physical gradient of Y^2
+        const double D = (1.0 - Xv) - Y2;
+        const double rD = 1.0 / D;
+        const double g = Xv * (1.0 - Xv);
+        n2 = 1.0 - g * rD;
+        const double rD2 = rD * rD;
+        const double dX = -(fma(1.0 - 2.0 * Xv, D, g)) * rD2;    // dN^2/dX
+        const double dY2 = -g * rD2;                             // dN^2/d(Y^2)
+        fx = 0.5 * fma(dY2, Y2x, dX * Xx);
+        fy = 0.5 * fma(dY2, Y2y, dX * Xy);
     } else {
         const double rR = 1.0 / (m.R0 + x);
         const double Yv = ys * (m.Y0R0 * rR);
@@ -303,7 +321,7 @@ __device__ __forceinline__ void rk_hist_add(double *sh, int b, double w)
     if (lane == leader && b >= 0) atomicAdd(&sh[b], sum);
 }
 
-template <int INTERP, bool XMODE, bool ABSORB>
+template <int INTERP, int MODE, bool ABSORB>
 __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
 {
     extern __shared__ double sh_hist[];
@@ -356,7 +374,7 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
         if (p.n2_min) p.n2_min[ray] = n2min;
         if (p.ham_end) {
             double fx, fy, al, n2;
-            rk_eval<INTERP, XMODE, false>(m, xs, ys, x, y, fx, fy, al, n2);
+            rk_eval<INTERP, MODE, false>(m, xs, ys, x, y, fx, fy, al, n2);
             p.ham_end[ray] = fma(px, px, py * py) - n2;
         }
         if (p.turn_index) p.turn_index[ray] = turn;
@@ -379,7 +397,7 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
         phi = 0.0; sig = 0.0; tau = 0.0; h = p.h0;
         nacc = 0; nrej = 0; after_reject = false; land = 0; turn = -1;
         double n2;
-        rk_eval<INTERP, XMODE, ABSORB>(m, xs, ys, x, y, f1x, f1y, a1, n2);
+        rk_eval<INTERP, MODE, ABSORB>(m, xs, ys, x, y, f1x, f1y, a1, n2);
         n2min = n2;
         store_state();
         if (!inside(x, y)) { status = START_OUTSIDE; retire(); return false; }
@@ -412,7 +430,7 @@ __global__ void __launch_bounds__(kBlock, STB_RK_MINB) rk_kernel(const Params p)
             xn = fma(hh, sx, x); yn = fma(hh, sy, y);
             pxn = fma(hh, sfx, px); pyn = fma(hh, sfy, py);
             kpx[i + 1] = pxn; kpy[i + 1] = pyn;
-            rk_eval<INTERP, XMODE, ABSORB>(m, xs, ys, xn, yn, kfx[i + 1], kfy[i + 1], alast, n2n);
+            rk_eval<INTERP, MODE, ABSORB>(m, xs, ys, xn, yn, kfx[i + 1], kfy[i + 1], alast, n2n);
             if (ABSORB && i < 5) ssig = fma(cA[5][i + 1], alast, ssig);
         }
         // (xn, yn, pxn, pyn) is the 5th-order solution (row 5 = b); stage 7 is its derivative
@@ -572,6 +590,53 @@ __global__ void interleave2_kernel(const double *__restrict__ a, const double *_
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = make_double2(a[i], b[i]);
+}
+
+// Y^2 = (omega_ce/omega)^2 on the nodes of the medium's grid from a tabulated equilibrium (include/sidtrace_b200_rk.h,
+// stb_equilibrium_t; the table of the reference's Equilibrium class, equilibrium.py:11-49, interpolated bilinearly
+// as its RectBivariateSpline(kx=1, ky=1) does).  One thread per node; plain IEEE operations in a fixed order (the
+// library is compiled -fmad=false), so oracle/rk_oracle.c reproduces the table bit for bit.
+struct EqTable {
+    const double *psi;     // [nr][nz]
+    const double *fpol;    // [nf]
+    int nr, nz, nf;
+    double rleft, zlow, rdr, rdz;     // first node, 1/spacing (1/m)
+    double simagx, rdpsi;             // F grid: psi = simagx + k / rdpsi
+    double r0_cm, z0_cm, ypt;
+};
+__global__ void equilibrium_y2_kernel(const EqTable e, int nx, int ny, double xorg, double yorg, double dx, double dy,
+                                      double *__restrict__ y2)
+{
+    const long long n = (long long)nx * ny;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(k / nx), i = (int)(k - (long long)j * nx);
+        const double R = (e.r0_cm + (xorg + dx * (double)i)) * 0.01;
+        const double Z = ((yorg + dy * (double)j) - e.z0_cm) * 0.01;
+        const double u = (R - e.rleft) * e.rdr, v = (Z - e.zlow) * e.rdz;
+        // cell clamped to the table, fraction not: outside, the edge cell's bilinear patch is continued
+        const int iu = max(0, min(__double2int_rd(u), e.nr - 2));
+        const int iv = max(0, min(__double2int_rd(v), e.nz - 2));
+        const double t = u - (double)iu, s = v - (double)iv;
+        const double *q = e.psi + (long long)iu * e.nz + iv;
+        const double p00 = q[0], p01 = q[1], p10 = q[e.nz], p11 = q[e.nz + 1];    // p[R index][Z index]
+        const double dR0 = p10 - p00, dR1 = p11 - p01;        // along R at the two Z nodes
+        const double lo = p00 + t * dR0, hi = p01 + t * dR1;
+        const double psi = lo + s * (hi - lo);
+        const double psiR = (dR0 + s * (dR1 - dR0)) * e.rdr;  // dpsi/dR
+        const double psiZ = (hi - lo) * e.rdz;                // dpsi/dZ
+        // F(psi): linear on the uniform psi grid, held at the ends
+        double w = (psi - e.simagx) * e.rdpsi;
+        w = w > 0.0 ? w : 0.0;
+        const double wmax = (double)(e.nf - 1);
+        w = w < wmax ? w : wmax;
+        const int iw = min(__double2int_rd(w), e.nf - 2);
+        const double fw = w - (double)iw;
+        const double F = e.fpol[iw] + fw * (e.fpol[iw + 1] - e.fpol[iw]);
+        const double rR = 1.0 / R;
+        const double BR = -(psiZ * rR), BZ = psiR * rR, Bp = F * rR;
+        const double B2 = (BR * BR + BZ * BZ) + Bp * Bp;
+        y2[k] = (e.ypt * e.ypt) * B2;
+    }
 }
 
 // Cubic B-spline prefilter along one axis: for every line, solve c[i-1] + 4 c[i] + c[i+1] = 6 f[i]

@@ -18,13 +18,66 @@ from typing import Optional
 import numpy as np
 
 from . import _cabi
-from ._cabi import StbMediumDesc, StbRk, lib
+from ._cabi import StbEquilibrium, StbMediumDesc, StbRk, lib
 from .nfield import critical_den
 
 LEFT_DOMAIN, TAU_MAX, MAX_STEPS, STEP_UNDERFLOW, START_OUTSIDE, STOP_LINE = range(6)
 INTERP = {"bilinear": 0, "catmull-rom": 1, "bspline": 2}
 
 ELECTRON_CYCLOTRON_HZ_PER_T = 2.799249e10
+
+
+class Equilibrium:
+    """A tabulated axisymmetric equilibrium with the fields of the reference's ``Equilibrium`` class
+    (equilibrium.py:11-49, geqdsk-like; SI units): ``psi[nx, ny]`` on the rectangle ``[rleft, rleft + rdim] x
+    [zmid - zdim/2, zmid + zdim/2]`` (R-major, "so (x,y) axis order is in geqdsk format"), ``fpol`` = R B_phi on a
+    uniform psi grid from ``simagx`` to ``sibdry``.  Any object with these attributes will do -- an instance of
+    the reference's own class included.  The library interpolates psi bilinearly, as the reference's
+    ``_psi_interp = RectBivariateSpline(..., kx=1, ky=1)`` does (equilibrium.py:46-49)."""
+
+    def __init__(self, psi, fpol, *, rleft, rdim, zmid, zdim, simagx, sibdry):
+        self.psi = np.ascontiguousarray(psi, dtype=np.float64)
+        self.fpol = np.ascontiguousarray(fpol, dtype=np.float64)
+        self.nx, self.ny = self.psi.shape
+        self.rleft, self.rdim, self.zmid, self.zdim = float(rleft), float(rdim), float(zmid), float(zdim)
+        self.simagx, self.sibdry = float(simagx), float(sibdry)
+
+    @classmethod
+    def solovev(cls, *, R0=0.55, a=0.08, kappa=1.0, B0=2.2, psi_b=2.0e-3, nr=129, nz=129, half=0.1, nf=65):
+        """Solov'ev equilibrium psi = psi_b/(a^2 R0^2) [R^2 Z^2/kappa^2 + (R^2 - R0^2)^2/4], F = B0 R0 (vacuum
+        toroidal field), tabulated like a geqdsk file.  Defaults: the FT-2 size of equilibrium.py:16-29
+        (R0 = 0.55 m, 0.2 m box, 2.2 T).  Analytic, so tests can compare B against the closed form."""
+        R = np.linspace(R0 - half, R0 + half, nr)
+        Z = np.linspace(-half, half, nz)
+        RR, ZZ = np.meshgrid(R, Z, indexing="ij")
+        psi = psi_b / (a * a * R0 * R0) * (RR ** 2 * ZZ ** 2 / kappa ** 2 + (RR ** 2 - R0 ** 2) ** 2 / 4)
+        eq = cls(psi, np.full(nf, B0 * R0), rleft=R0 - half, rdim=2 * half, zmid=0.0, zdim=2 * half, simagx=0.0, sibdry=psi_b)
+        eq.analytic = dict(R0=R0, a=a, kappa=kappa, B0=B0, psi_b=psi_b)
+        return eq
+
+    def analytic_B(self, R, Z):
+        """(B_R, B_Z, B_phi) of the Solov'ev equilibrium at (R, Z) in metres (only for ``solovev`` instances)."""
+        p = self.analytic
+        c = p["psi_b"] / (p["a"] ** 2 * p["R0"] ** 2)
+        return (-c * 2 * R * Z / p["kappa"] ** 2, c * (2 * Z ** 2 / p["kappa"] ** 2 + (R ** 2 - p["R0"] ** 2)),
+                p["B0"] * p["R0"] / R)
+
+
+def _equilibrium_struct(eq, freq, r0_cm, z0_cm):
+    """stb_equilibrium_t for ``eq`` plus the arrays it points to (keep them alive while the struct is in use)."""
+    psi = np.ascontiguousarray(eq.psi, dtype=np.float64)
+    fpol = np.ascontiguousarray(eq.fpol, dtype=np.float64)
+    if psi.ndim != 2 or min(psi.shape) < 2 or fpol.ndim != 1 or fpol.size < 2:
+        raise ValueError("the equilibrium needs psi[nr >= 2, nz >= 2] and fpol[nf >= 2]")
+    e = StbEquilibrium()
+    e.struct_size = ctypes.sizeof(StbEquilibrium)
+    e.nr, e.nz = psi.shape
+    e.rleft, e.rdim, e.zmid, e.zdim = float(eq.rleft), float(eq.rdim), float(eq.zmid), float(eq.zdim)
+    e.psi, e.fpol, e.nf = psi.ctypes.data, fpol.ctypes.data, fpol.size
+    e.simagx, e.sibdry = float(eq.simagx), float(eq.sibdry)
+    e.r0_cm, e.z0_cm = float(r0_cm), float(z0_cm)
+    e.y_per_tesla = ELECTRON_CYCLOTRON_HZ_PER_T / float(freq)
+    return e, (psi, fpol)
 
 
 def _torch():
@@ -39,7 +92,11 @@ class Medium:
     'catmull-rom' (C1 local bicubic patches) or 'bilinear'."""
 
     def __init__(self, X, x, y, *, alpha=None, mode: str = "O", Y0: float = 0.0, R0: float = 55.0,
-                 interp: str = "bspline"):
+                 interp: str = "bspline", Y2=None, equilibrium=None, freq: Optional[float] = None, z0: float = 0.0):
+        """X mode: Y = Y0 R0/(R0 + x) (analytic toroidal field) unless ``Y2`` -- the [ny, nx] node table of
+        (omega_ce/omega)^2 -- or ``equilibrium`` (an ``Equilibrium``; needs ``freq``) is given: then Y^2 is
+        interpolated like X, from the caller's table or from |B| of the tabulated equilibrium, evaluated on the
+        device at the nodes (R = (R0 + x)/100 m, Z = (y - z0)/100 m)."""
         X = np.ascontiguousarray(X, dtype=np.float64)
         x = np.asarray(x, dtype=np.float64)
         y = np.asarray(y, dtype=np.float64)
@@ -60,6 +117,17 @@ class Medium:
             alpha = np.ascontiguousarray(alpha, dtype=np.float64)
             if alpha.shape != X.shape:
                 raise ValueError("alpha must have the shape of X")
+        if (Y2 is not None or equilibrium is not None) and mode != "X":
+            raise ValueError("Y2 / equilibrium belong to the X mode")
+        if Y2 is not None and equilibrium is not None:
+            raise ValueError("give Y2 or equilibrium, not both")
+        if Y2 is not None:
+            Y2 = np.ascontiguousarray(Y2, dtype=np.float64)
+            if Y2.shape != X.shape:
+                raise ValueError("Y2 must have the shape of X")
+        if equilibrium is not None and not (freq and freq > 0):
+            raise ValueError("equilibrium= needs freq= (Y = f_ce / freq)")
+        self.tabulated_B = Y2 is not None or equilibrium is not None
         self.nx, self.ny = int(x.size), int(y.size)
         self.xorg, self.yorg, self.dx, self.dy = float(x[0]), float(y[0]), float(dx), float(dy)
         self.mode, self.Y0, self.R0, self.interp = mode, float(Y0), float(R0), interp
@@ -74,28 +142,35 @@ class Medium:
         d.X = X.ctypes.data
         d.alpha = alpha.ctypes.data if alpha is not None else None
         d.on_device = 0
-        d.mode = 1 if mode == "X" else 0
+        d.mode = (2 if self.tabulated_B else 1) if mode == "X" else 0
         d.interp = INTERP[interp]
         d.Y0, d.R0 = self.Y0, self.R0
+        keep = None
+        if Y2 is not None:
+            d.Y2 = Y2.ctypes.data
+        elif equilibrium is not None:
+            es, keep = _equilibrium_struct(equilibrium, freq, self.R0, z0)
+            d.equilibrium = ctypes.addressof(es)
         h = ctypes.c_void_p()
         _cabi.check(lib.stb_medium_create(ctypes.byref(d), ctypes.byref(h)))
         self._h = h
 
     @classmethod
     def from_density(cls, n, x, y, *, freq: float = 136.268e9, den_unit="cm^-3", alpha=None, mode: str = "O",
-                     btor: float = 2.2, R0: float = 55.0, interp: str = "bspline") -> "Medium":
+                     btor: float = 2.2, R0: float = 55.0, interp: str = "bspline", equilibrium=None, z0: float = 0.0) -> "Medium":
         """n in cm^-3 (times ``den_unit``) on nodes -> X = n / n_c(freq) (den.py:335-348); the
-        X mode's Y0 = f_ce(btor) / freq with the rmain/btor defaults of equilibrium.py:289."""
+        X mode's Y0 = f_ce(btor) / freq with the rmain/btor defaults of equilibrium.py:289, or -- with
+        ``equilibrium`` -- |B| from the tabulated psi(R, Z) and F(psi)."""
         X = np.asarray(n, dtype=np.float64) / critical_den(freq, den_unit=den_unit)
         Y0 = ELECTRON_CYCLOTRON_HZ_PER_T * btor / freq if mode == "X" else 0.0
-        return cls(X, x, y, alpha=alpha, mode=mode, Y0=Y0, R0=R0, interp=interp)
+        return cls(X, x, y, alpha=alpha, mode=mode, Y0=Y0, R0=R0, interp=interp, equilibrium=equilibrium, freq=freq, z0=z0)
 
     def table(self, which: str = "X") -> np.ndarray:
         """The table the kernel reads, copied back: node values, or for the B-spline the
         (ny+2, nx+2) coefficients the device prefilter produced."""
         pad = 2 if self.interp == "bspline" else 0
         out = np.empty((self.ny + pad, self.nx + pad))
-        _cabi.check(lib.stb_medium_table(self._h, 0 if which == "X" else 1, out.ctypes.data, out.size))
+        _cabi.check(lib.stb_medium_table(self._h, {"X": 0, "alpha": 1, "Y2": 2}[which], out.ctypes.data, out.size))
         return out
 
     def close(self) -> None:

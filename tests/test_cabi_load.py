@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol():
 
 @pytest.mark.parametrize("cname, pyname", [("stb_batch_t", "StbBatch"), ("stb_launch_t", "StbLaunch"),
                                            ("stb_beam_t", "StbBeam"), ("stb_tube_t", "StbTube"), ("stb_overlap_t", "StbOverlap"),
-                                           ("stb_medium_desc_t", "StbMediumDesc"),
+                                           ("stb_medium_desc_t", "StbMediumDesc"), ("stb_equilibrium_t", "StbEquilibrium"),
                                            ("stb_rk_t", "StbRk")])
 def test_struct_layout_matches_c(tmp_path, cname, pyname):
     from rayrtrace_b200 import _cabi

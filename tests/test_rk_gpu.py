@@ -407,3 +407,94 @@ def test_beam_receiver_phases_parity_path_converges_to_rk(ph):
     print("rk phase, 201 vs 401:", np.abs(rk_phase[0] - rk_phase[1])[both].max(), "parity - rk:", worst)
     assert np.abs(rk_phase[0] - rk_phase[1])[both].max() < 0.15
     assert worst[0] < 2.0 and 1.35 < worst[0] / worst[1] < 2.7      # 0.69 -> 0.44 rad measured (kinked profile: below 2x)
+
+
+# ---------------------------------------------------------------- X mode with |B| from a tabulated equilibrium
+def _eq_dict(eq, freq, r0_cm=55.0, z0_cm=0.0):
+    from rayrtrace_b200.physics import ELECTRON_CYCLOTRON_HZ_PER_T
+    return dict(psi=eq.psi, fpol=eq.fpol, rleft=eq.rleft, rdim=eq.rdim, zmid=eq.zmid, zdim=eq.zdim, simagx=eq.simagx,
+                sibdry=eq.sibdry, r0_cm=r0_cm, z0_cm=z0_cm, y_per_tesla=ELECTRON_CYCLOTRON_HZ_PER_T / freq)
+
+
+@pytest.mark.parametrize("interp", INTERPS)
+def test_equilibrium_table_built_on_the_device_is_bitwise_the_checkers(ph, rk, interp):
+    """STB_RK_MODE_X_TABLE: the library evaluates |B|^2 of the tabulated psi(R, Z), F(psi) (the reference's Equilibrium
+    fields, equilibrium.py:11-49, bilinear psi) at the medium's nodes on the device; the checker does the same
+    operations on the CPU.  Node tables (and their spline coefficients) agree bit for bit, on a non-square grid
+    that sticks out of the psi rectangle on one side."""
+    freq = 70e9
+    eq = ph.Equilibrium.solovev(kappa=1.3, nr=97, nz=81, nf=33)
+    eq.fpol = eq.fpol * np.linspace(1.0, 1.02, eq.fpol.size)          # F varies with psi: exercises the F lookup
+    xs = np.linspace(-10, 12, 141)                                     # R up to 0.67 m: beyond rleft + rdim = 0.65
+    ys = np.linspace(-9, 9, 111)
+    X = 0.2 * np.exp(-(xs[None, :] ** 2 + ys[:, None] ** 2) / 20.0)
+    med = ph.Medium(X, xs, ys, mode="X", R0=55.0, interp=interp, equilibrium=eq, freq=freq)
+    y2 = rk.equilibrium_y2(_eq_dict(eq, freq), xs.size, ys.size, med.xorg, med.yorg, med.dx, med.dy)
+    want = rk.prefilter(y2) if interp == "bspline" else y2
+    assert med.table("Y2").tobytes() == want.tobytes()
+    # the same table handed over as Y2= gives the same medium
+    med2 = ph.Medium(X, xs, ys, mode="X", R0=55.0, interp=interp, Y2=y2)
+    assert med2.table("Y2").tobytes() == want.tobytes()
+    # and it is the Solov'ev field: toroidal part exact, poloidal part to the accuracy of a bilinear psi
+    RR, ZZ = (55.0 + xs[None, :]) * 0.01 + 0 * ys[:, None], ys[:, None] * 0.01 + 0 * xs[None, :]
+    inside = (RR < eq.rleft + eq.rdim) & (np.abs(ZZ) < eq.zdim / 2)
+    BR, BZ, _ = eq.analytic_B(RR, ZZ)
+    F = np.interp(np.clip((eq.analytic["psi_b"] / (eq.analytic["a"] ** 2 * eq.analytic["R0"] ** 2)
+                           * (RR ** 2 * ZZ ** 2 / 1.3 ** 2 + (RR ** 2 - 0.55 ** 2) ** 2 / 4)), eq.simagx, eq.sibdry),
+                  np.linspace(eq.simagx, eq.sibdry, eq.fpol.size), eq.fpol)
+    ypt = ph.ELECTRON_CYCLOTRON_HZ_PER_T / freq
+    exact = ypt ** 2 * (BR ** 2 + BZ ** 2 + (F / RR) ** 2)
+    assert np.max(np.abs(y2 - exact)[inside] / exact[inside]) < 2e-3
+
+
+@pytest.mark.parametrize("interp", INTERPS)
+@pytest.mark.parametrize("absorb", [False, True])
+def test_tabulated_field_x_mode_bitwise(ph, rk, interp, absorb):
+    xs, X, alpha = _tables(with_alpha=absorb, peak=0.3)
+    freq = 60e9
+    eq = ph.Equilibrium.solovev(kappa=1.2, psi_b=6e-3, nr=129, nz=129, half=0.12)
+    n = 3000
+    x0, y0, px, py = _beam(n)
+    rng = np.random.default_rng(17)
+    xscale = rng.uniform(0.2, 2.4, n)
+    yscale = rng.uniform(0.8, 1.2, n)
+    amp = rng.uniform(0.5, 1.5, n)
+    kw = dict(rtol=1e-8, atol_r=1e-8, atol_p=1e-8, h0=0.05, hmin=1e-10, hmax=0.4, max_steps=5000)
+    med = ph.Medium(X, xs, xs, alpha=alpha, mode="X", R0=55.0, interp=interp, equilibrium=eq, freq=freq)
+    res = _gpu(ph, med, x0, y0, px, py, xscale=xscale, yscale=yscale, amp=amp, L=48, aux=True,
+               nbins=32 if absorb else 0, r_lcs=7.85, rho_max=1.5, **kw)
+    y2 = rk.equilibrium_y2(_eq_dict(eq, freq), xs.size, xs.size, med.xorg, med.yorg, med.dx, med.dy)
+    om = rk.Medium(X, med.xorg, med.yorg, med.dx, med.dy, alpha=alpha, mode="XT", Y2=y2, interp=INTERP_ID[interp])
+    want = rk.trace(om, x0, y0, px, py, xscale=xscale, yscale=yscale, amp=amp, L=48, aux=True,
+                    nbins=32 if absorb else 0, r_lcs=7.85, rho_max=1.5, threads=8, **kw)
+    _same(res, want)
+    assert res.traj.cpu().numpy().tobytes() == want["traj"].tobytes()
+    assert want["nacc"].min() > 3 and len(set(want["status"].tolist())) >= 2
+    if absorb:
+        h = res.hist.cpu().numpy()
+        assert np.abs(h - want["hist"]).sum() <= 1e-9 * np.abs(want["hist"]).sum()
+
+
+def test_tabulated_toroidal_field_reproduces_the_analytic_x_mode(ph):
+    """A Y^2 table sampled from the analytic field Y0 R0/(R0 + x) on a fine grid: rays end where the analytic X mode
+    puts them (the spline of a smooth table is accurate to ~1e-8 here)."""
+    import torch
+    xs = np.linspace(-10, 10, 401)
+    X = 0.3 * np.exp(-(xs[None, :] ** 2 + xs[:, None] ** 2) / 14.0)
+    Y0, R0 = 0.45, 55.0
+    Y2 = ((Y0 * R0 / (R0 + xs)) ** 2)[None, :] + 0 * xs[:, None]
+    x0, y0, px, py = _beam(2000, seed=3)
+    a = ph.Medium(X, xs, xs, mode="X", Y0=Y0, R0=R0)
+    b = ph.Medium(X, xs, xs, mode="X", R0=R0, Y2=Y2)
+    dev = lambda v: torch.from_numpy(np.ascontiguousarray(v)).cuda()
+    Na = ph.refractive_index(a, dev(x0), dev(y0))
+    Nb = ph.refractive_index(b, dev(x0), dev(y0))
+    assert float((Na - Nb).abs().max()) < 1e-9
+    ra = ph.trace_rk(a, dev(x0), dev(y0), Na * dev(px), Na * dev(py), rtol=1e-10, stop=(9.0, "y"))
+    rb = ph.trace_rk(b, dev(x0), dev(y0), Nb * dev(px), Nb * dev(py), rtol=1e-10, stop=(9.0, "y"))
+    torch.cuda.synchronize()
+    assert torch.equal(ra.status, rb.status)
+    on = ra.status == ph.STOP_LINE                  # the free end state is wherever the last step happened to land
+    assert int(on.sum()) > 1000
+    assert float((ra.end_state - rb.end_state)[:, on].abs().max()) < 1e-6
+    assert float((ra.phi - rb.phi)[on].abs().max()) < 1e-6

@@ -449,3 +449,79 @@ def test_reference_scheme_converges_to_the_rk_solution_at_first_order():
     assert max(rk_cross) - min(rk_cross) < 5e-5            # the RK answer barely depends on the grid
     assert diffs[0] < 0.08 and diffs[2] < 0.02
     assert 1.7 < diffs[0] / diffs[1] < 2.4 and 1.7 < diffs[1] / diffs[2] < 2.4
+
+
+# ---------------------------------------------------------------- X mode with |B| from a tabulated equilibrium (mode "XT")
+def _solovev_tables(nr=257, nz=257, half=0.12, R0=0.55, a=0.08, kappa=1.2, B0=2.2, psi_b=6e-3, nf=33):
+    R = np.linspace(R0 - half, R0 + half, nr)
+    Z = np.linspace(-half, half, nz)
+    RR, ZZ = np.meshgrid(R, Z, indexing="ij")
+    c = psi_b / (a * a * R0 * R0)
+    psi = c * (RR ** 2 * ZZ ** 2 / kappa ** 2 + (RR ** 2 - R0 ** 2) ** 2 / 4)
+    eq = dict(psi=psi, fpol=np.full(nf, B0 * R0), rleft=R0 - half, rdim=2 * half, zmid=0.0, zdim=2 * half, simagx=0.0,
+              sibdry=psi_b, r0_cm=100 * R0, z0_cm=0.0, y_per_tesla=2.799249e10 / 60e9)
+
+    def B(Rm, Zm):
+        return -c * 2 * Rm * Zm / kappa ** 2, c * (2 * Zm ** 2 / kappa ** 2 + (Rm ** 2 - R0 ** 2)), B0 * R0 / Rm
+    return eq, B
+
+
+def test_equilibrium_table_is_the_solovev_field():
+    """|B|^2 from the bilinear psi(R, Z) table (the reference's Equilibrium fields, equilibrium.py:11-49): the
+    toroidal part is exact, the poloidal part converges at first order in the psi grid spacing."""
+    xs = np.linspace(-10, 10, 101)
+    errs = []
+    for n in (65, 129, 257):
+        eq, B = _solovev_tables(nr=n, nz=n)
+        y2 = rk.equilibrium_y2(eq, xs.size, xs.size, xs[0], xs[0], xs[1] - xs[0], xs[1] - xs[0])
+        RR, ZZ = (55.0 + xs[None, :]) * 0.01 + 0 * xs[:, None], xs[:, None] * 0.01 + 0 * xs[None, :]
+        BR, BZ, Bp = B(RR, ZZ)
+        exact = eq["y_per_tesla"] ** 2 * (BR ** 2 + BZ ** 2 + Bp ** 2)
+        pol = eq["y_per_tesla"] ** 2 * (BR ** 2 + BZ ** 2)
+        errs.append(np.max(np.abs(y2 - exact)) / pol.max())
+    assert errs[2] < 0.02 and errs[0] / errs[2] > 3.0        # first order: 4x finer grid, ~4x smaller error
+    assert np.max(np.abs(y2 - exact) / exact) < 1e-3
+
+
+def test_tabulated_field_force_is_the_gradient_of_n2():
+    """Mode XT: fx, fy = grad(N^2)/2 with N^2 = 1 - X(1-X)/(1-X-Y^2) and BOTH X and Y^2 interpolated: centred
+    differences of the N^2 the evaluation itself reports."""
+    xs = np.linspace(-10, 10, 161)
+    X = 0.3 * np.exp(-((xs[None, :] - 0.5) ** 2 + 1.2 * xs[:, None] ** 2) / 15.0)
+    eq, _ = _solovev_tables()
+    d = xs[1] - xs[0]
+    y2 = rk.equilibrium_y2(eq, xs.size, xs.size, xs[0], xs[0], d, d)
+    med = rk.Medium(X, xs[0], xs[0], d, d, mode="XT", Y2=y2)
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        x, y = rng.uniform(-8, 8, 2)
+        xs_, ys_ = rng.uniform(0.5, 1.5), rng.uniform(0.8, 1.2)
+        fx, fy, _, n2 = med.eval(x, y, xs_, ys_)
+        h = 1e-5
+        gx = (med.eval(x + h, y, xs_, ys_)[3] - med.eval(x - h, y, xs_, ys_)[3]) / (2 * h)
+        gy = (med.eval(x, y + h, xs_, ys_)[3] - med.eval(x, y - h, xs_, ys_)[3]) / (2 * h)
+        assert abs(fx - gx / 2) < 1e-7 * max(1, abs(gx)) and abs(fy - gy / 2) < 1e-7 * max(1, abs(gy))
+
+
+def test_tabulated_toroidal_field_equals_the_analytic_x_mode():
+    """A Y^2 table sampled from Y0 R0/(R0 + x): mode XT reproduces mode X (end states, optical path) to the
+    accuracy of the spline; and the poloidal field of a real equilibrium shifts the right-hand cut-off."""
+    xs = np.linspace(-10, 10, 401)
+    d = xs[1] - xs[0]
+    X = 0.3 * np.exp(-(xs[None, :] ** 2 + xs[:, None] ** 2) / 14.0)
+    Y0, R0 = 0.45, 55.0
+    Y2 = ((Y0 * R0 / (R0 + xs)) ** 2)[None, :] + 0 * xs[:, None]
+    a = rk.Medium(X, xs[0], xs[0], d, d, mode="X", Y0=Y0, R0=R0)
+    b = rk.Medium(X, xs[0], xs[0], d, d, mode="XT", Y2=Y2)
+    rng = np.random.default_rng(2)
+    n = 200
+    x0, y0, th = rng.uniform(-6, 6, n), np.full(n, -9.5), rng.uniform(-0.4, 0.4, n)
+    N = np.array([np.sqrt(a.eval(x0[i], y0[i])[3]) for i in range(n)])
+    # end the rays ON a receiver line: the free end state is wherever the last step happened to land
+    ra = rk.trace(a, x0, y0, N * np.sin(th), N * np.cos(th), rtol=1e-10, threads=4, stop=(9.0, "y"))
+    rb = rk.trace(b, x0, y0, N * np.sin(th), N * np.cos(th), rtol=1e-10, threads=4, stop=(9.0, "y"))
+    assert np.array_equal(ra["status"], rb["status"])
+    on = ra["status"] == rk.STOP_LINE
+    assert on.sum() > n // 2
+    assert np.max(np.abs(ra["end_state"] - rb["end_state"])[:, on]) < 1e-6
+    assert np.max(np.abs(ra["phi"] - rb["phi"])[on]) < 1e-6
