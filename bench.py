@@ -542,7 +542,8 @@ def run_b200(args):
         bw = ctypes.c_double()
         _cabi.check(_cabi.lib.stb_measure_store_bw(8 << 30, ctypes.byref(bw)))
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        kw0 = dict(kw, tiled=False, refill=False)
+        cells = sidtrace.pick_cells(d_in[2], d_in[3])     # the fan climbs in y: the y-major table (picked outside the timed region)
+        kw0 = dict(kw, tiled=False, refill=False, cells=cells)
         o0 = sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state)
         for _ in range(3):
             sidtrace.trace_batch(field, *d_in, out=o0, **kw0)
@@ -556,8 +557,11 @@ def run_b200(args):
         endpoint = {"value": ep, "unit": UNIT, "ms_per_launch": e0.elapsed_time(e1) / args.steps,
                     "fp64_peak_tflops_measured": tf.value, "store_bw_gbs_measured": bw.value,
                     "fp64_frac": ep * FLOPS_PER_RAY_STEP / (tf.value * 1e12) if tf.value else None,
-                    "note": "step counts + end states only (static grid, hoisted per-cell products); 16 algorithmic flops per "
-                            "ray-step (SURVEY 8d) over a dependent-free DFMA peak measured in this run"}
+                    "cells": cells + "-major",
+                    "dispatch_ceiling": "7.2e11 ray-steps/s with every gather an L1 hit (profiles/r02/dual_ray_endpoint.txt): an FP64 "
+                                        "instruction holds its scheduler's dispatch port two cycles, 34.5 + 14 cycles per ray-step",
+                    "note": "step counts + end states only (static grid, two rays per thread, hoisted per-cell products); 16 algorithmic "
+                            "flops per ray-step (SURVEY 8d) over a dependent-free DFMA peak measured in this run"}
         del traj
         out.traj = h_out.traj = None
         torch.cuda.empty_cache()

@@ -241,6 +241,9 @@ namespace {
 
 using stb::KParams;
 
+// STB_DUAL=0 in the environment keeps the one-ray-per-thread endpoint kernel on the static grid (A/B measurements)
+const bool g_dual = [] { const char *e = getenv("STB_DUAL"); return !(e && e[0] == '0'); }();
+
 struct LaunchCtx {
     stb_field_s *f;
     bool refill;
@@ -265,6 +268,17 @@ int launch_one(const KParams &p0, const LaunchCtx &c)
     }
     const size_t smem = HIST ? (size_t)p0.nbins * sizeof(double) : 0;
     if (p0.nrays <= 0) return STB_OK;
+    // step counts / end states only, static grid: two rays per thread (endpoint_dual_kernel)
+    if constexpr (!TRAJ && !EXTRAS && !HIST && !TILED && !CROSS && !STRAY) {
+        if (!c.refill && g_dual) {
+            const long long blocks = (p0.nrays + 2 * stb::kBlock - 1) / (2 * stb::kBlock);
+            if (blocks > 0x7fffffffLL) return fail(STB_ERR_ARG, "too many rays for a static grid");
+            stb::endpoint_dual_kernel<DIVC, HOIST><<<(unsigned)blocks, stb::kBlock, 0, s>>>(p0);
+            g_launches++;
+            CU(cudaGetLastError());
+            return STB_OK;
+        }
+    }
     long long blocks_all = (p0.nrays + stb::kBlock - 1) / stb::kBlock;
     if (c.refill) {
         auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, true, TILED, CROSS, STRAY, LOOKUP, stb::kBlock, HOIST>;

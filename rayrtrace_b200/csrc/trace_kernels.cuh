@@ -134,20 +134,23 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_first()
     return pol;
 }
 
-// What bounds the kernels WITHOUT trajectory output is the dependent chain of one ray-step, not the FP64 pipe
-// and not instruction issue.  Measured on B200 (tools/probe/latency_probe.cu, profiles/r02/latency_probe.txt,
-// occupancy_curve_endpoints.txt): FP64 operations 8.3 cycles, F2I.F64 ~19, a warp-uniform 32-byte gather 60-70
-// cycles from L1 and 300+ from L2, one ray-step of one warp 437 cycles in isolation and ~570 in the kernel;
-// the kernel's run time does not move between 1 and 8 warps per scheduler and reaches 5.3-6.3e11 ray-steps/s
-// at the 12 the 40-register cap allows (ncu: half of all stall samples sit on the first use of the gathered
-// cell).  A ray enters a new cell -- a new 32-byte sector, whatever the layout -- almost every step, and the
-// four warps of a CTA ride the same cells in convoy, so each of them waits for the same L2 fill.
-// Tried against that, measured, dropped (profiles/r02/prefetch_dropped.txt): `prefetch.global.L1` of the
+// What bounds the kernels WITHOUT trajectory output.  Measured on B200 (tools/probe/latency_probe.cu,
+// profiles/r02/latency_probe.txt, occupancy_curve_endpoints.txt, dual_ray_endpoint.txt): FP64 operations 8.3
+// cycles, F2I.F64 ~19, a warp-uniform 32-byte gather 60-70 cycles from L1 and 300+ from L2, one ray-step of one
+// warp 437 cycles in isolation and ~570 in the kernel.  Up to 8 warps per scheduler the kernel is bound by that
+// latency (its run time does not move between 1 and 8); at the 12 the 40-register cap allows it is not any more:
+// two rays per thread (72 instead of 48 independent chains per SM, endpoint_dual_kernel) buy 3.5 %, and forcing
+// every gather onto one L1-resident cell buys 11 % more.  What is left is the instruction stream itself -- an
+// FP64 instruction holds its scheduler's dispatch port for two cycles, so a ray-step costs (instructions + 14)
+// dispatch cycles, and 7.2e11 ray-steps/s is 94 % of what the 592 schedulers can dispatch.
+// A ray enters a new cell -- a new 32-byte sector, whatever the layout -- almost every step, and the four warps
+// of a CTA ride the same cells in convoy, so each of them waits for the same L2 fill: that is the 11 %.
+// Tried against it, measured, dropped (profiles/r02/prefetch_dropped.txt): `prefetch.global.L1` of the
 // neighbouring cells (CCTL.E.PF1 leaves the probe's chain at 438 cycles: no effect, 2 % slower in the
 // kernel); real 4-byte "touch" loads of the cells 2 ahead and behind along the fast axis of the y-major
 // table (the probe's chain drops to 289 cycles and the kernel's demand-gather stall samples fall 4x, but the
-// two extra LSU instructions per step cost more than they save at full occupancy: 1.28 -> 1.40 ms, and
-// 1.9x slower on rays in random order, where every lane touches a sector of its own).
+// two extra LSU instructions per step cost more dispatch cycles than the wait they remove: 1.28 -> 1.40 ms,
+// and 1.9x slower on rays in random order, where every lane touches a sector of its own).
 constexpr int kTablePadCells = 8;   // cells of padding on either side of every cell table (room for such experiments)
 
 // one 32-byte cell of the hoisted table = one LDG.E.ENL2.256.CONSTANT
@@ -842,6 +845,142 @@ __global__ void transpose_cells_kernel(const T *__restrict__ in, T *__restrict__
         const int ix = bx + j, iy = by + threadIdx.x;
         if (ix < nxm1 && iy < nym1) out[(long long)ix * nym1 + iy] = tile[threadIdx.x][j];
     }
+}
+
+// Endpoint mode, static grid, TWO rays per thread.  The kernels without trajectory output are bound by the latency
+// of the step's dependent chain (see above): throughput = independent chains in flight / chain latency, and one
+// ray per thread caps the chains at the 48 warps/SM the register file allows.  Here a thread carries rays
+// r and r + BLOCK of its CTA's 2*BLOCK consecutive rays, so every warp has two independent chains to issue from
+// (launch-state loads and per-ray results stay coalesced).  While both rays are alive and in the common case --
+// all four dividends in div_pair's guarded exponent range, both new states +finite, inside the grid, below the
+// cap -- one loop iteration steps both; anything else is settled by the exact single-ray step / guard, and once
+// one ray has ended the other finishes alone.  Same operations on the same operands as step(): bit-identical.
+#ifndef STB_MINB_DUAL
+#define STB_MINB_DUAL 9       // 56 registers, 36 warps = 72 rays in flight per SM (6 / 8 / 9 / 10 CTAs per SM measured:
+#endif                        // 1.418 / 1.285 / 1.255 / 1.254 ms per 10^6 rays; one ray per thread: 1.299 ms)
+struct DualRay { double x, y, kx, ky; int ind, i; };
+
+template <bool DIVC, bool HOIST>
+__global__ void __launch_bounds__(kBlock, STB_MINB_DUAL) endpoint_dual_kernel(const KParams p)
+{
+    const long long rA = (long long)blockIdx.x * (2 * kBlock) + threadIdx.x, rB = rA + kBlock;
+    const int Lm1 = p.Lm1;
+
+    auto guard = [&](const DualRay &s) -> bool {       // sidtracemodule.c:36 on state s.i, exact (see trace_kernel)
+        const int ix = __double2int_rz(s.x), iy = __double2int_rz(s.y);
+        return (s.i < Lm1) & in_range(s.x, ix, p.nxm1) & in_range(s.y, iy, p.nym1);
+    };
+    auto cell_of = [&](const DualRay &s) -> int { return __double2int_rz(s.y) * p.csy + __double2int_rz(s.x) * p.csx; };
+    auto load = [&](long long r, DualRay &s) -> bool {
+        if (r >= p.nrays) return false;
+        s.x = p.x0[r]; s.y = p.y0[r]; s.kx = p.kx0[r]; s.ky = p.ky0[r]; s.i = 0;
+        if (!guard(s)) return false;
+        s.ind = cell_of(s);
+        return true;
+    };
+    auto cell = [&](int ind, double &tx, double &ty, double &sx, double &sy) {
+#ifdef STB_DIAG_FIXED_CELL     // timing diagnostic only (wrong results): every gather hits the same L1 line
+        ind &= 3;
+#endif
+        if (HOIST) {
+            const double4 h = ld_cell4<false>(&p.field4[ind]);
+            tx = h.x; ty = h.y; sx = h.z; sy = h.w;
+        } else {
+            const double2 m = ld_cell2<false>(&p.field[ind]);
+            tx = __dmul_rn(__dmul_rn(p.sst, m.x), 0.5); ty = __dmul_rn(__dmul_rn(p.sst, m.y), 0.5);
+            sx = __dmul_rn(p.st, m.x); sy = __dmul_rn(p.st, m.y);
+        }
+    };
+    // the exact step from the kept state s.i (the reference's loop body + guard): true when state i+1 is kept too
+    auto exact_step = [&](DualRay &s) -> bool {
+        double tx, ty, sx, sy;
+        cell(s.ind, tx, ty, sx, sy);
+        const double vx = __dadd_rn(tx, __dmul_rn(s.kx, p.st)), vy = __dadd_rn(ty, __dmul_rn(s.ky, p.st));
+        double wx, wy;
+        div_pair<DIVC>(vx, vy, p.dx, p.dy, p.rdx, p.rdy, wx, wy);
+        s.x = __dadd_rn(s.x, wx); s.y = __dadd_rn(s.y, wy);
+        s.kx = __dadd_rn(s.kx, sx); s.ky = __dadd_rn(s.ky, sy);
+        ++s.i;
+        if (!guard(s)) return false;
+        s.ind = cell_of(s);
+        return true;
+    };
+    auto exp_bits = [](double v) -> unsigned { return ((unsigned)__double2hiint(v) & 0x7ff00000u) - (623u << 20); };
+    auto quick_ok = [&](const DualRay &s, int ix, int iy) -> bool {
+        return ((unsigned)__double2hiint(s.x) < 0x7ff00000u) & ((unsigned)ix < (unsigned)p.nxm1)
+             & ((unsigned)__double2hiint(s.y) < 0x7ff00000u) & ((unsigned)iy < (unsigned)p.nym1) & (s.i < Lm1);
+    };
+    auto retire = [&](long long r, const DualRay &s) {
+        if (r >= p.nrays) return;
+        if (p.nsteps) p.nsteps[r] = s.i;
+        if (p.endst) {
+            p.endst[0 * p.nrays + r] = s.x; p.endst[1 * p.nrays + r] = s.y;
+            p.endst[2 * p.nrays + r] = s.kx; p.endst[3 * p.nrays + r] = s.ky;
+        }
+    };
+
+    DualRay a{}, b{};
+    bool la = load(rA, a), lb = load(rB, b);
+
+    // ---- both rays alive
+#pragma unroll 1
+    while (la & lb) {
+        double txa, tya, sxa, sya, txb, tyb, sxb, syb;
+        cell(a.ind, txa, tya, sxa, sya);
+        cell(b.ind, txb, tyb, sxb, syb);
+        const double vxa = __dadd_rn(txa, __dmul_rn(a.kx, p.st)), vya = __dadd_rn(tya, __dmul_rn(a.ky, p.st));
+        const double vxb = __dadd_rn(txb, __dmul_rn(b.kx, p.st)), vyb = __dadd_rn(tyb, __dmul_rn(b.ky, p.st));
+        if (DIVC && max(max(exp_bits(vxa), exp_bits(vya)), max(exp_bits(vxb), exp_bits(vyb))) > (800u << 20)) {
+            la = exact_step(a);                       // nothing committed yet: redo both exactly
+            lb = exact_step(b);
+            continue;
+        }
+        double wxa, wya, wxb, wyb;
+        if (DIVC) {
+            const double qxa = __dmul_rn(vxa, p.rdx), qya = __dmul_rn(vya, p.rdy), qxb = __dmul_rn(vxb, p.rdx), qyb = __dmul_rn(vyb, p.rdy);
+            const double exa = __fma_rn(-qxa, p.dx, vxa), eya = __fma_rn(-qya, p.dy, vya);
+            const double exb = __fma_rn(-qxb, p.dx, vxb), eyb = __fma_rn(-qyb, p.dy, vyb);
+            wxa = __fma_rn(exa, p.rdx, qxa); wya = __fma_rn(eya, p.rdy, qya);
+            wxb = __fma_rn(exb, p.rdx, qxb); wyb = __fma_rn(eyb, p.rdy, qyb);
+        } else {
+            wxa = __ddiv_rn(vxa, p.dx); wya = __ddiv_rn(vya, p.dy); wxb = __ddiv_rn(vxb, p.dx); wyb = __ddiv_rn(vyb, p.dy);
+        }
+        a.x = __dadd_rn(a.x, wxa); a.y = __dadd_rn(a.y, wya); a.kx = __dadd_rn(a.kx, sxa); a.ky = __dadd_rn(a.ky, sya); ++a.i;
+        b.x = __dadd_rn(b.x, wxb); b.y = __dadd_rn(b.y, wyb); b.kx = __dadd_rn(b.kx, sxb); b.ky = __dadd_rn(b.ky, syb); ++b.i;
+        const int ixa = __double2int_rz(a.x), iya = __double2int_rz(a.y), ixb = __double2int_rz(b.x), iyb = __double2int_rz(b.y);
+        a.ind = iya * p.csy + ixa * p.csx;
+        b.ind = iyb * p.csy + ixb * p.csx;
+        const bool oka = quick_ok(a, ixa, iya), okb = quick_ok(b, ixb, iyb);
+        if (oka & okb) continue;
+        la = oka || guard(a);                         // -0.0 passes the reference's `>= 0`
+        lb = okb || guard(b);
+    }
+    // ---- one ray left
+    if (la | lb) {
+        DualRay &s = la ? a : b;
+        bool alive = true;
+#pragma unroll 1
+        while (alive) {
+            double tx, ty, sx, sy;
+            cell(s.ind, tx, ty, sx, sy);
+            const double vx = __dadd_rn(tx, __dmul_rn(s.kx, p.st)), vy = __dadd_rn(ty, __dmul_rn(s.ky, p.st));
+            if (DIVC && max(exp_bits(vx), exp_bits(vy)) > (800u << 20)) { alive = exact_step(s); continue; }
+            double wx, wy;
+            if (DIVC) {
+                const double qx = __dmul_rn(vx, p.rdx), qy = __dmul_rn(vy, p.rdy);
+                const double ex = __fma_rn(-qx, p.dx, vx), ey = __fma_rn(-qy, p.dy, vy);
+                wx = __fma_rn(ex, p.rdx, qx); wy = __fma_rn(ey, p.rdy, qy);
+            } else {
+                wx = __ddiv_rn(vx, p.dx); wy = __ddiv_rn(vy, p.dy);
+            }
+            s.x = __dadd_rn(s.x, wx); s.y = __dadd_rn(s.y, wy); s.kx = __dadd_rn(s.kx, sx); s.ky = __dadd_rn(s.ky, sy); ++s.i;
+            const int ix = __double2int_rz(s.x), iy = __double2int_rz(s.y);
+            s.ind = iy * p.csy + ix * p.csx;
+            alive = quick_ok(s, ix, iy) || guard(s);
+        }
+    }
+    retire(rA, a);
+    retire(rB, b);
 }
 
 // {ax, ay} -> interleaved double2 per cell.  (A 2x4-cell blocked layout was measured and dropped:
