@@ -139,6 +139,48 @@ __global__ void k_step_fast_axis(const double4 *tab, int nxm1, int nym1, double 
     out[threadIdx.x] = x + y + kx + ky + sink; if (threadIdx.x == 0) { cyc[0] = t1 - t0; cyc[1] = i; }
 }
 
+// Does an FP64 instruction hold the scheduler's dispatch port for two cycles?  Every warp runs NF independent DFMA
+// chains and NS independent FFMA chains per iteration, 16 warps per scheduler.  If dispatch costs one cycle per
+// instruction whatever its pipe, an iteration takes max(2 NF, NF + NS) cycles per warp and scheduler (the FP64 pipe
+// is half rate); if an FP64 instruction blocks dispatch while it drains into its 16-lane pipe, 2 NF + NS.
+template <int NF, int NS>
+__global__ void __launch_bounds__(1024) k_mix(double *out, int iters, double a, double b, float fa, float fb)
+{
+    double d[NF > 0 ? NF : 1];
+    float f[NS > 0 ? NS : 1];
+#pragma unroll
+    for (int k = 0; k < NF; ++k) d[k] = threadIdx.x + k;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) f[k] = threadIdx.x + k;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < (NF > NS ? NF : NS); ++k) {
+            if (k < NF) d[k] = __fma_rn(d[k], a, b);
+            if (k < NS) f[k] = __fmaf_rn(f[k], fa, fb);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < NF; ++k) s += d[k];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) s += f[k];
+    if (s == 123.456) out[threadIdx.x] = s;
+}
+template <int NF, int NS>
+static void run_mix(double *out, int sms, double ghz)
+{
+    const int iters = 20000;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_mix<NF, NS><<<sms * 2, 1024>>>(out, 100, 1.0000001, 0.5, 1.0000001f, 0.5f);
+    cudaEventRecord(e0);
+    k_mix<NF, NS><<<sms * 2, 1024>>>(out, iters, 1.0000001, 0.5, 1.0000001f, 0.5f);
+    cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double cyc = ms * 1e-3 * ghz * 1e9 / (16.0 * iters);     // 64 warps/SM = 16 per scheduler
+    printf("%2d DFMA + %2d FFMA per iteration, 16 warps/scheduler: %6.1f cycles per warp-iteration "
+           "(one dispatch cycle each: %d; FP64 holds the port two: %d)\n", NF, NS, cyc, (2 * NF > NF + NS ? 2 * NF : NF + NS), 2 * NF + NS);
+}
+
 int main()
 {
     double *out; long long *cyc; int *iout;
@@ -190,6 +232,17 @@ int main()
         for (int rep = 0; rep < 3; ++rep) { k_step_fast_axis<3><<<1, 32>>>(d, nxm1, nym1, 0.9, 1.0, 1.0, out, cyc, 100000); CK(cudaDeviceSynchronize()); }
         printf("%-56s %8.1f cycles (%lld steps)\n", "  + prefetch.global.L1 of cell +4 (next line)", (double)cyc[0] / cyc[1], cyc[1]);
         cudaFree(d); free(h);
+    }
+    {
+        int sms = 0, khz = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+        const double ghz = khz * 1e-6;
+        run_mix<8, 0>(out, sms, ghz);
+        run_mix<0, 8>(out, sms, ghz);
+        run_mix<8, 8>(out, sms, ghz);
+        run_mix<4, 12>(out, sms, ghz);
+        run_mix<8, 16>(out, sms, ghz);
     }
     int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     printf("SM clock (attribute): %d kHz\n", clk);
