@@ -11,7 +11,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <cstdint>
 #include <cstdio>
+#include <mutex>
 
 extern "C" int stb_internal_fail(int code, const char *msg);
 extern "C" void stb_internal_count_launch(void);
@@ -30,6 +32,32 @@ int failf(int code, const char *what, cudaError_t e)
         cudaError_t e_ = (call);                                             \
         if (e_ != cudaSuccess) { rc = failf(e_ == cudaErrorMemoryAllocation ? STB_ERR_NOMEM : STB_ERR_CUDA, #call, e_); goto done; } \
     } while (0)
+
+// Scratch for the sort comes from a memory pool of the library's own whose release threshold is "never": the
+// device's default pool hands its memory back at every synchronisation, which made every plan pay 5-25 ms of
+// allocation for 0.2 ms of work (profiles/r02/plan_pool.txt).
+std::mutex g_pool_mu;
+cudaMemPool_t g_pool[64] = {};
+cudaError_t scratch_pool(cudaMemPool_t *out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_pool[dev]) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if ((e = cudaMemPoolCreate(&g_pool[dev], &props)) != cudaSuccess) return e;
+        uint64_t keep = UINT64_MAX;
+        if ((e = cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return e;
+    }
+    *out = g_pool[dev];
+    return cudaSuccess;
+}
 
 __global__ void iota_kernel(int *v, long long n)
 {
@@ -78,6 +106,7 @@ extern "C" int stb_traj_plan(const int32_t *nsteps, int64_t nrays, int32_t tile,
     int *keys_out = nullptr, *vals_in = nullptr, *vals_out = nullptr;
     long long *rows = nullptr;
     void *tmp = nullptr;
+    cudaMemPool_t pool = nullptr;
     size_t tmp_sort = 0, tmp_scan = 0, tmp_bytes = 0;
     long long total = 0;
     const int threads = 256;
@@ -86,11 +115,12 @@ extern "C" int stb_traj_plan(const int32_t *nsteps, int64_t nrays, int32_t tile,
     PCU(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_sort, nsteps, keys_out, vals_in, vals_out, (int)nrays, 0, end_bit, s));
     PCU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, rows, (long long *)tile_off, (int)(ntiles + 1), s));
     tmp_bytes = tmp_sort > tmp_scan ? tmp_sort : tmp_scan;
-    PCU(cudaMallocAsync((void **)&keys_out, (size_t)nrays * sizeof(int), s));
-    PCU(cudaMallocAsync((void **)&vals_in, (size_t)nrays * sizeof(int), s));
-    PCU(cudaMallocAsync((void **)&vals_out, (size_t)nrays * sizeof(int), s));
-    PCU(cudaMallocAsync((void **)&rows, (size_t)(ntiles + 1) * sizeof(long long), s));
-    PCU(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, s));
+    PCU(scratch_pool(&pool));
+    PCU(cudaMallocFromPoolAsync((void **)&keys_out, (size_t)nrays * sizeof(int), pool, s));
+    PCU(cudaMallocFromPoolAsync((void **)&vals_in, (size_t)nrays * sizeof(int), pool, s));
+    PCU(cudaMallocFromPoolAsync((void **)&vals_out, (size_t)nrays * sizeof(int), pool, s));
+    PCU(cudaMallocFromPoolAsync((void **)&rows, (size_t)(ntiles + 1) * sizeof(long long), pool, s));
+    PCU(cudaMallocFromPoolAsync(&tmp, tmp_bytes ? tmp_bytes : 16, pool, s));
 
     iota_kernel<<<blocks, threads, 0, s>>>(vals_in, nrays);
     stb_internal_count_launch();

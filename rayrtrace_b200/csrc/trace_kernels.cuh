@@ -372,7 +372,7 @@ trace_kernel(const KParams p)
     const double dg = axis_y ? p.dy : p.dx;
     double c0p = 0, g0 = 0, dcur = 0;
     int cidx = -1, ncross = 0, neq = 0;
-    bool below = false, above = false;
+    int sgn_or = 0, sgn_and = -1;   // OR / AND of the high words of every kept state's line offset: any below / any above the line
     // state n-1 = the last kept state, assigned once when the ray ends (retire() extrapolates from it)
     double pxg = 0, pyg = 0, pkx = 0, pky = 0, plax = 0, pph = 0;
     int pind = 0;
@@ -424,7 +424,7 @@ trace_kernel(const KParams p)
             c0p = axis_y ? p.y0p[r] : p.x0p[r];
             g0 = axis_y ? y : x;
             dcur = c0p - p.cross_val;            // c0p + (g0 - g0) * dg - val
-            cidx = -1; ncross = 0; neq = 0; below = above = false;
+            cidx = -1; ncross = 0; neq = 0; sgn_or = 0; sgn_and = -1;
             if (LOOKUP) {
                 x0p = p.x0p[r]; y0p = p.y0p[r]; xg0 = x; yg0 = y;
                 cx = cy = clax = cph = qnan;
@@ -501,7 +501,10 @@ trace_kernel(const KParams p)
             int count = 0, flags = 0;
             if (neq > 0) {                              // ray.py:142-143: exact hit(s), nothing inserted
                 count = neq; flags = 1;
-            } else if (below && above) {                // ray.py:144-146
+            } else if (sgn_or < 0 && sgn_and >= 0) {    // kept states on both sides of the line, ray.py:144-146.  (A zero
+                                                        // offset would count for its sign bit's side -- but then neq > 0
+                                                        // and the branch above was taken; NaN offsets find no crossing
+                                                        // on either path.)
                 count = cidx >= 0 ? ncross : 0;
             } else if (i >= 1) {                        // ray.py:147-148: heading for the line past the end
                 const double cl = c0p + ((axis_y ? pyg : pxg) - g0) * dg;
@@ -600,16 +603,11 @@ trace_kernel(const KParams p)
 
         if (CROSS) {
             // state i is kept; lax, ph are its running sums; dcur = its receiver coordinate - val
-            if (dcur == 0.0) {                         // ray.py:142-143: an existing point lies on the line
-                if (neq == 0) {
-                    cidx = i;
-                    const CrossCtx c{p.field, p.x0p, p.y0p, p.x0, p.y0, p.cross_state, p.nrays, p.dx, p.dy, p.cross_val, axis_y};
-                    cross_exact_hit(c, ray, x, y, kx, ky, lax, ph);
-                }
-                ++neq;
-            }
-            below |= dcur < 0.0;
-            above |= dcur > 0.0;
+            // (the exact-hit test `dcur == 0` of ray.py:142-143 moved behind the product test at the bottom of the
+            // step: one DMUL + one DSETP per step cover it together with the sign change; an FP64 compare costs
+            // two dispatch cycles, and these passes are dispatch-bound)
+            sgn_or |= __double2hiint(dcur);
+            sgn_and &= __double2hiint(dcur);
             if (LOOKUP) {
                 // the polyline Beam.field_r sees after addpoint: kept states plus the inserted crossing
                 // point, phase recomputed (ray.py:205-216, 122-126).  Before the insertion its sums equal
@@ -646,7 +644,7 @@ trace_kernel(const KParams p)
         const double ky1 = __dadd_rn(ky, HOIST ? h.w : __dmul_rn(st, m.y));     // :45
 
         if (EXTRAS) {
-            if (turn < 0 && ((ky > 0.0 && ky1 <= 0.0) || (ky < 0.0 && ky1 >= 0.0))) {
+            if (!(ky * ky1 > 0.0) && turn < 0 && ((ky > 0.0 && ky1 <= 0.0) || (ky < 0.0 && ky1 >= 0.0))) {
                 turn = i + 1;
                 if (p.turn_state) {
                     p.turn_state[0 * p.nrays + ray] = x1;  p.turn_state[1 * p.nrays + ray] = y1;
@@ -662,13 +660,23 @@ trace_kernel(const KParams p)
         const bool ok1 = guard(x1, y1, i + 1, ind1);              // :36 on state i+1
         if (CROSS) {
             const double d1 = (c0p + ((axis_y ? y1 : x1) - g0) * dg) - p.cross_val;
-            // a sign change between two KEPT states (ray.py:144-146); the first one is solved for
-            if (ok1 && dcur * d1 < 0.0) {
-                if (ncross == 0 && neq == 0) {
-                    const bool got = capture(x, y, kx, ky, ind, lax, ph, st, i + 1);
-                    if (LOOKUP) cap_seg = got;
+            if (!(dcur * d1 > 0.0)) {                      // rare: a zero offset, a sign change, an underflowed or NaN product
+                if (dcur == 0.0) {                         // ray.py:142-143: the kept state i lies on the line
+                    if (neq == 0) {
+                        cidx = i;
+                        const CrossCtx c{p.field, p.x0p, p.y0p, p.x0, p.y0, p.cross_state, p.nrays, p.dx, p.dy, p.cross_val, axis_y};
+                        cross_exact_hit(c, ray, x, y, kx, ky, lax, ph);
+                    }
+                    ++neq;
                 }
-                ++ncross;
+                // a sign change between two KEPT states (ray.py:144-146); the first one is solved for
+                if (ok1 && dcur * d1 < 0.0) {
+                    if (ncross == 0 && neq == 0) {
+                        const bool got = capture(x, y, kx, ky, ind, lax, ph, st, i + 1);
+                        if (LOOKUP) cap_seg = got;
+                    }
+                    ++ncross;
+                }
             }
             dcur = d1;
         }
@@ -764,7 +772,15 @@ trace_kernel(const KParams p)
                         if (why == 1 || (why == 0 && !step())) break;
                     }
                 } else {
-                    while (step()) { }
+                    // the fused-sum and histogram passes gain 4 % / 1.5 % from a loop unrolled by two (ptxas then
+                    // rotates the state registers instead of copying them); trajectories, crossing and lookup lose
+                    // 3-4 % (profiles/r02/crossopt_unr2.txt)
+                    if (EXTRAS && !CROSS && !TRAJ) {
+#pragma unroll 2
+                        while (step()) { }
+                    } else {
+                        while (step()) { }
+                    }
                 }
             }
             if (TILED) __syncwarp();

@@ -107,3 +107,16 @@ def test_coherent_order_groups_neighbouring_rays():
     rnd = ((x0[1:] - x0[:-1]).abs() / 10 + (th[1:] - th[:-1]).abs() / 0.6)[torch.isfinite(x0[1:]) & torch.isfinite(x0[:-1])]
     assert jump.median() < 0.05 * rnd.median()
 
+
+
+def test_pick_cells_follows_the_launch_directions():
+    """sidtrace.pick_cells (host logic, no device): the cell-table layout follows the rays -- y-major when the
+    launch wave vectors point mostly along y, the reference's x-major rows (sidtracemodule.c:38) otherwise."""
+    from rayrtrace_b200 import sidtrace
+    rng = np.random.default_rng(3)
+    ang = rng.uniform(-0.4, 0.4, 100_000)
+    assert sidtrace.pick_cells(np.sin(ang), np.cos(ang)) == "y"          # a fan shooting upwards (the FT-2 antennas)
+    assert sidtrace.pick_cells(np.cos(ang), np.sin(ang)) == "x"
+    assert sidtrace.pick_cells(-np.sin(ang), -np.cos(ang)) == "y"        # downwards counts the same
+    assert sidtrace.pick_cells(np.empty(0), np.empty(0)) == "x"
+    assert sidtrace.pick_cells(np.array([1.0]), np.array([1.0])) == "x"  # a tie keeps the reference layout
