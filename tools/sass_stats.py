@@ -44,7 +44,8 @@ FP64 = ("DMUL", "DADD", "DFMA", "DSETP", "DMNMX")
 
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    name = mangled(args)
+    # a mangled name may be given directly (e.g. _ZN3stb20endpoint_dual_kernelILb1ELb1EEEvNS_7KParamsE)
+    name = args[0] if len(args) == 1 and args[0].startswith("_Z") else mangled(args)
     ins = disasm(name)
     if not ins:
         sys.exit(f"{name}: not found in {LIB}")
