@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--no-traj-export", action="store_true", help="skip the trajectories-to-host side measurement")
     ap.add_argument("--no-config5", action="store_true", help="skip the sharded config-5 block")
     ap.add_argument("--config5-rays", type=int, default=12_500_000, help="config-5 rays per GPU (10^8 / 8)")
+    ap.add_argument("--config5-chunks", type=int, default=8, help="config-5: pieces a shard is traced in (the exchange of a piece "
+                    "hides under the trace of the next; only the last one is exposed)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed trajectory digest against the oracle")
     ap.add_argument("--no-app", action="store_true", help="skip the application-level (ft2.phases) block")
     ap.add_argument("--layout", default="tiled", choices=["tiled", "ray"],
@@ -339,7 +341,7 @@ def run_config5(args, rank, world, local_rank, dev, comm):
     def one():
         # static grid: a clean beam has no stragglers, and CTAs that retire let the exchange kernels in
         return rd.trace_sharded(field, None, staged=staged, nbins=nbins, hist_kw=hist_kw, gather="root", comm=comm,
-                                chunks=4, refill=False, timing=True, **kw)
+                                chunks=args.config5_chunks, refill=False, timing=True, **kw)
 
     for _ in range(2):
         res, hist, gathered, tm = one()
@@ -380,7 +382,8 @@ def run_config5(args, rank, world, local_rank, dev, comm):
             "workload": f"config5: {n_global}-ray seven-beam fan on a 201x201 grid sharded over {world} GPU(s) "
                         f"({args.config5_rays} rays each, 256-ray blocks round-robin), endpoints + {nbins}-bin deposition "
                         f"histogram; NCCL all-reduce of the histogram; step counts + end states of ALL rays gathered in "
-                        f"global ray order on rank 0 (36 B/ray), exchange of chunk k under the trace of chunk k+1",
+                        f"global ray order on rank 0 (36 B/ray), {args.config5_chunks} chunks, exchange of chunk k under the trace "
+                        f"of chunk k+1",
             "value": float(work.item()) / (ms_pass * 1e-3), "unit": UNIT, "ms_per_step": ms_pass, "steps": reps,
             "ray_steps_per_step": float(work.item()), "kernel_ms": ms_kernel, "exchange_exposed_ms": ms_exposed,
             "exchange_frac_of_pass": ms_exposed / ms_total if ms_total else None,

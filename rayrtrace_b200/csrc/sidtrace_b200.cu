@@ -266,7 +266,7 @@ int launch_one(const KParams &p0, const LaunchCtx &c)
             return STB_OK;
         }
     }
-    const size_t smem = HIST ? (size_t)p0.nbins * sizeof(double) : 0;
+    const size_t smem = HIST ? (size_t)p0.nbins * sizeof(double) * (p0.hist_table ? 3 : 1) : 0;
     if (p0.nrays <= 0) return STB_OK;
     // step counts / end states only, static grid: two rays per thread (endpoint_dual_kernel)
     if constexpr (!TRAJ && !EXTRAS && !HIST && !TILED && !CROSS && !STRAY) {
@@ -521,6 +521,7 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     // the square root and both divisions of the flux label whenever the ray is still inside its bin; it
     // pays off as soon as a bin is about one step wide (failing it costs 2 of ~60 instructions)
     p.hist_annulus = b->hist && p.hist_dr >= 1.0 * std::fmin(std::fabs(b->dx), std::fabs(b->dy));
+    p.hist_table = p.hist_annulus && b->nbins <= 2048;        // 3 x 16 KB of shared memory per CTA at most
     p.counter = nullptr;                 // assigned per persistent launch (launch_one)
     p.cross_axis = b->cross_axis; p.cross_val = b->cross_val;
     p.x0p = b->x0_phys; p.y0p = b->y0_phys;

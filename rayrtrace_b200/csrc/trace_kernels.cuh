@@ -83,7 +83,8 @@ struct KParams {
     double xorg, yorg, r_lcs, rho_max;
     double r_rlcs, r_rhomax;             // RN(1/r_lcs), RN(1/rho_max) for the constant-divisor quotients
     double hist_dr;                      // radial bin width in cm
-    int hist_annulus;                    // bins span >= 4 steps: use the squared-radius annulus test
+    int hist_annulus;                    // bins at least a step wide: use the squared-radius annulus test
+    int hist_table;                      // ... and keep every bin's (shrunk) squared-radius bounds in shared memory
     unsigned long long *counter;         // ray queue head (refill schedule)
     // receiver-line crossing (CROSS)
     int cross_axis;                      // 1: y = cross_val, 2: x = cross_val (physical cm)
@@ -242,20 +243,28 @@ __device__ __forceinline__ double kmod(double kx, double ky)
     return __dsqrt_rn(__dadd_rn(__dmul_rn(kx, kx), __dmul_rn(ky, ky)));
 }
 
-// Adds w to shared-memory bin b for every active lane; lanes of the warp that
-// hit the same bin are combined first (match.any) so each distinct bin costs
-// one shared atomic per warp-step.
+// Adds w to shared-memory bin b for every active lane; lanes of the warp that hit the same bin are combined
+// first (match.any) so each distinct bin costs one shared atomic per warp-flush.  The peers' values are summed
+// in log2(peers) rounds (every round each remaining peer takes the value of the next remaining one, then every
+// second peer drops out) -- neighbouring rays change bin together, so the usual group is the whole warp: 5
+// rounds instead of the 32 sequential shuffles of round 1's lane-order loop.  Deterministic for a given set of
+// active lanes (a fixed tree).
 __device__ __forceinline__ void hist_add(double *sh, int b, double w)
 {
-    const unsigned peers = __match_any_sync(__activemask(), b);
+    const unsigned active = __activemask();
+    unsigned peers = __match_any_sync(active, b);
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(peers) - 1;
-    double sum = 0.0;
-    // fixed lane order: deterministic within the warp
-    for (unsigned m = peers; m; m &= m - 1) {
-        const int src = __ffs(m) - 1;
-        const double v = __shfl_sync(peers, w, src);
-        sum = __dadd_rn(sum, v);
+    int rel = __popc(peers & ((1u << lane) - 1u));          // my rank among my peers
+    peers &= 0xfffffffeu << lane;                           // peers above me
+    double sum = w;
+    while (__any_sync(active, peers != 0)) {
+        const int next = __ffs(peers);                      // 1 + lane of the next remaining peer above me, 0 = none
+        const double t = __shfl_sync(active, sum, next ? next - 1 : lane);
+        if (next) sum = __dadd_rn(sum, t);
+        const bool done = rel & 1;                          // odd ranks have handed their value down: they drop out
+        peers &= __ballot_sync(active, !done);
+        rel >>= 1;
     }
     if (lane == leader && b >= 0) atomicAdd(&sh[b], sum);
 }
@@ -341,8 +350,19 @@ __global__ void __launch_bounds__(BLOCK, CROSS ? STB_MINB_CROSS : (HIST || EXTRA
 trace_kernel(const KParams p)
 {
     extern __shared__ double sh_hist[];
+    // HIST with hist_table: sh_lo[b], sh_hi[b] = the squared physical radii between which a point is certainly in
+    // bin b (the bin's edges shrunk by 1e-12, far more than the rounding of the exact formula) -- the same
+    // expressions the per-lane annulus below uses
+    double *sh_lo = sh_hist + p.nbins, *sh_hi = sh_hist + 2 * p.nbins;
     if (HIST) {
-        for (int b = threadIdx.x; b < p.nbins; b += BLOCK) sh_hist[b] = 0.0;
+        for (int b = threadIdx.x; b < p.nbins; b += BLOCK) {
+            sh_hist[b] = 0.0;
+            if (p.hist_table) {
+                const double a = p.hist_dr * (double)b, b2 = p.hist_dr * (double)(b + 1);
+                sh_lo[b] = a * a * (1.0 + 1e-12);
+                sh_hi[b] = b2 * b2 * (1.0 - 1e-12);
+            }
+        }
         __syncthreads();
     }
 
@@ -571,11 +591,29 @@ trace_kernel(const KParams p)
                 const double yp = __dadd_rn(p.yorg, __dmul_rn(y, p.dy));
                 const double r2 = __dadd_rn(__dmul_rn(xp, xp), __dmul_rn(yp, yp));
                 if (!p.hist_annulus || !(r2 > r2lo && r2 < r2hi)) {
-                    const double rho = div_const<DIVC>(__dsqrt_rn(r2), p.r_lcs, p.r_rlcs);
+                    // a ray that leaves its bin is almost always in one of the two neighbouring bins: their
+                    // certain-annuli come from shared memory (two loads + two compares each) before the exact
+                    // label (square root, two exact quotients, conversion) is computed at all
                     int bnew = -1;
-                    if (rho < p.rho_max) {
-                        const int b = __double2int_rz(div_const<DIVC>(__dmul_rn(rho, (double)p.nbins), p.rho_max, p.r_rhomax));
-                        if (b >= 0 && b < p.nbins) bnew = b;
+                    bool known = false;
+                    if (p.hist_table && binprev >= 0) {
+                        const int bu = binprev + 1, bd = binprev - 1;
+                        if (bu < p.nbins) {
+                            const double lo = sh_lo[bu], hi = sh_hi[bu];
+                            if (r2 > lo && r2 < hi) { bnew = bu; r2lo = lo; r2hi = hi; known = true; }
+                        }
+                        if (!known && bd >= 0) {
+                            const double lo = sh_lo[bd], hi = sh_hi[bd];
+                            if (r2 > lo && r2 < hi) { bnew = bd; r2lo = lo; r2hi = hi; known = true; }
+                        }
+                    }
+                    double rho = 0.0;
+                    if (!known) {
+                        rho = div_const<DIVC>(__dsqrt_rn(r2), p.r_lcs, p.r_rlcs);
+                        if (rho < p.rho_max) {
+                            const int b = __double2int_rz(div_const<DIVC>(__dmul_rn(rho, (double)p.nbins), p.rho_max, p.r_rhomax));
+                            if (b >= 0 && b < p.nbins) bnew = b;
+                        }
                     }
                     if (bnew != binprev) {
                         if (binacc != 0.0) hist_add(sh_hist, binprev, binacc);
@@ -584,7 +622,9 @@ trace_kernel(const KParams p)
                     }
                     // annulus of the bin just found, in squared physical radius
                     const double dr = p.hist_dr;
-                    if (!p.hist_annulus) {
+                    if (known) {
+                        // bounds already taken from the table
+                    } else if (!p.hist_annulus) {
                         // bins narrower than a step: the test would fail most of the time
                     } else if (bnew >= 0) {
                         const double a = dr * (double)bnew, b2 = dr * (double)(bnew + 1);
