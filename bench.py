@@ -361,11 +361,17 @@ def run_config5(args, rank, world, local_rank, dev, comm):
     torch.cuda.synchronize()
     parts = np.array([[t.ms()[k] for k in ("kernel_ms", "total_ms", "exchange_exposed_ms")] for t in tms]).mean(0)
     v = torch.tensor([e0.elapsed_time(e1) / reps, parts[0], parts[1], parts[2]], dtype=torch.float64, device=dev)
+    vmin = v.clone()
     work = res.nsteps.sum().to(torch.float64).reshape(1)
     if world > 1:
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        dist.all_reduce(vmin, op=dist.ReduceOp.MIN)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    ms_pass, ms_kernel, ms_total, ms_exposed = (float(x) for x in v.tolist())
+    ms_pass, ms_kernel, ms_total, ms_wait = (float(x) for x in v.tolist())
+    ms_kernel_min = float(vmin[1])
+    # what the exchange adds to the pass = what is left after the SLOWEST rank's last trace kernel has finished
+    # (a rank that finishes tracing early waits for that rank in the all-reduce: that wait is load skew, not exchange)
+    ms_exposed = max(ms_pass - ms_kernel, 0.0)
     out = None
     if rank == 0:
         # spot check of the gathered result (untimed): 4096 global rays, their step counts and end states
@@ -385,8 +391,12 @@ def run_config5(args, rank, world, local_rank, dev, comm):
                         f"global ray order on rank 0 (36 B/ray), {args.config5_chunks} chunks, exchange of chunk k under the trace "
                         f"of chunk k+1",
             "value": float(work.item()) / (ms_pass * 1e-3), "unit": UNIT, "ms_per_step": ms_pass, "steps": reps,
-            "ray_steps_per_step": float(work.item()), "kernel_ms": ms_kernel, "exchange_exposed_ms": ms_exposed,
-            "exchange_frac_of_pass": ms_exposed / ms_total if ms_total else None,
+            "ray_steps_per_step": float(work.item()), "kernel_ms": ms_kernel, "kernel_ms_fastest_rank": ms_kernel_min,
+            "exchange_exposed_ms": ms_exposed, "exchange_frac_of_pass": ms_exposed / ms_pass if ms_pass else None,
+            "wait_after_own_trace_ms_max_rank": ms_wait,
+            "note": "kernel_ms = the slowest rank's trace (the root: NCCL's receive and the unshuffle kernels of earlier chunks share "
+                    "its SMs); exchange_exposed_ms = pass - kernel_ms, the exchange left on the critical path; the wait of the "
+                    "fastest rank for the slowest one in the all-reduce is load skew, reported separately",
             "gathered_bytes_on_root": int(n_global) * 36, "hist_sum": float(hist.sum().item()),
             "transport": "stb_comm_* (NCCL via the C ABI)" if comm is not None else "single rank: no exchange",
             "gathered_spot_check": {"result": "ok" if same else "MISMATCH", "rays": int(len(sel)),

@@ -252,8 +252,22 @@ __device__ __forceinline__ double kmod(double kx, double ky)
 __device__ __forceinline__ void hist_add(double *sh, int b, double w)
 {
     const unsigned active = __activemask();
-    unsigned peers = __match_any_sync(active, b);
     const int lane = threadIdx.x & 31;
+#ifndef STB_HIST_NO_BUTTERFLY
+    if (active == 0xffffffffu) {
+        // the whole warp flushes, and (neighbouring rays) usually into one bin: xor butterfly, one atomic
+        int same;
+        __match_all_sync(active, b, &same);
+        if (same) {
+            double sum = w;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum = __dadd_rn(sum, __shfl_xor_sync(active, sum, o));
+            if (lane == 0 && b >= 0) atomicAdd(&sh[b], sum);
+            return;
+        }
+    }
+#endif
+    unsigned peers = __match_any_sync(active, b);
     const int leader = __ffs(peers) - 1;
     int rel = __popc(peers & ((1u << lane) - 1u));          // my rank among my peers
     peers &= 0xfffffffeu << lane;                           // peers above me
