@@ -292,6 +292,14 @@ def trace_sharded(field, launch, *, L, st, dx, dy, amp=None, nbins=0, hist_kw=No
         rbuf_e = torch.empty((world, 4, cnp), dtype=torch.float64, device=dev)
     xs = _exchange_stream(dev)
     lib = _cabi.lib
+    # the chunks are traced on two alternating side streams: chunk c+1's CTAs fill the SMs while chunk c's last
+    # wave drains, instead of every chunk paying its own tail in stream order (they write disjoint outputs and
+    # add to the histogram with atomics)
+    ts = _trace_streams(dev)
+    ev0 = torch.cuda.Event()
+    ev0.record(main)
+    for t in ts:
+        t.wait_event(ev0)
     for c in range(nchunks):
         lo = c * cnp
         hi = min(lo + cnp, n_loc)
@@ -303,12 +311,15 @@ def trace_sharded(field, launch, *, L, st, dx, dy, amp=None, nbins=0, hist_kw=No
             full = hi - lo == cnp
             e_c = end_loc[c] if full else torch.empty((4, hi - lo), dtype=torch.float64, device=dev)
             out.end_state = e_c
-            sidtrace.trace_batch(field, *[a[lo:hi] for a in d_in], L=L, st=st, dx=dx, dy=dy,
-                                 amp=d_amp[lo:hi] if d_amp is not None else None, hist=hist, out=out, **hkw, **kw)
-            if not full:
-                end_loc[c][:, :hi - lo].copy_(e_c)
+            with torch.cuda.stream(ts[c % 2]):
+                sidtrace.trace_batch(field, *[a[lo:hi] for a in d_in], L=L, st=st, dx=dx, dy=dy,
+                                     amp=d_amp[lo:hi] if d_amp is not None else None, hist=hist, out=out, **hkw, **kw)
+                if not full:
+                    end_loc[c][:, :hi - lo].copy_(e_c)
         ev = torch.cuda.Event()
-        ev.record(main)
+        ev.record(ts[c % 2])
+        if c >= nchunks - 2:
+            main.wait_event(ev)                           # main resumes after the last chunk of either stream
         if tm and c == nchunks - 1:
             tm.traced.record(main)
         xs.wait_event(ev)
@@ -337,6 +348,18 @@ def trace_sharded(field, launch, *, L, st, dx, dy, amp=None, nbins=0, hist_kw=No
 
 
 _xstreams: dict = {}
+_tstreams: dict = {}
+
+
+def _trace_streams(dev):
+    """Two side streams per device for the chunk traces of ``trace_sharded``."""
+    import torch
+    key = (dev.type, dev.index)
+    s = _tstreams.get(key)
+    if s is None:
+        s = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        _tstreams[key] = s
+    return s
 
 
 def _exchange_stream(dev):
