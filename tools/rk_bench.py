@@ -34,7 +34,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nrays", type=int, default=1_000_000)
     ap.add_argument("--nx", type=int, default=1001)
-    ap.add_argument("--mode", default="O")
+    ap.add_argument("--mode", default="O", help="O, X (analytic 1/R field) or XT (X mode, |B| from a tabulated Solov'ev equilibrium)")
     ap.add_argument("--interp", default="bspline")
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--absorb", action="store_true")
@@ -51,7 +51,9 @@ def main():
     from rayrtrace_b200 import physics as ph
     torch.cuda.set_device(0)
     xs, X, alpha = medium_tables(args.nx, args.absorb)
-    med = ph.Medium(X, xs, xs, alpha=alpha, mode=args.mode, Y0=0.45, R0=55.0, interp=args.interp)
+    eq = ph.Equilibrium.solovev(kappa=1.2, psi_b=6e-3, nr=129, nz=129, half=0.12) if args.mode == "XT" else None
+    med = ph.Medium(X, xs, xs, alpha=alpha, mode="X" if args.mode == "XT" else args.mode, Y0=0.45, R0=55.0, interp=args.interp,
+                    equilibrium=eq, freq=137.5e9 if eq else None)
     n = args.nrays
     g = torch.Generator(device="cuda").manual_seed(0)
     x0 = (torch.rand(n, generator=g, dtype=torch.float64, device="cuda") - 0.5) * 10
@@ -82,7 +84,7 @@ def main():
     acc, rej = int(res.nacc.sum()), int(res.nrej.sum())
     attempts = acc + rej
     line = {
-        "kernel": f"stbrk::rk_kernel<{ph.INTERP[args.interp]},{int(args.mode == 'X')},{int(args.absorb)}>",
+        "kernel": f"stbrk::rk_kernel<{ph.INTERP[args.interp]},{dict(O=0, X=1, XT=2)[args.mode]},{int(args.absorb)}>",
         "workload": f"{n} rays, {args.nx}^2 {args.interp} medium, {args.mode} mode, rtol {args.rtol:g}"
                     + (", absorption + 64-bin deposition" if args.absorb else "")
                     + (", shuffled launch order" if args.shuffled else ", rays ordered along the launch line")
@@ -97,8 +99,13 @@ def main():
     if not args.no_cpu:
         from oracle import rk
         m = min(args.cpu_rays, n)
+        y2 = None
+        if eq is not None:
+            y2 = rk.equilibrium_y2(dict(psi=eq.psi, fpol=eq.fpol, rleft=eq.rleft, rdim=eq.rdim, zmid=eq.zmid, zdim=eq.zdim,
+                                        simagx=eq.simagx, sibdry=eq.sibdry, r0_cm=55.0, z0_cm=0.0,
+                                        y_per_tesla=ph.ELECTRON_CYCLOTRON_HZ_PER_T / 137.5e9), args.nx, args.nx, med.xorg, med.yorg, med.dx, med.dy)
         om = rk.Medium(X, med.xorg, med.yorg, med.dx, med.dy, alpha=alpha, mode=args.mode, Y0=0.45, R0=55.0,
-                       interp=ph.INTERP[args.interp])
+                       interp=ph.INTERP[args.interp], Y2=y2)
         h = [a[:m].cpu().numpy() for a in (x0, y0, px, py)]
         cores = os.cpu_count() or 1
         ckw = dict(kw, h0=0.5 * min(med.dx, med.dy), threads=cores)
