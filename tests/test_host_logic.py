@@ -84,6 +84,36 @@ def test_rk_medium_argument_validation_needs_no_device():
         physics.Medium(X, x, x, alpha=np.zeros((3, 3)))
     with pytest.raises(ValueError, match="2 x 2"):
         physics.Medium(np.zeros((1, 9)), x, x[:1])
+    # the tabulated-field X mode (STB_RK_MODE_X_TABLE)
+    eq = physics.Equilibrium.solovev(nr=9, nz=9, nf=5)
+    with pytest.raises(ValueError):
+        physics.Medium(X, x, x, mode="O", Y2=np.zeros_like(X))           # a field table belongs to the X mode
+    with pytest.raises(ValueError):
+        physics.Medium(X, x, x, mode="X", Y2=np.zeros_like(X), equilibrium=eq, freq=60e9)
+    with pytest.raises(ValueError):
+        physics.Medium(X, x, x, mode="X", equilibrium=eq)                # Y = f_ce / freq needs the frequency
+    with pytest.raises(ValueError):
+        physics.Medium(X, x, x, mode="X", Y2=np.zeros((3, 3)))
+
+
+def test_solovev_equilibrium_tables():
+    """physics.Equilibrium.solovev: psi = 0 on the axis, ~psi_b on the midplane at R0 + a, and the analytic field is
+    -psi_Z/R, psi_R/R of the table (centred differences) with F = B0 R0."""
+    from rayrtrace_b200 import physics
+    eq = physics.Equilibrium.solovev(R0=0.55, a=0.08, kappa=1.3, psi_b=2e-3, nr=201, nz=201)
+    R = np.linspace(eq.rleft, eq.rleft + eq.rdim, eq.nx)
+    Z = np.linspace(eq.zmid - eq.zdim / 2, eq.zmid + eq.zdim / 2, eq.ny)
+    i0, j0 = np.argmin(abs(R - 0.55)), np.argmin(abs(Z))
+    assert abs(eq.psi[i0, j0]) < 1e-12 and eq.psi.min() >= 0
+    assert abs(eq.psi[np.argmin(abs(R - 0.63)), j0] / 2e-3 - 1) < 0.2
+    dR, dZ = R[1] - R[0], Z[1] - Z[0]
+    pR = (eq.psi[2:, 1:-1] - eq.psi[:-2, 1:-1]) / (2 * dR)
+    pZ = (eq.psi[1:-1, 2:] - eq.psi[1:-1, :-2]) / (2 * dZ)
+    RR, ZZ = np.meshgrid(R[1:-1], Z[1:-1], indexing="ij")
+    BR, BZ, Bp = eq.analytic_B(RR, ZZ)
+    assert np.max(np.abs(BR + pZ / RR)) < 1e-3 * np.max(np.abs(BR))
+    assert np.max(np.abs(BZ - pR / RR)) < 1e-3 * np.max(np.abs(BZ))
+    assert np.allclose(Bp * RR, 2.2 * 0.55)
 
 
 def test_coherent_order_groups_neighbouring_rays():
