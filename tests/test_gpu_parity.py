@@ -1306,3 +1306,38 @@ def test_gpu_tail_equals_host_tail_on_a_folded_many_page_beam(st, torch_mod):
     if host[5] is not None:
         np.testing.assert_allclose(gpu[5], host[5], rtol=1e-6)
         assert float(gpu[3]) == pytest.approx(float(host[3]), rel=1e-8)
+
+
+@pytest.mark.parametrize("world,rows,elem,n_global,stride_pad", [(8, 4, 8, 256 * 37 + 101, 0), (8, 1, 4, 256 * 37 + 101, 0), (3, 4, 8, 256 * 10, 3),
+                                                                  (2, 1, 4, 256 * 5 + 1, 1), (5, 2, 8, 7, 0)])
+def test_unshuffle_blocks_on_one_gpu(st, torch_mod, world, rows, elem, n_global, stride_pad):
+    """stb_unshuffle_blocks (gathered shards -> global ray order) needs no communicator: gathered buffers are made on
+    one GPU and the result compared with the index map written out in NumPy -- whole runs (the 16-byte vector
+    kernel), an odd destination stride (the element-wise fallback), a partial last block, a chunk offset g0."""
+    import ctypes
+    from rayrtrace_b200 import _cabi
+    B = 256
+    nb = -(-n_global // B)
+    lblocks = -(-nb // world)
+    dt, tdt = (np.float64, torch_mod.float64) if elem == 8 else (np.int32, torch_mod.int32)
+    rng = np.random.default_rng(world * 100 + rows)
+    src = rng.integers(-2 ** 30, 2 ** 30, (world, rows, lblocks * B)).astype(dt)
+    for chunk_lo, chunk_n in ((0, lblocks), (1, max(lblocks - 1, 0))):         # the whole shard; a chunk that starts at local block 1
+        if chunk_n == 0:
+            continue
+        stride = n_global + stride_pad
+        dst = torch_mod.full((rows, stride), -7, dtype=tdt, device="cuda")
+        part = np.ascontiguousarray(src[:, :, chunk_lo * B:(chunk_lo + chunk_n) * B])
+        d_src = torch_mod.from_numpy(part).cuda()
+        g0 = chunk_lo * world * B
+        _cabi.check(_cabi.lib.stb_unshuffle_blocks(d_src.data_ptr(), dst.data_ptr(), world, rows, chunk_n, B, elem, g0, n_global,
+                                                   stride, ctypes.c_void_p(torch_mod.cuda.current_stream().cuda_stream)))
+        torch_mod.cuda.synchronize()
+        want = np.full((rows, stride), -7, dtype=dt)
+        for r in range(world):
+            for lb in range(chunk_n):
+                g = g0 + (lb * world + r) * B
+                m = min(B, n_global - g)
+                if m > 0:
+                    want[:, g:g + m] = part[r, :, lb * B:lb * B + m]
+        assert np.array_equal(dst.cpu().numpy(), want)
