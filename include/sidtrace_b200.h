@@ -166,7 +166,12 @@ typedef struct stb_batch_s {
      * L rows per tile): the plan stb_traj_plan made from the step counts of a first pass.  Slot s of
      * the plan holds ray traj_perm[s] (-1: empty); tile t = slots [t*T, (t+1)*T) owns rows
      * traj_tile_off[t] .. traj_tile_off[t+1] of T x 4 doubles; state j of the ray in slot s is at
-     * traj[((traj_tile_off[s/T] + j)*T + s%T)*4].  No ray steps past the rows of its tile. */
+     * traj[((traj_tile_off[s/T] + j)*T + s%T)*4].  No ray steps past the rows of its tile.
+     * traj_perm WITHOUT traj_tile_off (any flags, device I/O): the ORDER the rays are traced in -- slot s is ray
+     * traj_perm[s] (-1: empty), traj_nslots >= nrays slots.  For launch sets that arrive in random order (sweeps):
+     * sorted by launch cell the lanes of a warp gather from the same few cells.  Per-ray outputs and ray-major
+     * trajectories are written at the ray's own index; tiled trajectories are laid out by SLOT
+     * (traj_nslots = ceil(nrays/T)*T). */
     const int32_t *traj_perm;      /* [traj_nslots]                                              */
     const int64_t *traj_tile_off;  /* [traj_nslots/T + 1]                                        */
     int64_t  traj_nslots;          /* ceil(nrays/T)*T                                            */

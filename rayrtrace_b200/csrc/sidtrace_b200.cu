@@ -258,7 +258,7 @@ int launch_one(const KParams &p0, const LaunchCtx &c)
     // static tiled trajectories over 256-ray tiles: 256-thread CTAs, one 8 KB row per CTA-step
     if constexpr (TRAJ && TILED && !EXTRAS && !HIST && !CROSS && !STRAY) {
         if (!c.refill && p0.tile == 256 && p0.nrays > 0) {
-            const long long blocks = (p0.nrays + 255) / 256;
+            const long long blocks = ((p0.perm ? p0.nslots : p0.nrays) + 255) / 256;
             if (blocks > 0x7fffffffLL) return fail(STB_ERR_ARG, "too many rays for a static grid");
             stb::trace_kernel<true, false, false, DIVC, false, true, false, false, false, 256, HOIST><<<(unsigned)blocks, 256, 0, s>>>(p0);
             g_launches++;
@@ -268,10 +268,11 @@ int launch_one(const KParams &p0, const LaunchCtx &c)
     }
     const size_t smem = HIST ? (size_t)p0.nbins * sizeof(double) * (p0.hist_table ? 3 : 1) : 0;
     if (p0.nrays <= 0) return STB_OK;
+    const long long nwork = p0.perm ? p0.nslots : p0.nrays;     // slots to hand out
     // step counts / end states only, static grid: two rays per thread (endpoint_dual_kernel)
     if constexpr (!TRAJ && !EXTRAS && !HIST && !TILED && !CROSS && !STRAY) {
         if (!c.refill && g_dual) {
-            const long long blocks = (p0.nrays + 2 * stb::kBlock - 1) / (2 * stb::kBlock);
+            const long long blocks = (nwork + 2 * stb::kBlock - 1) / (2 * stb::kBlock);
             if (blocks > 0x7fffffffLL) return fail(STB_ERR_ARG, "too many rays for a static grid");
             stb::endpoint_dual_kernel<DIVC, HOIST><<<(unsigned)blocks, stb::kBlock, 0, s>>>(p0);
             g_launches++;
@@ -279,7 +280,7 @@ int launch_one(const KParams &p0, const LaunchCtx &c)
             return STB_OK;
         }
     }
-    long long blocks_all = (p0.nrays + stb::kBlock - 1) / stb::kBlock;
+    long long blocks_all = (nwork + stb::kBlock - 1) / stb::kBlock;
     if (c.refill) {
         auto kern = stb::trace_kernel<TRAJ, EXTRAS, HIST, DIVC, true, TILED, CROSS, STRAY, LOOKUP, stb::kBlock, HOIST>;
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -501,8 +502,9 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
     if (p.tile != 32 && p.tile != 64 && p.tile != 128 && p.tile != 256)
         return fail(STB_ERR_ARG, "stb_trace_batch: traj_tile must be 32, 64, 128 or 256 (got %d)", b->traj_tile);
     p.perm = nullptr; p.tile_off = nullptr; p.nslots = 0;
-    if (b->traj_perm || b->traj_tile_off) {
-        if (!(b->flags & STB_F_TRAJ_TILED) || !b->traj_perm || !b->traj_tile_off)
+    if (b->traj_tile_off) {
+        // packed tiled trajectories (stb_traj_plan)
+        if (!(b->flags & STB_F_TRAJ_TILED) || !b->traj_perm)
             return fail(STB_ERR_ARG, "stb_trace_batch: a packed plan needs STB_F_TRAJ_TILED, traj_perm and traj_tile_off");
         const long long want = (b->nrays + p.tile - 1) / p.tile * p.tile;
         if (b->traj_nslots != want)
@@ -510,6 +512,15 @@ int fill_params(stb_field_t f, const stb_batch_t *b, KParams &p, bool &divc)
         if (b->flags & STB_F_HOST_IO)
             return fail(STB_ERR_ARG, "stb_trace_batch: a packed plan lives in device memory (no STB_F_HOST_IO)");
         p.perm = b->traj_perm; p.tile_off = (const long long *)b->traj_tile_off; p.nslots = b->traj_nslots;
+    } else if (b->traj_perm) {
+        // tracing order only: slot -> ray; tiled trajectories are laid out by slot
+        const long long want = (b->flags & STB_F_TRAJ_TILED) ? (b->nrays + p.tile - 1) / p.tile * p.tile : b->nrays;
+        if (b->traj_nslots < b->nrays || ((b->flags & STB_F_TRAJ_TILED) && b->traj && b->traj_nslots != want))
+            return fail(STB_ERR_ARG, "stb_trace_batch: traj_nslots = %lld does not fit %lld rays (tiled trajectories: ceil(nrays/T)*T = %lld)",
+                        (long long)b->traj_nslots, (long long)b->nrays, want);
+        if (b->flags & (STB_F_HOST_IO | STB_F_TRAJ_HOST))
+            return fail(STB_ERR_ARG, "stb_trace_batch: a tracing order (traj_perm) needs device I/O");
+        p.perm = b->traj_perm; p.nslots = b->traj_nslots;
     }
     p.nsteps = b->nsteps; p.endst = b->end_state;
     p.turn = b->turn_index; p.turn_state = b->turn_state; p.lax_end = b->lax_end; p.ph_end = b->ph_end;

@@ -68,7 +68,10 @@ struct KParams {
     double *traj;
     long long stride;                    // doubles per ray (ray-major layout)
     int tile;                            // rays per tile (tiled layout): 32, 64, 128 or 256
-    // packed tiled layout (stb_traj_plan): slot -> ray, first row of every tile, slots = ntiles * tile
+    // perm: slot -> ray (-1 = empty).  With tile_off: the packed tiled layout of stb_traj_plan (first row of every
+    // tile, slots = ntiles * tile).  Without: just the ORDER the rays are traced in (coherent_order: launch sets in
+    // random order) -- per-ray outputs and ray-major trajectories land at the ray's own index, tiled trajectories at
+    // the slot
     const int *perm;
     const long long *tile_off;
     long long nslots;
@@ -441,14 +444,14 @@ trace_kernel(const KParams p)
         if (STRAY && p.st_ray) { st_r = p.st_ray[r]; sst_r = __dmul_rn(st_r, st_r); }
         i = 0;
         if (TRAJ) {
-            if (TILED && p.perm) {
+            if (TILED && p.tile_off) {
                 // packed: tile t owns rows tile_off[t] .. tile_off[t+1] (sized for its longest ray); never
                 // step beyond them, whatever the plan was made from
                 const long long t = slot / p.tile, row0 = p.tile_off[t];
                 tp = p.traj + (row0 * p.tile + (slot - t * p.tile)) * 4;
                 Lm1 = min(p.L - 1, (int)(p.tile_off[t + 1] - row0) - 1);
             } else {
-                tp = TILED ? p.traj + ((r / p.tile) * (long long)p.L * p.tile + (r % p.tile)) * 4
+                tp = TILED ? p.traj + ((slot / p.tile) * (long long)p.L * p.tile + (slot % p.tile)) * 4
                            : p.traj + r * p.stride;
             }
             st_state<true>(tp, x, y, kx, ky);
@@ -807,17 +810,17 @@ trace_kernel(const KParams p)
         // No vote per step: lanes that finish early wait at the reconvergence point after the
         // inner loop, which for a tile of neighbouring rays costs a few steps.
         long long r = REFILL ? 0 : (long long)blockIdx.x * BLOCK + threadIdx.x;
-        const bool packed = TILED && p.perm != nullptr;
+        const bool ordered = p.perm != nullptr;
         for (;;) {
             if (REFILL) {   // TILED: one aggregated claim of 32 consecutive rays (slots) per warp
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(p.counter, 32ull);
                 base = __shfl_sync(FULL, base, 0);
-                if ((long long)base >= (packed ? p.nslots : p.nrays)) break;
+                if ((long long)base >= (ordered ? p.nslots : p.nrays)) break;
                 r = (long long)base + lane;
             }
             const long long slot = r;
-            if (packed) r = slot < p.nslots ? (long long)p.perm[slot] : -1;
+            if (ordered) r = slot < p.nslots ? (long long)p.perm[slot] : -1;
             const bool has = r >= 0 && r < p.nrays;
             if (has && launch(r, slot)) {
                 if (LEAN) {
@@ -866,14 +869,16 @@ trace_kernel(const KParams p)
                 unsigned long long base = 0;
                 if (lane == leader) base = atomicAdd(p.counter, (unsigned long long)want);
                 base = __shfl_sync(FULL, base, leader);
+                const long long nclaim = p.perm ? p.nslots : p.nrays;
                 if (!active) {
-                    const long long r = (long long)base + __popc(idle & ((1u << lane) - 1u));
-                    if (r < p.nrays) {
-                        if (launch(r, r)) active = true;
+                    const long long slot = (long long)base + __popc(idle & ((1u << lane) - 1u));
+                    const long long r = slot >= nclaim ? -1 : p.perm ? (long long)p.perm[slot] : slot;
+                    if (r >= 0 && r < p.nrays) {
+                        if (launch(r, slot)) active = true;
                         else retire();                      // a ray that takes no step
                     }
                 }
-                more = (long long)(base + want) < p.nrays;
+                more = (long long)(base + want) < nclaim;
                 act = __ballot_sync(FULL, active);
             }
             if (act == 0) {
@@ -933,7 +938,10 @@ struct DualRay { double x, y, kx, ky; int ind, i; };
 template <bool DIVC, bool HOIST>
 __global__ void __launch_bounds__(kBlock, STB_MINB_DUAL) endpoint_dual_kernel(const KParams p)
 {
-    const long long rA = (long long)blockIdx.x * (2 * kBlock) + threadIdx.x, rB = rA + kBlock;
+    const long long sA = (long long)blockIdx.x * (2 * kBlock) + threadIdx.x, sB = sA + kBlock;
+    const long long nslot = p.perm ? p.nslots : p.nrays;
+    const long long rA = sA >= nslot ? -1 : p.perm ? (long long)p.perm[sA] : sA;      // perm: the order the rays are traced in
+    const long long rB = sB >= nslot ? -1 : p.perm ? (long long)p.perm[sB] : sB;
     const int Lm1 = p.Lm1;
 
     auto guard = [&](const DualRay &s) -> bool {       // sidtracemodule.c:36 on state s.i, exact (see trace_kernel)
@@ -942,7 +950,7 @@ __global__ void __launch_bounds__(kBlock, STB_MINB_DUAL) endpoint_dual_kernel(co
     };
     auto cell_of = [&](const DualRay &s) -> int { return __double2int_rz(s.y) * p.csy + __double2int_rz(s.x) * p.csx; };
     auto load = [&](long long r, DualRay &s) -> bool {
-        if (r >= p.nrays) return false;
+        if (r < 0 || r >= p.nrays) return false;
         s.x = p.x0[r]; s.y = p.y0[r]; s.kx = p.kx0[r]; s.ky = p.ky0[r]; s.i = 0;
         if (!guard(s)) return false;
         s.ind = cell_of(s);
@@ -981,7 +989,7 @@ __global__ void __launch_bounds__(kBlock, STB_MINB_DUAL) endpoint_dual_kernel(co
              & ((unsigned)__double2hiint(s.y) < 0x7ff00000u) & ((unsigned)iy < (unsigned)p.nym1) & (s.i < Lm1);
     };
     auto retire = [&](long long r, const DualRay &s) {
-        if (r >= p.nrays) return;
+        if (r < 0 || r >= p.nrays) return;
         if (p.nsteps) p.nsteps[r] = s.i;
         if (p.endst) {
             p.endst[0 * p.nrays + r] = s.x; p.endst[1 * p.nrays + r] = s.y;

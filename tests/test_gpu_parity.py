@@ -1341,3 +1341,62 @@ def test_unshuffle_blocks_on_one_gpu(st, torch_mod, world, rows, elem, n_global,
                 if m > 0:
                     want[:, g:g + m] = part[r, :, lb * B:lb * B + m]
         assert np.array_equal(dst.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("mode", ["endpoints", "extras", "cross", "hist", "traj", "traj-tiled"])
+@pytest.mark.parametrize("device_io,refill", [(False, None), (True, None), (True, True), (True, False)])
+def test_sort_rays_returns_the_callers_order(st, torch_mod, oracle_mod, mode, device_io, refill):
+    """trace_batch(sort_rays=True) traces a random-order launch set along a Morton curve of launch cells (coherent
+    gathers) and hands every per-ray result back in the caller's order; trajectories stay in traced order and are
+    read through slot_of.  Bit-identical to the unsorted launch and to the oracle."""
+    rng = np.random.default_rng(41)
+    nx, ny, n, L = 150, 131, 3001, 400
+    ax, ay = random_field(rng, nx, ny, scale=0.02)
+    x0, y0, kx0, ky0 = random_launch(rng, n, nx, ny)
+    x0[0] = -1.0; y0[1] = np.nan; kx0[2] = 0.0
+    f = st.Field(ax, ay, nx, ny)
+    up = (lambda a: torch_mod.from_numpy(np.ascontiguousarray(a)).cuda()) if device_io else (lambda a: a)
+    kw = dict(L=L, st=0.41, dx=0.9, dy=1.1)
+    if mode == "traj":
+        kw.update(traj=True)
+    elif mode == "traj-tiled":
+        kw.update(traj=True, tiled=True)
+    elif mode == "extras":
+        kw.update(want_extras=True)
+    elif mode == "cross":
+        kw.update(cross=(70.0, "y"), x0_phys=up(x0 * 0.9 - 3.0), y0_phys=up(y0 * 1.1 + 2.0))
+    elif mode == "hist":
+        kw.update(nbins=32, amp=up(rng.uniform(0.5, 1, n)), xorg=-60.0, yorg=-70.0, r_lcs=50.0, rho_max=1.4)
+    ins = [up(a) for a in (x0, y0, kx0, ky0)]
+    if not device_io:
+        with pytest.raises(ValueError):                 # the order is applied inside the kernel: device I/O only
+            st.trace_batch(f, *ins, sort_rays=True, **kw)
+        f.close()
+        return
+    a = st.trace_batch(f, *ins, sort_rays=True, refill=refill, **kw)
+    b = st.trace_batch(f, *ins, refill=refill, **kw)
+    torch_mod.cuda.synchronize()
+    host = lambda v: v.cpu().numpy() if device_io else np.asarray(v)
+    want = oracle_mod.trace_batch(x0, y0, kx0, ky0, L, 0.41, 0.9, 1.1, nx, ny, ax, ay)
+    assert np.array_equal(host(a.nsteps), want["nsteps"])
+    assert host(a.end_state).tobytes() == want["end"].tobytes()
+    for name in ("turn_index", "turn_state", "lax_end", "ph_end", "cross_count", "cross_index", "cross_flags", "cross_state"):
+        va, vb = getattr(a, name), getattr(b, name)
+        if va is not None:
+            assert host(va).tobytes() == host(vb).tobytes(), name
+    if mode == "hist":
+        assert np.abs(host(a.hist) - host(b.hist)).sum() <= 1e-12 * np.abs(host(b.hist)).sum()
+    if mode.startswith("traj"):
+        if mode == "traj-tiled":
+            assert sorted(host(a.order).tolist()) == list(range(n)) and a.slot_of is not None
+        else:
+            assert a.slot_of is None                     # ray-major rows sit at the ray's own index
+        for r in (0, 1, 7, n // 2, n - 1):
+            k = int(want["nsteps"][r])
+            assert host(a.ray_states(r, k + 1)).tobytes() == want["traj"][r, :k + 1].tobytes()
+        assert host(a.traj_ray_major()).tobytes() == want["traj"].tobytes()
+    # a precomputed order can be reused
+    order = st.coherent_order(*ins)
+    c = st.trace_batch(f, *ins, order=order, refill=refill, **{k: v for k, v in kw.items() if k != "traj"})
+    assert np.array_equal(host(c.nsteps), want["nsteps"])
+    f.close()

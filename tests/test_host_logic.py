@@ -150,3 +150,21 @@ def test_pick_cells_follows_the_launch_directions():
     assert sidtrace.pick_cells(-np.sin(ang), -np.cos(ang)) == "y"        # downwards counts the same
     assert sidtrace.pick_cells(np.empty(0), np.empty(0)) == "x"
     assert sidtrace.pick_cells(np.array([1.0]), np.array([1.0])) == "x"  # a tie keeps the reference layout
+
+
+def test_coherent_order_of_the_parity_path_groups_launch_cells():
+    """sidtrace.coherent_order (host logic): a permutation that puts rays of the same 4 x 4-cell block and direction
+    sector next to each other, whatever NaN / out-of-grid launches it is given."""
+    from rayrtrace_b200 import sidtrace
+    rng = np.random.default_rng(9)
+    n = 20000
+    x0, y0 = rng.uniform(0, 200, n), rng.uniform(0, 200, n)
+    ang = rng.uniform(-np.pi, np.pi, n)
+    x0[:3] = [np.nan, -5.0, 1e9]
+    p = sidtrace.coherent_order(x0, y0, np.sin(ang), np.cos(ang))
+    assert sorted(p.tolist()) == list(range(n))
+    bx, by = (np.nan_to_num(x0[p]).clip(0, 65535).astype(int) >> 2), (np.nan_to_num(y0[p]).clip(0, 65535).astype(int) >> 2)
+    same_block = (bx[1:] == bx[:-1]) & (by[1:] == by[:-1])
+    assert same_block.mean() > 0.8                       # 2500 blocks, 20000 rays: neighbours mostly share a block
+    jump = np.abs(np.diff(bx)) + np.abs(np.diff(by))
+    assert np.median(jump[~same_block]) <= 2             # and the curve moves to an adjacent block

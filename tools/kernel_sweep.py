@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--only", default="", help="comma-separated substrings; a variant runs if any matches")
     ap.add_argument("--hoist", default="on", choices=["on", "off", "both"], help="hoisted per-cell products (default) or plain cells")
     ap.add_argument("--cells", default="x", choices=["x", "y", "both"], help="cell-table layout: the reference's x-major rows, the y-major copy, or both")
+    ap.add_argument("--sorted", action="store_true", help="order the rays by launch cell (Morton) and direction first (not timed)")
+    ap.add_argument("--sort-rays", choices=["off", "timed", "reuse"], default="off",
+                    help="trace_batch(sort_rays=True): the coherent order computed inside the timed region, or once and reused")
     ap.add_argument("--L", type=int, default=0, help="states per ray (0 = the case's default cap)")
     ap.add_argument("--store-pattern", action="store_true", help="only run the store-pattern microbenchmark")
     args = ap.parse_args()
@@ -38,6 +41,20 @@ def main():
     dev = torch.device("cuda", 0)
     nf = case.nfield
     field = sidtrace.Field(np.ascontiguousarray(nf.ax), np.ascontiguousarray(nf.ay), nf.nx, nf.ny)
+    if args.sorted:
+        xg, yg, kx, ky = case.launch
+        ix, iy = np.clip(xg.astype(np.int64), 0, 65535), np.clip(yg.astype(np.int64), 0, 65535)
+
+        def spread(v):
+            v = (v | (v << 8)) & 0x00FF00FF
+            v = (v | (v << 4)) & 0x0F0F0F0F
+            v = (v | (v << 2)) & 0x33333333
+            return (v | (v << 1)) & 0x55555555
+        ang = np.floor((np.arctan2(kx, ky) + np.pi) / (2 * np.pi) * 64).astype(np.int64)
+        key = ((spread(ix >> 2) | (spread(iy >> 2) << 1)) << 6) | ang          # 4x4-cell blocks, then direction
+        order = np.argsort(key, kind="stable")
+        case.launch = tuple(np.ascontiguousarray(a[order]) for a in case.launch)
+        case.amp, case.x0, case.y0 = (np.ascontiguousarray(a[order]) for a in (case.amp, case.x0, case.y0))
     d_in = [torch.from_numpy(a).to(dev) for a in case.launch]
     d_amp = torch.from_numpy(np.ascontiguousarray(case.amp)).to(dev)
     d_xp = torch.from_numpy(np.ascontiguousarray(case.x0)).to(dev)
@@ -84,6 +101,10 @@ def main():
             continue
         o = sidtrace.BatchResult(nsteps=out.nsteps, end_state=out.end_state)
         k = dict(kw, refill=refill, div_ieee=div_ieee, hoist=hoist, cells=cells)
+        if args.sort_rays == "timed":
+            k["sort_rays"] = True
+        elif args.sort_rays == "reuse":
+            k["order"] = sidtrace.coherent_order(*d_in)
         if mode in ("traj-exact", "traj-pass2"):
             # two-pass exactly-sized arena: the whole of trace_exact, or its second pass alone (plan given)
             if refill:
