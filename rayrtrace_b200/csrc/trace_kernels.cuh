@@ -36,9 +36,15 @@ namespace stb {
 
 constexpr int kBlock = 128;   // threads per CTA (4 warps); the tiled trajectory kernel also runs with 256
 #ifndef STB_MINB_CROSS
-#define STB_MINB_CROSS 5      // crossing / lookup passes: 96 registers, 20 warps/SM (1 / 4 / 5 / 6 CTAs per SM measured:
+#define STB_MINB_CROSS 5      // crossing / lookup passes, static grid: 96 registers, 20 warps/SM (1 / 4 / 5 / 6 CTAs per SM measured:
                               // cross 4.48 / 4.51 / 4.17 / 4.47 ms, lookup 9.99 / 6.94 / 6.64 / 6.81 ms per 10^6 rays,
                               // profiles/r02/kernel_sweep_restructured.txt)
+#endif
+#ifndef STB_MINB_CROSS_REFILL
+#define STB_MINB_CROSS_REFILL 7   // the same passes on the persistent schedule (what Beam / ft2.phases launch): 72 registers with
+                                  // a few spills, 28 warps/SM.  5 / 6 / 7 / 8 CTAs per SM: cross 4.11 / 3.96 / 3.75 / 3.85 ms,
+                                  // lookup 5.83 / 5.62 / 5.37 / 7.36 ms (profiles/r02/cross_occupancy.txt); the static grid
+                                  // loses with more than 5
 #endif
 #ifndef STB_MINB_EXTRAS
 #define STB_MINB_EXTRAS 1     // fused sums / histogram
@@ -363,7 +369,8 @@ __device__ __noinline__ void cross_exact_hit(const CrossCtx c, long long ray, do
 // 20 FP64-pipe instructions.
 template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool REFILL, bool TILED = false, bool CROSS = false,
           bool STRAY = true, bool LOOKUP = false, int BLOCK = kBlock, bool HOIST = false>
-__global__ void __launch_bounds__(BLOCK, CROSS ? STB_MINB_CROSS : (HIST || EXTRAS) ? STB_MINB_EXTRAS : STB_MINB * kBlock / BLOCK)
+__global__ void __launch_bounds__(BLOCK, CROSS ? (REFILL ? STB_MINB_CROSS_REFILL : STB_MINB_CROSS)
+                                          : (HIST || EXTRAS) ? STB_MINB_EXTRAS : STB_MINB * kBlock / BLOCK)
 trace_kernel(const KParams p)
 {
     extern __shared__ double sh_hist[];
