@@ -47,8 +47,9 @@ constexpr int kBlock = 128;   // threads per CTA (4 warps); the tiled trajectory
                                   // loses with more than 5
 #endif
 #ifndef STB_MINB_EXTRAS
-#define STB_MINB_EXTRAS 1     // fused sums / histogram
-#endif
+#define STB_MINB_EXTRAS 8     // fused sums / histogram: 64 registers without spills, 32 warps/SM: 1-4 % over the 72 registers ptxas takes
+#endif                        // when left alone -- except for the fused-sum pass on the persistent schedule (-8 %), which keeps 1
+                              // (profiles/r02/extras_occupancy.txt)
 #ifndef STB_MINB
 #define STB_MINB 12           // min resident CTAs/SM asked of ptxas for the lean variants: 40 registers,
 #endif                        // 48 warps/SM (measured: +4..7 % in endpoint mode, neutral for trajectories;
@@ -370,7 +371,7 @@ __device__ __noinline__ void cross_exact_hit(const CrossCtx c, long long ray, do
 template <bool TRAJ, bool EXTRAS, bool HIST, bool DIVC, bool REFILL, bool TILED = false, bool CROSS = false,
           bool STRAY = true, bool LOOKUP = false, int BLOCK = kBlock, bool HOIST = false>
 __global__ void __launch_bounds__(BLOCK, CROSS ? (REFILL ? STB_MINB_CROSS_REFILL : STB_MINB_CROSS)
-                                          : (HIST || EXTRAS) ? STB_MINB_EXTRAS : STB_MINB * kBlock / BLOCK)
+                                          : (HIST || EXTRAS) ? ((EXTRAS && !HIST && REFILL) ? 1 : STB_MINB_EXTRAS) : STB_MINB * kBlock / BLOCK)
 trace_kernel(const KParams p)
 {
     extern __shared__ double sh_hist[];
