@@ -578,7 +578,7 @@ def run_b200(args):
         del traj
         out.traj = h_out.traj = None
         torch.cuda.empty_cache()
-        kx = dict(L=L, st=case.st, dx=case.dx, dy=case.dy)
+        kx = dict(L=L, st=case.st, dx=case.dx, dy=case.dy, refill=False, cells=cells)   # a clean, ordered beam: pass 1 on the static grid
         r = None
         for _ in range(2):
             r = sidtrace.trace_exact(field, *d_in, **kx)
@@ -592,7 +592,7 @@ def run_b200(args):
         exact = {"value": steps_per_launch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
                  "arena_bytes": int(r.plan.arena_bytes), "cap_sized_arena_bytes": int(((n + 255) // 256) * L * 256 * 32),
                  "frac_of_hbm_peak": steps_per_launch * 32 / (ms * 1e-3) / 1e9 / load_peaks()[0],
-                 "note": "sidtrace.trace_exact: pass 1 (step counts, no trajectories) + stb_traj_plan (sort by length, "
+                 "note": "sidtrace.trace_exact(refill=False): pass 1 (step counts, no trajectories; static grid, two rays per thread) + stb_traj_plan (sort by length, "
                          "exact tile sizes) + pass 2 (trajectories into the packed arena); the whole of it timed"}
         del r
         torch.cuda.empty_cache()
