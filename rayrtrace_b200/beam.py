@@ -587,7 +587,10 @@ def receiver_field_device(beam: Beam, y, axis="y"):
     nf = bun.n_field
     fld = _device_field(nf)
     dev = torch.device("cuda", torch.cuda.current_device())
-    kw = dict(L=int(bun.L), st=bun.st, dx=float(nf.dx[0]), dy=float(nf.dy[0]))
+    # the cell table whose fast axis follows the beam (same cells, same bits; STB_F_YMAJOR): the FT-2 antennas shoot
+    # along y, so their rays find the next cells in the same cache line of the y-major copy
+    cells = "y" if abs(beam.ky0) > abs(beam.kx0) else "x"
+    kw = dict(L=int(bun.L), st=bun.st, dx=float(nf.dx[0]), dy=float(nf.dy[0]), cells=cells)
 
     def up(a):
         return a if hasattr(a, "is_cuda") else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
