@@ -316,6 +316,7 @@ def trace_sharded(field, launch, *, L, st, dx, dy, amp=None, nbins=0, hist_kw=No
                                      amp=d_amp[lo:hi] if d_amp is not None else None, hist=hist, out=out, **hkw, **kw)
                 if not full:
                     end_loc[c][:, :hi - lo].copy_(e_c)
+                    e_c.record_stream(ts[c % 2])          # allocated on the main stream, used on this one
         ev = torch.cuda.Event()
         ev.record(ts[c % 2])
         if c >= nchunks - 2:
