@@ -58,6 +58,8 @@ typedef struct stb_medium_s *stb_medium_t;
  * equilibrium.py:46-49 -- and fpol = R B_phi on a uniform psi grid from simagx to sibdry).  SI units (m, Wb/rad, T m).
  * From it, at every node (x, y) of the medium's grid (R = (r0_cm + x)/100, Z = (y - z0_cm)/100):
  *     B_R = -(1/R) dpsi/dZ,  B_Z = (1/R) dpsi/dR,  B_phi = F(psi)/R  (F held at fpol[nf-1] outside the last surface)
+ *     (psi itself bilinear; grad psi = central differences at the table's nodes, interpolated bilinearly, so that the
+ *      poloidal field is continuous -- the gradient of the bilinear patch jumps at every cell edge)
  *     Y^2 = (y_per_tesla)^2 (B_R^2 + B_Z^2 + B_phi^2),   y_per_tesla = e/(m_e omega)
  * No reference code evaluates B from this table (equilibrium.py is never called by the tracer); this is the
  * north_star's "psi(R, Z), B components" for the extension's X mode. */

@@ -202,11 +202,22 @@ void rk_oracle_equilibrium_y2(const double *psi_tab, int nr, int nz, double rlef
             const double t = u - (double)iu, s = v - (double)iv;
             const double *q = psi_tab + (long long)iu * nz + iv;
             const double p00 = q[0], p01 = q[1], p10 = q[nz], p11 = q[nz + 1];
-            const double dR0 = p10 - p00, dR1 = p11 - p01;
-            const double lo = p00 + t * dR0, hi = p01 + t * dR1;
+            const double lo = p00 + t * (p10 - p00), hi = p01 + t * (p11 - p01);
             const double psi = lo + s * (hi - lo);
-            const double psiR = (dR0 + s * (dR1 - dR0)) * rdr;
-            const double psiZ = (hi - lo) * rdz;
+            /* grad psi: central differences at the four corner nodes, interpolated bilinearly (continuous field) */
+            double gR[2][2], gZ[2][2];
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b) {
+                    const int ia = iu + a, ib = iv + b;
+                    const int a0 = ia - 1 > 0 ? ia - 1 : 0, a1 = ia + 1 < nr - 1 ? ia + 1 : nr - 1;
+                    const int b0 = ib - 1 > 0 ? ib - 1 : 0, b1 = ib + 1 < nz - 1 ? ib + 1 : nz - 1;
+                    gR[a][b] = (psi_tab[(long long)a1 * nz + ib] - psi_tab[(long long)a0 * nz + ib]) * (a1 - a0 == 2 ? 0.5 * rdr : rdr);
+                    gZ[a][b] = (psi_tab[(long long)ia * nz + b1] - psi_tab[(long long)ia * nz + b0]) * (b1 - b0 == 2 ? 0.5 * rdz : rdz);
+                }
+            const double rlo = gR[0][0] + t * (gR[1][0] - gR[0][0]), rhi = gR[0][1] + t * (gR[1][1] - gR[0][1]);
+            const double psiR = rlo + s * (rhi - rlo);
+            const double zlo = gZ[0][0] + t * (gZ[1][0] - gZ[0][0]), zhi = gZ[0][1] + t * (gZ[1][1] - gZ[0][1]);
+            const double psiZ = zlo + s * (zhi - zlo);
             double w = (psi - simagx) * rdpsi;
             w = w > 0.0 ? w : 0.0;
             const double wmax = (double)(nf - 1);

@@ -619,11 +619,25 @@ __global__ void equilibrium_y2_kernel(const EqTable e, int nx, int ny, double xo
         const double t = u - (double)iu, s = v - (double)iv;
         const double *q = e.psi + (long long)iu * e.nz + iv;
         const double p00 = q[0], p01 = q[1], p10 = q[e.nz], p11 = q[e.nz + 1];    // p[R index][Z index]
-        const double dR0 = p10 - p00, dR1 = p11 - p01;        // along R at the two Z nodes
-        const double lo = p00 + t * dR0, hi = p01 + t * dR1;
-        const double psi = lo + s * (hi - lo);
-        const double psiR = (dR0 + s * (dR1 - dR0)) * e.rdr;  // dpsi/dR
-        const double psiZ = (hi - lo) * e.rdz;                // dpsi/dZ
+        const double lo = p00 + t * (p10 - p00), hi = p01 + t * (p11 - p01);
+        const double psi = lo + s * (hi - lo);                                    // bilinear, as equilibrium.py:46-49
+        // grad psi: central differences at the four corner nodes (one-sided on the border), interpolated bilinearly --
+        // a CONTINUOUS poloidal field.  (The gradient of the bilinear patch itself jumps at every cell edge of the psi
+        // grid; sampled onto the medium's finer grid those jumps cost the step controller 7x the steps.)
+        double gR[2][2], gZ[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int ia = iu + a, ib = iv + b;
+                const int a0 = max(ia - 1, 0), a1 = min(ia + 1, e.nr - 1), b0 = max(ib - 1, 0), b1 = min(ib + 1, e.nz - 1);
+                gR[a][b] = (e.psi[(long long)a1 * e.nz + ib] - e.psi[(long long)a0 * e.nz + ib]) * (a1 - a0 == 2 ? 0.5 * e.rdr : e.rdr);
+                gZ[a][b] = (e.psi[(long long)ia * e.nz + b1] - e.psi[(long long)ia * e.nz + b0]) * (b1 - b0 == 2 ? 0.5 * e.rdz : e.rdz);
+            }
+        const double rlo = gR[0][0] + t * (gR[1][0] - gR[0][0]), rhi = gR[0][1] + t * (gR[1][1] - gR[0][1]);
+        const double psiR = rlo + s * (rhi - rlo);            // dpsi/dR
+        const double zlo = gZ[0][0] + t * (gZ[1][0] - gZ[0][0]), zhi = gZ[0][1] + t * (gZ[1][1] - gZ[0][1]);
+        const double psiZ = zlo + s * (zhi - zlo);            // dpsi/dZ
         // F(psi): linear on the uniform psi grid, held at the ends
         double w = (psi - e.simagx) * e.rdpsi;
         w = w > 0.0 ? w : 0.0;

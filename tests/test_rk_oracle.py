@@ -467,8 +467,9 @@ def _solovev_tables(nr=257, nz=257, half=0.12, R0=0.55, a=0.08, kappa=1.2, B0=2.
 
 
 def test_equilibrium_table_is_the_solovev_field():
-    """|B|^2 from the bilinear psi(R, Z) table (the reference's Equilibrium fields, equilibrium.py:11-49): the
-    toroidal part is exact, the poloidal part converges at first order in the psi grid spacing."""
+    """|B|^2 from the psi(R, Z) table (the reference's Equilibrium fields, equilibrium.py:11-49): the toroidal part is
+    exact, the poloidal part (central differences at the nodes, interpolated bilinearly: a continuous field)
+    converges at second order in the psi grid spacing."""
     xs = np.linspace(-10, 10, 101)
     errs = []
     for n in (65, 129, 257):
@@ -479,8 +480,8 @@ def test_equilibrium_table_is_the_solovev_field():
         exact = eq["y_per_tesla"] ** 2 * (BR ** 2 + BZ ** 2 + Bp ** 2)
         pol = eq["y_per_tesla"] ** 2 * (BR ** 2 + BZ ** 2)
         errs.append(np.max(np.abs(y2 - exact)) / pol.max())
-    assert errs[2] < 0.02 and errs[0] / errs[2] > 3.0        # first order: 4x finer grid, ~4x smaller error
-    assert np.max(np.abs(y2 - exact) / exact) < 1e-3
+    assert errs[2] < 5e-5 and errs[0] / errs[2] > 12.0       # second order: 4x finer grid, ~16x smaller error
+    assert np.max(np.abs(y2 - exact) / exact) < 5e-6
 
 
 def test_tabulated_field_force_is_the_gradient_of_n2():
