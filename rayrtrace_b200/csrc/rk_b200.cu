@@ -45,6 +45,7 @@ struct stb_medium_s {
     int mode = 0, interp = 2;
     double *X = nullptr, *alpha = nullptr, *Y2 = nullptr;
     double2 *XA = nullptr;                   // {X, alpha} interleaved (only with an absorption table)
+    double2 *XY = nullptr;                   // {X, Y^2} interleaved (tabulated-field X mode)
     unsigned long long *counter = nullptr;   // kCounters queue heads used round-robin; a slot is handed out again
                                              // only after the launch that used it last has finished (counter_ev)
     cudaEvent_t counter_ev[64] = {};
@@ -195,17 +196,25 @@ int stb_medium_create(const stb_medium_desc_t *d, stb_medium_t *out)
             if ((e = cudaGetLastError()) == cudaSuccess) e = cudaDeviceSynchronize();
         }
     }
+    if (e == cudaSuccess && m->Y2) {     // also with absorption: the end-of-ray Hamiltonian is evaluated without the alpha table
+        const long long nt = (long long)(tbytes / sizeof(double));
+        if ((e = cudaMalloc(&m->XY, (size_t)nt * sizeof(double2))) == cudaSuccess) {
+            stbrk::interleave2_kernel<<<148 * 8, 256>>>(m->X, m->Y2, m->XY, nt);
+            stb_internal_count_launch();
+            if ((e = cudaGetLastError()) == cudaSuccess) e = cudaDeviceSynchronize();
+        }
+    }
     cudaFree(nodes); cudaFree(half); cudaFree(piv); cudaFree(y2nodes); cudaFree(eq_psi); cudaFree(eq_f);
     if (e != cudaSuccess) {
         const int rc = fail(e == cudaErrorMemoryAllocation ? STB_ERR_NOMEM : STB_ERR_CUDA, "stb_medium_create: %s",
                             cudaGetErrorString(e));
-        cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->XA); cudaFree(m->Y2); cudaFree(m->counter);
+        cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->XA); cudaFree(m->XY); cudaFree(m->Y2); cudaFree(m->counter);
         delete m;
         return rc;
     }
     m->mode = d->mode;
     m->interp = d->interp;
-    m->m.X = m->X; m->m.alpha = m->alpha; m->m.XA = m->XA; m->m.Y2 = m->Y2;
+    m->m.X = m->X; m->m.alpha = m->alpha; m->m.XA = m->XA; m->m.Y2 = m->Y2; m->m.XY = m->XY;
     m->m.nx = d->nx; m->m.ny = d->ny;
     m->m.xorg = d->xorg; m->m.yorg = d->yorg;
     m->m.rdx = 1.0 / d->dx; m->m.rdy = 1.0 / d->dy;
@@ -230,7 +239,7 @@ int stb_medium_table(stb_medium_t m, int which, double *host_out, size_t count)
 int stb_medium_destroy(stb_medium_t m)
 {
     if (!m) return STB_OK;
-    cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->XA); cudaFree(m->Y2); cudaFree(m->counter);
+    cudaFree(m->X); cudaFree(m->alpha); cudaFree(m->XA); cudaFree(m->XY); cudaFree(m->Y2); cudaFree(m->counter);
     for (auto &e : m->counter_ev) if (e) cudaEventDestroy(e);
     delete m;
     return STB_OK;

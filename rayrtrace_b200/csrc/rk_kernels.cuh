@@ -31,6 +31,7 @@ struct Medium {
     const double *alpha;   // power absorption coefficient per unit tau (same layout), or nullptr
     const double2 *XA;     // {X, alpha} interleaved per node (media with absorption), or nullptr
     const double *Y2;      // MODE 2: (omega_ce/omega)^2 node table (same layout as X), or nullptr
+    const double2 *XY;     // MODE 2 without absorption: {X, Y^2} interleaved per node (one 16-byte load serves both), or nullptr
     int nx, ny;
     double xorg, yorg;     // physical position of node (0, 0)
     double rdx, rdy;       // 1/dx, 1/dy
@@ -208,6 +209,60 @@ __device__ __forceinline__ void table_eval2(const double2 *__restrict__ T, int n
     }
 }
 
+// Value and gradient of BOTH components of an interleaved table ({X, Y^2}, MODE 2): each component sees exactly the
+// arithmetic of table_eval, so results do not depend on the layout.
+template <int INTERP>
+__device__ __forceinline__ void table_eval2g(const double2 *__restrict__ T, int nx, int ny, int iu, int iv, double t, double s,
+                                             double &f, double &fu, double &fv, double &g, double &gu, double &gv)
+{
+    if (INTERP == 0) {
+        const double2 *r0 = T + (long long)iv * nx + iu;
+        const double2 a = __ldg(r0), b = __ldg(r0 + 1), c = __ldg(r0 + nx), d = __ldg(r0 + nx + 1);
+        {
+            const double ba = b.x - a.x, dc = d.x - c.x;
+            const double lo = fma(t, ba, a.x), hi = fma(t, dc, c.x);
+            f = fma(s, hi - lo, lo); fu = fma(s, dc - ba, ba); fv = hi - lo;
+        }
+        {
+            const double ba = b.y - a.y, dc = d.y - c.y;
+            const double lo = fma(t, ba, a.y), hi = fma(t, dc, c.y);
+            g = fma(s, hi - lo, lo); gu = fma(s, dc - ba, ba); gv = hi - lo;
+        }
+    } else {
+        double wx[4], dx[4], wy[4], dy[4];
+        if (INTERP == 1) {
+            cr_weights(t, wx, dx);
+            cr_weights(s, wy, dy);
+        } else {
+            bs_weights(t, wx, dx);
+            bs_weights(s, wy, dy);
+        }
+        double rv[4], rd[4], qv[4], qd[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double2 v0, v1, v2, v3;
+            if (INTERP == 1) {
+                const double2 *row = T + (long long)clampi(iv - 1 + j, 0, ny - 1) * nx;
+                v0 = __ldg(row + clampi(iu - 1, 0, nx - 1)); v1 = __ldg(row + iu); v2 = __ldg(row + iu + 1);
+                v3 = __ldg(row + clampi(iu + 2, 0, nx - 1));
+            } else {
+                const double2 *row = T + (long long)(iv + j) * (nx + 2) + iu;
+                v0 = __ldg(row); v1 = __ldg(row + 1); v2 = __ldg(row + 2); v3 = __ldg(row + 3);
+            }
+            rv[j] = fma(wx[3], v3.x, fma(wx[2], v2.x, fma(wx[1], v1.x, wx[0] * v0.x)));
+            rd[j] = fma(dx[3], v3.x, fma(dx[2], v2.x, fma(dx[1], v1.x, dx[0] * v0.x)));
+            qv[j] = fma(wx[3], v3.y, fma(wx[2], v2.y, fma(wx[1], v1.y, wx[0] * v0.y)));
+            qd[j] = fma(dx[3], v3.y, fma(dx[2], v2.y, fma(dx[1], v1.y, dx[0] * v0.y)));
+        }
+        f = fma(wy[3], rv[3], fma(wy[2], rv[2], fma(wy[1], rv[1], wy[0] * rv[0])));
+        fu = fma(wy[3], rd[3], fma(wy[2], rd[2], fma(wy[1], rd[1], wy[0] * rd[0])));
+        fv = fma(dy[3], rv[3], fma(dy[2], rv[2], fma(dy[1], rv[1], dy[0] * rv[0])));
+        g = fma(wy[3], qv[3], fma(wy[2], qv[2], fma(wy[1], qv[1], wy[0] * qv[0])));
+        gu = fma(wy[3], qd[3], fma(wy[2], qd[2], fma(wy[1], qd[1], wy[0] * qd[0])));
+        gv = fma(dy[3], qv[3], fma(dy[2], qv[2], fma(dy[1], qv[1], dy[0] * qv[0])));
+    }
+}
+
 // Right-hand side at (x, y): force = grad(N^2)/2, absorption coefficient, N^2.
 #ifndef STB_RK_EVAL_INLINE
 #define STB_RK_EVAL_INLINE __forceinline__
@@ -227,8 +282,9 @@ __device__ STB_RK_EVAL_INLINE void rk_eval(const Medium &m, double xs, double ys
     const int iu = max(0, min(__double2int_rd(u), m.nx - 2));
     const int iv = max(0, min(__double2int_rd(v), m.ny - 2));
     const double t = u - (double)iu, s = v - (double)iv;
-    double F, Fu, Fv;
+    double F, Fu, Fv, G = 0, Gu = 0, Gv = 0;
     if (ABSORB) table_eval2<INTERP>(m.XA, m.nx, m.ny, iu, iv, t, s, F, Fu, Fv, al);
+    else if (MODE == 2) table_eval2g<INTERP>(m.XY, m.nx, m.ny, iu, iv, t, s, F, Fu, Fv, G, Gu, Gv);
     else table_eval<INTERP, true>(m.X, m.nx, m.ny, iu, iv, t, s, F, Fu, Fv);
     const double Xv = xs * F;
     const double Xx = xs * (Fu * m.rdx), Xy = xs * (Fv * m.rdy);   // physical gradient of X
@@ -237,8 +293,7 @@ __device__ STB_RK_EVAL_INLINE void rk_eval(const Medium &m, double xs, double ys
         fx = -0.5 * Xx;
         fy = -0.5 * Xy;
     } else if (MODE == 2) {
-        double G, Gu, Gv;
-        table_eval<INTERP, true>(m.Y2, m.nx, m.ny, iu, iv, t, s, G, Gu, Gv);
+        if (ABSORB) table_eval<INTERP, true>(m.Y2, m.nx, m.ny, iu, iv, t, s, G, Gu, Gv);   // {X, alpha} came interleaved
         const double ys2 = ys * ys;
         const double Y2 = ys2 * G;
         const double Y2x = ys2 * (Gu * m.rdx), Y2y = ys2 * (Gv * m.rdy);   // physical gradient of Y^2
