@@ -326,7 +326,8 @@ def trace_rays(n_field, x0, y0, kx0, ky0, freq, amp=None, *, max_steps: Optional
     L = int(max_steps) if max_steps else int(Ray.MaxStep)
     st = float(n_field.st * Ray.kStep)
     f = _device_field(n_field)
-    kw = dict(L=L, st=st, dx=float(n_field.dx[0]), dy=float(n_field.dy[0]), want_extras=want_extras, cross=receiver)
+    kw = dict(L=L, st=st, dx=float(n_field.dx[0]), dy=float(n_field.dy[0]), want_extras=want_extras, cross=receiver,
+              cells=_st.pick_cells(kx, ky))      # the cell table whose fast axis follows the fan (same cells, same bits)
     d_x0 = d_y0 = None
     if receiver or not host_results:
         d_x0, d_y0 = torch.from_numpy(x0.copy()).to(dev), torch.from_numpy(y0.copy()).to(dev)
