@@ -837,10 +837,10 @@ trace_kernel(const KParams p)
                         if (why == 1 || (why == 0 && !step())) break;
                     }
                 } else {
-                    // the fused-sum and histogram passes gain 4 % / 1.5 % from a loop unrolled by two (ptxas then
+                    // the fused-sum and histogram passes gain 4 % / 1-5 % from a loop unrolled by two (ptxas then
                     // rotates the state registers instead of copying them); trajectories, crossing and lookup lose
                     // 3-4 % (profiles/r02/crossopt_unr2.txt)
-                    if (EXTRAS && !CROSS && !TRAJ) {
+                    if ((EXTRAS || HIST) && !CROSS && !TRAJ) {
 #pragma unroll 2
                         while (step()) { }
                     } else {
